@@ -1,0 +1,99 @@
+// Shared types for the sm_100a reverse-diffusion engine.
+//
+// Layout convention (DESIGN.md "Data layout in HBM"): every activation is a
+// channels-last row matrix [rows, C] with C contiguous.  Stroke-level tensors at
+// pyramid level l (T_l = T >> l) use the PADDED ROW layout
+//     row(b, t) = b * (T_l + 1) + 1 + t,      row(b, -1) = b * (T_l + 1) is all-zero,
+// plus one trailing zero row, so a k=3 'same' conv1d (reference cnn.py:32-47) is
+// three row-shifted GEMMs over the flat matrix with the zero halo already in
+// memory.  Text rows ([B*L, C]) and style rows ([B*70, C]) carry no padding.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dhg {
+
+typedef __nv_bfloat16 bf16;
+
+enum Precision { PREC_FP32 = 0, PREC_BF16 = 1 };
+
+// How a flat row index maps to (sample, position): rows are grouped in periods
+// of `period` rows per sample; if `pad_first`, the first row of each period is
+// the zero halo row.  Rows >= nvalid (= B * period) are trailing padding.
+struct RowMap {
+  int period;
+  int pad_first;
+  int nvalid;
+};
+
+// Epilogue applied to one GEMM output row (see rowpost_kernel / the tcgen05
+// epilogue).  Order: acc + bias|rowbias -> + res_pre -> LayerNorm -> FiLM ->
+// + res_post -> zero if halo row -> store raw and/or SiLU'd copy.
+struct Epilogue {
+  const float* bias;       // [N] or null
+  const float* rowbias;    // [period - pad_first, N] indexed by position (bias folded in) or null
+  const void* res_pre;     // activation dtype, same row index, or null
+  int res_pre_pitch;
+  int ln;                  // LayerNorm over the N outputs, eps 1e-6, no affine
+  const float* gamma;      // FiLM: gamma[b * film_bstride + n]; null = no FiLM
+  const float* beta;
+  int film_bstride;        // 0 = one vector shared by the whole batch (sampling)
+  const void* res_post;    // activation dtype or null
+  int res_post_pitch;
+  int res_post_up;         // 1: res_post lives one pyramid level down: row b*(period_lo)+1+pos/2
+  int res_post_period_lo;
+  void* out_raw;           // activation dtype or null
+  int out_raw_pitch;
+  void* out_act;           // SiLU(value), activation dtype or null
+  int out_act_pitch;
+  RowMap map;
+};
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// 4 consecutive activation elements <-> float4
+template <typename T> __device__ __forceinline__ float4 load4(const T* p);
+template <> __device__ __forceinline__ float4 load4<float>(const float* p) {
+  return *reinterpret_cast<const float4*>(p);
+}
+template <> __device__ __forceinline__ float4 load4<bf16>(const bf16* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+template <typename T> __device__ __forceinline__ void store4(T* p, float4 v);
+template <> __device__ __forceinline__ void store4<float>(float* p, float4 v) {
+  *reinterpret_cast<float4*>(p) = v;
+}
+template <> __device__ __forceinline__ void store4<bf16>(bf16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace dhg

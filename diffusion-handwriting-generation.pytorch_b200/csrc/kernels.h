@@ -1,0 +1,66 @@
+// Kernel launch interface shared by the engine and the kernel translation units.
+#pragma once
+#include "common.cuh"
+
+namespace dhg {
+
+struct AttnParams {
+  const void* q; const void* k; const void* v; void* o;   // activation dtype
+  int q_pitch, k_pitch, v_pitch, o_pitch;                  // elements per row
+  int q_period, q_pad;                                     // row(b, t) = b*q_period + q_pad + t
+  int k_period, k_pad;
+  int B, H, D, Tq, Tk;
+  float scale;                                             // 1/sqrt(D)
+  const int64_t* text;                                     // [B, Tk] token ids (0 = masked key) or null
+};
+
+struct HeadParams {
+  int B, T;
+  float* eps_out;          // [B,T,2] or null
+  float* pen_out;          // pen_out[i*pen_stride + pen_offset] or null
+  int pen_stride, pen_offset;
+  float* x_io;             // [B,T,2] current x (null: no posterior update)
+  float* x_out;            // where the updated x goes (null: in place); row stride x_out_stride
+  int x_out_stride;
+  const float* noise;      // [B,T,2] injected draw or null (= zero)
+  int mode;                // 0 "new", 1 "standard"
+  float c_eps, c_eps2, c_div, c_noise;
+};
+
+template <typename TA>
+void launch_gemm_simt(const TA* A, int lda, int rows, const float* W, int K, int N, int taps,
+                      float* out, cudaStream_t st);
+template <typename T>
+void launch_rowpost(const float* acc, int rows, int N, const Epilogue& e, cudaStream_t st);
+template <typename T>
+int launch_attention_simt(const AttnParams& p, cudaStream_t st);
+template <typename T>
+void launch_film_rows(const T* in, T* out, int rows, int C, int period, const float* gamma,
+                      const float* beta, int bstride, cudaStream_t st);
+template <typename T>
+void launch_pool(const T* in, T* out_raw, T* out_act, int B, int Tlo, int C, cudaStream_t st);
+template <typename T>
+void launch_input_dense(const float* x, const float* W, const float* bias, T* out_raw, T* out_act,
+                        int B, int Tn, int C, cudaStream_t st);
+template <typename T>
+void launch_heads_update(const T* h, int C, const float* Wo, const float* bo, const float* Wp,
+                         const float* bp, const HeadParams& p, cudaStream_t st);
+void launch_posterior(const float* x, const float* eps, const float* z, float* out, size_t n, int mode,
+                      float c_eps, float c_eps2, float c_div, float c_noise, int num_sms, cudaStream_t st);
+void launch_sigma_ffn(const float* sigma, const float* w1, const float* b1, const float* w2, const float* b2,
+                      int H, float* out, int n, cudaStream_t st);
+void launch_film_table(const float* sig, const float* Wc, const float* bc, int tot, float* out, int n, cudaStream_t st);
+template <typename T>
+void launch_embed_ln(const int64_t* ids, const float* emb, int vocab, int C, T* out, int rows, int* err, cudaStream_t st);
+template <typename T>
+void launch_silu_convert(const float* in, T* out, size_t n, cudaStream_t st);
+
+// tcgen05 / TMA GEMM (gemm_tc.cu).  A: bf16 [rows, K] pitch lda; W: bf16 [taps][N][K]
+// (K contiguous).  Epilogue fused.  Returns 0 on success.
+struct TcGemmPlan;  // opaque: tensor maps + launch geometry, built once at plan time
+TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W, int K, int N, int taps,
+                                const Epilogue& e, char* err, int errlen);
+void tc_gemm_plan_destroy(TcGemmPlan*);
+int tc_gemm_launch(const TcGemmPlan*, const Epilogue& e, cudaStream_t st);
+
+}  // namespace dhg

@@ -1,0 +1,67 @@
+"""ctypes binding of include/dhg_b200.h.  There is no fallback: if the library
+is missing or cannot be loaded, importing the compute entry points raises."""
+import ctypes
+import os
+
+from .build import LIB_PATH
+
+_lib = None
+
+c_i32, c_i64, c_u64 = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64
+c_vp, c_cp = ctypes.c_void_p, ctypes.c_char_p
+
+
+class DhgConfig(ctypes.Structure):
+    _fields_ = [("num_layers", c_i32), ("channels", c_i32)]
+
+
+# name -> (restype, argtypes); every symbol include/dhg_b200.h declares
+SIGNATURES = {
+    "dhg_last_error": (c_cp, []),
+    "dhg_abi_version": (c_i32, []),
+    "dhg_create": (c_i32, [c_i32, ctypes.POINTER(DhgConfig), ctypes.POINTER(c_vp)]),
+    "dhg_destroy": (c_i32, [c_vp]),
+    "dhg_num_weights": (c_i32, [c_vp]),
+    "dhg_weight_name": (c_cp, [c_vp, c_i32]),
+    "dhg_weight_ndim": (c_i32, [c_vp, c_i32]),
+    "dhg_weight_dim": (c_i64, [c_vp, c_i32, c_i32]),
+    "dhg_load_weight": (c_i32, [c_vp, c_cp, c_vp, ctypes.POINTER(c_i64), c_i32]),
+    "dhg_set_schedule": (c_i32, [c_vp, c_vp, c_vp]),
+    "dhg_finalize": (c_i32, [c_vp]),
+    "dhg_plan": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32]),
+    "dhg_denoise": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "dhg_sample": (c_i32, [c_vp, c_i32, c_vp, c_vp, c_u64, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    "dhg_sample_host": (c_i32, [c_vp, c_i32, c_vp, c_vp, c_u64, c_vp, c_vp, c_i32, c_vp]),
+    "dhg_posterior_step": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "dhg_last_launch_count": (c_i64, [c_vp]),
+    "dhg_plan_bytes": (c_i64, [c_vp]),
+    "dhg_set_option": (c_i32, [c_vp, c_cp, c_i32]),
+    "dhg_debug_read": (c_i64, [c_vp, c_cp, c_vp, c_i64]),
+    "dhg_debug_tc_gemm": (c_i32, [c_i32, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+}
+
+
+class DhgError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the C-ABI library.  Raises if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DhgError(
+                f"{LIB_PATH} is not built. Run `python __graft_entry__.py build` "
+                "(needs nvcc). There is no CPU or PyTorch fallback for this path."
+            )
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the symbol is missing
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise DhgError(lib().dhg_last_error().decode("utf-8", "replace"))

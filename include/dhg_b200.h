@@ -1,0 +1,143 @@
+/* dhg_b200 -- C ABI of the B200-native reverse-diffusion sampling engine.
+ *
+ * Drop-in boundary for the sampling hot path of
+ * sleep3r/Diffusion-Handwriting-Generation.pytorch.  The reference has no FFI
+ * layer; its boundary is the Python call surface.  Each entry
+ * point below names the reference interface it stands behind.  The binding a
+ * maintainer adds on the reference side is the ctypes stub in INTEGRATION.md.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on failure; the message for
+ *    the calling thread is dhg_last_error().  No exceptions cross the boundary.
+ *  - "dev" pointers are CUDA device pointers on the ctx's device, "host"
+ *    pointers are ordinary host memory.  All are BORROWED for the duration of
+ *    the call (for stream-ordered calls: until the work enqueued on `stream`
+ *    has completed); the library never frees or keeps them.
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *  - one ctx per device; a ctx is not re-entrant: one host thread at a time.
+ *  - there is no CPU fallback: every entry point that computes needs a CUDA
+ *    device of compute capability 10.x and fails loudly otherwise.
+ */
+#ifndef DHG_B200_H
+#define DHG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dhg_ctx dhg_ctx;
+
+/* training_args.{att_layers_num, channels} of config.yml, read by the reference at
+ * diffusion_handwriting_generation/checkpoint.py:280-286. */
+typedef struct dhg_config {
+  int32_t num_layers; /* att_layers_num */
+  int32_t channels;   /* channels (c1); c2 = 3*c1/2, c3 = 2*c1.  Must be 128: the
+                         reference hard-codes the 32-wide sigma embedding
+                         (conditioning.py:9) */
+} dhg_config;
+
+#define DHG_PREC_FP32 0 /* fp32 storage, fp32 CUDA-core accumulate (parity mode) */
+#define DHG_PREC_BF16 1 /* bf16 storage, tcgen05 bf16 MMA, fp32 accumulate/statistics */
+
+#define DHG_MODE_NEW 0      /* utils/nn.py:90-112 new_diffusion_step (inference.py default) */
+#define DHG_MODE_STANDARD 1 /* utils/nn.py:64-87 standard_diffusion_step */
+
+#define DHG_NUM_STEPS 60 /* utils/nn.py:21 */
+
+/* Message of the last failure on the calling thread ("" if none). */
+const char* dhg_last_error(void);
+/* ABI version of this library (bumped on any signature change). */
+int32_t dhg_abi_version(void);
+
+/* Replaces: DiffusionModel(num_layers, c1, c2, c3, drop) construction in
+ * checkpoint.py:280-286 (load_model).  Needs a CUDA device. */
+int32_t dhg_create(int32_t device, const dhg_config* cfg, dhg_ctx** out);
+int32_t dhg_destroy(dhg_ctx* ctx);
+
+/* The state_dict layout this ctx expects (model_final.pth, written by
+ * train.py:131; 323 fp32 tensors for best_exp).  Enumerate to validate or drive a loader. */
+int32_t dhg_num_weights(const dhg_ctx* ctx);
+const char* dhg_weight_name(const dhg_ctx* ctx, int32_t index);
+int32_t dhg_weight_ndim(const dhg_ctx* ctx, int32_t index);
+int64_t dhg_weight_dim(const dhg_ctx* ctx, int32_t index, int32_t d);
+
+/* Replaces: load_checkpoint()/load_state_dict(strict=True), checkpoint.py:92-130.
+ * host_data: fp32, C-contiguous, `ndim` dims in `shape`.  Unknown name or shape
+ * mismatch fails (strict). */
+int32_t dhg_load_weight(dhg_ctx* ctx, const char* name, const float* host_data,
+                        const int64_t* shape, int32_t ndim);
+/* Optional: override the beta / alpha-bar schedule (60 fp32 each) with the values
+ * the host computed (utils/nn.py:19-39, inference.py:81).  Default: computed here. */
+int32_t dhg_set_schedule(dhg_ctx* ctx, const float* host_beta, const float* host_alpha_bar);
+/* Strict check that every weight arrived; repacks weights for the kernels and
+ * precomputes the per-step FiLM vectors for the 60 sampling noise levels.
+ * Replaces model.to(device); model.eval() (checkpoint.py:295-296). */
+int32_t dhg_finalize(dhg_ctx* ctx);
+
+/* Allocates workspace and builds the launch sequence for a problem shape:
+ * batch (chunk) B, T stroke points (multiple of 8, inference.py:78), L text
+ * tokens, S style tokens of width 1280 (14 from StyleExtractor; text_style.py:59).
+ * A later call replaces the previous plan. */
+int32_t dhg_plan(dhg_ctx* ctx, int32_t B, int32_t T, int32_t L, int32_t S, int32_t precision);
+
+/* Replaces: DiffusionModel.forward(strokes, text, sigma, style_vector) ->
+ * (eps, pen_lifts, None), model.py:121-182.  All dev pointers, shapes of the
+ * current plan: strokes [B,T,2] f32, text [B,L] i64, sigma [B] f32,
+ * style [B,S,1280] f32 -> eps [B,T,2] f32, pen [B,T] f32.  Stream-ordered. */
+int32_t dhg_denoise(dhg_ctx* ctx, const float* dev_strokes, const int64_t* dev_text,
+                    const float* dev_sigma, const float* dev_style, float* dev_eps,
+                    float* dev_pen, void* stream);
+
+/* Replaces: the 60-step loop of infer(), inference.py:81-96, for `batch`
+ * samples (any batch >= 1: processed in chunks of the planned B).
+ * x0 [batch,T,2] f32; noise [60,batch,T,2] f32, noise[i] consumed at loop index i
+ * (the draw of randn_like in utils/nn.py:86,111), or NULL with `seed` for the
+ * library's own counter-based generator; text [batch,L] i64; style
+ * [batch,S,1280] f32 -> out [batch,T,3] f32 = cat(x, pen_lifts of the last step).
+ * Stream-ordered; the chain runs as one CUDA graph per chunk. */
+int32_t dhg_sample(dhg_ctx* ctx, int32_t batch, const float* dev_x0, const float* dev_noise,
+                   uint64_t seed, const int64_t* dev_text, const float* dev_style, int32_t mode,
+                   float* dev_out, void* stream);
+/* Same, with HOST buffers: the host->device copies of every input, the chain,
+ * and the device->host copy of the result all happen inside the call, which
+ * returns when `host_out` is complete. */
+int32_t dhg_sample_host(dhg_ctx* ctx, int32_t batch, const float* host_x0, const float* host_noise,
+                        uint64_t seed, const int64_t* host_text, const float* host_style,
+                        int32_t mode, float* host_out);
+
+/* Replaces: new_diffusion_step / standard_diffusion_step (utils/nn.py:64-112)
+ * with the noise draw injected: one fused streaming kernel over n = B*T*2 floats.
+ * step = loop index i in [0,60).  dev_noise may be NULL (treated as zeros).
+ * dev_out may alias dev_x. */
+int32_t dhg_posterior_step(dhg_ctx* ctx, int32_t step, int32_t mode, const float* dev_x,
+                           const float* dev_eps, const float* dev_noise, float* dev_out,
+                           int64_t n, void* stream);
+
+/* Number of kernels this library enqueued in the most recent dhg_denoise /
+ * dhg_sample / dhg_sample_host call (graph nodes count individually). */
+int64_t dhg_last_launch_count(const dhg_ctx* ctx);
+/* Bytes of device memory held by the current plan. */
+int64_t dhg_plan_bytes(const dhg_ctx* ctx);
+/* Engine switches, mainly for tests: key "gemm" = 0 CUDA-core GEMM + row epilogue
+ * kernel, 1 tcgen05 GEMM with fused epilogue (bf16 precision only; default 1);
+ * "graph" = 0/1 use CUDA graphs in dhg_sample (default 1).  Takes effect at the next dhg_plan. */
+int32_t dhg_set_option(dhg_ctx* ctx, const char* key, int32_t value);
+
+/* Test hook: copy a named intermediate activation of the last forward ("h1", "h2c",
+ * "h2", "h3c", "h3", "att_in", "att0".., "d3", "d2", "d1", "text_act", ...) to host as
+ * fp32 [B, positions, C] without halo rows.  host_out NULL: returns the element count.
+ * Returns the element count, or -1 on failure.  Synchronises the device. */
+int64_t dhg_debug_read(dhg_ctx* ctx, const char* name, float* host_out, int64_t capacity);
+
+/* Test hook: run one tcgen05 GEMM (bf16 in, fused epilogue) against caller-provided
+ * device buffers.  Not part of the reference-facing surface. */
+int32_t dhg_debug_tc_gemm(int32_t device, const void* dev_a_bf16, int32_t lda, int32_t rows,
+                          const void* dev_w_bf16, int32_t K, int32_t N, int32_t taps,
+                          const float* dev_bias, void* dev_out_bf16, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DHG_B200_H */
