@@ -1,0 +1,258 @@
+"""Parity of the CUDA path (through the C ABI) with the reference: golden vectors produced by the
+reference itself, the CPU oracle on seeded inputs, and size-independent properties at the
+BASELINE batch size.  Needs a B200: run with `-m gpu`.
+
+Tolerances (BASELINE.json north_star / SURVEY.md 8d):
+  fp32 mode : strokes rel-L2 <= 1e-3 after the full 60-step chain, pen-lift (p > 0.5) agreement >= 99.9 %
+  bf16 mode : strokes rel-L2 <= 1.5e-2, pen-lift agreement >= 97 % over positions with
+              |p_ref - 0.5| > 0.02 (random-init pen probabilities sit near 0.5; the CPU bf16-autocast
+              reference itself lands at 6e-3 / 98.7 %)
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dhg_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FP32_REL, FP32_PEN = 1e-3, 0.999
+BF16_REL, BF16_PEN, BF16_PEN_MARGIN = 1.5e-2, 0.97, 0.02
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm()).item()
+
+
+def _pen_agree(out, ref, margin=0.0):
+    sure = (ref - 0.5).abs() > margin
+    return ((out > 0.5) == (ref > 0.5))[sure].float().mean().item()
+
+
+@pytest.fixture(scope="module")
+def writers(state_dict):
+    from dhg_b200 import DiffusionWriter
+
+    ws = {
+        "fp32": DiffusionWriter(state_dict=state_dict, num_layers=2, channels=128, dtype="fp32"),
+        "bf16": DiffusionWriter(state_dict=state_dict, num_layers=2, channels=128, dtype="bf16"),
+    }
+    yield ws
+    for w in ws.values():
+        w.close()
+
+
+def _t(g, *keys):
+    return tuple(torch.tensor(g[k]) for k in keys)
+
+
+# ----------------------------------------------------------------------------- single forward
+@pytest.mark.parametrize("case", ["fwd_small", "fwd_reftest"])
+def test_denoise_fp32_matches_reference_golden(writers, golden, case):
+    g = golden(case)
+    strokes, text, sigma, style = _t(g, "strokes", "text", "sigma", "style")
+    eps, pen, third = writers["fp32"].denoise(strokes, text, sigma, style)
+    assert third is None and eps.shape == strokes.shape and pen.shape == strokes.shape[:2]
+    assert _rel(eps.cpu(), torch.tensor(g["eps"])) < 1e-4
+    assert (pen.cpu() - torch.tensor(g["pen"])).abs().max() < 1e-4
+
+
+def test_denoise_bf16_matches_reference_golden(writers, golden):
+    g = golden("fwd_small")
+    strokes, text, sigma, style = _t(g, "strokes", "text", "sigma", "style")
+    eps, pen, _ = writers["bf16"].denoise(strokes, text, sigma, style)
+    assert _rel(eps.cpu(), torch.tensor(g["eps"])) < BF16_REL
+    assert (pen.cpu() - torch.tensor(g["pen"])).abs().max() < 1e-2
+
+
+def test_denoise_accepts_reference_sigma_shapes(writers, golden):
+    g = golden("fwd_small")
+    strokes, text, sigma, style = _t(g, "strokes", "text", "sigma", "style")
+    w = writers["fp32"]
+    a = w.denoise(strokes, text, sigma, style)[0]                      # [B,1]   (train.py)
+    b = w.denoise(strokes, text, sigma.reshape(-1, 1, 1), style)[0]    # [B,1,1] (inference.py)
+    c = w.denoise(strokes, text.int(), sigma.reshape(-1), style)[0]    # IntTensor text
+    assert torch.equal(a, b) and torch.equal(a, c)
+
+
+def test_intermediate_activations_match_oracle(writers, state_dict, golden):
+    g = golden("fwd_small")
+    strokes, text, sigma, style = _t(g, "strokes", "text", "sigma", "style")
+    taps = {}
+    O.denoiser_forward(state_dict, strokes, text, sigma, style, taps=taps)
+    for mode, tol in (("fp32", 1e-5), ("bf16", 1.5e-2)):
+        w = writers[mode]
+        w.denoise(strokes, text, sigma, style)
+        for name in ("h1", "h2c", "h2", "h3c", "h3", "att_in", "att0", "att1", "d3", "d2", "d1"):
+            got = w.debug_read(name).reshape(taps[name].shape)
+            assert _rel(got, taps[name]) < tol, (mode, name)
+
+
+# ----------------------------------------------------------------------------- full chains
+def test_chain_c1_fp32_matches_reference_golden(writers, golden):
+    g = golden("chain_c1")     # BASELINE configs[0]: batch 1, 'Follow the White Rabbit', T=392
+    text, style, x0, noise = _t(g, "text", "style", "x0", "noise")
+    out = writers["fp32"].sample(text, style, x0=x0, noise=noise).cpu()
+    ref = torch.tensor(g["out_new"])
+    assert out.shape == (1, 392, 3)
+    assert _rel(out[..., :2], ref[..., :2]) < FP32_REL
+    assert _pen_agree(out[..., 2], ref[..., 2]) >= FP32_PEN
+
+
+@pytest.mark.parametrize("mode", ["new", "standard"])
+def test_chain_small_fp32_both_modes(writers, golden, mode):
+    g = golden("chain_small")  # ragged text (zero padding), both update rules
+    text, style, x0, noise = _t(g, "text", "style", "x0", "noise")
+    out = writers["fp32"].sample(text, style, x0=x0, noise=noise, diffusion_mode=mode).cpu()
+    ref = torch.tensor(g["out_" + mode])
+    assert _rel(out[..., :2], ref[..., :2]) < FP32_REL
+    assert _pen_agree(out[..., 2], ref[..., 2]) >= FP32_PEN
+
+
+@pytest.mark.parametrize("case,key", [("chain_c1", "out_new"), ("chain_small", "out_new"), ("chain_small", "out_standard")])
+def test_chain_bf16_within_stated_tolerance(writers, golden, case, key):
+    g = golden(case)
+    text, style, x0, noise = _t(g, "text", "style", "x0", "noise")
+    mode = key.split("_", 1)[1]
+    out = writers["bf16"].sample(text, style, x0=x0, noise=noise, diffusion_mode=mode).cpu()
+    ref = torch.tensor(g[key])
+    assert _rel(out[..., :2], ref[..., :2]) < BF16_REL
+    assert _pen_agree(out[..., 2], ref[..., 2], BF16_PEN_MARGIN) >= BF16_PEN
+
+
+def test_host_buffer_entry_point_matches_device_entry_point(writers, golden):
+    g = golden("chain_small")
+    text, style, x0, noise = _t(g, "text", "style", "x0", "noise")
+    w = writers["fp32"]
+    a = w.sample(text, style, x0=x0, noise=noise).cpu()
+    b = w.sample_host(text, style, x0, noise)
+    assert torch.equal(a, b)
+    assert w.last_launch_count > 60 * 50
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_chunking_and_graph_do_not_change_results(state_dict, golden, dtype):
+    from dhg_b200 import DiffusionWriter
+
+    g = golden("chain_small")
+    text, style, x0, noise = _t(g, "text", "style", "x0", "noise")
+    outs = []
+    for chunk, graph in ((8, 1), (2, 1), (1, 0)):   # 3 samples: one chunk / ragged 2+1 / one by one, no graph
+        w = DiffusionWriter(state_dict=state_dict, num_layers=2, channels=128, dtype=dtype, chunk=chunk, graph=graph)
+        outs.append(w.sample(text, style, x0=x0, noise=noise).cpu())
+        w.close()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+# ----------------------------------------------------------------------------- BASELINE size (configs[1])
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_batch64_properties_and_oracle_spot_check(writers, state_dict, dtype):
+    """B=64, T=392, L=24: (1) replicated prompts give identical rows, (2) permuting the batch permutes
+    the output, (3) two of the 64 chains are compared with the CPU oracle."""
+    w = writers[dtype]
+    gen = torch.Generator().manual_seed(1234)
+    B, T, L = 64, 392, 24
+    text = torch.randint(2, 73, (B, L), generator=gen)
+    text[:, -1] = 1
+    text[5, 15:] = 0
+    text[5, 14] = 1
+    style = torch.randn(B, 14, 1280, generator=gen)
+    x0 = torch.randn(B, T, 2, generator=gen)
+    noise = torch.randn(60, B, T, 2, generator=gen)
+    for t in (text, style, x0):
+        t[7] = t[3]                 # sample 7 is a replica of sample 3
+    noise[:, 7] = noise[:, 3]
+    out = w.sample(text, style, x0=x0, noise=noise).cpu()
+    assert torch.isfinite(out).all()
+    assert torch.equal(out[7], out[3])
+    perm = torch.randperm(B, generator=gen)
+    out_p = w.sample(text[perm], style[perm], x0=x0[perm], noise=noise[:, perm]).cpu()
+    assert torch.equal(out_p, out[perm])
+    idx = [3, 5]
+    ref = O.reverse_chain(state_dict, text[idx], style[idx], x0[idx], noise[:, idx])
+    rel_tol, pen_tol, margin = (FP32_REL, FP32_PEN, 0.0) if dtype == "fp32" else (BF16_REL, BF16_PEN, BF16_PEN_MARGIN)
+    assert _rel(out[idx][..., :2], ref[..., :2]) < rel_tol
+    assert _pen_agree(out[idx][..., 2], ref[..., 2], margin) >= pen_tol
+
+
+# ----------------------------------------------------------------------------- posterior update kernel
+@pytest.mark.parametrize("mode", ["new", "standard"])
+def test_posterior_step_matches_reference_formula(writers, mode):
+    w = writers["fp32"]
+    gen = torch.Generator().manual_seed(5)
+    x, eps, z = (torch.randn(4, 392, 2, generator=gen) for _ in range(3))
+    beta = O.beta_schedule()
+    abar = O.alpha_bar(beta)
+    for i in (59, 31, 1, 0):
+        a = abar[i] * torch.ones(4, 1, 1)
+        b = beta[i] * torch.ones(4, 1, 1)
+        if mode == "new":
+            ref = O.posterior_new(x, eps, b, a, abar[i - 1] if i > 1 else torch.tensor(1.0), z)
+        else:
+            ref = O.posterior_standard(x, eps, b, a, z, add_sigma=bool(i))
+        got = w.posterior_step(i, x, eps, z, diffusion_mode=mode).cpu()
+        assert (got - ref).abs().max() < 1e-5 * max(1.0, ref.abs().max().item())
+    # empty input is a no-op
+    assert w.posterior_step(3, torch.zeros(0, 8, 2), torch.zeros(0, 8, 2)).numel() == 0
+
+
+# ----------------------------------------------------------------------------- errors and the reference-facing surface
+def test_error_behaviour(writers, state_dict, golden):
+    from dhg_b200 import DiffusionWriter
+    from dhg_b200._abi import DhgError
+
+    w = writers["fp32"]
+    g = golden("fwd_small")
+    strokes, text, sigma, style = _t(g, "strokes", "text", "sigma", "style")
+    with pytest.raises(DhgError, match="multiple of 8"):
+        w.denoise(strokes[:, :60], text, sigma, style)
+    bad = text.clone()
+    bad[0, 0] = 73
+    with pytest.raises(IndexError):
+        w.denoise(strokes, bad, sigma, style)
+    with pytest.raises(ValueError):
+        w.sample(text, style, x0=strokes, noise=torch.zeros(59, 3, 64, 2))
+    sd = dict(state_dict)
+    sd.pop("enc3.mha.wq.bias")
+    with pytest.raises(RuntimeError, match="missing keys"):
+        DiffusionWriter(state_dict=sd, num_layers=2, channels=128)
+    sd = dict(state_dict)
+    sd["extra.weight"] = torch.zeros(1)
+    with pytest.raises(RuntimeError, match="unexpected key"):
+        DiffusionWriter(state_dict=sd, num_layers=2, channels=128)
+    sd = dict(state_dict)
+    sd["enc1.fc.weight"] = torch.zeros(128, 64)
+    with pytest.raises(RuntimeError, match="size mismatch"):
+        DiffusionWriter(state_dict=sd, num_layers=2, channels=128)
+
+
+def test_load_model_and_infer_drop_in(tmp_path, state_dict, golden):
+    """config.yml + model_final.pth in an experiment directory, like `make infer`."""
+    import shutil
+
+    from dhg_b200 import infer, load_model
+
+    exp = tmp_path / "exp"
+    exp.mkdir()
+    shutil.copy(os.path.join(os.path.dirname(__file__), "golden", "config.yml"), exp / "config.yml")
+    torch.save({"state_dict": {"module." + k: v for k, v in state_dict.items()}}, exp / "checkpoint_500.pth")
+    torch.save(state_dict, exp / "model_final.pth")
+    model, device = load_model(str(exp / "config.yml"), str(exp / "checkpoint_500.pth"))
+    assert device == "cuda"
+    g = golden("fwd_small")
+    strokes, text, sigma, style = _t(g, "strokes", "text", "sigma", "style")
+    eps, pen, _ = model.eval()(strokes, text, sigma, style)
+    assert _rel(eps.cpu(), torch.tensor(g["eps"])) < 1e-4
+    torch.save(torch.tensor(golden("chain_c1")["style"][0]), tmp_path / "style.pt")
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        strokes = infer("Follow the White Rabbit", str(tmp_path / "style.pt"), experiment_path=str(exp), output="pred", seed=1)
+    finally:
+        os.chdir(cwd)
+    assert strokes.shape == (392, 3) and torch.isfinite(strokes).all()
+    assert (tmp_path / "pred.png").exists()
+    with pytest.raises(ValueError):
+        infer("x", str(tmp_path / "style.pt"), experiment_path=str(tmp_path / "nope"))
