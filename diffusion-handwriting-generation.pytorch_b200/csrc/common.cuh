@@ -39,6 +39,7 @@ struct Epilogue {
   const float* gamma;      // FiLM: gamma[b * film_bstride + n]; null = no FiLM
   const float* beta;
   int film_bstride;        // 0 = one vector shared by the whole batch (sampling)
+  int film_planned;        // plan-time flag: gamma/beta will be supplied at launch
   const void* res_post;    // activation dtype or null
   int res_post_pitch;
   int res_post_up;         // 1: res_post lives one pyramid level down: row b*(period_lo)+1+pos/2

@@ -395,6 +395,7 @@ struct Builder {
     e.rowbias = s.rowbias;
     e.res_pre = s.res_pre.p; e.res_pre_pitch = s.res_pre.C;
     e.ln = s.ln ? 1 : 0;
+    e.film_planned = s.film_off >= 0 ? 1 : 0;
     e.res_post = s.res_post.p; e.res_post_pitch = s.res_post.C;
     e.res_post_up = s.res_post_up ? 1 : 0; e.res_post_period_lo = s.res_post_period_lo;
     e.out_raw = s.out_raw.p; e.out_raw_pitch = s.out_raw.C;
@@ -1119,6 +1120,41 @@ int32_t dhg_debug_tc_gemm(int32_t device, const void* a, int32_t lda, int32_t ro
   tc_gemm_plan_destroy(p);
   if (rc) return 1;
   if (ce != cudaSuccess) return fail("dhg_debug_tc_gemm: %s", cudaGetErrorString(ce));
+  return 0;
+}
+
+int32_t dhg_debug_tc_gemm_ex(int32_t device, const void* a, int32_t lda, int32_t rows, const void* w, int32_t K, int32_t N,
+                             int32_t taps, const dhg_debug_epilogue* d, int32_t repeats, float* ms_per_launch, void* stream) {
+  if (!d) return fail("dhg_debug_tc_gemm_ex: null epilogue");
+  CUDA_OK(cudaSetDevice(device));
+  Epilogue e;
+  memset(&e, 0, sizeof(e));
+  e.bias = d->bias; e.rowbias = d->rowbias;
+  e.res_pre = d->res_pre; e.res_pre_pitch = d->res_pre_pitch;
+  e.ln = d->ln;
+  e.gamma = d->gamma; e.beta = d->beta; e.film_bstride = d->film_bstride; e.film_planned = d->gamma ? 1 : 0;
+  e.res_post = d->res_post; e.res_post_pitch = d->res_post_pitch; e.res_post_up = d->res_post_up;
+  e.res_post_period_lo = d->res_post_period_lo;
+  e.out_raw = d->out_raw; e.out_raw_pitch = d->out_raw_pitch;
+  e.out_act = d->out_act; e.out_act_pitch = d->out_act_pitch;
+  e.map = RowMap{d->period > 0 ? d->period : (rows > 0 ? rows : 1), d->pad_first, d->nvalid > 0 ? d->nvalid : rows};
+  char buf[512];
+  TcGemmPlan* p = tc_gemm_plan_create((const bf16*)a, lda, rows, (const bf16*)w, K, N, taps, e, buf, sizeof(buf));
+  if (!p) return fail("dhg_debug_tc_gemm_ex: %s", buf);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  tc_gemm_launch(p, e, st);
+  cudaEventRecord(e0, st);
+  for (int i = 0; i < repeats; ++i) tc_gemm_launch(p, e, st);
+  cudaEventRecord(e1, st);
+  cudaError_t ce = cudaStreamSynchronize(st);
+  float ms = 0.f;
+  if (ce == cudaSuccess && repeats > 0) cudaEventElapsedTime(&ms, e0, e1);
+  if (ms_per_launch) *ms_per_launch = repeats > 0 ? ms / repeats : 0.f;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  tc_gemm_plan_destroy(p);
+  if (ce != cudaSuccess) return fail("dhg_debug_tc_gemm_ex: %s", cudaGetErrorString(ce));
   return 0;
 }
 

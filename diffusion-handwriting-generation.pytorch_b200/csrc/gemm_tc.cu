@@ -1,21 +1,27 @@
-// tcgen05 / TMEM / TMA GEMM with the fused row epilogue, sm_100a.
+// tcgen05 / TMEM / TMA GEMM with the fused row epilogue, sm_100a.  Persistent, warp-specialised.
 //
 //   out[m, n] = epilogue( sum_{tap<taps} sum_{k<K} A[m + tap - taps/2, k] * W[tap][n][k] )
 //
-// One CTA computes one 128 x BN output tile (BN <= 256, or 384 = two N=192 MMAs when a
-// LayerNorm needs the whole 384-wide row).  Warp roles (192 threads):
-//   warps 0-3  epilogue: thread = one accumulator row (TMEM lane); tcgen05.ld 32 columns at a time
-//   warp  4    TMA producer: A tile [128 rows x 64 k] and W tile [BN x 64 k] per k-block, SWIZZLE_128B,
-//              row-shifted A coordinates implement the conv taps, TMA zero-fill implements every edge
-//   warp  5    TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, bf16 x bf16 -> fp32 in TMEM)
-// Pipelines: smem full/empty mbarriers between TMA and MMA, one tmem_full barrier to the epilogue.
-// Several CTAs are resident per SM (smem <= ~100 KB, TMEM <= 256 columns each for BN <= 256), so one
-// CTA's epilogue overlaps another CTA's MMA main loop.
+// One CTA per SM loops over 128 x BN output tiles (BN <= 256, or 384 = two N=192 MMAs when a
+// LayerNorm needs the whole 384-wide row).  Warp roles (320 threads):
+//   warp  0    TMA producer: A tile [128 rows x 64 k] and W tile [BN x 64 k] per k-block, SWIZZLE_128B;
+//              row-shifted A coordinates implement the conv taps, TMA zero-fill implements every edge.
+//              Runs ahead across tiles through a ring of smem stages.
+//   warp  1    TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, bf16 x bf16 -> fp32 in
+//              TMEM).  Two accumulator stages (2 x 256 columns) when BN <= 256, so the MMAs of tile
+//              i+1 overlap the epilogue of tile i.
+//   warps 2-9  epilogue: warp (q, half) owns TMEM lanes [32q, 32q+32) and one half of the tile's
+//              32-column chunks; thread = one accumulator row.  Residual / per-position-bias rows are
+//              prefetched with cp.async into a per-warp swizzled ring (coalesced global reads), the
+//              bf16 outputs go through a per-warp swizzled staging tile and leave as coalesced 16-byte
+//              stores.  Bias / FiLM vectors live in shared memory for the whole kernel.
+// Pipelines: smem full/empty mbarriers (TMA <-> MMA), tmem full/empty mbarriers (MMA <-> epilogue).
 //
 // The epilogue is the one documented in common.cuh (bias|rowbias, residual, LayerNorm, FiLM, residual,
 // halo-row zeroing, raw and/or SiLU'd bf16 stores).  LayerNorm: pass 1 adds bias/residual, writes the
-// row back to TMEM and accumulates shifted sums; pass 2 normalises.  Reference ops fused here:
-// Linear/Conv1d (cnn.py:32-49, attention.py:58-61), LayerNorm (model.py:25), AffineTransformLayer
+// row back to TMEM and accumulates shifted sums per column half, the halves are merged with Chan's
+// formula through shared memory; pass 2 normalises.  Reference ops fused here: Linear/Conv1d
+// (cnn.py:32-49, attention.py:58-61), LayerNorm (model.py:25), AffineTransformLayer
 // (conditioning.py:16-19), SiLU (cnn.py:25), residual adds and nearest upsample (model.py:169-176).
 #include <cuda.h>
 #include <stdio.h>
@@ -28,18 +34,30 @@ namespace {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;   // bf16 elements per k-block = 128 bytes = one SWIZZLE_128B row
-constexpr int TC_THREADS = 192;
-constexpr uint32_t kSpinLimit = 1u << 27;
+constexpr int TC_THREADS = 320;
+constexpr int EPI_WARPS = 8;
+constexpr int AUX_RING_BYTES = 8192;   // per epilogue warp: 4 x 2 KB (bf16 rows) or 2 x 4 KB (fp32 rows)
+constexpr int OUT_STAGE_BYTES = 2048;  // per epilogue warp: 32 rows x 32 bf16
+constexpr int TMEM_COLS = 512;
+constexpr uint32_t kSpinLimit = 1u << 28;
+
+enum { AUX_NONE = 0, AUX_RES_PRE = 1, AUX_RES_POST = 2, AUX_RES_POST_UP = 3, AUX_ROWBIAS = 4 };
 
 struct TcShape {
   int rows, K, N, taps;
-  int BN;         // tile width
+  int BN;          // tile width
+  int n_groups;    // N / BN
+  int num_tiles;   // m_tiles * n_groups
   int stages;
-  int kb_per_tap; // ceil(K / 64)
-  int umma_n;     // N of one tcgen05.mma (BN, or 192 when BN == 384)
-  int n_umma;     // MMAs per k-step along N (1 or 2)
+  int kb_per_tap;  // ceil(K / 64)
+  int umma_n;      // N of one tcgen05.mma (BN, or 192 when BN == 384)
+  int n_umma;      // MMAs per k-step along N (1 or 2)
   uint32_t idesc;
-  int tmem_cols;
+  int acc_stages;  // 1 or 2 TMEM accumulator stages
+  int aux_kind;
+  int vec_bias_n;  // floats of bias staged in smem (0 or N)
+  int film_n;      // floats of gamma / beta staged in smem (0 or N)
+  uint32_t stage_bytes, off_aux, off_out, off_vec, off_ln, off_bar;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -49,6 +67,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -66,7 +87,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > kSpinLimit) {
-      printf("tc_gemm: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      printf("tc_gemm: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
       __trap();
     }
   }
@@ -131,215 +152,370 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-// 32 consecutive bf16 (64 B) <-> fp32 registers
-__device__ __forceinline__ void add_bf16x32(const bf16* p, float* v) {
-  const uint4* q = reinterpret_cast<const uint4*>(p);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint4 u = q[i];
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
-      v[i * 8 + j * 2] += f.x;
-      v[i * 8 + j * 2 + 1] += f.y;
-    }
-  }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-template <bool kSilu>
-__device__ __forceinline__ void store_bf16x32(bf16* p, const float* v) {
-  uint4* q = reinterpret_cast<uint4*>(p);
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// SiLU through one MUFU op: x * sigmoid(x) = h + h * tanh(h), h = x / 2  (tanh.approx: ~2^-11 relative,
+// below the bf16 rounding of the stored result).
+__device__ __forceinline__ float silu_fast(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ void add_bf16x8(const uint4& u, float* v) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint32_t w[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float a = v[i * 8 + j * 2], b = v[i * 8 + j * 2 + 1];
-      if (kSilu) { a = silu_f(a); b = silu_f(b); }
-      const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-      w[j] = *reinterpret_cast<const uint32_t*>(&h);
-    }
-    q[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+    v[j * 2] += f.x;
+    v[j * 2 + 1] += f.y;
   }
 }
 
-__global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
-                                                             const __grid_constant__ CUtensorMap map_w,
-                                                             const TcShape sh, const Epilogue e) {
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                const __grid_constant__ CUtensorMap map_w,
+                                                                const TcShape sh, const Epilogue e) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: 1024-aligned tiles, then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t a_bytes = TC_BM * TC_BK * 2;           // 16 KB
-  const uint32_t b_bytes = (uint32_t)sh.BN * TC_BK * 2;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)sh.stages * stage_bytes);
-  uint64_t* full_bar = bars;                 // [stages]
-  uint64_t* empty_bar = bars + sh.stages;    // [stages]
-  uint64_t* tmem_full_bar = bars + 2 * sh.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * sh.stages + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sh.off_bar);
+  uint64_t* full_bar = bars;                       // [stages]
+  uint64_t* empty_bar = bars + sh.stages;          // [stages]
+  uint64_t* tmem_full_bar = bars + 2 * sh.stages;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* bias_s = reinterpret_cast<float*>(smem + sh.off_vec);
+  float* gamma_s = bias_s + sh.vec_bias_n;
+  float* betap_s = gamma_s + sh.film_n;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * TC_BM;
-  const int n0 = blockIdx.y * sh.BN;
   const int num_kb = sh.taps * sh.kb_per_tap;
+  const uint32_t a_bytes = TC_BM * TC_BK * 2;  // 16 KB
+  const bool film = e.gamma != nullptr;
+  const bool film_s = film && e.film_bstride == 0 && sh.film_n > 0;   // FiLM vectors shared by the batch -> smem
+  const bool fold_bias = film_s && !e.ln && sh.vec_bias_n > 0;        // (acc + b) * g + beta = acc * g + (b * g + beta)
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
     for (int s = 0; s < sh.stages; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
-    mbar_init(smem_u32(tmem_full_bar), 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tmem_full_bar[a]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[a]), EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 5) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)sh.tmem_cols) : "memory");
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int n = threadIdx.x; n < sh.vec_bias_n; n += TC_THREADS) bias_s[n] = __ldg(e.bias + n);
+  if (film_s) {
+    for (int n = threadIdx.x; n < sh.film_n; n += TC_THREADS) {
+      const float g = __ldg(e.gamma + n), b = __ldg(e.beta + n);
+      gamma_s[n] = g;
+      betap_s[n] = fold_bias ? fmaf(__ldg(e.bias + n), g, b) : b;
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       const int half_taps = sh.taps / 2;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % sh.stages;
-        const uint32_t phase = (uint32_t)(kb / sh.stages) & 1u;
-        mbar_wait(smem_u32(&empty_bar[s]), phase ^ 1u);
-        const int tap = kb / sh.kb_per_tap, kk = (kb - tap * sh.kb_per_tap) * TC_BK;
-        const uint32_t a_dst = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t b_dst = a_dst + a_bytes;
-        const uint32_t fb = smem_u32(&full_bar[s]);
-        mbar_expect_tx(fb, stage_bytes);
-        tma_load_2d(a_dst, &map_a, fb, kk, m0 + tap - half_taps);
-        for (int j = 0; j < sh.n_umma; ++j)
-          tma_load_2d(b_dst + (uint32_t)j * sh.umma_n * TC_BK * 2, &map_w, fb, kk, tap * sh.N + n0 + j * sh.umma_n);
+      uint32_t g = 0;
+      for (int t = blockIdx.x; t < sh.num_tiles; t += gridDim.x) {
+        const int mt = t / sh.n_groups, ng = t - mt * sh.n_groups;
+        const int m0 = mt * TC_BM, n0 = ng * sh.BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          const uint32_t s = g % (uint32_t)sh.stages;
+          const uint32_t phase = (g / (uint32_t)sh.stages) & 1u;
+          mbar_wait(smem_u32(&empty_bar[s]), phase ^ 1u);
+          const int tap = kb / sh.kb_per_tap, kk = (kb - tap * sh.kb_per_tap) * TC_BK;
+          const uint32_t a_dst = smem_u32(smem + (size_t)s * sh.stage_bytes);
+          const uint32_t b_dst = a_dst + a_bytes;
+          const uint32_t fb = smem_u32(&full_bar[s]);
+          mbar_expect_tx(fb, sh.stage_bytes);
+          tma_load_2d(a_dst, &map_a, fb, kk, m0 + tap - half_taps);
+          for (int j = 0; j < sh.n_umma; ++j)
+            tma_load_2d(b_dst + (uint32_t)j * sh.umma_n * TC_BK * 2, &map_w, fb, kk, tap * sh.N + n0 + j * sh.umma_n);
+        }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % sh.stages;
-        const uint32_t phase = (uint32_t)(kb / sh.stages) & 1u;
-        mbar_wait(smem_u32(&full_bar[s]), phase);
+      uint32_t g = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < sh.num_tiles; t += gridDim.x, ++it) {
+        const int as = sh.acc_stages == 2 ? (it & 1) : 0;
+        const uint32_t use = sh.acc_stages == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;
+        mbar_wait(smem_u32(&tmem_empty_bar[as]), (use & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t b_addr = a_addr + a_bytes;
+        const uint32_t acc = tmem_base + (uint32_t)as * 256u;
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          const uint32_t s = g % (uint32_t)sh.stages;
+          const uint32_t phase = (g / (uint32_t)sh.stages) & 1u;
+          mbar_wait(smem_u32(&full_bar[s]), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)s * sh.stage_bytes);
+          const uint32_t b_addr = a_addr + a_bytes;
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          const uint64_t adesc = umma_desc_sw128(a_addr + k * 32);
-          for (int j = 0; j < sh.n_umma; ++j) {
-            const uint64_t bdesc = umma_desc_sw128(b_addr + (uint32_t)j * sh.umma_n * TC_BK * 2 + k * 32);
-            umma_bf16(tmem_base + (uint32_t)j * sh.umma_n, adesc, bdesc, sh.idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t adesc = umma_desc_sw128(a_addr + k * 32);
+            for (int j = 0; j < sh.n_umma; ++j) {
+              const uint64_t bdesc = umma_desc_sw128(b_addr + (uint32_t)j * sh.umma_n * TC_BK * 2 + k * 32);
+              umma_bf16(acc + (uint32_t)j * sh.umma_n, adesc, bdesc, sh.idesc, (kb | k) ? 1u : 0u);
+            }
           }
+          umma_commit(smem_u32(&empty_bar[s]));        // frees the smem stage when these MMAs retire
         }
-        umma_commit(smem_u32(&empty_bar[s]));        // frees the smem stage when these MMAs retire
+        umma_commit(smem_u32(&tmem_full_bar[as]));     // accumulator complete
       }
-      umma_commit(smem_u32(tmem_full_bar));          // accumulator complete
     }
   } else {
-    // ===== epilogue: warps 0..3, thread = row =====
-    mbar_wait(smem_u32(tmem_full_bar), 0);
-    tc_fence_after();
-    const int m = m0 + warp * 32 + lane;
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const bool in_range = m < sh.rows;
-    const int mm = in_range ? m : 0;
-    const int b = mm / e.map.period;
-    const int j = mm - b * e.map.period;
-    const bool is_pad = (mm >= e.map.nvalid) || (e.map.pad_first && j == 0);
-    const int pos = is_pad ? 0 : j - e.map.pad_first;
-    const int N = sh.N;
-    const float* biasp = e.rowbias ? e.rowbias + (size_t)pos * N : e.bias;
-    const bf16* rpre = e.res_pre ? reinterpret_cast<const bf16*>(e.res_pre) + (size_t)mm * e.res_pre_pitch : nullptr;
-    const float* gam = e.gamma ? e.gamma + (size_t)b * e.film_bstride : nullptr;
-    const float* bet = e.gamma ? e.beta + (size_t)b * e.film_bstride : nullptr;
-    const bf16* rpost = nullptr;
-    if (e.res_post) {
-      const size_t rr = e.res_post_up ? (size_t)b * e.res_post_period_lo + 1 + (pos >> 1) : (size_t)mm;
-      rpost = reinterpret_cast<const bf16*>(e.res_post) + rr * e.res_post_pitch;
-    }
-    bf16* oraw = e.out_raw ? reinterpret_cast<bf16*>(e.out_raw) + (size_t)mm * e.out_raw_pitch : nullptr;
-    bf16* oact = e.out_act ? reinterpret_cast<bf16*>(e.out_act) + (size_t)mm * e.out_act_pitch : nullptr;
-    const bool live = in_range && !is_pad;
-    float v[32];
-    float mean = 0.f, rstd = 1.f;
-    if (e.ln) {
-      // pass 1: x = acc + bias + res_pre -> back to TMEM; shifted sums for mean / variance
-      float shift = 0.f, s1 = 0.f, s2 = 0.f;
-      for (int c0 = 0; c0 < sh.BN; c0 += 32) {
-        tmem_ld32(trow + c0, v);
-        const int n = n0 + c0;
-        if (biasp) {
+    // ===== epilogue: warps 2..9; warp (q, half): TMEM lanes [32q, 32q+32), one half of the column chunks =====
+    const int ew = warp - 2, q = warp & 3, half = ew >> 2;
+    const int nch = sh.BN >> 5;
+    const int c_lo = half ? ((nch + 1) >> 1) : 0;
+    const int c_hi = half ? nch : ((nch + 1) >> 1);
+    const int my_nch = c_hi - c_lo;
+    const int other_nch = nch - my_nch;
+    uint8_t* aux_ring = smem + sh.off_aux + (size_t)ew * AUX_RING_BYTES;
+    uint8_t* out_st = smem + sh.off_out + (size_t)ew * OUT_STAGE_BYTES;
+    float4* ln_s = reinterpret_cast<float4*>(smem + sh.off_ln);   // [2 parity][128 rows] {mean0, M2_0, mean1, M2_1}
+    const int aux_kind = sh.aux_kind;
+    const bool aux_f32 = aux_kind == AUX_ROWBIAS;
+    const int aux_depth = aux_f32 ? 2 : 4;
+    const uint32_t aux_slot_bytes = aux_f32 ? 4096u : 2048u;
+    const char* aux_base = nullptr;
+    size_t aux_pitch_bytes = 0;
+    if (aux_kind == AUX_RES_PRE) { aux_base = (const char*)e.res_pre; aux_pitch_bytes = (size_t)e.res_pre_pitch * 2; }
+    else if (aux_kind == AUX_RES_POST || aux_kind == AUX_RES_POST_UP) { aux_base = (const char*)e.res_post; aux_pitch_bytes = (size_t)e.res_post_pitch * 2; }
+    else if (aux_kind == AUX_ROWBIAS) { aux_base = (const char*)e.rowbias; aux_pitch_bytes = (size_t)sh.N * 4; }
+    const bool aux_in_pass1 = e.ln && aux_kind == AUX_RES_PRE;
+    const bool aux_in_final = aux_kind != AUX_NONE && !aux_in_pass1;
+    const int r_tile = q * 32 + lane;   // my accumulator row inside the tile
+    const uint32_t lane_sel = ((uint32_t)(q * 32)) << 16;
+
+    int it = 0;
+    for (int t = blockIdx.x; t < sh.num_tiles; t += gridDim.x, ++it) {
+      const int mt = t / sh.n_groups, ng = t - mt * sh.n_groups;
+      const int m0 = mt * TC_BM, n0 = ng * sh.BN;
+      const int as = sh.acc_stages == 2 ? (it & 1) : 0;
+      const uint32_t use = sh.acc_stages == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;
+      const uint32_t trow = tmem_base + (uint32_t)as * 256u + lane_sel;
+
+      // ---- per-row bookkeeping ----
+      const int m = m0 + r_tile;
+      const bool in_range = m < sh.rows;
+      const int mm = in_range ? m : 0;
+      const int b = mm / e.map.period;
+      const int j = mm - b * e.map.period;
+      const bool is_pad = (mm >= e.map.nvalid) || (e.map.pad_first && j == 0);
+      const int pos = is_pad ? 0 : j - e.map.pad_first;
+      const bool live = in_range && !is_pad;
+      int aux_src = -1;   // source row of my residual / bias row, -1 = none (zero-filled)
+      if (aux_kind == AUX_RES_PRE || aux_kind == AUX_RES_POST) aux_src = in_range ? m : -1;
+      else if (aux_kind == AUX_RES_POST_UP) aux_src = live ? b * e.res_post_period_lo + 1 + (pos >> 1) : -1;
+      else if (aux_kind == AUX_ROWBIAS) aux_src = live ? pos : -1;
+
+      // cp.async one chunk of aux rows (32 rows x 32 columns) into ring slot ci % depth
+      auto issue_aux = [&](int ci) {
+        if (ci < my_nch) {
+          const int col0 = n0 + (c_lo + ci) * 32;
+          const uint32_t slot = smem_u32(aux_ring + (size_t)(ci % aux_depth) * aux_slot_bytes);
+          if (aux_f32) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(biasp + n + i));
-            v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
+            for (int i = 0; i < 8; ++i) {
+              const int rr = i * 4 + (lane >> 3), piece = lane & 7;
+              const int src = __shfl_sync(0xffffffffu, aux_src, rr);
+              const char* gp = aux_base + (size_t)(src < 0 ? 0 : src) * aux_pitch_bytes + (size_t)col0 * 4 + piece * 16;
+              cp_async16(slot + rr * 128 + ((piece ^ (rr & 7)) << 4), gp, src < 0 ? 0u : 16u);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = i * 8 + (lane >> 2), piece = lane & 3;
+              const int src = __shfl_sync(0xffffffffu, aux_src, rr);
+              const char* gp = aux_base + (size_t)(src < 0 ? 0 : src) * aux_pitch_bytes + (size_t)col0 * 2 + piece * 16;
+              cp_async16(slot + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4), gp, src < 0 ? 0u : 16u);
+            }
           }
         }
-        if (rpre && live) add_bf16x32(rpre + n, v);
-        if (c0 == 0) shift = v[0];
+        cp_async_commit();
+      };
+      // wait for chunk ci's aux rows, add mine to v, refill the slot with chunk ci + depth
+      auto consume_aux = [&](int ci, float* v) {
+        if (aux_f32) cp_async_wait<1>(); else cp_async_wait<3>();
+        __syncwarp();
+        const uint8_t* slot = aux_ring + (size_t)(ci % aux_depth) * aux_slot_bytes;
+        if (aux_f32) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float dlt = v[i] - shift;
-          s1 += dlt;
-          s2 = fmaf(dlt, dlt, s2);
-        }
-        tmem_st32(trow + c0, v);
-      }
-      const float inv_n = 1.f / (float)sh.BN;
-      const float dm = s1 * inv_n;
-      mean = shift + dm;
-      rstd = rsqrtf(fmaxf(s2 * inv_n - dm * dm, 0.f) + 1e-6f);
-    }
-    for (int c0 = 0; c0 < sh.BN; c0 += 32) {
-      const int n = n0 + c0;
-      tmem_ld32(trow + c0, v);   // warp-collective: executed by all lanes, also for dead rows
-      if (n >= N) continue;      // tile column tail (BN does not divide N): nothing to store
-      if (!in_range) continue;
-      if (!live) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0.f;
-      } else {
-        if (e.ln) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = (v[i] - mean) * rstd;
+          for (int p = 0; p < 8; ++p) {
+            const float4 f = *reinterpret_cast<const float4*>(slot + lane * 128 + ((p ^ (lane & 7)) << 4));
+            v[p * 4] += f.x; v[p * 4 + 1] += f.y; v[p * 4 + 2] += f.z; v[p * 4 + 3] += f.w;
+          }
         } else {
-          if (biasp) {
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const uint4 u = *reinterpret_cast<const uint4*>(slot + lane * 64 + ((p ^ ((lane >> 1) & 3)) << 4));
+            add_bf16x8(u, v + p * 8);
+          }
+        }
+        __syncwarp();
+        issue_aux(ci + aux_depth);
+      };
+      // bf16 store of my 32 values through the swizzled staging tile: coalesced 16-byte global stores
+      auto store_chunk = [&](void* gout, int pitch, int col0, const float* v, bool act) {
+        bf16* gbase = reinterpret_cast<bf16*>(gout);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          uint32_t w[4];
+#pragma unroll
+          for (int k2 = 0; k2 < 4; ++k2) {
+            float a = v[p * 8 + k2 * 2], c = v[p * 8 + k2 * 2 + 1];
+            if (act) { a = silu_fast(a); c = silu_fast(c); }
+            w[k2] = pack_bf16x2(a, c);
+          }
+          *reinterpret_cast<uint4*>(out_st + lane * 64 + ((p ^ ((lane >> 1) & 3)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = i * 8 + (lane >> 2), piece = lane & 3;
+          const uint4 d = *reinterpret_cast<const uint4*>(out_st + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4));
+          const int mrow = m0 + q * 32 + rr;
+          if (mrow < sh.rows) *reinterpret_cast<uint4*>(gbase + (size_t)mrow * pitch + col0 + piece * 8) = d;
+        }
+        __syncwarp();
+      };
+
+      if (aux_in_pass1 || (aux_in_final && !e.ln)) {
+        for (int ci = 0; ci < aux_depth; ++ci) issue_aux(ci);
+      }
+      mbar_wait(smem_u32(&tmem_full_bar[as]), use & 1u);
+      tc_fence_after();
+
+      float v[32];
+      float mean = 0.f, rstd = 1.f;
+      if (e.ln) {
+        // pass 1: x = acc + bias + res_pre -> back to TMEM; shifted sums over my column half
+        float shift = 0.f, s1 = 0.f, s2 = 0.f;
+        for (int ci = 0; ci < my_nch; ++ci) {
+          const int c = c_lo + ci;
+          tmem_ld32(trow + c * 32, v);
+          if (sh.vec_bias_n) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(biasp + n + i));
+              const float4 bb = *reinterpret_cast<const float4*>(bias_s + n0 + c * 32 + i);
               v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
             }
           }
-          if (rpre) add_bf16x32(rpre + n, v);
+          if (aux_in_pass1) consume_aux(ci, v);
+          if (ci == 0) shift = v[0];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float dlt = v[i] - shift;
+            s1 += dlt;
+            s2 = fmaf(dlt, dlt, s2);
+          }
+          tmem_st32(trow + c * 32, v);
         }
-        if (gam) {
+        if (aux_in_final) {
+          for (int ci = 0; ci < aux_depth; ++ci) issue_aux(ci);
+        }
+        const float n_h = (float)(my_nch * 32), n_o = (float)(other_nch * 32), n_t = (float)sh.BN;
+        const float mean_h = shift + s1 / n_h;
+        const float m2_h = fmaxf(s2 - s1 * s1 / n_h, 0.f);
+        float* st = reinterpret_cast<float*>(ln_s + (size_t)(it & 1) * TC_BM + r_tile);
+        st[half * 2] = mean_h;
+        st[half * 2 + 1] = m2_h;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        const float mean_o = st[(half ^ 1) * 2], m2_o = st[(half ^ 1) * 2 + 1];
+        const float delta = mean_o - mean_h;
+        mean = (n_h * mean_h + n_o * mean_o) / n_t;
+        const float m2 = m2_h + m2_o + delta * delta * (n_h * n_o / n_t);
+        rstd = rsqrtf(m2 / n_t + 1e-6f);
+      }
+      const float nmr = -mean * rstd;
+      const float* gam_g = nullptr;
+      const float* bet_g = nullptr;
+      if (film && !film_s) {   // per-sample FiLM vectors (dhg_denoise with per-sample sigma): global loads
+        gam_g = e.gamma + (size_t)b * e.film_bstride;
+        bet_g = e.beta + (size_t)b * e.film_bstride;
+      }
+      for (int ci = 0; ci < my_nch; ++ci) {
+        const int c = c_lo + ci;
+        const int n = n0 + c * 32;
+        tmem_ld32(trow + c * 32, v);
+        if (ci == my_nch - 1) {   // my last TMEM read of this tile: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+        }
+        if (e.ln) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], rstd, nmr);
+        } else {
+          if (sh.vec_bias_n && !fold_bias) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 bb = *reinterpret_cast<const float4*>(bias_s + n + i);
+              v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
+            }
+          }
+          if (aux_kind == AUX_ROWBIAS || aux_kind == AUX_RES_PRE) consume_aux(ci, v);
+        }
+        if (film_s) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
-            const float4 g = __ldg(reinterpret_cast<const float4*>(gam + n + i));
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(bet + n + i));
+            const float4 g = *reinterpret_cast<const float4*>(gamma_s + n + i);
+            const float4 bb = *reinterpret_cast<const float4*>(betap_s + n + i);
+            v[i] = fmaf(v[i], g.x, bb.x); v[i + 1] = fmaf(v[i + 1], g.y, bb.y);
+            v[i + 2] = fmaf(v[i + 2], g.z, bb.z); v[i + 3] = fmaf(v[i + 3], g.w, bb.w);
+          }
+        } else if (gam_g) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gam_g + n + i));
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bet_g + n + i));
             v[i] = fmaf(v[i], g.x, bb.x); v[i + 1] = fmaf(v[i + 1], g.y, bb.y);
             v[i + 2] = fmaf(v[i + 2], g.z, bb.z); v[i + 3] = fmaf(v[i + 3], g.w, bb.w);
           }
         }
-        if (rpost) add_bf16x32(rpost + n, v);
+        if (aux_kind == AUX_RES_POST || aux_kind == AUX_RES_POST_UP) consume_aux(ci, v);
+        if (!live) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+        if (e.out_raw) store_chunk(e.out_raw, e.out_raw_pitch, n, v, false);
+        if (e.out_act) store_chunk(e.out_act, e.out_act_pitch, n, v, true);
       }
-      if (oraw) store_bf16x32<false>(oraw + n, v);
-      if (oact) store_bf16x32<true>(oact + n, v);
+      if (aux_kind != AUX_NONE) cp_async_wait<0>();
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)sh.tmem_cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
   }
 }
 
@@ -394,36 +570,68 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   }
   int BN = 0;
   if (e.ln) {
-    if (!(N <= 256 || N == 384)) { snprintf(err, errlen, "LayerNorm epilogue needs N <= 256 or N == 384, got %d", N); return nullptr; }
+    if (!((N <= 256 && N >= 64) || N == 384)) { snprintf(err, errlen, "LayerNorm epilogue needs 64 <= N <= 256 or N == 384, got %d", N); return nullptr; }
     BN = N;
   } else {
-    for (int cand : {256, 192, 128, 96, 64, 32})
+    for (int cand : {256, 192, 128, 96, 64})
       if (N % cand == 0) { BN = cand; break; }
   }
-  if (BN == 0 || BN % 16) { snprintf(err, errlen, "no tile width for N=%d", N); return nullptr; }
+  if (BN == 0 || BN % 32) { snprintf(err, errlen, "no tile width for N=%d", N); return nullptr; }
+  int aux_kind = AUX_NONE, naux = 0;
+  if (e.rowbias) { aux_kind = AUX_ROWBIAS; ++naux; }
+  if (e.res_pre) { aux_kind = AUX_RES_PRE; ++naux; }
+  if (e.res_post) { aux_kind = e.res_post_up ? AUX_RES_POST_UP : AUX_RES_POST; ++naux; }
+  if (naux > 1) { snprintf(err, errlen, "at most one of rowbias / res_pre / res_post per GEMM"); return nullptr; }
+  if (aux_kind == AUX_ROWBIAS && e.ln) { snprintf(err, errlen, "rowbias with LayerNorm is not supported"); return nullptr; }
+  if ((e.res_pre && e.res_pre_pitch % 8) || (e.res_post && e.res_post_pitch % 8) || (e.out_raw && e.out_raw_pitch % 8) ||
+      (e.out_act && e.out_act_pitch % 8)) {
+    snprintf(err, errlen, "row pitches must be multiples of 8 elements");
+    return nullptr;
+  }
+  int dev = 0, num_sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+
   TcGemmPlan* p = new TcGemmPlan();
   TcShape& sh = p->sh;
   sh.rows = rows; sh.K = K; sh.N = N; sh.taps = taps; sh.BN = BN;
+  sh.n_groups = N / BN;
+  const int m_tiles = (rows + TC_BM - 1) / TC_BM;
+  sh.num_tiles = m_tiles * sh.n_groups;
   sh.kb_per_tap = (K + TC_BK - 1) / TC_BK;
   sh.n_umma = BN > 256 ? 2 : 1;
   sh.umma_n = BN / sh.n_umma;
   // cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6) | a_format BF16 (1) [7,10) | b_format BF16 (1) [10,13) |
   // a,b K-major (0) | N>>3 [17,23) | M>>4 [24,29)
   sh.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(sh.umma_n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-  sh.tmem_cols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : BN <= 256 ? 256 : 512;
-  const size_t stage_bytes = (size_t)TC_BM * TC_BK * 2 + (size_t)BN * TC_BK * 2;
-  const int num_kb = taps * sh.kb_per_tap;
-  int stages = BN <= 256 ? 2 : 3;   // <= ~100 KB so that >= 2 CTAs share an SM (BN=384: one CTA)
-  if (stages > num_kb) stages = num_kb;
+  sh.acc_stages = BN <= 256 ? 2 : 1;
+  sh.aux_kind = aux_kind;
+  sh.vec_bias_n = (e.bias && !e.rowbias) ? N : 0;
+  sh.film_n = e.film_planned ? N : 0;
+  sh.stage_bytes = (uint32_t)(TC_BM * TC_BK * 2 + BN * TC_BK * 2);
+  // smem carve-up after the stage ring: aux rings, out staging, vectors, LN exchange, barriers
+  const size_t fixed = (aux_kind != AUX_NONE ? (size_t)EPI_WARPS * AUX_RING_BYTES : 0) + (size_t)EPI_WARPS * OUT_STAGE_BYTES +
+                       (size_t)(sh.vec_bias_n + 2 * sh.film_n) * 4 + (e.ln ? 2 * TC_BM * 16 : 0) + 32 * 8 + 64;
+  const size_t budget = 227 * 1024 - 1024 - fixed;
+  int stages = (int)(budget / sh.stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) { snprintf(err, errlen, "not enough shared memory for BN=%d", BN); delete p; return nullptr; }
   sh.stages = stages;
-  p->smem = stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
-  p->grid = dim3((rows + TC_BM - 1) / TC_BM, N / BN);
+  uint32_t off = (uint32_t)stages * sh.stage_bytes;
+  sh.off_aux = off; off += aux_kind != AUX_NONE ? EPI_WARPS * AUX_RING_BYTES : 0;
+  sh.off_out = off; off += EPI_WARPS * OUT_STAGE_BYTES;
+  sh.off_vec = off; off += (uint32_t)(sh.vec_bias_n + 2 * sh.film_n) * 4;
+  off = (off + 15u) & ~15u;
+  sh.off_ln = off; off += e.ln ? 2 * TC_BM * 16 : 0;
+  sh.off_bar = off; off += 32 * 8 + 64;
+  p->smem = off + 1024;
+  p->grid = dim3(sh.num_tiles < num_sms ? sh.num_tiles : num_sms);
   if (!make_map(&p->map_a, A, (uint64_t)rows, (uint64_t)K, (uint64_t)lda, TC_BM, err, errlen) ||
       !make_map(&p->map_w, W, (uint64_t)taps * N, (uint64_t)K, (uint64_t)K, (uint32_t)sh.umma_n, err, errlen)) {
     delete p;
     return nullptr;
   }
-  cudaError_t ce = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaError_t ce = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (ce != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); delete p; return nullptr; }
   return p;
 }

@@ -15,6 +15,16 @@ class DhgConfig(ctypes.Structure):
     _fields_ = [("num_layers", c_i32), ("channels", c_i32)]
 
 
+class DebugEpilogue(ctypes.Structure):
+    """dhg_debug_epilogue of include/dhg_b200.h (test hook)."""
+    _fields_ = [
+        ("bias", c_vp), ("rowbias", c_vp), ("res_pre", c_vp), ("res_pre_pitch", c_i32), ("ln", c_i32),
+        ("gamma", c_vp), ("beta", c_vp), ("film_bstride", c_i32), ("res_post", c_vp), ("res_post_pitch", c_i32),
+        ("res_post_up", c_i32), ("res_post_period_lo", c_i32), ("out_raw", c_vp), ("out_raw_pitch", c_i32),
+        ("out_act", c_vp), ("out_act_pitch", c_i32), ("period", c_i32), ("pad_first", c_i32), ("nvalid", c_i32),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/dhg_b200.h declares
 SIGNATURES = {
     "dhg_last_error": (c_cp, []),
@@ -38,6 +48,8 @@ SIGNATURES = {
     "dhg_set_option": (c_i32, [c_vp, c_cp, c_i32]),
     "dhg_debug_read": (c_i64, [c_vp, c_cp, c_vp, c_i64]),
     "dhg_debug_tc_gemm": (c_i32, [c_i32, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "dhg_debug_tc_gemm_ex": (c_i32, [c_i32, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, ctypes.POINTER(DebugEpilogue),
+                                     c_i32, ctypes.POINTER(ctypes.c_float), c_vp]),
 }
 
 

@@ -137,6 +137,34 @@ int32_t dhg_debug_tc_gemm(int32_t device, const void* dev_a_bf16, int32_t lda, i
                           const void* dev_w_bf16, int32_t K, int32_t N, int32_t taps,
                           const float* dev_bias, void* dev_out_bf16, void* stream);
 
+/* Test hook: the same GEMM with every fused-epilogue feature exposed (see csrc/common.cuh for the
+ * order of operations).  All pointers are device pointers; null = feature off.  Row r of the flat
+ * matrices maps to sample r / period, position r % period - pad_first; rows >= nvalid and (when
+ * pad_first) rows with r % period == 0 are halo rows and are written as zeros. */
+typedef struct dhg_debug_epilogue {
+  const float* bias;       /* [N] */
+  const float* rowbias;    /* [period - pad_first, N] fp32, bias folded in */
+  const void* res_pre;     /* bf16 [rows, res_pre_pitch] */
+  int32_t res_pre_pitch;
+  int32_t ln;              /* LayerNorm over N, eps 1e-6 */
+  const float* gamma;      /* FiLM: gamma[b * film_bstride + n] */
+  const float* beta;
+  int32_t film_bstride;
+  const void* res_post;    /* bf16 */
+  int32_t res_post_pitch;
+  int32_t res_post_up;     /* res_post lives one level down: row b*period_lo + 1 + pos/2 */
+  int32_t res_post_period_lo;
+  void* out_raw;           /* bf16 [rows, out_raw_pitch] */
+  int32_t out_raw_pitch;
+  void* out_act;           /* bf16 SiLU(value) */
+  int32_t out_act_pitch;
+  int32_t period, pad_first, nvalid;
+} dhg_debug_epilogue;
+int32_t dhg_debug_tc_gemm_ex(int32_t device, const void* dev_a_bf16, int32_t lda, int32_t rows,
+                             const void* dev_w_bf16, int32_t K, int32_t N, int32_t taps,
+                             const dhg_debug_epilogue* epi, int32_t repeats, float* ms_per_launch,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

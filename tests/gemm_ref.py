@@ -1,0 +1,99 @@
+"""Plain fp32 PyTorch reference of the fused tcgen05 GEMM + row epilogue (csrc/common.cuh order of
+operations), and a ctypes driver for the `dhg_debug_tc_gemm_ex` test hook.  Shared by the GPU tests
+and tools/gemm_bench.py."""
+import ctypes
+
+import torch
+
+from dhg_b200 import _abi
+
+
+def make_case(rows, K, N, taps, *, period=None, pad_first=0, bias=True, rowbias=False, res_pre=False, ln=False,
+              film=0, res_post=False, up=False, raw=True, act=False, seed=0, device="cuda"):
+    """film: 0 none, 1 one vector for the batch (bstride 0), 2 per-sample vectors."""
+    g = torch.Generator().manual_seed(seed)
+    period = period or rows
+    nb = (rows + period - 1) // period
+    nvalid = (rows // period) * period if period != rows else rows
+    c = {"rows": rows, "K": K, "N": N, "taps": taps, "period": period, "pad_first": pad_first, "nvalid": nvalid, "ln": ln}
+    r = torch.arange(rows)
+    pad = (r >= nvalid) | ((r % period == 0) if pad_first else torch.zeros(rows, dtype=torch.bool))
+    a = torch.randn(rows, K, generator=g)
+    a[pad] = 0
+    c["a"] = a.bfloat16().to(device)
+    c["w"] = (torch.randn(taps, N, K, generator=g) / (K * taps) ** 0.5).bfloat16().to(device)
+    c["pad"] = pad.to(device)
+    c["bias"] = torch.randn(N, generator=g).to(device) if bias and not rowbias else None
+    c["rowbias"] = torch.randn(period - pad_first, N, generator=g).to(device) if rowbias else None
+    c["res_pre"] = torch.randn(rows, N, generator=g).bfloat16().to(device) if res_pre else None
+    if film == 1:
+        c["gamma"], c["beta"], c["bstride"] = (1 + 0.3 * torch.randn(N, generator=g)).to(device), torch.randn(N, generator=g).to(device), 0
+    elif film == 2:
+        c["gamma"] = (1 + 0.3 * torch.randn(nb, 2 * N, generator=g)).to(device)
+        c["beta"], c["bstride"] = c["gamma"][:, N:], 2 * N
+    else:
+        c["gamma"] = c["beta"] = None
+        c["bstride"] = 0
+    c["up"] = up
+    if res_post and up:
+        plo = (period - pad_first) // 2 + 1
+        c["period_lo"] = plo
+        c["res_post"] = torch.randn(nb * plo + 1, N, generator=g).bfloat16().to(device)
+    elif res_post:
+        c["period_lo"] = 0
+        c["res_post"] = torch.randn(rows, N, generator=g).bfloat16().to(device)
+    else:
+        c["period_lo"], c["res_post"] = 0, None
+    c["out_raw"] = torch.full((rows, N), float("nan"), dtype=torch.bfloat16, device=device) if raw else None
+    c["out_act"] = torch.full((rows, N), float("nan"), dtype=torch.bfloat16, device=device) if act else None
+    return c
+
+
+def reference(c):
+    rows, N, taps, period, pf = c["rows"], c["N"], c["taps"], c["period"], c["pad_first"]
+    af, wf = c["a"].float(), c["w"].float()
+    x = torch.zeros(rows, N, device=af.device)
+    for t in range(taps):
+        shift = t - taps // 2
+        src = torch.zeros_like(af)
+        lo, hi = max(0, -shift), min(rows, rows - shift)
+        src[lo:hi] = af[lo + shift:hi + shift]
+        x += src @ wf[t].T
+    r = torch.arange(rows, device=af.device)
+    b = r // period
+    pos = (r % period - pf).clamp(min=0)
+    if c["rowbias"] is not None:
+        x += c["rowbias"][pos]
+    elif c["bias"] is not None:
+        x += c["bias"][None]
+    if c["res_pre"] is not None:
+        x += c["res_pre"].float()
+    if c["ln"]:
+        x = torch.nn.functional.layer_norm(x, (N,), eps=1e-6)
+    if c["gamma"] is not None:
+        if c["bstride"]:
+            x = x * c["gamma"][b, :N] + c["gamma"][b, N:]
+        else:
+            x = x * c["gamma"][None] + c["beta"][None]
+    if c["res_post"] is not None:
+        if c["up"]:
+            x += c["res_post"].float()[b * c["period_lo"] + 1 + pos // 2]
+        else:
+            x += c["res_post"].float()
+    x[c["pad"]] = 0
+    return x
+
+
+def run(lib, c, repeats=0):
+    p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+    N = c["N"]
+    e = _abi.DebugEpilogue(
+        p(c["bias"]), p(c["rowbias"]), p(c["res_pre"]), N, int(c["ln"]), p(c["gamma"]), p(c["beta"]), c["bstride"],
+        p(c["res_post"]), N, int(c["up"]), c["period_lo"], p(c["out_raw"]), N, p(c["out_act"]), N,
+        c["period"], c["pad_first"], c["nvalid"])
+    ms = ctypes.c_float(0)
+    rc = lib.dhg_debug_tc_gemm_ex(0, p(c["a"]), c["K"], c["rows"], p(c["w"]), c["K"], N, c["taps"], ctypes.byref(e),
+                                  repeats, ctypes.byref(ms), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, lib.dhg_last_error().decode()
+    torch.cuda.synchronize()
+    return ms.value

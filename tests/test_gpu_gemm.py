@@ -2,6 +2,10 @@
 PyTorch reference of the same op (bf16 inputs, fp32 accumulate), over every (K, N, taps) family the
 denoiser uses, ragged row counts, the K=96 tail and the 3-tap row-shift with zero halo."""
 import ctypes
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 import pytest
 import torch
@@ -39,3 +43,50 @@ def test_tc_gemm_matches_torch(built_lib, rows, K, N, taps):
     err = (out.float() - ref).abs().max().item()
     assert torch.isfinite(out.float()).all()
     assert err < 2e-2 * max(1.0, ref.abs().max().item()), err
+
+
+# every fused-epilogue combination the denoiser uses (engine.cu: conv_block / encoder_layer / build_plan)
+EPI_CASES = [
+    # name, rows, K, N, taps, kwargs
+    ("conv_film_act", 1000, 128, 64, 3, dict(period=50, pad_first=1, film=1, raw=False, act=True)),
+    ("conv_film_act_n96", 700, 128, 96, 3, dict(period=99, pad_first=1, film=1, raw=False, act=True)),
+    ("conv_skip_raw", 1500, 192, 128, 3, dict(period=197, pad_first=1)),
+    ("fc_film_respost", 1300, 128, 128, 1, dict(period=99, pad_first=1, film=1, res_post=True, act=True)),
+    ("fc_film_respost_256", 900, 256, 256, 1, dict(period=99, pad_first=1, film=1, res_post=True)),
+    ("skipconv_up", 1183, 128, 192, 3, dict(period=169, pad_first=1, res_post=True, up=True, act=True)),
+    ("skipconv_up_384", 797, 256, 384, 3, dict(period=99, pad_first=1, res_post=True, up=True, act=True)),
+    ("rowbias_q", 1379, 192, 192, 1, dict(period=197, pad_first=1, rowbias=True)),
+    ("rowbias_qkv", 1379, 192, 576, 1, dict(period=197, pad_first=1, rowbias=True)),
+    ("rowbias_qkv_1152", 451, 384, 1152, 1, dict(period=50, pad_first=1, rowbias=True)),
+    ("rowbias_text", 240, 256, 512, 1, dict(period=24, pad_first=0, rowbias=True)),
+    ("ln_film_respost_192", 1379, 192, 192, 1, dict(period=197, pad_first=1, ln=True, film=1, res_post=True)),
+    ("ln_film_respre_256", 991, 256, 256, 1, dict(period=99, pad_first=1, ln=True, film=1, res_pre=True, act=True)),
+    ("ln_film_respre_384", 451, 384, 384, 1, dict(period=50, pad_first=1, ln=True, film=1, res_pre=True)),
+    ("ln_film_respost_384", 451, 768, 384, 1, dict(period=50, pad_first=1, ln=True, film=1, res_post=True)),
+    ("ln_film_text", 240, 384, 192, 1, dict(period=24, pad_first=0, ln=True, film=1)),
+    ("ln_only_style", 700, 768, 384, 1, dict(period=70, pad_first=0, ln=True)),
+    ("film_per_sample", 1000, 128, 128, 3, dict(period=50, pad_first=1, film=2, raw=False, act=True)),
+    ("ln_film_per_sample", 451, 384, 384, 1, dict(period=50, pad_first=1, ln=True, film=2, res_pre=True)),
+    ("ffn1_act_768", 451, 384, 768, 1, dict(period=50, pad_first=1, raw=False, act=True)),
+    ("many_tiles", 40000, 128, 128, 3, dict(period=393, pad_first=1, film=1, raw=False, act=True)),
+    ("many_tiles_ln384", 30000, 384, 384, 1, dict(period=50, pad_first=1, ln=True, film=1, res_pre=True)),
+]
+
+
+@pytest.mark.parametrize("name,rows,K,N,taps,kw", EPI_CASES, ids=[c[0] for c in EPI_CASES])
+def test_tc_gemm_fused_epilogue(built_lib, name, rows, K, N, taps, kw):
+    import gemm_ref
+
+    c = gemm_ref.make_case(rows, K, N, taps, seed=len(name) + rows, **kw)
+    gemm_ref.run(built_lib, c)
+    ref = gemm_ref.reference(c)
+    scale = max(1.0, ref.abs().max().item())
+    if c["out_raw"] is not None:
+        assert torch.isfinite(c["out_raw"].float()).all()
+        err = (c["out_raw"].float() - ref).abs().max().item()
+        assert err < 2e-2 * scale, (name, "raw", err)
+    if c["out_act"] is not None:
+        sref = torch.nn.functional.silu(ref)
+        assert torch.isfinite(c["out_act"].float()).all()
+        err = (c["out_act"].float() - sref).abs().max().item()
+        assert err < 2e-2 * scale, (name, "act", err)
