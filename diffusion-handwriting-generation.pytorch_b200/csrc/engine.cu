@@ -132,6 +132,8 @@ struct Plan {
   std::vector<Op> once_ops, step_ops;
   Act head_in;
   std::vector<TcGemmPlan*> tc_plans;
+  std::vector<AttnTcPlan*> attn_plans;
+  int attn_impl = 1;
   cudaStream_t cap_stream = nullptr;
   cudaGraphExec_t graphs[4] = {nullptr, nullptr, nullptr, nullptr};  // [mode*2 + has_noise]
   int64_t launches_once = 0, launches_step = 0;
@@ -162,7 +164,7 @@ struct dhg_ctx {
   float *in_W = nullptr, *in_b = nullptr, *out_W = nullptr, *out_b = nullptr, *pen_W = nullptr, *pen_b = nullptr;
   std::vector<void*> allocs;
   Plan* plan = nullptr;
-  int opt_gemm = 1, opt_graph = 1, opt_sample_offset = 0;
+  int opt_gemm = 1, opt_graph = 1, opt_sample_offset = 0, opt_attn = 1;
   int64_t last_launches = 0;
 };
 
@@ -326,6 +328,7 @@ void free_plan(Plan* p) {
   for (int i = 0; i < 4; ++i)
     if (p->graphs[i]) cudaGraphExecDestroy(p->graphs[i]);
   for (auto t : p->tc_plans) tc_gemm_plan_destroy(t);
+  for (auto t : p->attn_plans) attn_tc_plan_destroy(t);
   if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
   for (auto a : p->allocs) cudaFree(a);
   delete p;
@@ -435,7 +438,7 @@ struct Builder {
   }
 
   void attention(const void* q, int qp, const void* k, int kp, const void* v, int vp, const Act& o, int H, int D,
-                 int Tq, int q_period, int q_pad, int Tk, int k_period, int k_pad, bool masked) {
+                 int Tq, int q_period, int q_pad, int Tk, int k_period, int k_pad, bool masked, int q_rows, int k_rows) {
     if (failed) return;
     AttnParams a;
     a.q = q; a.k = k; a.v = v; a.o = o.p;
@@ -446,6 +449,14 @@ struct Builder {
     a.text = masked ? P->text : nullptr;
     Plan* Pl = P;
     *nlaunch += 1;
+    if (P->prec == PREC_BF16 && P->attn_impl == 1 && attn_tc_supported(a)) {
+      char buf[512];
+      AttnTcPlan* ap = attn_tc_plan_create(a, q_rows, k_rows, buf, sizeof(buf));
+      if (!ap) { fail("plan: tcgen05 attention: %s", buf); failed = true; return; }
+      P->attn_plans.push_back(ap);
+      ops->push_back([=](cudaStream_t st, const StepCtx&) -> int { return attn_tc_launch(ap, st); });
+      return;
+    }
     ops->push_back([=](cudaStream_t st, const StepCtx&) -> int {
       const int r = Pl->prec == PREC_FP32 ? launch_attention_simt<float>(a, st) : launch_attention_simt<bf16>(a, st);
       return r ? fail("attention: unsupported head depth %d", a.D) : 0;
@@ -525,12 +536,12 @@ struct Builder {
     gemm(tp, p + ".mha.kv", skv, mt);
     EpiSpec sq; sq.rowbias = rb_q; sq.out_raw = q;
     gemm(x, p + ".mha.wq", sq, m);
-    attention(q.p, dm, kv.p, 2 * dm, col(kv, dm), 2 * dm, o, heads, D, Tl, Tl + 1, 1, L, L, 0, true);
+    attention(q.p, dm, kv.p, 2 * dm, col(kv, dm), 2 * dm, o, heads, D, Tl, Tl + 1, 1, L, L, 0, true, R, P->RT);
     EpiSpec sd; sd.ln = true; sd.film_off = film(p + ".affine1"); sd.res_post = x; sd.out_raw = x2;
     gemm(o, p + ".mha.dense", sd, m);
     EpiSpec sqkv; sqkv.rowbias = rb_qkv; sqkv.out_raw = qkv;
     gemm(x2, p + ".mha2.qkv", sqkv, m);
-    attention(qkv.p, 3 * dm, col(qkv, dm), 3 * dm, col(qkv, 2 * dm), 3 * dm, o2, heads, D, Tl, Tl + 1, 1, Tl, Tl + 1, 1, false);
+    attention(qkv.p, 3 * dm, col(qkv, dm), 3 * dm, col(qkv, 2 * dm), 3 * dm, o2, heads, D, Tl, Tl + 1, 1, Tl, Tl + 1, 1, false, R, R);
     EpiSpec sd2; sd2.res_pre = x2; sd2.ln = true; sd2.film_off = film(p + ".affine2"); sd2.out_raw = x3r; sd2.out_act = x3a;
     gemm(o2, p + ".mha2.dense", sd2, m);
     EpiSpec sf1; sf1.out_act = hid;
@@ -599,7 +610,7 @@ int build_plan(dhg_ctx* c, Plan* P) {
   bd.film_rows(t0, tf, L, bd.film(ts + ".affine2"));
   { EpiSpec s; s.out_raw = skv; bd.gemm(sf, ts + ".mha.kv", s, bd.map_style()); }
   { EpiSpec s; s.out_raw = tq; bd.gemm(tf, ts + ".mha.wq", s, bd.map_text()); }
-  bd.attention(tq.p, d, skv.p, 2 * d, bd.col(skv, d), 2 * d, to, 8, d / 8, L, L, 0, P->SP, P->SP, 0, false);
+  bd.attention(tq.p, d, skv.p, 2 * d, bd.col(skv, d), 2 * d, to, 8, d / 8, L, L, 0, P->SP, P->SP, 0, false, P->RT, P->RS);
   { EpiSpec s; s.res_pre = tf; s.ln = true; s.film_off = bd.film(ts + ".affine3"); s.out_act = t1a;
     bd.gemm(to, ts + ".mha.dense", s, bd.map_text()); }
   { EpiSpec s; s.out_act = th; bd.gemm(t1a, ts + ".text_ffn.1", s, bd.map_text()); }
@@ -929,6 +940,7 @@ int32_t dhg_plan(dhg_ctx* c, int32_t B, int32_t T, int32_t L, int32_t S, int32_t
   Plan* P = new Plan();
   P->B = B; P->T = T; P->L = L; P->S = S; P->prec = precision;
   P->gemm_impl = (precision == DHG_PREC_BF16) ? c->opt_gemm : 0;
+  P->attn_impl = (precision == DHG_PREC_BF16) ? c->opt_attn : 0;
   if (build_plan(c, P)) { free_plan(P); return 1; }
   CUDA_OK(cudaDeviceSynchronize());
   c->plan = P;
@@ -1073,6 +1085,7 @@ int32_t dhg_set_option(dhg_ctx* c, const char* key, int32_t value) {
   if (!c || !key) return fail("dhg_set_option: null argument");
   if (!strcmp(key, "gemm")) c->opt_gemm = value ? 1 : 0;
   else if (!strcmp(key, "graph")) c->opt_graph = value ? 1 : 0;
+  else if (!strcmp(key, "attn")) c->opt_attn = value ? 1 : 0;
   else if (!strcmp(key, "sample_offset")) c->opt_sample_offset = value;
   else return fail("dhg_set_option: unknown key %s", key);
   return 0;
@@ -1155,6 +1168,42 @@ int32_t dhg_debug_tc_gemm_ex(int32_t device, const void* a, int32_t lda, int32_t
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   tc_gemm_plan_destroy(p);
   if (ce != cudaSuccess) return fail("dhg_debug_tc_gemm_ex: %s", cudaGetErrorString(ce));
+  return 0;
+}
+
+int32_t dhg_debug_attention(int32_t device, const dhg_debug_attn* d, int32_t impl, int32_t repeats, float* ms_per_launch,
+                            void* stream) {
+  if (!d) return fail("dhg_debug_attention: null argument");
+  CUDA_OK(cudaSetDevice(device));
+  AttnParams a;
+  a.q = d->q; a.k = d->k; a.v = d->v; a.o = d->o;
+  a.q_pitch = d->q_pitch; a.k_pitch = d->k_pitch; a.v_pitch = d->v_pitch; a.o_pitch = d->o_pitch;
+  a.q_period = d->q_period; a.q_pad = d->q_pad; a.k_period = d->k_period; a.k_pad = d->k_pad;
+  a.B = d->B; a.H = d->H; a.D = d->D; a.Tq = d->Tq; a.Tk = d->Tk;
+  a.scale = 1.0f / sqrtf((float)d->D);
+  a.text = d->text;
+  cudaStream_t st = (cudaStream_t)stream;
+  AttnTcPlan* ap = nullptr;
+  if (impl == 1) {
+    char buf[512];
+    ap = attn_tc_plan_create(a, d->q_rows, d->k_rows, buf, sizeof(buf));
+    if (!ap) return fail("dhg_debug_attention: %s", buf);
+  }
+  auto launch = [&]() -> int { return ap ? attn_tc_launch(ap, st) : launch_attention_simt<bf16>(a, st); };
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  int rc = launch();
+  cudaEventRecord(e0, st);
+  for (int i = 0; i < repeats && !rc; ++i) rc = launch();
+  cudaEventRecord(e1, st);
+  cudaError_t ce = cudaStreamSynchronize(st);
+  float ms = 0.f;
+  if (ce == cudaSuccess && repeats > 0) cudaEventElapsedTime(&ms, e0, e1);
+  if (ms_per_launch) *ms_per_launch = repeats > 0 ? ms / repeats : 0.f;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (ap) attn_tc_plan_destroy(ap);
+  if (rc) return fail("dhg_debug_attention: unsupported shape");
+  if (ce != cudaSuccess) return fail("dhg_debug_attention: %s", cudaGetErrorString(ce));
   return 0;
 }
 

@@ -63,4 +63,12 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
 void tc_gemm_plan_destroy(TcGemmPlan*);
 int tc_gemm_launch(const TcGemmPlan*, const Epilogue& e, cudaStream_t st);
 
+// tcgen05 attention for head depth 64 and Tk <= 256 (attention_tc.cu).  q_rows / k_rows: total rows
+// of the q / k,v row matrices (TMA bounds).
+struct AttnTcPlan;
+bool attn_tc_supported(const AttnParams& p);
+AttnTcPlan* attn_tc_plan_create(const AttnParams& p, int q_rows, int k_rows, char* err, int errlen);
+void attn_tc_plan_destroy(AttnTcPlan*);
+int attn_tc_launch(const AttnTcPlan*, cudaStream_t st);
+
 }  // namespace dhg

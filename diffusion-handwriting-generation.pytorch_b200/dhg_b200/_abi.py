@@ -25,6 +25,17 @@ class DebugEpilogue(ctypes.Structure):
     ]
 
 
+class DebugAttn(ctypes.Structure):
+    """dhg_debug_attn of include/dhg_b200.h (test hook)."""
+    _fields_ = [
+        ("q", c_vp), ("k", c_vp), ("v", c_vp), ("o", c_vp),
+        ("q_pitch", c_i32), ("k_pitch", c_i32), ("v_pitch", c_i32), ("o_pitch", c_i32),
+        ("q_period", c_i32), ("q_pad", c_i32), ("k_period", c_i32), ("k_pad", c_i32),
+        ("B", c_i32), ("H", c_i32), ("D", c_i32), ("Tq", c_i32), ("Tk", c_i32),
+        ("q_rows", c_i32), ("k_rows", c_i32), ("text", c_vp),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/dhg_b200.h declares
 SIGNATURES = {
     "dhg_last_error": (c_cp, []),
@@ -48,6 +59,7 @@ SIGNATURES = {
     "dhg_set_option": (c_i32, [c_vp, c_cp, c_i32]),
     "dhg_debug_read": (c_i64, [c_vp, c_cp, c_vp, c_i64]),
     "dhg_debug_tc_gemm": (c_i32, [c_i32, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "dhg_debug_attention": (c_i32, [c_i32, ctypes.POINTER(DebugAttn), c_i32, c_i32, ctypes.POINTER(ctypes.c_float), c_vp]),
     "dhg_debug_tc_gemm_ex": (c_i32, [c_i32, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, ctypes.POINTER(DebugEpilogue),
                                      c_i32, ctypes.POINTER(ctypes.c_float), c_vp]),
 }

@@ -165,6 +165,19 @@ int32_t dhg_debug_tc_gemm_ex(int32_t device, const void* dev_a_bf16, int32_t lda
                              const dhg_debug_epilogue* epi, int32_t repeats, float* ms_per_launch,
                              void* stream);
 
+/* Test hook: one attention launch over caller-provided bf16 row matrices (head h = columns
+ * [h*D, h*D+D)); row(b, t) = b*period + pad + t.  impl 0 = CUDA-core kernel, 1 = tcgen05 kernel. */
+typedef struct dhg_debug_attn {
+  const void* q; const void* k; const void* v; void* o;
+  int32_t q_pitch, k_pitch, v_pitch, o_pitch;
+  int32_t q_period, q_pad, k_period, k_pad;
+  int32_t B, H, D, Tq, Tk;
+  int32_t q_rows, k_rows;   /* total rows of the q / k,v matrices */
+  const int64_t* text;      /* [B, Tk] token ids (0 = masked key) or NULL */
+} dhg_debug_attn;
+int32_t dhg_debug_attention(int32_t device, const dhg_debug_attn* a, int32_t impl, int32_t repeats,
+                            float* ms_per_launch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

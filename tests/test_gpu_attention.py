@@ -1,0 +1,93 @@
+"""The attention kernels on their own (C-ABI test hook) against torch SDPA in fp32 on the same bf16
+inputs: self-attention over the padded stroke rows at every pyramid level, masked cross-attention
+over text rows (including a fully padded prompt), ragged sizes, and the 8x48 text/style shape."""
+import ctypes
+import math
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from dhg_b200 import _abi  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def run_attention(lib, B, H, D, Tq, Tk, self_attn, masked, impl, seed=0, repeats=0):
+    g = torch.Generator().manual_seed(seed)
+    dm = H * D
+    if self_attn:   # q | k | v packed in one [rows, 3*dm] matrix, padded rows (pad_first = 1)
+        period, pad = Tq + 1, 1
+        rows = B * period + 1
+        qkv = torch.randn(rows, 3 * dm, generator=g).bfloat16().cuda()
+        q, k, v = qkv, qkv[:, dm:], qkv[:, 2 * dm:]
+        qp = kp = vp = 3 * dm
+        kperiod, kpad, krows = period, pad, rows
+    else:           # q [rows, dm] padded rows; k | v packed [B*Tk, 2*dm], no padding
+        period, pad = Tq + 1, 1
+        rows = B * period + 1
+        q = torch.randn(rows, dm, generator=g).bfloat16().cuda()
+        kv = torch.randn(B * Tk, 2 * dm, generator=g).bfloat16().cuda()
+        k, v = kv, kv[:, dm:]
+        qp, kp, vp = dm, 2 * dm, 2 * dm
+        kperiod, kpad, krows = Tk, 0, B * Tk
+    text = None
+    if masked:
+        text = torch.randint(1, 73, (B, Tk), generator=g)
+        for b in range(B):
+            n = int(torch.randint(1, Tk + 1, (1,), generator=g))
+            text[b, n:] = 0
+        text[B // 2] = 0          # one fully padded prompt: uniform attention in the reference
+        text = text.cuda()
+    o = torch.full((rows, dm), float("nan"), dtype=torch.bfloat16, device="cuda")
+    vp_ = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+    a = _abi.DebugAttn(vp_(q), vp_(k), vp_(v), vp_(o), qp, kp, vp, dm, period, pad, kperiod, kpad, B, H, D, Tq, Tk,
+                       rows, krows, vp_(text))
+    ms = ctypes.c_float(0)
+    rc = lib.dhg_debug_attention(0, ctypes.byref(a), impl, repeats, ctypes.byref(ms),
+                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, lib.dhg_last_error().decode()
+    torch.cuda.synchronize()
+
+    def rows_of(m, per, pd, T, width):
+        idx = (torch.arange(B, device="cuda")[:, None] * per + pd + torch.arange(T, device="cuda")[None]).reshape(-1)
+        return m[idx][:, :width].float().reshape(B, T, H, D).transpose(1, 2)
+
+    qf, kf, vf = rows_of(q, period, pad, Tq, dm), rows_of(k, kperiod, kpad, Tk, dm), rows_of(v, kperiod, kpad, Tk, dm)
+    mask = None
+    if masked:
+        mask = (text == 0).float()[:, None, None, :] * -1e9
+    ref = torch.nn.functional.scaled_dot_product_attention(qf, kf, vf, attn_mask=mask, scale=1.0 / math.sqrt(D))
+    got = rows_of(o, period, pad, Tq, dm)
+    return got, ref, ms.value
+
+
+CASES = [
+    # name, B, H, D, Tq, Tk, self, masked
+    ("self_L1", 5, 3, 64, 196, 196, True, False),
+    ("self_L2", 7, 4, 64, 98, 98, True, False),
+    ("self_L3", 9, 6, 64, 49, 49, True, False),
+    ("self_small", 3, 3, 64, 32, 32, True, False),
+    ("self_tiny", 2, 6, 64, 8, 8, True, False),
+    ("self_256", 2, 3, 64, 256, 256, True, False),
+    ("cross_L1", 5, 3, 64, 196, 24, False, True),
+    ("cross_L3", 9, 6, 64, 49, 24, False, True),
+    ("cross_L81", 4, 4, 64, 150, 81, False, True),
+    ("cross_10", 3, 3, 64, 32, 10, False, True),
+]
+
+
+@pytest.mark.parametrize("name,B,H,D,Tq,Tk,self_attn,masked", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("impl", [0, 1], ids=["simt", "tcgen05"])
+def test_attention_matches_sdpa(built_lib, impl, name, B, H, D, Tq, Tk, self_attn, masked):
+    got, ref, _ = run_attention(built_lib, B, H, D, Tq, Tk, self_attn, masked, impl, seed=len(name) + Tq)
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    assert err < 3e-2, (name, impl, err)
+
+
+def test_text_style_attention_simt(built_lib):
+    got, ref, _ = run_attention(built_lib, 6, 8, 48, 24, 70, False, False, 0, seed=5)
+    assert (got - ref).abs().max().item() < 3e-2
