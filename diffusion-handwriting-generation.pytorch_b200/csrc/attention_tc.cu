@@ -88,30 +88,41 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 4) {
-    if (lane == 0) {
-      const uint32_t lb = smem_u32(bar_load);
+    // the whole warp runs this (uniform) sequence; one elected lane issues TMA / tcgen05
+    const bool leader = elect_one();
+    const uint32_t lb = smem_u32(bar_load);
+    if (leader) {
       mbar_expect_tx(lb, (uint32_t)(128 * 128 + 2 * N * 128));
       tma_load_2d(smem_u32(q_s), &map_q, lb, h * 64, b * p.q_period + p.q_pad + qt * 128);
       tma_load_2d(smem_u32(k_s), &map_k, lb, h * 64, b * p.k_period + p.k_pad);
       tma_load_2d(smem_u32(v_s), &map_v, lb, h * 64, b * p.k_period + p.k_pad);
-      mbar_wait(lb, 0);
-      tc_fence_after();
-      // S = Q K^T
+    }
+    mbar_wait(lb, 0);
+    tc_fence_after();
+    // S = Q K^T
+    const uint32_t qlo = umma_desc_lo(smem_u32(q_s)), klo = umma_desc_lo(smem_u32(k_s));
+    if (leader) {
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        umma_bf16(tmem_base, umma_desc_sw128(smem_u32(q_s) + k * 32), umma_desc_sw128(smem_u32(k_s) + k * 32), sh.idesc_s, k ? 1u : 0u);
+        umma_bf16(tmem_base, umma_desc_make(qlo + 2 * k, kDescHiSw128), umma_desc_make(klo + 2 * k, kDescHiSw128), sh.idesc_s, k ? 1u : 0u);
       umma_commit(smem_u32(bar_s));
-      // O = P V   (P written by the softmax threads over the Q/K tiles)
-      mbar_wait(smem_u32(bar_p), 0);
-      tc_fence_after();
-      const int nk = N >> 4;
+    }
+    __syncwarp();
+    // O = P V   (P written by the softmax threads over the Q/K tiles)
+    mbar_wait(smem_u32(bar_p), 0);
+    tc_fence_after();
+    const int nk = N >> 4;
+    const uint32_t vlo = umma_desc_lo(smem_u32(v_s)) & ~(1u << 16);   // MN-major: LBO field set below
+    const uint32_t vlo_mn = vlo | ((1024u >> 4) << 16);
+    if (leader) {
       for (int kk = 0; kk < nk; ++kk) {
-        const uint64_t adesc = umma_desc_sw128(smem_u32(q_s) + (uint32_t)(kk >> 2) * 16384u + (uint32_t)(kk & 3) * 32u);
-        const uint64_t bdesc = umma_desc_sw128_mn(smem_u32(v_s) + (uint32_t)kk * 2048u);
-        umma_bf16(tmem_base, adesc, bdesc, sh.idesc_o, kk ? 1u : 0u);
+        const uint32_t alo = qlo + (uint32_t)(kk >> 2) * (16384u >> 4) + (uint32_t)(kk & 3) * 2u;
+        umma_bf16(tmem_base, umma_desc_make(alo, kDescHiSw128), umma_desc_make(vlo_mn + (uint32_t)kk * (2048u >> 4), kDescHiSw128),
+                  sh.idesc_o, kk ? 1u : 0u);
       }
       umma_commit(smem_u32(bar_o));
     }
+    __syncwarp();
   } else {
     const int r = warp * 32 + lane;           // query row inside the tile = TMEM lane
     const int tq = qt * 128 + r;

@@ -1082,6 +1082,9 @@ int64_t dhg_last_launch_count(const dhg_ctx* c) { return c ? c->last_launches : 
 int64_t dhg_plan_bytes(const dhg_ctx* c) { return (c && c->plan) ? (int64_t)c->plan->bytes : 0; }
 
 int32_t dhg_set_option(dhg_ctx* c, const char* key, int32_t value) {
+  if (key && !strcmp(key, "tap_shift")) { tc_gemm_set_option(0, value); return 0; }
+  if (key && !strcmp(key, "tap_base_offset")) { tc_gemm_set_option(1, value); return 0; }
+  if (key && !strcmp(key, "w_resident")) { tc_gemm_set_option(2, value); return 0; }
   if (!c || !key) return fail("dhg_set_option: null argument");
   if (!strcmp(key, "gemm")) c->opt_gemm = value ? 1 : 0;
   else if (!strcmp(key, "graph")) c->opt_graph = value ? 1 : 0;

@@ -45,8 +45,12 @@ struct TcShape {
   int rows, K, N, taps;
   int BN;          // tile width
   int n_groups;    // N / BN
-  int num_tiles;   // m_tiles * n_groups
-  int stages;
+  int m_tiles;
+  int stages_a, stages_w;   // A ring / W ring depth (W ring unused when w_resident)
+  int tap_shift;   // taps == 3: one A tile of 130 rows per k-block, the three taps are row-shifted descriptors
+  int w_resident;  // all W tiles of this CTA's column group stay in smem for the whole kernel
+  int sticky;      // CTA c only works on column group c % n_groups
+  int tap_base_offset;   // experiment: descriptor base_offset for the shifted taps
   int kb_per_tap;  // ceil(K / 64)
   int umma_n;      // N of one tcgen05.mma (BN, or 192 when BN == 384)
   int n_umma;      // MMAs per k-step along N (1 or 2)
@@ -55,7 +59,7 @@ struct TcShape {
   int aux_kind;
   int vec_bias_n;  // floats of bias staged in smem (0 or N)
   int film_n;      // floats of gamma / beta staged in smem (0 or N)
-  uint32_t stage_bytes, off_aux, off_out, off_vec, off_ln, off_bar;
+  uint32_t a_stage_bytes, a_tx_bytes, w_tile_bytes, off_w, off_aux, off_out, off_vec, off_ln, off_bar;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
@@ -64,18 +68,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sh.off_bar);
-  uint64_t* full_bar = bars;                       // [stages]
-  uint64_t* empty_bar = bars + sh.stages;          // [stages]
-  uint64_t* tmem_full_bar = bars + 2 * sh.stages;  // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* full_a = bars;                     // [8]
+  uint64_t* empty_a = bars + 8;                // [8]
+  uint64_t* full_w = bars + 16;                // [8]
+  uint64_t* empty_w = bars + 24;               // [8]
+  uint64_t* w_all_bar = bars + 32;             // resident W landed
+  uint64_t* tmem_full_bar = bars + 33;         // [2]
+  uint64_t* tmem_empty_bar = bars + 35;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 37);
   float* bias_s = reinterpret_cast<float*>(smem + sh.off_vec);
   float* gamma_s = bias_s + sh.vec_bias_n;
   float* betap_s = gamma_s + sh.film_n;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_kb = sh.taps * sh.kb_per_tap;
-  const uint32_t a_bytes = TC_BM * TC_BK * 2;  // 16 KB
+  // work assignment: tile `it` of this CTA -> (m tile, column group)
+  const int cta_groups = sh.sticky ? sh.n_groups : 1;
+  const int my_group = sh.sticky ? (int)(blockIdx.x % sh.n_groups) : 0;
+  const int t_first = sh.sticky ? (int)(blockIdx.x / sh.n_groups) : (int)blockIdx.x;
+  const int t_step = (int)gridDim.x / cta_groups;
+  const int t_end = sh.sticky ? sh.m_tiles : sh.m_tiles * sh.n_groups;
+  uint8_t* a_ring = smem;
+  uint8_t* w_base = smem + sh.off_w;
   const bool film = e.gamma != nullptr;
   const bool film_s = film && e.film_bstride == 0 && sh.film_n > 0;   // FiLM vectors shared by the batch -> smem
   const bool fold_bias = film_s && !e.ln && sh.vec_bias_n > 0;        // (acc + b) * g + beta = acc * g + (b * g + beta)
@@ -83,10 +96,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
-    for (int s = 0; s < sh.stages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(smem_u32(&full_a[s]), 1);
+      mbar_init(smem_u32(&empty_a[s]), 1);
+      mbar_init(smem_u32(&full_w[s]), 1);
+      mbar_init(smem_u32(&empty_w[s]), 1);
     }
+    mbar_init(smem_u32(w_all_bar), 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tmem_full_bar[a]), 1);
       mbar_init(smem_u32(&tmem_empty_bar[a]), EPI_WARPS);
@@ -113,56 +129,127 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
-      const int half_taps = sh.taps / 2;
-      uint32_t g = 0;
-      for (int t = blockIdx.x; t < sh.num_tiles; t += gridDim.x) {
-        const int mt = t / sh.n_groups, ng = t - mt * sh.n_groups;
+    {
+      const bool leader = elect_one();
+      const int a_row_off = sh.tap_shift ? -1 : -(sh.taps / 2);
+      const int a_loads_per_kb = sh.tap_shift ? 1 : sh.taps;   // taps without the shift trick: one A tile per tap
+      if (sh.w_resident) {
+        const int n0 = my_group * sh.BN;
+        const uint32_t wb = smem_u32(w_all_bar);
+        if (leader) mbar_expect_tx(wb, (uint32_t)(sh.taps * sh.kb_per_tap) * sh.w_tile_bytes);
+        for (int tap = 0; tap < sh.taps; ++tap)
+          for (int kbi = 0; kbi < sh.kb_per_tap; ++kbi) {
+            const uint32_t dst = smem_u32(w_base + (size_t)(tap * sh.kb_per_tap + kbi) * sh.w_tile_bytes);
+            if (leader)
+              for (int j = 0; j < sh.n_umma; ++j)
+                tma_load_2d(dst + (uint32_t)j * sh.umma_n * TC_BK * 2, &map_w, wb, kbi * TC_BK, tap * sh.N + n0 + j * sh.umma_n);
+          }
+      }
+      uint32_t ga = 0, gw = 0;
+      for (int t = t_first; t < t_end; t += t_step) {
+        const int mt = sh.sticky ? t : t / sh.n_groups;
+        const int ng = sh.sticky ? my_group : t - mt * sh.n_groups;
         const int m0 = mt * TC_BM, n0 = ng * sh.BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++g) {
-          const uint32_t s = g % (uint32_t)sh.stages;
-          const uint32_t phase = (g / (uint32_t)sh.stages) & 1u;
-          mbar_wait(smem_u32(&empty_bar[s]), phase ^ 1u);
-          const int tap = kb / sh.kb_per_tap, kk = (kb - tap * sh.kb_per_tap) * TC_BK;
-          const uint32_t a_dst = smem_u32(smem + (size_t)s * sh.stage_bytes);
-          const uint32_t b_dst = a_dst + a_bytes;
-          const uint32_t fb = smem_u32(&full_bar[s]);
-          mbar_expect_tx(fb, sh.stage_bytes);
-          tma_load_2d(a_dst, &map_a, fb, kk, m0 + tap - half_taps);
-          for (int j = 0; j < sh.n_umma; ++j)
-            tma_load_2d(b_dst + (uint32_t)j * sh.umma_n * TC_BK * 2, &map_w, fb, kk, tap * sh.N + n0 + j * sh.umma_n);
+        for (int kbi = 0; kbi < sh.kb_per_tap; ++kbi) {
+          const int kk = kbi * TC_BK;
+          for (int al = 0; al < a_loads_per_kb; ++al) {
+            const uint32_t sa = ga % (uint32_t)sh.stages_a;
+            mbar_wait(smem_u32(&empty_a[sa]), ((ga / (uint32_t)sh.stages_a) & 1u) ^ 1u);
+            const uint32_t fb = smem_u32(&full_a[sa]);
+            if (leader) {
+              mbar_expect_tx(fb, sh.a_tx_bytes);
+              tma_load_2d(smem_u32(a_ring + (size_t)sa * sh.a_stage_bytes), &map_a, fb, kk, m0 + a_row_off + al);
+            }
+            ++ga;
+            if (!sh.w_resident) {
+              const int tap_lo = sh.tap_shift ? 0 : al, tap_hi = sh.tap_shift ? sh.taps : al + 1;
+              for (int tap = tap_lo; tap < tap_hi; ++tap) {
+                const uint32_t sw = gw % (uint32_t)sh.stages_w;
+                mbar_wait(smem_u32(&empty_w[sw]), ((gw / (uint32_t)sh.stages_w) & 1u) ^ 1u);
+                const uint32_t fw = smem_u32(&full_w[sw]);
+                const uint32_t dst = smem_u32(w_base + (size_t)sw * sh.w_tile_bytes);
+                if (leader) {
+                  mbar_expect_tx(fw, sh.w_tile_bytes);
+                  for (int j = 0; j < sh.n_umma; ++j)
+                    tma_load_2d(dst + (uint32_t)j * sh.umma_n * TC_BK * 2, &map_w, fw, kk, tap * sh.N + n0 + j * sh.umma_n);
+                }
+                ++gw;
+              }
+            }
+          }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      uint32_t g = 0;
+    // ===== MMA issuer: the whole warp runs the (uniform) loop, one elected lane issues tcgen05 =====
+    {
+      const bool leader = elect_one();
+      const int a_loads_per_kb = sh.tap_shift ? 1 : sh.taps;
+      const uint32_t nb2 = (uint32_t)sh.umma_n * TC_BK * 2;   // byte offset of the second N half (BN = 384)
+      if (sh.w_resident) {
+        mbar_wait(smem_u32(w_all_bar), 0);
+        tc_fence_after();
+      }
+      uint32_t ga = 0, gw = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < sh.num_tiles; t += gridDim.x, ++it) {
+      for (int t = t_first; t < t_end; t += t_step, ++it) {
         const int as = sh.acc_stages == 2 ? (it & 1) : 0;
         const uint32_t use = sh.acc_stages == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;
         mbar_wait(smem_u32(&tmem_empty_bar[as]), (use & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)as * 256u;
-        for (int kb = 0; kb < num_kb; ++kb, ++g) {
-          const uint32_t s = g % (uint32_t)sh.stages;
-          const uint32_t phase = (g / (uint32_t)sh.stages) & 1u;
-          mbar_wait(smem_u32(&full_bar[s]), phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)s * sh.stage_bytes);
-          const uint32_t b_addr = a_addr + a_bytes;
+        uint32_t accum = 0;
+        for (int kbi = 0; kbi < sh.kb_per_tap; ++kbi) {
+          for (int al = 0; al < a_loads_per_kb; ++al) {
+            const uint32_t sa = ga % (uint32_t)sh.stages_a;
+            mbar_wait(smem_u32(&full_a[sa]), (ga / (uint32_t)sh.stages_a) & 1u);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(a_ring + (size_t)sa * sh.a_stage_bytes);
+            const int tap_lo = sh.tap_shift ? 0 : al, tap_hi = sh.tap_shift ? sh.taps : al + 1;
+            for (int tap = tap_lo; tap < tap_hi; ++tap) {
+              uint32_t b_addr;
+              uint32_t sw = 0;
+              if (sh.w_resident) {
+                b_addr = smem_u32(w_base + (size_t)(tap * sh.kb_per_tap + kbi) * sh.w_tile_bytes);
+              } else {
+                sw = gw % (uint32_t)sh.stages_w;
+                mbar_wait(smem_u32(&full_w[sw]), (gw / (uint32_t)sh.stages_w) & 1u);
+                tc_fence_after();
+                b_addr = smem_u32(w_base + (size_t)sw * sh.w_tile_bytes);
+              }
+              // shifted tap: logical row r of this operand is physical row r + tap of the 130-row tile
+              // (the 128B swizzle is a function of the absolute smem address, so a +128 B start just works)
+              const uint32_t alo = umma_desc_lo(a_addr + (sh.tap_shift ? (uint32_t)tap * 128u : 0u));
+              const uint32_t blo = umma_desc_lo(b_addr);
+              if (leader) {
+                if (sh.n_umma == 1) {
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            const uint64_t adesc = umma_desc_sw128(a_addr + k * 32);
-            for (int j = 0; j < sh.n_umma; ++j) {
-              const uint64_t bdesc = umma_desc_sw128(b_addr + (uint32_t)j * sh.umma_n * TC_BK * 2 + k * 32);
-              umma_bf16(acc + (uint32_t)j * sh.umma_n, adesc, bdesc, sh.idesc, (kb | k) ? 1u : 0u);
+                  for (int k = 0; k < TC_BK / 16; ++k) {
+                    umma_bf16(acc, umma_desc_make(alo + 2 * k, kDescHiSw128), umma_desc_make(blo + 2 * k, kDescHiSw128), sh.idesc, accum);
+                    accum = 1;
+                  }
+                } else {
+                  const uint32_t blo2 = umma_desc_lo(b_addr + nb2);
+#pragma unroll
+                  for (int k = 0; k < TC_BK / 16; ++k) {
+                    umma_bf16(acc, umma_desc_make(alo + 2 * k, kDescHiSw128), umma_desc_make(blo + 2 * k, kDescHiSw128), sh.idesc, accum);
+                    umma_bf16(acc + (uint32_t)sh.umma_n, umma_desc_make(alo + 2 * k, kDescHiSw128), umma_desc_make(blo2 + 2 * k, kDescHiSw128), sh.idesc, accum);
+                    accum = 1;
+                  }
+                }
+                if (!sh.w_resident) umma_commit(smem_u32(&empty_w[sw]));   // frees the W slot when these MMAs retire
+              }
+              accum = 1;
+              __syncwarp();
+              if (!sh.w_resident) ++gw;
             }
+            if (leader) umma_commit(smem_u32(&empty_a[sa]));               // frees the A slot
+            __syncwarp();
+            ++ga;
           }
-          umma_commit(smem_u32(&empty_bar[s]));        // frees the smem stage when these MMAs retire
         }
-        umma_commit(smem_u32(&tmem_full_bar[as]));     // accumulator complete
+        if (leader) umma_commit(smem_u32(&tmem_full_bar[as]));             // accumulator complete
+        __syncwarp();
       }
     }
   } else {
@@ -191,8 +278,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     const uint32_t lane_sel = ((uint32_t)(q * 32)) << 16;
 
     int it = 0;
-    for (int t = blockIdx.x; t < sh.num_tiles; t += gridDim.x, ++it) {
-      const int mt = t / sh.n_groups, ng = t - mt * sh.n_groups;
+    for (int t = t_first; t < t_end; t += t_step, ++it) {
+      const int mt = sh.sticky ? t : t / sh.n_groups;
+      const int ng = sh.sticky ? my_group : t - mt * sh.n_groups;
       const int m0 = mt * TC_BM, n0 = ng * sh.BN;
       const int as = sh.acc_stages == 2 ? (it & 1) : 0;
       const uint32_t use = sh.acc_stages == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;
@@ -397,6 +485,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 
 }  // namespace
 
+// experiment switches (dhg_set_option: "tap_shift", "tap_base_offset", "w_resident")
+int g_opt_tap_shift = 1, g_opt_tap_base_offset = 0, g_opt_w_resident = 1;
+void tc_gemm_set_option(int which, int value) {
+  if (which == 0) g_opt_tap_shift = value;
+  else if (which == 1) g_opt_tap_base_offset = value;
+  else if (which == 2) g_opt_w_resident = value;
+}
+
 struct TcGemmPlan {
   CUtensorMap map_a, map_w;
   TcShape sh;
@@ -439,7 +535,7 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   sh.rows = rows; sh.K = K; sh.N = N; sh.taps = taps; sh.BN = BN;
   sh.n_groups = N / BN;
   const int m_tiles = (rows + TC_BM - 1) / TC_BM;
-  sh.num_tiles = m_tiles * sh.n_groups;
+  sh.m_tiles = m_tiles;
   sh.kb_per_tap = (K + TC_BK - 1) / TC_BK;
   sh.n_umma = BN > 256 ? 2 : 1;
   sh.umma_n = BN / sh.n_umma;
@@ -450,25 +546,51 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   sh.aux_kind = aux_kind;
   sh.vec_bias_n = (e.bias && !e.rowbias) ? N : 0;
   sh.film_n = e.film_planned ? N : 0;
-  sh.stage_bytes = (uint32_t)(TC_BM * TC_BK * 2 + BN * TC_BK * 2);
-  // smem carve-up after the stage ring: aux rings, out staging, vectors, LN exchange, barriers
+  sh.tap_shift = (taps == 3 && g_opt_tap_shift) ? 1 : 0;
+  sh.tap_base_offset = g_opt_tap_base_offset;
+  const int a_rows = sh.tap_shift ? TC_BM + 2 : TC_BM;
+  sh.a_tx_bytes = (uint32_t)a_rows * TC_BK * 2;
+  sh.a_stage_bytes = (sh.a_tx_bytes + 1023u) & ~1023u;
+  sh.w_tile_bytes = (uint32_t)BN * TC_BK * 2;
+  // smem carve-up: A ring | W ring or resident W | aux rings | out staging | vectors | LN exchange | barriers
   const size_t fixed = (aux_kind != AUX_NONE ? (size_t)EPI_WARPS * AUX_RING_BYTES : 0) + (size_t)EPI_WARPS * OUT_STAGE_BYTES +
-                       (size_t)(sh.vec_bias_n + 2 * sh.film_n) * 4 + (e.ln ? 2 * TC_BM * 16 : 0) + 32 * 8 + 64;
+                       (size_t)(sh.vec_bias_n + 2 * sh.film_n) * 4 + 16 + (e.ln ? 2 * TC_BM * 16 : 0) + 64 * 8;
   const size_t budget = 227 * 1024 - 1024 - fixed;
-  int stages = (int)(budget / sh.stage_bytes);
-  if (stages > 8) stages = 8;
-  if (stages < 2) { snprintf(err, errlen, "not enough shared memory for BN=%d", BN); delete p; return nullptr; }
-  sh.stages = stages;
-  uint32_t off = (uint32_t)stages * sh.stage_bytes;
+  const size_t w_all = (size_t)taps * sh.kb_per_tap * sh.w_tile_bytes;
+  const int a_per_tile = sh.kb_per_tap * (sh.tap_shift ? 1 : taps);
+  sh.w_resident = (g_opt_w_resident && w_all + 3 * (size_t)sh.a_stage_bytes <= budget && m_tiles * sh.n_groups > num_sms) ? 1 : 0;
+  sh.sticky = (sh.w_resident && sh.n_groups > 1) ? 1 : 0;
+  size_t w_bytes;
+  if (sh.w_resident) {
+    int sa = (int)((budget - w_all) / sh.a_stage_bytes);
+    sh.stages_a = sa > 8 ? 8 : sa;
+    sh.stages_w = 1;
+    w_bytes = w_all;
+  } else {
+    const int w_per_a = sh.tap_shift ? taps : 1;
+    int sa = (int)(budget / (sh.a_stage_bytes + (size_t)w_per_a * sh.w_tile_bytes));
+    if (sa < 2) sa = 2;
+    if (sa > 8) sa = 8;
+    if ((size_t)sa * sh.a_stage_bytes + 2 * (size_t)sh.w_tile_bytes > budget) { snprintf(err, errlen, "not enough shared memory for BN=%d", BN); delete p; return nullptr; }
+    int sw = (int)((budget - (size_t)sa * sh.a_stage_bytes) / sh.w_tile_bytes);
+    sh.stages_a = sa;
+    sh.stages_w = sw > 8 ? 8 : sw;
+    w_bytes = (size_t)sh.stages_w * sh.w_tile_bytes;
+  }
+  (void)a_per_tile;
+  uint32_t off = (uint32_t)sh.stages_a * sh.a_stage_bytes;
+  sh.off_w = off; off += (uint32_t)w_bytes;
   sh.off_aux = off; off += aux_kind != AUX_NONE ? EPI_WARPS * AUX_RING_BYTES : 0;
   sh.off_out = off; off += EPI_WARPS * OUT_STAGE_BYTES;
   sh.off_vec = off; off += (uint32_t)(sh.vec_bias_n + 2 * sh.film_n) * 4;
   off = (off + 15u) & ~15u;
   sh.off_ln = off; off += e.ln ? 2 * TC_BM * 16 : 0;
-  sh.off_bar = off; off += 32 * 8 + 64;
+  sh.off_bar = off; off += 64 * 8;
   p->smem = off + 1024;
-  p->grid = dim3(sh.num_tiles < num_sms ? sh.num_tiles : num_sms);
-  if (!make_map(&p->map_a, A, (uint64_t)rows, (uint64_t)K, (uint64_t)lda, TC_BM, err, errlen) ||
+  int grid = m_tiles * sh.n_groups < num_sms ? m_tiles * sh.n_groups : num_sms;
+  if (sh.sticky) grid = (num_sms / sh.n_groups) * sh.n_groups;
+  p->grid = dim3(grid);
+  if (!make_map(&p->map_a, A, (uint64_t)rows, (uint64_t)K, (uint64_t)lda, (uint32_t)a_rows, err, errlen) ||
       !make_map(&p->map_w, W, (uint64_t)taps * N, (uint64_t)K, (uint64_t)K, (uint32_t)sh.umma_n, err, errlen)) {
     delete p;
     return nullptr;

@@ -83,6 +83,11 @@ def lib():
             fn = getattr(handle, name)  # AttributeError if the symbol is missing
             fn.restype, fn.argtypes = res, args
         _lib = handle
+        # experiment switches for the kernels, e.g. DHG_OPTS="tap_shift=0,w_resident=0"
+        for kv in filter(None, os.environ.get("DHG_OPTS", "").split(",")):
+            k, v = kv.split("=")
+            if handle.dhg_set_option(None, k.strip().encode(), int(v)) != 0:
+                raise DhgError(handle.dhg_last_error().decode())
     return _lib
 
 
