@@ -1085,6 +1085,7 @@ int32_t dhg_set_option(dhg_ctx* c, const char* key, int32_t value) {
   if (key && !strcmp(key, "tap_shift")) { tc_gemm_set_option(0, value); return 0; }
   if (key && !strcmp(key, "tap_base_offset")) { tc_gemm_set_option(1, value); return 0; }
   if (key && !strcmp(key, "w_resident")) { tc_gemm_set_option(2, value); return 0; }
+  if (key && !strcmp(key, "specialize")) { tc_gemm_set_option(3, value); return 0; }
   if (!c || !key) return fail("dhg_set_option: null argument");
   if (!strcmp(key, "gemm")) c->opt_gemm = value ? 1 : 0;
   else if (!strcmp(key, "graph")) c->opt_graph = value ? 1 : 0;

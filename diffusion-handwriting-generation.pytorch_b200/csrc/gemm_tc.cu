@@ -62,6 +62,10 @@ struct TcShape {
   uint32_t a_stage_bytes, a_tx_bytes, w_tile_bytes, off_w, off_aux, off_out, off_vec, off_ln, off_bar;
 };
 
+// Template parameters fix the epilogue variant at compile time (-1 = read the flag at run time: the
+// generic instance).  kLN: LayerNorm; kAUX: AUX_* kind; kFILM: 0 none, 1 vectors shared by the batch
+// (smem), 2 per-sample vectors (global loads); kOUT: 1 raw, 2 SiLU'd, 3 both.
+template <int kLN, int kAUX, int kFILM, int kOUT>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_w,
                                                                 const TcShape sh, const Epilogue e) {
@@ -254,16 +258,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     }
   } else {
     // ===== epilogue: warps 2..9; warp (q, half): TMEM lanes [32q, 32q+32), one half of the column chunks =====
+    const bool ln = kLN >= 0 ? (kLN != 0) : (e.ln != 0);
+    const int aux_kind = kAUX >= 0 ? kAUX : sh.aux_kind;
+    const int film_mode = kFILM >= 0 ? kFILM : (film ? (film_s ? 1 : 2) : 0);
+    const int out_mode = kOUT >= 0 ? kOUT : ((e.out_raw ? 1 : 0) | (e.out_act ? 2 : 0));
+    const bool has_bias = sh.vec_bias_n > 0;
     const int ew = warp - 2, q = warp & 3, half = ew >> 2;
     const int nch = sh.BN >> 5;
     const int c_lo = half ? ((nch + 1) >> 1) : 0;
     const int c_hi = half ? nch : ((nch + 1) >> 1);
     const int my_nch = c_hi - c_lo;
     const int other_nch = nch - my_nch;
-    uint8_t* aux_ring = smem + sh.off_aux + (size_t)ew * AUX_RING_BYTES;
-    uint8_t* out_st = smem + sh.off_out + (size_t)ew * OUT_STAGE_BYTES;
+    const uint32_t aux_ring = smem_u32(smem + sh.off_aux + (size_t)ew * AUX_RING_BYTES);
+    const uint32_t out_st = smem_u32(smem + sh.off_out + (size_t)ew * OUT_STAGE_BYTES);
+    const uint32_t bias_sa = smem_u32(bias_s), gamma_sa = smem_u32(gamma_s), betap_sa = smem_u32(betap_s);
     float4* ln_s = reinterpret_cast<float4*>(smem + sh.off_ln);   // [2 parity][128 rows] {mean0, M2_0, mean1, M2_1}
-    const int aux_kind = sh.aux_kind;
     const bool aux_f32 = aux_kind == AUX_ROWBIAS;
     const int aux_depth = aux_f32 ? 2 : 4;
     const uint32_t aux_slot_bytes = aux_f32 ? 4096u : 2048u;
@@ -272,10 +281,87 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     if (aux_kind == AUX_RES_PRE) { aux_base = (const char*)e.res_pre; aux_pitch_bytes = (size_t)e.res_pre_pitch * 2; }
     else if (aux_kind == AUX_RES_POST || aux_kind == AUX_RES_POST_UP) { aux_base = (const char*)e.res_post; aux_pitch_bytes = (size_t)e.res_post_pitch * 2; }
     else if (aux_kind == AUX_ROWBIAS) { aux_base = (const char*)e.rowbias; aux_pitch_bytes = (size_t)sh.N * 4; }
-    const bool aux_in_pass1 = e.ln && aux_kind == AUX_RES_PRE;
-    const bool aux_in_final = aux_kind != AUX_NONE && !aux_in_pass1;
+    const bool aux_in_pass1 = ln && aux_kind == AUX_RES_PRE;
     const int r_tile = q * 32 + lane;   // my accumulator row inside the tile
     const uint32_t lane_sel = ((uint32_t)(q * 32)) << 16;
+    // swizzled staging offsets: thread-per-row side (my row = lane) and coalesced side (4 lanes per row)
+    const uint32_t st_row = (uint32_t)lane * 64u, st_sw = (uint32_t)((lane >> 1) & 3);
+    const uint32_t co_rr = (uint32_t)(lane >> 2), co_piece = (uint32_t)(lane & 3);
+    const int period = e.map.period, pad_first = e.map.pad_first, nvalid = e.map.nvalid;
+
+    // aux rows are prefetched as one flat sequence of 32x32 chunks across tiles (tile it, chunk ci) ->
+    // flat index it * my_nch + ci, ring slot = flat % depth, so the loads for the next tile are already in
+    // flight while this tile is being finished.
+    uint32_t aux_issued = 0, aux_consumed = 0;
+    auto issue_aux_flat = [&]() {
+      const uint32_t f = aux_issued++;
+      const int fit = (int)(f / (uint32_t)my_nch), ci = (int)(f - (uint32_t)fit * (uint32_t)my_nch);
+      const int ft = t_first + fit * t_step;
+      if (ft < t_end) {
+        const int fmt = sh.sticky ? ft : ft / sh.n_groups;
+        const int fng = sh.sticky ? my_group : ft - fmt * sh.n_groups;
+        const int fm = fmt * TC_BM + r_tile;
+        // source row of my residual / bias row in that tile, -1 = none (zero-filled)
+        const bool f_in = fm < sh.rows;
+        int aux_src = -1;
+        if (aux_kind == AUX_RES_PRE || aux_kind == AUX_RES_POST) {
+          aux_src = f_in ? fm : -1;
+        } else {
+          const int fmm = f_in ? fm : 0;
+          const int fb = fmm / period;
+          const int fj = fmm - fb * period;
+          const bool f_pad = (fmm >= nvalid) || (pad_first && fj == 0);
+          const int fpos = f_pad ? 0 : fj - pad_first;
+          const bool f_live = f_in && !f_pad;
+          if (aux_kind == AUX_RES_POST_UP) aux_src = f_live ? fb * e.res_post_period_lo + 1 + (fpos >> 1) : -1;
+          else aux_src = f_live ? fpos : -1;
+        }
+        const int col0 = fng * sh.BN + (c_lo + ci) * 32;
+        const uint32_t slot = aux_ring + (f % (uint32_t)aux_depth) * aux_slot_bytes;
+        if (aux_f32) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + (lane >> 3), piece = lane & 7;
+            const int src = __shfl_sync(0xffffffffu, aux_src, rr);
+            const char* gp = aux_base + (size_t)(src < 0 ? 0 : src) * aux_pitch_bytes + (size_t)col0 * 4 + piece * 16;
+            cp_async16(slot + rr * 128 + ((piece ^ (rr & 7)) << 4), gp, src < 0 ? 0u : 16u);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = i * 8 + (lane >> 2), piece = lane & 3;
+            const int src = __shfl_sync(0xffffffffu, aux_src, rr);
+            const char* gp = aux_base + (size_t)(src < 0 ? 0 : src) * aux_pitch_bytes + (size_t)col0 * 2 + piece * 16;
+            cp_async16(slot + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4), gp, src < 0 ? 0u : 16u);
+          }
+        }
+      }
+      cp_async_commit();
+    };
+    // wait for the oldest aux chunk, add my row of it to v, refill its slot with the next flat chunk
+    auto consume_aux = [&](float* v) {
+      if (aux_f32) cp_async_wait<1>(); else cp_async_wait<3>();
+      __syncwarp();
+      const uint32_t slot = aux_ring + (aux_consumed % (uint32_t)aux_depth) * aux_slot_bytes;
+      ++aux_consumed;
+      if (aux_f32) {
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          const float4 f = lds128f_v(slot + lane * 128 + ((p ^ (lane & 7)) << 4));
+          v[p * 4] += f.x; v[p * 4 + 1] += f.y; v[p * 4 + 2] += f.z; v[p * 4 + 3] += f.w;
+        }
+      } else {
+        uint4 u[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) u[p] = lds128_v(slot + st_row + ((p ^ st_sw) << 4));
+#pragma unroll
+        for (int p = 0; p < 4; ++p) add_bf16x8(u[p], v + p * 8);
+      }
+      __syncwarp();
+      issue_aux_flat();
+    };
+    if (aux_kind != AUX_NONE)
+      for (int i = 0; i < aux_depth; ++i) issue_aux_flat();
 
     int it = 0;
     for (int t = t_first; t < t_end; t += t_step, ++it) {
@@ -290,65 +376,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       const int m = m0 + r_tile;
       const bool in_range = m < sh.rows;
       const int mm = in_range ? m : 0;
-      const int b = mm / e.map.period;
-      const int j = mm - b * e.map.period;
-      const bool is_pad = (mm >= e.map.nvalid) || (e.map.pad_first && j == 0);
-      const int pos = is_pad ? 0 : j - e.map.pad_first;
+      const int b = mm / period;
+      const int j = mm - b * period;
+      const bool is_pad = (mm >= nvalid) || (pad_first && j == 0);
       const bool live = in_range && !is_pad;
-      int aux_src = -1;   // source row of my residual / bias row, -1 = none (zero-filled)
-      if (aux_kind == AUX_RES_PRE || aux_kind == AUX_RES_POST) aux_src = in_range ? m : -1;
-      else if (aux_kind == AUX_RES_POST_UP) aux_src = live ? b * e.res_post_period_lo + 1 + (pos >> 1) : -1;
-      else if (aux_kind == AUX_ROWBIAS) aux_src = live ? pos : -1;
+      // coalesced side: my 4 (row, 16-byte piece) slots of a 32-row x 32-column chunk
+      const int co_rows_left = sh.rows - (m0 + q * 32);     // rows of this warp's slab that exist
+      const size_t co_row0 = (size_t)(m0 + q * 32) + co_rr;
 
-      // cp.async one chunk of aux rows (32 rows x 32 columns) into ring slot ci % depth
-      auto issue_aux = [&](int ci) {
-        if (ci < my_nch) {
-          const int col0 = n0 + (c_lo + ci) * 32;
-          const uint32_t slot = smem_u32(aux_ring + (size_t)(ci % aux_depth) * aux_slot_bytes);
-          if (aux_f32) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = i * 4 + (lane >> 3), piece = lane & 7;
-              const int src = __shfl_sync(0xffffffffu, aux_src, rr);
-              const char* gp = aux_base + (size_t)(src < 0 ? 0 : src) * aux_pitch_bytes + (size_t)col0 * 4 + piece * 16;
-              cp_async16(slot + rr * 128 + ((piece ^ (rr & 7)) << 4), gp, src < 0 ? 0u : 16u);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int rr = i * 8 + (lane >> 2), piece = lane & 3;
-              const int src = __shfl_sync(0xffffffffu, aux_src, rr);
-              const char* gp = aux_base + (size_t)(src < 0 ? 0 : src) * aux_pitch_bytes + (size_t)col0 * 2 + piece * 16;
-              cp_async16(slot + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4), gp, src < 0 ? 0u : 16u);
-            }
-          }
-        }
-        cp_async_commit();
-      };
-      // wait for chunk ci's aux rows, add mine to v, refill the slot with chunk ci + depth
-      auto consume_aux = [&](int ci, float* v) {
-        if (aux_f32) cp_async_wait<1>(); else cp_async_wait<3>();
-        __syncwarp();
-        const uint8_t* slot = aux_ring + (size_t)(ci % aux_depth) * aux_slot_bytes;
-        if (aux_f32) {
-#pragma unroll
-          for (int p = 0; p < 8; ++p) {
-            const float4 f = *reinterpret_cast<const float4*>(slot + lane * 128 + ((p ^ (lane & 7)) << 4));
-            v[p * 4] += f.x; v[p * 4 + 1] += f.y; v[p * 4 + 2] += f.z; v[p * 4 + 3] += f.w;
-          }
-        } else {
-#pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const uint4 u = *reinterpret_cast<const uint4*>(slot + lane * 64 + ((p ^ ((lane >> 1) & 3)) << 4));
-            add_bf16x8(u, v + p * 8);
-          }
-        }
-        __syncwarp();
-        issue_aux(ci + aux_depth);
-      };
       // bf16 store of my 32 values through the swizzled staging tile: coalesced 16-byte global stores
       auto store_chunk = [&](void* gout, int pitch, int col0, const float* v, bool act) {
-        bf16* gbase = reinterpret_cast<bf16*>(gout);
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
           uint32_t w[4];
@@ -358,41 +395,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
             if (act) { a = silu_fast(a); c = silu_fast(c); }
             w[k2] = pack_bf16x2(a, c);
           }
-          *reinterpret_cast<uint4*>(out_st + lane * 64 + ((p ^ ((lane >> 1) & 3)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          sts128(out_st + st_row + ((p ^ st_sw) << 4), make_uint4(w[0], w[1], w[2], w[3]));
         }
         __syncwarp();
+        uint4 d[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int rr = i * 8 + (lane >> 2), piece = lane & 3;
-          const uint4 d = *reinterpret_cast<const uint4*>(out_st + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4));
-          const int mrow = m0 + q * 32 + rr;
-          if (mrow < sh.rows) *reinterpret_cast<uint4*>(gbase + (size_t)mrow * pitch + col0 + piece * 8) = d;
+          const uint32_t rr = (uint32_t)i * 8u + co_rr;
+          d[i] = lds128_v(out_st + rr * 64u + ((co_piece ^ ((rr >> 1) & 3u)) << 4));
         }
+        bf16* gp = reinterpret_cast<bf16*>(gout) + co_row0 * (size_t)pitch + col0 + co_piece * 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if ((int)(i * 8 + co_rr) < co_rows_left) *reinterpret_cast<uint4*>(gp + (size_t)i * 8 * pitch) = d[i];
         __syncwarp();
       };
 
-      if (aux_in_pass1 || (aux_in_final && !e.ln)) {
-        for (int ci = 0; ci < aux_depth; ++ci) issue_aux(ci);
-      }
       mbar_wait(smem_u32(&tmem_full_bar[as]), use & 1u);
       tc_fence_after();
 
       float v[32];
       float mean = 0.f, rstd = 1.f;
-      if (e.ln) {
+      if (ln) {
         // pass 1: x = acc + bias + res_pre -> back to TMEM; shifted sums over my column half
         float shift = 0.f, s1 = 0.f, s2 = 0.f;
         for (int ci = 0; ci < my_nch; ++ci) {
           const int c = c_lo + ci;
           tmem_ld32(trow + c * 32, v);
-          if (sh.vec_bias_n) {
+          if (has_bias) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const float4 bb = *reinterpret_cast<const float4*>(bias_s + n0 + c * 32 + i);
+              const float4 bb = lds128f(bias_sa + (uint32_t)(n0 + c * 32 + i) * 4u);
               v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
             }
           }
-          if (aux_in_pass1) consume_aux(ci, v);
+          if (aux_in_pass1) consume_aux(v);
           if (ci == 0) shift = v[0];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -401,9 +438,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
             s2 = fmaf(dlt, dlt, s2);
           }
           tmem_st32(trow + c * 32, v);
-        }
-        if (aux_in_final) {
-          for (int ci = 0; ci < aux_depth; ++ci) issue_aux(ci);
         }
         const float n_h = (float)(my_nch * 32), n_o = (float)(other_nch * 32), n_t = (float)sh.BN;
         const float mean_h = shift + s1 / n_h;
@@ -421,7 +455,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       const float nmr = -mean * rstd;
       const float* gam_g = nullptr;
       const float* bet_g = nullptr;
-      if (film && !film_s) {   // per-sample FiLM vectors (dhg_denoise with per-sample sigma): global loads
+      if (film_mode == 2) {   // per-sample FiLM vectors (dhg_denoise with per-sample sigma): global loads
         gam_g = e.gamma + (size_t)b * e.film_bstride;
         bet_g = e.beta + (size_t)b * e.film_bstride;
       }
@@ -434,28 +468,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
         }
-        if (e.ln) {
+        if (ln) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], rstd, nmr);
         } else {
-          if (sh.vec_bias_n && !fold_bias) {
+          if (has_bias && !(film_mode == 1)) {   // film_mode 1 without LN: bias is folded into beta'
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const float4 bb = *reinterpret_cast<const float4*>(bias_s + n + i);
+              const float4 bb = lds128f(bias_sa + (uint32_t)(n + i) * 4u);
               v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
             }
           }
-          if (aux_kind == AUX_ROWBIAS || aux_kind == AUX_RES_PRE) consume_aux(ci, v);
+          if (aux_kind == AUX_ROWBIAS || aux_kind == AUX_RES_PRE) consume_aux(v);
         }
-        if (film_s) {
+        if (film_mode == 1) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
-            const float4 g = *reinterpret_cast<const float4*>(gamma_s + n + i);
-            const float4 bb = *reinterpret_cast<const float4*>(betap_s + n + i);
+            const float4 g = lds128f(gamma_sa + (uint32_t)(n + i) * 4u);
+            const float4 bb = lds128f(betap_sa + (uint32_t)(n + i) * 4u);
             v[i] = fmaf(v[i], g.x, bb.x); v[i + 1] = fmaf(v[i + 1], g.y, bb.y);
             v[i + 2] = fmaf(v[i + 2], g.z, bb.z); v[i + 3] = fmaf(v[i + 3], g.w, bb.w);
           }
-        } else if (gam_g) {
+        } else if (film_mode == 2) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const float4 g = __ldg(reinterpret_cast<const float4*>(gam_g + n + i));
@@ -464,16 +498,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
             v[i + 2] = fmaf(v[i + 2], g.z, bb.z); v[i + 3] = fmaf(v[i + 3], g.w, bb.w);
           }
         }
-        if (aux_kind == AUX_RES_POST || aux_kind == AUX_RES_POST_UP) consume_aux(ci, v);
+        if (aux_kind == AUX_RES_POST || aux_kind == AUX_RES_POST_UP) consume_aux(v);
         if (!live) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
-        if (e.out_raw) store_chunk(e.out_raw, e.out_raw_pitch, n, v, false);
-        if (e.out_act) store_chunk(e.out_act, e.out_act_pitch, n, v, true);
+        if (out_mode & 1) store_chunk(e.out_raw, e.out_raw_pitch, n, v, false);
+        if (out_mode & 2) store_chunk(e.out_act, e.out_act_pitch, n, v, true);
       }
-      if (aux_kind != AUX_NONE) cp_async_wait<0>();
     }
+    if (aux_kind != AUX_NONE) cp_async_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -486,11 +520,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 }  // namespace
 
 // experiment switches (dhg_set_option: "tap_shift", "tap_base_offset", "w_resident")
-int g_opt_tap_shift = 1, g_opt_tap_base_offset = 0, g_opt_w_resident = 1;
+int g_opt_tap_shift = 1, g_opt_tap_base_offset = 0, g_opt_w_resident = 1, g_opt_specialize = 1;
 void tc_gemm_set_option(int which, int value) {
   if (which == 0) g_opt_tap_shift = value;
   else if (which == 1) g_opt_tap_base_offset = value;
   else if (which == 2) g_opt_w_resident = value;
+  else if (which == 3) g_opt_specialize = value;
+}
+
+typedef void (*TcKernFn)(const CUtensorMap, const CUtensorMap, const TcShape, const Epilogue);
+struct TcKernEntry { int ln, aux, film, out; TcKernFn fn; };
+#define DHG_TC_K(ln, aux, film, out) {ln, aux, film, out, tc_gemm_kernel<ln, aux, film, out>}
+// Every epilogue variant the denoiser plan uses (engine.cu), film = 1 (sampling: one FiLM vector per step);
+// anything else (per-sample FiLM in dhg_denoise, test-only combinations) runs the generic instance.
+static const TcKernEntry kTcKernels[] = {
+    DHG_TC_K(0, AUX_NONE, 0, 1),          // conv_skip, att_dense, wq / kv of the text-style MHA
+    DHG_TC_K(0, AUX_NONE, 0, 2),          // ffn.1, text_ffn.1, style_ffn.1
+    DHG_TC_K(0, AUX_NONE, 1, 2),          // conv1, conv2
+    DHG_TC_K(0, AUX_RES_POST, 1, 1),      // fc + skip
+    DHG_TC_K(0, AUX_RES_POST_UP, 0, 3),   // skip_conv_k + upsample
+    DHG_TC_K(0, AUX_ROWBIAS, 0, 1),       // q / kv / qkv projections with the PE-folded bias table
+    DHG_TC_K(1, AUX_NONE, 1, 1),          // text_dense
+    DHG_TC_K(1, AUX_NONE, 0, 1),          // style_ffn.3
+    DHG_TC_K(1, AUX_NONE, 1, 2),          // text_ffn.3
+    DHG_TC_K(1, AUX_RES_POST, 1, 1),      // mha.dense
+    DHG_TC_K(1, AUX_RES_PRE, 1, 3),       // mha2.dense
+    DHG_TC_K(1, AUX_RES_PRE, 1, 1),       // ffn.3
+    DHG_TC_K(1, AUX_RES_PRE, 1, 2),       // text-style mha.dense
+    DHG_TC_K(-1, -1, -1, -1),             // generic
+};
+static TcKernFn pick_kernel(int ln, int aux, int film, int out) {
+  const int n = (int)(sizeof(kTcKernels) / sizeof(kTcKernels[0]));
+  if (g_opt_specialize)
+    for (int i = 0; i < n - 1; ++i)
+      if (kTcKernels[i].ln == ln && kTcKernels[i].aux == aux && kTcKernels[i].film == film && kTcKernels[i].out == out)
+        return kTcKernels[i].fn;
+  return kTcKernels[n - 1].fn;
 }
 
 struct TcGemmPlan {
@@ -498,6 +563,8 @@ struct TcGemmPlan {
   TcShape sh;
   dim3 grid;
   size_t smem;
+  TcKernFn fn_shared;    // FiLM (if any) with one vector for the batch
+  TcKernFn fn_generic;   // per-sample FiLM or anything unusual
 };
 
 TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W, int K, int N, int taps, const Epilogue& e,
@@ -595,15 +662,23 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
     delete p;
     return nullptr;
   }
-  cudaError_t ce = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (ce != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); delete p; return nullptr; }
+  const int out_mode = (e.out_raw ? 1 : 0) | (e.out_act ? 2 : 0);
+  p->fn_shared = pick_kernel(e.ln ? 1 : 0, aux_kind, e.film_planned ? 1 : 0, out_mode);
+  p->fn_generic = pick_kernel(-1, -1, -1, -1);
+  for (TcKernFn fn : {p->fn_shared, p->fn_generic}) {
+    cudaError_t ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (ce != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); delete p; return nullptr; }
+  }
   return p;
 }
 
 void tc_gemm_plan_destroy(TcGemmPlan* p) { delete p; }
 
 int tc_gemm_launch(const TcGemmPlan* p, const Epilogue& e, cudaStream_t st) {
-  tc_gemm_kernel<<<p->grid, TC_THREADS, p->smem, st>>>(p->map_a, p->map_w, p->sh, e);
+  // the specialised instance assumes FiLM vectors shared by the batch (or no FiLM at all)
+  const bool shared_ok = e.gamma ? (e.film_bstride == 0 && p->sh.film_n > 0) : (p->sh.film_n == 0);
+  TcKernFn fn = shared_ok ? p->fn_shared : p->fn_generic;
+  fn<<<p->grid, TC_THREADS, p->smem, st>>>(p->map_a, p->map_w, p->sh, e);
   return 0;
 }
 

@@ -62,7 +62,7 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
                                 const Epilogue& e, char* err, int errlen);
 void tc_gemm_plan_destroy(TcGemmPlan*);
 int tc_gemm_launch(const TcGemmPlan*, const Epilogue& e, cudaStream_t st);
-void tc_gemm_set_option(int which, int value);   // 0 tap_shift, 1 tap_base_offset, 2 w_resident (experiments)
+void tc_gemm_set_option(int which, int value);   // 0 tap_shift, 1 tap_base_offset, 2 w_resident, 3 specialize (experiments)
 
 // tcgen05 attention for head depth 64 and Tk <= 256 (attention_tc.cu).  q_rows / k_rows: total rows
 // of the q / k,v row matrices (TMA bounds).
