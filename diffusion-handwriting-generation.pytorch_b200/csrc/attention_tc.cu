@@ -1,4 +1,4 @@
-// Fused tensor-core attention for head depth 64, sm_100a (tcgen05 / TMEM / TMA).
+// Fused tensor-core attention for head depth 64 or 48, sm_100a (tcgen05 / TMEM / TMA).
 //
 //   O[b, tq, h, :] = softmax_j( scale * <Q[b,tq,h,:], K[b,j,h,:]> + mask[b,j] ) @ V[b,j,h,:]
 //
@@ -93,17 +93,18 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
     const uint32_t lb = smem_u32(bar_load);
     if (leader) {
       mbar_expect_tx(lb, (uint32_t)(128 * 128 + 2 * N * 128));
-      tma_load_2d(smem_u32(q_s), &map_q, lb, h * 64, b * p.q_period + p.q_pad + qt * 128);
-      tma_load_2d(smem_u32(k_s), &map_k, lb, h * 64, b * p.k_period + p.k_pad);
-      tma_load_2d(smem_u32(v_s), &map_v, lb, h * 64, b * p.k_period + p.k_pad);
+      // 64-column boxes starting at the head's first column; for D = 48 the last 16 columns belong to
+      // the next head (or are zero-filled past the matrix) and are never touched by the MMAs
+      tma_load_2d(smem_u32(q_s), &map_q, lb, h * p.D, b * p.q_period + p.q_pad + qt * 128);
+      tma_load_2d(smem_u32(k_s), &map_k, lb, h * p.D, b * p.k_period + p.k_pad);
+      tma_load_2d(smem_u32(v_s), &map_v, lb, h * p.D, b * p.k_period + p.k_pad);
     }
     mbar_wait(lb, 0);
     tc_fence_after();
     // S = Q K^T
     const uint32_t qlo = umma_desc_lo(smem_u32(q_s)), klo = umma_desc_lo(smem_u32(k_s));
     if (leader) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
+      for (int k = 0; k < (p.D >> 4); ++k)
         umma_bf16(tmem_base, umma_desc_make(qlo + 2 * k, kDescHiSw128), umma_desc_make(klo + 2 * k, kDescHiSw128), sh.idesc_s, k ? 1u : 0u);
       umma_commit(smem_u32(bar_s));
     }
@@ -170,13 +171,14 @@ __global__ void __launch_bounds__(AT_THREADS) attn_tc_kernel(const __grid_consta
     mbar_wait(smem_u32(bar_o), 0);
     tc_fence_after();
     const float inv = 1.f / sum;
-    bf16* orow = reinterpret_cast<bf16*>(p.o) + ((size_t)b * p.q_period + p.q_pad + tq) * p.o_pitch + h * 64;
+    bf16* orow = reinterpret_cast<bf16*>(p.o) + ((size_t)b * p.q_period + p.q_pad + tq) * p.o_pitch + h * p.D;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       tmem_ld32(trow + c * 32, v);
       if (tq < p.Tq) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
+          if (c * 32 + g * 8 >= p.D) break;
           const uint4 u = make_uint4(pack_bf16x2(v[g * 8] * inv, v[g * 8 + 1] * inv), pack_bf16x2(v[g * 8 + 2] * inv, v[g * 8 + 3] * inv),
                                      pack_bf16x2(v[g * 8 + 4] * inv, v[g * 8 + 5] * inv), pack_bf16x2(v[g * 8 + 6] * inv, v[g * 8 + 7] * inv));
           *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = u;
@@ -203,7 +205,7 @@ struct AttnTcPlan {
 };
 
 bool attn_tc_supported(const AttnParams& p) {
-  return p.D == 64 && p.Tk >= 1 && p.Tk <= 256 && p.q_pitch % 8 == 0 && p.k_pitch % 8 == 0 && p.v_pitch % 8 == 0 &&
+  return (p.D == 64 || p.D == 48) && p.Tk >= 1 && p.Tk <= 256 && p.q_pitch % 8 == 0 && p.k_pitch % 8 == 0 && p.v_pitch % 8 == 0 &&
          p.o_pitch % 8 == 0;
 }
 
@@ -220,7 +222,7 @@ AttnTcPlan* attn_tc_plan_create(const AttnParams& p, int q_rows, int k_rows, cha
   // c_format F32 [4,6) | a,b BF16 [7,10),[10,13) | b_major [16] | N>>3 [17,23) | M>>4 [24,29)
   const uint32_t base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
   sh.idesc_s = base | ((uint32_t)(sh.N >> 3) << 17);
-  sh.idesc_o = base | (1u << 16) | ((uint32_t)(64 >> 3) << 17);   // B = V is MN-major
+  sh.idesc_o = base | (1u << 16) | ((uint32_t)(p.D >> 3) << 17);   // B = V is MN-major, N = head depth
   sh.scale_log2 = p.scale * 1.4426950408889634f;
   const uint32_t kv_bytes = (uint32_t)sh.N * 128u;
   uint32_t pq = 16384u + kv_bytes;                    // Q | K
@@ -236,7 +238,7 @@ AttnTcPlan* attn_tc_plan_create(const AttnParams& p, int q_rows, int k_rows, cha
   if (smem < floor_smem) smem = floor_smem < min_smem ? floor_smem : min_smem;
   a->smem = smem;
   a->grid = dim3((p.Tq + 127) / 128, p.H, p.B);
-  const uint64_t qcols = (uint64_t)p.H * 64, kcols = (uint64_t)p.H * 64;
+  const uint64_t qcols = (uint64_t)p.H * p.D, kcols = (uint64_t)p.H * p.D;
   if (!make_map(&a->map_q, p.q, (uint64_t)q_rows, qcols, (uint64_t)p.q_pitch, 128, err, errlen) ||
       !make_map(&a->map_k, p.k, (uint64_t)k_rows, kcols, (uint64_t)p.k_pitch, (uint32_t)sh.N, err, errlen) ||
       !make_map(&a->map_v, p.v, (uint64_t)k_rows, kcols, (uint64_t)p.v_pitch, (uint32_t)sh.N, err, errlen)) {

@@ -32,7 +32,9 @@ struct RowMap {
 // + res_post -> zero if halo row -> store raw and/or SiLU'd copy.
 struct Epilogue {
   const float* bias;       // [N] or null
-  const float* rowbias;    // [period - pad_first, N] indexed by position (bias folded in) or null
+  const float* rowbias;    // [period - pad_first, N] indexed by position (bias folded in) or null  (CUDA-core path)
+  const void* rowbias16;   // bf16 [period - pad_first, rowbias16_cols]: per-position term added on top of `bias`
+  int rowbias16_cols;      //   for output columns < rowbias16_cols (tcgen05 path), or null
   const void* res_pre;     // activation dtype, same row index, or null
   int res_pre_pitch;
   int ln;                  // LayerNorm over the N outputs, eps 1e-6, no affine

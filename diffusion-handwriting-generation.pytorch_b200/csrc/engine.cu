@@ -101,6 +101,8 @@ struct Act {
 struct EpiSpec {
   bool bias = true;
   const float* rowbias = nullptr;
+  const void* rowbias16 = nullptr;
+  int rowbias16_cols = 0;
   Act res_pre;
   bool ln = false;
   int film_off = -1;
@@ -351,7 +353,7 @@ std::vector<float> pe_table(int len, int dim, float pos_factor) {
 }
 
 // rowbias[pos, n] = bias[n] + sum_k PE[pos,k] * W[k][n] for columns [n_pe0, n_pe1); bias only elsewhere.
-int make_rowbias(Plan* P, const Lin& W, const std::vector<float>& pe, int len, int n_pe0, int n_pe1, float** out) {
+int make_rowbias(Plan* P, const Lin& W, const std::vector<float>& pe, int len, int n_pe0, int n_pe1, float** out, void** out16) {
   std::vector<float> t((size_t)len * W.N);
   for (int i = 0; i < len; ++i)
     for (int n = 0; n < W.N; ++n) {
@@ -362,6 +364,15 @@ int make_rowbias(Plan* P, const Lin& W, const std::vector<float>& pe, int len, i
     }
   if (dev_alloc(P->allocs, (void**)out, t.size() * sizeof(float), &P->bytes)) return 1;
   CUDA_OK(cudaMemcpy(*out, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (out16) {   // bf16 [len, n_pe1 - n_pe0] table of the positional term alone (the bias stays an fp32 vector)
+    const int cols = n_pe1 - n_pe0;
+    std::vector<bf16> t16((size_t)len * cols);
+    for (int i = 0; i < len; ++i)
+      for (int n = 0; n < cols; ++n)
+        t16[(size_t)i * cols + n] = __float2bfloat16_rn(t[(size_t)i * W.N + n_pe0 + n] - W.h_b[n_pe0 + n]);
+    if (dev_alloc(P->allocs, out16, t16.size() * sizeof(bf16), &P->bytes)) return 1;
+    CUDA_OK(cudaMemcpy(*out16, t16.data(), t16.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+  }
   return 0;
 }
 
@@ -394,8 +405,11 @@ struct Builder {
     if (A.C != W->K) { fail("plan: gemm %s K mismatch (%d vs %d)", wkey.c_str(), A.C, W->K); failed = true; return; }
     Epilogue e;
     memset(&e, 0, sizeof(e));
-    e.bias = (s.bias && !s.rowbias) ? W->bias : nullptr;
-    e.rowbias = s.rowbias;
+    const bool tc_path = P->prec == PREC_BF16 && P->gemm_impl == 1;
+    e.bias = (s.bias && (tc_path || !s.rowbias)) ? W->bias : nullptr;
+    e.rowbias = tc_path ? nullptr : s.rowbias;
+    e.rowbias16 = tc_path ? s.rowbias16 : nullptr;
+    e.rowbias16_cols = s.rowbias16_cols;
     e.res_pre = s.res_pre.p; e.res_pre_pitch = s.res_pre.C;
     e.ln = s.ln ? 1 : 0;
     e.film_planned = s.film_off >= 0 ? 1 : 0;
@@ -522,24 +536,25 @@ struct Builder {
     // positional-embedding-folded bias tables
     const std::vector<float> pe_x = pe_table(Tl, dm, pos_factor), pe_t = pe_table(L, dm, 1.0f);
     float *rb_q = nullptr, *rb_kv = nullptr, *rb_qkv = nullptr;
+    void *rb16_q = nullptr, *rb16_kv = nullptr, *rb16_qkv = nullptr;
     if (!failed) {
-      if (make_rowbias(P, c->lins.at(p + ".mha.wq"), pe_x, Tl, 0, dm, &rb_q) ||
-          make_rowbias(P, c->lins.at(p + ".mha.kv"), pe_t, L, 0, dm, &rb_kv) ||          // k gets PE, v does not
-          make_rowbias(P, c->lins.at(p + ".mha2.qkv"), pe_x, Tl, 0, 2 * dm, &rb_qkv))   // q,k get PE, v does not
+      if (make_rowbias(P, c->lins.at(p + ".mha.wq"), pe_x, Tl, 0, dm, &rb_q, &rb16_q) ||
+          make_rowbias(P, c->lins.at(p + ".mha.kv"), pe_t, L, 0, dm, &rb_kv, &rb16_kv) ||          // k gets PE, v does not
+          make_rowbias(P, c->lins.at(p + ".mha2.qkv"), pe_x, Tl, 0, 2 * dm, &rb_qkv, &rb16_qkv))   // q,k get PE, v does not
         failed = true;
     }
     Act tp = act(P->RT, dm), kv = act(P->RT, 2 * dm), q = act(R, dm), o = act(R, dm), x2 = act(R, dm);
     Act qkv = act(R, 3 * dm), o2 = act(R, dm), x3r = act(R, dm), x3a = act(R, dm), hid = act(R, 2 * dm), out = act(R, dm);
     EpiSpec s; s.ln = true; s.film_off = film(p + ".affine0"); s.out_raw = tp;
     gemm(text_act, p + ".text_dense", s, mt);
-    EpiSpec skv; skv.rowbias = rb_kv; skv.out_raw = kv;
+    EpiSpec skv; skv.rowbias = rb_kv; skv.rowbias16 = rb16_kv; skv.rowbias16_cols = dm; skv.out_raw = kv;
     gemm(tp, p + ".mha.kv", skv, mt);
-    EpiSpec sq; sq.rowbias = rb_q; sq.out_raw = q;
+    EpiSpec sq; sq.rowbias = rb_q; sq.rowbias16 = rb16_q; sq.rowbias16_cols = dm; sq.out_raw = q;
     gemm(x, p + ".mha.wq", sq, m);
     attention(q.p, dm, kv.p, 2 * dm, col(kv, dm), 2 * dm, o, heads, D, Tl, Tl + 1, 1, L, L, 0, true, R, P->RT);
     EpiSpec sd; sd.ln = true; sd.film_off = film(p + ".affine1"); sd.res_post = x; sd.out_raw = x2;
     gemm(o, p + ".mha.dense", sd, m);
-    EpiSpec sqkv; sqkv.rowbias = rb_qkv; sqkv.out_raw = qkv;
+    EpiSpec sqkv; sqkv.rowbias = rb_qkv; sqkv.rowbias16 = rb16_qkv; sqkv.rowbias16_cols = 2 * dm; sqkv.out_raw = qkv;
     gemm(x2, p + ".mha2.qkv", sqkv, m);
     attention(qkv.p, 3 * dm, col(qkv, dm), 3 * dm, col(qkv, 2 * dm), 3 * dm, o2, heads, D, Tl, Tl + 1, 1, Tl, Tl + 1, 1, false, R, R);
     EpiSpec sd2; sd2.res_pre = x2; sd2.ln = true; sd2.film_off = film(p + ".affine2"); sd2.out_raw = x3r; sd2.out_act = x3a;
@@ -1146,7 +1161,7 @@ int32_t dhg_debug_tc_gemm_ex(int32_t device, const void* a, int32_t lda, int32_t
   CUDA_OK(cudaSetDevice(device));
   Epilogue e;
   memset(&e, 0, sizeof(e));
-  e.bias = d->bias; e.rowbias = d->rowbias;
+  e.bias = d->bias; e.rowbias16 = d->rowbias; e.rowbias16_cols = d->rowbias_cols;
   e.res_pre = d->res_pre; e.res_pre_pitch = d->res_pre_pitch;
   e.ln = d->ln;
   e.gamma = d->gamma; e.beta = d->beta; e.film_bstride = d->film_bstride; e.film_planned = d->gamma ? 1 : 0;

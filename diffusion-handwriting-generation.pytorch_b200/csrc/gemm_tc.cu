@@ -273,14 +273,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     const uint32_t out_st = smem_u32(smem + sh.off_out + (size_t)ew * OUT_STAGE_BYTES);
     const uint32_t bias_sa = smem_u32(bias_s), gamma_sa = smem_u32(gamma_s), betap_sa = smem_u32(betap_s);
     float4* ln_s = reinterpret_cast<float4*>(smem + sh.off_ln);   // [2 parity][128 rows] {mean0, M2_0, mean1, M2_1}
-    const bool aux_f32 = aux_kind == AUX_ROWBIAS;
+    const bool aux_f32 = false;   // (fp32 aux rows: unused since the per-position bias table became bf16)
+    const int aux_ncols = aux_kind == AUX_ROWBIAS ? e.rowbias16_cols : 0x7fffffff;   // aux only for columns below this
     const int aux_depth = aux_f32 ? 2 : 4;
     const uint32_t aux_slot_bytes = aux_f32 ? 4096u : 2048u;
     const char* aux_base = nullptr;
     size_t aux_pitch_bytes = 0;
     if (aux_kind == AUX_RES_PRE) { aux_base = (const char*)e.res_pre; aux_pitch_bytes = (size_t)e.res_pre_pitch * 2; }
     else if (aux_kind == AUX_RES_POST || aux_kind == AUX_RES_POST_UP) { aux_base = (const char*)e.res_post; aux_pitch_bytes = (size_t)e.res_post_pitch * 2; }
-    else if (aux_kind == AUX_ROWBIAS) { aux_base = (const char*)e.rowbias; aux_pitch_bytes = (size_t)sh.N * 4; }
+    else if (aux_kind == AUX_ROWBIAS) { aux_base = (const char*)e.rowbias16; aux_pitch_bytes = (size_t)e.rowbias16_cols * 2; }
     const bool aux_in_pass1 = ln && aux_kind == AUX_RES_PRE;
     const int r_tile = q * 32 + lane;   // my accumulator row inside the tile
     const uint32_t lane_sel = ((uint32_t)(q * 32)) << 16;
@@ -318,7 +319,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         }
         const int col0 = fng * sh.BN + (c_lo + ci) * 32;
         const uint32_t slot = aux_ring + (f % (uint32_t)aux_depth) * aux_slot_bytes;
-        if (aux_f32) {
+        if (col0 >= aux_ncols) {
+          // no per-position term for these columns
+        } else if (aux_f32) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = i * 4 + (lane >> 3), piece = lane & 7;
@@ -339,12 +342,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       cp_async_commit();
     };
     // wait for the oldest aux chunk, add my row of it to v, refill its slot with the next flat chunk
-    auto consume_aux = [&](float* v) {
+    auto consume_aux = [&](float* v, int col0) {
       if (aux_f32) cp_async_wait<1>(); else cp_async_wait<3>();
       __syncwarp();
       const uint32_t slot = aux_ring + (aux_consumed % (uint32_t)aux_depth) * aux_slot_bytes;
       ++aux_consumed;
-      if (aux_f32) {
+      if (col0 >= aux_ncols) {
+        // nothing was loaded for this chunk
+      } else if (aux_f32) {
 #pragma unroll
         for (int p = 0; p < 8; ++p) {
           const float4 f = lds128f_v(slot + lane * 128 + ((p ^ (lane & 7)) << 4));
@@ -429,7 +434,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
               v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
             }
           }
-          if (aux_in_pass1) consume_aux(v);
+          if (aux_in_pass1) consume_aux(v, n0 + c * 32);
           if (ci == 0) shift = v[0];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -479,7 +484,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
               v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
             }
           }
-          if (aux_kind == AUX_ROWBIAS || aux_kind == AUX_RES_PRE) consume_aux(v);
+          if (aux_kind == AUX_ROWBIAS || aux_kind == AUX_RES_PRE) consume_aux(v, n);
         }
         if (film_mode == 1) {
 #pragma unroll
@@ -498,7 +503,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
             v[i + 2] = fmaf(v[i + 2], g.z, bb.z); v[i + 3] = fmaf(v[i + 3], g.w, bb.w);
           }
         }
-        if (aux_kind == AUX_RES_POST || aux_kind == AUX_RES_POST_UP) consume_aux(v);
+        if (aux_kind == AUX_RES_POST || aux_kind == AUX_RES_POST_UP) consume_aux(v, n);
         if (!live) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -583,11 +588,12 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   }
   if (BN == 0 || BN % 32) { snprintf(err, errlen, "no tile width for N=%d", N); return nullptr; }
   int aux_kind = AUX_NONE, naux = 0;
-  if (e.rowbias) { aux_kind = AUX_ROWBIAS; ++naux; }
+  if (e.rowbias16) { aux_kind = AUX_ROWBIAS; ++naux; }
   if (e.res_pre) { aux_kind = AUX_RES_PRE; ++naux; }
   if (e.res_post) { aux_kind = e.res_post_up ? AUX_RES_POST_UP : AUX_RES_POST; ++naux; }
   if (naux > 1) { snprintf(err, errlen, "at most one of rowbias / res_pre / res_post per GEMM"); return nullptr; }
   if (aux_kind == AUX_ROWBIAS && e.ln) { snprintf(err, errlen, "rowbias with LayerNorm is not supported"); return nullptr; }
+  if (e.rowbias16 && (e.rowbias16_cols % 32 || e.rowbias16_cols > N)) { snprintf(err, errlen, "rowbias16_cols must be a multiple of 32 and <= N"); return nullptr; }
   if ((e.res_pre && e.res_pre_pitch % 8) || (e.res_post && e.res_post_pitch % 8) || (e.out_raw && e.out_raw_pitch % 8) ||
       (e.out_act && e.out_act_pitch % 8)) {
     snprintf(err, errlen, "row pitches must be multiples of 8 elements");
@@ -611,7 +617,7 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   sh.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(sh.umma_n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
   sh.acc_stages = BN <= 256 ? 2 : 1;
   sh.aux_kind = aux_kind;
-  sh.vec_bias_n = (e.bias && !e.rowbias) ? N : 0;
+  sh.vec_bias_n = e.bias ? N : 0;
   sh.film_n = e.film_planned ? N : 0;
   sh.tap_shift = (taps == 3 && g_opt_tap_shift) ? 1 : 0;
   sh.tap_base_offset = g_opt_tap_base_offset;

@@ -18,7 +18,7 @@ class DhgConfig(ctypes.Structure):
 class DebugEpilogue(ctypes.Structure):
     """dhg_debug_epilogue of include/dhg_b200.h (test hook)."""
     _fields_ = [
-        ("bias", c_vp), ("rowbias", c_vp), ("res_pre", c_vp), ("res_pre_pitch", c_i32), ("ln", c_i32),
+        ("bias", c_vp), ("rowbias", c_vp), ("rowbias_cols", c_i32), ("res_pre", c_vp), ("res_pre_pitch", c_i32), ("ln", c_i32),
         ("gamma", c_vp), ("beta", c_vp), ("film_bstride", c_i32), ("res_post", c_vp), ("res_post_pitch", c_i32),
         ("res_post_up", c_i32), ("res_post_period_lo", c_i32), ("out_raw", c_vp), ("out_raw_pitch", c_i32),
         ("out_act", c_vp), ("out_act_pitch", c_i32), ("period", c_i32), ("pad_first", c_i32), ("nvalid", c_i32),

@@ -143,7 +143,8 @@ int32_t dhg_debug_tc_gemm(int32_t device, const void* dev_a_bf16, int32_t lda, i
  * pad_first) rows with r % period == 0 are halo rows and are written as zeros. */
 typedef struct dhg_debug_epilogue {
   const float* bias;       /* [N] */
-  const float* rowbias;    /* [period - pad_first, N] fp32, bias folded in */
+  const void* rowbias;     /* bf16 [period - pad_first, rowbias_cols]: per-position term for columns < rowbias_cols */
+  int32_t rowbias_cols;
   const void* res_pre;     /* bf16 [rows, res_pre_pitch] */
   int32_t res_pre_pitch;
   int32_t ln;              /* LayerNorm over N, eps 1e-6 */

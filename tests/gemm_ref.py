@@ -23,8 +23,10 @@ def make_case(rows, K, N, taps, *, period=None, pad_first=0, bias=True, rowbias=
     c["a"] = a.bfloat16().to(device)
     c["w"] = (torch.randn(taps, N, K, generator=g) / (K * taps) ** 0.5).bfloat16().to(device)
     c["pad"] = pad.to(device)
-    c["bias"] = torch.randn(N, generator=g).to(device) if bias and not rowbias else None
-    c["rowbias"] = torch.randn(period - pad_first, N, generator=g).to(device) if rowbias else None
+    c["bias"] = torch.randn(N, generator=g).to(device) if bias else None
+    # per-position term (bf16) for the first rowbias_cols columns only (q / k get positional embeddings, v does not)
+    c["rowbias_cols"] = (N if N <= 256 else (2 * N // 3) // 32 * 32) if rowbias else 0
+    c["rowbias"] = torch.randn(period - pad_first, c["rowbias_cols"], generator=g).bfloat16().to(device) if rowbias else None
     c["res_pre"] = torch.randn(rows, N, generator=g).bfloat16().to(device) if res_pre else None
     if film == 1:
         c["gamma"], c["beta"], c["bstride"] = (1 + 0.3 * torch.randn(N, generator=g)).to(device), torch.randn(N, generator=g).to(device), 0
@@ -62,10 +64,10 @@ def reference(c):
     r = torch.arange(rows, device=af.device)
     b = r // period
     pos = (r % period - pf).clamp(min=0)
-    if c["rowbias"] is not None:
-        x += c["rowbias"][pos]
-    elif c["bias"] is not None:
+    if c["bias"] is not None:
         x += c["bias"][None]
+    if c["rowbias"] is not None:
+        x[:, :c["rowbias_cols"]] += c["rowbias"].float()[pos]
     if c["res_pre"] is not None:
         x += c["res_pre"].float()
     if c["ln"]:
@@ -88,7 +90,7 @@ def run(lib, c, repeats=0):
     p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
     N = c["N"]
     e = _abi.DebugEpilogue(
-        p(c["bias"]), p(c["rowbias"]), p(c["res_pre"]), N, int(c["ln"]), p(c["gamma"]), p(c["beta"]), c["bstride"],
+        p(c["bias"]), p(c["rowbias"]), c["rowbias_cols"], p(c["res_pre"]), N, int(c["ln"]), p(c["gamma"]), p(c["beta"]), c["bstride"],
         p(c["res_post"]), N, int(c["up"]), c["period_lo"], p(c["out_raw"]), N, p(c["out_act"]), N,
         c["period"], c["pad_first"], c["nvalid"])
     ms = ctypes.c_float(0)

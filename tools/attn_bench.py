@@ -13,13 +13,15 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 lib = _abi.lib()
 CASES = [("self L1 196x196 h3", 3, 196, 196, True, False, 1), ("self L2 98x98 h4", 4, 98, 98, True, False, 1),
          ("self L3 49x49 h6", 6, 49, 49, True, False, 2), ("cross L1 196x24 h3", 3, 196, 24, False, True, 1),
-         ("cross L2 98x24 h4", 4, 98, 24, False, True, 1), ("cross L3 49x24 h6", 6, 49, 24, False, True, 2)]
+         ("cross L2 98x24 h4", 4, 98, 24, False, True, 1), ("cross L3 49x24 h6", 6, 49, 24, False, True, 2),
+         ("text-style 24x70 h8 d48", 8, 24, 70, False, False, 1)]
 tot = [0.0, 0.0]
 for name, H, Tq, Tk, sa, mk, cnt in CASES:
     line = f"{name:22s}"
     for impl in (0, 1):
-        got, ref, ms = run_attention(lib, B, H, 64, Tq, Tk, sa, mk, impl, seed=1, repeats=5)
-        fl = 4.0 * B * H * Tq * Tk * 64
+        D = 48 if "d48" in name else 64
+        got, ref, ms = run_attention(lib, B, H, D, Tq, Tk, sa, mk, impl, seed=1, repeats=5)
+        fl = 4.0 * B * H * Tq * Tk * D
         line += f"  impl{impl}: {ms*1e3:8.1f} us {fl/ms/1e9:7.1f} TF/s err {(got-ref).abs().max().item():.2e}"
         tot[impl] += cnt * ms * 1e3
     print(line, flush=True)

@@ -85,7 +85,7 @@ for name, cnt, rows, K, N, taps, kw in CASES:
     if c["res_post"] is not None:
         by += c["res_post"].numel() * 2
     if c["rowbias"] is not None:
-        by += c["rowbias"].numel() * 4
+        by += c["rowbias"].numel() * 2
     us = ms * 1e3
     print(f"      {name:38s} {us:8.1f} {fl/us/1e6:7.1f} {by/us/1e3:7.0f}  {cnt}")
     tot_us += cnt * us; tot_fl += cnt * fl; tot_by += cnt * by
