@@ -27,6 +27,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <functional>
@@ -1097,8 +1098,8 @@ int64_t dhg_last_launch_count(const dhg_ctx* c) { return c ? c->last_launches : 
 int64_t dhg_plan_bytes(const dhg_ctx* c) { return (c && c->plan) ? (int64_t)c->plan->bytes : 0; }
 
 int32_t dhg_set_option(dhg_ctx* c, const char* key, int32_t value) {
-  if (key && !strcmp(key, "tap_shift")) { tc_gemm_set_option(0, value); return 0; }
-  if (key && !strcmp(key, "tap_base_offset")) { tc_gemm_set_option(1, value); return 0; }
+  if (key && !strcmp(key, "interleave")) { tc_gemm_set_option(4, value); return 0; }
+  if (key && !strcmp(key, "mma_repeat")) { tc_gemm_set_option(5, value); return 0; }
   if (key && !strcmp(key, "w_resident")) { tc_gemm_set_option(2, value); return 0; }
   if (key && !strcmp(key, "specialize")) { tc_gemm_set_option(3, value); return 0; }
   if (!c || !key) return fail("dhg_set_option: null argument");
@@ -1174,6 +1175,26 @@ int32_t dhg_debug_tc_gemm_ex(int32_t device, const void* a, int32_t lda, int32_t
   TcGemmPlan* p = tc_gemm_plan_create((const bf16*)a, lda, rows, (const bf16*)w, K, N, taps, e, buf, sizeof(buf));
   if (!p) return fail("dhg_debug_tc_gemm_ex: %s", buf);
   cudaStream_t st = (cudaStream_t)stream;
+  if (getenv("DHG_DESCRIBE")) { tc_gemm_describe(p, buf, sizeof(buf)); fprintf(stderr, "tc_gemm plan: %s\n", buf); }
+  if (getenv("DHG_TRACE")) {   // timeline of CTA 0 for one launch, printed to stderr
+    const int cap = 4096;   // entries per role (3 roles)
+    unsigned long long* tb = nullptr;
+    cudaMalloc(&tb, 3 * cap * sizeof(unsigned long long));
+    cudaMemset(tb, 0, 3 * cap * sizeof(unsigned long long));
+    tc_gemm_launch(p, e, st);   // warm
+    cudaStreamSynchronize(st);
+    tc_gemm_set_trace(p, tb, cap);
+    tc_gemm_launch(p, e, st);
+    cudaStreamSynchronize(st);
+    tc_gemm_set_trace(p, nullptr, 0);
+    std::vector<unsigned long long> h(3 * cap);
+    cudaMemcpy(h.data(), tb, 3 * cap * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(tb);
+    unsigned long long t0 = ~0ull;
+    for (auto x : h) if (x && (x >> 16) < t0) t0 = x >> 16;
+    for (auto x : h)
+      if (x) fprintf(stderr, "TR %llu %02x %u\n", (x >> 16) - t0, (unsigned)((x >> 8) & 0xff), (unsigned)(x & 0xff));
+  }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   tc_gemm_launch(p, e, st);

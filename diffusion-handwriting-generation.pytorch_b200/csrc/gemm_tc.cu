@@ -10,7 +10,7 @@
 //   warp  1    TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, bf16 x bf16 -> fp32 in
 //              TMEM).  Two accumulator stages (2 x 256 columns) when BN <= 256, so the MMAs of tile
 //              i+1 overlap the epilogue of tile i.
-//   warps 2-9  epilogue: warp (q, half) owns TMEM lanes [32q, 32q+32) and one half of the tile's
+//   warps 2+   epilogue (16 warps): warp (q, part) owns TMEM lanes [32q, 32q+32) and one part of the tile's
 //              32-column chunks; thread = one accumulator row.  Residual / per-position-bias rows are
 //              prefetched with cp.async into a per-warp swizzled ring (coalesced global reads), the
 //              bf16 outputs go through a per-warp swizzled staging tile and leave as coalesced 16-byte
@@ -33,9 +33,15 @@ using namespace tc;
 namespace {
 
 constexpr int TC_BM = 128;
-constexpr int TC_THREADS = 320;
-constexpr int EPI_WARPS = 8;
-constexpr int AUX_RING_BYTES = 8192;   // per epilogue warp: 4 x 2 KB (bf16 rows) or 2 x 4 KB (fp32 rows)
+#ifndef DHG_EPI_PARTS
+#define DHG_EPI_PARTS 2
+#endif
+constexpr int EPI_PARTS = DHG_EPI_PARTS;              // epilogue warps per TMEM lane quarter (column split)
+constexpr int EPI_WARPS = 4 * EPI_PARTS;
+constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int AUX_DEPTH = 8 / EPI_PARTS;              // aux ring slots per epilogue warp
+constexpr int AUX_SLOT_BYTES = 2048;                  // 32 rows x 32 bf16
+constexpr int AUX_RING_BYTES = AUX_DEPTH * AUX_SLOT_BYTES;
 constexpr int OUT_STAGE_BYTES = 2048;  // per epilogue warp: 32 rows x 32 bf16
 constexpr int TMEM_COLS = 512;
 
@@ -46,11 +52,11 @@ struct TcShape {
   int BN;          // tile width
   int n_groups;    // N / BN
   int m_tiles;
+  int G;           // row tiles per super-tile (independent accumulators interleaved by the MMA warp)
+  int m_super;     // ceil(m_tiles / G)
   int stages_a, stages_w;   // A ring / W ring depth (W ring unused when w_resident)
-  int tap_shift;   // taps == 3: one A tile of 130 rows per k-block, the three taps are row-shifted descriptors
   int w_resident;  // all W tiles of this CTA's column group stay in smem for the whole kernel
   int sticky;      // CTA c only works on column group c % n_groups
-  int tap_base_offset;   // experiment: descriptor base_offset for the shifted taps
   int kb_per_tap;  // ceil(K / 64)
   int umma_n;      // N of one tcgen05.mma (BN, or 192 when BN == 384)
   int n_umma;      // MMAs per k-step along N (1 or 2)
@@ -60,7 +66,100 @@ struct TcShape {
   int vec_bias_n;  // floats of bias staged in smem (0 or N)
   int film_n;      // floats of gamma / beta staged in smem (0 or N)
   uint32_t a_stage_bytes, a_tx_bytes, w_tile_bytes, off_w, off_aux, off_out, off_vec, off_ln, off_bar;
+  unsigned long long* trace;   // debug: CTA 0 appends (clock << 16 | code << 8 | tile) events; trace[0] = count
+  int trace_cap;
 };
+
+// fire-and-forget store into the role's private region (role 0 producer, 1 MMA, 2 first epilogue warp): no atomics,
+// no round trip, so the traced warp is barely perturbed
+#define DHG_TR(code, tile)                                                                        \
+  do {                                                                                            \
+    if (sh.trace && blockIdx.x == 0 && lane == 0 && tr_n < (unsigned)sh.trace_cap)                \
+      sh.trace[(size_t)tr_role * sh.trace_cap + tr_n++] =                                         \
+          ((unsigned long long)clock64() << 16) | ((unsigned long long)(code) << 8) | (unsigned)((tile) & 0xff); \
+  } while (0)
+
+// The MMA warp's main loop, specialised on the tap count and on the number of interleaved accumulators so that
+// everything inside a k-block is straight-line code (the single issuing warp is latency-critical: every
+// instruction between two tcgen05.mma shows up in the tile time).
+template <int TAPS, int G>
+__device__ __forceinline__ void mma_issue_loop(const TcShape& sh, const bool leader, const uint32_t tmem_base,
+                                               const uint32_t a_ring_addr, const uint32_t w_addr, uint64_t* full_a,
+                                               uint64_t* empty_a, uint64_t* full_w, uint64_t* empty_w,
+                                               uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, const int t_first,
+                                               const int t_end, const int t_step, unsigned& tr_n, const int tr_role,
+                                               const int lane) {
+  const uint32_t nb2 = (uint32_t)sh.umma_n * TC_BK * 2;   // byte offset of the second N half (BN = 384)
+  const bool two_n = sh.n_umma == 2;
+  const bool resident = sh.w_resident != 0;
+  uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
+  int it = 0;
+  for (int t = t_first; t < t_end; t += t_step, ++it) {
+    const int as = sh.acc_stages == 2 ? (it & 1) : 0;
+    const uint32_t use = sh.acc_stages == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;
+    mbar_wait(smem_u32(&tmem_empty_bar[as]), (use & 1u) ^ 1u);
+    tc_fence_after();
+    DHG_TR(0x20, it);
+    const uint32_t acc = tmem_base + (uint32_t)as * 256u;
+    for (int kbi = 0; kbi < sh.kb_per_tap; ++kbi) {
+      uint32_t alo[G], slot[G];
+#pragma unroll
+      for (int sub = 0; sub < G; ++sub) {
+        mbar_wait(smem_u32(&full_a[sa]), pa);
+        slot[sub] = sa;
+        alo[sub] = umma_desc_lo(a_ring_addr + sa * sh.a_stage_bytes);
+        if (++sa == (uint32_t)sh.stages_a) { sa = 0; pa ^= 1u; }
+      }
+      tc_fence_after();
+      DHG_TR(0x21, it);
+      const uint32_t first = kbi == 0 ? 0u : 1u;
+#pragma unroll
+      for (int tap = 0; tap < TAPS; ++tap) {
+        uint32_t b_addr;
+        if (resident) {
+          b_addr = w_addr + (uint32_t)(tap * sh.kb_per_tap + kbi) * sh.w_tile_bytes;
+        } else {
+          mbar_wait(smem_u32(&full_w[sw]), pw);
+          tc_fence_after();
+          b_addr = w_addr + sw * sh.w_tile_bytes;
+        }
+        const uint32_t blo = umma_desc_lo(b_addr);
+        if (leader) {
+          // shifted tap: logical row r of the A operand is physical row r + tap of the 130-row tile (the 128B
+          // swizzle is a function of the absolute smem address, so a +128 B start address just works)
+          if (!two_n) {
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k)
+#pragma unroll
+              for (int sub = 0; sub < G; ++sub)
+                umma_bf16(acc + (uint32_t)(sub * sh.BN), umma_desc_make(alo[sub] + tap * 8 + 2 * k, kDescHiSw128),
+                          umma_desc_make(blo + 2 * k, kDescHiSw128), sh.idesc, (tap | k) ? 1u : first);
+          } else {
+            const uint32_t blo2 = umma_desc_lo(b_addr + nb2);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              umma_bf16(acc, umma_desc_make(alo[0] + tap * 8 + 2 * k, kDescHiSw128), umma_desc_make(blo + 2 * k, kDescHiSw128), sh.idesc,
+                        (tap | k) ? 1u : first);
+              umma_bf16(acc + (uint32_t)sh.umma_n, umma_desc_make(alo[0] + tap * 8 + 2 * k, kDescHiSw128),
+                        umma_desc_make(blo2 + 2 * k, kDescHiSw128), sh.idesc, (tap | k) ? 1u : first);
+            }
+          }
+          if (!resident) umma_commit(smem_u32(&empty_w[sw]));   // frees the W slot when these MMAs retire
+        }
+        __syncwarp();
+        if (!resident && ++sw == (uint32_t)sh.stages_w) { sw = 0; pw ^= 1u; }
+      }
+      if (leader) {
+#pragma unroll
+        for (int sub = 0; sub < G; ++sub) umma_commit(smem_u32(&empty_a[slot[sub]]));   // frees the A slots
+      }
+      __syncwarp();
+    }
+    if (leader) umma_commit(smem_u32(&tmem_full_bar[as]));   // accumulators complete
+    __syncwarp();
+    DHG_TR(0x22, it);
+  }
+}
 
 // Template parameters fix the epilogue variant at compile time (-1 = read the flag at run time: the
 // generic instance).  kLN: LayerNorm; kAUX: AUX_* kind; kFILM: 0 none, 1 vectors shared by the batch
@@ -85,12 +184,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   float* betap_s = gamma_s + sh.film_n;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned tr_n = 0;
+  const int tr_role = warp < 2 ? warp : 2;
   // work assignment: tile `it` of this CTA -> (m tile, column group)
   const int cta_groups = sh.sticky ? sh.n_groups : 1;
   const int my_group = sh.sticky ? (int)(blockIdx.x % sh.n_groups) : 0;
   const int t_first = sh.sticky ? (int)(blockIdx.x / sh.n_groups) : (int)blockIdx.x;
   const int t_step = (int)gridDim.x / cta_groups;
-  const int t_end = sh.sticky ? sh.m_tiles : sh.m_tiles * sh.n_groups;
+  const int t_end = sh.sticky ? sh.m_super : sh.m_super * sh.n_groups;   // work items = (super-tile, column group)
   uint8_t* a_ring = smem;
   uint8_t* w_base = smem + sh.off_w;
   const bool film = e.gamma != nullptr;
@@ -132,151 +233,93 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    {
-      const bool leader = elect_one();
-      const int a_row_off = sh.tap_shift ? -1 : -(sh.taps / 2);
-      const int a_loads_per_kb = sh.tap_shift ? 1 : sh.taps;   // taps without the shift trick: one A tile per tap
-      if (sh.w_resident) {
-        const int n0 = my_group * sh.BN;
-        const uint32_t wb = smem_u32(w_all_bar);
-        if (leader) mbar_expect_tx(wb, (uint32_t)(sh.taps * sh.kb_per_tap) * sh.w_tile_bytes);
-        for (int tap = 0; tap < sh.taps; ++tap)
-          for (int kbi = 0; kbi < sh.kb_per_tap; ++kbi) {
-            const uint32_t dst = smem_u32(w_base + (size_t)(tap * sh.kb_per_tap + kbi) * sh.w_tile_bytes);
-            if (leader)
-              for (int j = 0; j < sh.n_umma; ++j)
-                tma_load_2d(dst + (uint32_t)j * sh.umma_n * TC_BK * 2, &map_w, wb, kbi * TC_BK, tap * sh.N + n0 + j * sh.umma_n);
-          }
-      }
-      uint32_t ga = 0, gw = 0;
-      for (int t = t_first; t < t_end; t += t_step) {
-        const int mt = sh.sticky ? t : t / sh.n_groups;
-        const int ng = sh.sticky ? my_group : t - mt * sh.n_groups;
-        const int m0 = mt * TC_BM, n0 = ng * sh.BN;
+    // ===== TMA producer: the whole warp runs the (uniform) loop, one elected lane issues the copies =====
+    const bool leader = elect_one();
+    const int a_row_off = sh.taps == 3 ? -1 : 0;   // 3 taps: one 130-row tile starting one row early
+    if (sh.w_resident) {
+      const int n0 = my_group * sh.BN;
+      const uint32_t wb = smem_u32(w_all_bar);
+      if (leader) mbar_expect_tx(wb, (uint32_t)(sh.taps * sh.kb_per_tap) * sh.w_tile_bytes);
+      for (int tap = 0; tap < sh.taps; ++tap)
         for (int kbi = 0; kbi < sh.kb_per_tap; ++kbi) {
-          const int kk = kbi * TC_BK;
-          for (int al = 0; al < a_loads_per_kb; ++al) {
-            const uint32_t sa = ga % (uint32_t)sh.stages_a;
-            mbar_wait(smem_u32(&empty_a[sa]), ((ga / (uint32_t)sh.stages_a) & 1u) ^ 1u);
-            const uint32_t fb = smem_u32(&full_a[sa]);
+          const uint32_t dst = smem_u32(w_base + (size_t)(tap * sh.kb_per_tap + kbi) * sh.w_tile_bytes);
+          if (leader)
+            for (int j = 0; j < sh.n_umma; ++j)
+              tma_load_2d(dst + (uint32_t)j * sh.umma_n * TC_BK * 2, &map_w, wb, kbi * TC_BK, tap * sh.N + n0 + j * sh.umma_n);
+        }
+    }
+    // ring positions are kept incrementally (no integer division in these latency-critical loops)
+    uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
+    for (int t = t_first; t < t_end; t += t_step) {
+      const int mts = sh.sticky ? t : t / sh.n_groups;
+      const int ng = sh.sticky ? my_group : t - mts * sh.n_groups;
+      const int n0 = ng * sh.BN;
+      for (int kbi = 0; kbi < sh.kb_per_tap; ++kbi) {
+        const int kk = kbi * TC_BK;
+        for (int sub = 0; sub < sh.G; ++sub) {   // the G row tiles of this super-tile share every W tile
+          mbar_wait(smem_u32(&empty_a[sa]), pa ^ 1u);
+          DHG_TR(0x10, sa);
+          const uint32_t fb = smem_u32(&full_a[sa]);
+          if (leader) {
+            mbar_expect_tx(fb, sh.a_tx_bytes);
+            tma_load_2d(smem_u32(a_ring + (size_t)sa * sh.a_stage_bytes), &map_a, fb, kk, (mts * sh.G + sub) * TC_BM + a_row_off);
+          }
+          if (++sa == (uint32_t)sh.stages_a) { sa = 0; pa ^= 1u; }
+        }
+        if (!sh.w_resident) {
+          for (int tap = 0; tap < sh.taps; ++tap) {
+            mbar_wait(smem_u32(&empty_w[sw]), pw ^ 1u);
+            const uint32_t fw = smem_u32(&full_w[sw]);
+            const uint32_t dst = smem_u32(w_base + (size_t)sw * sh.w_tile_bytes);
             if (leader) {
-              mbar_expect_tx(fb, sh.a_tx_bytes);
-              tma_load_2d(smem_u32(a_ring + (size_t)sa * sh.a_stage_bytes), &map_a, fb, kk, m0 + a_row_off + al);
+              mbar_expect_tx(fw, sh.w_tile_bytes);
+              for (int j = 0; j < sh.n_umma; ++j)
+                tma_load_2d(dst + (uint32_t)j * sh.umma_n * TC_BK * 2, &map_w, fw, kk, tap * sh.N + n0 + j * sh.umma_n);
             }
-            ++ga;
-            if (!sh.w_resident) {
-              const int tap_lo = sh.tap_shift ? 0 : al, tap_hi = sh.tap_shift ? sh.taps : al + 1;
-              for (int tap = tap_lo; tap < tap_hi; ++tap) {
-                const uint32_t sw = gw % (uint32_t)sh.stages_w;
-                mbar_wait(smem_u32(&empty_w[sw]), ((gw / (uint32_t)sh.stages_w) & 1u) ^ 1u);
-                const uint32_t fw = smem_u32(&full_w[sw]);
-                const uint32_t dst = smem_u32(w_base + (size_t)sw * sh.w_tile_bytes);
-                if (leader) {
-                  mbar_expect_tx(fw, sh.w_tile_bytes);
-                  for (int j = 0; j < sh.n_umma; ++j)
-                    tma_load_2d(dst + (uint32_t)j * sh.umma_n * TC_BK * 2, &map_w, fw, kk, tap * sh.N + n0 + j * sh.umma_n);
-                }
-                ++gw;
-              }
-            }
+            if (++sw == (uint32_t)sh.stages_w) { sw = 0; pw ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp runs the (uniform) loop, one elected lane issues tcgen05 =====
-    {
-      const bool leader = elect_one();
-      const int a_loads_per_kb = sh.tap_shift ? 1 : sh.taps;
-      const uint32_t nb2 = (uint32_t)sh.umma_n * TC_BK * 2;   // byte offset of the second N half (BN = 384)
-      if (sh.w_resident) {
-        mbar_wait(smem_u32(w_all_bar), 0);
-        tc_fence_after();
-      }
-      uint32_t ga = 0, gw = 0;
-      int it = 0;
-      for (int t = t_first; t < t_end; t += t_step, ++it) {
-        const int as = sh.acc_stages == 2 ? (it & 1) : 0;
-        const uint32_t use = sh.acc_stages == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;
-        mbar_wait(smem_u32(&tmem_empty_bar[as]), (use & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t acc = tmem_base + (uint32_t)as * 256u;
-        uint32_t accum = 0;
-        for (int kbi = 0; kbi < sh.kb_per_tap; ++kbi) {
-          for (int al = 0; al < a_loads_per_kb; ++al) {
-            const uint32_t sa = ga % (uint32_t)sh.stages_a;
-            mbar_wait(smem_u32(&full_a[sa]), (ga / (uint32_t)sh.stages_a) & 1u);
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(a_ring + (size_t)sa * sh.a_stage_bytes);
-            const int tap_lo = sh.tap_shift ? 0 : al, tap_hi = sh.tap_shift ? sh.taps : al + 1;
-            for (int tap = tap_lo; tap < tap_hi; ++tap) {
-              uint32_t b_addr;
-              uint32_t sw = 0;
-              if (sh.w_resident) {
-                b_addr = smem_u32(w_base + (size_t)(tap * sh.kb_per_tap + kbi) * sh.w_tile_bytes);
-              } else {
-                sw = gw % (uint32_t)sh.stages_w;
-                mbar_wait(smem_u32(&full_w[sw]), (gw / (uint32_t)sh.stages_w) & 1u);
-                tc_fence_after();
-                b_addr = smem_u32(w_base + (size_t)sw * sh.w_tile_bytes);
-              }
-              // shifted tap: logical row r of this operand is physical row r + tap of the 130-row tile
-              // (the 128B swizzle is a function of the absolute smem address, so a +128 B start just works)
-              const uint32_t alo = umma_desc_lo(a_addr + (sh.tap_shift ? (uint32_t)tap * 128u : 0u));
-              const uint32_t blo = umma_desc_lo(b_addr);
-              if (leader) {
-                if (sh.n_umma == 1) {
-#pragma unroll
-                  for (int k = 0; k < TC_BK / 16; ++k) {
-                    umma_bf16(acc, umma_desc_make(alo + 2 * k, kDescHiSw128), umma_desc_make(blo + 2 * k, kDescHiSw128), sh.idesc, accum);
-                    accum = 1;
-                  }
-                } else {
-                  const uint32_t blo2 = umma_desc_lo(b_addr + nb2);
-#pragma unroll
-                  for (int k = 0; k < TC_BK / 16; ++k) {
-                    umma_bf16(acc, umma_desc_make(alo + 2 * k, kDescHiSw128), umma_desc_make(blo + 2 * k, kDescHiSw128), sh.idesc, accum);
-                    umma_bf16(acc + (uint32_t)sh.umma_n, umma_desc_make(alo + 2 * k, kDescHiSw128), umma_desc_make(blo2 + 2 * k, kDescHiSw128), sh.idesc, accum);
-                    accum = 1;
-                  }
-                }
-                if (!sh.w_resident) umma_commit(smem_u32(&empty_w[sw]));   // frees the W slot when these MMAs retire
-              }
-              accum = 1;
-              __syncwarp();
-              if (!sh.w_resident) ++gw;
-            }
-            if (leader) umma_commit(smem_u32(&empty_a[sa]));               // frees the A slot
-            __syncwarp();
-            ++ga;
-          }
-        }
-        if (leader) umma_commit(smem_u32(&tmem_full_bar[as]));             // accumulator complete
-        __syncwarp();
-      }
+    // Accumulating MMAs into one TMEM tile do not issue back to back (measured ~130 cycles apart at N = 128
+    // against a 64-cycle floor), so a super-tile keeps G independent accumulators (G row tiles x the same W
+    // tile) and interleaves them.
+    const bool leader = elect_one();
+    if (sh.w_resident) {
+      mbar_wait(smem_u32(w_all_bar), 0);
+      tc_fence_after();
     }
+    const uint32_t a_ring_addr = smem_u32(a_ring), w_addr = smem_u32(w_base);
+#define DHG_MMA_LOOP(TAPS, GG)                                                                                          \
+  mma_issue_loop<TAPS, GG>(sh, leader, tmem_base, a_ring_addr, w_addr, full_a, empty_a, full_w, empty_w, tmem_full_bar, \
+                           tmem_empty_bar, t_first, t_end, t_step, tr_n, tr_role, lane)
+    if (sh.taps == 3) {
+      if (sh.G == 4) DHG_MMA_LOOP(3, 4); else if (sh.G == 2) DHG_MMA_LOOP(3, 2); else DHG_MMA_LOOP(3, 1);
+    } else {
+      if (sh.G == 4) DHG_MMA_LOOP(1, 4); else if (sh.G == 2) DHG_MMA_LOOP(1, 2); else DHG_MMA_LOOP(1, 1);
+    }
+#undef DHG_MMA_LOOP
   } else {
-    // ===== epilogue: warps 2..9; warp (q, half): TMEM lanes [32q, 32q+32), one half of the column chunks =====
+    // ===== epilogue warps; warp (q, part): TMEM lanes [32q, 32q+32), one contiguous part of the column chunks =====
     const bool ln = kLN >= 0 ? (kLN != 0) : (e.ln != 0);
     const int aux_kind = kAUX >= 0 ? kAUX : sh.aux_kind;
     const int film_mode = kFILM >= 0 ? kFILM : (film ? (film_s ? 1 : 2) : 0);
     const int out_mode = kOUT >= 0 ? kOUT : ((e.out_raw ? 1 : 0) | (e.out_act ? 2 : 0));
     const bool has_bias = sh.vec_bias_n > 0;
-    const int ew = warp - 2, q = warp & 3, half = ew >> 2;
+    const int ew = warp - 2, q = warp & 3, part = ew >> 2;
     const int nch = sh.BN >> 5;
-    const int c_lo = half ? ((nch + 1) >> 1) : 0;
-    const int c_hi = half ? nch : ((nch + 1) >> 1);
+    const int c_lo = (part * nch) / EPI_PARTS;          // my contiguous range of 32-column chunks (may be empty)
+    const int c_hi = ((part + 1) * nch) / EPI_PARTS;
     const int my_nch = c_hi - c_lo;
-    const int other_nch = nch - my_nch;
     const uint32_t aux_ring = smem_u32(smem + sh.off_aux + (size_t)ew * AUX_RING_BYTES);
     const uint32_t out_st = smem_u32(smem + sh.off_out + (size_t)ew * OUT_STAGE_BYTES);
     const uint32_t bias_sa = smem_u32(bias_s), gamma_sa = smem_u32(gamma_s), betap_sa = smem_u32(betap_s);
-    float4* ln_s = reinterpret_cast<float4*>(smem + sh.off_ln);   // [2 parity][128 rows] {mean0, M2_0, mean1, M2_1}
-    const bool aux_f32 = false;   // (fp32 aux rows: unused since the per-position bias table became bf16)
+    float2* ln_s = reinterpret_cast<float2*>(smem + sh.off_ln);   // [2 parity][128 rows][EPI_PARTS] {mean, M2} of each column part
     const int aux_ncols = aux_kind == AUX_ROWBIAS ? e.rowbias16_cols : 0x7fffffff;   // aux only for columns below this
-    const int aux_depth = aux_f32 ? 2 : 4;
-    const uint32_t aux_slot_bytes = aux_f32 ? 4096u : 2048u;
+    constexpr int aux_depth = AUX_DEPTH;
+    constexpr uint32_t aux_slot_bytes = AUX_SLOT_BYTES;
     const char* aux_base = nullptr;
     size_t aux_pitch_bytes = 0;
     if (aux_kind == AUX_RES_PRE) { aux_base = (const char*)e.res_pre; aux_pitch_bytes = (size_t)e.res_pre_pitch * 2; }
@@ -294,14 +337,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     // flat index it * my_nch + ci, ring slot = flat % depth, so the loads for the next tile are already in
     // flight while this tile is being finished.
     uint32_t aux_issued = 0, aux_consumed = 0;
+    int iss_t = t_first, iss_sub = 0, iss_ci = 0;   // (super-tile, row tile, chunk) of the next flat chunk to issue
     auto issue_aux_flat = [&]() {
       const uint32_t f = aux_issued++;
-      const int fit = (int)(f / (uint32_t)my_nch), ci = (int)(f - (uint32_t)fit * (uint32_t)my_nch);
-      const int ft = t_first + fit * t_step;
+      const int ft = iss_t, fsub = iss_sub, ci = iss_ci;
+      if (++iss_ci == my_nch) {
+        iss_ci = 0;
+        if (++iss_sub == sh.G) { iss_sub = 0; iss_t += t_step; }
+      }
       if (ft < t_end) {
-        const int fmt = sh.sticky ? ft : ft / sh.n_groups;
-        const int fng = sh.sticky ? my_group : ft - fmt * sh.n_groups;
-        const int fm = fmt * TC_BM + r_tile;
+        const int fmts = sh.sticky ? ft : ft / sh.n_groups;
+        const int fng = sh.sticky ? my_group : ft - fmts * sh.n_groups;
+        const int fm = (fmts * sh.G + fsub) * TC_BM + r_tile;
         // source row of my residual / bias row in that tile, -1 = none (zero-filled)
         const bool f_in = fm < sh.rows;
         int aux_src = -1;
@@ -319,17 +366,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         }
         const int col0 = fng * sh.BN + (c_lo + ci) * 32;
         const uint32_t slot = aux_ring + (f % (uint32_t)aux_depth) * aux_slot_bytes;
-        if (col0 >= aux_ncols) {
-          // no per-position term for these columns
-        } else if (aux_f32) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = i * 4 + (lane >> 3), piece = lane & 7;
-            const int src = __shfl_sync(0xffffffffu, aux_src, rr);
-            const char* gp = aux_base + (size_t)(src < 0 ? 0 : src) * aux_pitch_bytes + (size_t)col0 * 4 + piece * 16;
-            cp_async16(slot + rr * 128 + ((piece ^ (rr & 7)) << 4), gp, src < 0 ? 0u : 16u);
-          }
-        } else {
+        if (col0 < aux_ncols) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int rr = i * 8 + (lane >> 2), piece = lane & 3;
@@ -343,19 +380,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     };
     // wait for the oldest aux chunk, add my row of it to v, refill its slot with the next flat chunk
     auto consume_aux = [&](float* v, int col0) {
-      if (aux_f32) cp_async_wait<1>(); else cp_async_wait<3>();
+      cp_async_wait<AUX_DEPTH - 1>();
       __syncwarp();
       const uint32_t slot = aux_ring + (aux_consumed % (uint32_t)aux_depth) * aux_slot_bytes;
       ++aux_consumed;
-      if (col0 >= aux_ncols) {
-        // nothing was loaded for this chunk
-      } else if (aux_f32) {
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          const float4 f = lds128f_v(slot + lane * 128 + ((p ^ (lane & 7)) << 4));
-          v[p * 4] += f.x; v[p * 4 + 1] += f.y; v[p * 4 + 2] += f.z; v[p * 4 + 3] += f.w;
-        }
-      } else {
+      if (col0 < aux_ncols) {
         uint4 u[4];
 #pragma unroll
         for (int p = 0; p < 4; ++p) u[p] = lds128_v(slot + st_row + ((p ^ st_sw) << 4));
@@ -365,17 +394,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       __syncwarp();
       issue_aux_flat();
     };
-    if (aux_kind != AUX_NONE)
+    const bool aux_active = aux_kind != AUX_NONE && my_nch > 0;
+    if (aux_active)
       for (int i = 0; i < aux_depth; ++i) issue_aux_flat();
 
-    int it = 0;
+    int it = 0, tile_no = 0;
     for (int t = t_first; t < t_end; t += t_step, ++it) {
-      const int mt = sh.sticky ? t : t / sh.n_groups;
-      const int ng = sh.sticky ? my_group : t - mt * sh.n_groups;
-      const int m0 = mt * TC_BM, n0 = ng * sh.BN;
-      const int as = sh.acc_stages == 2 ? (it & 1) : 0;
-      const uint32_t use = sh.acc_stages == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;
-      const uint32_t trow = tmem_base + (uint32_t)as * 256u + lane_sel;
+     const int mts = sh.sticky ? t : t / sh.n_groups;
+     const int ng = sh.sticky ? my_group : t - mts * sh.n_groups;
+     const int n0 = ng * sh.BN;
+     const int as = sh.acc_stages == 2 ? (it & 1) : 0;
+     const uint32_t use = sh.acc_stages == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;
+     if (ew == 0) DHG_TR(0x30, it);
+     mbar_wait(smem_u32(&tmem_full_bar[as]), use & 1u);
+     tc_fence_after();
+     if (ew == 0) DHG_TR(0x31, it);
+     for (int sub = 0; sub < sh.G; ++sub, ++tile_no) {
+      const int m0 = (mts * sh.G + sub) * TC_BM;
+      const bool last_sub = sub == sh.G - 1;
+      const uint32_t trow = tmem_base + (uint32_t)as * 256u + (uint32_t)(sub * sh.BN) + lane_sel;
 
       // ---- per-row bookkeeping ----
       const int m = m0 + r_tile;
@@ -416,9 +453,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         __syncwarp();
       };
 
-      mbar_wait(smem_u32(&tmem_full_bar[as]), use & 1u);
-      tc_fence_after();
-
       float v[32];
       float mean = 0.f, rstd = 1.f;
       if (ln) {
@@ -444,17 +478,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
           }
           tmem_st32(trow + c * 32, v);
         }
-        const float n_h = (float)(my_nch * 32), n_o = (float)(other_nch * 32), n_t = (float)sh.BN;
-        const float mean_h = shift + s1 / n_h;
-        const float m2_h = fmaxf(s2 - s1 * s1 / n_h, 0.f);
-        float* st = reinterpret_cast<float*>(ln_s + (size_t)(it & 1) * TC_BM + r_tile);
-        st[half * 2] = mean_h;
-        st[half * 2 + 1] = m2_h;
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-        const float mean_o = st[(half ^ 1) * 2], m2_o = st[(half ^ 1) * 2 + 1];
-        const float delta = mean_o - mean_h;
-        mean = (n_h * mean_h + n_o * mean_o) / n_t;
-        const float m2 = m2_h + m2_o + delta * delta * (n_h * n_o / n_t);
+        // merge the column parts (Chan's parallel mean / M2 update) through shared memory
+        float2* st = ln_s + ((size_t)(tile_no & 1) * TC_BM + r_tile) * EPI_PARTS;
+        if (my_nch > 0) {
+          const float n_h = (float)(my_nch * 32);
+          st[part] = make_float2(shift + s1 / n_h, fmaxf(s2 - s1 * s1 / n_h, 0.f));
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(32 * EPI_PARTS) : "memory");
+        float n_acc = 0.f, m2 = 0.f;
+        mean = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < EPI_PARTS; ++pp) {
+          const int cnt = (((pp + 1) * nch) / EPI_PARTS - (pp * nch) / EPI_PARTS) * 32;
+          if (cnt > 0) {
+            const float2 o = st[pp];
+            const float n_p = (float)cnt, n_new = n_acc + n_p;
+            const float delta = o.x - mean;
+            mean += delta * (n_p / n_new);
+            m2 += o.y + delta * delta * (n_acc * n_p / n_new);
+            n_acc = n_new;
+          }
+        }
+        const float n_t = (float)sh.BN;
         rstd = rsqrtf(m2 / n_t + 1e-6f);
       }
       const float nmr = -mean * rstd;
@@ -464,11 +509,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         gam_g = e.gamma + (size_t)b * e.film_bstride;
         bet_g = e.beta + (size_t)b * e.film_bstride;
       }
+      if (my_nch == 0 && last_sub) {   // no column chunk for this warp in this tile shape: just release the accumulators
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+      }
       for (int ci = 0; ci < my_nch; ++ci) {
         const int c = c_lo + ci;
         const int n = n0 + c * 32;
         tmem_ld32(trow + c * 32, v);
-        if (ci == my_nch - 1) {   // my last TMEM read of this tile: hand the accumulator back to the MMA warp
+        if (ci == my_nch - 1 && last_sub) {   // my last TMEM read of this super-tile: hand the accumulators back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
@@ -511,8 +561,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         if (out_mode & 1) store_chunk(e.out_raw, e.out_raw_pitch, n, v, false);
         if (out_mode & 2) store_chunk(e.out_act, e.out_act_pitch, n, v, true);
       }
+     }
+     if (ew == 0) DHG_TR(0x32, it);
     }
-    if (aux_kind != AUX_NONE) cp_async_wait<0>();
+    if (aux_active) cp_async_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -524,12 +576,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 
 }  // namespace
 
-// experiment switches (dhg_set_option: "tap_shift", "tap_base_offset", "w_resident")
-int g_opt_tap_shift = 1, g_opt_tap_base_offset = 0, g_opt_w_resident = 1, g_opt_specialize = 1;
+// experiment switches (dhg_set_option: "w_resident", "specialize", "interleave")
+int g_opt_w_resident = 1, g_opt_specialize = 1, g_opt_interleave = 1, g_opt_mma_repeat = 1;
 void tc_gemm_set_option(int which, int value) {
-  if (which == 0) g_opt_tap_shift = value;
-  else if (which == 1) g_opt_tap_base_offset = value;
-  else if (which == 2) g_opt_w_resident = value;
+  if (which == 2) g_opt_w_resident = value;
+  else if (which == 4) g_opt_interleave = value;
+  else if (which == 5) g_opt_mma_repeat = value;
   else if (which == 3) g_opt_specialize = value;
 }
 
@@ -617,21 +669,26 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   sh.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(sh.umma_n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
   sh.acc_stages = BN <= 256 ? 2 : 1;
   sh.aux_kind = aux_kind;
+  sh.trace = nullptr; sh.trace_cap = 0;
   sh.vec_bias_n = e.bias ? N : 0;
   sh.film_n = e.film_planned ? N : 0;
-  sh.tap_shift = (taps == 3 && g_opt_tap_shift) ? 1 : 0;
-  sh.tap_base_offset = g_opt_tap_base_offset;
-  const int a_rows = sh.tap_shift ? TC_BM + 2 : TC_BM;
+  // independent accumulators per super-tile: as many as fit in one 256-column TMEM group, at most 4
+  int G = 1;
+  if (g_opt_interleave && BN <= 128) G = BN <= 64 ? 4 : 2;
+  while (G > 1 && (m_tiles + G - 1) / G * sh.n_groups < num_sms) G >>= 1;   // keep every SM busy on small problems
+  sh.G = G;
+  sh.m_super = (m_tiles + G - 1) / G;
+  const int a_rows = taps == 3 ? TC_BM + 2 : TC_BM;
   sh.a_tx_bytes = (uint32_t)a_rows * TC_BK * 2;
   sh.a_stage_bytes = (sh.a_tx_bytes + 1023u) & ~1023u;
   sh.w_tile_bytes = (uint32_t)BN * TC_BK * 2;
   // smem carve-up: A ring | W ring or resident W | aux rings | out staging | vectors | LN exchange | barriers
   const size_t fixed = (aux_kind != AUX_NONE ? (size_t)EPI_WARPS * AUX_RING_BYTES : 0) + (size_t)EPI_WARPS * OUT_STAGE_BYTES +
-                       (size_t)(sh.vec_bias_n + 2 * sh.film_n) * 4 + 16 + (e.ln ? 2 * TC_BM * 16 : 0) + 64 * 8;
+                       (size_t)(sh.vec_bias_n + 2 * sh.film_n) * 4 + 16 + (e.ln ? 2 * TC_BM * EPI_PARTS * 8 : 0) + 64 * 8;
   const size_t budget = 227 * 1024 - 1024 - fixed;
   const size_t w_all = (size_t)taps * sh.kb_per_tap * sh.w_tile_bytes;
-  const int a_per_tile = sh.kb_per_tap * (sh.tap_shift ? 1 : taps);
-  sh.w_resident = (g_opt_w_resident && w_all + 3 * (size_t)sh.a_stage_bytes <= budget && m_tiles * sh.n_groups > num_sms) ? 1 : 0;
+  const int min_a = G > 1 ? 2 * G : 3;
+  sh.w_resident = (g_opt_w_resident && w_all + (size_t)min_a * sh.a_stage_bytes <= budget && sh.m_super * sh.n_groups > num_sms) ? 1 : 0;
   sh.sticky = (sh.w_resident && sh.n_groups > 1) ? 1 : 0;
   size_t w_bytes;
   if (sh.w_resident) {
@@ -640,9 +697,9 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
     sh.stages_w = 1;
     w_bytes = w_all;
   } else {
-    const int w_per_a = sh.tap_shift ? taps : 1;
-    int sa = (int)(budget / (sh.a_stage_bytes + (size_t)w_per_a * sh.w_tile_bytes));
-    if (sa < 2) sa = 2;
+    // per k-block: G A tiles and `taps` W tiles
+    int sa = (int)(budget / ((size_t)G * sh.a_stage_bytes + (size_t)taps * sh.w_tile_bytes)) * G;
+    if (sa < 2 * G) sa = G > 1 ? 2 * G : 2;
     if (sa > 8) sa = 8;
     if ((size_t)sa * sh.a_stage_bytes + 2 * (size_t)sh.w_tile_bytes > budget) { snprintf(err, errlen, "not enough shared memory for BN=%d", BN); delete p; return nullptr; }
     int sw = (int)((budget - (size_t)sa * sh.a_stage_bytes) / sh.w_tile_bytes);
@@ -650,17 +707,17 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
     sh.stages_w = sw > 8 ? 8 : sw;
     w_bytes = (size_t)sh.stages_w * sh.w_tile_bytes;
   }
-  (void)a_per_tile;
+  if (sh.stages_a < G) { snprintf(err, errlen, "A ring too small for %d interleaved tiles", G); delete p; return nullptr; }
   uint32_t off = (uint32_t)sh.stages_a * sh.a_stage_bytes;
   sh.off_w = off; off += (uint32_t)w_bytes;
   sh.off_aux = off; off += aux_kind != AUX_NONE ? EPI_WARPS * AUX_RING_BYTES : 0;
   sh.off_out = off; off += EPI_WARPS * OUT_STAGE_BYTES;
   sh.off_vec = off; off += (uint32_t)(sh.vec_bias_n + 2 * sh.film_n) * 4;
   off = (off + 15u) & ~15u;
-  sh.off_ln = off; off += e.ln ? 2 * TC_BM * 16 : 0;
+  sh.off_ln = off; off += e.ln ? 2 * TC_BM * EPI_PARTS * 8 : 0;
   sh.off_bar = off; off += 64 * 8;
   p->smem = off + 1024;
-  int grid = m_tiles * sh.n_groups < num_sms ? m_tiles * sh.n_groups : num_sms;
+  int grid = sh.m_super * sh.n_groups < num_sms ? sh.m_super * sh.n_groups : num_sms;
   if (sh.sticky) grid = (num_sms / sh.n_groups) * sh.n_groups;
   p->grid = dim3(grid);
   if (!make_map(&p->map_a, A, (uint64_t)rows, (uint64_t)K, (uint64_t)lda, (uint32_t)a_rows, err, errlen) ||
@@ -679,6 +736,11 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
 }
 
 void tc_gemm_plan_destroy(TcGemmPlan* p) { delete p; }
+void tc_gemm_set_trace(TcGemmPlan* p, unsigned long long* buf, int cap) { p->sh.trace = buf; p->sh.trace_cap = cap; }
+void tc_gemm_describe(const TcGemmPlan* p, char* out, int n) {
+  snprintf(out, n, "BN=%d groups=%d m_tiles=%d G=%d stages_a=%d stages_w=%d resident=%d sticky=%d acc_stages=%d grid=%d smem=%zu", p->sh.BN, p->sh.n_groups,
+           p->sh.m_tiles, p->sh.G, p->sh.stages_a, p->sh.stages_w, p->sh.w_resident, p->sh.sticky, p->sh.acc_stages, (int)p->grid.x, p->smem);
+}
 
 int tc_gemm_launch(const TcGemmPlan* p, const Epilogue& e, cudaStream_t st) {
   // the specialised instance assumes FiLM vectors shared by the batch (or no FiLM at all)

@@ -61,8 +61,10 @@ struct TcGemmPlan;  // opaque: tensor maps + launch geometry, built once at plan
 TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W, int K, int N, int taps,
                                 const Epilogue& e, char* err, int errlen);
 void tc_gemm_plan_destroy(TcGemmPlan*);
+void tc_gemm_set_trace(TcGemmPlan*, unsigned long long* buf, int cap);   // debug timeline of CTA 0
+void tc_gemm_describe(const TcGemmPlan*, char* out, int n);
 int tc_gemm_launch(const TcGemmPlan*, const Epilogue& e, cudaStream_t st);
-void tc_gemm_set_option(int which, int value);   // 0 tap_shift, 1 tap_base_offset, 2 w_resident, 3 specialize (experiments)
+void tc_gemm_set_option(int which, int value);   // 2 w_resident, 3 specialize, 4 interleave (experiments)
 
 // tcgen05 attention for head depth 64 and Tk <= 256 (attention_tc.cu).  q_rows / k_rows: total rows
 // of the q / k,v row matrices (TMA bounds).
