@@ -90,6 +90,8 @@ struct Lin {
 struct StepCtx {
   const float* cond;  // FiLM vectors: cond[b * bstride + off]
   int bstride;
+  bool skip_input_dense;  // in_raw / in_act were already written by the previous step's head kernel
+  bool fuse_next_input;   // this step's head kernel also writes in_raw / in_act of the next step
   HeadParams head;
 };
 typedef std::function<int(cudaStream_t, const StepCtx&)> Op;
@@ -133,7 +135,7 @@ struct Plan {
   size_t scratch_elems = 0;
   int* err_flag = nullptr;
   std::vector<Op> once_ops, step_ops;
-  Act head_in;
+  Act head_in, in_raw, in_act;
   std::vector<TcGemmPlan*> tc_plans;
   std::vector<AttnTcPlan*> attn_plans;
   int attn_impl = 1;
@@ -638,7 +640,9 @@ int build_plan(dhg_ctx* c, Plan* P) {
   {
     Plan* Pl = P;
     P->launches_step += 1;
+    P->in_raw = in_raw; P->in_act = in_act;
     P->step_ops.push_back([=](cudaStream_t st, const StepCtx& sc) -> int {
+      if (sc.skip_input_dense) return 0;
       const float* x = sc.head.x_io ? sc.head.x_io : Pl->x_state;
       if (Pl->prec == PREC_FP32)
         launch_input_dense<float>(x, c->in_W, c->in_b, (float*)in_raw.p, (float*)in_act.p, Pl->B, Pl->T, in_raw.C, st);
@@ -698,11 +702,13 @@ int build_plan(dhg_ctx* c, Plan* P) {
     P->step_ops.push_back([=](cudaStream_t st, const StepCtx& sc) -> int {
       HeadParams hp = sc.head;
       if (hp.x_io == nullptr && hp.eps_out == nullptr) return fail("head: nothing to do");
-      if (Pl->prec == PREC_FP32)
-        launch_heads_update<float>((const float*)d1.p, d1.C, c->out_W, c->out_b, c->pen_W, c->pen_b, hp, st);
-      else
-        launch_heads_update<bf16>((const bf16*)d1.p, d1.C, c->out_W, c->out_b, c->pen_W, c->pen_b, hp, st);
-      return 0;
+      if (sc.fuse_next_input) {
+        hp.next_raw = Pl->in_raw.p; hp.next_act = Pl->in_act.p; hp.in_W = c->in_W; hp.in_b = c->in_b;
+      }
+      const int rc = Pl->prec == PREC_FP32
+          ? launch_heads_update<float>((const float*)d1.p, d1.C, c->out_W, c->out_b, c->pen_W, c->pen_b, hp, st)
+          : launch_heads_update<bf16>((const bf16*)d1.p, d1.C, c->out_W, c->out_b, c->pen_W, c->pen_b, hp, st);
+      return rc ? fail("head kernel: unsupported channel count %d", d1.C) : 0;
     });
   }
   if (P->scratch_elems && !(P->prec == PREC_BF16 && P->gemm_impl == 1))
@@ -754,6 +760,8 @@ int run_chain(dhg_ctx* c, Plan* P, int mode, bool has_noise, cudaStream_t st) {
   if (run_ops(P->once_ops, st, sc)) return 1;
   for (int i = DHG_NUM_STEPS - 1; i >= 0; --i) {
     sc.cond = c->cond60 + (size_t)i * c->film_total;
+    sc.skip_input_dense = i != DHG_NUM_STEPS - 1;   // written by the previous step's head kernel
+    sc.fuse_next_input = i != 0;
     head_for_step(c, P, i, mode, has_noise, false, &sc.head);
     if (run_ops(P->step_ops, st, sc)) return 1;
   }
@@ -1028,7 +1036,7 @@ int32_t dhg_sample(dhg_ctx* c, int32_t batch, const float* x0, const float* nois
                               cudaMemcpyDeviceToDevice, st));
     if (launch_chain(c, P, mode, true, st)) return 1;
     CUDA_OK(cudaMemcpyAsync(out + (size_t)c0 * P->T * 3, P->out, (size_t)nb * P->T * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    launches += P->launches_once + (int64_t)DHG_NUM_STEPS * P->launches_step;
+    launches += P->launches_once + (int64_t)DHG_NUM_STEPS * P->launches_step - (DHG_NUM_STEPS - 1);   // input_dense is fused after step 1
   }
   c->last_launches = launches;
   return 0;
@@ -1099,6 +1107,7 @@ int64_t dhg_plan_bytes(const dhg_ctx* c) { return (c && c->plan) ? (int64_t)c->p
 
 int32_t dhg_set_option(dhg_ctx* c, const char* key, int32_t value) {
   if (key && !strcmp(key, "interleave")) { tc_gemm_set_option(4, value); return 0; }
+  if (key && !strcmp(key, "attn_dbg")) { attn_tc_set_debug(value); return 0; }
   if (key && !strcmp(key, "mma_repeat")) { tc_gemm_set_option(5, value); return 0; }
   if (key && !strcmp(key, "w_resident")) { tc_gemm_set_option(2, value); return 0; }
   if (key && !strcmp(key, "specialize")) { tc_gemm_set_option(3, value); return 0; }

@@ -517,7 +517,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       for (int ci = 0; ci < my_nch; ++ci) {
         const int c = c_lo + ci;
         const int n = n0 + c * 32;
+        if (ew == 0) DHG_TR(0x33, ci);
         tmem_ld32(trow + c * 32, v);
+        if (ew == 0) DHG_TR(0x34, ci);
         if (ci == my_nch - 1 && last_sub) {   // my last TMEM read of this super-tile: hand the accumulators back
           tc_fence_before();
           __syncwarp();
@@ -558,6 +560,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
+        if (ew == 0) DHG_TR(0x35, ci);
         if (out_mode & 1) store_chunk(e.out_raw, e.out_raw_pitch, n, v, false);
         if (out_mode & 2) store_chunk(e.out_act, e.out_act_pitch, n, v, true);
       }

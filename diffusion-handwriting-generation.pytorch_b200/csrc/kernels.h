@@ -25,6 +25,12 @@ struct HeadParams {
   const float* noise;      // [B,T,2] injected draw or null (= zero)
   int mode;                // 0 "new", 1 "standard"
   float c_eps, c_eps2, c_div, c_noise;
+  // fused input_dense of the NEXT denoiser step (model.py:139 applied to the updated x): padded-row
+  // [rows, C] raw and SiLU'd copies, activation dtype; null = not fused
+  void* next_raw;
+  void* next_act;
+  const float* in_W;       // [C, 2]
+  const float* in_b;       // [C]
 };
 
 template <typename TA>
@@ -43,7 +49,7 @@ template <typename T>
 void launch_input_dense(const float* x, const float* W, const float* bias, T* out_raw, T* out_act,
                         int B, int Tn, int C, cudaStream_t st);
 template <typename T>
-void launch_heads_update(const T* h, int C, const float* Wo, const float* bo, const float* Wp,
+int launch_heads_update(const T* h, int C, const float* Wo, const float* bo, const float* Wp,
                          const float* bp, const HeadParams& p, cudaStream_t st);
 void launch_posterior(const float* x, const float* eps, const float* z, float* out, size_t n, int mode,
                       float c_eps, float c_eps2, float c_div, float c_noise, int num_sms, cudaStream_t st);
@@ -73,5 +79,6 @@ bool attn_tc_supported(const AttnParams& p);
 AttnTcPlan* attn_tc_plan_create(const AttnParams& p, int q_rows, int k_rows, char* err, int errlen);
 void attn_tc_plan_destroy(AttnTcPlan*);
 int attn_tc_launch(const AttnTcPlan*, cudaStream_t st);
+void attn_tc_set_debug(int flags);   // timing experiments only
 
 }  // namespace dhg

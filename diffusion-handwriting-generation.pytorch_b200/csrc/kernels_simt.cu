@@ -369,25 +369,35 @@ template void launch_film_rows<bf16>(const bf16*, bf16*, int, int, int, const fl
 // AvgPool1d(2) over T in the padded row layout (model.py:93): level l -> l+1.
 // ---------------------------------------------------------------------------
 template <typename T>
-__global__ void pool_kernel(const T* __restrict__ in, T* __restrict__ out_raw, T* __restrict__ out_act,
-                            int B, int Tlo, int C) {
-  const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int c4 = C >> 2;
-  if (i4 >= (size_t)B * Tlo * c4) return;
-  const int c = (int)(i4 % c4) * 4;
-  const size_t bt = i4 / c4;
-  const int t = (int)(bt % Tlo), b = (int)(bt / Tlo);
-  const size_t rin = (size_t)b * (2 * Tlo + 1) + 1 + 2 * t;
-  const size_t rout = (size_t)b * (Tlo + 1) + 1 + t;
-  const float4 x0 = load4<T>(in + rin * C + c), x1 = load4<T>(in + (rin + 1) * C + c);
-  const float4 m = make_float4(0.5f * (x0.x + x1.x), 0.5f * (x0.y + x1.y), 0.5f * (x0.z + x1.z), 0.5f * (x0.w + x1.w));
-  if (out_raw) store4<T>(out_raw + rout * C + c, m);
-  if (out_act) store4<T>(out_act + rout * C + c, make_float4(silu_f(m.x), silu_f(m.y), silu_f(m.z), silu_f(m.w)));
+__global__ void __launch_bounds__(256) pool_kernel(const T* __restrict__ in, T* __restrict__ out_raw, T* __restrict__ out_act,
+                                                   int B, int Tlo, int C) {
+  const int c8 = C >> 3;
+  const size_t total = (size_t)B * Tlo * c8;
+  for (size_t i8 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i8 < total; i8 += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i8 % c8) * 8;
+    const size_t bt = i8 / c8;
+    const int t = (int)(bt % Tlo), b = (int)(bt / Tlo);
+    const size_t rin = (size_t)b * (2 * Tlo + 1) + 1 + 2 * t;
+    const size_t rout = (size_t)b * (Tlo + 1) + 1 + t;
+    float x0[8], x1[8], m[8];
+    load8<T>(in + rin * C + c, x0);
+    load8<T>(in + (rin + 1) * C + c, x1);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = 0.5f * (x0[k] + x1[k]);
+    if (out_raw) store8<T>(out_raw + rout * C + c, m);
+    if (out_act) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m[k] = silu_f(m[k]);
+      store8<T>(out_act + rout * C + c, m);
+    }
+  }
 }
 template <typename T>
 void launch_pool(const T* in, T* out_raw, T* out_act, int B, int Tlo, int C, cudaStream_t st) {
-  const size_t n4 = (size_t)B * Tlo * (C >> 2);
-  pool_kernel<T><<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(in, out_raw, out_act, B, Tlo, C);
+  const size_t n8 = (size_t)B * Tlo * (C >> 3);
+  size_t blocks = (n8 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pool_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(in, out_raw, out_act, B, Tlo, C);
 }
 template void launch_pool<float>(const float*, float*, float*, int, int, int, cudaStream_t);
 template void launch_pool<bf16>(const bf16*, bf16*, bf16*, int, int, int, cudaStream_t);
@@ -424,9 +434,11 @@ template void launch_input_dense<float>(const float*, const float*, const float*
 template void launch_input_dense<bf16>(const float*, const float*, const float*, bf16*, bf16*, int, int, int, cudaStream_t);
 
 // ---------------------------------------------------------------------------
-// Output heads + fused posterior update: one warp per stroke point.
+// Output heads + fused posterior update (+ fused input_dense of the next step).
+// 8 lanes per stroke point (each lane owns 16 of the C = 128 channels), 4 points per warp, grid-stride.
 //   eps = Linear(C,2)(h), pen = sigmoid(Linear(C,1)(h))          model.py:179-181
 //   x  <- posterior(x, eps, z)                                   utils/nn.py:84-87,110-112
+//   next step: in = Linear(2,C)(x) -> raw and SiLU'd rows        model.py:139 (+ cnn.py:25)
 // ---------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) heads_update_kernel(const T* __restrict__ h, int C,
@@ -434,33 +446,52 @@ __global__ void __launch_bounds__(256) heads_update_kernel(const T* __restrict__
                                                            const float* __restrict__ bo,
                                                            const float* __restrict__ Wp /*[1,C]*/,
                                                            const float* __restrict__ bp, HeadParams p) {
-  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= (size_t)p.B * p.T) return;
-  const int b = (int)(warp / p.T), t = (int)(warp - (size_t)b * p.T);
-  const T* row = h + ((size_t)b * (p.T + 1) + 1 + t) * C;
-  float e0 = 0.f, e1 = 0.f, pl = 0.f;
-  for (int c = lane * 4; c < C; c += 128) {
-    const float4 x = load4<T>(row + c);
-    const float4 w0 = *reinterpret_cast<const float4*>(Wo + c);
-    const float4 w1 = *reinterpret_cast<const float4*>(Wo + C + c);
-    const float4 wp = *reinterpret_cast<const float4*>(Wp + c);
-    e0 += x.x * w0.x + x.y * w0.y + x.z * w0.z + x.w * w0.w;
-    e1 += x.x * w1.x + x.y * w1.y + x.z * w1.z + x.w * w1.w;
-    pl += x.x * wp.x + x.y * wp.y + x.z * wp.z + x.w * wp.w;
+  const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+  const int c0 = sub * 16;   // my 16 channels (C == 128)
+  float w0[16], w1[16], wp[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { w0[i] = Wo[c0 + i]; w1[i] = Wo[C + c0 + i]; wp[i] = Wp[c0 + i]; }
+  const float b0 = bo[0], b1 = bo[1], bpv = bp[0];
+  float iw0[16], iw1[16], ib[16];   // input_dense rows of my channels (next step)
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    iw0[i] = p.next_raw ? p.in_W[(c0 + i) * 2] : 0.f;
+    iw1[i] = p.next_raw ? p.in_W[(c0 + i) * 2 + 1] : 0.f;
+    ib[i] = p.next_raw ? p.in_b[c0 + i] : 0.f;
   }
-  e0 = warp_sum(e0) + bo[0];
-  e1 = warp_sum(e1) + bo[1];
-  pl = warp_sum(pl) + bp[0];
-  if (lane == 0) {
-    const size_t i = warp;
-    if (p.eps_out) { p.eps_out[i * 2] = e0; p.eps_out[i * 2 + 1] = e1; }
-    if (p.pen_out) p.pen_out[i * p.pen_stride + p.pen_offset] = 1.f / (1.f + expf(-pl));
+  const size_t npts = (size_t)p.B * p.T;
+  const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t base = warp0 * 4; base < npts; base += nwarps * 4) {
+    const size_t i = base + grp;
+    const bool ok = i < npts;
+    const size_t ii = ok ? i : 0;
+    const int b = (int)(ii / p.T), t = (int)(ii - (size_t)b * p.T);
+    const size_t row = (size_t)b * (p.T + 1) + 1 + t;
+    const T* hr = h + row * C + c0;
+    float e0 = 0.f, e1 = 0.f, pl = 0.f;
+    float xv[16];
+    load8<T>(hr, xv);
+    load8<T>(hr + 8, xv + 8);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      e0 = fmaf(xv[k], w0[k], e0);
+      e1 = fmaf(xv[k], w1[k], e1);
+      pl = fmaf(xv[k], wp[k], pl);
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      e0 += __shfl_xor_sync(0xffffffffu, e0, o);
+      e1 += __shfl_xor_sync(0xffffffffu, e1, o);
+      pl += __shfl_xor_sync(0xffffffffu, pl, o);
+    }
+    e0 += b0; e1 += b1; pl += bpv;
+    if (!ok) continue;
+    float y0 = 0.f, y1 = 0.f;
     if (p.x_io) {
       const float x0 = p.x_io[i * 2], x1 = p.x_io[i * 2 + 1];
       float z0 = 0.f, z1 = 0.f;
       if (p.noise) { z0 = p.noise[i * 2]; z1 = p.noise[i * 2 + 1]; }
-      float y0, y1;
       if (p.mode == 0) {  // "new": (x - sqrt(1-abar) eps) / sqrt(1-beta) + z sqrt(1-abar_next)
         y0 = (x0 - p.c_eps * e0) / p.c_div + z0 * p.c_noise;
         y1 = (x1 - p.c_eps * e1) / p.c_div + z1 * p.c_noise;
@@ -468,20 +499,43 @@ __global__ void __launch_bounds__(256) heads_update_kernel(const T* __restrict__
         y0 = p.c_div * (x0 - p.c_eps * e0 / p.c_eps2) + p.c_noise * z0;
         y1 = p.c_div * (x1 - p.c_eps * e1 / p.c_eps2) + p.c_noise * z1;
       }
-      float* xo = p.x_out ? p.x_out : p.x_io;
-      xo[i * p.x_out_stride] = y0;
-      xo[i * p.x_out_stride + 1] = y1;
+    }
+    if (sub == 0) {
+      if (p.eps_out) { p.eps_out[i * 2] = e0; p.eps_out[i * 2 + 1] = e1; }
+      if (p.pen_out) p.pen_out[i * p.pen_stride + p.pen_offset] = 1.f / (1.f + expf(-pl));
+      if (p.x_io) {
+        float* xo = p.x_out ? p.x_out : p.x_io;
+        xo[i * p.x_out_stride] = y0;
+        xo[i * p.x_out_stride + 1] = y1;
+      }
+    }
+    if (p.next_raw) {   // input_dense of the next step on the updated point
+      T* nr = reinterpret_cast<T*>(p.next_raw) + row * C + c0;
+      T* na = reinterpret_cast<T*>(p.next_act) + row * C + c0;
+      float v[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) v[k] = fmaf(y1, iw1[k], fmaf(y0, iw0[k], ib[k]));
+      store8<T>(nr, v);
+      store8<T>(nr + 8, v + 8);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) v[k] = silu_f(v[k]);
+      store8<T>(na, v);
+      store8<T>(na + 8, v + 8);
     }
   }
 }
 template <typename T>
-void launch_heads_update(const T* h, int C, const float* Wo, const float* bo, const float* Wp,
-                         const float* bp, const HeadParams& p, cudaStream_t st) {
-  const size_t nw = (size_t)p.B * p.T;
-  heads_update_kernel<T><<<(unsigned)((nw + 7) / 8), 256, 0, st>>>(h, C, Wo, bo, Wp, bp, p);
+int launch_heads_update(const T* h, int C, const float* Wo, const float* bo, const float* Wp,
+                        const float* bp, const HeadParams& p, cudaStream_t st) {
+  if (C != 128) return 1;
+  const size_t nw = ((size_t)p.B * p.T + 3) / 4;
+  size_t blocks = (nw + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  heads_update_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(h, C, Wo, bo, Wp, bp, p);
+  return 0;
 }
-template void launch_heads_update<float>(const float*, int, const float*, const float*, const float*, const float*, const HeadParams&, cudaStream_t);
-template void launch_heads_update<bf16>(const bf16*, int, const float*, const float*, const float*, const float*, const HeadParams&, cudaStream_t);
+template int launch_heads_update<float>(const float*, int, const float*, const float*, const float*, const float*, const HeadParams&, cudaStream_t);
+template int launch_heads_update<bf16>(const bf16*, int, const float*, const float*, const float*, const float*, const HeadParams&, cudaStream_t);
 
 // ---------------------------------------------------------------------------
 // Standalone posterior update (drop-in for utils/nn.py:64-112 with injected z):

@@ -1,4 +1,5 @@
-"""Run one GEMM family a few times (for ncu).  python tools/gemm_one.py rows K N taps [film] [res_post] [ln]"""
+"""Run one GEMM family a few times (for ncu / DHG_TRACE).
+python tools/gemm_one.py rows K N taps [period=393] [film] [res_post] [res_pre] [ln] [rowbias] [act] [both]"""
 import os
 import sys
 
@@ -12,12 +13,18 @@ from dhg_b200 import _abi  # noqa: E402
 rows, K, N, taps = (int(x) for x in sys.argv[1:5])
 flags = sys.argv[5:]
 kw = dict(period=393, pad_first=1)
+for f in flags:
+    if f.startswith("period="):
+        kw["period"] = int(f[7:])
 if "film" in flags:
-    kw.update(film=1, raw=False, act=True)
-if "res_post" in flags:
-    kw.update(res_post=True, raw=True, act=False)
-if "ln" in flags:
-    kw.update(ln=True)
+    kw.update(film=1)
+if "act" in flags:
+    kw.update(raw=False, act=True)
+if "both" in flags:
+    kw.update(raw=True, act=True)
+for k in ("res_post", "res_pre", "ln", "rowbias"):
+    if k in flags:
+        kw[k] = True
 c = gemm_ref.make_case(rows, K, N, taps, seed=1, **kw)
 ms = gemm_ref.run(_abi.lib(), c, repeats=3)
 print(f"rows={rows} K={K} N={N} taps={taps} {flags}: {ms*1e3:.1f} us")

@@ -1,6 +1,7 @@
 """Summarise DHG_TRACE output of the GEMM kernel (timeline of CTA 0).  python tools/trace_summary.py file [first last]"""
 import sys
-names = {0x10: 'P_slot', 0x20: 'M_tmem_ok', 0x21: 'M_a_ok', 0x22: 'M_commit', 0x30: 'E_wait', 0x31: 'E_full_ok', 0x32: 'E_done'}
+names = {0x10: 'P_slot', 0x20: 'M_tmem_ok', 0x21: 'M_a_ok', 0x22: 'M_commit', 0x30: 'E_wait', 0x31: 'E_full_ok', 0x32: 'E_done',
+         0x33: ' e_chunk', 0x34: ' e_ld_done', 0x35: ' e_math_done'}
 ev = []
 for l in open(sys.argv[1]):
     if l.startswith('tc_gemm plan'): print(l.strip())
@@ -9,8 +10,13 @@ for l in open(sys.argv[1]):
 ev.sort()
 lo, hi = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (6, 8)
 print(len(ev), 'events; span', ev[-1][0] - ev[0][0], 'cycles')
+show = False
 for t, c, i in ev:
-    if c != 0x10 and lo <= i <= hi: print(f"   {t:8d} {names[c]:10s} tile {i}")
+    if c == 0x10: continue
+    if c == 0x30: show = lo <= i <= hi
+    if c >= 0x30:
+        if show: print(f"   {t:8d} {names[c]:12s} {i}")
+    elif lo <= i <= hi: print(f"   {t:8d} {names[c]:12s} tile {i}")
 ed = [t for t, c, i in ev if c == 0x32]
 ew = [t for t, c, i in ev if c == 0x30]; ef = [t for t, c, i in ev if c == 0x31]
 mt = [t for t, c, i in ev if c == 0x20]; mc = [t for t, c, i in ev if c == 0x22]
