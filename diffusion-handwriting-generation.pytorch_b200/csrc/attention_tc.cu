@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __
   const int N = sh.N, NS = sh.NS;
   const int stride = (int)gridDim.x * NS;   // item stride of one slot
 
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // programmatic dependent launch, see gemm_tc.cu
   if (warp == 0) {
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // q / k / v come from the previous kernel of the chain
 
   if (warp < NS) {
     // ===== control warp of slot `warp`: one elected lane issues TMA / tcgen05 for the slot's items in turn =====
@@ -247,8 +249,8 @@ __global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __
 
 }  // namespace
 
-int g_attn_dbg = 0, g_attn_halves = 1;
-void attn_tc_set_debug(int v) { if (v >= 0) g_attn_dbg = v; else g_attn_halves = -v; }
+int g_attn_dbg = 0, g_attn_halves = 1, g_attn_pdl = 1;
+void attn_tc_set_debug(int v) { if (v >= 0) g_attn_dbg = v; else if (v <= -100) g_attn_pdl = v == -101; else g_attn_halves = -v; }
 
 struct AttnTcPlan {
   CUtensorMap map_q, map_k, map_v;
@@ -323,8 +325,17 @@ AttnTcPlan* attn_tc_plan_create(const AttnParams& p, int q_rows, int k_rows, cha
 void attn_tc_plan_destroy(AttnTcPlan* a) { delete a; }
 
 int attn_tc_launch(const AttnTcPlan* a, cudaStream_t st) {
-  attn_tc_kernel<<<a->grid, a->threads, a->smem, st>>>(a->map_q, a->map_k, a->map_v, a->sh, a->p);
-  return 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = a->grid;
+  cfg.blockDim = dim3(a->threads);
+  cfg.dynamicSmemBytes = a->smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_attn_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, attn_tc_kernel, a->map_q, a->map_k, a->map_v, a->sh, a->p) == cudaSuccess ? 0 : 1;
 }
 
 }  // namespace dhg

@@ -442,7 +442,7 @@ struct Builder {
         ee.beta = sc.cond + film_off + N;
         ee.film_bstride = sc.bstride;
       }
-      if (tcp) return tc_gemm_launch(tcp, ee, st);
+      if (tcp) return tc_gemm_launch(tcp, ee, st) ? fail("tcgen05 gemm launch failed: %s", cudaGetErrorString(cudaGetLastError())) : 0;
       if (Pl->prec == PREC_FP32) {
         launch_gemm_simt<float>((const float*)Ap, K, rows, W->w32, K, N, taps, Pl->scratch, st);
         launch_rowpost<float>(Pl->scratch, rows, N, ee, st);
@@ -471,7 +471,9 @@ struct Builder {
       AttnTcPlan* ap = attn_tc_plan_create(a, q_rows, k_rows, buf, sizeof(buf));
       if (!ap) { fail("plan: tcgen05 attention: %s", buf); failed = true; return; }
       P->attn_plans.push_back(ap);
-      ops->push_back([=](cudaStream_t st, const StepCtx&) -> int { return attn_tc_launch(ap, st); });
+      ops->push_back([=](cudaStream_t st, const StepCtx&) -> int {
+        return attn_tc_launch(ap, st) ? fail("tcgen05 attention launch failed: %s", cudaGetErrorString(cudaGetLastError())) : 0;
+      });
       return;
     }
     ops->push_back([=](cudaStream_t st, const StepCtx&) -> int {
@@ -1108,7 +1110,7 @@ int64_t dhg_plan_bytes(const dhg_ctx* c) { return (c && c->plan) ? (int64_t)c->p
 int32_t dhg_set_option(dhg_ctx* c, const char* key, int32_t value) {
   if (key && !strcmp(key, "interleave")) { tc_gemm_set_option(4, value); return 0; }
   if (key && !strcmp(key, "attn_dbg")) { attn_tc_set_debug(value); return 0; }
-  if (key && !strcmp(key, "mma_repeat")) { tc_gemm_set_option(5, value); return 0; }
+  if (key && !strcmp(key, "pdl")) { tc_gemm_set_option(6, value); attn_tc_set_debug(value ? -101 : -100); return 0; }
   if (key && !strcmp(key, "w_resident")) { tc_gemm_set_option(2, value); return 0; }
   if (key && !strcmp(key, "specialize")) { tc_gemm_set_option(3, value); return 0; }
   if (!c || !key) return fail("dhg_set_option: null argument");

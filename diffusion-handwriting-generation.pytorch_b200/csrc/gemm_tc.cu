@@ -198,6 +198,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   const bool film_s = film && e.film_bstride == 0 && sh.film_n > 0;   // FiLM vectors shared by the batch -> smem
   const bool fold_bias = film_s && !e.ln && sh.vec_bias_n > 0;        // (acc + b) * g + beta = acc * g + (b * g + beta)
 
+  // Programmatic dependent launch: let the next kernel of the chain start its own prologue (barrier init, TMEM
+  // allocation, weight loads) on SMs this grid has already left; everything that reads or writes activations
+  // waits for the previous kernel below (griddepcontrol.wait).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
@@ -248,6 +252,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
               tma_load_2d(dst + (uint32_t)j * sh.umma_n * TC_BK * 2, &map_w, wb, kbi * TC_BK, tap * sh.N + n0 + j * sh.umma_n);
         }
     }
+    // weights are constants; the activations are produced by the previous kernel of the chain
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // ring positions are kept incrementally (no integer division in these latency-critical loops)
     uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
     for (int t = t_first; t < t_end; t += t_step) {
@@ -303,6 +309,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 #undef DHG_MMA_LOOP
   } else {
     // ===== epilogue warps; warp (q, part): TMEM lanes [32q, 32q+32), one contiguous part of the column chunks =====
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // residual rows are read / outputs written only after the previous kernel
     const bool ln = kLN >= 0 ? (kLN != 0) : (e.ln != 0);
     const int aux_kind = kAUX >= 0 ? kAUX : sh.aux_kind;
     const int film_mode = kFILM >= 0 ? kFILM : (film ? (film_s ? 1 : 2) : 0);
@@ -580,11 +587,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 }  // namespace
 
 // experiment switches (dhg_set_option: "w_resident", "specialize", "interleave")
-int g_opt_w_resident = 1, g_opt_specialize = 1, g_opt_interleave = 1, g_opt_mma_repeat = 1;
+int g_opt_w_resident = 1, g_opt_specialize = 1, g_opt_interleave = 1, g_opt_pdl = 1;
 void tc_gemm_set_option(int which, int value) {
   if (which == 2) g_opt_w_resident = value;
   else if (which == 4) g_opt_interleave = value;
-  else if (which == 5) g_opt_mma_repeat = value;
+  else if (which == 6) g_opt_pdl = value;
   else if (which == 3) g_opt_specialize = value;
 }
 
@@ -749,8 +756,17 @@ int tc_gemm_launch(const TcGemmPlan* p, const Epilogue& e, cudaStream_t st) {
   // the specialised instance assumes FiLM vectors shared by the batch (or no FiLM at all)
   const bool shared_ok = e.gamma ? (e.film_bstride == 0 && p->sh.film_n > 0) : (p->sh.film_n == 0);
   TcKernFn fn = shared_ok ? p->fn_shared : p->fn_generic;
-  fn<<<p->grid, TC_THREADS, p->smem, st>>>(p->map_a, p->map_w, p->sh, e);
-  return 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = p->grid;
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = p->smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_opt_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, fn, p->map_a, p->map_w, p->sh, e) == cudaSuccess ? 0 : 1;
 }
 
 }  // namespace dhg
