@@ -211,6 +211,20 @@ def run_b200(args, rank, world, local_rank):
     post_us = p0.elapsed_time(p1) / 64 * 1e3
     post_gbs = 16.0 * n / (post_us * 1e-6) / 1e9   # 32*T bytes per sample: read x, eps, z + write x (fp32)
 
+    # ---- the dominant kernel on its own: every tcgen05 GEMM launch of one denoiser step, timed per family ----
+    gemm = None
+    if rank == 0 and args.gemm_roofline and B == 1024:
+        w_bytes = w.plan_bytes
+        w.close()          # free the 6 GB plan before allocating the GEMM operands
+        del text, style, x0, noise, big, outb, eps, out
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from gemm_cases import time_step_gemms
+
+        gemm = time_step_gemms(B, repeats=5)
+    else:
+        w_bytes = w.plan_bytes
+
     if rank != 0:
         return
     peaks = measured_peaks()
@@ -226,7 +240,7 @@ def run_b200(args, rank, world, local_rank):
                         "seeded random-init weights, injected noise",
             "per_gpu_batch": B, "global_batch": B * world, "T": T, "L": L, "chunk": min(B, args.chunk),
             "parallelism": f"batch-sharded x{world}, no collective in the loop",
-            "l2": f"working set {w.plan_bytes / 1e9:.1f} GB per chain >> 126 MB L2 (inputs larger than L2)",
+            "l2": f"working set {w_bytes / 1e9:.1f} GB per chain >> 126 MB L2 (inputs larger than L2)",
         },
         "us_per_denoiser_step": ms_step / NUM_STEPS * 1e3,
         "finite": finite,
@@ -244,6 +258,17 @@ def run_b200(args, rank, world, local_rank):
             "us_per_launch": post_us, "bytes_per_launch": 16 * n, "peak_source": peaks["source"],
         },
     }
+    if gemm:
+        us = gemm["us"]
+        line["roofline_gemm"] = {
+            "kernel": "tc_gemm_kernel (all %d launches of one denoiser step, each family timed alone, 5 launches per family)" % gemm["launches"],
+            "bound": "hbm", "achieved": gemm["bytes"] / us / 1e3, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": gemm["bytes"] / us / 1e3 / peaks["hbm_gbs"], "traffic": None,
+            "tflops": gemm["flop"] / us / 1e6, "tensor_frac": gemm["flop"] / us / 1e6 / peaks["bf16_tflops"],
+            "us_per_step": us, "share_of_step": us / (ms_step / NUM_STEPS * 1e3),
+            "algorithmic_bytes_per_step": gemm["bytes"], "flop_per_step": gemm["flop"],
+            "peak_source": peaks["source"] + " (burst figures: families timed in isolation)",
+        }
     if args.cpu_baseline and world >= 1:
         lines_s, s_chain, cores = cpu_oracle_leg(args.ref_batch, 1, 1)
         line["cpu_baseline"] = {
@@ -265,6 +290,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--ref-batch", type=int, default=32, help="prompts per CPU-baseline chain")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-gemm-roofline", dest="gemm_roofline", action="store_false")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: >= 3 warm-up steps

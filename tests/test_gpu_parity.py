@@ -90,6 +90,29 @@ def test_intermediate_activations_match_oracle(writers, state_dict, golden):
             assert _rel(got, taps[name]) < tol, (mode, name)
 
 
+@pytest.mark.parametrize("name,B,T,L,pad_from", [
+    ("train_shape_c4", 3, 480, 50, 31),      # BASELINE configs[3] shape: T=480, text padded with 0 up to L=50
+    ("long_line_c5", 2, 1200, 81, None),     # BASELINE configs[4] shape: T=1200 strokes, 80 chars + end token
+    ("tiny", 1, 8, 1, None),                 # smallest legal shape: one token, T=8
+    ("all_padding_text", 2, 64, 12, 0),      # every text token is padding: uniform cross-attention in the reference
+])
+def test_denoise_other_shapes_match_oracle(writers, state_dict, name, B, T, L, pad_from):
+    g = torch.Generator().manual_seed(len(name) + T)
+    strokes = torch.randn(B, T, 2, generator=g)
+    text = torch.randint(2, 73, (B, L), generator=g)
+    text[:, -1] = 1
+    if pad_from is not None:
+        text[:, pad_from:] = 0
+    sigma = torch.rand(B, 1, generator=g) * 0.9 + 0.05
+    style = torch.randn(B, 14, 1280, generator=g)
+    eps_o, pen_o = O.denoiser_forward(state_dict, strokes, text, sigma, style)
+    for mode, tol, ptol in (("fp32", 1e-4, 1e-4), ("bf16", BF16_REL, 1e-2)):
+        eps, pen, _ = writers[mode].denoise(strokes, text, sigma, style)
+        assert torch.isfinite(eps).all() and torch.isfinite(pen).all()
+        assert _rel(eps.cpu(), eps_o) < tol, (name, mode)
+        assert (pen.cpu() - pen_o).abs().max() < ptol, (name, mode)
+
+
 # ----------------------------------------------------------------------------- full chains
 def test_chain_c1_fp32_matches_reference_golden(writers, golden):
     g = golden("chain_c1")     # BASELINE configs[0]: batch 1, 'Follow the White Rabbit', T=392
