@@ -56,7 +56,8 @@ struct TcShape {
   int m_super;     // ceil(m_tiles / G)
   int stages_a, stages_w;   // A ring / W ring depth (W ring unused when w_resident)
   int w_resident;  // all W tiles of this CTA's column group stay in smem for the whole kernel
-  int sticky;      // CTA c only works on column group c % n_groups
+  int sticky;      // each CTA works on one column group only
+  int grp_cta0[13];   // sticky: first CTA of each column group (n_groups + 1 entries)
   int kb_per_tap;  // ceil(K / 64)
   int umma_n;      // N of one tcgen05.mma (BN, or 192 when BN == 384)
   int n_umma;      // MMAs per k-step along N (1 or 2)
@@ -187,10 +188,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   unsigned tr_n = 0;
   const int tr_role = warp < 2 ? warp : 2;
   // work assignment: tile `it` of this CTA -> (m tile, column group)
-  const int cta_groups = sh.sticky ? sh.n_groups : 1;
-  const int my_group = sh.sticky ? (int)(blockIdx.x % sh.n_groups) : 0;
-  const int t_first = sh.sticky ? (int)(blockIdx.x / sh.n_groups) : (int)blockIdx.x;
-  const int t_step = (int)gridDim.x / cta_groups;
+  // sticky: the CTAs [grp_cta0[g], grp_cta0[g+1]) work on column group g only (more CTAs for the groups whose
+  // epilogue also has per-position bias rows to fetch), so that group's W tiles can stay resident
+  int my_group = 0, t_first = (int)blockIdx.x, t_step = (int)gridDim.x;
+  if (sh.sticky) {
+    while (my_group + 1 < sh.n_groups && (int)blockIdx.x >= sh.grp_cta0[my_group + 1]) ++my_group;
+    t_first = (int)blockIdx.x - sh.grp_cta0[my_group];
+    t_step = sh.grp_cta0[my_group + 1] - sh.grp_cta0[my_group];
+  }
   const int t_end = sh.sticky ? sh.m_super : sh.m_super * sh.n_groups;   // work items = (super-tile, column group)
   uint8_t* a_ring = smem;
   uint8_t* w_base = smem + sh.off_w;
@@ -345,32 +350,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     // flight while this tile is being finished.
     uint32_t aux_issued = 0, aux_consumed = 0;
     int iss_t = t_first, iss_sub = 0, iss_ci = 0;   // (super-tile, row tile, chunk) of the next flat chunk to issue
+    int iss_src = -1, iss_ng = 0;                   // cached per issue tile: my row's source row, the column group
     auto issue_aux_flat = [&]() {
       const uint32_t f = aux_issued++;
       const int ft = iss_t, fsub = iss_sub, ci = iss_ci;
-      if (++iss_ci == my_nch) {
-        iss_ci = 0;
-        if (++iss_sub == sh.G) { iss_sub = 0; iss_t += t_step; }
-      }
       if (ft < t_end) {
-        const int fmts = sh.sticky ? ft : ft / sh.n_groups;
-        const int fng = sh.sticky ? my_group : ft - fmts * sh.n_groups;
-        const int fm = (fmts * sh.G + fsub) * TC_BM + r_tile;
-        // source row of my residual / bias row in that tile, -1 = none (zero-filled)
-        const bool f_in = fm < sh.rows;
-        int aux_src = -1;
-        if (aux_kind == AUX_RES_PRE || aux_kind == AUX_RES_POST) {
-          aux_src = f_in ? fm : -1;
-        } else {
-          const int fmm = f_in ? fm : 0;
-          const int fb = fmm / period;
-          const int fj = fmm - fb * period;
-          const bool f_pad = (fmm >= nvalid) || (pad_first && fj == 0);
-          const int fpos = f_pad ? 0 : fj - pad_first;
-          const bool f_live = f_in && !f_pad;
-          if (aux_kind == AUX_RES_POST_UP) aux_src = f_live ? fb * e.res_post_period_lo + 1 + (fpos >> 1) : -1;
-          else aux_src = f_live ? fpos : -1;
+        if (ci == 0) {   // first chunk of a row tile: where does my row's residual / bias row live?
+          const int fmts = sh.sticky ? ft : ft / sh.n_groups;
+          iss_ng = sh.sticky ? my_group : ft - fmts * sh.n_groups;
+          const int fm = (fmts * sh.G + fsub) * TC_BM + r_tile;
+          const bool f_in = fm < sh.rows;
+          if (aux_kind == AUX_RES_PRE || aux_kind == AUX_RES_POST) {
+            iss_src = f_in ? fm : -1;
+          } else {
+            const int fmm = f_in ? fm : 0;
+            const int fb = fmm / period;
+            const int fj = fmm - fb * period;
+            const bool f_pad = (fmm >= nvalid) || (pad_first && fj == 0);
+            const int fpos = f_pad ? 0 : fj - pad_first;
+            const bool f_live = f_in && !f_pad;
+            if (aux_kind == AUX_RES_POST_UP) iss_src = f_live ? fb * e.res_post_period_lo + 1 + (fpos >> 1) : -1;
+            else iss_src = f_live ? fpos : -1;
+          }
         }
+        const int aux_src = iss_src, fng = iss_ng;
         const int col0 = fng * sh.BN + (c_lo + ci) * 32;
         const uint32_t slot = aux_ring + (f % (uint32_t)aux_depth) * aux_slot_bytes;
         if (col0 < aux_ncols) {
@@ -382,6 +385,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
             cp_async16(slot + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4), gp, src < 0 ? 0u : 16u);
           }
         }
+      }
+      if (++iss_ci == my_nch) {
+        iss_ci = 0;
+        if (++iss_sub == sh.G) { iss_sub = 0; iss_t += t_step; }
       }
       cp_async_commit();
     };
@@ -728,7 +735,21 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   sh.off_bar = off; off += 64 * 8;
   p->smem = off + 1024;
   int grid = sh.m_super * sh.n_groups < num_sms ? sh.m_super * sh.n_groups : num_sms;
-  if (sh.sticky) grid = (num_sms / sh.n_groups) * sh.n_groups;
+  if (sh.sticky) {
+    if (sh.n_groups > 12) { snprintf(err, errlen, "too many column groups"); delete p; return nullptr; }
+    // CTAs per group in proportion to the estimated per-tile epilogue cost (groups with per-position bias rows: 1.35)
+    double wsum = 0, w[12];
+    for (int g = 0; g < sh.n_groups; ++g) { w[g] = (aux_kind == AUX_ROWBIAS && g * BN < e.rowbias16_cols) ? 1.35 : 1.0; wsum += w[g]; }
+    int used = 0;
+    sh.grp_cta0[0] = 0;
+    for (int g = 0; g < sh.n_groups; ++g) {
+      int n = g == sh.n_groups - 1 ? num_sms - used : (int)(num_sms * w[g] / wsum + 0.5);
+      if (n < 1) n = 1;
+      used += n;
+      sh.grp_cta0[g + 1] = used;
+    }
+    grid = used;
+  }
   p->grid = dim3(grid);
   if (!make_map(&p->map_a, A, (uint64_t)rows, (uint64_t)K, (uint64_t)lda, (uint32_t)a_rows, err, errlen) ||
       !make_map(&p->map_w, W, (uint64_t)taps * N, (uint64_t)K, (uint64_t)K, (uint32_t)sh.umma_n, err, errlen)) {

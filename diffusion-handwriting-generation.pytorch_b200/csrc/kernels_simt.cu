@@ -435,52 +435,50 @@ template void launch_input_dense<bf16>(const float*, const float*, const float*,
 
 // ---------------------------------------------------------------------------
 // Output heads + fused posterior update (+ fused input_dense of the next step).
-// 8 lanes per stroke point (each lane owns 16 of the C = 128 channels), 4 points per warp, grid-stride.
+// 16 lanes per stroke point (each lane owns 8 of the C = 128 channels), 2 points per warp, grid-stride.
 //   eps = Linear(C,2)(h), pen = sigmoid(Linear(C,1)(h))          model.py:179-181
 //   x  <- posterior(x, eps, z)                                   utils/nn.py:84-87,110-112
 //   next step: in = Linear(2,C)(x) -> raw and SiLU'd rows        model.py:139 (+ cnn.py:25)
 // ---------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) heads_update_kernel(const T* __restrict__ h, int C,
-                                                           const float* __restrict__ Wo /*[2,C]*/,
-                                                           const float* __restrict__ bo,
-                                                           const float* __restrict__ Wp /*[1,C]*/,
-                                                           const float* __restrict__ bp, HeadParams p) {
-  const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
-  const int c0 = sub * 16;   // my 16 channels (C == 128)
-  float w0[16], w1[16], wp[16];
+__global__ void __launch_bounds__(256, 3) heads_update_kernel(const T* __restrict__ h, int C,
+                                                              const float* __restrict__ Wo /*[2,C]*/,
+                                                              const float* __restrict__ bo,
+                                                              const float* __restrict__ Wp /*[1,C]*/,
+                                                              const float* __restrict__ bp, HeadParams p) {
+  // 16 lanes per stroke point (each lane owns 8 of the C = 128 channels: one 16-byte access per row for bf16),
+  // 2 points per warp, grid-stride
+  const int lane = threadIdx.x & 31, sub = lane & 15, grp = lane >> 4;
+  const int c0 = sub * 8;
+  float w0[8], w1[8], wp[8], iw0[8], iw1[8], ib[8];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) { w0[i] = Wo[c0 + i]; w1[i] = Wo[C + c0 + i]; wp[i] = Wp[c0 + i]; }
-  const float b0 = bo[0], b1 = bo[1], bpv = bp[0];
-  float iw0[16], iw1[16], ib[16];   // input_dense rows of my channels (next step)
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    iw0[i] = p.next_raw ? p.in_W[(c0 + i) * 2] : 0.f;
+  for (int i = 0; i < 8; ++i) {
+    w0[i] = Wo[c0 + i]; w1[i] = Wo[C + c0 + i]; wp[i] = Wp[c0 + i];
+    iw0[i] = p.next_raw ? p.in_W[(c0 + i) * 2] : 0.f;       // input_dense rows of my channels (next step)
     iw1[i] = p.next_raw ? p.in_W[(c0 + i) * 2 + 1] : 0.f;
     ib[i] = p.next_raw ? p.in_b[c0 + i] : 0.f;
   }
+  const float b0 = bo[0], b1 = bo[1], bpv = bp[0];
   const size_t npts = (size_t)p.B * p.T;
   const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-  for (size_t base = warp0 * 4; base < npts; base += nwarps * 4) {
+  for (size_t base = warp0 * 2; base < npts; base += nwarps * 2) {
     const size_t i = base + grp;
     const bool ok = i < npts;
     const size_t ii = ok ? i : 0;
     const int b = (int)(ii / p.T), t = (int)(ii - (size_t)b * p.T);
     const size_t row = (size_t)b * (p.T + 1) + 1 + t;
-    const T* hr = h + row * C + c0;
+    float xv[8];
+    load8<T>(h + row * C + c0, xv);
     float e0 = 0.f, e1 = 0.f, pl = 0.f;
-    float xv[16];
-    load8<T>(hr, xv);
-    load8<T>(hr + 8, xv + 8);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
+    for (int k = 0; k < 8; ++k) {
       e0 = fmaf(xv[k], w0[k], e0);
       e1 = fmaf(xv[k], w1[k], e1);
       pl = fmaf(xv[k], wp[k], pl);
     }
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
+    for (int o = 8; o > 0; o >>= 1) {
       e0 += __shfl_xor_sync(0xffffffffu, e0, o);
       e1 += __shfl_xor_sync(0xffffffffu, e1, o);
       pl += __shfl_xor_sync(0xffffffffu, pl, o);
@@ -489,15 +487,15 @@ __global__ void __launch_bounds__(256) heads_update_kernel(const T* __restrict__
     if (!ok) continue;
     float y0 = 0.f, y1 = 0.f;
     if (p.x_io) {
-      const float x0 = p.x_io[i * 2], x1 = p.x_io[i * 2 + 1];
-      float z0 = 0.f, z1 = 0.f;
-      if (p.noise) { z0 = p.noise[i * 2]; z1 = p.noise[i * 2 + 1]; }
+      const float2 xx = *reinterpret_cast<const float2*>(p.x_io + i * 2);
+      float2 zz = make_float2(0.f, 0.f);
+      if (p.noise) zz = *reinterpret_cast<const float2*>(p.noise + i * 2);
       if (p.mode == 0) {  // "new": (x - sqrt(1-abar) eps) / sqrt(1-beta) + z sqrt(1-abar_next)
-        y0 = (x0 - p.c_eps * e0) / p.c_div + z0 * p.c_noise;
-        y1 = (x1 - p.c_eps * e1) / p.c_div + z1 * p.c_noise;
+        y0 = (xx.x - p.c_eps * e0) / p.c_div + zz.x * p.c_noise;
+        y1 = (xx.y - p.c_eps * e1) / p.c_div + zz.y * p.c_noise;
       } else {            // "standard": (1/sqrt(1-beta)) (x - beta eps / sqrt(1-abar)) + sqrt(beta) z
-        y0 = p.c_div * (x0 - p.c_eps * e0 / p.c_eps2) + p.c_noise * z0;
-        y1 = p.c_div * (x1 - p.c_eps * e1 / p.c_eps2) + p.c_noise * z1;
+        y0 = p.c_div * (xx.x - p.c_eps * e0 / p.c_eps2) + p.c_noise * zz.x;
+        y1 = p.c_div * (xx.y - p.c_eps * e1 / p.c_eps2) + p.c_noise * zz.y;
       }
     }
     if (sub == 0) {
@@ -510,17 +508,13 @@ __global__ void __launch_bounds__(256) heads_update_kernel(const T* __restrict__
       }
     }
     if (p.next_raw) {   // input_dense of the next step on the updated point
-      T* nr = reinterpret_cast<T*>(p.next_raw) + row * C + c0;
-      T* na = reinterpret_cast<T*>(p.next_act) + row * C + c0;
-      float v[16];
+      float v[8];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) v[k] = fmaf(y1, iw1[k], fmaf(y0, iw0[k], ib[k]));
-      store8<T>(nr, v);
-      store8<T>(nr + 8, v + 8);
+      for (int k = 0; k < 8; ++k) v[k] = fmaf(y1, iw1[k], fmaf(y0, iw0[k], ib[k]));
+      store8<T>(reinterpret_cast<T*>(p.next_raw) + row * C + c0, v);
 #pragma unroll
-      for (int k = 0; k < 16; ++k) v[k] = silu_f(v[k]);
-      store8<T>(na, v);
-      store8<T>(na + 8, v + 8);
+      for (int k = 0; k < 8; ++k) v[k] = silu_f(v[k]);
+      store8<T>(reinterpret_cast<T*>(p.next_act) + row * C + c0, v);
     }
   }
 }
@@ -528,9 +522,9 @@ template <typename T>
 int launch_heads_update(const T* h, int C, const float* Wo, const float* bo, const float* Wp,
                         const float* bp, const HeadParams& p, cudaStream_t st) {
   if (C != 128) return 1;
-  const size_t nw = ((size_t)p.B * p.T + 3) / 4;
+  const size_t nw = ((size_t)p.B * p.T + 1) / 2;
   size_t blocks = (nw + 7) / 8;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > 148 * 12) blocks = 148 * 12;
   heads_update_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(h, C, Wo, bo, Wp, bp, p);
   return 0;
 }
