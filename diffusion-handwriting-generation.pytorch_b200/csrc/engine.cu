@@ -1110,6 +1110,7 @@ int64_t dhg_plan_bytes(const dhg_ctx* c) { return (c && c->plan) ? (int64_t)c->p
 int32_t dhg_set_option(dhg_ctx* c, const char* key, int32_t value) {
   if (key && !strcmp(key, "interleave")) { tc_gemm_set_option(4, value); return 0; }
   if (key && !strcmp(key, "attn_dbg")) { attn_tc_set_debug(value); return 0; }
+  if (key && !strcmp(key, "pair")) { tc_gemm_set_option(7, value); return 0; }
   if (key && !strcmp(key, "pdl")) { tc_gemm_set_option(6, value); attn_tc_set_debug(value ? -101 : -100); return 0; }
   if (key && !strcmp(key, "w_resident")) { tc_gemm_set_option(2, value); return 0; }
   if (key && !strcmp(key, "specialize")) { tc_gemm_set_option(3, value); return 0; }
@@ -1208,9 +1209,10 @@ int32_t dhg_debug_tc_gemm_ex(int32_t device, const void* a, int32_t lda, int32_t
   }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
-  tc_gemm_launch(p, e, st);
+  int lrc = tc_gemm_launch(p, e, st);
   cudaEventRecord(e0, st);
-  for (int i = 0; i < repeats; ++i) tc_gemm_launch(p, e, st);
+  for (int i = 0; i < repeats && !lrc; ++i) lrc = tc_gemm_launch(p, e, st);
+  if (lrc) { tc_gemm_plan_destroy(p); return fail("dhg_debug_tc_gemm_ex: launch failed: %s", cudaGetErrorString(cudaGetLastError())); }
   cudaEventRecord(e1, st);
   cudaError_t ce = cudaStreamSynchronize(st);
   float ms = 0.f;

@@ -57,6 +57,7 @@ struct TcShape {
   int stages_a, stages_w;   // A ring / W ring depth (W ring unused when w_resident)
   int w_resident;  // all W tiles of this CTA's column group stay in smem for the whole kernel
   int sticky;      // each CTA works on one column group only
+  int pair;        // cta_group::2: the two CTAs of a cluster share every MMA (M = 256: 128 rows each) and each loads half of W
   int grp_cta0[13];   // sticky: first CTA of each column group (n_groups + 1 entries)
   int kb_per_tap;  // ceil(K / 64)
   int umma_n;      // N of one tcgen05.mma (BN, or 192 when BN == 384)
@@ -83,14 +84,14 @@ struct TcShape {
 // The MMA warp's main loop, specialised on the tap count and on the number of interleaved accumulators so that
 // everything inside a k-block is straight-line code (the single issuing warp is latency-critical: every
 // instruction between two tcgen05.mma shows up in the tile time).
-template <int TAPS, int G>
+template <int TAPS, int G, bool PAIR>
 __device__ __forceinline__ void mma_issue_loop(const TcShape& sh, const bool leader, const uint32_t tmem_base,
                                                const uint32_t a_ring_addr, const uint32_t w_addr, uint64_t* full_a,
                                                uint64_t* empty_a, uint64_t* full_w, uint64_t* empty_w,
                                                uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, const int t_first,
                                                const int t_end, const int t_step, unsigned& tr_n, const int tr_role,
                                                const int lane) {
-  const uint32_t nb2 = (uint32_t)sh.umma_n * TC_BK * 2;   // byte offset of the second N half (BN = 384)
+  const uint32_t nb2 = (uint32_t)(PAIR ? sh.umma_n / 2 : sh.umma_n) * TC_BK * 2;   // byte offset of the second N half (BN = 384)
   const bool two_n = sh.n_umma == 2;
   const bool resident = sh.w_resident != 0;
   uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
@@ -132,31 +133,43 @@ __device__ __forceinline__ void mma_issue_loop(const TcShape& sh, const bool lea
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k)
 #pragma unroll
-              for (int sub = 0; sub < G; ++sub)
-                umma_bf16(acc + (uint32_t)(sub * sh.BN), umma_desc_make(alo[sub] + tap * 8 + 2 * k, kDescHiSw128),
-                          umma_desc_make(blo + 2 * k, kDescHiSw128), sh.idesc, (tap | k) ? 1u : first);
+              for (int sub = 0; sub < G; ++sub) {
+                if (PAIR)
+                  umma_bf16_pair(acc, umma_desc_make(alo[0] + tap * 8 + 2 * k, kDescHiSw128), umma_desc_make(blo + 2 * k, kDescHiSw128),
+                                 sh.idesc, (tap | k) ? 1u : first);
+                else
+                  umma_bf16(acc + (uint32_t)(sub * sh.BN), umma_desc_make(alo[sub] + tap * 8 + 2 * k, kDescHiSw128),
+                            umma_desc_make(blo + 2 * k, kDescHiSw128), sh.idesc, (tap | k) ? 1u : first);
+              }
           } else {
             const uint32_t blo2 = umma_desc_lo(b_addr + nb2);
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k) {
-              umma_bf16(acc, umma_desc_make(alo[0] + tap * 8 + 2 * k, kDescHiSw128), umma_desc_make(blo + 2 * k, kDescHiSw128), sh.idesc,
-                        (tap | k) ? 1u : first);
-              umma_bf16(acc + (uint32_t)sh.umma_n, umma_desc_make(alo[0] + tap * 8 + 2 * k, kDescHiSw128),
-                        umma_desc_make(blo2 + 2 * k, kDescHiSw128), sh.idesc, (tap | k) ? 1u : first);
+              if (PAIR) {
+                umma_bf16_pair(acc, umma_desc_make(alo[0] + tap * 8 + 2 * k, kDescHiSw128), umma_desc_make(blo + 2 * k, kDescHiSw128),
+                               sh.idesc, (tap | k) ? 1u : first);
+                umma_bf16_pair(acc + (uint32_t)sh.umma_n, umma_desc_make(alo[0] + tap * 8 + 2 * k, kDescHiSw128),
+                               umma_desc_make(blo2 + 2 * k, kDescHiSw128), sh.idesc, (tap | k) ? 1u : first);
+              } else {
+                umma_bf16(acc, umma_desc_make(alo[0] + tap * 8 + 2 * k, kDescHiSw128), umma_desc_make(blo + 2 * k, kDescHiSw128), sh.idesc,
+                          (tap | k) ? 1u : first);
+                umma_bf16(acc + (uint32_t)sh.umma_n, umma_desc_make(alo[0] + tap * 8 + 2 * k, kDescHiSw128),
+                          umma_desc_make(blo2 + 2 * k, kDescHiSw128), sh.idesc, (tap | k) ? 1u : first);
+              }
             }
           }
-          if (!resident) umma_commit(smem_u32(&empty_w[sw]));   // frees the W slot when these MMAs retire
+          if (!resident) { if (PAIR) umma_commit_pair(smem_u32(&empty_w[sw])); else umma_commit(smem_u32(&empty_w[sw])); }   // frees the W slot (in both CTAs of a pair) when these MMAs retire
         }
         __syncwarp();
         if (!resident && ++sw == (uint32_t)sh.stages_w) { sw = 0; pw ^= 1u; }
       }
       if (leader) {
 #pragma unroll
-        for (int sub = 0; sub < G; ++sub) umma_commit(smem_u32(&empty_a[slot[sub]]));   // frees the A slots
+        for (int sub = 0; sub < G; ++sub) { if (PAIR) umma_commit_pair(smem_u32(&empty_a[slot[sub]])); else umma_commit(smem_u32(&empty_a[slot[sub]])); }   // frees the A slots
       }
       __syncwarp();
     }
-    if (leader) umma_commit(smem_u32(&tmem_full_bar[as]));   // accumulators complete
+    if (leader) { if (PAIR) umma_commit_pair(smem_u32(&tmem_full_bar[as])); else umma_commit(smem_u32(&tmem_full_bar[as])); }   // accumulators complete
     __syncwarp();
     DHG_TR(0x22, it);
   }
@@ -165,7 +178,7 @@ __device__ __forceinline__ void mma_issue_loop(const TcShape& sh, const bool lea
 // Template parameters fix the epilogue variant at compile time (-1 = read the flag at run time: the
 // generic instance).  kLN: LayerNorm; kAUX: AUX_* kind; kFILM: 0 none, 1 vectors shared by the batch
 // (smem), 2 per-sample vectors (global loads); kOUT: 1 raw, 2 SiLU'd, 3 both.
-template <int kLN, int kAUX, int kFILM, int kOUT>
+template <int kLN, int kAUX, int kFILM, int kOUT, bool kPAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_w,
                                                                 const TcShape sh, const Epilogue e) {
@@ -190,7 +203,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   // work assignment: tile `it` of this CTA -> (m tile, column group)
   // sticky: the CTAs [grp_cta0[g], grp_cta0[g+1]) work on column group g only (more CTAs for the groups whose
   // epilogue also has per-position bias rows to fetch), so that group's W tiles can stay resident
-  int my_group = 0, t_first = (int)blockIdx.x, t_step = (int)gridDim.x;
+  // pair mode: the two CTAs of a cluster work on two consecutive row tiles of the same column group
+  const uint32_t cta_rank = kPAIR ? cluster_ctarank() : 0u;
+  const int tiles_per_super = kPAIR ? 2 : sh.G;
+  int my_group = 0, t_first = kPAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, t_step = kPAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   if (sh.sticky) {
     while (my_group + 1 < sh.n_groups && (int)blockIdx.x >= sh.grp_cta0[my_group + 1]) ++my_group;
     t_first = (int)blockIdx.x - sh.grp_cta0[my_group];
@@ -219,14 +235,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     mbar_init(smem_u32(w_all_bar), 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tmem_full_bar[a]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[a]), EPI_WARPS);
+      mbar_init(smem_u32(&tmem_empty_bar[a]), EPI_WARPS * (kPAIR ? 2 : 1));   // pair: rank 0 collects both CTAs' epilogues
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (kPAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   for (int n = threadIdx.x; n < sh.vec_bias_n; n += TC_THREADS) bias_s[n] = __ldg(e.bias + n);
   if (film_s) {
@@ -238,6 +259,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if (kPAIR) cluster_sync_all();   // the peer's barriers are initialised before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -272,8 +294,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
           DHG_TR(0x10, sa);
           const uint32_t fb = smem_u32(&full_a[sa]);
           if (leader) {
-            mbar_expect_tx(fb, sh.a_tx_bytes);
-            tma_load_2d(smem_u32(a_ring + (size_t)sa * sh.a_stage_bytes), &map_a, fb, kk, (mts * sh.G + sub) * TC_BM + a_row_off);
+            const int row0 = (mts * tiles_per_super + sub + (int)cta_rank) * TC_BM + a_row_off;
+            if (kPAIR) {   // both CTAs' bytes are counted on rank 0's barrier
+              if (cta_rank == 0) mbar_expect_tx(fb, 2 * sh.a_tx_bytes);
+              tma_load_2d_pair(smem_u32(a_ring + (size_t)sa * sh.a_stage_bytes), &map_a, fb, kk, row0);
+            } else {
+              mbar_expect_tx(fb, sh.a_tx_bytes);
+              tma_load_2d(smem_u32(a_ring + (size_t)sa * sh.a_stage_bytes), &map_a, fb, kk, row0);
+            }
           }
           if (++sa == (uint32_t)sh.stages_a) { sa = 0; pa ^= 1u; }
         }
@@ -283,9 +311,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
             const uint32_t fw = smem_u32(&full_w[sw]);
             const uint32_t dst = smem_u32(w_base + (size_t)sw * sh.w_tile_bytes);
             if (leader) {
-              mbar_expect_tx(fw, sh.w_tile_bytes);
-              for (int j = 0; j < sh.n_umma; ++j)
-                tma_load_2d(dst + (uint32_t)j * sh.umma_n * TC_BK * 2, &map_w, fw, kk, tap * sh.N + n0 + j * sh.umma_n);
+              if (kPAIR) {   // each CTA of the pair loads its half of the N rows of every MMA's B operand
+                const int hn = sh.umma_n >> 1;
+                if (cta_rank == 0) mbar_expect_tx(fw, 2 * sh.w_tile_bytes);
+                for (int j = 0; j < sh.n_umma; ++j)
+                  tma_load_2d_pair(dst + (uint32_t)j * hn * TC_BK * 2, &map_w, fw, kk, tap * sh.N + n0 + j * sh.umma_n + (int)cta_rank * hn);
+              } else {
+                mbar_expect_tx(fw, sh.w_tile_bytes);
+                for (int j = 0; j < sh.n_umma; ++j)
+                  tma_load_2d(dst + (uint32_t)j * sh.umma_n * TC_BK * 2, &map_w, fw, kk, tap * sh.N + n0 + j * sh.umma_n);
+              }
             }
             if (++sw == (uint32_t)sh.stages_w) { sw = 0; pw ^= 1u; }
           }
@@ -304,14 +339,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     }
     const uint32_t a_ring_addr = smem_u32(a_ring), w_addr = smem_u32(w_base);
 #define DHG_MMA_LOOP(TAPS, GG)                                                                                          \
-  mma_issue_loop<TAPS, GG>(sh, leader, tmem_base, a_ring_addr, w_addr, full_a, empty_a, full_w, empty_w, tmem_full_bar, \
+  mma_issue_loop<TAPS, GG, false>(sh, leader, tmem_base, a_ring_addr, w_addr, full_a, empty_a, full_w, empty_w, tmem_full_bar, \
                            tmem_empty_bar, t_first, t_end, t_step, tr_n, tr_role, lane)
-    if (sh.taps == 3) {
+#define DHG_MMA_LOOP_PAIR(TAPS)                                                                                         \
+  mma_issue_loop<TAPS, 1, true>(sh, leader, tmem_base, a_ring_addr, w_addr, full_a, empty_a, full_w, empty_w, tmem_full_bar, \
+                           tmem_empty_bar, t_first, t_end, t_step, tr_n, tr_role, lane)
+    if (kPAIR) {
+      if (cta_rank == 0) {   // rank 0 issues for both CTAs
+        if (sh.taps == 3) DHG_MMA_LOOP_PAIR(3); else DHG_MMA_LOOP_PAIR(1);
+      }
+    } else if (sh.taps == 3) {
       if (sh.G == 4) DHG_MMA_LOOP(3, 4); else if (sh.G == 2) DHG_MMA_LOOP(3, 2); else DHG_MMA_LOOP(3, 1);
     } else {
       if (sh.G == 4) DHG_MMA_LOOP(1, 4); else if (sh.G == 2) DHG_MMA_LOOP(1, 2); else DHG_MMA_LOOP(1, 1);
     }
 #undef DHG_MMA_LOOP
+#undef DHG_MMA_LOOP_PAIR
   } else {
     // ===== epilogue warps; warp (q, part): TMEM lanes [32q, 32q+32), one contiguous part of the column chunks =====
     asm volatile("griddepcontrol.wait;" ::: "memory");   // residual rows are read / outputs written only after the previous kernel
@@ -358,7 +401,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         if (ci == 0) {   // first chunk of a row tile: where does my row's residual / bias row live?
           const int fmts = sh.sticky ? ft : ft / sh.n_groups;
           iss_ng = sh.sticky ? my_group : ft - fmts * sh.n_groups;
-          const int fm = (fmts * sh.G + fsub) * TC_BM + r_tile;
+          const int fm = (fmts * tiles_per_super + fsub + (int)cta_rank) * TC_BM + r_tile;
           const bool f_in = fm < sh.rows;
           if (aux_kind == AUX_RES_PRE || aux_kind == AUX_RES_POST) {
             iss_src = f_in ? fm : -1;
@@ -424,7 +467,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
      tc_fence_after();
      if (ew == 0) DHG_TR(0x31, it);
      for (int sub = 0; sub < sh.G; ++sub, ++tile_no) {
-      const int m0 = (mts * sh.G + sub) * TC_BM;
+      const int m0 = (mts * tiles_per_super + sub + (int)cta_rank) * TC_BM;
       const bool last_sub = sub == sh.G - 1;
       const uint32_t trow = tmem_base + (uint32_t)as * 256u + (uint32_t)(sub * sh.BN) + lane_sel;
 
@@ -526,7 +569,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       if (my_nch == 0 && last_sub) {   // no column chunk for this warp in this tile shape: just release the accumulators
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+        if (lane == 0) { if (cta_rank) mbar_arrive_remote(smem_u32(&tmem_empty_bar[as]), 0); else mbar_arrive(smem_u32(&tmem_empty_bar[as])); }
       }
       for (int ci = 0; ci < my_nch; ++ci) {
         const int c = c_lo + ci;
@@ -537,7 +580,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         if (ci == my_nch - 1 && last_sub) {   // my last TMEM read of this super-tile: hand the accumulators back
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[as]));
+          if (lane == 0) { if (cta_rank) mbar_arrive_remote(smem_u32(&tmem_empty_bar[as]), 0); else mbar_arrive(smem_u32(&tmem_empty_bar[as])); }
         }
         if (ln) {
 #pragma unroll
@@ -585,26 +628,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if (kPAIR) cluster_sync_all();   // the peer may still be signalling my barriers / reading my smem through the MMA
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    if (kPAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
   }
 }
 
 }  // namespace
 
 // experiment switches (dhg_set_option: "w_resident", "specialize", "interleave")
-int g_opt_w_resident = 1, g_opt_specialize = 1, g_opt_interleave = 1, g_opt_pdl = 1;
+int g_opt_w_resident = 1, g_opt_specialize = 1, g_opt_interleave = 1, g_opt_pdl = 1, g_opt_pair = 1;
 void tc_gemm_set_option(int which, int value) {
   if (which == 2) g_opt_w_resident = value;
   else if (which == 4) g_opt_interleave = value;
   else if (which == 6) g_opt_pdl = value;
+  else if (which == 7) g_opt_pair = value;
   else if (which == 3) g_opt_specialize = value;
 }
 
 typedef void (*TcKernFn)(const CUtensorMap, const CUtensorMap, const TcShape, const Epilogue);
-struct TcKernEntry { int ln, aux, film, out; TcKernFn fn; };
-#define DHG_TC_K(ln, aux, film, out) {ln, aux, film, out, tc_gemm_kernel<ln, aux, film, out>}
+struct TcKernEntry { int ln, aux, film, out; TcKernFn fn, fn_pair; };   // fn_pair: the cta_group::2 build (cluster launch only)
+#define DHG_TC_K(ln, aux, film, out) {ln, aux, film, out, tc_gemm_kernel<ln, aux, film, out, false>, tc_gemm_kernel<ln, aux, film, out, true>}
 // Every epilogue variant the denoiser plan uses (engine.cu), film = 1 (sampling: one FiLM vector per step);
 // anything else (per-sample FiLM in dhg_denoise, test-only combinations) runs the generic instance.
 static const TcKernEntry kTcKernels[] = {
@@ -623,13 +671,13 @@ static const TcKernEntry kTcKernels[] = {
     DHG_TC_K(1, AUX_RES_PRE, 1, 2),       // text-style mha.dense
     DHG_TC_K(-1, -1, -1, -1),             // generic
 };
-static TcKernFn pick_kernel(int ln, int aux, int film, int out) {
+static TcKernFn pick_kernel(int ln, int aux, int film, int out, bool pair) {
   const int n = (int)(sizeof(kTcKernels) / sizeof(kTcKernels[0]));
   if (g_opt_specialize)
     for (int i = 0; i < n - 1; ++i)
       if (kTcKernels[i].ln == ln && kTcKernels[i].aux == aux && kTcKernels[i].film == film && kTcKernels[i].out == out)
-        return kTcKernels[i].fn;
-  return kTcKernels[n - 1].fn;
+        return pair ? kTcKernels[i].fn_pair : kTcKernels[i].fn;
+  return pair ? kTcKernels[n - 1].fn_pair : kTcKernels[n - 1].fn;
 }
 
 struct TcGemmPlan {
@@ -707,6 +755,19 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   const int min_a = G > 1 ? 2 * G : 3;
   sh.w_resident = (g_opt_w_resident && w_all + (size_t)min_a * sh.a_stage_bytes <= budget && sh.m_super * sh.n_groups > num_sms) ? 1 : 0;
   sh.sticky = (sh.w_resident && sh.n_groups > 1) ? 1 : 0;
+  // W does not fit: pair the CTAs of a cluster (cta_group::2) so that each SM only ingests half of every W tile
+  // Measured (profiles/): pairing pays when the MMA / W-stream phase dominates the tile (K*taps >= 512 and a light
+  // epilogue, or the single-buffered 384-wide LayerNorm rows); with g_opt_pair == 2 every non-resident GEMM is paired.
+  const int out_mode_plan = (e.out_raw ? 1 : 0) | (e.out_act ? 2 : 0);
+  const bool pair_pays = BN == 384 || (taps * K >= 512 && out_mode_plan != 3 && !(e.ln && N <= 192));
+  sh.pair = (!sh.w_resident && g_opt_pair && (g_opt_pair == 2 || pair_pays) && G == 1 && sh.umma_n % 16 == 0 &&
+             (m_tiles + 1) / 2 * sh.n_groups >= num_sms / 2) ? 1 : 0;
+  if (sh.pair) {
+    sh.m_super = (m_tiles + 1) / 2;
+    sh.w_tile_bytes = (uint32_t)(BN / 2) * TC_BK * 2;
+    // idesc: M = 256 across the pair
+    sh.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(sh.umma_n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  }
   size_t w_bytes;
   if (sh.w_resident) {
     int sa = (int)((budget - w_all) / sh.a_stage_bytes);
@@ -735,6 +796,10 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   sh.off_bar = off; off += 64 * 8;
   p->smem = off + 1024;
   int grid = sh.m_super * sh.n_groups < num_sms ? sh.m_super * sh.n_groups : num_sms;
+  if (sh.pair) {
+    const int pairs = sh.m_super * sh.n_groups < num_sms / 2 ? sh.m_super * sh.n_groups : num_sms / 2;
+    grid = 2 * pairs;
+  }
   if (sh.sticky) {
     if (sh.n_groups > 12) { snprintf(err, errlen, "too many column groups"); delete p; return nullptr; }
     // CTAs per group in proportion to the estimated per-tile epilogue cost (groups with per-position bias rows: 1.35)
@@ -752,13 +817,13 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   }
   p->grid = dim3(grid);
   if (!make_map(&p->map_a, A, (uint64_t)rows, (uint64_t)K, (uint64_t)lda, (uint32_t)a_rows, err, errlen) ||
-      !make_map(&p->map_w, W, (uint64_t)taps * N, (uint64_t)K, (uint64_t)K, (uint32_t)sh.umma_n, err, errlen)) {
+      !make_map(&p->map_w, W, (uint64_t)taps * N, (uint64_t)K, (uint64_t)K, (uint32_t)(sh.pair ? sh.umma_n / 2 : sh.umma_n), err, errlen)) {
     delete p;
     return nullptr;
   }
   const int out_mode = (e.out_raw ? 1 : 0) | (e.out_act ? 2 : 0);
-  p->fn_shared = pick_kernel(e.ln ? 1 : 0, aux_kind, e.film_planned ? 1 : 0, out_mode);
-  p->fn_generic = pick_kernel(-1, -1, -1, -1);
+  p->fn_shared = pick_kernel(e.ln ? 1 : 0, aux_kind, e.film_planned ? 1 : 0, out_mode, sh.pair != 0);
+  p->fn_generic = pick_kernel(-1, -1, -1, -1, sh.pair != 0);
   for (TcKernFn fn : {p->fn_shared, p->fn_generic}) {
     cudaError_t ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (ce != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); delete p; return nullptr; }
@@ -769,7 +834,7 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
 void tc_gemm_plan_destroy(TcGemmPlan* p) { delete p; }
 void tc_gemm_set_trace(TcGemmPlan* p, unsigned long long* buf, int cap) { p->sh.trace = buf; p->sh.trace_cap = cap; }
 void tc_gemm_describe(const TcGemmPlan* p, char* out, int n) {
-  snprintf(out, n, "BN=%d groups=%d m_tiles=%d G=%d stages_a=%d stages_w=%d resident=%d sticky=%d acc_stages=%d grid=%d smem=%zu", p->sh.BN, p->sh.n_groups,
+  snprintf(out, n, "pair=%d BN=%d groups=%d m_tiles=%d G=%d stages_a=%d stages_w=%d resident=%d sticky=%d acc_stages=%d grid=%d smem=%zu", p->sh.pair, p->sh.BN, p->sh.n_groups,
            p->sh.m_tiles, p->sh.G, p->sh.stages_a, p->sh.stages_w, p->sh.w_resident, p->sh.sticky, p->sh.acc_stages, (int)p->grid.x, p->smem);
 }
 
@@ -782,11 +847,22 @@ int tc_gemm_launch(const TcGemmPlan* p, const Epilogue& e, cudaStream_t st) {
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = p->smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (g_opt_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (p->sh.pair) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = g_opt_pdl ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, fn, p->map_a, p->map_w, p->sh, e) == cudaSuccess ? 0 : 1;
 }
 
