@@ -42,7 +42,7 @@ constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int AUX_DEPTH = 8 / EPI_PARTS;              // aux ring slots per epilogue warp
 constexpr int AUX_SLOT_BYTES = 2048;                  // 32 rows x 32 bf16
 constexpr int AUX_RING_BYTES = AUX_DEPTH * AUX_SLOT_BYTES;
-constexpr int OUT_STAGE_BYTES = 2048;  // per epilogue warp: 32 rows x 32 bf16
+constexpr int OUT_STAGE_BYTES = 4096;  // per epilogue warp: 2 x (32 rows x 32 bf16), alternating between TMA stores
 constexpr int TMEM_COLS = 512;
 
 enum { AUX_NONE = 0, AUX_RES_PRE = 1, AUX_RES_POST = 2, AUX_RES_POST_UP = 3, AUX_ROWBIAS = 4 };
@@ -57,6 +57,7 @@ struct TcShape {
   int stages_a, stages_w;   // A ring / W ring depth (W ring unused when w_resident)
   int w_resident;  // all W tiles of this CTA's column group stay in smem for the whole kernel
   int sticky;      // each CTA works on one column group only
+  int out_bufs;    // staging tiles per epilogue warp for the TMA stores (2, or 1 when shared memory is tight)
   int pair;        // cta_group::2: the two CTAs of a cluster share every MMA (M = 256: 128 rows each) and each loads half of W
   int grp_cta0[13];   // sticky: first CTA of each column group (n_groups + 1 entries)
   int kb_per_tap;  // ceil(K / 64)
@@ -181,6 +182,8 @@ __device__ __forceinline__ void mma_issue_loop(const TcShape& sh, const bool lea
 template <int kLN, int kAUX, int kFILM, int kOUT, bool kPAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_w,
+                                                                const __grid_constant__ CUtensorMap map_oraw,
+                                                                const __grid_constant__ CUtensorMap map_oact,
                                                                 const TcShape sh, const Epilogue e) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -226,6 +229,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_oraw)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_oact)) : "memory");
     for (int s = 0; s < 8; ++s) {
       mbar_init(smem_u32(&full_a[s]), 1);
       mbar_init(smem_u32(&empty_a[s]), 1);
@@ -369,7 +374,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     const int c_hi = ((part + 1) * nch) / EPI_PARTS;
     const int my_nch = c_hi - c_lo;
     const uint32_t aux_ring = smem_u32(smem + sh.off_aux + (size_t)ew * AUX_RING_BYTES);
-    const uint32_t out_st = smem_u32(smem + sh.off_out + (size_t)ew * OUT_STAGE_BYTES);
+    const uint32_t out_st = smem_u32(smem + sh.off_out + (size_t)ew * (sh.out_bufs == 2 ? OUT_STAGE_BYTES : OUT_STAGE_BYTES / 2));
     const uint32_t bias_sa = smem_u32(bias_s), gamma_sa = smem_u32(gamma_s), betap_sa = smem_u32(betap_s);
     float2* ln_s = reinterpret_cast<float2*>(smem + sh.off_ln);   // [2 parity][128 rows][EPI_PARTS] {mean, M2} of each column part
     const int aux_ncols = aux_kind == AUX_ROWBIAS ? e.rowbias16_cols : 0x7fffffff;   // aux only for columns below this
@@ -385,13 +390,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     const uint32_t lane_sel = ((uint32_t)(q * 32)) << 16;
     // swizzled staging offsets: thread-per-row side (my row = lane) and coalesced side (4 lanes per row)
     const uint32_t st_row = (uint32_t)lane * 64u, st_sw = (uint32_t)((lane >> 1) & 3);
-    const uint32_t co_rr = (uint32_t)(lane >> 2), co_piece = (uint32_t)(lane & 3);
     const int period = e.map.period, pad_first = e.map.pad_first, nvalid = e.map.nvalid;
 
     // aux rows are prefetched as one flat sequence of 32x32 chunks across tiles (tile it, chunk ci) ->
     // flat index it * my_nch + ci, ring slot = flat % depth, so the loads for the next tile are already in
     // flight while this tile is being finished.
-    uint32_t aux_issued = 0, aux_consumed = 0;
+    uint32_t aux_issued = 0, aux_consumed = 0, st_flip = 0;
     int iss_t = t_first, iss_sub = 0, iss_ci = 0;   // (super-tile, row tile, chunk) of the next flat chunk to issue
     int iss_src = -1, iss_ng = 0;                   // cached per issue tile: my row's source row, the column group
     auto issue_aux_flat = [&]() {
@@ -479,12 +483,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       const int j = mm - b * period;
       const bool is_pad = (mm >= nvalid) || (pad_first && j == 0);
       const bool live = in_range && !is_pad;
-      // coalesced side: my 4 (row, 16-byte piece) slots of a 32-row x 32-column chunk
-      const int co_rows_left = sh.rows - (m0 + q * 32);     // rows of this warp's slab that exist
-      const size_t co_row0 = (size_t)(m0 + q * 32) + co_rr;
 
-      // bf16 store of my 32 values through the swizzled staging tile: coalesced 16-byte global stores
-      auto store_chunk = [&](void* gout, int pitch, int col0, const float* v, bool act) {
+      // bf16 store of my 32 values: thread-per-row into the SWIZZLE_64B staging tile, then ONE TMA store of the
+      // [32 rows x 32 columns] chunk (rows past the end of the matrix are clipped by the tensor map)
+      auto store_chunk = [&](const CUtensorMap* omap, int col0, const float* v, bool act) {
+        const uint32_t buf = out_st + ((st_flip && sh.out_bufs == 2) ? 2048u : 0u);
+        st_flip ^= 1u;
+        if (lane == 0) {   // the store that last read this buffer is done with it
+          if (sh.out_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+        }
+        __syncwarp();
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
           uint32_t w[4];
@@ -494,20 +502,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
             if (act) { a = silu_fast(a); c = silu_fast(c); }
             w[k2] = pack_bf16x2(a, c);
           }
-          sts128(out_st + st_row + ((p ^ st_sw) << 4), make_uint4(w[0], w[1], w[2], w[3]));
+          sts128(buf + st_row + ((p ^ st_sw) << 4), make_uint4(w[0], w[1], w[2], w[3]));
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // my generic-proxy writes -> visible to the TMA engine
         __syncwarp();
-        uint4 d[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t rr = (uint32_t)i * 8u + co_rr;
-          d[i] = lds128_v(out_st + rr * 64u + ((co_piece ^ ((rr >> 1) & 3u)) << 4));
+        if (lane == 0) {
+          tma_store_2d(omap, buf, col0, m0 + q * 32);
+          bulk_commit();
         }
-        bf16* gp = reinterpret_cast<bf16*>(gout) + co_row0 * (size_t)pitch + col0 + co_piece * 8;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if ((int)(i * 8 + co_rr) < co_rows_left) *reinterpret_cast<uint4*>(gp + (size_t)i * 8 * pitch) = d[i];
-        __syncwarp();
       };
 
       float v[32];
@@ -618,13 +620,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
         if (ew == 0) DHG_TR(0x35, ci);
-        if (out_mode & 1) store_chunk(e.out_raw, e.out_raw_pitch, n, v, false);
-        if (out_mode & 2) store_chunk(e.out_act, e.out_act_pitch, n, v, true);
+        if (out_mode & 1) store_chunk(&map_oraw, n, v, false);
+        if (out_mode & 2) store_chunk(&map_oact, n, v, true);
       }
      }
      if (ew == 0) DHG_TR(0x32, it);
     }
     if (aux_active) cp_async_wait<0>();
+    if (lane == 0) bulk_wait<0>();   // all my output tiles have left shared memory and are written
   }
   tc_fence_before();
   __syncthreads();
@@ -650,7 +653,7 @@ void tc_gemm_set_option(int which, int value) {
   else if (which == 3) g_opt_specialize = value;
 }
 
-typedef void (*TcKernFn)(const CUtensorMap, const CUtensorMap, const TcShape, const Epilogue);
+typedef void (*TcKernFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcShape, const Epilogue);
 struct TcKernEntry { int ln, aux, film, out; TcKernFn fn, fn_pair; };   // fn_pair: the cta_group::2 build (cluster launch only)
 #define DHG_TC_K(ln, aux, film, out) {ln, aux, film, out, tc_gemm_kernel<ln, aux, film, out, false>, tc_gemm_kernel<ln, aux, film, out, true>}
 // Every epilogue variant the denoiser plan uses (engine.cu), film = 1 (sampling: one FiLM vector per step);
@@ -681,7 +684,7 @@ static TcKernFn pick_kernel(int ln, int aux, int film, int out, bool pair) {
 }
 
 struct TcGemmPlan {
-  CUtensorMap map_a, map_w;
+  CUtensorMap map_a, map_w, map_oraw, map_oact;
   TcShape sh;
   dim3 grid;
   size_t smem;
@@ -748,9 +751,15 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   sh.a_stage_bytes = (sh.a_tx_bytes + 1023u) & ~1023u;
   sh.w_tile_bytes = (uint32_t)BN * TC_BK * 2;
   // smem carve-up: A ring | W ring or resident W | aux rings | out staging | vectors | LN exchange | barriers
-  const size_t fixed = (aux_kind != AUX_NONE ? (size_t)EPI_WARPS * AUX_RING_BYTES : 0) + (size_t)EPI_WARPS * OUT_STAGE_BYTES +
-                       (size_t)(sh.vec_bias_n + 2 * sh.film_n) * 4 + 16 + (e.ln ? 2 * TC_BM * EPI_PARTS * 8 : 0) + 64 * 8;
-  const size_t budget = 227 * 1024 - 1024 - fixed;
+  size_t fixed = (aux_kind != AUX_NONE ? (size_t)EPI_WARPS * AUX_RING_BYTES : 0) + (size_t)EPI_WARPS * OUT_STAGE_BYTES +
+                 (size_t)(sh.vec_bias_n + 2 * sh.film_n) * 4 + 16 + (e.ln ? 2 * TC_BM * EPI_PARTS * 8 : 0) + 64 * 8;
+  size_t budget = 227 * 1024 - 1024 - fixed;
+  sh.out_bufs = 2;
+  if (2 * (size_t)(sh.a_stage_bytes + BN * TC_BK * 2) > budget) {   // not even two A + two W stages: give up the second store tile
+    sh.out_bufs = 1;
+    fixed -= (size_t)EPI_WARPS * OUT_STAGE_BYTES / 2;
+    budget += (size_t)EPI_WARPS * OUT_STAGE_BYTES / 2;
+  }
   const size_t w_all = (size_t)taps * sh.kb_per_tap * sh.w_tile_bytes;
   const int min_a = G > 1 ? 2 * G : 3;
   sh.w_resident = (g_opt_w_resident && w_all + (size_t)min_a * sh.a_stage_bytes <= budget && sh.m_super * sh.n_groups > num_sms) ? 1 : 0;
@@ -789,7 +798,7 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   uint32_t off = (uint32_t)sh.stages_a * sh.a_stage_bytes;
   sh.off_w = off; off += (uint32_t)w_bytes;
   sh.off_aux = off; off += aux_kind != AUX_NONE ? EPI_WARPS * AUX_RING_BYTES : 0;
-  sh.off_out = off; off += EPI_WARPS * OUT_STAGE_BYTES;
+  sh.off_out = off; off += EPI_WARPS * OUT_STAGE_BYTES / (sh.out_bufs == 2 ? 1 : 2);
   sh.off_vec = off; off += (uint32_t)(sh.vec_bias_n + 2 * sh.film_n) * 4;
   off = (off + 15u) & ~15u;
   sh.off_ln = off; off += e.ln ? 2 * TC_BM * EPI_PARTS * 8 : 0;
@@ -818,6 +827,13 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   p->grid = dim3(grid);
   if (!make_map(&p->map_a, A, (uint64_t)rows, (uint64_t)K, (uint64_t)lda, (uint32_t)a_rows, err, errlen) ||
       !make_map(&p->map_w, W, (uint64_t)taps * N, (uint64_t)K, (uint64_t)K, (uint32_t)(sh.pair ? sh.umma_n / 2 : sh.umma_n), err, errlen)) {
+    delete p;
+    return nullptr;
+  }
+  // output tensor maps: [32 rows x 32 columns] SWIZZLE_64B boxes for the epilogue's TMA stores
+  p->map_oraw = p->map_a; p->map_oact = p->map_a;   // placeholders for absent outputs (never used)
+  if ((e.out_raw && !make_map(&p->map_oraw, e.out_raw, (uint64_t)rows, (uint64_t)N, (uint64_t)e.out_raw_pitch, 32, err, errlen, 32)) ||
+      (e.out_act && !make_map(&p->map_oact, e.out_act, (uint64_t)rows, (uint64_t)N, (uint64_t)e.out_act_pitch, 32, err, errlen, 32))) {
     delete p;
     return nullptr;
   }
@@ -863,7 +879,7 @@ int tc_gemm_launch(const TcGemmPlan* p, const Epilogue& e, cudaStream_t st) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, fn, p->map_a, p->map_w, p->sh, e) == cudaSuccess ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, fn, p->map_a, p->map_w, p->map_oraw, p->map_oact, p->sh, e) == cudaSuccess ? 0 : 1;
 }
 
 }  // namespace dhg

@@ -106,6 +106,17 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) 
       ::"r"(bar), "r"(rank) : "memory");
 }
 
+// TMA store of a [box] tile from shared to global memory (bulk async group of the issuing thread)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
 }
@@ -243,16 +254,18 @@ inline EncodeTiledFn get_encode() {
 }
 
 // 2D bf16 row-major tensor [rows, cols] with row pitch `pitch` elements; box = [box_rows, 64 cols], SWIZZLE_128B.
-inline bool make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows, char* err, int errlen) {
+// box = [box_rows, box_cols]; box_cols = 64 -> SWIZZLE_128B (operand tiles), 32 -> SWIZZLE_64B (epilogue store tiles)
+inline bool make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows, char* err, int errlen,
+                     uint32_t box_cols = TC_BK) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { snprintf(err, errlen, "cuTensorMapEncodeTiled entry point not available"); return false; }
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {pitch * 2};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(err, errlen, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu pitch=%llu box_rows=%u", (int)r,
              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch, box_rows);
