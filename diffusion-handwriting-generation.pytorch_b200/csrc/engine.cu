@@ -958,7 +958,7 @@ int32_t dhg_plan(dhg_ctx* c, int32_t B, int32_t T, int32_t L, int32_t S, int32_t
   if (B < 1 || L < 1 || S < 1) return fail("dhg_plan: B, L, S must be >= 1");
   if (T < 8 || T % 8) return fail("dhg_plan: T must be a positive multiple of 8 (inference.py:78); got %d", T);
   if (precision != DHG_PREC_FP32 && precision != DHG_PREC_BF16) return fail("dhg_plan: bad precision %d", precision);
-  if ((long long)B * (T + 1) + 1 > 0x7fffffffLL / 4) return fail("dhg_plan: B*T too large for one chunk; plan a smaller B and let dhg_sample chunk");
+  if ((long long)B * (T + 1) + 1 >= (1LL << 24)) return fail("dhg_plan: B*T too large for one chunk (needs B*(T+1) < 2^24 rows); plan a smaller B and let dhg_sample chunk");
   CUDA_OK(cudaSetDevice(c->device));
   CUDA_OK(cudaDeviceSynchronize());
   free_plan(c->plan);

@@ -82,6 +82,15 @@ struct TcShape {
           ((unsigned long long)clock64() << 16) | ((unsigned long long)(code) << 8) | (unsigned)((tile) & 0xff); \
   } while (0)
 
+// m / period and m % period for 0 <= m < 2^24 (checked at plan time) without the ~40-instruction integer division:
+// float estimate, exact after one correction step either way.
+__device__ __forceinline__ void fast_divmod(int m, int period, float inv_period, int& q, int& r) {
+  q = __float2int_rz(__int2float_rz(m) * inv_period);
+  r = m - q * period;
+  if (r < 0) { r += period; --q; }
+  if (r >= period) { r -= period; ++q; }
+}
+
 // The MMA warp's main loop, specialised on the tap count and on the number of interleaved accumulators so that
 // everything inside a k-block is straight-line code (the single issuing warp is latency-critical: every
 // instruction between two tcgen05.mma shows up in the tile time).
@@ -367,7 +376,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     const int aux_kind = kAUX >= 0 ? kAUX : sh.aux_kind;
     const int film_mode = kFILM >= 0 ? kFILM : (film ? (film_s ? 1 : 2) : 0);
     const int out_mode = kOUT >= 0 ? kOUT : ((e.out_raw ? 1 : 0) | (e.out_act ? 2 : 0));
-    const bool has_bias = sh.vec_bias_n > 0;
+    const bool has_bias = kLN >= 0 ? true : sh.vec_bias_n > 0;   // every specialised variant has a bias vector (checked at plan time)
     const int ew = warp - 2, q = warp & 3, part = ew >> 2;
     const int nch = sh.BN >> 5;
     const int c_lo = (part * nch) / EPI_PARTS;          // my contiguous range of 32-column chunks (may be empty)
@@ -391,6 +400,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     // swizzled staging offsets: thread-per-row side (my row = lane) and coalesced side (4 lanes per row)
     const uint32_t st_row = (uint32_t)lane * 64u, st_sw = (uint32_t)((lane >> 1) & 3);
     const int period = e.map.period, pad_first = e.map.pad_first, nvalid = e.map.nvalid;
+    const float inv_period = 1.0f / (float)period;
 
     // aux rows are prefetched as one flat sequence of 32x32 chunks across tiles (tile it, chunk ci) ->
     // flat index it * my_nch + ci, ring slot = flat % depth, so the loads for the next tile are already in
@@ -411,8 +421,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
             iss_src = f_in ? fm : -1;
           } else {
             const int fmm = f_in ? fm : 0;
-            const int fb = fmm / period;
-            const int fj = fmm - fb * period;
+            int fb, fj;
+            fast_divmod(fmm, period, inv_period, fb, fj);
             const bool f_pad = (fmm >= nvalid) || (pad_first && fj == 0);
             const int fpos = f_pad ? 0 : fj - pad_first;
             const bool f_live = f_in && !f_pad;
@@ -479,8 +489,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       const int m = m0 + r_tile;
       const bool in_range = m < sh.rows;
       const int mm = in_range ? m : 0;
-      const int b = mm / period;
-      const int j = mm - b * period;
+      int b, j;
+      fast_divmod(mm, period, inv_period, b, j);
       const bool is_pad = (mm >= nvalid) || (pad_first && j == 0);
       const bool live = in_range && !is_pad;
 
@@ -576,9 +586,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       for (int ci = 0; ci < my_nch; ++ci) {
         const int c = c_lo + ci;
         const int n = n0 + c * 32;
-        if (ew == 0) DHG_TR(0x33, ci);
         tmem_ld32(trow + c * 32, v);
-        if (ew == 0) DHG_TR(0x34, ci);
         if (ci == my_nch - 1 && last_sub) {   // my last TMEM read of this super-tile: hand the accumulators back
           tc_fence_before();
           __syncwarp();
@@ -619,7 +627,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
-        if (ew == 0) DHG_TR(0x35, ci);
         if (out_mode & 1) store_chunk(&map_oraw, n, v, false);
         if (out_mode & 2) store_chunk(&map_oact, n, v, true);
       }
@@ -694,6 +701,7 @@ struct TcGemmPlan {
 
 TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W, int K, int N, int taps, const Epilogue& e,
                                 char* err, int errlen) {
+  if (rows >= (1 << 24)) { snprintf(err, errlen, "rows = %d: the epilogue's row arithmetic needs rows < 2^24 (plan a smaller chunk)", rows); return nullptr; }
   if (rows <= 0 || K % 8 || N % 32 || (taps != 1 && taps != 3)) {
     snprintf(err, errlen, "unsupported shape rows=%d K=%d N=%d taps=%d", rows, K, N, taps);
     return nullptr;
@@ -838,7 +846,8 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
     return nullptr;
   }
   const int out_mode = (e.out_raw ? 1 : 0) | (e.out_act ? 2 : 0);
-  p->fn_shared = pick_kernel(e.ln ? 1 : 0, aux_kind, e.film_planned ? 1 : 0, out_mode, sh.pair != 0);
+  p->fn_shared = e.bias ? pick_kernel(e.ln ? 1 : 0, aux_kind, e.film_planned ? 1 : 0, out_mode, sh.pair != 0)
+                        : pick_kernel(-1, -1, -1, -1, sh.pair != 0);   // the specialised variants assume a bias vector
   p->fn_generic = pick_kernel(-1, -1, -1, -1, sh.pair != 0);
   for (TcKernFn fn : {p->fn_shared, p->fn_generic}) {
     cudaError_t ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
