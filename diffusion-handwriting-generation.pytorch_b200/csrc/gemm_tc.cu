@@ -408,6 +408,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     uint32_t aux_issued = 0, aux_consumed = 0, st_flip = 0;
     int iss_t = t_first, iss_sub = 0, iss_ci = 0;   // (super-tile, row tile, chunk) of the next flat chunk to issue
     int iss_src = -1, iss_ng = 0;                   // cached per issue tile: my row's source row, the column group
+    int iss_row0 = 0;                               //   and (same-row residuals) the first row of my 32-row slab
+    const bool aux_same_row = aux_kind == AUX_RES_PRE || aux_kind == AUX_RES_POST;
+    const bool aux_col_limited = aux_kind == AUX_ROWBIAS;
     auto issue_aux_flat = [&]() {
       const uint32_t f = aux_issued++;
       const int ft = iss_t, fsub = iss_sub, ci = iss_ci;
@@ -417,8 +420,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
           iss_ng = sh.sticky ? my_group : ft - fmts * sh.n_groups;
           const int fm = (fmts * tiles_per_super + fsub + (int)cta_rank) * TC_BM + r_tile;
           const bool f_in = fm < sh.rows;
-          if (aux_kind == AUX_RES_PRE || aux_kind == AUX_RES_POST) {
-            iss_src = f_in ? fm : -1;
+          if (aux_same_row) {
+            iss_row0 = fm - lane;
           } else {
             const int fmm = f_in ? fm : 0;
             int fb, fj;
@@ -433,7 +436,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         const int aux_src = iss_src, fng = iss_ng;
         const int col0 = fng * sh.BN + (c_lo + ci) * 32;
         const uint32_t slot = aux_ring + (f % (uint32_t)aux_depth) * aux_slot_bytes;
-        if (col0 < aux_ncols) {
+        if (aux_same_row) {   // residual rows = my own rows: lane -> (row, 16-byte piece) directly
+          const char* gp0 = aux_base + (size_t)col0 * 2 + (lane & 3) * 16;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = i * 8 + (lane >> 2);
+            const int src = iss_row0 + rr;
+            const bool ok = src < sh.rows;
+            cp_async16(slot + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4), gp0 + (size_t)(ok ? src : 0) * aux_pitch_bytes, ok ? 16u : 0u);
+          }
+        } else if (!aux_col_limited || col0 < aux_ncols) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int rr = i * 8 + (lane >> 2), piece = lane & 3;
@@ -455,7 +467,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       __syncwarp();
       const uint32_t slot = aux_ring + (aux_consumed % (uint32_t)aux_depth) * aux_slot_bytes;
       ++aux_consumed;
-      if (col0 < aux_ncols) {
+      if (!aux_col_limited || col0 < aux_ncols) {
         uint4 u[4];
 #pragma unroll
         for (int p = 0; p < 4; ++p) u[p] = lds128_v(slot + st_row + ((p ^ st_sw) << 4));
@@ -496,13 +508,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 
       // bf16 store of my 32 values: thread-per-row into the SWIZZLE_64B staging tile, then ONE TMA store of the
       // [32 rows x 32 columns] chunk (rows past the end of the matrix are clipped by the tensor map)
-      auto store_chunk = [&](const CUtensorMap* omap, int col0, const float* v, bool act) {
+      // Buffer reuse: right after committing store k, lane 0 waits until store k-1 has been read out of its buffer
+      // (the buffer store k+1 will use); the other lanes learn about it through the next warp barrier they pass:
+      // the one in front of the next chunk's tcgen05.ld, or `sync_first` for a second store of the same chunk.
+      auto store_chunk = [&](const CUtensorMap* omap, int col0, const float* v, bool act, bool sync_first) {
         const uint32_t buf = out_st + ((st_flip && sh.out_bufs == 2) ? 2048u : 0u);
         st_flip ^= 1u;
-        if (lane == 0) {   // the store that last read this buffer is done with it
-          if (sh.out_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
-        }
-        __syncwarp();
+        if (sync_first) __syncwarp();
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
           uint32_t w[4];
@@ -519,6 +531,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         if (lane == 0) {
           tma_store_2d(omap, buf, col0, m0 + q * 32);
           bulk_commit();
+          if (sh.out_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
         }
       };
 
@@ -627,8 +640,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
-        if (out_mode & 1) store_chunk(&map_oraw, n, v, false);
-        if (out_mode & 2) store_chunk(&map_oact, n, v, true);
+        if (out_mode & 1) store_chunk(&map_oraw, n, v, false, false);
+        if (out_mode & 2) store_chunk(&map_oact, n, v, true, (out_mode & 1) != 0);
       }
      }
      if (ew == 0) DHG_TR(0x32, it);
