@@ -170,18 +170,29 @@ __global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __
         }
         mbar_wait(smem_u32(&sb[1]), par);
         tc_fence_after();
-        // pass 1: row maximum of scale*s + mask (log2 units); keys >= Tk never count
+        // pass 1: row maximum (log2 units); keys >= Tk never count.  Unmasked: max over the raw scores, scaled once
+        // (scale > 0); only the last chunk can contain padding keys.
+        const int c_full = p.Tk >> 5;   // chunks [0, c_full) hold real keys only
         float mx = (sh.dbg & 1) ? 0.f : -INFINITY;
         for (int c = c_lo; c < ((sh.dbg & 1) ? c_lo : c_hi); ++c) {
           tmem_ld32(trow + c * 32, v);
+          if (masked) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int j = c * 32 + i;
-            float t = v[i] * sh.scale_log2;
-            if (masked) t += mask_s[j];
-            if (j < p.Tk) mx = fmaxf(mx, t);
+            for (int i = 0; i < 32; ++i) {
+              const int j = c * 32 + i;
+              const float t = fmaf(v[i], sh.scale_log2, mask_s[j]);
+              if (j < p.Tk) mx = fmaxf(mx, t);
+            }
+          } else if (c < c_full) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, v[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < p.Tk) mx = fmaxf(mx, v[i]);
           }
         }
+        if (!masked) mx *= sh.scale_log2;
         if (sh.halves == 2) {
           xchg[half * 128 + r] = mx;
           asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(gthreads) : "memory");
@@ -189,18 +200,29 @@ __global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __
         }
         // pass 2: p = 2^(t - max), row sum, bf16 P into the swizzled K-major operand layout
         float sum = 0.f;
+        const float nmx = -mx;
         for (int c = c_lo; c < c_hi; ++c) {
           tmem_ld32(trow + c * 32, v);
+          if (masked || c >= c_full) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int j = c * 32 + i;
-            float t = v[i] * sh.scale_log2;
-            if (masked) t += mask_s[j];
-            t -= mx;
-            float e = t;
-            if (!(sh.dbg & 2)) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
-            v[i] = j < p.Tk ? e : 0.f;
-            sum += v[i];
+            for (int i = 0; i < 32; ++i) {
+              const int j = c * 32 + i;
+              float t = fmaf(v[i], sh.scale_log2, nmx);
+              if (masked) t += mask_s[j];
+              float e = t;
+              if (!(sh.dbg & 2)) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+              v[i] = j < p.Tk ? e : 0.f;
+              sum += v[i];
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float t = fmaf(v[i], sh.scale_log2, nmx);
+              float e = t;
+              if (!(sh.dbg & 2)) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+              v[i] = e;
+              sum += e;
+            }
           }
           const uint32_t blk = smem_u32(q_s) + (uint32_t)(c >> 1) * 16384u + (uint32_t)r * 128u;
 #pragma unroll

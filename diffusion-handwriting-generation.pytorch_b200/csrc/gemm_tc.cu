@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     t_step = sh.grp_cta0[my_group + 1] - sh.grp_cta0[my_group];
   }
   const int t_end = sh.sticky ? sh.m_super : sh.m_super * sh.n_groups;   // work items = (super-tile, column group)
+  const bool one_group = sh.sticky || sh.n_groups == 1;   // work item index == super-tile index (no division needed)
   uint8_t* a_ring = smem;
   uint8_t* w_base = smem + sh.off_w;
   const bool film = e.gamma != nullptr;
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     // ring positions are kept incrementally (no integer division in these latency-critical loops)
     uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
     for (int t = t_first; t < t_end; t += t_step) {
-      const int mts = sh.sticky ? t : t / sh.n_groups;
+      const int mts = one_group ? t : t / sh.n_groups;
       const int ng = sh.sticky ? my_group : t - mts * sh.n_groups;
       const int n0 = ng * sh.BN;
       for (int kbi = 0; kbi < sh.kb_per_tap; ++kbi) {
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       const int ft = iss_t, fsub = iss_sub, ci = iss_ci;
       if (ft < t_end) {
         if (ci == 0) {   // first chunk of a row tile: where does my row's residual / bias row live?
-          const int fmts = sh.sticky ? ft : ft / sh.n_groups;
+          const int fmts = one_group ? ft : ft / sh.n_groups;
           iss_ng = sh.sticky ? my_group : ft - fmts * sh.n_groups;
           const int fm = (fmts * tiles_per_super + fsub + (int)cta_rank) * TC_BM + r_tile;
           const bool f_in = fm < sh.rows;
@@ -483,7 +484,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 
     int it = 0, tile_no = 0;
     for (int t = t_first; t < t_end; t += t_step, ++it) {
-     const int mts = sh.sticky ? t : t / sh.n_groups;
+     const int mts = one_group ? t : t / sh.n_groups;
      const int ng = sh.sticky ? my_group : t - mts * sh.n_groups;
      const int n0 = ng * sh.BN;
      const int as = sh.acc_stages == 2 ? (it & 1) : 0;
