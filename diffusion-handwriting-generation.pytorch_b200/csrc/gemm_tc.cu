@@ -42,7 +42,7 @@ constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int AUX_DEPTH = 8 / EPI_PARTS;              // aux ring slots per epilogue warp
 constexpr int AUX_SLOT_BYTES = 2048;                  // 32 rows x 32 bf16
 constexpr int AUX_RING_BYTES = AUX_DEPTH * AUX_SLOT_BYTES;
-constexpr int OUT_STAGE_BYTES = 4096;  // per epilogue warp: 2 x (32 rows x 32 bf16), alternating between TMA stores
+constexpr int OUT_STAGE_BYTES = (DHG_EPI_PARTS == 4 ? 2048 : 4096);  // per epilogue warp: 2 x (32 rows x 32 bf16), alternating between TMA stores
 constexpr int TMEM_COLS = 512;
 
 enum { AUX_NONE = 0, AUX_RES_PRE = 1, AUX_RES_POST = 2, AUX_RES_POST_UP = 3, AUX_ROWBIAS = 4 };
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     const int c_hi = ((part + 1) * nch) / EPI_PARTS;
     const int my_nch = c_hi - c_lo;
     const uint32_t aux_ring = smem_u32(smem + sh.off_aux + (size_t)ew * AUX_RING_BYTES);
-    const uint32_t out_st = smem_u32(smem + sh.off_out + (size_t)ew * (sh.out_bufs == 2 ? OUT_STAGE_BYTES : OUT_STAGE_BYTES / 2));
+    const uint32_t out_st = smem_u32(smem + sh.off_out + (size_t)ew * (sh.out_bufs == 2 ? OUT_STAGE_BYTES : 2048));
     const uint32_t bias_sa = smem_u32(bias_s), gamma_sa = smem_u32(gamma_s), betap_sa = smem_u32(betap_s);
     float2* ln_s = reinterpret_cast<float2*>(smem + sh.off_ln);   // [2 parity][128 rows][EPI_PARTS] {mean, M2} of each column part
     const int aux_ncols = aux_kind == AUX_ROWBIAS ? e.rowbias16_cols : 0x7fffffff;   // aux only for columns below this
@@ -776,8 +776,8 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   size_t fixed = (aux_kind != AUX_NONE ? (size_t)EPI_WARPS * AUX_RING_BYTES : 0) + (size_t)EPI_WARPS * OUT_STAGE_BYTES +
                  (size_t)(sh.vec_bias_n + 2 * sh.film_n) * 4 + 16 + (e.ln ? 2 * TC_BM * EPI_PARTS * 8 : 0) + 64 * 8;
   size_t budget = 227 * 1024 - 1024 - fixed;
-  sh.out_bufs = 2;
-  if (2 * (size_t)(sh.a_stage_bytes + BN * TC_BK * 2) > budget) {   // not even two A + two W stages: give up the second store tile
+  sh.out_bufs = OUT_STAGE_BYTES >= 4096 ? 2 : 1;
+  if (sh.out_bufs == 2 && 2 * (size_t)(sh.a_stage_bytes + BN * TC_BK * 2) > budget) {   // not even two A + two W stages: give up the second store tile
     sh.out_bufs = 1;
     fixed -= (size_t)EPI_WARPS * OUT_STAGE_BYTES / 2;
     budget += (size_t)EPI_WARPS * OUT_STAGE_BYTES / 2;
@@ -820,7 +820,7 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   uint32_t off = (uint32_t)sh.stages_a * sh.a_stage_bytes;
   sh.off_w = off; off += (uint32_t)w_bytes;
   sh.off_aux = off; off += aux_kind != AUX_NONE ? EPI_WARPS * AUX_RING_BYTES : 0;
-  sh.off_out = off; off += EPI_WARPS * OUT_STAGE_BYTES / (sh.out_bufs == 2 ? 1 : 2);
+  sh.off_out = off; off += EPI_WARPS * (sh.out_bufs == 2 ? OUT_STAGE_BYTES : 2048);
   sh.off_vec = off; off += (uint32_t)(sh.vec_bias_n + 2 * sh.film_n) * 4;
   off = (off + 15u) & ~15u;
   sh.off_ln = off; off += e.ln ? 2 * TC_BM * EPI_PARTS * 8 : 0;
