@@ -30,6 +30,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <functional>
 #include <map>
 #include <string>
@@ -44,6 +45,8 @@ using namespace dhg;
 // error plumbing
 // ---------------------------------------------------------------------------
 static thread_local char g_err[1024] = "";
+static int g_opt_autotune = 1;  // time every GEMM tile configuration at plan time and keep the fastest ("autotune")
+static int g_opt_overlap = 1;   // text side of step i-1 beside the stroke side of step i (dhg_set_option "overlap")
 static int fail(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -92,6 +95,8 @@ struct StepCtx {
   int bstride;
   bool skip_input_dense;  // in_raw / in_act were already written by the previous step's head kernel
   bool fuse_next_input;   // this step's head kernel also writes in_raw / in_act of the next step
+  int text_set;           // which copy of the text-side buffers this step's cross-attention reads
+  cudaEvent_t text_ready; // recorded after that copy was produced on the text stream (null: same stream, already ordered)
   HeadParams head;
 };
 typedef std::function<int(cudaStream_t, const StepCtx&)> Op;
@@ -134,14 +139,22 @@ struct Plan {
   float* scratch = nullptr;   // fp32 accumulators of the CUDA-core GEMM path
   size_t scratch_elems = 0;
   int* err_flag = nullptr;
-  std::vector<Op> once_ops, step_ops;
+  // once_ops: step-independent; text_ops[set]: the part of a step that depends on sigma but not on x (TextStyleEncoder,
+  // text_dense and k/v projections of every EncoderLayer); step_ops: everything that depends on x.  With two text sets
+  // the text side of step i-1 runs on text_stream while the stroke side of step i runs on the caller's stream.
+  std::vector<Op> once_ops, text_ops[2], step_ops;
+  int text_sets = 1;
+  cudaStream_t text_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_text[DHG_NUM_STEPS] = {};
   Act head_in, in_raw, in_act;
   std::vector<TcGemmPlan*> tc_plans;
   std::vector<AttnTcPlan*> attn_plans;
   int attn_impl = 1;
   cudaStream_t cap_stream = nullptr;
   cudaGraphExec_t graphs[4] = {nullptr, nullptr, nullptr, nullptr};  // [mode*2 + has_noise]
-  int64_t launches_once = 0, launches_step = 0;
+  int64_t launches_once = 0, launches_step = 0, launches_text = 0;
+  struct HostStage { float *x = nullptr, *noise = nullptr, *style = nullptr, *out = nullptr; int64_t* text = nullptr; int cap = 0; };
+  HostStage stage;   // device copies of dhg_sample_host's host buffers
   struct Tap { Act a; int period; int pad; };
   std::map<std::string, Tap> taps;  // named activations readable through dhg_debug_read
 };
@@ -335,7 +348,13 @@ void free_plan(Plan* p) {
   for (auto t : p->tc_plans) tc_gemm_plan_destroy(t);
   for (auto t : p->attn_plans) attn_tc_plan_destroy(t);
   if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
+  if (p->text_stream) cudaStreamDestroy(p->text_stream);
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  for (auto e : p->ev_text)
+    if (e) cudaEventDestroy(e);
   for (auto a : p->allocs) cudaFree(a);
+  for (void* q : {(void*)p->stage.x, (void*)p->stage.noise, (void*)p->stage.style, (void*)p->stage.out, (void*)p->stage.text})
+    if (q) cudaFree(q);
   delete p;
 }
 
@@ -400,6 +419,83 @@ struct Builder {
   RowMap map_text() const { return RowMap{P->L, 0, P->RT}; }
   RowMap map_style() const { return RowMap{P->SP, 0, P->RS}; }
 
+  // Time the launch under every tile configuration the kernel supports for this shape (tile width, interleaved
+  // accumulators, resident or streamed W, CTA pairs) on the plan's own buffers and keep the fastest.  All configurations
+  // compute the same bits (kernels.h TcTune), so this only moves time.  `base` is the plan of the built-in rule.
+  TcGemmPlan* autotune(TcGemmPlan* base, const bf16* Ap, int lda, int rows, const Lin* W, const Epilogue& e, const Epilogue& et,
+                       const std::string& wkey) {
+    const int N = W->N;
+    cudaStream_t st = P->cap_stream;
+    cudaEvent_t e0, e1;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { fail("autotune: event"); tc_gemm_plan_destroy(base); return nullptr; }
+    // false: this configuration cannot be launched (skipped); a failure that poisons the context is caught by the
+    // synchronisation at the end
+    auto time_plan = [&](TcGemmPlan* p, float* ms) -> bool {
+      for (int i = 0; i < 2; ++i)
+        if (tc_gemm_launch(p, et, st)) { cudaGetLastError(); return false; }
+      cudaEventRecord(e0, st);
+      const int reps = 4;
+      for (int i = 0; i < reps; ++i)
+        if (tc_gemm_launch(p, et, st)) { cudaGetLastError(); return false; }
+      cudaEventRecord(e1, st);
+      if (cudaEventSynchronize(e1) != cudaSuccess) return false;
+      cudaEventElapsedTime(ms, e0, e1);
+      *ms /= reps;
+      return true;
+    };
+    TcTune best_cfg, cfg0;
+    tc_gemm_plan_config(base, &cfg0);
+    best_cfg = cfg0;
+    float best = 0.f, t0 = 0.f;
+    bool ok = time_plan(base, &best);
+    t0 = best;
+    TcGemmPlan* best_plan = base;
+    std::vector<TcTune> seen{cfg0};
+    std::vector<int> bns;
+    if (e.ln) bns.push_back(N);
+    else
+      for (int bn : {384, 256, 192, 128, 96, 64})
+        if (N % bn == 0) bns.push_back(bn);
+    for (size_t bi = 0; ok && bi < bns.size(); ++bi) {
+      const int bn = bns[bi];
+      for (int g : {1, 2, 4}) {
+        if (g * bn > 256 && g > 1) continue;
+        for (int mode = 0; mode < 3; ++mode) {   // 0: resident W, 1: streamed W, 2: streamed W + CTA pairs
+          if (mode == 2 && g != 1) continue;
+          TcTune t{bn, g, mode == 0 ? 1 : 0, mode == 2 ? 1 : 0};
+          char buf[256];
+          TcGemmPlan* p = tc_gemm_plan_create(Ap, lda, rows, W->w16, W->K, N, W->taps, e, buf, sizeof(buf), &t);
+          if (!p) continue;   // configuration not available for this shape
+          TcTune got;
+          tc_gemm_plan_config(p, &got);
+          bool dup = false;
+          for (auto& sn : seen) dup = dup || (sn.bn == got.bn && sn.g == got.g && sn.resident == got.resident && sn.pair == got.pair);
+          float ms = 0.f;
+          if (dup || !time_plan(p, &ms)) { tc_gemm_plan_destroy(p); continue; }
+          seen.push_back(got);
+          if (ms < best * 0.985f) {   // must win by more than the timing noise
+            tc_gemm_plan_destroy(best_plan);
+            best_plan = p; best = ms; best_cfg = got;
+          } else {
+            tc_gemm_plan_destroy(p);
+          }
+        }
+      }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (!ok || cudaStreamSynchronize(st) != cudaSuccess) {
+      fail("autotune %s: launch failed: %s", wkey.c_str(), cudaGetErrorString(cudaGetLastError()));
+      tc_gemm_plan_destroy(best_plan);
+      return nullptr;
+    }
+    if (getenv("DHG_DESCRIBE"))
+      fprintf(stderr, "autotune %-28s rows=%d K=%d N=%d taps=%d: rule {bn=%d g=%d res=%d pair=%d} %.1f us -> {bn=%d g=%d res=%d pair=%d} %.1f us (%zu tried)\n",
+              wkey.c_str(), rows, W->K, N, W->taps, cfg0.bn, cfg0.g, cfg0.resident, cfg0.pair, t0 * 1e3f, best_cfg.bn, best_cfg.g,
+              best_cfg.resident, best_cfg.pair, best * 1e3f, seen.size());
+    return best_plan;
+  }
+
   void gemm(const Act& A, const std::string& wkey, const EpiSpec& s, const RowMap& map) {
     if (failed) return;
     auto it = c->lins.find(wkey);
@@ -432,6 +528,12 @@ struct Builder {
       char buf[512];
       tcp = tc_gemm_plan_create((const bf16*)Ap, A.C, rows, W->w16, K, N, taps, e, buf, sizeof(buf));
       if (!tcp) { fail("plan: tcgen05 gemm %s: %s", wkey.c_str(), buf); failed = true; return; }
+      if (g_opt_autotune) {
+        Epilogue et = e;
+        if (film_off >= 0) { et.gamma = c->cond60 + film_off; et.beta = c->cond60 + film_off + N; et.film_bstride = 0; }
+        tcp = autotune(tcp, (const bf16*)Ap, A.C, rows, W, e, et, wkey);
+        if (!tcp) { failed = true; return; }
+      }
       P->tc_plans.push_back(tcp);
     }
     *nlaunch += tcp ? 1 : 2;
@@ -454,32 +556,48 @@ struct Builder {
     });
   }
 
-  void attention(const void* q, int qp, const void* k, int kp, const void* v, int vp, const Act& o, int H, int D,
-                 int Tq, int q_period, int q_pad, int Tk, int k_period, int k_pad, bool masked, int q_rows, int k_rows) {
+  // k / v may exist in up to two copies (text sets); the launch picks sc.text_set.  wait_text: this is the first
+  // consumer of the text side in a step, so it first waits for the text stream's event (if the step has one).
+  void attention_sets(const void* q, int qp, const void* const* ks, const void* const* vs, int nsets, int kp, int vp,
+                      const Act& o, int H, int D, int Tq, int q_period, int q_pad, int Tk, int k_period, int k_pad,
+                      bool masked, int q_rows, int k_rows, bool wait_text) {
     if (failed) return;
-    AttnParams a;
-    a.q = q; a.k = k; a.v = v; a.o = o.p;
-    a.q_pitch = qp; a.k_pitch = kp; a.v_pitch = vp; a.o_pitch = o.C;
-    a.q_period = q_period; a.q_pad = q_pad; a.k_period = k_period; a.k_pad = k_pad;
-    a.B = P->B; a.H = H; a.D = D; a.Tq = Tq; a.Tk = Tk;
-    a.scale = 1.0f / sqrtf((float)D);
-    a.text = masked ? P->text : nullptr;
+    AttnParams a[2];
+    AttnTcPlan* plans[2] = {nullptr, nullptr};
     Plan* Pl = P;
     *nlaunch += 1;
-    if (P->prec == PREC_BF16 && P->attn_impl == 1 && attn_tc_supported(a)) {
-      char buf[512];
-      AttnTcPlan* ap = attn_tc_plan_create(a, q_rows, k_rows, buf, sizeof(buf));
-      if (!ap) { fail("plan: tcgen05 attention: %s", buf); failed = true; return; }
-      P->attn_plans.push_back(ap);
-      ops->push_back([=](cudaStream_t st, const StepCtx&) -> int {
-        return attn_tc_launch(ap, st) ? fail("tcgen05 attention launch failed: %s", cudaGetErrorString(cudaGetLastError())) : 0;
-      });
-      return;
+    bool tc = false;
+    for (int s = 0; s < nsets; ++s) {
+      a[s].q = q; a[s].k = ks[s]; a[s].v = vs[s]; a[s].o = o.p;
+      a[s].q_pitch = qp; a[s].k_pitch = kp; a[s].v_pitch = vp; a[s].o_pitch = o.C;
+      a[s].q_period = q_period; a[s].q_pad = q_pad; a[s].k_period = k_period; a[s].k_pad = k_pad;
+      a[s].B = P->B; a[s].H = H; a[s].D = D; a[s].Tq = Tq; a[s].Tk = Tk;
+      a[s].scale = 1.0f / sqrtf((float)D);
+      a[s].text = masked ? P->text : nullptr;
+      if (P->prec == PREC_BF16 && P->attn_impl == 1 && attn_tc_supported(a[s])) {
+        char buf[512];
+        plans[s] = attn_tc_plan_create(a[s], q_rows, k_rows, buf, sizeof(buf));
+        if (!plans[s]) { fail("plan: tcgen05 attention: %s", buf); failed = true; return; }
+        P->attn_plans.push_back(plans[s]);
+        tc = true;
+      }
     }
-    ops->push_back([=](cudaStream_t st, const StepCtx&) -> int {
-      const int r = Pl->prec == PREC_FP32 ? launch_attention_simt<float>(a, st) : launch_attention_simt<bf16>(a, st);
-      return r ? fail("attention: unsupported head depth %d", a.D) : 0;
+    if (nsets == 1) { a[1] = a[0]; plans[1] = plans[0]; }
+    const AttnParams a0 = a[0], a1 = a[1];
+    AttnTcPlan *p0 = plans[0], *p1 = plans[1];
+    ops->push_back([=](cudaStream_t st, const StepCtx& sc) -> int {
+      if (wait_text && sc.text_ready && cudaStreamWaitEvent(st, sc.text_ready, 0) != cudaSuccess)
+        return fail("cudaStreamWaitEvent(text side): %s", cudaGetErrorString(cudaGetLastError()));
+      const int set = sc.text_set ? 1 : 0;
+      if (tc) return attn_tc_launch(set ? p1 : p0, st) ? fail("tcgen05 attention launch failed: %s", cudaGetErrorString(cudaGetLastError())) : 0;
+      const AttnParams& aa = set ? a1 : a0;
+      const int r = Pl->prec == PREC_FP32 ? launch_attention_simt<float>(aa, st) : launch_attention_simt<bf16>(aa, st);
+      return r ? fail("attention: unsupported head depth %d", aa.D) : 0;
     });
+  }
+  void attention(const void* q, int qp, const void* k, int kp, const void* v, int vp, const Act& o, int H, int D,
+                 int Tq, int q_period, int q_pad, int Tk, int k_period, int k_pad, bool masked, int q_rows, int k_rows) {
+    attention_sets(q, qp, &k, &v, 1, kp, vp, o, H, D, Tq, q_period, q_pad, Tk, k_period, k_pad, masked, q_rows, k_rows, false);
   }
 
   void film_rows(const Act& in, const Act& out, int period, int film_off) {
@@ -533,30 +651,46 @@ struct Builder {
     return out;
   }
 
-  // model.py:35-58
-  Act encoder_layer(const std::string& p, const Act& x, const Act& text_act, int heads, float pos_factor, int level) {
-    const int R = P->R[level], dm = x.C, Tl = P->Tl[level], L = P->L;
-    const RowMap m = map_level(level), mt = map_text();
-    const int D = dm / heads;
-    // positional-embedding-folded bias tables
-    const std::vector<float> pe_x = pe_table(Tl, dm, pos_factor), pe_t = pe_table(L, dm, 1.0f);
-    float *rb_q = nullptr, *rb_kv = nullptr, *rb_qkv = nullptr;
-    void *rb16_q = nullptr, *rb16_kv = nullptr, *rb16_qkv = nullptr;
-    if (!failed) {
-      if (make_rowbias(P, c->lins.at(p + ".mha.wq"), pe_x, Tl, 0, dm, &rb_q, &rb16_q) ||
-          make_rowbias(P, c->lins.at(p + ".mha.kv"), pe_t, L, 0, dm, &rb_kv, &rb16_kv) ||          // k gets PE, v does not
-          make_rowbias(P, c->lins.at(p + ".mha2.qkv"), pe_x, Tl, 0, 2 * dm, &rb_qkv, &rb16_qkv))   // q,k get PE, v does not
-        failed = true;
-    }
-    Act tp = act(P->RT, dm), kv = act(P->RT, 2 * dm), q = act(R, dm), o = act(R, dm), x2 = act(R, dm);
-    Act qkv = act(R, 3 * dm), o2 = act(R, dm), x3r = act(R, dm), x3a = act(R, dm), hid = act(R, 2 * dm), out = act(R, dm);
+  // model.py:42-45, text side of an EncoderLayer: text' = FiLM0(LN(text_dense(SiLU(text)))), then the k | v projections
+  // of the cross-attention (k gets the text positional embedding folded into a per-position bias row, v does not).
+  Act encoder_text(const std::string& p, const Act& text_act) {
+    if (failed) return Act();
+    const int dm = c->lins.at(p + ".text_dense").N, L = P->L;
+    const RowMap mt = map_text();
+    const std::vector<float> pe_t = pe_table(L, dm, 1.0f);
+    float* rb_kv = nullptr;
+    void* rb16_kv = nullptr;
+    if (make_rowbias(P, c->lins.at(p + ".mha.kv"), pe_t, L, 0, dm, &rb_kv, &rb16_kv)) { failed = true; return Act(); }
+    Act tp = act(P->RT, dm), kv = act(P->RT, 2 * dm);
     EpiSpec s; s.ln = true; s.film_off = film(p + ".affine0"); s.out_raw = tp;
     gemm(text_act, p + ".text_dense", s, mt);
     EpiSpec skv; skv.rowbias = rb_kv; skv.rowbias16 = rb16_kv; skv.rowbias16_cols = dm; skv.out_raw = kv;
     gemm(tp, p + ".mha.kv", skv, mt);
+    return kv;
+  }
+
+  // model.py:35-58, stroke side (kvs: the k | v rows written by encoder_text, one per text set)
+  Act encoder_layer(const std::string& p, const Act& x, const Act* kvs, int nsets, int heads, float pos_factor, int level,
+                    bool first_text_consumer) {
+    const int R = P->R[level], dm = x.C, Tl = P->Tl[level], L = P->L;
+    const RowMap m = map_level(level);
+    const int D = dm / heads;
+    // positional-embedding-folded bias tables
+    const std::vector<float> pe_x = pe_table(Tl, dm, pos_factor);
+    float *rb_q = nullptr, *rb_qkv = nullptr;
+    void *rb16_q = nullptr, *rb16_qkv = nullptr;
+    if (!failed) {
+      if (make_rowbias(P, c->lins.at(p + ".mha.wq"), pe_x, Tl, 0, dm, &rb_q, &rb16_q) ||
+          make_rowbias(P, c->lins.at(p + ".mha2.qkv"), pe_x, Tl, 0, 2 * dm, &rb_qkv, &rb16_qkv))   // q,k get PE, v does not
+        failed = true;
+    }
+    Act q = act(R, dm), o = act(R, dm), x2 = act(R, dm);
+    Act qkv = act(R, 3 * dm), o2 = act(R, dm), x3r = act(R, dm), x3a = act(R, dm), hid = act(R, 2 * dm), out = act(R, dm);
     EpiSpec sq; sq.rowbias = rb_q; sq.rowbias16 = rb16_q; sq.rowbias16_cols = dm; sq.out_raw = q;
     gemm(x, p + ".mha.wq", sq, m);
-    attention(q.p, dm, kv.p, 2 * dm, col(kv, dm), 2 * dm, o, heads, D, Tl, Tl + 1, 1, L, L, 0, true, R, P->RT);
+    const void *ks[2], *vs[2];
+    for (int s = 0; s < nsets; ++s) { ks[s] = kvs[s].p; vs[s] = col(kvs[s], dm); }
+    attention_sets(q.p, dm, ks, vs, nsets, 2 * dm, 2 * dm, o, heads, D, Tl, Tl + 1, 1, L, L, 0, true, R, P->RT, first_text_consumer);
     EpiSpec sd; sd.ln = true; sd.film_off = film(p + ".affine1"); sd.res_post = x; sd.out_raw = x2;
     gemm(o, p + ".mha.dense", sd, m);
     EpiSpec sqkv; sqkv.rowbias = rb_qkv; sqkv.rowbias16 = rb16_qkv; sqkv.rowbias16_cols = 2 * dm; sqkv.out_raw = qkv;
@@ -622,21 +756,42 @@ int build_plan(dhg_ctx* c, Plan* P) {
   once.gemm(sh, ts + ".style_ffn.3", e2, once.map_style());
   if (once.failed) return 1;
 
-  // ---- per-step part ----
-  Builder bd{c, P, &P->step_ops, &P->launches_step};
-  Act sf = bd.act(P->RS, d), tf = bd.act(P->RT, d), skv = bd.act(P->RS, 2 * d), tq = bd.act(P->RT, d);
-  Act to = bd.act(P->RT, d), t1a = bd.act(P->RT, d), th = bd.act(P->RT, 2 * d), text_act = bd.act(P->RT, d);
-  bd.film_rows(s0, sf, P->SP, bd.film(ts + ".affine1"));
-  bd.film_rows(t0, tf, L, bd.film(ts + ".affine2"));
-  { EpiSpec s; s.out_raw = skv; bd.gemm(sf, ts + ".mha.kv", s, bd.map_style()); }
-  { EpiSpec s; s.out_raw = tq; bd.gemm(tf, ts + ".mha.wq", s, bd.map_text()); }
-  bd.attention(tq.p, d, skv.p, 2 * d, bd.col(skv, d), 2 * d, to, 8, d / 8, L, L, 0, P->SP, P->SP, 0, false, P->RT, P->RS);
-  { EpiSpec s; s.res_pre = tf; s.ln = true; s.film_off = bd.film(ts + ".affine3"); s.out_act = t1a;
-    bd.gemm(to, ts + ".mha.dense", s, bd.map_text()); }
-  { EpiSpec s; s.out_act = th; bd.gemm(t1a, ts + ".text_ffn.1", s, bd.map_text()); }
-  { EpiSpec s; s.ln = true; s.film_off = bd.film(ts + ".affine4"); s.out_act = text_act;
-    bd.gemm(th, ts + ".text_ffn.3", s, bd.map_text()); }
+  // ---- per-step, text side (depends on the step through FiLM only, never on x): one op list per text set ----
+  std::vector<std::string> enc_names = {"enc3", "enc5"};
+  for (int i = 0; i < c->cfg.num_layers; ++i) enc_names.push_back("att_layers." + std::to_string(i));
+  // two sets (and a second stream) only where every text-side launch is a self-contained tcgen05 kernel: the CUDA-core
+  // GEMM path shares one fp32 scratch buffer between launches and must stay serial
+  P->text_sets = (g_opt_overlap && P->prec == PREC_BF16 && P->gemm_impl == 1) ? 2 : 1;
+  if (P->text_sets == 2) {
+    CUDA_OK(cudaStreamCreateWithFlags(&P->text_stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming));
+    for (auto& e : P->ev_text) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  std::vector<Act> kv_sets[2];
+  Act text_act0, tf0, sf0, t1a0, to0;
+  for (int set = 0; set < P->text_sets; ++set) {
+    int64_t other = 0;
+    Builder tb{c, P, &P->text_ops[set], set == 0 ? &P->launches_text : &other};
+    Act sf = tb.act(P->RS, d), tf = tb.act(P->RT, d), skv = tb.act(P->RS, 2 * d), tq = tb.act(P->RT, d);
+    Act to = tb.act(P->RT, d), t1a = tb.act(P->RT, d), th = tb.act(P->RT, 2 * d), text_act = tb.act(P->RT, d);
+    tb.film_rows(s0, sf, P->SP, tb.film(ts + ".affine1"));
+    tb.film_rows(t0, tf, L, tb.film(ts + ".affine2"));
+    { EpiSpec s; s.out_raw = skv; tb.gemm(sf, ts + ".mha.kv", s, tb.map_style()); }
+    { EpiSpec s; s.out_raw = tq; tb.gemm(tf, ts + ".mha.wq", s, tb.map_text()); }
+    tb.attention(tq.p, d, skv.p, 2 * d, tb.col(skv, d), 2 * d, to, 8, d / 8, L, L, 0, P->SP, P->SP, 0, false, P->RT, P->RS);
+    { EpiSpec s; s.res_pre = tf; s.ln = true; s.film_off = tb.film(ts + ".affine3"); s.out_act = t1a;
+      tb.gemm(to, ts + ".mha.dense", s, tb.map_text()); }
+    { EpiSpec s; s.out_act = th; tb.gemm(t1a, ts + ".text_ffn.1", s, tb.map_text()); }
+    { EpiSpec s; s.ln = true; s.film_off = tb.film(ts + ".affine4"); s.out_act = text_act;
+      tb.gemm(th, ts + ".text_ffn.3", s, tb.map_text()); }
+    for (auto& name : enc_names) kv_sets[set].push_back(tb.encoder_text(name, text_act));
+    if (tb.failed) return 1;
+    if (set == 0) { text_act0 = text_act; tf0 = tf; sf0 = sf; t1a0 = t1a; to0 = to; }
+  }
+  auto kvs_of = [&](int layer, Act* out2) { for (int s = 0; s < P->text_sets; ++s) out2[s] = kv_sets[s][layer]; };
 
+  // ---- per-step, stroke side ----
+  Builder bd{c, P, &P->step_ops, &P->launches_step};
   // input_dense (model.py:139)
   Act in_raw = bd.act(P->R[0], c1), in_act = bd.act(P->R[0], c1);
   {
@@ -659,17 +814,20 @@ int build_plan(dhg_ctx* c, Plan* P) {
     if (level >= 0) P->taps[name] = Plan::Tap{a, P->Tl[level] + 1, 1};
     else P->taps[name] = Plan::Tap{a, level == -1 ? P->L : P->SP, 0};
   };
-  tap("text_act", text_act, -1); tap("tf", tf, -1); tap("sf", sf, -2); tap("t1a", t1a, -1); tap("to", to, -1);
+  tap("text_act", text_act0, -1); tap("tf", tf0, -1); tap("sf", sf0, -2); tap("t1a", t1a0, -1); tap("to", to0, -1);
   tap("in_raw", in_raw, 0); tap("h1", h1, 0);
   Act p1r = bd.act(P->R[1], c1), p1a = bd.act(P->R[1], c1);
   bd.pool(h1, p1r, p1a, P->Tl[1]);
   Act h2c = bd.conv_block("enc2", p1r, p1a, c2, 1, false, &dummy);
-  Act h2 = bd.encoder_layer("enc3", h2c, text_act, 3, 4.0f, 1);
+  Act kvl[2];
+  kvs_of(0, kvl);
+  Act h2 = bd.encoder_layer("enc3", h2c, kvl, P->text_sets, 3, 4.0f, 1, true);
   tap("h2c", h2c, 1); tap("h2", h2, 1);
   Act p2r = bd.act(P->R[2], c2), p2a = bd.act(P->R[2], c2);
   bd.pool(h2, p2r, p2a, P->Tl[2]);
   Act h3c = bd.conv_block("enc4", p2r, p2a, c3, 2, false, &dummy);
-  Act h3 = bd.encoder_layer("enc5", h3c, text_act, 4, 2.0f, 2);
+  kvs_of(1, kvl);
+  Act h3 = bd.encoder_layer("enc5", h3c, kvl, P->text_sets, 4, 2.0f, 2, false);
   tap("h3c", h3c, 2); tap("h3", h3, 2);
   Act p3r = bd.act(P->R[3], c3);
   bd.pool(h3, p3r, Act(), P->Tl[3]);
@@ -677,7 +835,8 @@ int build_plan(dhg_ctx* c, Plan* P) {
   { EpiSpec s; s.out_raw = xa; bd.gemm(p3r, "att_dense", s, bd.map_level(3)); }
   tap("att_in", xa, 3);
   for (int i = 0; i < c->cfg.num_layers; ++i) {
-    xa = bd.encoder_layer("att_layers." + std::to_string(i), xa, text_act, 6, 1.0f, 3);
+    kvs_of(2 + i, kvl);
+    xa = bd.encoder_layer("att_layers." + std::to_string(i), xa, kvl, P->text_sets, 6, 1.0f, 3, false);
     tap(("att" + std::to_string(i)).c_str(), xa, 3);
   }
   // decoder: upsample(x) + skip_conv(h) (model.py:169-176), then ConvBlock
@@ -760,10 +919,31 @@ int run_chain(dhg_ctx* c, Plan* P, int mode, bool has_noise, cudaStream_t st) {
   sc.cond = c->cond60;
   sc.bstride = 0;
   if (run_ops(P->once_ops, st, sc)) return 1;
+  // The text side of a step does not depend on x: with two text sets, step i-1's text side runs on text_stream while
+  // step i's stroke side runs on st (it fills the SMs the stroke kernels leave idle in their last wave, and the other
+  // way round).  Set (i & 1) is written for step i; its previous reader was step i+2, which ended before step i+1 began.
+  const bool overlap = P->text_sets == 2;
+  auto text_ctx = [&](int i) {
+    StepCtx t;
+    memset(&t, 0, sizeof(t));
+    t.cond = c->cond60 + (size_t)i * c->film_total;
+    t.bstride = 0;
+    return t;
+  };
+  if (overlap && run_ops(P->text_ops[(DHG_NUM_STEPS - 1) & 1], st, text_ctx(DHG_NUM_STEPS - 1))) return 1;
   for (int i = DHG_NUM_STEPS - 1; i >= 0; --i) {
+    if (overlap && i > 0) {
+      CUDA_OK(cudaEventRecord(P->ev_fork, st));
+      CUDA_OK(cudaStreamWaitEvent(P->text_stream, P->ev_fork, 0));
+      if (run_ops(P->text_ops[(i - 1) & 1], P->text_stream, text_ctx(i - 1))) return 1;
+      CUDA_OK(cudaEventRecord(P->ev_text[i - 1], P->text_stream));
+    }
+    if (!overlap && run_ops(P->text_ops[0], st, text_ctx(i))) return 1;
     sc.cond = c->cond60 + (size_t)i * c->film_total;
     sc.skip_input_dense = i != DHG_NUM_STEPS - 1;   // written by the previous step's head kernel
     sc.fuse_next_input = i != 0;
+    sc.text_set = overlap ? (i & 1) : 0;
+    sc.text_ready = (overlap && i != DHG_NUM_STEPS - 1) ? P->ev_text[i] : nullptr;
     head_for_step(c, P, i, mode, has_noise, false, &sc.head);
     if (run_ops(P->step_ops, st, sc)) return 1;
   }
@@ -995,6 +1175,7 @@ int32_t dhg_denoise(dhg_ctx* c, const float* strokes, const int64_t* text, const
   sc.head.pen_stride = 1;
   sc.head.pen_offset = 0;
   if (run_ops(P->once_ops, st, sc)) return 1;
+  if (run_ops(P->text_ops[0], st, sc)) return 1;
   // input_dense reads sc.head.x_io when set; here it must read the caller's strokes without updating them
   StepCtx sc_in = sc;
   sc_in.head.x_io = const_cast<float*>(strokes);
@@ -1003,7 +1184,7 @@ int32_t dhg_denoise(dhg_ctx* c, const float* strokes, const int64_t* text, const
     if (P->step_ops[i](st, is_head ? sc : sc_in)) return 1;
   }
   CUDA_OK(cudaGetLastError());
-  c->last_launches = 2 + P->launches_once + P->launches_step;
+  c->last_launches = 2 + P->launches_once + P->launches_text + P->launches_step;
   return 0;
 }
 
@@ -1038,7 +1219,7 @@ int32_t dhg_sample(dhg_ctx* c, int32_t batch, const float* x0, const float* nois
                               cudaMemcpyDeviceToDevice, st));
     if (launch_chain(c, P, mode, true, st)) return 1;
     CUDA_OK(cudaMemcpyAsync(out + (size_t)c0 * P->T * 3, P->out, (size_t)nb * P->T * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    launches += P->launches_once + (int64_t)DHG_NUM_STEPS * P->launches_step - (DHG_NUM_STEPS - 1);   // input_dense is fused after step 1
+    launches += P->launches_once + (int64_t)DHG_NUM_STEPS * (P->launches_text + P->launches_step) - (DHG_NUM_STEPS - 1);   // input_dense is fused after step 1
   }
   c->last_launches = launches;
   return 0;
@@ -1051,30 +1232,40 @@ int32_t dhg_sample_host(dhg_ctx* c, int32_t batch, const float* x0, const float*
   Plan* P = c->plan;
   CUDA_OK(cudaSetDevice(c->device));
   const size_t xs = (size_t)P->T * 2, ss = (size_t)P->S * kStyleWidth;
-  float *dx = nullptr, *dn = nullptr, *dst = nullptr, *dout = nullptr;
-  int64_t* dt = nullptr;
-  std::vector<void*> tmp;
-  int rc = 0;
+  // device staging for the host buffers: owned by the plan and kept between calls (no allocation, clearing or freeing
+  // inside the call once it has been sized)
+  Plan::HostStage& hs = P->stage;
+  if (batch > hs.cap) {
+    CUDA_OK(cudaDeviceSynchronize());
+    for (void* p : {(void*)hs.x, (void*)hs.noise, (void*)hs.style, (void*)hs.out, (void*)hs.text})
+      if (p) cudaFree(p);
+    hs = Plan::HostStage();
+    CUDA_OK(cudaMalloc((void**)&hs.x, (size_t)batch * xs * sizeof(float)));
+    CUDA_OK(cudaMalloc((void**)&hs.style, (size_t)batch * ss * sizeof(float)));
+    CUDA_OK(cudaMalloc((void**)&hs.text, (size_t)batch * P->L * sizeof(int64_t)));
+    CUDA_OK(cudaMalloc((void**)&hs.out, (size_t)batch * P->T * 3 * sizeof(float)));
+    CUDA_OK(cudaMalloc((void**)&hs.noise, (size_t)DHG_NUM_STEPS * batch * xs * sizeof(float)));
+    hs.cap = batch;
+  }
+  const bool timing = getenv("DHG_TIMING") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    cudaStreamSynchronize(P->cap_stream);
+    fprintf(stderr, "dhg_sample_host: %-10s at %.2f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  };
   cudaStream_t st = P->cap_stream;
-  do {
-    if ((rc = dev_alloc(tmp, (void**)&dx, (size_t)batch * xs * sizeof(float)))) break;
-    if ((rc = dev_alloc(tmp, (void**)&dst, (size_t)batch * ss * sizeof(float)))) break;
-    if ((rc = dev_alloc(tmp, (void**)&dt, (size_t)batch * P->L * sizeof(int64_t)))) break;
-    if ((rc = dev_alloc(tmp, (void**)&dout, (size_t)batch * P->T * 3 * sizeof(float)))) break;
-    if (noise && (rc = dev_alloc(tmp, (void**)&dn, (size_t)DHG_NUM_STEPS * batch * xs * sizeof(float)))) break;
-    cudaError_t e = cudaMemcpyAsync(dx, x0, (size_t)batch * xs * sizeof(float), cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dst, style, (size_t)batch * ss * sizeof(float), cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dt, text, (size_t)batch * P->L * sizeof(int64_t), cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess && noise)
-      e = cudaMemcpyAsync(dn, noise, (size_t)DHG_NUM_STEPS * batch * xs * sizeof(float), cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) { rc = fail("dhg_sample_host: H2D copy failed: %s", cudaGetErrorString(e)); break; }
-    if ((rc = dhg_sample(c, batch, dx, dn, seed, dt, dst, mode, dout, st))) break;
-    e = cudaMemcpyAsync(out, dout, (size_t)batch * P->T * 3 * sizeof(float), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) { rc = fail("dhg_sample_host: %s", cudaGetErrorString(e)); break; }
-  } while (0);
-  for (auto p : tmp) cudaFree(p);
-  return rc;
+  CUDA_OK(cudaMemcpyAsync(hs.x, x0, (size_t)batch * xs * sizeof(float), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(hs.style, style, (size_t)batch * ss * sizeof(float), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(hs.text, text, (size_t)batch * P->L * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  if (noise) CUDA_OK(cudaMemcpyAsync(hs.noise, noise, (size_t)DHG_NUM_STEPS * batch * xs * sizeof(float), cudaMemcpyHostToDevice, st));
+  lap("h2d");
+  if (dhg_sample(c, batch, hs.x, noise ? hs.noise : nullptr, seed, hs.text, hs.style, mode, hs.out, st)) return 1;
+  lap("chain");
+  CUDA_OK(cudaMemcpyAsync(out, hs.out, (size_t)batch * P->T * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  lap("d2h");
+  return 0;
 }
 
 int32_t dhg_posterior_step(dhg_ctx* c, int32_t step, int32_t mode, const float* x, const float* eps, const float* noise,
@@ -1113,6 +1304,12 @@ int32_t dhg_set_option(dhg_ctx* c, const char* key, int32_t value) {
   if (key && !strcmp(key, "pair")) { tc_gemm_set_option(7, value); return 0; }
   if (key && !strcmp(key, "pdl")) { tc_gemm_set_option(6, value); attn_tc_set_debug(value ? -101 : -100); return 0; }
   if (key && !strcmp(key, "w_resident")) { tc_gemm_set_option(2, value); return 0; }
+  if (key && !strcmp(key, "overlap")) { g_opt_overlap = value ? 1 : 0; return 0; }
+  if (key && !strcmp(key, "autotune")) { g_opt_autotune = value ? 1 : 0; return 0; }
+  if (key && !strcmp(key, "tune_bn")) { tc_gemm_set_option(10, value); return 0; }
+  if (key && !strcmp(key, "tune_g")) { tc_gemm_set_option(11, value); return 0; }
+  if (key && !strcmp(key, "tune_resident")) { tc_gemm_set_option(12, value); return 0; }
+  if (key && !strcmp(key, "tune_pair")) { tc_gemm_set_option(13, value); return 0; }
   if (key && !strcmp(key, "specialize")) { tc_gemm_set_option(3, value); return 0; }
   if (!c || !key) return fail("dhg_set_option: null argument");
   if (!strcmp(key, "gemm")) c->opt_gemm = value ? 1 : 0;

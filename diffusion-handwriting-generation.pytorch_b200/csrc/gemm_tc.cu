@@ -666,8 +666,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 
 // experiment switches (dhg_set_option: "w_resident", "specialize", "interleave")
 int g_opt_w_resident = 1, g_opt_specialize = 1, g_opt_interleave = 1, g_opt_pdl = 1, g_opt_pair = 1;
+// forced tile configuration for plans created without an explicit TcTune (tests sweep these through dhg_set_option)
+static TcTune g_tune_default = {-1, -1, -1, -1};
 void tc_gemm_set_option(int which, int value) {
-  if (which == 2) g_opt_w_resident = value;
+  if (which == 10) g_tune_default.bn = value;
+  else if (which == 11) g_tune_default.g = value;
+  else if (which == 12) g_tune_default.resident = value;
+  else if (which == 13) g_tune_default.pair = value;
+  else if (which == 2) g_opt_w_resident = value;
   else if (which == 4) g_opt_interleave = value;
   else if (which == 6) g_opt_pdl = value;
   else if (which == 7) g_opt_pair = value;
@@ -714,7 +720,8 @@ struct TcGemmPlan {
 };
 
 TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W, int K, int N, int taps, const Epilogue& e,
-                                char* err, int errlen) {
+                                char* err, int errlen, const TcTune* tune) {
+  const TcTune tn = tune ? *tune : g_tune_default;
   if (rows >= (1 << 24)) { snprintf(err, errlen, "rows = %d: the epilogue's row arithmetic needs rows < 2^24 (plan a smaller chunk)", rows); return nullptr; }
   if (rows <= 0 || K % 8 || N % 32 || (taps != 1 && taps != 3)) {
     snprintf(err, errlen, "unsupported shape rows=%d K=%d N=%d taps=%d", rows, K, N, taps);
@@ -727,6 +734,10 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   } else {
     for (int cand : {256, 192, 128, 96, 64})
       if (N % cand == 0) { BN = cand; break; }
+    if (tn.bn > 0) {
+      if (N % tn.bn || tn.bn % 32 || (tn.bn > 256 && tn.bn != 384)) { snprintf(err, errlen, "tile width %d does not fit N=%d", tn.bn, N); return nullptr; }
+      BN = tn.bn;
+    }
   }
   if (BN == 0 || BN % 32) { snprintf(err, errlen, "no tile width for N=%d", N); return nullptr; }
   int aux_kind = AUX_NONE, naux = 0;
@@ -765,6 +776,10 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   // independent accumulators per super-tile: as many as fit in one 256-column TMEM group, at most 4
   int G = 1;
   if (g_opt_interleave && BN <= 128) G = BN <= 64 ? 4 : 2;
+  if (tn.g > 0) {
+    if ((tn.g != 1 && tn.g != 2 && tn.g != 4) || (tn.g > 1 && tn.g * BN > 256)) { snprintf(err, errlen, "%d interleaved accumulators of %d columns do not fit a 256-column TMEM group", tn.g, BN); delete p; return nullptr; }
+    G = tn.g;
+  }
   while (G > 1 && (m_tiles + G - 1) / G * sh.n_groups < num_sms) G >>= 1;   // keep every SM busy on small problems
   sh.G = G;
   sh.m_super = (m_tiles + G - 1) / G;
@@ -784,14 +799,16 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   }
   const size_t w_all = (size_t)taps * sh.kb_per_tap * sh.w_tile_bytes;
   const int min_a = G > 1 ? 2 * G : 3;
-  sh.w_resident = (g_opt_w_resident && w_all + (size_t)min_a * sh.a_stage_bytes <= budget && sh.m_super * sh.n_groups > num_sms) ? 1 : 0;
+  const int want_resident = tn.resident >= 0 ? tn.resident : g_opt_w_resident;
+  sh.w_resident = (want_resident && w_all + (size_t)min_a * sh.a_stage_bytes <= budget && sh.m_super * sh.n_groups > num_sms) ? 1 : 0;
   sh.sticky = (sh.w_resident && sh.n_groups > 1) ? 1 : 0;
   // W does not fit: pair the CTAs of a cluster (cta_group::2) so that each SM only ingests half of every W tile
   // Measured (profiles/): pairing pays when the MMA / W-stream phase dominates the tile (K*taps >= 512 and a light
   // epilogue, or the single-buffered 384-wide LayerNorm rows); with g_opt_pair == 2 every non-resident GEMM is paired.
   const int out_mode_plan = (e.out_raw ? 1 : 0) | (e.out_act ? 2 : 0);
   const bool pair_pays = BN == 384 || (taps * K >= 512 && out_mode_plan != 3 && !(e.ln && N <= 192));
-  sh.pair = (!sh.w_resident && g_opt_pair && (g_opt_pair == 2 || pair_pays) && G == 1 && sh.umma_n % 16 == 0 &&
+  const bool want_pair = tn.pair >= 0 ? tn.pair != 0 : (g_opt_pair && (g_opt_pair == 2 || pair_pays));
+  sh.pair = (!sh.w_resident && want_pair && G == 1 && sh.umma_n % 16 == 0 &&
              (m_tiles + 1) / 2 * sh.n_groups >= num_sms / 2) ? 1 : 0;
   if (sh.pair) {
     sh.m_super = (m_tiles + 1) / 2;
@@ -872,6 +889,9 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
 
 void tc_gemm_plan_destroy(TcGemmPlan* p) { delete p; }
 void tc_gemm_set_trace(TcGemmPlan* p, unsigned long long* buf, int cap) { p->sh.trace = buf; p->sh.trace_cap = cap; }
+void tc_gemm_plan_config(const TcGemmPlan* p, TcTune* out) {
+  out->bn = p->sh.BN; out->g = p->sh.G; out->resident = p->sh.w_resident; out->pair = p->sh.pair;
+}
 void tc_gemm_describe(const TcGemmPlan* p, char* out, int n) {
   snprintf(out, n, "pair=%d BN=%d groups=%d m_tiles=%d G=%d stages_a=%d stages_w=%d resident=%d sticky=%d acc_stages=%d grid=%d smem=%zu", p->sh.pair, p->sh.BN, p->sh.n_groups,
            p->sh.m_tiles, p->sh.G, p->sh.stages_a, p->sh.stages_w, p->sh.w_resident, p->sh.sticky, p->sh.acc_stages, (int)p->grid.x, p->smem);

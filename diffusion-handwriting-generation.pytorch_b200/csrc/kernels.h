@@ -64,13 +64,19 @@ void launch_silu_convert(const float* in, T* out, size_t n, cudaStream_t st);
 // tcgen05 / TMA GEMM (gemm_tc.cu).  A: bf16 [rows, K] pitch lda; W: bf16 [taps][N][K]
 // (K contiguous).  Epilogue fused.  Returns 0 on success.
 struct TcGemmPlan;  // opaque: tensor maps + launch geometry, built once at plan time
+// Tile configuration of a plan; -1 = the built-in rule.  bn: tile width (divides N; LayerNorm rows always use N);
+// g: independent accumulators per super-tile (g * bn <= 256); resident: keep W in shared memory for the whole launch
+// (if it fits); pair: cta_group::2 CTA pairs (only with streamed W and g == 1).  Every configuration computes the same
+// bits: the K order of a row's dot product does not depend on it.
+struct TcTune { int bn, g, resident, pair; };
 TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W, int K, int N, int taps,
-                                const Epilogue& e, char* err, int errlen);
+                                const Epilogue& e, char* err, int errlen, const TcTune* tune = nullptr);
+void tc_gemm_plan_config(const TcGemmPlan*, TcTune* out);   // what the plan ended up with
 void tc_gemm_plan_destroy(TcGemmPlan*);
 void tc_gemm_set_trace(TcGemmPlan*, unsigned long long* buf, int cap);   // debug timeline of CTA 0
 void tc_gemm_describe(const TcGemmPlan*, char* out, int n);
 int tc_gemm_launch(const TcGemmPlan*, const Epilogue& e, cudaStream_t st);
-void tc_gemm_set_option(int which, int value);   // 2 w_resident, 3 specialize, 4 interleave (experiments)
+void tc_gemm_set_option(int which, int value);   // 2 w_resident, 3 specialize, 4 interleave, 6 pdl, 7 pair; 10..13 forced TcTune {bn, g, resident, pair}
 
 // tcgen05 attention for head depth 64 and Tk <= 256 (attention_tc.cu).  q_rows / k_rows: total rows
 // of the q / k,v row matrices (TMA bounds).

@@ -122,7 +122,9 @@ int64_t dhg_last_launch_count(const dhg_ctx* ctx);
 int64_t dhg_plan_bytes(const dhg_ctx* ctx);
 /* Engine switches, mainly for tests: key "gemm" = 0 CUDA-core GEMM + row epilogue
  * kernel, 1 tcgen05 GEMM with fused epilogue (bf16 precision only; default 1);
- * "graph" = 0/1 use CUDA graphs in dhg_sample (default 1).  Takes effect at the next dhg_plan. */
+ * "graph" = 0/1 use CUDA graphs in dhg_sample (default 1); "overlap" = 0/1 run the text side of the
+ * next step on a second stream beside the stroke side of the current step (default 1, tcgen05 path
+ * only; ctx may be NULL).  Takes effect at the next dhg_plan. */
 int32_t dhg_set_option(dhg_ctx* ctx, const char* key, int32_t value);
 
 /* Test hook: copy a named intermediate activation of the last forward ("h1", "h2c",

@@ -90,3 +90,62 @@ def test_tc_gemm_fused_epilogue(built_lib, name, rows, K, N, taps, kw):
         assert torch.isfinite(c["out_act"].float()).all()
         err = (c["out_act"].float() - sref).abs().max().item()
         assert err < 2e-2 * scale, (name, "act", err)
+
+
+# The plan-time autotuner (engine.cu Builder::autotune) may pick any of these for a GEMM of the denoiser, so every one
+# must compute the same bits as the built-in rule: tile width x interleaved accumulators x {resident W, streamed W,
+# streamed W + CTA pairs}.
+TUNE_CASES = [
+    ("conv_film_act", 20000, 128, 64, 3, dict(period=50, pad_first=1, film=1, raw=False, act=True)),
+    ("fc_film_respost", 21000, 128, 128, 1, dict(period=99, pad_first=1, film=1, res_post=True, act=True)),
+    ("skipconv_up", 23660, 128, 192, 3, dict(period=169, pad_first=1, res_post=True, up=True, act=True)),
+    ("rowbias_qkv", 20685, 192, 576, 1, dict(period=197, pad_first=1, rowbias=True)),
+    ("rowbias_qkv_1152", 20050, 384, 1152, 1, dict(period=50, pad_first=1, rowbias=True)),
+    ("ffn1_act_768", 20050, 384, 768, 1, dict(period=50, pad_first=1, raw=False, act=True)),
+    ("conv_skip_256", 19999, 384, 256, 3, dict(period=99, pad_first=1)),
+    ("ln_film_respre_384", 20050, 384, 384, 1, dict(period=50, pad_first=1, ln=True, film=1, res_pre=True)),
+    ("ln_film_respost_192", 20685, 192, 192, 1, dict(period=197, pad_first=1, ln=True, film=1, res_post=True)),
+]
+
+
+@pytest.mark.parametrize("name,rows,K,N,taps,kw", TUNE_CASES, ids=[c[0] for c in TUNE_CASES])
+def test_tc_gemm_every_tile_configuration_gives_the_same_bits(built_lib, name, rows, K, N, taps, kw):
+    import gemm_ref
+
+    def setopt(**o):
+        for k, v in o.items():
+            assert built_lib.dhg_set_option(None, f"tune_{k}".encode(), v) == 0
+
+    def outputs(c):
+        return [t.clone() for t in (c["out_raw"], c["out_act"]) if t is not None]
+
+    try:
+        setopt(bn=-1, g=-1, resident=-1, pair=-1)
+        c = gemm_ref.make_case(rows, K, N, taps, seed=len(name) + rows, **kw)
+        gemm_ref.run(built_lib, c)
+        base = outputs(c)
+        ref = gemm_ref.reference(c)
+        first = base[0].float() if c["out_raw"] is not None else None
+        if first is not None:
+            assert (first - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+        tried = 0
+        bns = [N] if kw.get("ln") else [b for b in (384, 256, 192, 128, 96, 64) if N % b == 0]
+        for bn in bns:
+            for g in (1, 2, 4):
+                if g > 1 and g * bn > 256:
+                    continue
+                for resident, pair in ((1, 0), (0, 0), (0, 1)):
+                    if pair and g != 1:
+                        continue
+                    setopt(bn=-1 if kw.get("ln") else bn, g=g, resident=resident, pair=pair)
+                    for t in (c["out_raw"], c["out_act"]):
+                        if t is not None:
+                            t.fill_(float("nan"))
+                    if gemm_ref.run(built_lib, c, allow_unavailable=True) is None:
+                        continue
+                    tried += 1
+                    for got, want in zip(outputs(c), base):
+                        assert torch.equal(got.view(torch.int16), want.view(torch.int16)), (name, bn, g, resident, pair)
+        assert tried >= 2, tried
+    finally:
+        setopt(bn=-1, g=-1, resident=-1, pair=-1)

@@ -18,3 +18,40 @@ def test_gemm_cases_under_switch(opts):
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_gemm.py"), "-x", "-q", "-m", "gpu",
                         "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, cwd=ROOT, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+_CHAIN = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, {root!r}); sys.path.insert(0, {pkg!r})
+from dhg_b200 import DiffusionWriter
+from oracle.dhg_oracle import init_state_dict
+w = DiffusionWriter(state_dict=init_state_dict(0), num_layers=2, channels=128, dtype="bf16")
+if len(sys.argv) > 2 and sys.argv[2] == "nograph":
+    assert w._lib.dhg_set_option(w._ctx, b"graph", 0) == 0
+g = torch.Generator().manual_seed(7)
+B, T, L = 48, 392, 24
+text = torch.randint(2, 73, (B, L), generator=g); text[:, -1] = 1; text[::3, 17:] = 0
+style = torch.randn(B, 14, 1280, generator=g)
+x0 = torch.randn(B, T, 2, generator=g)
+noise = torch.randn(60, B, T, 2, generator=g)
+out = w.sample(text, style, T=T, x0=x0, noise=noise)
+np.save(sys.argv[1], out.float().cpu().numpy())
+"""
+
+
+def test_chain_is_bit_identical_with_and_without_text_overlap(tmp_path):
+    """The text side of step i-1 runs on a second stream beside the stroke side of step i (engine.cu run_chain);
+    serial order (overlap=0), and the two streams without a CUDA graph, must give the same bits."""
+    import numpy as np
+
+    code = _CHAIN.format(root=ROOT, pkg=os.path.join(ROOT, "diffusion-handwriting-generation.pytorch_b200"))
+    outs = {}
+    for name, opts, graph in [("overlap", "", "graph"), ("serial", "overlap=0", "graph"), ("overlap_streams", "", "nograph")]:
+        f = str(tmp_path / f"{name}.npy")
+        r = subprocess.run([sys.executable, "-c", code, f, graph], env=dict(os.environ, DHG_OPTS=opts), capture_output=True, text=True,
+                           cwd=ROOT, timeout=900)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        outs[name] = np.load(f)
+    assert np.isfinite(outs["overlap"]).all()
+    assert np.array_equal(outs["overlap"], outs["serial"])
+    assert np.array_equal(outs["overlap"], outs["overlap_streams"])
