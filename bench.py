@@ -90,6 +90,10 @@ class ClockSampler:
     def stop(self):
         if self.proc:
             self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)   # the poller must be gone before the host-timed e2e leg starts
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -185,8 +189,11 @@ def run_b200(args, rank, world, local_rank):
     w.sample_host(text_h, style_h, x0_h, noise_h)
     barrier()
     t0 = time.perf_counter()
+    e2e_calls = []
     for _ in range(args.e2e_steps):
-        out_h = w.sample_host(text_h, style_h, x0_h, noise_h)
+        tc = time.perf_counter()
+        out_h = w.sample_host(text_h, style_h, x0_h, noise_h)   # returns after the device->host copy has completed
+        e2e_calls.append(round(1e3 * (time.perf_counter() - tc), 2))
     torch.cuda.synchronize(dev)
     e2e_s = maxreduce(time.perf_counter() - t0)
     barrier()
@@ -247,7 +254,7 @@ def run_b200(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "lines/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": args.e2e_steps, "api": "DiffusionWriter.sample_host -> dhg_sample_host (pinned host buffers)"},
+                "steps": args.e2e_steps, "ms_per_call": e2e_calls, "api": "DiffusionWriter.sample_host -> dhg_sample_host (pinned host buffers)"},
         "roofline": {
             "bound": "tensor", "achieved": tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": tflops / peak_tf,
             "traffic": None, "peak_source": peaks["source"] + " (bf16_tflops_sustained: chain timed inside a long step)",
@@ -287,7 +294,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="prompts per GPU")
     ap.add_argument("--chunk", type=int, default=1024, help="prompts per captured chain")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--ref-batch", type=int, default=32, help="prompts per CPU-baseline chain")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-gemm-roofline", dest="gemm_roofline", action="store_false")

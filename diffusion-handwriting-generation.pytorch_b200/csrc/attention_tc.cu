@@ -39,6 +39,7 @@ struct AttnTcShape {
   int halves;     // softmax warps per TMEM lane quarter (1 or 2): the score columns are split between them
   int QT;         // query tiles per (sample, head)
   int items;      // B * H * QT
+  int rev;        // walk the items from the last to the first
   uint32_t idesc_s, idesc_o;
   uint32_t off_k, off_v, off_mask, off_xchg, slot_bytes, off_bar;
   float scale_log2;   // scale * log2(e)
@@ -46,6 +47,7 @@ struct AttnTcShape {
 };
 
 __device__ __forceinline__ void item_coords(const AttnTcShape& sh, const AttnParams& p, int item, int& qt, int& h, int& b) {
+  if (sh.rev) item = sh.items - 1 - item;
   qt = item % sh.QT;
   const int bh = item / sh.QT;
   h = bh % p.H;
@@ -303,6 +305,7 @@ AttnTcPlan* attn_tc_plan_create(const AttnParams& p, int q_rows, int k_rows, cha
   sh.tmem_cols = cols <= 64 ? 64 : cols <= 128 ? 128 : 256;
   sh.QT = (p.Tq + 127) / 128;
   sh.items = p.B * p.H * sh.QT;
+  sh.rev = 0;
   // c_format F32 [4,6) | a,b BF16 [7,10),[10,13) | b_major [16] | N>>3 [17,23) | M>>4 [24,29)
   const uint32_t base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
   sh.idesc_s = base | ((uint32_t)(sh.N >> 3) << 17);
@@ -345,6 +348,7 @@ AttnTcPlan* attn_tc_plan_create(const AttnParams& p, int q_rows, int k_rows, cha
 }
 
 void attn_tc_plan_destroy(AttnTcPlan* a) { delete a; }
+void attn_tc_plan_set_reverse(AttnTcPlan* a, int rev) { a->sh.rev = rev ? 1 : 0; }
 
 int attn_tc_launch(const AttnTcPlan* a, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};

@@ -46,6 +46,7 @@ using namespace dhg;
 // ---------------------------------------------------------------------------
 static thread_local char g_err[1024] = "";
 static int g_opt_autotune = 1;  // time every GEMM tile configuration at plan time and keep the fastest ("autotune")
+static int g_opt_serpentine = 1; // consumer kernels walk their rows opposite to their producer ("serpentine")
 static int g_opt_overlap = 1;   // text side of step i-1 beside the stroke side of step i (dhg_set_option "overlap")
 static int fail(const char* fmt, ...) {
   va_list ap;
@@ -157,6 +158,7 @@ struct Plan {
   HostStage stage;   // device copies of dhg_sample_host's host buffers
   struct Tap { Act a; int period; int pad; };
   std::map<std::string, Tap> taps;  // named activations readable through dhg_debug_read
+  std::map<const void*, int> dir_of;   // walking direction of the kernel that wrote each activation (Builder::dir_of)
 };
 
 }  // namespace
@@ -405,6 +407,16 @@ struct Builder {
   int64_t* nlaunch;
   bool failed = false;
 
+  // Walking direction of the kernel that wrote each activation (P->dir_of: buffer -> 0 first row to last, 1 last to
+  // first).  A GEMM / attention launch walks its rows in the direction OPPOSITE to the producer of its input, so it
+  // starts on the rows that are still in L2 and meets the evicted ones last.  Kernels without a direction switch
+  // (pool, FiLM rows, heads) count as 0.
+  int dir_of(const void* p) const {
+    auto it = P->dir_of.find(p);
+    return it == P->dir_of.end() ? 0 : it->second;
+  }
+  void wrote(const void* p, int dir) { if (p) P->dir_of[p] = dir; }
+
   Act act(int rows, int C) {
     Act a;
     a.rows = rows;
@@ -534,6 +546,9 @@ struct Builder {
         tcp = autotune(tcp, (const bf16*)Ap, A.C, rows, W, e, et, wkey);
         if (!tcp) { failed = true; return; }
       }
+      const int dir = g_opt_serpentine ? !dir_of(Ap) : 0;
+      tc_gemm_plan_set_reverse(tcp, dir);
+      wrote(e.out_raw, dir); wrote(e.out_act, dir);
       P->tc_plans.push_back(tcp);
     }
     *nlaunch += tcp ? 1 : 2;
@@ -578,6 +593,9 @@ struct Builder {
         char buf[512];
         plans[s] = attn_tc_plan_create(a[s], q_rows, k_rows, buf, sizeof(buf));
         if (!plans[s]) { fail("plan: tcgen05 attention: %s", buf); failed = true; return; }
+        const int dir = g_opt_serpentine ? !dir_of(q) : 0;
+        attn_tc_plan_set_reverse(plans[s], dir);
+        wrote(o.p, dir);
         P->attn_plans.push_back(plans[s]);
         tc = true;
       }
@@ -1306,6 +1324,8 @@ int32_t dhg_set_option(dhg_ctx* c, const char* key, int32_t value) {
   if (key && !strcmp(key, "w_resident")) { tc_gemm_set_option(2, value); return 0; }
   if (key && !strcmp(key, "overlap")) { g_opt_overlap = value ? 1 : 0; return 0; }
   if (key && !strcmp(key, "autotune")) { g_opt_autotune = value ? 1 : 0; return 0; }
+  if (key && !strcmp(key, "serpentine")) { g_opt_serpentine = value ? 1 : 0; return 0; }
+  if (key && !strcmp(key, "tune_rev")) { tc_gemm_set_option(14, value); return 0; }
   if (key && !strcmp(key, "tune_bn")) { tc_gemm_set_option(10, value); return 0; }
   if (key && !strcmp(key, "tune_g")) { tc_gemm_set_option(11, value); return 0; }
   if (key && !strcmp(key, "tune_resident")) { tc_gemm_set_option(12, value); return 0; }

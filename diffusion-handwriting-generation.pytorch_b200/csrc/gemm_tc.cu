@@ -54,6 +54,7 @@ struct TcShape {
   int m_tiles;
   int G;           // row tiles per super-tile (independent accumulators interleaved by the MMA warp)
   int m_super;     // ceil(m_tiles / G)
+  int rev;         // walk the super-tiles from the last row to the first (see tc_gemm_plan_set_reverse)
   int stages_a, stages_w;   // A ring / W ring depth (W ring unused when w_resident)
   int w_resident;  // all W tiles of this CTA's column group stay in smem for the whole kernel
   int sticky;      // each CTA works on one column group only
@@ -299,8 +300,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     // ring positions are kept incrementally (no integer division in these latency-critical loops)
     uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
     for (int t = t_first; t < t_end; t += t_step) {
-      const int mts = one_group ? t : t / sh.n_groups;
-      const int ng = sh.sticky ? my_group : t - mts * sh.n_groups;
+      const int mts_f = one_group ? t : t / sh.n_groups;
+      const int ng = sh.sticky ? my_group : t - mts_f * sh.n_groups;
+      const int mts = sh.rev ? sh.m_super - 1 - mts_f : mts_f;
       const int n0 = ng * sh.BN;
       for (int kbi = 0; kbi < sh.kb_per_tap; ++kbi) {
         const int kk = kbi * TC_BK;
@@ -417,8 +419,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       const int ft = iss_t, fsub = iss_sub, ci = iss_ci;
       if (ft < t_end) {
         if (ci == 0) {   // first chunk of a row tile: where does my row's residual / bias row live?
-          const int fmts = one_group ? ft : ft / sh.n_groups;
-          iss_ng = sh.sticky ? my_group : ft - fmts * sh.n_groups;
+          const int fmts_f = one_group ? ft : ft / sh.n_groups;
+          iss_ng = sh.sticky ? my_group : ft - fmts_f * sh.n_groups;
+          const int fmts = sh.rev ? sh.m_super - 1 - fmts_f : fmts_f;
           const int fm = (fmts * tiles_per_super + fsub + (int)cta_rank) * TC_BM + r_tile;
           const bool f_in = fm < sh.rows;
           if (aux_same_row) {
@@ -484,8 +487,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 
     int it = 0, tile_no = 0;
     for (int t = t_first; t < t_end; t += t_step, ++it) {
-     const int mts = one_group ? t : t / sh.n_groups;
-     const int ng = sh.sticky ? my_group : t - mts * sh.n_groups;
+     const int mts_f = one_group ? t : t / sh.n_groups;
+     const int ng = sh.sticky ? my_group : t - mts_f * sh.n_groups;
+     const int mts = sh.rev ? sh.m_super - 1 - mts_f : mts_f;
      const int n0 = ng * sh.BN;
      const int as = sh.acc_stages == 2 ? (it & 1) : 0;
      const uint32_t use = sh.acc_stages == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;
@@ -668,8 +672,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 int g_opt_w_resident = 1, g_opt_specialize = 1, g_opt_interleave = 1, g_opt_pdl = 1, g_opt_pair = 1;
 // forced tile configuration for plans created without an explicit TcTune (tests sweep these through dhg_set_option)
 static TcTune g_tune_default = {-1, -1, -1, -1};
+static int g_tune_rev = 0;   // default walking direction of new plans (tests)
 void tc_gemm_set_option(int which, int value) {
-  if (which == 10) g_tune_default.bn = value;
+  if (which == 14) g_tune_rev = value ? 1 : 0;
+  else if (which == 10) g_tune_default.bn = value;
   else if (which == 11) g_tune_default.g = value;
   else if (which == 12) g_tune_default.resident = value;
   else if (which == 13) g_tune_default.pair = value;
@@ -771,6 +777,7 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   sh.acc_stages = BN <= 256 ? 2 : 1;
   sh.aux_kind = aux_kind;
   sh.trace = nullptr; sh.trace_cap = 0;
+  sh.rev = g_tune_rev;
   sh.vec_bias_n = e.bias ? N : 0;
   sh.film_n = e.film_planned ? N : 0;
   // independent accumulators per super-tile: as many as fit in one 256-column TMEM group, at most 4
@@ -889,6 +896,7 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
 
 void tc_gemm_plan_destroy(TcGemmPlan* p) { delete p; }
 void tc_gemm_set_trace(TcGemmPlan* p, unsigned long long* buf, int cap) { p->sh.trace = buf; p->sh.trace_cap = cap; }
+void tc_gemm_plan_set_reverse(TcGemmPlan* p, int rev) { p->sh.rev = rev ? 1 : 0; }
 void tc_gemm_plan_config(const TcGemmPlan* p, TcTune* out) {
   out->bn = p->sh.BN; out->g = p->sh.G; out->resident = p->sh.w_resident; out->pair = p->sh.pair;
 }

@@ -72,6 +72,9 @@ struct TcTune { int bn, g, resident, pair; };
 TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W, int K, int N, int taps,
                                 const Epilogue& e, char* err, int errlen, const TcTune* tune = nullptr);
 void tc_gemm_plan_config(const TcGemmPlan*, TcTune* out);   // what the plan ended up with
+// Walk the row tiles from the last to the first.  The engine gives every kernel the direction opposite to the kernel
+// that wrote its input, so it starts on the rows that are still in the 126 MB L2 (same bits either way).
+void tc_gemm_plan_set_reverse(TcGemmPlan*, int rev);
 void tc_gemm_plan_destroy(TcGemmPlan*);
 void tc_gemm_set_trace(TcGemmPlan*, unsigned long long* buf, int cap);   // debug timeline of CTA 0
 void tc_gemm_describe(const TcGemmPlan*, char* out, int n);
@@ -84,6 +87,7 @@ struct AttnTcPlan;
 bool attn_tc_supported(const AttnParams& p);
 AttnTcPlan* attn_tc_plan_create(const AttnParams& p, int q_rows, int k_rows, char* err, int errlen);
 void attn_tc_plan_destroy(AttnTcPlan*);
+void attn_tc_plan_set_reverse(AttnTcPlan*, int rev);   // work items from the last sample to the first
 int attn_tc_launch(const AttnTcPlan*, cudaStream_t st);
 void attn_tc_set_debug(int flags);   // timing experiments only
 

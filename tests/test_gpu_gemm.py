@@ -147,5 +147,10 @@ def test_tc_gemm_every_tile_configuration_gives_the_same_bits(built_lib, name, r
                     for got, want in zip(outputs(c), base):
                         assert torch.equal(got.view(torch.int16), want.view(torch.int16)), (name, bn, g, resident, pair)
         assert tried >= 2, tried
+        # row tiles walked from the last to the first (the engine alternates the direction from kernel to kernel)
+        setopt(bn=-1, g=-1, resident=-1, pair=-1, rev=1)
+        gemm_ref.run(built_lib, c)
+        for got, want in zip(outputs(c), base):
+            assert torch.equal(got.view(torch.int16), want.view(torch.int16)), (name, "reverse")
     finally:
-        setopt(bn=-1, g=-1, resident=-1, pair=-1)
+        setopt(bn=-1, g=-1, resident=-1, pair=-1, rev=0)
