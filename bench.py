@@ -102,6 +102,17 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def measured_traffic():
+    """DRAM bytes per denoiser step from the committed ncu capture (profiles/): dram__bytes_read + dram__bytes_write
+    summed over the launches of one step.  None when the summary is missing."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_step_dram_traffic_v12.json")
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return None
+
+
 def cpu_oracle_leg(batch, chains, warmup):
     """The reference's CPU path (oracle port, torch CPU fp32, all host cores) on a bounded sample of
     the same workload: `batch` prompts of T=392/L=24 through full 60-step chains."""
@@ -238,6 +249,7 @@ def run_b200(args, rank, world, local_rank):
     f_alg = flops_alg_per_sample_step(T, L)
     tflops = B * f_alg * NUM_STEPS / (ms_step * 1e-3) / 1e12
     peak_tf = peaks["bf16_tflops_sustained"]
+    traffic = measured_traffic()
     line = {
         "metric": "sampled handwriting lines/s (full 60-step reverse chain)", "value": value, "unit": "lines/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -257,7 +269,9 @@ def run_b200(args, rank, world, local_rank):
                 "steps": args.e2e_steps, "ms_per_call": e2e_calls, "api": "DiffusionWriter.sample_host -> dhg_sample_host (pinned host buffers)"},
         "roofline": {
             "bound": "tensor", "achieved": tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": tflops / peak_tf,
-            "traffic": None, "peak_source": peaks["source"] + " (bf16_tflops_sustained: chain timed inside a long step)",
+            "traffic": (traffic or {}).get("step_dram_bytes") if B == 1024 else None,
+            "traffic_unit": "DRAM bytes per denoiser step, all launches (ncu, profiles/r1_step_dram_traffic_v12.json)",
+            "peak_source": peaks["source"] + " (bf16_tflops_sustained: chain timed inside a long step)",
             "definition": "B * F_alg(T,L) * 60 / t_chain (SURVEY.md 8d); F_alg = %.1f MFLOP/sample/step" % (f_alg / 1e6),
         },
         "roofline_posterior_update": {
@@ -270,7 +284,9 @@ def run_b200(args, rank, world, local_rank):
         line["roofline_gemm"] = {
             "kernel": "tc_gemm_kernel (all %d launches of one denoiser step, each family timed alone, 5 launches per family)" % gemm["launches"],
             "bound": "hbm", "achieved": gemm["bytes"] / us / 1e3, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": gemm["bytes"] / us / 1e3 / peaks["hbm_gbs"], "traffic": None,
+            "frac": gemm["bytes"] / us / 1e3 / peaks["hbm_gbs"],
+            "traffic": (traffic or {}).get("gemm_dram_bytes_per_step"),
+            "traffic_unit": "DRAM bytes of the same launches (ncu, cold L2 per kernel; writes still in L2 at kernel end not counted)",
             "tflops": gemm["flop"] / us / 1e6, "tensor_frac": gemm["flop"] / us / 1e6 / peaks["bf16_tflops"],
             "us_per_step": us, "share_of_step": us / (ms_step / NUM_STEPS * 1e3),
             "algorithmic_bytes_per_step": gemm["bytes"], "flop_per_step": gemm["flop"],

@@ -30,6 +30,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <chrono>
 #include <functional>
 #include <map>
@@ -46,8 +47,9 @@ using namespace dhg;
 // ---------------------------------------------------------------------------
 static thread_local char g_err[1024] = "";
 static int g_opt_autotune = 1;  // time every GEMM tile configuration at plan time and keep the fastest ("autotune")
+static int g_opt_l2_hints = 1;   // streamed GEMM inputs get L2 evict-first priority ("l2_hints")
 static int g_opt_serpentine = 1; // consumer kernels walk their rows opposite to their producer ("serpentine")
-static int g_opt_overlap = 1;   // text side of step i-1 beside the stroke side of step i (dhg_set_option "overlap")
+static int g_opt_text_sets = 2;  // text sides of this many consecutive steps run at once (dhg_set_option "text_sets")
 static int fail(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -91,13 +93,14 @@ struct Lin {
   std::vector<float> h_b;
 };
 
+constexpr int kMaxTextSets = 6;
+
 struct StepCtx {
   const float* cond;  // FiLM vectors: cond[b * bstride + off]
   int bstride;
   bool skip_input_dense;  // in_raw / in_act were already written by the previous step's head kernel
   bool fuse_next_input;   // this step's head kernel also writes in_raw / in_act of the next step
   int text_set;           // which copy of the text-side buffers this step's cross-attention reads
-  cudaEvent_t text_ready; // recorded after that copy was produced on the text stream (null: same stream, already ordered)
   HeadParams head;
 };
 typedef std::function<int(cudaStream_t, const StepCtx&)> Op;
@@ -141,12 +144,13 @@ struct Plan {
   size_t scratch_elems = 0;
   int* err_flag = nullptr;
   // once_ops: step-independent; text_ops[set]: the part of a step that depends on sigma but not on x (TextStyleEncoder,
-  // text_dense and k/v projections of every EncoderLayer); step_ops: everything that depends on x.  With two text sets
-  // the text side of step i-1 runs on text_stream while the stroke side of step i runs on the caller's stream.
-  std::vector<Op> once_ops, text_ops[2], step_ops;
+  // text_dense and k/v projections of every EncoderLayer); step_ops: everything that depends on x.  The text side is
+  // small (192 row tiles on 148 SMs per launch), so the text sides of `text_sets` consecutive steps are run at once,
+  // one stream each, before the first of those steps: their launches fill each other's last waves.
+  std::vector<Op> once_ops, text_ops[kMaxTextSets], step_ops;
   int text_sets = 1;
-  cudaStream_t text_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_text[DHG_NUM_STEPS] = {};
+  cudaStream_t text_stream[kMaxTextSets] = {};   // [0] unused: set 0 runs on the caller's stream
+  cudaEvent_t ev_fork = nullptr, ev_text[kMaxTextSets] = {};
   Act head_in, in_raw, in_act;
   std::vector<TcGemmPlan*> tc_plans;
   std::vector<AttnTcPlan*> attn_plans;
@@ -350,7 +354,8 @@ void free_plan(Plan* p) {
   for (auto t : p->tc_plans) tc_gemm_plan_destroy(t);
   for (auto t : p->attn_plans) attn_tc_plan_destroy(t);
   if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
-  if (p->text_stream) cudaStreamDestroy(p->text_stream);
+  for (auto t : p->text_stream)
+    if (t) cudaStreamDestroy(t);
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
   for (auto e : p->ev_text)
     if (e) cudaEventDestroy(e);
@@ -548,6 +553,7 @@ struct Builder {
       }
       const int dir = g_opt_serpentine ? !dir_of(Ap) : 0;
       tc_gemm_plan_set_reverse(tcp, dir);
+      tc_gemm_plan_set_a_evict_first(tcp, g_opt_l2_hints);
       wrote(e.out_raw, dir); wrote(e.out_act, dir);
       P->tc_plans.push_back(tcp);
     }
@@ -571,14 +577,13 @@ struct Builder {
     });
   }
 
-  // k / v may exist in up to two copies (text sets); the launch picks sc.text_set.  wait_text: this is the first
-  // consumer of the text side in a step, so it first waits for the text stream's event (if the step has one).
+  // k / v may exist in several copies (text sets); the launch picks sc.text_set.
   void attention_sets(const void* q, int qp, const void* const* ks, const void* const* vs, int nsets, int kp, int vp,
                       const Act& o, int H, int D, int Tq, int q_period, int q_pad, int Tk, int k_period, int k_pad,
-                      bool masked, int q_rows, int k_rows, bool wait_text) {
+                      bool masked, int q_rows, int k_rows) {
     if (failed) return;
-    AttnParams a[2];
-    AttnTcPlan* plans[2] = {nullptr, nullptr};
+    std::vector<AttnParams> a(nsets);
+    std::vector<AttnTcPlan*> plans(nsets, nullptr);
     Plan* Pl = P;
     *nlaunch += 1;
     bool tc = false;
@@ -600,22 +605,16 @@ struct Builder {
         tc = true;
       }
     }
-    if (nsets == 1) { a[1] = a[0]; plans[1] = plans[0]; }
-    const AttnParams a0 = a[0], a1 = a[1];
-    AttnTcPlan *p0 = plans[0], *p1 = plans[1];
     ops->push_back([=](cudaStream_t st, const StepCtx& sc) -> int {
-      if (wait_text && sc.text_ready && cudaStreamWaitEvent(st, sc.text_ready, 0) != cudaSuccess)
-        return fail("cudaStreamWaitEvent(text side): %s", cudaGetErrorString(cudaGetLastError()));
-      const int set = sc.text_set ? 1 : 0;
-      if (tc) return attn_tc_launch(set ? p1 : p0, st) ? fail("tcgen05 attention launch failed: %s", cudaGetErrorString(cudaGetLastError())) : 0;
-      const AttnParams& aa = set ? a1 : a0;
-      const int r = Pl->prec == PREC_FP32 ? launch_attention_simt<float>(aa, st) : launch_attention_simt<bf16>(aa, st);
-      return r ? fail("attention: unsupported head depth %d", aa.D) : 0;
+      const int set = (sc.text_set >= 0 && sc.text_set < nsets) ? sc.text_set : 0;
+      if (tc) return attn_tc_launch(plans[set], st) ? fail("tcgen05 attention launch failed: %s", cudaGetErrorString(cudaGetLastError())) : 0;
+      const int r = Pl->prec == PREC_FP32 ? launch_attention_simt<float>(a[set], st) : launch_attention_simt<bf16>(a[set], st);
+      return r ? fail("attention: unsupported head depth %d", a[set].D) : 0;
     });
   }
   void attention(const void* q, int qp, const void* k, int kp, const void* v, int vp, const Act& o, int H, int D,
                  int Tq, int q_period, int q_pad, int Tk, int k_period, int k_pad, bool masked, int q_rows, int k_rows) {
-    attention_sets(q, qp, &k, &v, 1, kp, vp, o, H, D, Tq, q_period, q_pad, Tk, k_period, k_pad, masked, q_rows, k_rows, false);
+    attention_sets(q, qp, &k, &v, 1, kp, vp, o, H, D, Tq, q_period, q_pad, Tk, k_period, k_pad, masked, q_rows, k_rows);
   }
 
   void film_rows(const Act& in, const Act& out, int period, int film_off) {
@@ -688,8 +687,7 @@ struct Builder {
   }
 
   // model.py:35-58, stroke side (kvs: the k | v rows written by encoder_text, one per text set)
-  Act encoder_layer(const std::string& p, const Act& x, const Act* kvs, int nsets, int heads, float pos_factor, int level,
-                    bool first_text_consumer) {
+  Act encoder_layer(const std::string& p, const Act& x, const Act* kvs, int nsets, int heads, float pos_factor, int level) {
     const int R = P->R[level], dm = x.C, Tl = P->Tl[level], L = P->L;
     const RowMap m = map_level(level);
     const int D = dm / heads;
@@ -706,9 +704,9 @@ struct Builder {
     Act qkv = act(R, 3 * dm), o2 = act(R, dm), x3r = act(R, dm), x3a = act(R, dm), hid = act(R, 2 * dm), out = act(R, dm);
     EpiSpec sq; sq.rowbias = rb_q; sq.rowbias16 = rb16_q; sq.rowbias16_cols = dm; sq.out_raw = q;
     gemm(x, p + ".mha.wq", sq, m);
-    const void *ks[2], *vs[2];
+    const void *ks[kMaxTextSets], *vs[kMaxTextSets];
     for (int s = 0; s < nsets; ++s) { ks[s] = kvs[s].p; vs[s] = col(kvs[s], dm); }
-    attention_sets(q.p, dm, ks, vs, nsets, 2 * dm, 2 * dm, o, heads, D, Tl, Tl + 1, 1, L, L, 0, true, R, P->RT, first_text_consumer);
+    attention_sets(q.p, dm, ks, vs, nsets, 2 * dm, 2 * dm, o, heads, D, Tl, Tl + 1, 1, L, L, 0, true, R, P->RT);
     EpiSpec sd; sd.ln = true; sd.film_off = film(p + ".affine1"); sd.res_post = x; sd.out_raw = x2;
     gemm(o, p + ".mha.dense", sd, m);
     EpiSpec sqkv; sqkv.rowbias = rb_qkv; sqkv.rowbias16 = rb16_qkv; sqkv.rowbias16_cols = 2 * dm; sqkv.out_raw = qkv;
@@ -777,15 +775,17 @@ int build_plan(dhg_ctx* c, Plan* P) {
   // ---- per-step, text side (depends on the step through FiLM only, never on x): one op list per text set ----
   std::vector<std::string> enc_names = {"enc3", "enc5"};
   for (int i = 0; i < c->cfg.num_layers; ++i) enc_names.push_back("att_layers." + std::to_string(i));
-  // two sets (and a second stream) only where every text-side launch is a self-contained tcgen05 kernel: the CUDA-core
+  // several sets (and streams) only where every text-side launch is a self-contained tcgen05 kernel: the CUDA-core
   // GEMM path shares one fp32 scratch buffer between launches and must stay serial
-  P->text_sets = (g_opt_overlap && P->prec == PREC_BF16 && P->gemm_impl == 1) ? 2 : 1;
-  if (P->text_sets == 2) {
-    CUDA_OK(cudaStreamCreateWithFlags(&P->text_stream, cudaStreamNonBlocking));
+  P->text_sets = (P->prec == PREC_BF16 && P->gemm_impl == 1) ? std::min(std::max(g_opt_text_sets, 1), kMaxTextSets) : 1;
+  if (P->text_sets > 1) {
     CUDA_OK(cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming));
-    for (auto& e : P->ev_text) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (int i = 1; i < P->text_sets; ++i) {
+      CUDA_OK(cudaStreamCreateWithFlags(&P->text_stream[i], cudaStreamNonBlocking));
+      CUDA_OK(cudaEventCreateWithFlags(&P->ev_text[i], cudaEventDisableTiming));
+    }
   }
-  std::vector<Act> kv_sets[2];
+  std::vector<Act> kv_sets[kMaxTextSets];
   Act text_act0, tf0, sf0, t1a0, to0;
   for (int set = 0; set < P->text_sets; ++set) {
     int64_t other = 0;
@@ -837,15 +837,15 @@ int build_plan(dhg_ctx* c, Plan* P) {
   Act p1r = bd.act(P->R[1], c1), p1a = bd.act(P->R[1], c1);
   bd.pool(h1, p1r, p1a, P->Tl[1]);
   Act h2c = bd.conv_block("enc2", p1r, p1a, c2, 1, false, &dummy);
-  Act kvl[2];
+  Act kvl[kMaxTextSets];
   kvs_of(0, kvl);
-  Act h2 = bd.encoder_layer("enc3", h2c, kvl, P->text_sets, 3, 4.0f, 1, true);
+  Act h2 = bd.encoder_layer("enc3", h2c, kvl, P->text_sets, 3, 4.0f, 1);
   tap("h2c", h2c, 1); tap("h2", h2, 1);
   Act p2r = bd.act(P->R[2], c2), p2a = bd.act(P->R[2], c2);
   bd.pool(h2, p2r, p2a, P->Tl[2]);
   Act h3c = bd.conv_block("enc4", p2r, p2a, c3, 2, false, &dummy);
   kvs_of(1, kvl);
-  Act h3 = bd.encoder_layer("enc5", h3c, kvl, P->text_sets, 4, 2.0f, 2, false);
+  Act h3 = bd.encoder_layer("enc5", h3c, kvl, P->text_sets, 4, 2.0f, 2);
   tap("h3c", h3c, 2); tap("h3", h3, 2);
   Act p3r = bd.act(P->R[3], c3);
   bd.pool(h3, p3r, Act(), P->Tl[3]);
@@ -854,7 +854,7 @@ int build_plan(dhg_ctx* c, Plan* P) {
   tap("att_in", xa, 3);
   for (int i = 0; i < c->cfg.num_layers; ++i) {
     kvs_of(2 + i, kvl);
-    xa = bd.encoder_layer("att_layers." + std::to_string(i), xa, kvl, P->text_sets, 6, 1.0f, 3, false);
+    xa = bd.encoder_layer("att_layers." + std::to_string(i), xa, kvl, P->text_sets, 6, 1.0f, 3);
     tap(("att" + std::to_string(i)).c_str(), xa, 3);
   }
   // decoder: upsample(x) + skip_conv(h) (model.py:169-176), then ConvBlock
@@ -937,10 +937,10 @@ int run_chain(dhg_ctx* c, Plan* P, int mode, bool has_noise, cudaStream_t st) {
   sc.cond = c->cond60;
   sc.bstride = 0;
   if (run_ops(P->once_ops, st, sc)) return 1;
-  // The text side of a step does not depend on x: with two text sets, step i-1's text side runs on text_stream while
-  // step i's stroke side runs on st (it fills the SMs the stroke kernels leave idle in their last wave, and the other
-  // way round).  Set (i & 1) is written for step i; its previous reader was step i+2, which ended before step i+1 began.
-  const bool overlap = P->text_sets == 2;
+  // The text side of a step does not depend on x.  Before step i with (59 - i) % n == 0 the text sides of steps
+  // i, i-1, .., i-n+1 are launched together, set (j % n) for step j, set 0's on st and the others on their own streams
+  // (forked from and joined back into st); the previous reader of a set, step j+n, has finished by then.
+  const int n = P->text_sets;
   auto text_ctx = [&](int i) {
     StepCtx t;
     memset(&t, 0, sizeof(t));
@@ -948,20 +948,23 @@ int run_chain(dhg_ctx* c, Plan* P, int mode, bool has_noise, cudaStream_t st) {
     t.bstride = 0;
     return t;
   };
-  if (overlap && run_ops(P->text_ops[(DHG_NUM_STEPS - 1) & 1], st, text_ctx(DHG_NUM_STEPS - 1))) return 1;
   for (int i = DHG_NUM_STEPS - 1; i >= 0; --i) {
-    if (overlap && i > 0) {
-      CUDA_OK(cudaEventRecord(P->ev_fork, st));
-      CUDA_OK(cudaStreamWaitEvent(P->text_stream, P->ev_fork, 0));
-      if (run_ops(P->text_ops[(i - 1) & 1], P->text_stream, text_ctx(i - 1))) return 1;
-      CUDA_OK(cudaEventRecord(P->ev_text[i - 1], P->text_stream));
+    if ((DHG_NUM_STEPS - 1 - i) % n == 0) {
+      if (n > 1) CUDA_OK(cudaEventRecord(P->ev_fork, st));
+      for (int j = i; j > i - n && j >= 0; --j) {
+        const int set = j % n;
+        cudaStream_t ts = set == 0 ? st : P->text_stream[set];
+        if (set != 0) CUDA_OK(cudaStreamWaitEvent(ts, P->ev_fork, 0));
+        if (run_ops(P->text_ops[set], ts, text_ctx(j))) return 1;
+        if (set != 0) CUDA_OK(cudaEventRecord(P->ev_text[set], ts));
+      }
+      for (int j = i; j > i - n && j >= 0; --j)
+        if (j % n != 0) CUDA_OK(cudaStreamWaitEvent(st, P->ev_text[j % n], 0));
     }
-    if (!overlap && run_ops(P->text_ops[0], st, text_ctx(i))) return 1;
     sc.cond = c->cond60 + (size_t)i * c->film_total;
     sc.skip_input_dense = i != DHG_NUM_STEPS - 1;   // written by the previous step's head kernel
     sc.fuse_next_input = i != 0;
-    sc.text_set = overlap ? (i & 1) : 0;
-    sc.text_ready = (overlap && i != DHG_NUM_STEPS - 1) ? P->ev_text[i] : nullptr;
+    sc.text_set = i % n;
     head_for_step(c, P, i, mode, has_noise, false, &sc.head);
     if (run_ops(P->step_ops, st, sc)) return 1;
   }
@@ -1322,9 +1325,10 @@ int32_t dhg_set_option(dhg_ctx* c, const char* key, int32_t value) {
   if (key && !strcmp(key, "pair")) { tc_gemm_set_option(7, value); return 0; }
   if (key && !strcmp(key, "pdl")) { tc_gemm_set_option(6, value); attn_tc_set_debug(value ? -101 : -100); return 0; }
   if (key && !strcmp(key, "w_resident")) { tc_gemm_set_option(2, value); return 0; }
-  if (key && !strcmp(key, "overlap")) { g_opt_overlap = value ? 1 : 0; return 0; }
+  if (key && !strcmp(key, "text_sets")) { g_opt_text_sets = value; return 0; }
   if (key && !strcmp(key, "autotune")) { g_opt_autotune = value ? 1 : 0; return 0; }
   if (key && !strcmp(key, "serpentine")) { g_opt_serpentine = value ? 1 : 0; return 0; }
+  if (key && !strcmp(key, "l2_hints")) { g_opt_l2_hints = value ? 1 : 0; return 0; }
   if (key && !strcmp(key, "tune_rev")) { tc_gemm_set_option(14, value); return 0; }
   if (key && !strcmp(key, "tune_bn")) { tc_gemm_set_option(10, value); return 0; }
   if (key && !strcmp(key, "tune_g")) { tc_gemm_set_option(11, value); return 0; }
@@ -1438,6 +1442,39 @@ int32_t dhg_debug_tc_gemm_ex(int32_t device, const void* a, int32_t lda, int32_t
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   tc_gemm_plan_destroy(p);
   if (ce != cudaSuccess) return fail("dhg_debug_tc_gemm_ex: %s", cudaGetErrorString(ce));
+  return 0;
+}
+
+int32_t dhg_debug_time_text(dhg_ctx* c, int32_t sets, int32_t repeats, float* ms_per_step) {
+  if (check_ready(c, true)) return 1;
+  Plan* P = c->plan;
+  if (sets < 1 || sets > P->text_sets || repeats < 1 || !ms_per_step) return fail("dhg_debug_time_text: bad argument");
+  CUDA_OK(cudaSetDevice(c->device));
+  cudaStream_t st = P->cap_stream;
+  StepCtx sc;
+  memset(&sc, 0, sizeof(sc));
+  sc.cond = c->cond60;
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  for (int r = -2; r < repeats; ++r) {
+    if (r == 0) CUDA_OK(cudaEventRecord(e0, st));
+    if (sets > 1) CUDA_OK(cudaEventRecord(P->ev_fork, st));
+    for (int set = 0; set < sets; ++set) {
+      cudaStream_t ts = set == 0 ? st : P->text_stream[set];
+      if (set != 0) CUDA_OK(cudaStreamWaitEvent(ts, P->ev_fork, 0));
+      if (run_ops(P->text_ops[set], ts, sc)) return 1;
+      if (set != 0) CUDA_OK(cudaEventRecord(P->ev_text[set], ts));
+    }
+    for (int set = 1; set < sets; ++set) CUDA_OK(cudaStreamWaitEvent(st, P->ev_text[set], 0));
+  }
+  CUDA_OK(cudaEventRecord(e1, st));
+  CUDA_OK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_step = ms / (float)(repeats * sets);
   return 0;
 }
 

@@ -55,6 +55,7 @@ struct TcShape {
   int G;           // row tiles per super-tile (independent accumulators interleaved by the MMA warp)
   int m_super;     // ceil(m_tiles / G)
   int rev;         // walk the super-tiles from the last row to the first (see tc_gemm_plan_set_reverse)
+  int a_evict_first;   // A rows are read once by this launch: give them L2 evict-first priority
   int stages_a, stages_w;   // A ring / W ring depth (W ring unused when w_resident)
   int w_resident;  // all W tiles of this CTA's column group stay in smem for the whole kernel
   int sticky;      // each CTA works on one column group only
@@ -299,6 +300,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     asm volatile("griddepcontrol.wait;" ::: "memory");
     // ring positions are kept incrementally (no integer division in these latency-critical loops)
     uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
+    const uint64_t pol_a = l2_policy_evict_first();
     for (int t = t_first; t < t_end; t += t_step) {
       const int mts_f = one_group ? t : t / sh.n_groups;
       const int ng = sh.sticky ? my_group : t - mts_f * sh.n_groups;
@@ -314,10 +316,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
             const int row0 = (mts * tiles_per_super + sub + (int)cta_rank) * TC_BM + a_row_off;
             if (kPAIR) {   // both CTAs' bytes are counted on rank 0's barrier
               if (cta_rank == 0) mbar_expect_tx(fb, 2 * sh.a_tx_bytes);
-              tma_load_2d_pair(smem_u32(a_ring + (size_t)sa * sh.a_stage_bytes), &map_a, fb, kk, row0);
+              if (sh.a_evict_first) tma_load_2d_pair_hint(smem_u32(a_ring + (size_t)sa * sh.a_stage_bytes), &map_a, fb, kk, row0, pol_a);
+              else tma_load_2d_pair(smem_u32(a_ring + (size_t)sa * sh.a_stage_bytes), &map_a, fb, kk, row0);
             } else {
               mbar_expect_tx(fb, sh.a_tx_bytes);
-              tma_load_2d(smem_u32(a_ring + (size_t)sa * sh.a_stage_bytes), &map_a, fb, kk, row0);
+              if (sh.a_evict_first) tma_load_2d_hint(smem_u32(a_ring + (size_t)sa * sh.a_stage_bytes), &map_a, fb, kk, row0, pol_a);
+              else tma_load_2d(smem_u32(a_ring + (size_t)sa * sh.a_stage_bytes), &map_a, fb, kk, row0);
             }
           }
           if (++sa == (uint32_t)sh.stages_a) { sa = 0; pa ^= 1u; }
@@ -778,6 +782,7 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   sh.aux_kind = aux_kind;
   sh.trace = nullptr; sh.trace_cap = 0;
   sh.rev = g_tune_rev;
+  sh.a_evict_first = 0;
   sh.vec_bias_n = e.bias ? N : 0;
   sh.film_n = e.film_planned ? N : 0;
   // independent accumulators per super-tile: as many as fit in one 256-column TMEM group, at most 4
@@ -897,6 +902,7 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
 void tc_gemm_plan_destroy(TcGemmPlan* p) { delete p; }
 void tc_gemm_set_trace(TcGemmPlan* p, unsigned long long* buf, int cap) { p->sh.trace = buf; p->sh.trace_cap = cap; }
 void tc_gemm_plan_set_reverse(TcGemmPlan* p, int rev) { p->sh.rev = rev ? 1 : 0; }
+void tc_gemm_plan_set_a_evict_first(TcGemmPlan* p, int on) { p->sh.a_evict_first = (on && p->sh.n_groups == 1) ? 1 : 0; }
 void tc_gemm_plan_config(const TcGemmPlan* p, TcTune* out) {
   out->bn = p->sh.BN; out->g = p->sh.G; out->resident = p->sh.w_resident; out->pair = p->sh.pair;
 }

@@ -75,6 +75,8 @@ void tc_gemm_plan_config(const TcGemmPlan*, TcTune* out);   // what the plan end
 // Walk the row tiles from the last to the first.  The engine gives every kernel the direction opposite to the kernel
 // that wrote its input, so it starts on the rows that are still in the 126 MB L2 (same bits either way).
 void tc_gemm_plan_set_reverse(TcGemmPlan*, int rev);
+// A rows get L2 evict-first priority (only applied when every A row is read once, i.e. one column group).
+void tc_gemm_plan_set_a_evict_first(TcGemmPlan*, int on);
 void tc_gemm_plan_destroy(TcGemmPlan*);
 void tc_gemm_set_trace(TcGemmPlan*, unsigned long long* buf, int cap);   // debug timeline of CTA 0
 void tc_gemm_describe(const TcGemmPlan*, char* out, int n);

@@ -440,42 +440,75 @@ template void launch_input_dense<bf16>(const float*, const float*, const float*,
 //   x  <- posterior(x, eps, z)                                   utils/nn.py:84-87,110-112
 //   next step: in = Linear(2,C)(x) -> raw and SiLU'd rows        model.py:139 (+ cnn.py:25)
 // ---------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256, 3) heads_update_kernel(const T* __restrict__ h, int C,
+#ifndef DHG_HEADS_MINB
+#define DHG_HEADS_MINB 4
+#endif
+template <typename T_>
+__global__ void __launch_bounds__(256, DHG_HEADS_MINB) heads_update_kernel(const T_* __restrict__ h, int C,
                                                               const float* __restrict__ Wo /*[2,C]*/,
                                                               const float* __restrict__ bo,
                                                               const float* __restrict__ Wp /*[1,C]*/,
                                                               const float* __restrict__ bp, HeadParams p) {
   // 16 lanes per stroke point (each lane owns 8 of the C = 128 channels: one 16-byte access per row for bf16),
-  // 2 points per warp, grid-stride
+  // 2 points per warp, grid-stride.  The kernel is a stream (read h, write the next step's two input rows), so what
+  // matters is bytes in flight per SM: the six weight vectors live in shared memory instead of 48 registers (4 blocks
+  // per SM), and the row of the NEXT point is requested before the current one is worked on.
+  __shared__ __align__(16) float ws[6][128];   // w0 | w1 | wp | in_W[:,0] | in_W[:,1] | in_b
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) {
+    ws[0][i] = Wo[i]; ws[1][i] = Wo[C + i]; ws[2][i] = Wp[i];
+    ws[3][i] = p.next_raw ? p.in_W[i * 2] : 0.f;       // input_dense rows (next step)
+    ws[4][i] = p.next_raw ? p.in_W[i * 2 + 1] : 0.f;
+    ws[5][i] = p.next_raw ? p.in_b[i] : 0.f;
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31, sub = lane & 15, grp = lane >> 4;
   const int c0 = sub * 8;
-  float w0[8], w1[8], wp[8], iw0[8], iw1[8], ib[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    w0[i] = Wo[c0 + i]; w1[i] = Wo[C + c0 + i]; wp[i] = Wp[c0 + i];
-    iw0[i] = p.next_raw ? p.in_W[(c0 + i) * 2] : 0.f;       // input_dense rows of my channels (next step)
-    iw1[i] = p.next_raw ? p.in_W[(c0 + i) * 2 + 1] : 0.f;
-    ib[i] = p.next_raw ? p.in_b[c0 + i] : 0.f;
-  }
   const float b0 = bo[0], b1 = bo[1], bpv = bp[0];
-  const size_t npts = (size_t)p.B * p.T;
-  const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-  for (size_t base = warp0 * 2; base < npts; base += nwarps * 2) {
-    const size_t i = base + grp;
-    const bool ok = i < npts;
-    const size_t ii = ok ? i : 0;
-    const int b = (int)(ii / p.T), t = (int)(ii - (size_t)b * p.T);
-    const size_t row = (size_t)b * (p.T + 1) + 1 + t;
-    float xv[8];
-    load8<T>(h + row * C + c0, xv);
-    float e0 = 0.f, e1 = 0.f, pl = 0.f;
+  // 32-bit point indices (the plan guarantees B * (T + 1) < 2^24); the (sample, position) of my point advances by a
+  // fixed stride per iteration, so the row index is kept incrementally instead of dividing by T every time
+  const uint32_t npts = (uint32_t)p.B * (uint32_t)p.T, T = (uint32_t)p.T;
+  const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t stride = ((gridDim.x * blockDim.x) >> 5) * 2;
+  const uint32_t stride_b = stride / T, stride_t = stride - stride_b * T;
+  float xv[8], xn[8];
+  float2 xx = make_float2(0.f, 0.f), zz = make_float2(0.f, 0.f), xx_n = xx, zz_n = zz;
+  // point i = b * T + t lives in row b * (T + 1) + 1 + t = i + b + 1
+  auto fetch = [&](uint32_t i, uint32_t b, float* v, float2& x2, float2& z2) {
+    load8<T_>(h + (size_t)(i + b + 1) * C + c0, v);
+    if (p.x_io) x2 = *reinterpret_cast<const float2*>(p.x_io + (size_t)i * 2);
+    if (p.noise) z2 = *reinterpret_cast<const float2*>(p.noise + (size_t)i * 2);
+  };
+  uint32_t i = warp0 * 2 + grp;
+  uint32_t b = i / T, t = i - b * T;           // one division per thread
+  uint32_t i_n = i, b_n = b, t_n = t;          // the point after this one
+  auto advance = [&](uint32_t& ii, uint32_t& bb, uint32_t& tt) {
+    ii += stride; bb += stride_b; tt += stride_t;
+    if (tt >= T) { tt -= T; ++bb; }
+  };
+  if (i < npts) fetch(i, b, xn, xx_n, zz_n);
+  for (; i - grp < npts; advance(i, b, t)) {   // warp-uniform trip count (the shuffles below need both halves)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      e0 = fmaf(xv[k], w0[k], e0);
-      e1 = fmaf(xv[k], w1[k], e1);
-      pl = fmaf(xv[k], wp[k], pl);
+    for (int k = 0; k < 8; ++k) xv[k] = xn[k];
+    xx = xx_n; zz = zz_n;
+    advance(i_n, b_n, t_n);
+    if (i_n < npts) fetch(i_n, b_n, xn, xx_n, zz_n);
+    const bool ok = i < npts;
+    const size_t row = (size_t)i + b + 1;
+    float e0 = 0.f, e1 = 0.f, pl = 0.f;
+    {
+      const float4 *w0 = reinterpret_cast<const float4*>(&ws[0][c0]), *w1 = reinterpret_cast<const float4*>(&ws[1][c0]),
+                   *wp = reinterpret_cast<const float4*>(&ws[2][c0]);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const float4 a = w0[q], b = w1[q], c = wp[q];
+        const float aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, cw[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          e0 = fmaf(xv[q * 4 + k], aw[k], e0);
+          e1 = fmaf(xv[q * 4 + k], bw[k], e1);
+          pl = fmaf(xv[q * 4 + k], cw[k], pl);
+        }
+      }
     }
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) {
@@ -487,9 +520,6 @@ __global__ void __launch_bounds__(256, 3) heads_update_kernel(const T* __restric
     if (!ok) continue;
     float y0 = 0.f, y1 = 0.f;
     if (p.x_io) {
-      const float2 xx = *reinterpret_cast<const float2*>(p.x_io + i * 2);
-      float2 zz = make_float2(0.f, 0.f);
-      if (p.noise) zz = *reinterpret_cast<const float2*>(p.noise + i * 2);
       if (p.mode == 0) {  // "new": (x - sqrt(1-abar) eps) / sqrt(1-beta) + z sqrt(1-abar_next)
         y0 = (xx.x - p.c_eps * e0) / p.c_div + zz.x * p.c_noise;
         y1 = (xx.y - p.c_eps * e1) / p.c_div + zz.y * p.c_noise;
@@ -509,12 +539,20 @@ __global__ void __launch_bounds__(256, 3) heads_update_kernel(const T* __restric
     }
     if (p.next_raw) {   // input_dense of the next step on the updated point
       float v[8];
+      const float4 *i0 = reinterpret_cast<const float4*>(&ws[3][c0]), *i1 = reinterpret_cast<const float4*>(&ws[4][c0]),
+                   *ib = reinterpret_cast<const float4*>(&ws[5][c0]);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = fmaf(y1, iw1[k], fmaf(y0, iw0[k], ib[k]));
-      store8<T>(reinterpret_cast<T*>(p.next_raw) + row * C + c0, v);
+      for (int q = 0; q < 2; ++q) {
+        const float4 a = i0[q], b = i1[q], c = ib[q];
+        v[q * 4 + 0] = fmaf(y1, b.x, fmaf(y0, a.x, c.x));
+        v[q * 4 + 1] = fmaf(y1, b.y, fmaf(y0, a.y, c.y));
+        v[q * 4 + 2] = fmaf(y1, b.z, fmaf(y0, a.z, c.z));
+        v[q * 4 + 3] = fmaf(y1, b.w, fmaf(y0, a.w, c.w));
+      }
+      store8<T_>(reinterpret_cast<T_*>(p.next_raw) + row * C + c0, v);
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] = silu_f(v[k]);
-      store8<T>(reinterpret_cast<T*>(p.next_act) + row * C + c0, v);
+      store8<T_>(reinterpret_cast<T_*>(p.next_act) + row * C + c0, v);
     }
   }
 }
@@ -524,7 +562,7 @@ int launch_heads_update(const T* h, int C, const float* Wo, const float* bo, con
   if (C != 128) return 1;
   const size_t nw = ((size_t)p.B * p.T + 1) / 2;
   size_t blocks = (nw + 7) / 8;
-  if (blocks > 148 * 12) blocks = 148 * 12;
+  if (blocks > 148 * 8) blocks = 148 * 8;   // two waves of 4 resident blocks per SM
   heads_update_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(h, C, Wo, bo, Wp, bp, p);
   return 0;
 }

@@ -59,6 +59,7 @@ SIGNATURES = {
     "dhg_set_option": (c_i32, [c_vp, c_cp, c_i32]),
     "dhg_debug_read": (c_i64, [c_vp, c_cp, c_vp, c_i64]),
     "dhg_debug_tc_gemm": (c_i32, [c_i32, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "dhg_debug_time_text": (c_i32, [c_vp, c_i32, c_i32, ctypes.POINTER(ctypes.c_float)]),
     "dhg_debug_attention": (c_i32, [c_i32, ctypes.POINTER(DebugAttn), c_i32, c_i32, ctypes.POINTER(ctypes.c_float), c_vp]),
     "dhg_debug_tc_gemm_ex": (c_i32, [c_i32, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, ctypes.POINTER(DebugEpilogue),
                                      c_i32, ctypes.POINTER(ctypes.c_float), c_vp]),

@@ -122,9 +122,11 @@ int64_t dhg_last_launch_count(const dhg_ctx* ctx);
 int64_t dhg_plan_bytes(const dhg_ctx* ctx);
 /* Engine switches, mainly for tests: key "gemm" = 0 CUDA-core GEMM + row epilogue
  * kernel, 1 tcgen05 GEMM with fused epilogue (bf16 precision only; default 1);
- * "graph" = 0/1 use CUDA graphs in dhg_sample (default 1); "overlap" = 0/1 run the text side of the
- * next step on a second stream beside the stroke side of the current step (default 1, tcgen05 path
- * only; ctx may be NULL).  Takes effect at the next dhg_plan. */
+ * "graph" = 0/1 use CUDA graphs in dhg_sample (default 1); with ctx NULL (process-wide): "text_sets" =
+ * 1..6 text sides of that many consecutive steps run at once on their own streams (default 4),
+ * "autotune" = 0/1 time the GEMM tile configurations at plan time (default 1), "serpentine" = 0/1
+ * alternate the row walking direction from kernel to kernel (default 1).  Takes effect at the next
+ * dhg_plan. */
 int32_t dhg_set_option(dhg_ctx* ctx, const char* key, int32_t value);
 
 /* Test hook: copy a named intermediate activation of the last forward ("h1", "h2c",
@@ -178,6 +180,10 @@ typedef struct dhg_debug_attn {
   int32_t q_rows, k_rows;   /* total rows of the q / k,v matrices */
   const int64_t* text;      /* [B, Tk] token ids (0 = masked key) or NULL */
 } dhg_debug_attn;
+/* Test / measurement hook: time the text side of a step (TextStyleEncoder + text_dense / kv of every
+ * EncoderLayer) of the current plan, `sets` steps at once (1 .. the plan's text sets), as ms per step. */
+int32_t dhg_debug_time_text(dhg_ctx* ctx, int32_t sets, int32_t repeats, float* ms_per_step);
+
 int32_t dhg_debug_attention(int32_t device, const dhg_debug_attn* a, int32_t impl, int32_t repeats,
                             float* ms_per_launch, void* stream);
 

@@ -40,14 +40,14 @@ np.save(sys.argv[1], out.float().cpu().numpy())
 
 
 def test_chain_is_bit_identical_with_and_without_text_overlap(tmp_path):
-    """The text side of step i-1 runs on a second stream beside the stroke side of step i (engine.cu run_chain);
-    serial order (overlap=0), the two streams without a CUDA graph, and the chain with every kernel walking its rows
+    """The text sides of 4 consecutive steps run at once on their own streams (engine.cu run_chain); one step at a
+    time (text_sets=1), three at a time on real streams without a CUDA graph, and the chain with every kernel walking its rows
     first-to-last under the built-in tile rule (serpentine=0,autotune=0) must give the same bits."""
     import numpy as np
 
     code = _CHAIN.format(root=ROOT, pkg=os.path.join(ROOT, "diffusion-handwriting-generation.pytorch_b200"))
     outs = {}
-    for name, opts, graph in [("overlap", "", "graph"), ("serial", "overlap=0", "graph"), ("overlap_streams", "", "nograph"),
+    for name, opts, graph in [("overlap", "", "graph"), ("serial", "text_sets=1", "graph"), ("overlap_streams", "text_sets=3", "nograph"),
                               ("one_direction", "serpentine=0,autotune=0", "graph")]:
         f = str(tmp_path / f"{name}.npy")
         r = subprocess.run([sys.executable, "-c", code, f, graph], env=dict(os.environ, DHG_OPTS=opts), capture_output=True, text=True,
