@@ -145,10 +145,15 @@ class DiffusionWriter:
             out[r, : len(i)] = torch.tensor(i)
         return out
 
-    @staticmethod
-    def _check_tokens(text):
+    def _check_tokens(self, text):
+        """Out-of-range ids raise IndexError like the reference's nn.Embedding.  For a CUDA tensor the check reads
+        the device (a synchronisation), so an unchanged tensor that already passed is not checked again."""
+        key = (text.data_ptr(), text._version, tuple(text.shape), str(text.device))
+        if text.is_cuda and key == getattr(self, "_tokens_ok", None):
+            return
         if text.numel() and (int(text.min()) < 0 or int(text.max()) >= 73):
             raise IndexError("text token id out of range [0, 73)")
+        self._tokens_ok = key
 
     # -- DiffusionModel.forward (model.py:121-182) -----------------------------
     @torch.no_grad()
