@@ -5,6 +5,7 @@ model and plotting (inference.py:60-96), for any batch size, through the C ABI
 in include/dhg_b200.h.  PyTorch is used for device memory and streams only.
 """
 import ctypes
+import weakref
 import re
 
 import torch
@@ -145,15 +146,17 @@ class DiffusionWriter:
             out[r, : len(i)] = torch.tensor(i)
         return out
 
-    def _check_tokens(self, text):
-        """Out-of-range ids raise IndexError like the reference's nn.Embedding.  For a CUDA tensor the check reads
-        the device (a synchronisation), so an unchanged tensor that already passed is not checked again."""
-        key = (text.data_ptr(), text._version, tuple(text.shape), str(text.device))
-        if text.is_cuda and key == getattr(self, "_tokens_ok", None):
+    def _check_tokens(self, text, original=None):
+        """Out-of-range ids raise IndexError like the reference's nn.Embedding.  Checking a CUDA tensor reads the
+        device (a synchronisation), so the very same tensor OBJECT, unmodified since it last passed (torch's version
+        counter), is not checked again.  `original`: the caller's tensor before any device copy."""
+        obj = original if isinstance(original, torch.Tensor) else text
+        ok = getattr(self, "_tokens_ok", None)
+        if ok is not None and ok[0]() is obj and ok[1] == obj._version:
             return
         if text.numel() and (int(text.min()) < 0 or int(text.max()) >= 73):
             raise IndexError("text token id out of range [0, 73)")
-        self._tokens_ok = key
+        self._tokens_ok = (weakref.ref(obj), obj._version)
 
     # -- DiffusionModel.forward (model.py:121-182) -----------------------------
     @torch.no_grad()
@@ -163,8 +166,9 @@ class DiffusionWriter:
         B, T, two = strokes.shape
         if two != 2:
             raise ValueError("strokes must be [B,T,2]")
+        text_in = text
         text = self._dev(text, torch.int64)
-        self._check_tokens(text)
+        self._check_tokens(text, text_in)
         style = self._dev(style_vector, torch.float32)
         if style.dim() != 3 or style.shape[0] != B or style.shape[2] != STYLE_WIDTH:
             raise ValueError("style_vector must be [B,S,1280]")
@@ -196,8 +200,9 @@ class DiffusionWriter:
             raise ValueError(f"diffusion_mode must be 'new' or 'standard', got {diffusion_mode!r}")
         if isinstance(text, (list, tuple)) and text and isinstance(text[0], str):
             text = self.encode(text)
+        text_in = text
         text = self._dev(text, torch.int64)
-        self._check_tokens(text)
+        self._check_tokens(text, text_in)
         B, L = text.shape
         style = self._dev(style_vector, torch.float32)
         if style.dim() != 3 or style.shape[0] != B or style.shape[2] != STYLE_WIDTH:
