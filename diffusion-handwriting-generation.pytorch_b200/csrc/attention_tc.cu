@@ -40,6 +40,7 @@ struct AttnTcShape {
   int QT;         // query tiles per (sample, head)
   int items;      // B * H * QT
   int rev;        // walk the items from the last to the first
+  int early;      // request the next item's tiles right after P V (else: after O has been stored)
   uint32_t idesc_s, idesc_o;
   uint32_t off_k, off_v, off_mask, off_xchg, slot_bytes, off_bar;
   float scale_log2;   // scale * log2(e)
@@ -104,21 +105,28 @@ __global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __
     const uint32_t vlo_mn = (umma_desc_lo(smem_u32(q_s + sh.off_v)) & ~(1u << 16)) | ((1024u >> 4) << 16);   // MN-major: LBO field
     const int nk = N >> 4;
     uint32_t par = 0;
-    for (int item = (int)blockIdx.x * NS + s; item < sh.items; item += stride, par ^= 1u) {
-      // slot free (its previous item is completely stored)?  -> load the next item
-      mbar_wait(smem_u32(&sb[4]), par ^ 1u);
+    const uint32_t lb = smem_u32(&sb[0]);
+    auto issue_load = [&](int it) {
       int qt, h, b;
-      item_coords(sh, p, item, qt, h, b);
-      const uint32_t lb = smem_u32(&sb[0]);
-      if (leader) {
-        mbar_expect_tx(lb, (uint32_t)(128 * 128 + 2 * N * 128));
-        // 64-column boxes starting at the head's first column; for D = 48 the last 16 columns belong to
-        // the next head (or are zero-filled past the matrix) and are never touched by the MMAs
-        tma_load_2d(smem_u32(q_s), &map_q, lb, h * p.D, b * p.q_period + p.q_pad + qt * 128);
-        tma_load_2d(smem_u32(q_s + sh.off_k), &map_k, lb, h * p.D, b * p.k_period + p.k_pad);
-        tma_load_2d(smem_u32(q_s + sh.off_v), &map_v, lb, h * p.D, b * p.k_period + p.k_pad);
+      item_coords(sh, p, it, qt, h, b);
+      mbar_expect_tx(lb, (uint32_t)(128 * 128 + 2 * N * 128));
+      // 64-column boxes starting at the head's first column; for D = 48 the last 16 columns belong to
+      // the next head (or are zero-filled past the matrix) and are never touched by the MMAs
+      tma_load_2d(smem_u32(q_s), &map_q, lb, h * p.D, b * p.q_period + p.q_pad + qt * 128);
+      tma_load_2d(smem_u32(q_s + sh.off_k), &map_k, lb, h * p.D, b * p.k_period + p.k_pad);
+      tma_load_2d(smem_u32(q_s + sh.off_v), &map_v, lb, h * p.D, b * p.k_period + p.k_pad);
+    };
+    // The smem tiles of a slot are free as soon as its P V product has completed (bar_o); the TMEM columns only when
+    // the softmax threads have read O out (bar_free).  So the next item's Q / K / V are requested right after bar_o and
+    // travel while O is normalised and stored; only the next S = Q K^T waits for bar_free.
+    if (sh.early && (int)blockIdx.x * NS + s < sh.items && leader) issue_load((int)blockIdx.x * NS + s);
+    for (int item = (int)blockIdx.x * NS + s; item < sh.items; item += stride, par ^= 1u) {
+      if (!sh.early) {   // load only when the slot is completely free
+        mbar_wait(smem_u32(&sb[4]), par ^ 1u);
+        if (leader) issue_load(item);
       }
       mbar_wait(lb, par);
+      if (sh.early) mbar_wait(smem_u32(&sb[4]), par ^ 1u);   // TMEM columns free (previous item's O has been read out)
       tc_fence_after();
       // S = Q K^T
       if (leader) {
@@ -139,6 +147,11 @@ __global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __
         umma_commit(smem_u32(&sb[3]));
       }
       __syncwarp();
+      if (sh.early && item + stride < sh.items) {
+        mbar_wait(smem_u32(&sb[3]), par);   // P V done: Q / K(P) / V tiles are dead
+        if (leader) issue_load(item + stride);
+        __syncwarp();
+      }
     }
   } else {
     // ===== softmax group of slot `slot`: thread = (query row, column half) =====
@@ -273,8 +286,8 @@ __global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __
 
 }  // namespace
 
-int g_attn_dbg = 0, g_attn_halves = 1, g_attn_pdl = 1;
-void attn_tc_set_debug(int v) { if (v >= 0) g_attn_dbg = v; else if (v <= -100) g_attn_pdl = v == -101; else g_attn_halves = -v; }
+int g_attn_dbg = 0, g_attn_halves = 1, g_attn_pdl = 1, g_attn_early = 1;
+void attn_tc_set_debug(int v) { if (v == -200 || v == -201) g_attn_early = v == -201; else if (v >= 0) g_attn_dbg = v; else if (v <= -100) g_attn_pdl = v == -101; else g_attn_halves = -v; }
 
 struct AttnTcPlan {
   CUtensorMap map_q, map_k, map_v;
@@ -306,6 +319,7 @@ AttnTcPlan* attn_tc_plan_create(const AttnParams& p, int q_rows, int k_rows, cha
   sh.QT = (p.Tq + 127) / 128;
   sh.items = p.B * p.H * sh.QT;
   sh.rev = 0;
+  sh.early = g_attn_early;
   // c_format F32 [4,6) | a,b BF16 [7,10),[10,13) | b_major [16] | N>>3 [17,23) | M>>4 [24,29)
   const uint32_t base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
   sh.idesc_s = base | ((uint32_t)(sh.N >> 3) << 17);
@@ -349,6 +363,7 @@ AttnTcPlan* attn_tc_plan_create(const AttnParams& p, int q_rows, int k_rows, cha
 
 void attn_tc_plan_destroy(AttnTcPlan* a) { delete a; }
 void attn_tc_plan_set_reverse(AttnTcPlan* a, int rev) { a->sh.rev = rev ? 1 : 0; }
+void attn_tc_plan_set_early_load(AttnTcPlan* a, int on) { a->sh.early = on ? 1 : 0; }
 
 int attn_tc_launch(const AttnTcPlan* a, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};

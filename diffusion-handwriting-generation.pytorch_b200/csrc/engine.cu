@@ -577,6 +577,30 @@ struct Builder {
     });
   }
 
+  // When to request the next item's Q / K / V tiles (attention_tc.cu): right after P V helps the shapes with few slots
+  // per SM and costs a little where 4-6 items are in flight anyway, so it is timed per shape like the GEMM tiles.
+  int attention_pick_early(AttnTcPlan* ap) {
+    cudaStream_t st = P->cap_stream;
+    cudaEvent_t e0, e1;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return -1;
+    float t[2] = {0.f, 0.f};
+    bool ok = true;
+    for (int v = 0; v < 2 && ok; ++v) {
+      attn_tc_plan_set_early_load(ap, v);
+      for (int i = 0; i < 2 && ok; ++i) ok = attn_tc_launch(ap, st) == 0;
+      cudaEventRecord(e0, st);
+      for (int i = 0; i < 4 && ok; ++i) ok = attn_tc_launch(ap, st) == 0;
+      cudaEventRecord(e1, st);
+      ok = ok && cudaEventSynchronize(e1) == cudaSuccess;
+      if (ok) cudaEventElapsedTime(&t[v], e0, e1);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (!ok) return -1;
+    if (getenv("DHG_DESCRIBE")) fprintf(stderr, "autotune attention: late load %.1f us, early load %.1f us\n", t[0] * 250.f, t[1] * 250.f);
+    return t[1] < t[0] * 0.985f ? 1 : 0;
+  }
+
   // k / v may exist in several copies (text sets); the launch picks sc.text_set.
   void attention_sets(const void* q, int qp, const void* const* ks, const void* const* vs, int nsets, int kp, int vp,
                       const Act& o, int H, int D, int Tq, int q_period, int q_pad, int Tk, int k_period, int k_pad,
@@ -584,6 +608,7 @@ struct Builder {
     if (failed) return;
     std::vector<AttnParams> a(nsets);
     std::vector<AttnTcPlan*> plans(nsets, nullptr);
+    int early = 1;
     Plan* Pl = P;
     *nlaunch += 1;
     bool tc = false;
@@ -601,6 +626,11 @@ struct Builder {
         const int dir = g_opt_serpentine ? !dir_of(q) : 0;
         attn_tc_plan_set_reverse(plans[s], dir);
         wrote(o.p, dir);
+        if (g_opt_autotune) {
+          if (s == 0) early = attention_pick_early(plans[0]);
+          if (early < 0) { fail("plan: attention autotune launch failed: %s", cudaGetErrorString(cudaGetLastError())); failed = true; return; }
+          attn_tc_plan_set_early_load(plans[s], early);
+        }
         P->attn_plans.push_back(plans[s]);
         tc = true;
       }
@@ -1322,6 +1352,7 @@ int64_t dhg_plan_bytes(const dhg_ctx* c) { return (c && c->plan) ? (int64_t)c->p
 int32_t dhg_set_option(dhg_ctx* c, const char* key, int32_t value) {
   if (key && !strcmp(key, "interleave")) { tc_gemm_set_option(4, value); return 0; }
   if (key && !strcmp(key, "attn_dbg")) { attn_tc_set_debug(value); return 0; }
+  if (key && !strcmp(key, "attn_early")) { attn_tc_set_debug(value ? -201 : -200); return 0; }
   if (key && !strcmp(key, "pair")) { tc_gemm_set_option(7, value); return 0; }
   if (key && !strcmp(key, "pdl")) { tc_gemm_set_option(6, value); attn_tc_set_debug(value ? -101 : -100); return 0; }
   if (key && !strcmp(key, "w_resident")) { tc_gemm_set_option(2, value); return 0; }

@@ -90,6 +90,7 @@ bool attn_tc_supported(const AttnParams& p);
 AttnTcPlan* attn_tc_plan_create(const AttnParams& p, int q_rows, int k_rows, char* err, int errlen);
 void attn_tc_plan_destroy(AttnTcPlan*);
 void attn_tc_plan_set_reverse(AttnTcPlan*, int rev);   // work items from the last sample to the first
+void attn_tc_plan_set_early_load(AttnTcPlan*, int on);   // next item's Q/K/V requested right after P V (default) or after O is stored
 int attn_tc_launch(const AttnTcPlan*, cudaStream_t st);
 void attn_tc_set_debug(int flags);   // timing experiments only
 

@@ -20,6 +20,15 @@ def test_gemm_cases_under_switch(opts):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_attention_cases_with_late_tile_loads():
+    """attention_tc.cu requests the next item's Q/K/V right after P V by default; the plan-time tuner may switch a
+    shape back to loading after O has been stored, so that order gets the same unit cases."""
+    env = dict(os.environ, DHG_OPTS="attn_early=0")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_attention.py"), "-x", "-q", "-m", "gpu",
+                        "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, cwd=ROOT, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 _CHAIN = r"""
 import sys, numpy as np, torch
 sys.path.insert(0, {root!r}); sys.path.insert(0, {pkg!r})
