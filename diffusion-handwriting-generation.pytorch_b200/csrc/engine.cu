@@ -48,6 +48,7 @@ using namespace dhg;
 static thread_local char g_err[1024] = "";
 static int g_opt_autotune = 1;  // time every GEMM tile configuration at plan time and keep the fastest ("autotune")
 static int g_opt_l2_hints = 1;   // streamed GEMM inputs get L2 evict-first priority ("l2_hints")
+static int g_opt_tail_fusion = 1; // chain: last fc + FiLM + skip + heads as one kernel on folded tables ("tail_fusion")
 static int g_opt_serpentine = 1; // consumer kernels walk their rows opposite to their producer ("serpentine")
 static int g_opt_text_sets = 2;  // text sides of this many consecutive steps run at once (dhg_set_option "text_sets")
 static int fail(const char* fmt, ...) {
@@ -101,6 +102,8 @@ struct StepCtx {
   bool skip_input_dense;  // in_raw / in_act were already written by the previous step's head kernel
   bool fuse_next_input;   // this step's head kernel also writes in_raw / in_act of the next step
   int text_set;           // which copy of the text-side buffers this step's cross-attention reads
+  bool fuse_tail;         // dec1.fc is not launched: the head kernel works on (a2, skip) with the step's folded tables
+  int step;               // sampling step index (tail tables)
   HeadParams head;
 };
 typedef std::function<int(cudaStream_t, const StepCtx&)> Op;
@@ -151,7 +154,7 @@ struct Plan {
   int text_sets = 1;
   cudaStream_t text_stream[kMaxTextSets] = {};   // [0] unused: set 0 runs on the caller's stream
   cudaEvent_t ev_fork = nullptr, ev_text[kMaxTextSets] = {};
-  Act head_in, in_raw, in_act;
+  Act head_in, in_raw, in_act, tail_a2, tail_skip;
   std::vector<TcGemmPlan*> tc_plans;
   std::vector<AttnTcPlan*> attn_plans;
   int attn_impl = 1;
@@ -184,6 +187,8 @@ struct dhg_ctx {
   float* film_b = nullptr;  // [tot]
   float *sff_w1 = nullptr, *sff_b1 = nullptr, *sff_w2 = nullptr, *sff_b2 = nullptr;
   float* cond60 = nullptr;  // [60, tot]
+  // tail fusion (see finalize): eps|pen = a2 . tail_A[step] + skip . tail_H + tail_c[step]
+  float *tail_A = nullptr, *tail_c = nullptr, *tail_H = nullptr;   // [60,3,C] | [60,3] | [3,C]
   float* emb = nullptr;     // [73, d]
   float *in_W = nullptr, *in_b = nullptr, *out_W = nullptr, *out_b = nullptr, *pen_W = nullptr, *pen_b = nullptr;
   std::vector<void*> allocs;
@@ -411,6 +416,7 @@ struct Builder {
   std::vector<Op>* ops;
   int64_t* nlaunch;
   bool failed = false;
+  bool tail_gemm = false;   // the next gemm() is dec1.fc: skipped when the step runs with the fused tail
 
   // Walking direction of the kernel that wrote each activation (P->dir_of: buffer -> 0 first row to last, 1 last to
   // first).  A GEMM / attention launch walks its rows in the direction OPPOSITE to the producer of its input, so it
@@ -558,7 +564,10 @@ struct Builder {
       P->tc_plans.push_back(tcp);
     }
     *nlaunch += tcp ? 1 : 2;
+    const bool skippable = tail_gemm;
+    tail_gemm = false;
     ops->push_back([=](cudaStream_t st, const StepCtx& sc) -> int {
+      if (skippable && sc.fuse_tail) return 0;
       Epilogue ee = e;
       if (film_off >= 0) {
         ee.gamma = sc.cond + film_off;
@@ -694,6 +703,7 @@ struct Builder {
     gemm(a1, p + ".conv2", s2, m);
     EpiSpec s3; s3.film_off = film(p + ".affine3"); s3.res_post = skip; s3.out_raw = out;
     if (want_act) { *out_act = act(R, Cout); s3.out_act = *out_act; }
+    if (p == "dec1") { P->tail_a2 = a2; P->tail_skip = skip; tail_gemm = true; }
     gemm(a2, p + ".fc", s3, m);
     return out;
   }
@@ -914,6 +924,15 @@ int build_plan(dhg_ctx* c, Plan* P) {
       if (sc.fuse_next_input) {
         hp.next_raw = Pl->in_raw.p; hp.next_act = Pl->in_act.p; hp.in_W = c->in_W; hp.in_b = c->in_b;
       }
+      if (sc.fuse_tail) {   // eps | pen = a2 . tail_A[step] + skip . tail_H + tail_c[step]  (dhg_finalize)
+        const int C = d1.C;
+        const float* A = c->tail_A + (size_t)sc.step * 3 * C;
+        const float* cc = c->tail_c + (size_t)sc.step * 3;
+        hp.h2 = Pl->tail_skip.p;
+        hp.w2 = c->tail_H;
+        return launch_heads_update<bf16>((const bf16*)Pl->tail_a2.p, C, A, cc, A + 2 * C, cc + 2, hp, st)
+                   ? fail("head kernel: unsupported channel count %d", C) : 0;
+      }
       const int rc = Pl->prec == PREC_FP32
           ? launch_heads_update<float>((const float*)d1.p, d1.C, c->out_W, c->out_b, c->pen_W, c->pen_b, hp, st)
           : launch_heads_update<bf16>((const bf16*)d1.p, d1.C, c->out_W, c->out_b, c->pen_W, c->pen_b, hp, st);
@@ -995,6 +1014,8 @@ int run_chain(dhg_ctx* c, Plan* P, int mode, bool has_noise, cudaStream_t st) {
     sc.skip_input_dense = i != DHG_NUM_STEPS - 1;   // written by the previous step's head kernel
     sc.fuse_next_input = i != 0;
     sc.text_set = i % n;
+    sc.fuse_tail = g_opt_tail_fusion && P->prec == PREC_BF16 && P->gemm_impl == 1;
+    sc.step = i;
     head_for_step(c, P, i, mode, has_noise, false, &sc.head);
     if (run_ops(P->step_ops, st, sc)) return 1;
   }
@@ -1179,6 +1200,38 @@ int32_t dhg_finalize(dhg_ctx* c) {
   launch_film_table(demb, c->film_W, c->film_b, c->film_total, c->cond60, DHG_NUM_STEPS, 0);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaDeviceSynchronize());
+  // Tail fusion.  The last ConvBlock ends with  d1 = FiLM3(fc(a2)) + skip  (cnn.py:83-87) and the heads are linear in d1
+  // (model.py:179-181), so with H = [output_dense; pen_lifts_dense] (3 x C):
+  //   d1 . H^T + b_H = a2 . (W_fc^T diag(gamma_s) H^T) + skip . H^T + ((b_fc * gamma_s + beta_s) . H^T + b_H)
+  // gamma_s / beta_s only depend on the step: 60 tiny tables, and neither the fc GEMM nor d1 exist in the chain.
+  {
+    const int C = c->c1;
+    const Lin& fc = c->lins.at("dec1.fc");
+    const int foff = c->film_off.at("dec1.affine3");
+    std::vector<float> cond((size_t)DHG_NUM_STEPS * c->film_total);
+    CUDA_OK(cudaMemcpy(cond.data(), c->cond60, cond.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    std::vector<float> H((size_t)3 * C), bH(3);
+    const auto& ow = c->raw.at("output_dense.weight");
+    const auto& pw = c->raw.at("pen_lifts_dense.0.weight");
+    for (int n = 0; n < C; ++n) { H[n] = ow[n]; H[C + n] = ow[C + n]; H[2 * C + n] = pw[n]; }
+    bH[0] = c->raw.at("output_dense.bias")[0]; bH[1] = c->raw.at("output_dense.bias")[1]; bH[2] = c->raw.at("pen_lifts_dense.0.bias")[0];
+    std::vector<float> A((size_t)DHG_NUM_STEPS * 3 * C), cc((size_t)DHG_NUM_STEPS * 3);
+    for (int s = 0; s < DHG_NUM_STEPS; ++s) {
+      const float* g = cond.data() + (size_t)s * c->film_total + foff;
+      const float* be = g + C;
+      for (int j = 0; j < 3; ++j) {
+        double acc_c = bH[j];
+        for (int n = 0; n < C; ++n) acc_c += ((double)fc.h_b[n] * g[n] + be[n]) * H[(size_t)j * C + n];
+        cc[(size_t)s * 3 + j] = (float)acc_c;
+        for (int k = 0; k < C; ++k) {
+          double a = 0.0;
+          for (int n = 0; n < C; ++n) a += (double)fc.h_w[(size_t)k * C + n] * g[n] * H[(size_t)j * C + n];   // h_w: [K][N]
+          A[((size_t)s * 3 + j) * C + k] = (float)a;
+        }
+      }
+    }
+    if (dev_upload(c->allocs, &c->tail_A, A) || dev_upload(c->allocs, &c->tail_c, cc) || dev_upload(c->allocs, &c->tail_H, H)) return 1;
+  }
   c->raw.clear();
   c->finalized = true;
   return 0;
@@ -1271,6 +1324,7 @@ int32_t dhg_sample(dhg_ctx* c, int32_t batch, const float* x0, const float* nois
     if (launch_chain(c, P, mode, true, st)) return 1;
     CUDA_OK(cudaMemcpyAsync(out + (size_t)c0 * P->T * 3, P->out, (size_t)nb * P->T * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     launches += P->launches_once + (int64_t)DHG_NUM_STEPS * (P->launches_text + P->launches_step) - (DHG_NUM_STEPS - 1);   // input_dense is fused after step 1
+    if (g_opt_tail_fusion && P->prec == PREC_BF16 && P->gemm_impl == 1) launches -= DHG_NUM_STEPS;   // dec1.fc lives in the head kernel
   }
   c->last_launches = launches;
   return 0;
@@ -1360,6 +1414,7 @@ int32_t dhg_set_option(dhg_ctx* c, const char* key, int32_t value) {
   if (key && !strcmp(key, "autotune")) { g_opt_autotune = value ? 1 : 0; return 0; }
   if (key && !strcmp(key, "serpentine")) { g_opt_serpentine = value ? 1 : 0; return 0; }
   if (key && !strcmp(key, "l2_hints")) { g_opt_l2_hints = value ? 1 : 0; return 0; }
+  if (key && !strcmp(key, "tail_fusion")) { g_opt_tail_fusion = value ? 1 : 0; return 0; }
   if (key && !strcmp(key, "tune_rev")) { tc_gemm_set_option(14, value); return 0; }
   if (key && !strcmp(key, "tune_bn")) { tc_gemm_set_option(10, value); return 0; }
   if (key && !strcmp(key, "tune_g")) { tc_gemm_set_option(11, value); return 0; }

@@ -31,6 +31,10 @@ struct HeadParams {
   void* next_act;
   const float* in_W;       // [C, 2]
   const float* in_b;       // [C]
+  // second input row matrix with its own [3, C] weights (tail fusion, engine.cu: the last ConvBlock's fc + FiLM +
+  // skip and the two heads collapse into  a2 . A_step + skip . H + c_step); null = single input
+  const void* h2;
+  const float* w2;
 };
 
 template <typename TA>

@@ -453,12 +453,15 @@ __global__ void __launch_bounds__(256, DHG_HEADS_MINB) heads_update_kernel(const
   // 2 points per warp, grid-stride.  The kernel is a stream (read h, write the next step's two input rows), so what
   // matters is bytes in flight per SM: the six weight vectors live in shared memory instead of 48 registers (4 blocks
   // per SM), and the row of the NEXT point is requested before the current one is worked on.
-  __shared__ __align__(16) float ws[6][128];   // w0 | w1 | wp | in_W[:,0] | in_W[:,1] | in_b
+  __shared__ __align__(16) float ws[9][128];   // w0 | w1 | wp | in_W[:,0] | in_W[:,1] | in_b | second input's w0 | w1 | wp
+  const bool next_in = p.next_raw != nullptr || p.next_act != nullptr;
+  const bool two = p.h2 != nullptr;
   for (int i = threadIdx.x; i < 128; i += blockDim.x) {
     ws[0][i] = Wo[i]; ws[1][i] = Wo[C + i]; ws[2][i] = Wp[i];
-    ws[3][i] = p.next_raw ? p.in_W[i * 2] : 0.f;       // input_dense rows (next step)
-    ws[4][i] = p.next_raw ? p.in_W[i * 2 + 1] : 0.f;
-    ws[5][i] = p.next_raw ? p.in_b[i] : 0.f;
+    ws[3][i] = next_in ? p.in_W[i * 2] : 0.f;       // input_dense rows (next step)
+    ws[4][i] = next_in ? p.in_W[i * 2 + 1] : 0.f;
+    ws[5][i] = next_in ? p.in_b[i] : 0.f;
+    ws[6][i] = two ? p.w2[i] : 0.f; ws[7][i] = two ? p.w2[C + i] : 0.f; ws[8][i] = two ? p.w2[2 * C + i] : 0.f;
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, sub = lane & 15, grp = lane >> 4;
@@ -470,11 +473,15 @@ __global__ void __launch_bounds__(256, DHG_HEADS_MINB) heads_update_kernel(const
   const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t stride = ((gridDim.x * blockDim.x) >> 5) * 2;
   const uint32_t stride_b = stride / T, stride_t = stride - stride_b * T;
-  float xv[8], xn[8];
+  float xv[8], xn[8], sv[8], sn[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { xn[k] = 0.f; sn[k] = 0.f; }
   float2 xx = make_float2(0.f, 0.f), zz = make_float2(0.f, 0.f), xx_n = xx, zz_n = zz;
+  const T_* h2 = reinterpret_cast<const T_*>(p.h2);
   // point i = b * T + t lives in row b * (T + 1) + 1 + t = i + b + 1
   auto fetch = [&](uint32_t i, uint32_t b, float* v, float2& x2, float2& z2) {
     load8<T_>(h + (size_t)(i + b + 1) * C + c0, v);
+    if (two) load8<T_>(h2 + (size_t)(i + b + 1) * C + c0, sn);
     if (p.x_io) x2 = *reinterpret_cast<const float2*>(p.x_io + (size_t)i * 2);
     if (p.noise) z2 = *reinterpret_cast<const float2*>(p.noise + (size_t)i * 2);
   };
@@ -488,7 +495,7 @@ __global__ void __launch_bounds__(256, DHG_HEADS_MINB) heads_update_kernel(const
   if (i < npts) fetch(i, b, xn, xx_n, zz_n);
   for (; i - grp < npts; advance(i, b, t)) {   // warp-uniform trip count (the shuffles below need both halves)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) xv[k] = xn[k];
+    for (int k = 0; k < 8; ++k) { xv[k] = xn[k]; sv[k] = sn[k]; }
     xx = xx_n; zz = zz_n;
     advance(i_n, b_n, t_n);
     if (i_n < npts) fetch(i_n, b_n, xn, xx_n, zz_n);
@@ -507,6 +514,21 @@ __global__ void __launch_bounds__(256, DHG_HEADS_MINB) heads_update_kernel(const
           e0 = fmaf(xv[q * 4 + k], aw[k], e0);
           e1 = fmaf(xv[q * 4 + k], bw[k], e1);
           pl = fmaf(xv[q * 4 + k], cw[k], pl);
+        }
+      }
+      if (two) {
+        const float4 *u0 = reinterpret_cast<const float4*>(&ws[6][c0]), *u1 = reinterpret_cast<const float4*>(&ws[7][c0]),
+                     *up = reinterpret_cast<const float4*>(&ws[8][c0]);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const float4 a = u0[q], b = u1[q], c = up[q];
+          const float aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, cw[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            e0 = fmaf(sv[q * 4 + k], aw[k], e0);
+            e1 = fmaf(sv[q * 4 + k], bw[k], e1);
+            pl = fmaf(sv[q * 4 + k], cw[k], pl);
+          }
         }
       }
     }
@@ -537,7 +559,7 @@ __global__ void __launch_bounds__(256, DHG_HEADS_MINB) heads_update_kernel(const
         xo[i * p.x_out_stride + 1] = y1;
       }
     }
-    if (p.next_raw) {   // input_dense of the next step on the updated point
+    if (next_in) {   // input_dense of the next step on the updated point
       float v[8];
       const float4 *i0 = reinterpret_cast<const float4*>(&ws[3][c0]), *i1 = reinterpret_cast<const float4*>(&ws[4][c0]),
                    *ib = reinterpret_cast<const float4*>(&ws[5][c0]);
@@ -549,10 +571,10 @@ __global__ void __launch_bounds__(256, DHG_HEADS_MINB) heads_update_kernel(const
         v[q * 4 + 2] = fmaf(y1, b.z, fmaf(y0, a.z, c.z));
         v[q * 4 + 3] = fmaf(y1, b.w, fmaf(y0, a.w, c.w));
       }
-      store8<T_>(reinterpret_cast<T_*>(p.next_raw) + row * C + c0, v);
+      if (p.next_raw) store8<T_>(reinterpret_cast<T_*>(p.next_raw) + row * C + c0, v);
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] = silu_f(v[k]);
-      store8<T_>(reinterpret_cast<T_*>(p.next_act) + row * C + c0, v);
+      if (p.next_act) store8<T_>(reinterpret_cast<T_*>(p.next_act) + row * C + c0, v);
     }
   }
 }
