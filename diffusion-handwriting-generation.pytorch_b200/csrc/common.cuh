@@ -54,6 +54,16 @@ struct Epilogue {
 };
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// SiLU of a value that is stored in T right away: for bf16 the one-MUFU form h + h * tanh.approx(h), h = x / 2
+// (2^-11 relative, far below the bf16 rounding; 3 instructions instead of the ~15 of an fp32 division); fp32 keeps
+// the exact form (the fp32 mode is the parity mode).
+template <typename T> __device__ __forceinline__ float silu_out(float x) { return silu_f(x); }
+template <> __device__ __forceinline__ float silu_out<__nv_bfloat16>(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 
 template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }

@@ -48,6 +48,7 @@ using namespace dhg;
 static thread_local char g_err[1024] = "";
 static int g_opt_autotune = 1;  // time every GEMM tile configuration at plan time and keep the fastest ("autotune")
 static int g_opt_l2_hints = 1;   // streamed GEMM inputs get L2 evict-first priority ("l2_hints")
+static int g_opt_head_fusion = 1; // chain: enc1.conv_skip(input_dense(x)) computed from x by a K = 6 kernel ("head_fusion")
 static int g_opt_tail_fusion = 1; // chain: last fc + FiLM + skip + heads as one kernel on folded tables ("tail_fusion")
 static int g_opt_serpentine = 1; // consumer kernels walk their rows opposite to their producer ("serpentine")
 static int g_opt_text_sets = 2;  // text sides of this many consecutive steps run at once (dhg_set_option "text_sets")
@@ -102,6 +103,7 @@ struct StepCtx {
   bool skip_input_dense;  // in_raw / in_act were already written by the previous step's head kernel
   bool fuse_next_input;   // this step's head kernel also writes in_raw / in_act of the next step
   int text_set;           // which copy of the text-side buffers this step's cross-attention reads
+  bool fuse_head;         // enc1.conv_skip is computed from x (skip_from_x), the head kernel does not write in_raw
   bool fuse_tail;         // dec1.fc is not launched: the head kernel works on (a2, skip) with the step's folded tables
   int step;               // sampling step index (tail tables)
   HeadParams head;
@@ -189,6 +191,8 @@ struct dhg_ctx {
   float* cond60 = nullptr;  // [60, tot]
   // tail fusion (see finalize): eps|pen = a2 . tail_A[step] + skip . tail_H + tail_c[step]
   float *tail_A = nullptr, *tail_c = nullptr, *tail_H = nullptr;   // [60,3,C] | [60,3] | [3,C]
+  // head fusion: enc1.conv_skip(input_dense(x)) = sum_tau (x[t+tau] . head_M[tau] + head_v[tau]) + head_b
+  float *head_M = nullptr, *head_v = nullptr, *head_b = nullptr;   // [3,2,C] | [3,C] | [C]
   float* emb = nullptr;     // [73, d]
   float *in_W = nullptr, *in_b = nullptr, *out_W = nullptr, *out_b = nullptr, *pen_W = nullptr, *pen_b = nullptr;
   std::vector<void*> allocs;
@@ -417,6 +421,7 @@ struct Builder {
   int64_t* nlaunch;
   bool failed = false;
   bool tail_gemm = false;   // the next gemm() is dec1.fc: skipped when the step runs with the fused tail
+  bool head_gemm = false;   // the next gemm() is enc1.conv_skip: replaced by skip_from_x when the step runs with the fused head
 
   // Walking direction of the kernel that wrote each activation (P->dir_of: buffer -> 0 first row to last, 1 last to
   // first).  A GEMM / attention launch walks its rows in the direction OPPOSITE to the producer of its input, so it
@@ -564,10 +569,17 @@ struct Builder {
       P->tc_plans.push_back(tcp);
     }
     *nlaunch += tcp ? 1 : 2;
-    const bool skippable = tail_gemm;
+    const bool skippable = tail_gemm, replaceable = head_gemm;
     tail_gemm = false;
+    head_gemm = false;
+    dhg_ctx* cc = c;
     ops->push_back([=](cudaStream_t st, const StepCtx& sc) -> int {
       if (skippable && sc.fuse_tail) return 0;
+      if (replaceable && sc.fuse_head) {   // enc1.conv_skip(input_dense(x)) straight from the current x
+        const float* x = sc.head.x_io ? sc.head.x_io : Pl->x_state;
+        return launch_skip_from_x<bf16>(x, cc->head_M, cc->head_v, cc->head_b, (bf16*)e.out_raw, Pl->B, Pl->T, N, st)
+                   ? fail("skip_from_x: unsupported channel count %d", N) : 0;
+      }
       Epilogue ee = e;
       if (film_off >= 0) {
         ee.gamma = sc.cond + film_off;
@@ -696,6 +708,7 @@ struct Builder {
     const RowMap m = map_level(level);
     Act skip = act(R, Cout), a1 = act(R, Cout / 2), a2 = act(R, Cout), out = act(R, Cout);
     EpiSpec s0; s0.out_raw = skip;
+    if (p == "enc1") head_gemm = true;
     gemm(in_raw, p + ".conv_skip", s0, m);
     EpiSpec s1; s1.film_off = film(p + ".affine1"); s1.out_act = a1;
     gemm(in_act, p + ".conv1", s1, m);
@@ -922,7 +935,8 @@ int build_plan(dhg_ctx* c, Plan* P) {
       HeadParams hp = sc.head;
       if (hp.x_io == nullptr && hp.eps_out == nullptr) return fail("head: nothing to do");
       if (sc.fuse_next_input) {
-        hp.next_raw = Pl->in_raw.p; hp.next_act = Pl->in_act.p; hp.in_W = c->in_W; hp.in_b = c->in_b;
+        hp.next_raw = sc.fuse_head ? nullptr : Pl->in_raw.p;   // nobody reads in_raw when enc1.conv_skip works from x
+        hp.next_act = Pl->in_act.p; hp.in_W = c->in_W; hp.in_b = c->in_b;
       }
       if (sc.fuse_tail) {   // eps | pen = a2 . tail_A[step] + skip . tail_H + tail_c[step]  (dhg_finalize)
         const int C = d1.C;
@@ -1015,6 +1029,7 @@ int run_chain(dhg_ctx* c, Plan* P, int mode, bool has_noise, cudaStream_t st) {
     sc.fuse_next_input = i != 0;
     sc.text_set = i % n;
     sc.fuse_tail = g_opt_tail_fusion && P->prec == PREC_BF16 && P->gemm_impl == 1;
+    sc.fuse_head = g_opt_head_fusion && P->prec == PREC_BF16 && P->gemm_impl == 1;
     sc.step = i;
     head_for_step(c, P, i, mode, has_noise, false, &sc.head);
     if (run_ops(P->step_ops, st, sc)) return 1;
@@ -1232,6 +1247,28 @@ int32_t dhg_finalize(dhg_ctx* c) {
     }
     if (dev_upload(c->allocs, &c->tail_A, A) || dev_upload(c->allocs, &c->tail_c, cc) || dev_upload(c->allocs, &c->tail_H, H)) return 1;
   }
+  // Head fusion tables (kernels_simt.cu skip_from_x_kernel)
+  {
+    const int C = c->c1;
+    const Lin& sk = c->lins.at("enc1.conv_skip");   // h_w [3][K = C][N = C]
+    const auto& iw = c->raw.at("input_dense.weight");   // [C][2]
+    const auto& ib = c->raw.at("input_dense.bias");
+    std::vector<float> M((size_t)3 * 2 * C), v((size_t)3 * C);
+    for (int t = 0; t < 3; ++t)
+      for (int n = 0; n < C; ++n) {
+        double m0 = 0.0, m1 = 0.0, vv = 0.0;
+        for (int k = 0; k < C; ++k) {
+          const double w = sk.h_w[((size_t)t * C + k) * C + n];
+          m0 += (double)iw[(size_t)k * 2] * w;
+          m1 += (double)iw[(size_t)k * 2 + 1] * w;
+          vv += (double)ib[k] * w;
+        }
+        M[((size_t)t * 2 + 0) * C + n] = (float)m0;
+        M[((size_t)t * 2 + 1) * C + n] = (float)m1;
+        v[(size_t)t * C + n] = (float)vv;
+      }
+    if (dev_upload(c->allocs, &c->head_M, M) || dev_upload(c->allocs, &c->head_v, v) || dev_upload(c->allocs, &c->head_b, sk.h_b)) return 1;
+  }
   c->raw.clear();
   c->finalized = true;
   return 0;
@@ -1415,6 +1452,7 @@ int32_t dhg_set_option(dhg_ctx* c, const char* key, int32_t value) {
   if (key && !strcmp(key, "serpentine")) { g_opt_serpentine = value ? 1 : 0; return 0; }
   if (key && !strcmp(key, "l2_hints")) { g_opt_l2_hints = value ? 1 : 0; return 0; }
   if (key && !strcmp(key, "tail_fusion")) { g_opt_tail_fusion = value ? 1 : 0; return 0; }
+  if (key && !strcmp(key, "head_fusion")) { g_opt_head_fusion = value ? 1 : 0; return 0; }
   if (key && !strcmp(key, "tune_rev")) { tc_gemm_set_option(14, value); return 0; }
   if (key && !strcmp(key, "tune_bn")) { tc_gemm_set_option(10, value); return 0; }
   if (key && !strcmp(key, "tune_g")) { tc_gemm_set_option(11, value); return 0; }

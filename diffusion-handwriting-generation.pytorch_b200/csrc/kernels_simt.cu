@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(256) pool_kernel(const T* __restrict__ in, T* 
     if (out_raw) store8<T>(out_raw + rout * C + c, m);
     if (out_act) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) m[k] = silu_f(m[k]);
+      for (int k = 0; k < 8; ++k) m[k] = silu_out<T>(m[k]);
       store8<T>(out_act + rout * C + c, m);
     }
   }
@@ -422,7 +422,7 @@ __global__ void input_dense_kernel(const float* __restrict__ x, const float* __r
   for (int i = 0; i < 4; ++i) v[i] = fmaf(s.y, W[(c + i) * 2 + 1], fmaf(s.x, W[(c + i) * 2], bias[c + i]));
   const size_t r = (size_t)b * (Tn + 1) + 1 + t;
   store4<T>(out_raw + r * C + c, make_float4(v[0], v[1], v[2], v[3]));
-  store4<T>(out_act + r * C + c, make_float4(silu_f(v[0]), silu_f(v[1]), silu_f(v[2]), silu_f(v[3])));
+  store4<T>(out_act + r * C + c, make_float4(silu_out<T>(v[0]), silu_out<T>(v[1]), silu_out<T>(v[2]), silu_out<T>(v[3])));
 }
 template <typename T>
 void launch_input_dense(const float* x, const float* W, const float* bias, T* out_raw, T* out_act,
@@ -432,6 +432,74 @@ void launch_input_dense(const float* x, const float* W, const float* bias, T* ou
 }
 template void launch_input_dense<float>(const float*, const float*, const float*, float*, float*, int, int, int, cudaStream_t);
 template void launch_input_dense<bf16>(const float*, const float*, const float*, bf16*, bf16*, int, int, int, cudaStream_t);
+
+// ---------------------------------------------------------------------------
+// Head fusion: enc1.conv_skip(input_dense(x)) straight from x.  input_dense is linear (model.py:139) and conv_skip
+// sees its raw output (cnn.py:66), so
+//   skip[t] = sum over the taps tau in {-1,0,1} with 0 <= t+tau < T of (x[t+tau] . M_tau + v_tau) + b_skip,
+//   M_tau = W_in^T W_skip,tau (2 x C),  v_tau = b_in . W_skip,tau   (tables from dhg_finalize, fp32)
+// (positions outside the line are zero rows of the padded layout, NOT input_dense(0), hence the per-tap v_tau).
+// 16 lanes per stroke point, 8 channels per lane held in registers, grid-stride; writes the padded-row [rows, C] matrix.
+// ---------------------------------------------------------------------------
+constexpr int kSkipPts = 512;   // stroke points per block
+template <typename T_>
+__global__ void __launch_bounds__(256) skip_from_x_kernel(const float* __restrict__ x, const float* __restrict__ M /*[3][2][C]*/,
+                                                          const float* __restrict__ v /*[3][C]*/, const float* __restrict__ bsk,
+                                                          T_* __restrict__ out, int B, int Tn, int C) {
+  // A block owns kSkipPts consecutive points: their x (plus one neighbour on each side) is staged in shared memory with
+  // one coalesced burst, after that the block only computes and stores (the output is the whole traffic: C bf16 per point).
+  __shared__ float2 xs[kSkipPts + 2];
+  const uint32_t npts = (uint32_t)B * (uint32_t)Tn, T = (uint32_t)Tn;
+  const uint32_t p0 = blockIdx.x * kSkipPts;
+  for (uint32_t j = threadIdx.x; j < kSkipPts + 2; j += blockDim.x) {
+    const int64_t i = (int64_t)p0 + j - 1;
+    xs[j] = (i >= 0 && i < (int64_t)npts) ? *reinterpret_cast<const float2*>(x + (size_t)i * 2) : make_float2(0.f, 0.f);
+  }
+  const int sub = threadIdx.x & 15, pl = threadIdx.x >> 4;   // channel octet, point lane (16 points in flight per pass)
+  const int c0 = sub * 8;
+  float m[3][2][8], v0[8], v2[8], ball[8];   // ball: bias + all three per-tap constants (the interior case)
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    v0[k] = v[c0 + k];
+    v2[k] = v[2 * C + c0 + k];
+    ball[k] = bsk[c0 + k] + v[C + c0 + k] + v0[k] + v2[k];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      m[t][0][k] = M[(t * 2 + 0) * C + c0 + k];
+      m[t][1][k] = M[(t * 2 + 1) * C + c0 + k];
+    }
+  }
+  __syncthreads();
+  uint32_t i = p0 + pl;
+  uint32_t b = i / T, t = i - b * T;   // one division per thread; then t advances by 16 per pass
+  for (int j = pl; j < kSkipPts && i < npts; j += 16, i += 16) {
+    const bool has_l = t > 0, has_r = t + 1 < T;
+    const float2 xc = xs[j + 1];
+    const float2 xl = has_l ? xs[j] : make_float2(0.f, 0.f), xr = has_r ? xs[j + 2] : make_float2(0.f, 0.f);
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float a = ball[k];
+      a = fmaf(xc.x, m[1][0][k], a); a = fmaf(xc.y, m[1][1][k], a);
+      a = fmaf(xl.x, m[0][0][k], a); a = fmaf(xl.y, m[0][1][k], a);
+      a = fmaf(xr.x, m[2][0][k], a); a = fmaf(xr.y, m[2][1][k], a);
+      if (!has_l) a -= v0[k];   // first / last position of a line: that tap reads a zero row, not input_dense(0)
+      if (!has_r) a -= v2[k];
+      o[k] = a;
+    }
+    store8<T_>(out + ((size_t)i + b + 1) * C + c0, o);
+    t += 16;
+    while (t >= T) { t -= T; ++b; }
+  }
+}
+template <typename T>
+int launch_skip_from_x(const float* x, const float* M, const float* v, const float* bsk, T* out, int B, int Tn, int C, cudaStream_t st) {
+  if (C != 128) return 1;
+  const size_t npts = (size_t)B * Tn;
+  skip_from_x_kernel<T><<<(unsigned)((npts + kSkipPts - 1) / kSkipPts), 256, 0, st>>>(x, M, v, bsk, out, B, Tn, C);
+  return 0;
+}
+template int launch_skip_from_x<bf16>(const float*, const float*, const float*, const float*, bf16*, int, int, int, cudaStream_t);
 
 // ---------------------------------------------------------------------------
 // Output heads + fused posterior update (+ fused input_dense of the next step).
@@ -573,7 +641,7 @@ __global__ void __launch_bounds__(256, DHG_HEADS_MINB) heads_update_kernel(const
       }
       if (p.next_raw) store8<T_>(reinterpret_cast<T_*>(p.next_raw) + row * C + c0, v);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = silu_f(v[k]);
+      for (int k = 0; k < 8; ++k) v[k] = silu_out<T_>(v[k]);
       if (p.next_act) store8<T_>(reinterpret_cast<T_*>(p.next_act) + row * C + c0, v);
     }
   }
@@ -730,7 +798,7 @@ __global__ void silu_convert_kernel(const float* __restrict__ in, T* __restrict_
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const float4 x = reinterpret_cast<const float4*>(in)[i];
-  store4<T>(out + i * 4, make_float4(silu_f(x.x), silu_f(x.y), silu_f(x.z), silu_f(x.w)));
+  store4<T>(out + i * 4, make_float4(silu_out<T>(x.x), silu_out<T>(x.y), silu_out<T>(x.z), silu_out<T>(x.w)));
 }
 template <typename T>
 void launch_silu_convert(const float* in, T* out, size_t n, cudaStream_t st) {
