@@ -341,26 +341,34 @@ template int launch_attention_simt<bf16>(const AttnParams&, cudaStream_t);
 // FiLM over rows: out[r, c] = in[r, c] * gamma[b, c] + beta[b, c]   (conditioning.py:19)
 // ---------------------------------------------------------------------------
 template <typename T>
-__global__ void film_rows_kernel(const T* __restrict__ in, T* __restrict__ out, int rows, int C,
-                                 int period, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, int bstride) {
-  const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int c4 = C >> 2;
-  if (i4 >= (size_t)rows * c4) return;
-  const int r = (int)(i4 / c4), c = (int)(i4 - (size_t)r * c4) * 4;
-  const int b = r / period;
-  float4 x = load4<T>(in + (size_t)r * C + c);
-  const float4 g = *reinterpret_cast<const float4*>(gamma + (size_t)b * bstride + c);
-  const float4 bb = *reinterpret_cast<const float4*>(beta + (size_t)b * bstride + c);
-  x.x = fmaf(x.x, g.x, bb.x); x.y = fmaf(x.y, g.y, bb.y);
-  x.z = fmaf(x.z, g.z, bb.z); x.w = fmaf(x.w, g.w, bb.w);
-  store4<T>(out + (size_t)r * C + c, x);
+__global__ void __launch_bounds__(256) film_rows_kernel(const T* __restrict__ in, T* __restrict__ out, int rows, int C,
+                                                        int period, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, int bstride) {
+  // 8 channels (16 bytes of bf16) per thread, grid-stride, 32-bit index arithmetic (rows * C / 8 < 2^31 by the plan limit)
+  const uint32_t c8 = (uint32_t)C >> 3, total = (uint32_t)rows * c8;
+  for (uint32_t i8 = blockIdx.x * blockDim.x + threadIdx.x; i8 < total; i8 += gridDim.x * blockDim.x) {
+    const uint32_t r = i8 / c8, c = (i8 - r * c8) * 8;
+    const uint32_t b = bstride ? r / (uint32_t)period : 0u;
+    float x[8];
+    load8<T>(in + (size_t)r * C + c, x);
+    const float4* g = reinterpret_cast<const float4*>(gamma + (size_t)b * bstride + c);
+    const float4* bb = reinterpret_cast<const float4*>(beta + (size_t)b * bstride + c);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const float4 gq = g[q], bq = bb[q];
+      x[q * 4 + 0] = fmaf(x[q * 4 + 0], gq.x, bq.x); x[q * 4 + 1] = fmaf(x[q * 4 + 1], gq.y, bq.y);
+      x[q * 4 + 2] = fmaf(x[q * 4 + 2], gq.z, bq.z); x[q * 4 + 3] = fmaf(x[q * 4 + 3], gq.w, bq.w);
+    }
+    store8<T>(out + (size_t)r * C + c, x);
+  }
 }
 template <typename T>
 void launch_film_rows(const T* in, T* out, int rows, int C, int period, const float* gamma,
                       const float* beta, int bstride, cudaStream_t st) {
-  const size_t n4 = (size_t)rows * (C >> 2);
-  film_rows_kernel<T><<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(in, out, rows, C, period, gamma, beta, bstride);
+  const size_t n8 = (size_t)rows * (C >> 3);
+  size_t blocks = (n8 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  film_rows_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(in, out, rows, C, period, gamma, beta, bstride);
 }
 template void launch_film_rows<float>(const float*, float*, int, int, int, const float*, const float*, int, cudaStream_t);
 template void launch_film_rows<bf16>(const bf16*, bf16*, int, int, int, const float*, const float*, int, cudaStream_t);
@@ -371,12 +379,12 @@ template void launch_film_rows<bf16>(const bf16*, bf16*, int, int, int, const fl
 template <typename T>
 __global__ void __launch_bounds__(256) pool_kernel(const T* __restrict__ in, T* __restrict__ out_raw, T* __restrict__ out_act,
                                                    int B, int Tlo, int C) {
-  const int c8 = C >> 3;
-  const size_t total = (size_t)B * Tlo * c8;
-  for (size_t i8 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i8 < total; i8 += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i8 % c8) * 8;
-    const size_t bt = i8 / c8;
-    const int t = (int)(bt % Tlo), b = (int)(bt / Tlo);
+  // 32-bit index arithmetic: B * Tlo * C / 8 < 2^31 by the plan limit (B * (T + 1) < 2^24, C <= 384)
+  const uint32_t c8 = (uint32_t)C >> 3;
+  const uint32_t total = (uint32_t)B * (uint32_t)Tlo * c8;
+  for (uint32_t i8 = blockIdx.x * blockDim.x + threadIdx.x; i8 < total; i8 += gridDim.x * blockDim.x) {
+    const uint32_t bt = i8 / c8, c = (i8 - bt * c8) * 8;
+    const uint32_t b = bt / (uint32_t)Tlo, t = bt - b * (uint32_t)Tlo;
     const size_t rin = (size_t)b * (2 * Tlo + 1) + 1 + 2 * t;
     const size_t rout = (size_t)b * (Tlo + 1) + 1 + t;
     float x0[8], x1[8], m[8];
