@@ -9,18 +9,21 @@ for p in (ROOT, os.path.join(ROOT, "diffusion-handwriting-generation.pytorch_b20
         sys.path.insert(0, p)
 
 
-def step_gemm_cases(B, T=392, L=24, SP=70):
-    """[(name, launches per step, rows, K, N, taps, epilogue kwargs)]"""
+def step_gemm_cases(B, T=392, L=24, SP=70, chain=True):
+    """[(name, launches per step, rows, K, N, taps, epilogue kwargs)]
+
+    chain=True: the GEMMs a step of the sampling chain launches (63): enc1.conv_skip and dec1.fc are folded into
+    skip_from_x / the head kernel there; chain=False: all 65 of a stand-alone forward (dhg_denoise)."""
     lv = [dict(period=(T >> l) + 1, pad_first=1) for l in range(4)]
     R = [B * ((T >> l) + 1) + 1 for l in range(4)]
     tx, stl = dict(period=L, pad_first=0), dict(period=SP, pad_first=0)
     RT, RS = B * L, B * SP
     CASES = [
         # name, count per step, rows, K, N, taps, kwargs
-        ("L0 conv_skip 128->128", 1, R[0], 128, 128, 3, dict(**lv[0])),
+        ("L0 conv_skip 128->128", 0 if chain else 1, R[0], 128, 128, 3, dict(**lv[0])),
         ("L0 conv1 128->64 film act", 1, R[0], 128, 64, 3, dict(**lv[0], film=1, raw=False, act=True)),
         ("L0 conv2 64->128 film act", 2, R[0], 64, 128, 3, dict(**lv[0], film=1, raw=False, act=True)),
-        ("L0 fc 128 film +skip", 2, R[0], 128, 128, 1, dict(**lv[0], film=1, res_post=True)),
+        ("L0 fc 128 film +skip", 1 if chain else 2, R[0], 128, 128, 1, dict(**lv[0], film=1, res_post=True)),
         ("L0 skip_conv1 128->192 up", 1, R[0], 128, 192, 3, dict(**lv[0], res_post=True, up=True, act=True)),
         ("L0 dec1.conv_skip 192->128", 1, R[0], 192, 128, 3, dict(**lv[0])),
         ("L0 dec1.conv1 192->64", 1, R[0], 192, 64, 3, dict(**lv[0], film=1, raw=False, act=True)),
