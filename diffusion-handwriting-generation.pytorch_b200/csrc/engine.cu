@@ -488,9 +488,10 @@ struct Builder {
       const int bn = bns[bi];
       for (int g : {1, 2, 4}) {
         if (g * bn > 256 && g > 1) continue;
-        for (int mode = 0; mode < 3; ++mode) {   // 0: resident W, 1: streamed W, 2: streamed W + CTA pairs
-          if (mode == 2 && g != 1) continue;
-          TcTune t{bn, g, mode == 0 ? 1 : 0, mode == 2 ? 1 : 0};
+        for (int mode = 0; mode < 5; ++mode) {   // 0: resident W, 1: streamed W, 2: streamed W + CTA pairs,
+          if (mode >= 2 && g != 1) continue;       // 3 / 4: column-split LayerNorm cluster with resident / streamed W
+          if (mode >= 3 && !e.ln) continue;
+          TcTune t{bn, g, (mode == 0 || mode == 3) ? 1 : 0, mode == 2 ? 1 : mode >= 3 ? 2 : 0};
           char buf[256];
           TcGemmPlan* p = tc_gemm_plan_create(Ap, lda, rows, W->w16, W->K, N, W->taps, e, buf, sizeof(buf), &t);
           if (!p) continue;   // configuration not available for this shape

@@ -56,6 +56,7 @@ struct TcShape {
   int m_super;     // ceil(m_tiles / G)
   int rev;         // walk the super-tiles from the last row to the first (see tc_gemm_plan_set_reverse)
   int a_evict_first;   // A rows are read once by this launch: give them L2 evict-first priority
+  int split;           // column-split LayerNorm: 2-CTA cluster per row tile, rank = column half
   int stages_a, stages_w;   // A ring / W ring depth (W ring unused when w_resident)
   int w_resident;  // all W tiles of this CTA's column group stay in smem for the whole kernel
   int sticky;      // each CTA works on one column group only
@@ -190,7 +191,7 @@ __device__ __forceinline__ void mma_issue_loop(const TcShape& sh, const bool lea
 // Template parameters fix the epilogue variant at compile time (-1 = read the flag at run time: the
 // generic instance).  kLN: LayerNorm; kAUX: AUX_* kind; kFILM: 0 none, 1 vectors shared by the batch
 // (smem), 2 per-sample vectors (global loads); kOUT: 1 raw, 2 SiLU'd, 3 both.
-template <int kLN, int kAUX, int kFILM, int kOUT, bool kPAIR>
+template <int kLN, int kAUX, int kFILM, int kOUT, bool kPAIR, bool kSPLIT = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_w,
                                                                 const __grid_constant__ CUtensorMap map_oraw,
@@ -207,6 +208,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   uint64_t* tmem_full_bar = bars + 33;         // [2]
   uint64_t* tmem_empty_bar = bars + 35;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 37);
+  uint64_t* stats_bar = bars + 40;             // [2] split mode: the peer's LayerNorm partial statistics have landed
   float* bias_s = reinterpret_cast<float*>(smem + sh.off_vec);
   float* gamma_s = bias_s + sh.vec_bias_n;
   float* betap_s = gamma_s + sh.film_n;
@@ -218,16 +220,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   // sticky: the CTAs [grp_cta0[g], grp_cta0[g+1]) work on column group g only (more CTAs for the groups whose
   // epilogue also has per-position bias rows to fetch), so that group's W tiles can stay resident
   // pair mode: the two CTAs of a cluster work on two consecutive row tiles of the same column group
+  // split mode (LayerNorm rows wider than one double-buffered accumulator): the two CTAs of a cluster work on the SAME
+  // row tile, rank r on column half r; they only meet in the LayerNorm statistics (see the epilogue)
   const uint32_t cta_rank = kPAIR ? cluster_ctarank() : 0u;
+  const uint32_t split_rank = kSPLIT ? cluster_ctarank() : 0u;
+  constexpr bool kCLUSTER = kPAIR || kSPLIT;
   const int tiles_per_super = kPAIR ? 2 : sh.G;
-  int my_group = 0, t_first = kPAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, t_step = kPAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  int my_group = kSPLIT ? (int)split_rank : 0;
+  int t_first = kCLUSTER ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, t_step = kCLUSTER ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const bool bound_group = sh.sticky || kSPLIT;   // this CTA works on one column group only
   if (sh.sticky) {
     while (my_group + 1 < sh.n_groups && (int)blockIdx.x >= sh.grp_cta0[my_group + 1]) ++my_group;
     t_first = (int)blockIdx.x - sh.grp_cta0[my_group];
     t_step = sh.grp_cta0[my_group + 1] - sh.grp_cta0[my_group];
   }
-  const int t_end = sh.sticky ? sh.m_super : sh.m_super * sh.n_groups;   // work items = (super-tile, column group)
-  const bool one_group = sh.sticky || sh.n_groups == 1;   // work item index == super-tile index (no division needed)
+  const int t_end = bound_group ? sh.m_super : sh.m_super * sh.n_groups;   // work items = (super-tile, column group)
+  const bool one_group = bound_group || sh.n_groups == 1;   // work item index == super-tile index (no division needed)
   uint8_t* a_ring = smem;
   uint8_t* w_base = smem + sh.off_w;
   const bool film = e.gamma != nullptr;
@@ -254,6 +262,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       mbar_init(smem_u32(&tmem_full_bar[a]), 1);
       mbar_init(smem_u32(&tmem_empty_bar[a]), EPI_WARPS * (kPAIR ? 2 : 1));   // pair: rank 0 collects both CTAs' epilogues
     }
+    if (kSPLIT)
+      for (int a = 0; a < 2; ++a) mbar_init(smem_u32(&stats_bar[a]), EPI_WARPS * 32);   // every epilogue thread of the peer
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -276,7 +286,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
-  if (kPAIR) cluster_sync_all();   // the peer's barriers are initialised before anything is signalled across the pair
+  if (kCLUSTER) cluster_sync_all();   // the peer's barriers are initialised before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -303,7 +313,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     const uint64_t pol_a = l2_policy_evict_first();
     for (int t = t_first; t < t_end; t += t_step) {
       const int mts_f = one_group ? t : t / sh.n_groups;
-      const int ng = sh.sticky ? my_group : t - mts_f * sh.n_groups;
+      const int ng = bound_group ? my_group : t - mts_f * sh.n_groups;
       const int mts = sh.rev ? sh.m_super - 1 - mts_f : mts_f;
       const int n0 = ng * sh.BN;
       for (int kbi = 0; kbi < sh.kb_per_tap; ++kbi) {
@@ -392,7 +402,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     const uint32_t aux_ring = smem_u32(smem + sh.off_aux + (size_t)ew * AUX_RING_BYTES);
     const uint32_t out_st = smem_u32(smem + sh.off_out + (size_t)ew * (sh.out_bufs == 2 ? OUT_STAGE_BYTES : 2048));
     const uint32_t bias_sa = smem_u32(bias_s), gamma_sa = smem_u32(gamma_s), betap_sa = smem_u32(betap_s);
-    float2* ln_s = reinterpret_cast<float2*>(smem + sh.off_ln);   // [2 parity][128 rows][EPI_PARTS] {mean, M2} of each column part
+    float2* ln_s = reinterpret_cast<float2*>(smem + sh.off_ln);   // [2 parity][128 rows][EPI_PARTS (x2 in split mode)] {mean, M2} of each column part
     const int aux_ncols = aux_kind == AUX_ROWBIAS ? e.rowbias16_cols : 0x7fffffff;   // aux only for columns below this
     constexpr int aux_depth = AUX_DEPTH;
     constexpr uint32_t aux_slot_bytes = AUX_SLOT_BYTES;
@@ -424,7 +434,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       if (ft < t_end) {
         if (ci == 0) {   // first chunk of a row tile: where does my row's residual / bias row live?
           const int fmts_f = one_group ? ft : ft / sh.n_groups;
-          iss_ng = sh.sticky ? my_group : ft - fmts_f * sh.n_groups;
+          iss_ng = bound_group ? my_group : ft - fmts_f * sh.n_groups;
           const int fmts = sh.rev ? sh.m_super - 1 - fmts_f : fmts_f;
           const int fm = (fmts * tiles_per_super + fsub + (int)cta_rank) * TC_BM + r_tile;
           const bool f_in = fm < sh.rows;
@@ -492,7 +502,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     int it = 0, tile_no = 0;
     for (int t = t_first; t < t_end; t += t_step, ++it) {
      const int mts_f = one_group ? t : t / sh.n_groups;
-     const int ng = sh.sticky ? my_group : t - mts_f * sh.n_groups;
+     const int ng = bound_group ? my_group : t - mts_f * sh.n_groups;
      const int mts = sh.rev ? sh.m_super - 1 - mts_f : mts_f;
      const int n0 = ng * sh.BN;
      const int as = sh.acc_stages == 2 ? (it & 1) : 0;
@@ -547,8 +557,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       float v[32];
       float mean = 0.f, rstd = 1.f;
       if (ln) {
-        // pass 1: x = acc + bias + res_pre -> back to TMEM; shifted sums over my column half
-        float shift = 0.f, s1 = 0.f, s2 = 0.f;
+        // pass 1: x = acc + bias + res_pre -> back to TMEM; shifted sums per STATISTICS GROUP of columns.  A row always
+        // has the same groups whatever the tile configuration: a quarter of the row when the row has a multiple of 4
+        // chunks (so the plain / paired kernel, 2 groups per column part, and the column-split kernel, 1 group per
+        // part and CTA, merge the same partial sums in the same order and give the same bits), else one per part.
+        const bool quarters = !kSPLIT && (nch % (2 * EPI_PARTS)) == 0;   // plain / paired kernel with a row of 4k chunks
+        const int gpp = quarters ? 2 : 1;                                 // groups per part
+        const int g_nch = my_nch / gpp;                                                    // chunks per group
+        float shift0 = 0.f, s1a = 0.f, s2a = 0.f, shift1 = 0.f, s1b = 0.f, s2b = 0.f;
         for (int ci = 0; ci < my_nch; ++ci) {
           const int c = c_lo + ci;
           tmem_ld32(trow + c * 32, v);
@@ -560,27 +576,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
             }
           }
           if (aux_in_pass1) consume_aux(v, n0 + c * 32);
-          if (ci == 0) shift = v[0];
+          const bool second = gpp == 2 && ci >= g_nch;
+          if (ci == 0) shift0 = v[0];
+          if (gpp == 2 && ci == g_nch) shift1 = v[0];
+          const float shift = second ? shift1 : shift0;
+          float t1 = 0.f, t2 = 0.f;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float dlt = v[i] - shift;
-            s1 += dlt;
-            s2 = fmaf(dlt, dlt, s2);
+            t1 += dlt;
+            t2 = fmaf(dlt, dlt, t2);
           }
+          if (second) { s1b += t1; s2b += t2; } else { s1a += t1; s2a += t2; }
           tmem_st32(trow + c * 32, v);
         }
-        // merge the column parts (Chan's parallel mean / M2 update) through shared memory
-        float2* st = ln_s + ((size_t)(tile_no & 1) * TC_BM + r_tile) * EPI_PARTS;
+        // merge the groups (Chan's parallel mean / M2 update) through shared memory, in column order; in split mode
+        // the row's other half lives in the peer CTA: each side also writes its groups into the other's table (DSMEM)
+        // and announces them on the other's stats barrier.  Tables alternate with the tile parity: the peer can only
+        // be one tile ahead, because it needs my statistics to finish a tile.
+        constexpr int NG = 2 * EPI_PARTS;   // table entries per row (unused ones are skipped)
+        float2* st = ln_s + ((size_t)(tile_no & 1) * TC_BM + r_tile) * NG;
+        const int n_groups_row = kSPLIT ? 2 * EPI_PARTS : EPI_PARTS * gpp;
+        const int my_slot = kSPLIT ? (int)split_rank * EPI_PARTS + part : part * gpp;
         if (my_nch > 0) {
-          const float n_h = (float)(my_nch * 32);
-          st[part] = make_float2(shift + s1 / n_h, fmaxf(s2 - s1 * s1 / n_h, 0.f));
+          const float n_g = (float)(g_nch * 32);
+          const float2 ga = make_float2(shift0 + s1a / n_g, fmaxf(s2a - s1a * s1a / n_g, 0.f));
+          st[my_slot] = ga;
+          if (gpp == 2) st[my_slot + 1] = make_float2(shift1 + s1b / n_g, fmaxf(s2b - s1b * s1b / n_g, 0.f));
+          if (kSPLIT) st_shared_remote_f2(smem_u32(&st[my_slot]), split_rank ^ 1u, ga.x, ga.y);
         }
+        if (kSPLIT) mbar_arrive_remote(smem_u32(&stats_bar[tile_no & 1]), split_rank ^ 1u);
         asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(32 * EPI_PARTS) : "memory");
+        if (kSPLIT) mbar_wait_cluster(smem_u32(&stats_bar[tile_no & 1]), (uint32_t)(tile_no >> 1) & 1u);
         float n_acc = 0.f, m2 = 0.f;
         mean = 0.f;
-#pragma unroll
-        for (int pp = 0; pp < EPI_PARTS; ++pp) {
-          const int cnt = (((pp + 1) * nch) / EPI_PARTS - (pp * nch) / EPI_PARTS) * 32;
+        for (int pp = 0; pp < n_groups_row; ++pp) {
+          // group width: uniform in split / quarters mode, else the (possibly uneven) column part pp
+          const int cnt = (kSPLIT || quarters) ? (nch / (EPI_PARTS * gpp)) * 32
+                                               : (((pp + 1) * nch) / EPI_PARTS - (pp * nch) / EPI_PARTS) * 32;
           if (cnt > 0) {
             const float2 o = st[pp];
             const float n_p = (float)cnt, n_new = n_acc + n_p;
@@ -590,7 +623,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
             n_acc = n_new;
           }
         }
-        const float n_t = (float)sh.BN;
+        const float n_t = (float)(sh.BN * (kSPLIT ? 2 : 1));
         rstd = rsqrtf(m2 / n_t + 1e-6f);
       }
       const float nmr = -mean * rstd;
@@ -660,7 +693,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
-  if (kPAIR) cluster_sync_all();   // the peer may still be signalling my barriers / reading my smem through the MMA
+  if (kCLUSTER) cluster_sync_all();   // the peer may still be signalling my barriers / reading or writing my smem
   if (warp == 1) {
     tc_fence_after();
     if (kPAIR)
@@ -691,8 +724,9 @@ void tc_gemm_set_option(int which, int value) {
 }
 
 typedef void (*TcKernFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcShape, const Epilogue);
-struct TcKernEntry { int ln, aux, film, out; TcKernFn fn, fn_pair; };   // fn_pair: the cta_group::2 build (cluster launch only)
-#define DHG_TC_K(ln, aux, film, out) {ln, aux, film, out, tc_gemm_kernel<ln, aux, film, out, false>, tc_gemm_kernel<ln, aux, film, out, true>}
+struct TcKernEntry { int ln, aux, film, out; TcKernFn fn, fn_pair, fn_split; };   // fn_pair: the cta_group::2 build, fn_split: column-split LayerNorm (cluster launches only)
+#define DHG_TC_K(ln, aux, film, out) {ln, aux, film, out, tc_gemm_kernel<ln, aux, film, out, false>, tc_gemm_kernel<ln, aux, film, out, true>, nullptr}
+#define DHG_TC_KL(aux, film, out) {1, aux, film, out, tc_gemm_kernel<1, aux, film, out, false>, tc_gemm_kernel<1, aux, film, out, true>, tc_gemm_kernel<1, aux, film, out, false, true>}
 // Every epilogue variant the denoiser plan uses (engine.cu), film = 1 (sampling: one FiLM vector per step);
 // anything else (per-sample FiLM in dhg_denoise, test-only combinations) runs the generic instance.
 static const TcKernEntry kTcKernels[] = {
@@ -702,22 +736,23 @@ static const TcKernEntry kTcKernels[] = {
     DHG_TC_K(0, AUX_RES_POST, 1, 1),      // fc + skip
     DHG_TC_K(0, AUX_RES_POST_UP, 0, 3),   // skip_conv_k + upsample
     DHG_TC_K(0, AUX_ROWBIAS, 0, 1),       // q / kv / qkv projections with the PE-folded bias table
-    DHG_TC_K(1, AUX_NONE, 1, 1),          // text_dense
-    DHG_TC_K(1, AUX_NONE, 0, 1),          // style_ffn.3
-    DHG_TC_K(1, AUX_NONE, 1, 2),          // text_ffn.3
-    DHG_TC_K(1, AUX_RES_POST, 1, 1),      // mha.dense
-    DHG_TC_K(1, AUX_RES_PRE, 1, 3),       // mha2.dense
-    DHG_TC_K(1, AUX_RES_PRE, 1, 1),       // ffn.3
-    DHG_TC_K(1, AUX_RES_PRE, 1, 2),       // text-style mha.dense
-    DHG_TC_K(-1, -1, -1, -1),             // generic
+    DHG_TC_KL(AUX_NONE, 1, 1),          // text_dense
+    DHG_TC_KL(AUX_NONE, 0, 1),          // style_ffn.3
+    DHG_TC_KL(AUX_NONE, 1, 2),          // text_ffn.3
+    DHG_TC_KL(AUX_RES_POST, 1, 1),      // mha.dense
+    DHG_TC_KL(AUX_RES_PRE, 1, 3),       // mha2.dense
+    DHG_TC_KL(AUX_RES_PRE, 1, 1),       // ffn.3
+    DHG_TC_KL(AUX_RES_PRE, 1, 2),       // text-style mha.dense
+    {-1, -1, -1, -1, tc_gemm_kernel<-1, -1, -1, -1, false>, tc_gemm_kernel<-1, -1, -1, -1, true>, tc_gemm_kernel<-1, -1, -1, -1, false, true>},   // generic
 };
-static TcKernFn pick_kernel(int ln, int aux, int film, int out, bool pair) {
+static TcKernFn pick_kernel(int ln, int aux, int film, int out, int cluster_mode) {   // 0 plain, 1 CTA pair, 2 column-split LayerNorm
   const int n = (int)(sizeof(kTcKernels) / sizeof(kTcKernels[0]));
+  auto of = [&](const TcKernEntry& k) { return cluster_mode == 2 ? k.fn_split : cluster_mode == 1 ? k.fn_pair : k.fn; };
   if (g_opt_specialize)
     for (int i = 0; i < n - 1; ++i)
-      if (kTcKernels[i].ln == ln && kTcKernels[i].aux == aux && kTcKernels[i].film == film && kTcKernels[i].out == out)
-        return pair ? kTcKernels[i].fn_pair : kTcKernels[i].fn;
-  return pair ? kTcKernels[n - 1].fn_pair : kTcKernels[n - 1].fn;
+      if (kTcKernels[i].ln == ln && kTcKernels[i].aux == aux && kTcKernels[i].film == film && kTcKernels[i].out == out && of(kTcKernels[i]))
+        return of(kTcKernels[i]);
+  return of(kTcKernels[n - 1]);
 }
 
 struct TcGemmPlan {
@@ -738,9 +773,12 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
     return nullptr;
   }
   int BN = 0;
+  // pair == 2: column-split LayerNorm, a 2-CTA cluster per row tile, each CTA accumulates N/2 columns double-buffered
+  const bool split = tn.pair == 2;
+  if (split && !(e.ln && N % 128 == 0 && N / 2 <= 256)) { snprintf(err, errlen, "column-split mode does not fit: it needs a LayerNorm epilogue with N = 128, 256 or 384 (N=%d)", N); return nullptr; }
   if (e.ln) {
     if (!((N <= 256 && N >= 64) || N == 384)) { snprintf(err, errlen, "LayerNorm epilogue needs 64 <= N <= 256 or N == 384, got %d", N); return nullptr; }
-    BN = N;
+    BN = split ? N / 2 : N;
   } else {
     for (int cand : {256, 192, 128, 96, 64})
       if (N % cand == 0) { BN = cand; break; }
@@ -787,7 +825,8 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   sh.film_n = e.film_planned ? N : 0;
   // independent accumulators per super-tile: as many as fit in one 256-column TMEM group, at most 4
   int G = 1;
-  if (g_opt_interleave && BN <= 128) G = BN <= 64 ? 4 : 2;
+  if (g_opt_interleave && BN <= 128 && !split) G = BN <= 64 ? 4 : 2;
+  if (split && tn.g > 1) { snprintf(err, errlen, "column-split mode does not fit interleaved accumulators"); delete p; return nullptr; }
   if (tn.g > 0) {
     if ((tn.g != 1 && tn.g != 2 && tn.g != 4) || (tn.g > 1 && tn.g * BN > 256)) { snprintf(err, errlen, "%d interleaved accumulators of %d columns do not fit a 256-column TMEM group", tn.g, BN); delete p; return nullptr; }
     G = tn.g;
@@ -800,8 +839,9 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   sh.a_stage_bytes = (sh.a_tx_bytes + 1023u) & ~1023u;
   sh.w_tile_bytes = (uint32_t)BN * TC_BK * 2;
   // smem carve-up: A ring | W ring or resident W | aux rings | out staging | vectors | LN exchange | barriers
+  const size_t ln_bytes = e.ln ? (size_t)2 * TC_BM * (2 * EPI_PARTS) * 8 : 0;   // [2 tile parities][128 rows][2 * EPI_PARTS groups] {mean, M2}
   size_t fixed = (aux_kind != AUX_NONE ? (size_t)EPI_WARPS * AUX_RING_BYTES : 0) + (size_t)EPI_WARPS * OUT_STAGE_BYTES +
-                 (size_t)(sh.vec_bias_n + 2 * sh.film_n) * 4 + 16 + (e.ln ? 2 * TC_BM * EPI_PARTS * 8 : 0) + 64 * 8;
+                 (size_t)(sh.vec_bias_n + 2 * sh.film_n) * 4 + 16 + ln_bytes + 64 * 8;
   size_t budget = 227 * 1024 - 1024 - fixed;
   sh.out_bufs = OUT_STAGE_BYTES >= 4096 ? 2 : 1;
   if (sh.out_bufs == 2 && 2 * (size_t)(sh.a_stage_bytes + BN * TC_BK * 2) > budget) {   // not even two A + two W stages: give up the second store tile
@@ -813,13 +853,14 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   const int min_a = G > 1 ? 2 * G : 3;
   const int want_resident = tn.resident >= 0 ? tn.resident : g_opt_w_resident;
   sh.w_resident = (want_resident && w_all + (size_t)min_a * sh.a_stage_bytes <= budget && sh.m_super * sh.n_groups > num_sms) ? 1 : 0;
-  sh.sticky = (sh.w_resident && sh.n_groups > 1) ? 1 : 0;
+  sh.sticky = (sh.w_resident && sh.n_groups > 1 && !split) ? 1 : 0;
+  sh.split = split ? 1 : 0;
   // W does not fit: pair the CTAs of a cluster (cta_group::2) so that each SM only ingests half of every W tile
   // Measured (profiles/): pairing pays when the MMA / W-stream phase dominates the tile (K*taps >= 512 and a light
   // epilogue, or the single-buffered 384-wide LayerNorm rows); with g_opt_pair == 2 every non-resident GEMM is paired.
   const int out_mode_plan = (e.out_raw ? 1 : 0) | (e.out_act ? 2 : 0);
   const bool pair_pays = BN == 384 || (taps * K >= 512 && out_mode_plan != 3 && !(e.ln && N <= 192));
-  const bool want_pair = tn.pair >= 0 ? tn.pair != 0 : (g_opt_pair && (g_opt_pair == 2 || pair_pays));
+  const bool want_pair = split ? false : tn.pair >= 0 ? tn.pair != 0 : (g_opt_pair && (g_opt_pair == 2 || pair_pays));
   sh.pair = (!sh.w_resident && want_pair && G == 1 && sh.umma_n % 16 == 0 &&
              (m_tiles + 1) / 2 * sh.n_groups >= num_sms / 2) ? 1 : 0;
   if (sh.pair) {
@@ -852,7 +893,7 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   sh.off_out = off; off += EPI_WARPS * (sh.out_bufs == 2 ? OUT_STAGE_BYTES : 2048);
   sh.off_vec = off; off += (uint32_t)(sh.vec_bias_n + 2 * sh.film_n) * 4;
   off = (off + 15u) & ~15u;
-  sh.off_ln = off; off += e.ln ? 2 * TC_BM * EPI_PARTS * 8 : 0;
+  sh.off_ln = off; off += (uint32_t)ln_bytes;
   sh.off_bar = off; off += 64 * 8;
   p->smem = off + 1024;
   int grid = sh.m_super * sh.n_groups < num_sms ? sh.m_super * sh.n_groups : num_sms;
@@ -860,6 +901,7 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
     const int pairs = sh.m_super * sh.n_groups < num_sms / 2 ? sh.m_super * sh.n_groups : num_sms / 2;
     grid = 2 * pairs;
   }
+  if (sh.split) grid = 2 * (sh.m_super < num_sms / 2 ? sh.m_super : num_sms / 2);   // one cluster per row tile in flight
   if (sh.sticky) {
     if (sh.n_groups > 12) { snprintf(err, errlen, "too many column groups"); delete p; return nullptr; }
     // CTAs per group in proportion to the estimated per-tile epilogue cost (groups with per-position bias rows: 1.35)
@@ -889,9 +931,10 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
     return nullptr;
   }
   const int out_mode = (e.out_raw ? 1 : 0) | (e.out_act ? 2 : 0);
-  p->fn_shared = e.bias ? pick_kernel(e.ln ? 1 : 0, aux_kind, e.film_planned ? 1 : 0, out_mode, sh.pair != 0)
-                        : pick_kernel(-1, -1, -1, -1, sh.pair != 0);   // the specialised variants assume a bias vector
-  p->fn_generic = pick_kernel(-1, -1, -1, -1, sh.pair != 0);
+  const int cluster_mode = sh.split ? 2 : sh.pair ? 1 : 0;
+  p->fn_shared = e.bias ? pick_kernel(e.ln ? 1 : 0, aux_kind, e.film_planned ? 1 : 0, out_mode, cluster_mode)
+                        : pick_kernel(-1, -1, -1, -1, cluster_mode);   // the specialised variants assume a bias vector
+  p->fn_generic = pick_kernel(-1, -1, -1, -1, cluster_mode);
   for (TcKernFn fn : {p->fn_shared, p->fn_generic}) {
     cudaError_t ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (ce != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); delete p; return nullptr; }
@@ -902,9 +945,9 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
 void tc_gemm_plan_destroy(TcGemmPlan* p) { delete p; }
 void tc_gemm_set_trace(TcGemmPlan* p, unsigned long long* buf, int cap) { p->sh.trace = buf; p->sh.trace_cap = cap; }
 void tc_gemm_plan_set_reverse(TcGemmPlan* p, int rev) { p->sh.rev = rev ? 1 : 0; }
-void tc_gemm_plan_set_a_evict_first(TcGemmPlan* p, int on) { p->sh.a_evict_first = (on && p->sh.n_groups == 1) ? 1 : 0; }
+void tc_gemm_plan_set_a_evict_first(TcGemmPlan* p, int on) { p->sh.a_evict_first = (on && p->sh.n_groups == 1 && !p->sh.split) ? 1 : 0; }
 void tc_gemm_plan_config(const TcGemmPlan* p, TcTune* out) {
-  out->bn = p->sh.BN; out->g = p->sh.G; out->resident = p->sh.w_resident; out->pair = p->sh.pair;
+  out->bn = p->sh.BN; out->g = p->sh.G; out->resident = p->sh.w_resident; out->pair = p->sh.split ? 2 : p->sh.pair;
 }
 void tc_gemm_describe(const TcGemmPlan* p, char* out, int n) {
   snprintf(out, n, "pair=%d BN=%d groups=%d m_tiles=%d G=%d stages_a=%d stages_w=%d resident=%d sticky=%d acc_stages=%d grid=%d smem=%zu", p->sh.pair, p->sh.BN, p->sh.n_groups,
@@ -927,7 +970,7 @@ int tc_gemm_launch(const TcGemmPlan* p, const Epilogue& e, cudaStream_t st) {
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
   }
-  if (p->sh.pair) {
+  if (p->sh.pair || p->sh.split) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
     attr[na].val.clusterDim.x = 2;
     attr[na].val.clusterDim.y = 1;

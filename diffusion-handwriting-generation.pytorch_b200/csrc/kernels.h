@@ -72,8 +72,10 @@ void launch_silu_convert(const float* in, T* out, size_t n, cudaStream_t st);
 struct TcGemmPlan;  // opaque: tensor maps + launch geometry, built once at plan time
 // Tile configuration of a plan; -1 = the built-in rule.  bn: tile width (divides N; LayerNorm rows always use N);
 // g: independent accumulators per super-tile (g * bn <= 256); resident: keep W in shared memory for the whole launch
-// (if it fits); pair: cta_group::2 CTA pairs (only with streamed W and g == 1).  Every configuration computes the same
-// bits: the K order of a row's dot product does not depend on it.
+// (if it fits); pair: 1 = cta_group::2 CTA pairs (only with streamed W and g == 1), 2 = column-split LayerNorm (a 2-CTA
+// cluster per row tile, each CTA accumulates half of the row's columns double-buffered, LayerNorm statistics exchanged
+// through distributed shared memory; N = 128, 256 or 384).  Every configuration computes the same bits: the K order of
+// a row's dot product and the grouping of the LayerNorm partial sums do not depend on it.
 struct TcTune { int bn, g, resident, pair; };
 TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W, int K, int N, int taps,
                                 const Epilogue& e, char* err, int errlen, const TcTune* tune = nullptr);

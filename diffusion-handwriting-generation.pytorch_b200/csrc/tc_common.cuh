@@ -125,6 +125,31 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) 
       ::"r"(bar), "r"(rank) : "memory");
 }
 
+// Peer CTA of a 2-CTA cluster: write two floats into its shared memory at the address that `local` has in mine, and
+// wait on one of my mbarriers with cluster-scope acquire (pairs with the peer's mbar_arrive_remote, release.cluster).
+__device__ __forceinline__ void st_shared_remote_f2(uint32_t local, uint32_t rank, float a, float b) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "st.shared::cluster.v2.f32 [ra], {%2, %3};\n\t}"
+      ::"r"(local), "r"(rank), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0, ok = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) break;
+    if (++spins > kSpinLimit) {
+      printf("dhg tcgen05: cluster mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
 // TMA store of a [box] tile from shared to global memory (bulk async group of the issuing thread)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"

@@ -100,7 +100,7 @@ def run(lib, c, repeats=0, allow_unavailable=False):
                                   repeats, ctypes.byref(ms), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     if rc != 0 and allow_unavailable:
         msg = lib.dhg_last_error().decode()
-        assert any(k in msg for k in ("does not fit", "do not fit", "not enough shared memory", "too many column groups",
+        assert any(k in msg for k in ("does not fit", "do not fit", "not enough shared memory", "too many column groups", "does not fit",
                                       "A ring too small")), msg
         return None
     assert rc == 0, lib.dhg_last_error().decode()

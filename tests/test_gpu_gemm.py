@@ -105,6 +105,8 @@ TUNE_CASES = [
     ("conv_skip_256", 19999, 384, 256, 3, dict(period=99, pad_first=1)),
     ("ln_film_respre_384", 20050, 384, 384, 1, dict(period=50, pad_first=1, ln=True, film=1, res_pre=True)),
     ("ln_film_respost_192", 20685, 192, 192, 1, dict(period=197, pad_first=1, ln=True, film=1, res_post=True)),
+    ("ln_film_respre_256_act", 19999, 512, 256, 1, dict(period=99, pad_first=1, ln=True, film=1, res_pre=True, act=True)),
+    ("ln_film_k768_384_act", 20050, 768, 384, 1, dict(period=50, pad_first=1, ln=True, film=1, raw=False, act=True)),
 ]
 
 
@@ -134,8 +136,10 @@ def test_tc_gemm_every_tile_configuration_gives_the_same_bits(built_lib, name, r
             for g in (1, 2, 4):
                 if g > 1 and g * bn > 256:
                     continue
-                for resident, pair in ((1, 0), (0, 0), (0, 1)):
+                for resident, pair in ((1, 0), (0, 0), (0, 1), (1, 2), (0, 2)):   # pair 2: column-split LayerNorm cluster
                     if pair and g != 1:
+                        continue
+                    if pair == 2 and not (kw.get("ln") and N % 128 == 0):
                         continue
                     setopt(bn=-1 if kw.get("ln") else bn, g=g, resident=resident, pair=pair)
                     for t in (c["out_raw"], c["out_act"]):
