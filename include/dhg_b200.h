@@ -120,13 +120,20 @@ int32_t dhg_posterior_step(dhg_ctx* ctx, int32_t step, int32_t mode, const float
 int64_t dhg_last_launch_count(const dhg_ctx* ctx);
 /* Bytes of device memory held by the current plan. */
 int64_t dhg_plan_bytes(const dhg_ctx* ctx);
-/* Engine switches, mainly for tests: key "gemm" = 0 CUDA-core GEMM + row epilogue
- * kernel, 1 tcgen05 GEMM with fused epilogue (bf16 precision only; default 1);
- * "graph" = 0/1 use CUDA graphs in dhg_sample (default 1); with ctx NULL (process-wide): "text_sets" =
- * 1..6 text sides of that many consecutive steps run at once on their own streams (default 4),
- * "autotune" = 0/1 time the GEMM tile configurations at plan time (default 1), "serpentine" = 0/1
- * alternate the row walking direction from kernel to kernel (default 1).  Takes effect at the next
- * dhg_plan. */
+/* Engine switches, mainly for tests and A/B measurements.  Per context (take effect at the next dhg_plan):
+ *   "gemm"  0 CUDA-core GEMM + row epilogue kernel, 1 tcgen05 GEMM with fused epilogue (bf16 only; default 1)
+ *   "attn"  0 CUDA-core attention, 1 tcgen05 attention (bf16 only; default 1)
+ *   "graph" 0/1 one CUDA graph per chain in dhg_sample (default 1)
+ * Process-wide (ctx may be NULL; take effect at the next dhg_plan):
+ *   "text_sets"    1..6 text sides of that many consecutive steps run at once on their own streams (default 2)
+ *   "autotune"     0/1 time the GEMM tile configurations and the attention tile-load order at plan time (default 1)
+ *   "serpentine"   0/1 alternate the row walking direction from kernel to kernel (default 1)
+ *   "l2_hints"     0/1 L2 evict-first hint on streamed GEMM inputs (default 1)
+ *   "tail_fusion"  0/1 chain only: last fc + FiLM + skip + heads as one kernel on per-step folded tables (default 1)
+ *   "head_fusion"  0/1 chain only: enc1.conv_skip(input_dense(x)) straight from x (default 1)
+ *   "w_resident", "specialize", "interleave", "pair", "pdl", "attn_early", "tune_bn", "tune_g", "tune_resident",
+ *   "tune_pair", "tune_rev": kernel-selection overrides used by tests/test_gpu_kernel_variants.py and test_gpu_gemm.py
+ * None of them changes results beyond the documented tolerances; all but the two fusions leave the bits unchanged. */
 int32_t dhg_set_option(dhg_ctx* ctx, const char* key, int32_t value);
 
 /* Test hook: copy a named intermediate activation of the last forward ("h1", "h2c",
