@@ -231,9 +231,12 @@ class DiffusionWriter:
         return out
 
     @torch.no_grad()
-    def sample_host(self, text, style_vector, x0, noise, diffusion_mode="new"):
+    def sample_host(self, text, style_vector, x0, noise, diffusion_mode="new", out=None):
         """Same chain through the HOST-buffer entry point (`dhg_sample_host`): CPU tensors
-        in, CPU tensor out, all copies inside the call."""
+        in, CPU tensor out, all copies inside the call.  The device->host copy lands in a pinned
+        staging buffer owned by the writer (allocating pinned memory per call costs tens of
+        milliseconds every time the caching host allocator runs dry); the result is returned as a
+        fresh tensor, or written into `out` ([B,T,3] fp32 CPU; pinned: no staging copy at all)."""
         text = torch.as_tensor(text).to("cpu", torch.int64).contiguous()
         self._check_tokens(text)
         style = torch.as_tensor(style_vector).to("cpu", torch.float32).contiguous()
@@ -244,11 +247,24 @@ class DiffusionWriter:
         if tuple(x0.shape) != (B, T, 2) or tuple(noise.shape) != (NUM_STEPS, B, T, 2):
             raise ValueError("x0 must be [B,T,2] and noise [60,B,T,2]")
         self._plan(min(B, self.chunk), T, L, style.shape[1])
-        out = torch.empty(B, T, 3, dtype=torch.float32, pin_memory=True)
+        direct = out is not None and out.is_pinned() and out.is_contiguous()
+        if out is not None and (tuple(out.shape) != (B, T, 3) or out.dtype != torch.float32 or out.device.type != "cpu"):
+            raise ValueError("out must be a [B,T,3] fp32 CPU tensor")
+        if direct:
+            stage = out
+        else:
+            stage = getattr(self, "_host_stage", None)
+            if stage is None or tuple(stage.shape) != (B, T, 3):
+                stage = self._host_stage = torch.empty(B, T, 3, dtype=torch.float32, pin_memory=True)
         with torch.cuda.device(self.device):
             _abi.check(self._lib.dhg_sample_host(self._ctx, B, _ptr(x0), _ptr(noise), 0, _ptr(text), _ptr(style),
-                                                 _MODE[diffusion_mode], _ptr(out)))
-        return out
+                                                 _MODE[diffusion_mode], _ptr(stage)))
+        if direct:
+            return out
+        if out is not None:
+            out.copy_(stage)
+            return out
+        return stage.clone()
 
     # -- new_diffusion_step / standard_diffusion_step (utils/nn.py:64-112) -----
     @torch.no_grad()
