@@ -50,6 +50,13 @@ struct Epilogue {
   int out_raw_pitch;
   void* out_act;           // SiLU(value), activation dtype or null
   int out_act_pitch;
+  // dot mode (tcgen05 path, instead of out_raw / out_act): the row is not stored; its 3 dot products with dot_w[0..2]
+  // (fp32 [3, N]) go to dot_out[row * 4 + j] (fp32).  dot_act: the dots are taken of SiLU(value).  Used where the only
+  // reader of the row is a linear map onto 3 channels (the heads behind the last ConvBlock, engine.cu tail fusion).
+  const float* dot_w;
+  float* dot_out;
+  int dot_act;
+  int dot_planned;         // plan-time flag like film_planned: dot_w is supplied at launch
   RowMap map;
 };
 

@@ -49,7 +49,8 @@ static thread_local char g_err[1024] = "";
 static int g_opt_autotune = 1;  // time every GEMM tile configuration at plan time and keep the fastest ("autotune")
 static int g_opt_l2_hints = 1;   // streamed GEMM inputs get L2 evict-first priority ("l2_hints")
 static int g_opt_head_fusion = 1; // chain: enc1.conv_skip(input_dense(x)) computed from x by a K = 6 kernel ("head_fusion")
-static int g_opt_tail_fusion = 1; // chain: last fc + FiLM + skip + heads as one kernel on folded tables ("tail_fusion")
+static int g_opt_tail_fusion = 2; // chain: 1 last fc + FiLM + skip + heads as one kernel on folded tables, 2 also conv2 / conv_skip of the
+                                  // last block in dot mode, so neither a2 nor skip nor d1 exist ("tail_fusion")
 static int g_opt_serpentine = 1; // consumer kernels walk their rows opposite to their producer ("serpentine")
 static int g_opt_text_sets = 2;  // text sides of this many consecutive steps run at once (dhg_set_option "text_sets")
 static int fail(const char* fmt, ...) {
@@ -104,7 +105,8 @@ struct StepCtx {
   bool fuse_next_input;   // this step's head kernel also writes in_raw / in_act of the next step
   int text_set;           // which copy of the text-side buffers this step's cross-attention reads
   bool fuse_head;         // enc1.conv_skip is computed from x (skip_from_x), the head kernel does not write in_raw
-  bool fuse_tail;         // dec1.fc is not launched: the head kernel works on (a2, skip) with the step's folded tables
+  int fuse_tail;          // 1: dec1.fc is not launched, the head kernel works on (a2, skip) with the step's folded tables;
+                          // 2: dec1.conv2 / conv_skip run in dot mode and the head kernel only adds up their 3 dots per point
   int step;               // sampling step index (tail tables)
   HeadParams head;
 };
@@ -127,6 +129,11 @@ struct EpiSpec {
   bool res_post_up = false;
   int res_post_period_lo = 0;
   Act out_raw, out_act;
+  // dot mode (tail fusion level 2): 3 dot products per row instead of the stored row
+  float* dot_out = nullptr;
+  const float* dot_w = nullptr;   // constant [3, N] vectors, or
+  bool dot_w_per_step = false;    //   ctx->tail_A + step * 3 * N at launch
+  bool dot_act = false;
 };
 
 struct Plan {
@@ -157,6 +164,7 @@ struct Plan {
   cudaStream_t text_stream[kMaxTextSets] = {};   // [0] unused: set 0 runs on the caller's stream
   cudaEvent_t ev_fork = nullptr, ev_text[kMaxTextSets] = {};
   Act head_in, in_raw, in_act, tail_a2, tail_skip;
+  float *tail_dot_a2 = nullptr, *tail_dot_skip = nullptr;   // [R0, 4] fp32 each (tail fusion level 2)
   std::vector<TcGemmPlan*> tc_plans;
   std::vector<AttnTcPlan*> attn_plans;
   int attn_impl = 1;
@@ -421,6 +429,7 @@ struct Builder {
   int64_t* nlaunch;
   bool failed = false;
   bool tail_gemm = false;   // the next gemm() is dec1.fc: skipped when the step runs with the fused tail
+  const EpiSpec* tail_alt = nullptr;   // the next gemm() gets a second plan with this epilogue, used when sc.fuse_tail == 2
   bool head_gemm = false;   // the next gemm() is enc1.conv_skip: replaced by skip_from_x when the step runs with the fused head
 
   // Walking direction of the kernel that wrote each activation (P->dir_of: buffer -> 0 first row to last, 1 last to
@@ -569,6 +578,29 @@ struct Builder {
       wrote(e.out_raw, dir); wrote(e.out_act, dir);
       P->tc_plans.push_back(tcp);
     }
+    TcGemmPlan* tcp_alt = nullptr;
+    Epilogue e_alt = e;
+    const EpiSpec* alt = tail_alt;
+    tail_alt = nullptr;
+    const bool alt_w_per_step = alt && alt->dot_w_per_step;
+    if (alt && tcp) {
+      e_alt.out_raw = nullptr; e_alt.out_act = nullptr;
+      e_alt.res_post = nullptr; e_alt.res_post_up = 0;
+      e_alt.dot_out = alt->dot_out; e_alt.dot_act = alt->dot_act ? 1 : 0; e_alt.dot_planned = 1;
+      e_alt.dot_w = alt->dot_w_per_step ? c->tail_A : alt->dot_w;
+      char buf[512];
+      tcp_alt = tc_gemm_plan_create((const bf16*)Ap, A.C, rows, W->w16, K, N, taps, e_alt, buf, sizeof(buf));
+      if (!tcp_alt) { fail("plan: tcgen05 gemm %s (dot mode): %s", wkey.c_str(), buf); failed = true; return; }
+      if (g_opt_autotune) {
+        Epilogue et = e_alt;
+        if (film_off >= 0) { et.gamma = c->cond60 + film_off; et.beta = c->cond60 + film_off + N; et.film_bstride = 0; }
+        tcp_alt = autotune(tcp_alt, (const bf16*)Ap, A.C, rows, W, e_alt, et, wkey + " (dot)");
+        if (!tcp_alt) { failed = true; return; }
+      }
+      tc_gemm_plan_set_reverse(tcp_alt, g_opt_serpentine ? !dir_of(Ap) : 0);
+      tc_gemm_plan_set_a_evict_first(tcp_alt, g_opt_l2_hints);
+      P->tc_plans.push_back(tcp_alt);
+    }
     *nlaunch += tcp ? 1 : 2;
     const bool skippable = tail_gemm, replaceable = head_gemm;
     tail_gemm = false;
@@ -576,6 +608,12 @@ struct Builder {
     dhg_ctx* cc = c;
     ops->push_back([=](cudaStream_t st, const StepCtx& sc) -> int {
       if (skippable && sc.fuse_tail) return 0;
+      if (tcp_alt && sc.fuse_tail == 2) {
+        Epilogue ea = e_alt;
+        if (film_off >= 0) { ea.gamma = sc.cond + film_off; ea.beta = sc.cond + film_off + N; ea.film_bstride = sc.bstride; }
+        if (alt_w_per_step) ea.dot_w = cc->tail_A + (size_t)sc.step * 3 * N;
+        return tc_gemm_launch(tcp_alt, ea, st) ? fail("tcgen05 gemm (dot mode) launch failed: %s", cudaGetErrorString(cudaGetLastError())) : 0;
+      }
       if (replaceable && sc.fuse_head) {   // enc1.conv_skip(input_dense(x)) straight from the current x
         const float* x = sc.head.x_io ? sc.head.x_io : Pl->x_state;
         return launch_skip_from_x<bf16>(x, cc->head_M, cc->head_v, cc->head_b, (bf16*)e.out_raw, Pl->B, Pl->T, N, st)
@@ -708,12 +746,22 @@ struct Builder {
     const int R = P->R[level];
     const RowMap m = map_level(level);
     Act skip = act(R, Cout), a1 = act(R, Cout / 2), a2 = act(R, Cout), out = act(R, Cout);
+    const bool tail = p == "dec1" && P->prec == PREC_BF16 && P->gemm_impl == 1;
+    EpiSpec d0, d2;   // dot-mode twins of conv_skip and conv2 of the last block (tail fusion level 2)
+    if (tail) {
+      if (dev_alloc(P->allocs, (void**)&P->tail_dot_skip, (size_t)R * 4 * sizeof(float), &P->bytes) ||
+          dev_alloc(P->allocs, (void**)&P->tail_dot_a2, (size_t)R * 4 * sizeof(float), &P->bytes)) { failed = true; return Act(); }
+      d0.dot_out = P->tail_dot_skip; d0.dot_w = c->tail_H;
+      d2.film_off = film(p + ".affine2"); d2.dot_out = P->tail_dot_a2; d2.dot_w_per_step = true; d2.dot_act = true;
+    }
     EpiSpec s0; s0.out_raw = skip;
     if (p == "enc1") head_gemm = true;
+    if (tail) tail_alt = &d0;
     gemm(in_raw, p + ".conv_skip", s0, m);
     EpiSpec s1; s1.film_off = film(p + ".affine1"); s1.out_act = a1;
     gemm(in_act, p + ".conv1", s1, m);
     EpiSpec s2; s2.film_off = film(p + ".affine2"); s2.out_act = a2;
+    if (tail) tail_alt = &d2;
     gemm(a1, p + ".conv2", s2, m);
     EpiSpec s3; s3.film_off = film(p + ".affine3"); s3.res_post = skip; s3.out_raw = out;
     if (want_act) { *out_act = act(R, Cout); s3.out_act = *out_act; }
@@ -939,6 +987,10 @@ int build_plan(dhg_ctx* c, Plan* P) {
         hp.next_raw = sc.fuse_head ? nullptr : Pl->in_raw.p;   // nobody reads in_raw when enc1.conv_skip works from x
         hp.next_act = Pl->in_act.p; hp.in_W = c->in_W; hp.in_b = c->in_b;
       }
+      if (sc.fuse_tail == 2) {   // the two dot-mode GEMMs of this step left a2 . tail_A[step] and skip . tail_H per point
+        return launch_heads_from_dots<bf16>(Pl->tail_dot_a2, Pl->tail_dot_skip, c->tail_c + (size_t)sc.step * 3, d1.C, hp, st)
+                   ? fail("head kernel: unsupported channel count %d", d1.C) : 0;
+      }
       if (sc.fuse_tail) {   // eps | pen = a2 . tail_A[step] + skip . tail_H + tail_c[step]  (dhg_finalize)
         const int C = d1.C;
         const float* A = c->tail_A + (size_t)sc.step * 3 * C;
@@ -1029,7 +1081,7 @@ int run_chain(dhg_ctx* c, Plan* P, int mode, bool has_noise, cudaStream_t st) {
     sc.skip_input_dense = i != DHG_NUM_STEPS - 1;   // written by the previous step's head kernel
     sc.fuse_next_input = i != 0;
     sc.text_set = i % n;
-    sc.fuse_tail = g_opt_tail_fusion && P->prec == PREC_BF16 && P->gemm_impl == 1;
+    sc.fuse_tail = (P->prec == PREC_BF16 && P->gemm_impl == 1) ? g_opt_tail_fusion : 0;
     sc.fuse_head = g_opt_head_fusion && P->prec == PREC_BF16 && P->gemm_impl == 1;
     sc.step = i;
     head_for_step(c, P, i, mode, has_noise, false, &sc.head);
@@ -1452,7 +1504,7 @@ int32_t dhg_set_option(dhg_ctx* c, const char* key, int32_t value) {
   if (key && !strcmp(key, "autotune")) { g_opt_autotune = value ? 1 : 0; return 0; }
   if (key && !strcmp(key, "serpentine")) { g_opt_serpentine = value ? 1 : 0; return 0; }
   if (key && !strcmp(key, "l2_hints")) { g_opt_l2_hints = value ? 1 : 0; return 0; }
-  if (key && !strcmp(key, "tail_fusion")) { g_opt_tail_fusion = value ? 1 : 0; return 0; }
+  if (key && !strcmp(key, "tail_fusion")) { g_opt_tail_fusion = value < 0 ? 0 : value > 2 ? 2 : value; return 0; }
   if (key && !strcmp(key, "head_fusion")) { g_opt_head_fusion = value ? 1 : 0; return 0; }
   if (key && !strcmp(key, "tune_rev")) { tc_gemm_set_option(14, value); return 0; }
   if (key && !strcmp(key, "tune_bn")) { tc_gemm_set_option(10, value); return 0; }
@@ -1528,6 +1580,7 @@ int32_t dhg_debug_tc_gemm_ex(int32_t device, const void* a, int32_t lda, int32_t
   e.res_post_period_lo = d->res_post_period_lo;
   e.out_raw = d->out_raw; e.out_raw_pitch = d->out_raw_pitch;
   e.out_act = d->out_act; e.out_act_pitch = d->out_act_pitch;
+  e.dot_w = d->dot_w; e.dot_out = d->dot_out; e.dot_act = d->dot_act; e.dot_planned = d->dot_w ? 1 : 0;
   e.map = RowMap{d->period > 0 ? d->period : (rows > 0 ? rows : 1), d->pad_first, d->nvalid > 0 ? d->nvalid : rows};
   char buf[512];
   TcGemmPlan* p = tc_gemm_plan_create((const bf16*)a, lda, rows, (const bf16*)w, K, N, taps, e, buf, sizeof(buf));

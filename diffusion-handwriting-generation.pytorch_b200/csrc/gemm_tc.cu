@@ -57,6 +57,7 @@ struct TcShape {
   int rev;         // walk the super-tiles from the last row to the first (see tc_gemm_plan_set_reverse)
   int a_evict_first;   // A rows are read once by this launch: give them L2 evict-first priority
   int split;           // column-split LayerNorm: 2-CTA cluster per row tile, rank = column half
+  int dot_n;           // dot mode: 3 * N floats of dot vectors in shared memory (0 = normal stores)
   int stages_a, stages_w;   // A ring / W ring depth (W ring unused when w_resident)
   int w_resident;  // all W tiles of this CTA's column group stay in smem for the whole kernel
   int sticky;      // each CTA works on one column group only
@@ -212,6 +213,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   float* bias_s = reinterpret_cast<float*>(smem + sh.off_vec);
   float* gamma_s = bias_s + sh.vec_bias_n;
   float* betap_s = gamma_s + sh.film_n;
+  float* dot_s = betap_s + sh.film_n;          // [3][N] dot mode
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned tr_n = 0;
@@ -284,6 +286,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       betap_s[n] = fold_bias ? fmaf(__ldg(e.bias + n), g, b) : b;
     }
   }
+  for (int n = threadIdx.x; n < sh.dot_n; n += TC_THREADS) dot_s[n] = __ldg(e.dot_w + n);
   tc_fence_before();
   __syncthreads();
   if (kCLUSTER) cluster_sync_all();   // the peer's barriers are initialised before anything is signalled across the pair
@@ -392,7 +395,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     const bool ln = kLN >= 0 ? (kLN != 0) : (e.ln != 0);
     const int aux_kind = kAUX >= 0 ? kAUX : sh.aux_kind;
     const int film_mode = kFILM >= 0 ? kFILM : (film ? (film_s ? 1 : 2) : 0);
-    const int out_mode = kOUT >= 0 ? kOUT : ((e.out_raw ? 1 : 0) | (e.out_act ? 2 : 0));
+    const int out_mode = kOUT >= 0 ? kOUT : (sh.dot_n ? 4 : ((e.out_raw ? 1 : 0) | (e.out_act ? 2 : 0)));   // 4: dot mode
     const bool has_bias = kLN >= 0 ? true : sh.vec_bias_n > 0;   // every specialised variant has a bias vector (checked at plan time)
     const int ew = warp - 2, q = warp & 3, part = ew >> 2;
     const int nch = sh.BN >> 5;
@@ -555,6 +558,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       };
 
       float v[32];
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f;   // dot mode: my partial dot products of this row
       float mean = 0.f, rstd = 1.f;
       if (ln) {
         // pass 1: x = acc + bias + res_pre -> back to TMEM; shifted sums per STATISTICS GROUP of columns.  A row always
@@ -682,8 +686,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
-        if (out_mode & 1) store_chunk(&map_oraw, n, v, false, false);
-        if (out_mode & 2) store_chunk(&map_oact, n, v, true, (out_mode & 1) != 0);
+        if (out_mode == 4) {   // dot mode: 3 partial dot products of my columns, the row itself is not stored
+          const uint32_t dsa = smem_u32(dot_s) + (uint32_t)n * 4u;
+          const uint32_t nb = (uint32_t)sh.N * 4u;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float x0 = v[i], x1 = v[i + 1], x2 = v[i + 2], x3 = v[i + 3];
+            if (e.dot_act) { x0 = silu_fast(x0); x1 = silu_fast(x1); x2 = silu_fast(x2); x3 = silu_fast(x3); }
+            const float4 w0 = lds128f(dsa + (uint32_t)i * 4u), w1 = lds128f(dsa + nb + (uint32_t)i * 4u),
+                         w2 = lds128f(dsa + 2u * nb + (uint32_t)i * 4u);
+            d0 = fmaf(x0, w0.x, d0); d0 = fmaf(x1, w0.y, d0); d0 = fmaf(x2, w0.z, d0); d0 = fmaf(x3, w0.w, d0);
+            d1 = fmaf(x0, w1.x, d1); d1 = fmaf(x1, w1.y, d1); d1 = fmaf(x2, w1.z, d1); d1 = fmaf(x3, w1.w, d1);
+            d2 = fmaf(x0, w2.x, d2); d2 = fmaf(x1, w2.y, d2); d2 = fmaf(x2, w2.z, d2); d2 = fmaf(x3, w2.w, d2);
+          }
+        } else {
+          if (out_mode & 1) store_chunk(&map_oraw, n, v, false, false);
+          if (out_mode & 2) store_chunk(&map_oact, n, v, true, (out_mode & 1) != 0);
+        }
+      }
+      if (out_mode == 4) {   // add up the column parts of the row through shared memory (tables alternate with the tile parity)
+        float4* ds = reinterpret_cast<float4*>(smem + sh.off_ln) + (size_t)(tile_no & 1) * TC_BM * (EPI_PARTS - 1) + (size_t)r_tile * (EPI_PARTS - 1);
+        if (part > 0) ds[part - 1] = make_float4(d0, d1, d2, 0.f);
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(32 * EPI_PARTS) : "memory");
+        if (part == 0 && in_range) {
+#pragma unroll
+          for (int pp = 0; pp < EPI_PARTS - 1; ++pp) { const float4 o = ds[pp]; d0 += o.x; d1 += o.y; d2 += o.z; }
+          *reinterpret_cast<float4*>(e.dot_out + (size_t)m * 4) = make_float4(d0, d1, d2, 0.f);
+        }
       }
      }
      if (ew == 0) DHG_TR(0x32, it);
@@ -736,6 +765,8 @@ static const TcKernEntry kTcKernels[] = {
     DHG_TC_K(0, AUX_RES_POST, 1, 1),      // fc + skip
     DHG_TC_K(0, AUX_RES_POST_UP, 0, 3),   // skip_conv_k + upsample
     DHG_TC_K(0, AUX_ROWBIAS, 0, 1),       // q / kv / qkv projections with the PE-folded bias table
+    DHG_TC_K(0, AUX_NONE, 0, 4),          // dec1.conv_skip in dot mode (tail fusion)
+    DHG_TC_K(0, AUX_NONE, 1, 4),          // dec1.conv2 in dot mode
     DHG_TC_KL(AUX_NONE, 1, 1),          // text_dense
     DHG_TC_KL(AUX_NONE, 0, 1),          // style_ffn.3
     DHG_TC_KL(AUX_NONE, 1, 2),          // text_ffn.3
@@ -795,6 +826,12 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   if (naux > 1) { snprintf(err, errlen, "at most one of rowbias / res_pre / res_post per GEMM"); return nullptr; }
   if (aux_kind == AUX_ROWBIAS && e.ln) { snprintf(err, errlen, "rowbias with LayerNorm is not supported"); return nullptr; }
   if (e.rowbias16 && (e.rowbias16_cols % 32 || e.rowbias16_cols > N)) { snprintf(err, errlen, "rowbias16_cols must be a multiple of 32 and <= N"); return nullptr; }
+  const bool dot = e.dot_planned || e.dot_w != nullptr;
+  if (dot && (e.ln || e.out_raw || e.out_act || N > 256 || !e.dot_out)) { snprintf(err, errlen, "dot mode needs N <= 256, no LayerNorm, no stored outputs and a dot_out buffer"); return nullptr; }
+  if (dot) {
+    if (tn.bn > 0 && tn.bn != N) { snprintf(err, errlen, "dot mode does not fit a tile width below N"); return nullptr; }
+    BN = N;   // a row's dot products are formed inside one CTA
+  }
   if ((e.res_pre && e.res_pre_pitch % 8) || (e.res_post && e.res_post_pitch % 8) || (e.out_raw && e.out_raw_pitch % 8) ||
       (e.out_act && e.out_act_pitch % 8)) {
     snprintf(err, errlen, "row pitches must be multiples of 8 elements");
@@ -839,9 +876,11 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   sh.a_stage_bytes = (sh.a_tx_bytes + 1023u) & ~1023u;
   sh.w_tile_bytes = (uint32_t)BN * TC_BK * 2;
   // smem carve-up: A ring | W ring or resident W | aux rings | out staging | vectors | LN exchange | barriers
-  const size_t ln_bytes = e.ln ? (size_t)2 * TC_BM * (2 * EPI_PARTS) * 8 : 0;   // [2 tile parities][128 rows][2 * EPI_PARTS groups] {mean, M2}
+  sh.dot_n = dot ? 3 * N : 0;
+  // LayerNorm: [2 tile parities][128 rows][2 * EPI_PARTS groups] {mean, M2}; dot mode: [2][128][EPI_PARTS - 1] float4 partial dots
+  const size_t ln_bytes = e.ln ? (size_t)2 * TC_BM * (2 * EPI_PARTS) * 8 : dot ? (size_t)2 * TC_BM * (EPI_PARTS - 1) * 16 : 0;
   size_t fixed = (aux_kind != AUX_NONE ? (size_t)EPI_WARPS * AUX_RING_BYTES : 0) + (size_t)EPI_WARPS * OUT_STAGE_BYTES +
-                 (size_t)(sh.vec_bias_n + 2 * sh.film_n) * 4 + 16 + ln_bytes + 64 * 8;
+                 (size_t)(sh.vec_bias_n + 2 * sh.film_n + sh.dot_n) * 4 + 16 + ln_bytes + 64 * 8;
   size_t budget = 227 * 1024 - 1024 - fixed;
   sh.out_bufs = OUT_STAGE_BYTES >= 4096 ? 2 : 1;
   if (sh.out_bufs == 2 && 2 * (size_t)(sh.a_stage_bytes + BN * TC_BK * 2) > budget) {   // not even two A + two W stages: give up the second store tile
@@ -858,7 +897,7 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   // W does not fit: pair the CTAs of a cluster (cta_group::2) so that each SM only ingests half of every W tile
   // Measured (profiles/): pairing pays when the MMA / W-stream phase dominates the tile (K*taps >= 512 and a light
   // epilogue, or the single-buffered 384-wide LayerNorm rows); with g_opt_pair == 2 every non-resident GEMM is paired.
-  const int out_mode_plan = (e.out_raw ? 1 : 0) | (e.out_act ? 2 : 0);
+  const int out_mode_plan = dot ? 4 : ((e.out_raw ? 1 : 0) | (e.out_act ? 2 : 0));
   const bool pair_pays = BN == 384 || (taps * K >= 512 && out_mode_plan != 3 && !(e.ln && N <= 192));
   const bool want_pair = split ? false : tn.pair >= 0 ? tn.pair != 0 : (g_opt_pair && (g_opt_pair == 2 || pair_pays));
   sh.pair = (!sh.w_resident && want_pair && G == 1 && sh.umma_n % 16 == 0 &&
@@ -891,7 +930,7 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   sh.off_w = off; off += (uint32_t)w_bytes;
   sh.off_aux = off; off += aux_kind != AUX_NONE ? EPI_WARPS * AUX_RING_BYTES : 0;
   sh.off_out = off; off += EPI_WARPS * (sh.out_bufs == 2 ? OUT_STAGE_BYTES : 2048);
-  sh.off_vec = off; off += (uint32_t)(sh.vec_bias_n + 2 * sh.film_n) * 4;
+  sh.off_vec = off; off += (uint32_t)(sh.vec_bias_n + 2 * sh.film_n + sh.dot_n) * 4;
   off = (off + 15u) & ~15u;
   sh.off_ln = off; off += (uint32_t)ln_bytes;
   sh.off_bar = off; off += 64 * 8;
@@ -930,7 +969,7 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
     delete p;
     return nullptr;
   }
-  const int out_mode = (e.out_raw ? 1 : 0) | (e.out_act ? 2 : 0);
+  const int out_mode = dot ? 4 : ((e.out_raw ? 1 : 0) | (e.out_act ? 2 : 0));
   const int cluster_mode = sh.split ? 2 : sh.pair ? 1 : 0;
   p->fn_shared = e.bias ? pick_kernel(e.ln ? 1 : 0, aux_kind, e.film_planned ? 1 : 0, out_mode, cluster_mode)
                         : pick_kernel(-1, -1, -1, -1, cluster_mode);   // the specialised variants assume a bias vector

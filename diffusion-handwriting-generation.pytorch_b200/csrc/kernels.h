@@ -53,6 +53,8 @@ template <typename T>
 void launch_input_dense(const float* x, const float* W, const float* bias, T* out_raw, T* out_act,
                         int B, int Tn, int C, cudaStream_t st);
 template <typename T>
+int launch_heads_from_dots(const float* dot_a, const float* dot_b, const float* cst, int C, const HeadParams& p, cudaStream_t st);
+template <typename T>
 int launch_skip_from_x(const float* x, const float* M, const float* v, const float* bsk, T* out, int B, int Tn, int C, cudaStream_t st);
 template <typename T>
 int launch_heads_update(const T* h, int C, const float* Wo, const float* bo, const float* Wp,

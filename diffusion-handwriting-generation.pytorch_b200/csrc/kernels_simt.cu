@@ -654,6 +654,73 @@ __global__ void __launch_bounds__(256, DHG_HEADS_MINB) heads_update_kernel(const
     }
   }
 }
+// Tail fusion, level 2: the three head values of a point are already sitting in two [rows, 4] fp32 arrays (dot mode of
+// the last ConvBlock's conv2 and conv_skip GEMMs): eps | pen = dot_a[row] + dot_b[row] + c.  What is left is the
+// posterior update and input_dense of the next step: 16 lanes per point, 8 channels each, like heads_update_kernel.
+template <typename T_>
+__global__ void __launch_bounds__(256) heads_from_dots_kernel(const float4* __restrict__ dot_a, const float4* __restrict__ dot_b,
+                                                              const float* __restrict__ cst /*[3]*/, int C, HeadParams p) {
+  const int lane = threadIdx.x & 31, sub = lane & 15, grp = lane >> 4;
+  const int c0 = sub * 8;
+  float iw0[8], iw1[8], ib[8];
+  const bool next_in = p.next_raw != nullptr || p.next_act != nullptr;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    iw0[k] = next_in ? p.in_W[(c0 + k) * 2] : 0.f;
+    iw1[k] = next_in ? p.in_W[(c0 + k) * 2 + 1] : 0.f;
+    ib[k] = next_in ? p.in_b[c0 + k] : 0.f;
+  }
+  const float b0 = cst[0], b1 = cst[1], bpv = cst[2];
+  const uint32_t npts = (uint32_t)p.B * (uint32_t)p.T, T = (uint32_t)p.T;
+  const uint32_t stride = ((gridDim.x * blockDim.x) >> 5) * 2;
+  for (uint32_t i = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 2 + grp; i < npts; i += stride) {
+    const uint32_t b = i / T;
+    const size_t row = (size_t)i + b + 1;
+    const float4 da = dot_a[row], db = dot_b[row];
+    const float e0 = da.x + db.x + b0, e1 = da.y + db.y + b1, pl = da.z + db.z + bpv;
+    float y0 = 0.f, y1 = 0.f;
+    if (p.x_io) {
+      const float2 xx = *reinterpret_cast<const float2*>(p.x_io + (size_t)i * 2);
+      const float2 zz = p.noise ? *reinterpret_cast<const float2*>(p.noise + (size_t)i * 2) : make_float2(0.f, 0.f);
+      if (p.mode == 0) {
+        y0 = (xx.x - p.c_eps * e0) / p.c_div + zz.x * p.c_noise;
+        y1 = (xx.y - p.c_eps * e1) / p.c_div + zz.y * p.c_noise;
+      } else {
+        y0 = p.c_div * (xx.x - p.c_eps * e0 / p.c_eps2) + p.c_noise * zz.x;
+        y1 = p.c_div * (xx.y - p.c_eps * e1 / p.c_eps2) + p.c_noise * zz.y;
+      }
+    }
+    if (sub == 0) {
+      if (p.eps_out) { p.eps_out[(size_t)i * 2] = e0; p.eps_out[(size_t)i * 2 + 1] = e1; }
+      if (p.pen_out) p.pen_out[(size_t)i * p.pen_stride + p.pen_offset] = 1.f / (1.f + expf(-pl));
+      if (p.x_io) {
+        float* xo = p.x_out ? p.x_out : p.x_io;
+        xo[(size_t)i * p.x_out_stride] = y0;
+        xo[(size_t)i * p.x_out_stride + 1] = y1;
+      }
+    }
+    if (next_in) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaf(y1, iw1[k], fmaf(y0, iw0[k], ib[k]));
+      if (p.next_raw) store8<T_>(reinterpret_cast<T_*>(p.next_raw) + row * C + c0, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = silu_out<T_>(v[k]);
+      if (p.next_act) store8<T_>(reinterpret_cast<T_*>(p.next_act) + row * C + c0, v);
+    }
+  }
+}
+template <typename T>
+int launch_heads_from_dots(const float* dot_a, const float* dot_b, const float* cst, int C, const HeadParams& p, cudaStream_t st) {
+  if (C != 128) return 1;
+  const size_t nw = ((size_t)p.B * p.T + 1) / 2;
+  size_t blocks = (nw + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  heads_from_dots_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(dot_a), reinterpret_cast<const float4*>(dot_b), cst, C, p);
+  return 0;
+}
+template int launch_heads_from_dots<bf16>(const float*, const float*, const float*, int, const HeadParams&, cudaStream_t);
+
 template <typename T>
 int launch_heads_update(const T* h, int C, const float* Wo, const float* bo, const float* Wp,
                         const float* bp, const HeadParams& p, cudaStream_t st) {

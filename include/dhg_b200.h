@@ -171,6 +171,10 @@ typedef struct dhg_debug_epilogue {
   void* out_act;           /* bf16 SiLU(value) */
   int32_t out_act_pitch;
   int32_t period, pad_first, nvalid;
+  /* dot mode (instead of out_raw / out_act): dot_out[row * 4 + j] = <value or SiLU(value), dot_w[j, :]>, j < 3 */
+  const float* dot_w;      /* fp32 [3, N] or NULL */
+  float* dot_out;          /* fp32 [rows, 4] */
+  int32_t dot_act;
 } dhg_debug_epilogue;
 int32_t dhg_debug_tc_gemm_ex(int32_t device, const void* dev_a_bf16, int32_t lda, int32_t rows,
                              const void* dev_w_bf16, int32_t K, int32_t N, int32_t taps,

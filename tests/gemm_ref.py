@@ -9,8 +9,9 @@ from dhg_b200 import _abi
 
 
 def make_case(rows, K, N, taps, *, period=None, pad_first=0, bias=True, rowbias=False, res_pre=False, ln=False,
-              film=0, res_post=False, up=False, raw=True, act=False, seed=0, device="cuda"):
-    """film: 0 none, 1 one vector for the batch (bstride 0), 2 per-sample vectors."""
+              film=0, res_post=False, up=False, raw=True, act=False, dot=0, seed=0, device="cuda"):
+    """film: 0 none, 1 one vector for the batch (bstride 0), 2 per-sample vectors.
+    dot: 0 normal stores; 1 / 2 dot mode on the value / on SiLU(value) (no stored outputs)."""
     g = torch.Generator().manual_seed(seed)
     period = period or rows
     nb = (rows + period - 1) // period
@@ -46,8 +47,11 @@ def make_case(rows, K, N, taps, *, period=None, pad_first=0, bias=True, rowbias=
         c["res_post"] = torch.randn(rows, N, generator=g).bfloat16().to(device)
     else:
         c["period_lo"], c["res_post"] = 0, None
-    c["out_raw"] = torch.full((rows, N), float("nan"), dtype=torch.bfloat16, device=device) if raw else None
-    c["out_act"] = torch.full((rows, N), float("nan"), dtype=torch.bfloat16, device=device) if act else None
+    c["out_raw"] = torch.full((rows, N), float("nan"), dtype=torch.bfloat16, device=device) if raw and not dot else None
+    c["out_act"] = torch.full((rows, N), float("nan"), dtype=torch.bfloat16, device=device) if act and not dot else None
+    c["dot_act"] = 1 if dot == 2 else 0
+    c["dot_w"] = (torch.randn(3, N, generator=g) / N ** 0.5).to(device) if dot else None
+    c["dot_out"] = torch.full((rows, 4), float("nan"), device=device) if dot else None
     return c
 
 
@@ -94,7 +98,7 @@ def run(lib, c, repeats=0, allow_unavailable=False):
     e = _abi.DebugEpilogue(
         p(c["bias"]), p(c["rowbias"]), c["rowbias_cols"], p(c["res_pre"]), N, int(c["ln"]), p(c["gamma"]), p(c["beta"]), c["bstride"],
         p(c["res_post"]), N, int(c["up"]), c["period_lo"], p(c["out_raw"]), N, p(c["out_act"]), N,
-        c["period"], c["pad_first"], c["nvalid"])
+        c["period"], c["pad_first"], c["nvalid"], p(c.get("dot_w")), p(c.get("dot_out")), int(c.get("dot_act", 0)))
     ms = ctypes.c_float(0)
     rc = lib.dhg_debug_tc_gemm_ex(0, p(c["a"]), c["K"], c["rows"], p(c["w"]), c["K"], N, c["taps"], ctypes.byref(e),
                                   repeats, ctypes.byref(ms), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))

@@ -92,6 +92,31 @@ def test_tc_gemm_fused_epilogue(built_lib, name, rows, K, N, taps, kw):
         assert err < 2e-2 * scale, (name, "act", err)
 
 
+DOT_CASES = [
+    ("dot_conv_skip", 3000, 192, 128, 3, dict(period=393, pad_first=1, dot=1)),
+    ("dot_conv2_film_act", 3000, 64, 128, 3, dict(period=393, pad_first=1, film=1, dot=2)),
+    ("dot_many_tiles", 40000, 64, 128, 3, dict(period=393, pad_first=1, film=1, dot=2)),
+    ("dot_n256", 2000, 128, 256, 1, dict(period=99, pad_first=1, dot=1)),
+]
+
+
+@pytest.mark.parametrize("name,rows,K,N,taps,kw", DOT_CASES, ids=[c[0] for c in DOT_CASES])
+def test_tc_gemm_dot_mode(built_lib, name, rows, K, N, taps, kw):
+    """Dot mode (engine.cu tail fusion): the row is not stored, only its 3 dot products with fp32 vectors."""
+    import gemm_ref
+
+    c = gemm_ref.make_case(rows, K, N, taps, seed=len(name) + rows, **kw)
+    gemm_ref.run(built_lib, c)
+    x = gemm_ref.reference(c)
+    if c["dot_act"]:
+        x = torch.nn.functional.silu(x)
+    ref = x @ c["dot_w"].T
+    got = c["dot_out"][:, :3]
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    assert err < 1e-2 * max(1.0, ref.abs().max().item()), (name, err)   # bf16 inputs, fp32 accumulation, tanh.approx SiLU
+
+
 # The plan-time autotuner (engine.cu Builder::autotune) may pick any of these for a GEMM of the denoiser, so every one
 # must compute the same bits as the built-in rule: tile width x interleaved accumulators x {resident W, streamed W,
 # streamed W + CTA pairs}.
