@@ -134,6 +134,7 @@ struct EpiSpec {
   const float* dot_w = nullptr;   // constant [3, N] vectors, or
   bool dot_w_per_step = false;    //   ctx->tail_A + step * 3 * N at launch
   bool dot_act = false;
+  std::string alt_wkey;           // the dot-mode twin uses this packed weight instead (a conv folded onto its 3 readers)
 };
 
 struct Plan {
@@ -199,6 +200,7 @@ struct dhg_ctx {
   float* cond60 = nullptr;  // [60, tot]
   // tail fusion (see finalize): eps|pen = a2 . tail_A[step] + skip . tail_H + tail_c[step]
   float *tail_A = nullptr, *tail_c = nullptr, *tail_H = nullptr;   // [60,3,C] | [60,3] | [3,C]
+  float* tail_pick = nullptr;   // [3, 32] one-hot rows: dot mode reading columns 0..2 of the folded conv_skip
   // head fusion: enc1.conv_skip(input_dense(x)) = sum_tau (x[t+tau] . head_M[tau] + head_v[tau]) + head_b
   float *head_M = nullptr, *head_v = nullptr, *head_b = nullptr;   // [3,2,C] | [3,C] | [C]
   float* emb = nullptr;     // [73, d]
@@ -583,18 +585,27 @@ struct Builder {
     const EpiSpec* alt = tail_alt;
     tail_alt = nullptr;
     const bool alt_w_per_step = alt && alt->dot_w_per_step;
+    int Na = N;
     if (alt && tcp) {
       e_alt.out_raw = nullptr; e_alt.out_act = nullptr;
       e_alt.res_post = nullptr; e_alt.res_post_up = 0;
       e_alt.dot_out = alt->dot_out; e_alt.dot_act = alt->dot_act ? 1 : 0; e_alt.dot_planned = 1;
       e_alt.dot_w = alt->dot_w_per_step ? c->tail_A : alt->dot_w;
+      const Lin* Wa = W;
+      if (!alt->alt_wkey.empty()) {
+        auto ia = c->lins.find(alt->alt_wkey);
+        if (ia == c->lins.end() || ia->second.K != K || ia->second.taps != taps) { fail("plan: bad dot-mode weight %s", alt->alt_wkey.c_str()); failed = true; return; }
+        Wa = &ia->second;
+        e_alt.bias = Wa->bias;
+      }
+      Na = Wa->N;
       char buf[512];
-      tcp_alt = tc_gemm_plan_create((const bf16*)Ap, A.C, rows, W->w16, K, N, taps, e_alt, buf, sizeof(buf));
+      tcp_alt = tc_gemm_plan_create((const bf16*)Ap, A.C, rows, Wa->w16, K, Na, taps, e_alt, buf, sizeof(buf));
       if (!tcp_alt) { fail("plan: tcgen05 gemm %s (dot mode): %s", wkey.c_str(), buf); failed = true; return; }
       if (g_opt_autotune) {
         Epilogue et = e_alt;
-        if (film_off >= 0) { et.gamma = c->cond60 + film_off; et.beta = c->cond60 + film_off + N; et.film_bstride = 0; }
-        tcp_alt = autotune(tcp_alt, (const bf16*)Ap, A.C, rows, W, e_alt, et, wkey + " (dot)");
+        if (film_off >= 0) { et.gamma = c->cond60 + film_off; et.beta = c->cond60 + film_off + Na; et.film_bstride = 0; }
+        tcp_alt = autotune(tcp_alt, (const bf16*)Ap, A.C, rows, Wa, e_alt, et, wkey + " (dot)");
         if (!tcp_alt) { failed = true; return; }
       }
       tc_gemm_plan_set_reverse(tcp_alt, g_opt_serpentine ? !dir_of(Ap) : 0);
@@ -610,8 +621,8 @@ struct Builder {
       if (skippable && sc.fuse_tail) return 0;
       if (tcp_alt && sc.fuse_tail == 2) {
         Epilogue ea = e_alt;
-        if (film_off >= 0) { ea.gamma = sc.cond + film_off; ea.beta = sc.cond + film_off + N; ea.film_bstride = sc.bstride; }
-        if (alt_w_per_step) ea.dot_w = cc->tail_A + (size_t)sc.step * 3 * N;
+        if (film_off >= 0) { ea.gamma = sc.cond + film_off; ea.beta = sc.cond + film_off + Na; ea.film_bstride = sc.bstride; }
+        if (alt_w_per_step) ea.dot_w = cc->tail_A + (size_t)sc.step * 3 * Na;
         return tc_gemm_launch(tcp_alt, ea, st) ? fail("tcgen05 gemm (dot mode) launch failed: %s", cudaGetErrorString(cudaGetLastError())) : 0;
       }
       if (replaceable && sc.fuse_head) {   // enc1.conv_skip(input_dense(x)) straight from the current x
@@ -751,7 +762,9 @@ struct Builder {
     if (tail) {
       if (dev_alloc(P->allocs, (void**)&P->tail_dot_skip, (size_t)R * 4 * sizeof(float), &P->bytes) ||
           dev_alloc(P->allocs, (void**)&P->tail_dot_a2, (size_t)R * 4 * sizeof(float), &P->bytes)) { failed = true; return Act(); }
-      d0.dot_out = P->tail_dot_skip; d0.dot_w = c->tail_H;
+      // conv_skip is only read through H (3 x C): fold it, W'[tau] = H . W_skip[tau] (3 of 32 output columns, K unchanged);
+      // the 'dot vectors' just pick those 3 columns
+      d0.dot_out = P->tail_dot_skip; d0.dot_w = c->tail_pick; d0.alt_wkey = "dec1.conv_skip.heads";
       d2.film_off = film(p + ".affine2"); d2.dot_out = P->tail_dot_a2; d2.dot_w_per_step = true; d2.dot_act = true;
     }
     EpiSpec s0; s0.out_raw = skip;
@@ -1299,6 +1312,40 @@ int32_t dhg_finalize(dhg_ctx* c) {
       }
     }
     if (dev_upload(c->allocs, &c->tail_A, A) || dev_upload(c->allocs, &c->tail_c, cc) || dev_upload(c->allocs, &c->tail_H, H)) return 1;
+    // dec1.conv_skip folded onto the heads: W'[tau][j][k] = sum_n H[j][n] W_skip[tau][k][n], b'[j] = sum_n H[j][n] b_skip[n]
+    // (j < 3; padded to 32 output columns, the kernel's narrowest tile)
+    const Lin& sk = c->lins.at("dec1.conv_skip");
+    Lin F;
+    F.taps = sk.taps; F.K = sk.K; F.N = 32;
+    F.h_w.assign((size_t)F.taps * F.K * F.N, 0.f);
+    F.h_b.assign(F.N, 0.f);
+    std::vector<float> wr(F.h_w.size());
+    std::vector<bf16> w16(F.h_w.size());
+    for (int j = 0; j < 3; ++j) {
+      double bj = 0.0;
+      for (int n = 0; n < C; ++n) bj += (double)H[(size_t)j * C + n] * sk.h_b[n];
+      F.h_b[j] = (float)bj;
+      for (int t = 0; t < F.taps; ++t)
+        for (int k = 0; k < F.K; ++k) {
+          double a = 0.0;
+          for (int n = 0; n < C; ++n) a += (double)H[(size_t)j * C + n] * sk.h_w[((size_t)t * sk.K + k) * sk.N + n];
+          F.h_w[((size_t)t * F.K + k) * F.N + j] = (float)a;
+        }
+    }
+    for (int t = 0; t < F.taps; ++t)
+      for (int k = 0; k < F.K; ++k)
+        for (int n = 0; n < F.N; ++n) {
+          const bf16 hb = __float2bfloat16_rn(F.h_w[((size_t)t * F.K + k) * F.N + n]);
+          wr[((size_t)t * F.K + k) * F.N + n] = __bfloat162float(hb);
+          w16[((size_t)t * F.N + n) * F.K + k] = hb;
+        }
+    if (dev_upload(c->allocs, &F.w32, F.h_w) || dev_upload(c->allocs, &F.w32r, wr) || dev_upload(c->allocs, &F.bias, F.h_b)) return 1;
+    if (dev_alloc(c->allocs, (void**)&F.w16, w16.size() * sizeof(bf16))) return 1;
+    CUDA_OK(cudaMemcpy(F.w16, w16.data(), w16.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+    c->lins["dec1.conv_skip.heads"] = std::move(F);
+    std::vector<float> pick((size_t)3 * 32, 0.f);
+    for (int j = 0; j < 3; ++j) pick[(size_t)j * 32 + j] = 1.f;
+    if (dev_upload(c->allocs, &c->tail_pick, pick)) return 1;
   }
   // Head fusion tables (kernels_simt.cu skip_from_x_kernel)
   {

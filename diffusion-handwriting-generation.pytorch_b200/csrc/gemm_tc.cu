@@ -818,6 +818,12 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
       BN = tn.bn;
     }
   }
+  const bool dot = e.dot_planned || e.dot_w != nullptr;
+  if (dot && (e.ln || e.out_raw || e.out_act || N > 256 || !e.dot_out)) { snprintf(err, errlen, "dot mode needs N <= 256, no LayerNorm, no stored outputs and a dot_out buffer"); return nullptr; }
+  if (dot) {
+    if (tn.bn > 0 && tn.bn != N) { snprintf(err, errlen, "dot mode does not fit a tile width below N"); return nullptr; }
+    BN = N;   // a row's dot products are formed inside one CTA
+  }
   if (BN == 0 || BN % 32) { snprintf(err, errlen, "no tile width for N=%d", N); return nullptr; }
   int aux_kind = AUX_NONE, naux = 0;
   if (e.rowbias16) { aux_kind = AUX_ROWBIAS; ++naux; }
@@ -826,12 +832,6 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   if (naux > 1) { snprintf(err, errlen, "at most one of rowbias / res_pre / res_post per GEMM"); return nullptr; }
   if (aux_kind == AUX_ROWBIAS && e.ln) { snprintf(err, errlen, "rowbias with LayerNorm is not supported"); return nullptr; }
   if (e.rowbias16 && (e.rowbias16_cols % 32 || e.rowbias16_cols > N)) { snprintf(err, errlen, "rowbias16_cols must be a multiple of 32 and <= N"); return nullptr; }
-  const bool dot = e.dot_planned || e.dot_w != nullptr;
-  if (dot && (e.ln || e.out_raw || e.out_act || N > 256 || !e.dot_out)) { snprintf(err, errlen, "dot mode needs N <= 256, no LayerNorm, no stored outputs and a dot_out buffer"); return nullptr; }
-  if (dot) {
-    if (tn.bn > 0 && tn.bn != N) { snprintf(err, errlen, "dot mode does not fit a tile width below N"); return nullptr; }
-    BN = N;   // a row's dot products are formed inside one CTA
-  }
   if ((e.res_pre && e.res_pre_pitch % 8) || (e.res_post && e.res_post_pitch % 8) || (e.out_raw && e.out_raw_pitch % 8) ||
       (e.out_act && e.out_act_pitch % 8)) {
     snprintf(err, errlen, "row pitches must be multiples of 8 elements");

@@ -97,6 +97,7 @@ DOT_CASES = [
     ("dot_conv2_film_act", 3000, 64, 128, 3, dict(period=393, pad_first=1, film=1, dot=2)),
     ("dot_many_tiles", 40000, 64, 128, 3, dict(period=393, pad_first=1, film=1, dot=2)),
     ("dot_n256", 2000, 128, 256, 1, dict(period=99, pad_first=1, dot=1)),
+    ("dot_n32_folded_conv", 40000, 192, 32, 3, dict(period=393, pad_first=1, dot=1)),
 ]
 
 
