@@ -49,7 +49,7 @@ static thread_local char g_err[1024] = "";
 static int g_opt_autotune = 1;  // time every GEMM tile configuration at plan time and keep the fastest ("autotune")
 static int g_opt_l2_hints = 1;   // streamed GEMM inputs get L2 evict-first priority ("l2_hints")
 static int g_opt_head_fusion = 1; // chain: enc1.conv_skip(input_dense(x)) computed from x by a K = 6 kernel ("head_fusion")
-static int g_opt_tail_fusion = 2; // chain: 1 last fc + FiLM + skip + heads as one kernel on folded tables, 2 also conv2 / conv_skip of the
+static int g_opt_tail_fusion = 3; // chain: 1 last fc + FiLM + skip + heads as one kernel on folded tables, 2 also conv2 / conv_skip of the
                                   // last block in dot mode, so neither a2 nor skip nor d1 exist ("tail_fusion")
 static int g_opt_serpentine = 1; // consumer kernels walk their rows opposite to their producer ("serpentine")
 static int g_opt_text_sets = 2;  // text sides of this many consecutive steps run at once (dhg_set_option "text_sets")
@@ -764,7 +764,9 @@ struct Builder {
           dev_alloc(P->allocs, (void**)&P->tail_dot_a2, (size_t)R * 4 * sizeof(float), &P->bytes)) { failed = true; return Act(); }
       // conv_skip is only read through H (3 x C): fold it, W'[tau] = H . W_skip[tau] (3 of 32 output columns, K unchanged);
       // the 'dot vectors' just pick those 3 columns
-      d0.dot_out = P->tail_dot_skip; d0.dot_w = c->tail_pick; d0.alt_wkey = "dec1.conv_skip.heads";
+      d0.dot_out = P->tail_dot_skip;
+      if (g_opt_tail_fusion >= 3) { d0.dot_w = c->tail_pick; d0.alt_wkey = "dec1.conv_skip.heads"; }
+      else d0.dot_w = c->tail_H;
       d2.film_off = film(p + ".affine2"); d2.dot_out = P->tail_dot_a2; d2.dot_w_per_step = true; d2.dot_act = true;
     }
     EpiSpec s0; s0.out_raw = skip;
@@ -1094,7 +1096,7 @@ int run_chain(dhg_ctx* c, Plan* P, int mode, bool has_noise, cudaStream_t st) {
     sc.skip_input_dense = i != DHG_NUM_STEPS - 1;   // written by the previous step's head kernel
     sc.fuse_next_input = i != 0;
     sc.text_set = i % n;
-    sc.fuse_tail = (P->prec == PREC_BF16 && P->gemm_impl == 1) ? g_opt_tail_fusion : 0;
+    sc.fuse_tail = (P->prec == PREC_BF16 && P->gemm_impl == 1) ? (g_opt_tail_fusion > 2 ? 2 : g_opt_tail_fusion) : 0;
     sc.fuse_head = g_opt_head_fusion && P->prec == PREC_BF16 && P->gemm_impl == 1;
     sc.step = i;
     head_for_step(c, P, i, mode, has_noise, false, &sc.head);
@@ -1332,6 +1334,14 @@ int32_t dhg_finalize(dhg_ctx* c) {
           F.h_w[((size_t)t * F.K + k) * F.N + j] = (float)a;
         }
     }
+    // the folded weights carry the head values directly, so their bf16 rounding would show up in eps / pen: columns
+    // j + 3 hold the rounding residual of column j (the tile has 29 spare columns) and the dot vectors add both
+    for (int t = 0; t < F.taps; ++t)
+      for (int k = 0; k < F.K; ++k)
+        for (int j = 0; j < 3; ++j) {
+          const float a = F.h_w[((size_t)t * F.K + k) * F.N + j];
+          F.h_w[((size_t)t * F.K + k) * F.N + j + 3] = a - __bfloat162float(__float2bfloat16_rn(a));
+        }
     for (int t = 0; t < F.taps; ++t)
       for (int k = 0; k < F.K; ++k)
         for (int n = 0; n < F.N; ++n) {
@@ -1344,7 +1354,7 @@ int32_t dhg_finalize(dhg_ctx* c) {
     CUDA_OK(cudaMemcpy(F.w16, w16.data(), w16.size() * sizeof(bf16), cudaMemcpyHostToDevice));
     c->lins["dec1.conv_skip.heads"] = std::move(F);
     std::vector<float> pick((size_t)3 * 32, 0.f);
-    for (int j = 0; j < 3; ++j) pick[(size_t)j * 32 + j] = 1.f;
+    for (int j = 0; j < 3; ++j) { pick[(size_t)j * 32 + j] = 1.f; pick[(size_t)j * 32 + j + 3] = 1.f; }
     if (dev_upload(c->allocs, &c->tail_pick, pick)) return 1;
   }
   // Head fusion tables (kernels_simt.cu skip_from_x_kernel)
@@ -1551,7 +1561,7 @@ int32_t dhg_set_option(dhg_ctx* c, const char* key, int32_t value) {
   if (key && !strcmp(key, "autotune")) { g_opt_autotune = value ? 1 : 0; return 0; }
   if (key && !strcmp(key, "serpentine")) { g_opt_serpentine = value ? 1 : 0; return 0; }
   if (key && !strcmp(key, "l2_hints")) { g_opt_l2_hints = value ? 1 : 0; return 0; }
-  if (key && !strcmp(key, "tail_fusion")) { g_opt_tail_fusion = value < 0 ? 0 : value > 2 ? 2 : value; return 0; }
+  if (key && !strcmp(key, "tail_fusion")) { g_opt_tail_fusion = value < 0 ? 0 : value > 3 ? 3 : value; return 0; }
   if (key && !strcmp(key, "head_fusion")) { g_opt_head_fusion = value ? 1 : 0; return 0; }
   if (key && !strcmp(key, "tune_rev")) { tc_gemm_set_option(14, value); return 0; }
   if (key && !strcmp(key, "tune_bn")) { tc_gemm_set_option(10, value); return 0; }

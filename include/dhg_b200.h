@@ -129,7 +129,9 @@ int64_t dhg_plan_bytes(const dhg_ctx* ctx);
  *   "autotune"     0/1 time the GEMM tile configurations and the attention tile-load order at plan time (default 1)
  *   "serpentine"   0/1 alternate the row walking direction from kernel to kernel (default 1)
  *   "l2_hints"     0/1 L2 evict-first hint on streamed GEMM inputs (default 1)
- *   "tail_fusion"  0/1 chain only: last fc + FiLM + skip + heads as one kernel on per-step folded tables (default 1)
+ *   "tail_fusion"  0..3 chain only: 1 last fc + FiLM + skip + heads as one kernel on per-step folded tables, 2 also the
+ *                  last block's conv2 / conv_skip in dot mode (no a2, skip, d1), 3 conv_skip folded onto the 3 head
+ *                  channels (default 3)
  *   "head_fusion"  0/1 chain only: enc1.conv_skip(input_dense(x)) straight from x (default 1)
  *   "w_resident", "specialize", "interleave", "pair", "pdl", "attn_early", "tune_bn", "tune_g", "tune_resident",
  *   "tune_pair", "tune_rev": kernel-selection overrides used by tests/test_gpu_kernel_variants.py and test_gpu_gemm.py
