@@ -673,15 +673,31 @@ __global__ void __launch_bounds__(256) heads_from_dots_kernel(const float4* __re
   const float b0 = cst[0], b1 = cst[1], bpv = cst[2];
   const uint32_t npts = (uint32_t)p.B * (uint32_t)p.T, T = (uint32_t)p.T;
   const uint32_t stride = ((gridDim.x * blockDim.x) >> 5) * 2;
-  for (uint32_t i = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 2 + grp; i < npts; i += stride) {
-    const uint32_t b = i / T;
+  const uint32_t stride_b = stride / T, stride_t = stride - stride_b * T;
+  // the inputs of the NEXT point are requested before the current one is worked on (the kernel is a latency chain
+  // otherwise); (sample, position) advance incrementally, one division per thread
+  uint32_t i = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 2 + grp;
+  uint32_t b = i / T, t = i - b * T;
+  float4 da_n = make_float4(0.f, 0.f, 0.f, 0.f), db_n = da_n;
+  float2 xx_n = make_float2(0.f, 0.f), zz_n = xx_n;
+  auto fetch = [&](uint32_t ii, uint32_t bb) {
+    const size_t r = (size_t)ii + bb + 1;
+    da_n = dot_a[r]; db_n = dot_b[r];
+    if (p.x_io) xx_n = *reinterpret_cast<const float2*>(p.x_io + (size_t)ii * 2);
+    if (p.noise) zz_n = *reinterpret_cast<const float2*>(p.noise + (size_t)ii * 2);
+  };
+  if (i < npts) fetch(i, b);
+  for (; i < npts;) {
     const size_t row = (size_t)i + b + 1;
-    const float4 da = dot_a[row], db = dot_b[row];
+    const float4 da = da_n, db = db_n;
+    const float2 xx = xx_n, zz = zz_n;
+    const uint32_t i_cur = i;
+    i += stride; b += stride_b; t += stride_t;
+    if (t >= T) { t -= T; ++b; }
+    if (i < npts) fetch(i, b);
     const float e0 = da.x + db.x + b0, e1 = da.y + db.y + b1, pl = da.z + db.z + bpv;
     float y0 = 0.f, y1 = 0.f;
     if (p.x_io) {
-      const float2 xx = *reinterpret_cast<const float2*>(p.x_io + (size_t)i * 2);
-      const float2 zz = p.noise ? *reinterpret_cast<const float2*>(p.noise + (size_t)i * 2) : make_float2(0.f, 0.f);
       if (p.mode == 0) {
         y0 = (xx.x - p.c_eps * e0) / p.c_div + zz.x * p.c_noise;
         y1 = (xx.y - p.c_eps * e1) / p.c_div + zz.y * p.c_noise;
@@ -691,12 +707,12 @@ __global__ void __launch_bounds__(256) heads_from_dots_kernel(const float4* __re
       }
     }
     if (sub == 0) {
-      if (p.eps_out) { p.eps_out[(size_t)i * 2] = e0; p.eps_out[(size_t)i * 2 + 1] = e1; }
-      if (p.pen_out) p.pen_out[(size_t)i * p.pen_stride + p.pen_offset] = 1.f / (1.f + expf(-pl));
+      if (p.eps_out) { p.eps_out[(size_t)i_cur * 2] = e0; p.eps_out[(size_t)i_cur * 2 + 1] = e1; }
+      if (p.pen_out) p.pen_out[(size_t)i_cur * p.pen_stride + p.pen_offset] = 1.f / (1.f + expf(-pl));
       if (p.x_io) {
         float* xo = p.x_out ? p.x_out : p.x_io;
-        xo[(size_t)i * p.x_out_stride] = y0;
-        xo[(size_t)i * p.x_out_stride + 1] = y1;
+        xo[(size_t)i_cur * p.x_out_stride] = y0;
+        xo[(size_t)i_cur * p.x_out_stride + 1] = y1;
       }
     }
     if (next_in) {
