@@ -491,9 +491,14 @@ __global__ void __launch_bounds__(256) skip_from_x_kernel(const float* __restric
       a = fmaf(xc.x, m[1][0][k], a); a = fmaf(xc.y, m[1][1][k], a);
       a = fmaf(xl.x, m[0][0][k], a); a = fmaf(xl.y, m[0][1][k], a);
       a = fmaf(xr.x, m[2][0][k], a); a = fmaf(xr.y, m[2][1][k], a);
-      if (!has_l) a -= v0[k];   // first / last position of a line: that tap reads a zero row, not input_dense(0)
-      if (!has_r) a -= v2[k];
       o[k] = a;
+    }
+    if (!(has_l && has_r)) {   // first / last position of a line (2 of T): that tap reads a zero row, not input_dense(0)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (!has_l) o[k] -= v0[k];
+        if (!has_r) o[k] -= v2[k];
+      }
     }
     store8<T_>(out + ((size_t)i + b + 1) * C + c0, o);
     t += 16;
@@ -671,6 +676,7 @@ __global__ void __launch_bounds__(256) heads_from_dots_kernel(const float4* __re
     ib[k] = next_in ? p.in_b[c0 + k] : 0.f;
   }
   const float b0 = cst[0], b1 = cst[1], bpv = cst[2];
+  const float r_div = 1.f / p.c_div, r_eps2 = p.c_eps2 != 0.f ? 1.f / p.c_eps2 : 0.f;
   const uint32_t npts = (uint32_t)p.B * (uint32_t)p.T, T = (uint32_t)p.T;
   const uint32_t stride = ((gridDim.x * blockDim.x) >> 5) * 2;
   const uint32_t stride_b = stride / T, stride_t = stride - stride_b * T;
@@ -698,12 +704,13 @@ __global__ void __launch_bounds__(256) heads_from_dots_kernel(const float4* __re
     const float e0 = da.x + db.x + b0, e1 = da.y + db.y + b1, pl = da.z + db.z + bpv;
     float y0 = 0.f, y1 = 0.f;
     if (p.x_io) {
+      // bf16 chain only: the two divisions of the update formulas as multiplications by reciprocals taken once per thread
       if (p.mode == 0) {
-        y0 = (xx.x - p.c_eps * e0) / p.c_div + zz.x * p.c_noise;
-        y1 = (xx.y - p.c_eps * e1) / p.c_div + zz.y * p.c_noise;
+        y0 = fmaf(zz.x, p.c_noise, (xx.x - p.c_eps * e0) * r_div);
+        y1 = fmaf(zz.y, p.c_noise, (xx.y - p.c_eps * e1) * r_div);
       } else {
-        y0 = p.c_div * (xx.x - p.c_eps * e0 / p.c_eps2) + p.c_noise * zz.x;
-        y1 = p.c_div * (xx.y - p.c_eps * e1 / p.c_eps2) + p.c_noise * zz.y;
+        y0 = fmaf(p.c_noise, zz.x, p.c_div * (xx.x - p.c_eps * e0 * r_eps2));
+        y1 = fmaf(p.c_noise, zz.y, p.c_div * (xx.y - p.c_eps * e1 * r_eps2));
       }
     }
     if (sub == 0) {
