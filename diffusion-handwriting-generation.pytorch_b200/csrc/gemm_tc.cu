@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 #pragma unroll
           for (int k2 = 0; k2 < 4; ++k2) {
             float a = v[p * 8 + k2 * 2], c = v[p * 8 + k2 * 2 + 1];
-            if (act) { a = silu_fast(a); c = silu_fast(c); }
+            if (act) silu_fast2(a, c);
             w[k2] = pack_bf16x2(a, c);
           }
           sts128(buf + st_row + ((p ^ st_sw) << 4), make_uint4(w[0], w[1], w[2], w[3]));
@@ -576,7 +576,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               const float4 bb = lds128f(bias_sa + (uint32_t)(n0 + c * 32 + i) * 4u);
-              v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
+              add2(v[i], v[i + 1], bb.x, bb.y); add2(v[i + 2], v[i + 3], bb.z, bb.w);
             }
           }
           if (aux_in_pass1) consume_aux(v, n0 + c * 32);
@@ -653,13 +653,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         }
         if (ln) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], rstd, nmr);
+          for (int i = 0; i < 32; i += 2) fma2(v[i], v[i + 1], rstd, rstd, nmr, nmr);
         } else {
           if (has_bias && !(film_mode == 1)) {   // film_mode 1 without LN: bias is folded into beta'
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               const float4 bb = lds128f(bias_sa + (uint32_t)(n + i) * 4u);
-              v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
+              add2(v[i], v[i + 1], bb.x, bb.y); add2(v[i + 2], v[i + 3], bb.z, bb.w);
             }
           }
           if (aux_kind == AUX_ROWBIAS || aux_kind == AUX_RES_PRE) consume_aux(v, n);
@@ -669,8 +669,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
           for (int i = 0; i < 32; i += 4) {
             const float4 g = lds128f(gamma_sa + (uint32_t)(n + i) * 4u);
             const float4 bb = lds128f(betap_sa + (uint32_t)(n + i) * 4u);
-            v[i] = fmaf(v[i], g.x, bb.x); v[i + 1] = fmaf(v[i + 1], g.y, bb.y);
-            v[i + 2] = fmaf(v[i + 2], g.z, bb.z); v[i + 3] = fmaf(v[i + 3], g.w, bb.w);
+            fma2(v[i], v[i + 1], g.x, g.y, bb.x, bb.y);
+            fma2(v[i + 2], v[i + 3], g.z, g.w, bb.z, bb.w);
           }
         } else if (film_mode == 2) {
 #pragma unroll

@@ -254,6 +254,38 @@ __device__ __forceinline__ float silu_fast(float x) {
   return fmaf(h, t, h);
 }
 
+// Packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2, one issue slot for two lanes of work; same IEEE results as the scalar
+// forms).  The row epilogue is issue-bound with 2 warps per scheduler, so halving its arithmetic instructions pays.
+__device__ __forceinline__ void fma2(float& a0, float& a1, float b0, float b1, float c0, float c1) {   // a = a * b + c
+  unsigned long long a, b, c;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(c0), "f"(c1));
+  asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a) : "l"(b), "l"(c));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a));
+}
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {   // a += b
+  unsigned long long a, b;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a));
+}
+// SiLU of two values: h = x / 2 (FMUL2), tanh.approx per value (MUFU), h + h * t (FFMA2)
+__device__ __forceinline__ void silu_fast2(float& x0, float& x1) {
+  unsigned long long h, t, half2;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(h) : "f"(x0), "f"(x1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(half2) : "f"(0.5f));
+  asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(h) : "l"(half2));
+  float h0, h1, t0, t1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(h0), "=f"(h1) : "l"(h));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(t) : "f"(t0), "f"(t1));
+  asm("fma.rn.f32x2 %0, %1, %2, %1;" : "=l"(t) : "l"(h), "l"(t));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(t));
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
