@@ -296,6 +296,7 @@ struct AttnTcPlan {
   dim3 grid;
   int threads;
   size_t smem;
+  int pdl;   // programmatic dependent launch, as the option stood when the plan was built
 };
 
 bool attn_tc_supported(const AttnParams& p) {
@@ -310,6 +311,7 @@ AttnTcPlan* attn_tc_plan_create(const AttnParams& p, int q_rows, int k_rows, cha
   cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   AttnTcPlan* a = new AttnTcPlan();
   a->p = p;
+  a->pdl = g_attn_pdl;
   AttnTcShape& sh = a->sh;
   sh.N = (p.Tk + 15) & ~15;
   sh.nblk = (sh.N + 63) / 64;
@@ -375,7 +377,7 @@ int attn_tc_launch(const AttnTcPlan* a, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = g_attn_pdl ? 1 : 0;
+  cfg.numAttrs = a->pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, attn_tc_kernel, a->map_q, a->map_k, a->map_v, a->sh, a->p) == cudaSuccess ? 0 : 1;
 }
 

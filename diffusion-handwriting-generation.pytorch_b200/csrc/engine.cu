@@ -152,10 +152,14 @@ struct Plan {
   float* sigma_in = nullptr;  // [B]
   float* sig_emb = nullptr;   // [B,32]
   float* cond_b = nullptr;    // [B,tot] (dhg_denoise)
-  unsigned long long* rng = nullptr;  // {seed, sample offset}
   float* scratch = nullptr;   // fp32 accumulators of the CUDA-core GEMM path
   size_t scratch_elems = 0;
-  int* err_flag = nullptr;
+  int* err_flag = nullptr;    // set by embed_ln_kernel on a token id outside [0, vocab); read at the synchronising entry points
+  // dhg_set_option switches as they were when the plan was built: the chain (and its cached graphs) only ever see these
+  int opt_tail_fusion = 0, opt_head_fusion = 0;
+  // Every entry point works on the plan's own buffers and graph.  `ev_last` is recorded at the end of each call on the
+  // stream it used and waited for at the start of the next one, so calls on different streams are ordered.
+  cudaEvent_t ev_last = nullptr;
   // once_ops: step-independent; text_ops[set]: the part of a step that depends on sigma but not on x (TextStyleEncoder,
   // text_dense and k/v projections of every EncoderLayer); step_ops: everything that depends on x.  The text side is
   // small (192 row tiles on 148 SMs per launch), so the text sides of `text_sets` consecutive steps are run at once,
@@ -207,7 +211,7 @@ struct dhg_ctx {
   float *in_W = nullptr, *in_b = nullptr, *out_W = nullptr, *out_b = nullptr, *pen_W = nullptr, *pen_b = nullptr;
   std::vector<void*> allocs;
   Plan* plan = nullptr;
-  int opt_gemm = 1, opt_graph = 1, opt_sample_offset = 0, opt_attn = 1;
+  int opt_gemm = 1, opt_graph = 1, opt_attn = 1;
   int64_t last_launches = 0;
 };
 
@@ -376,6 +380,7 @@ void free_plan(Plan* p) {
   for (auto t : p->text_stream)
     if (t) cudaStreamDestroy(t);
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->ev_last) cudaEventDestroy(p->ev_last);
   for (auto e : p->ev_text)
     if (e) cudaEventDestroy(e);
   for (auto a : p->allocs) cudaFree(a);
@@ -765,7 +770,7 @@ struct Builder {
       // conv_skip is only read through H (3 x C): fold it, W'[tau] = H . W_skip[tau] (3 of 32 output columns, K unchanged);
       // the 'dot vectors' just pick those 3 columns
       d0.dot_out = P->tail_dot_skip;
-      if (g_opt_tail_fusion >= 3) { d0.dot_w = c->tail_pick; d0.alt_wkey = "dec1.conv_skip.heads"; }
+      if (P->opt_tail_fusion >= 3) { d0.dot_w = c->tail_pick; d0.alt_wkey = "dec1.conv_skip.heads"; }
       else d0.dot_w = c->tail_H;
       d2.film_off = film(p + ".affine2"); d2.dot_out = P->tail_dot_a2; d2.dot_w_per_step = true; d2.dot_act = true;
     }
@@ -859,9 +864,11 @@ int build_plan(dhg_ctx* c, Plan* P) {
   if (dev_alloc(P->allocs, (void**)&P->sigma_in, (size_t)B * sizeof(float), &P->bytes)) return 1;
   if (dev_alloc(P->allocs, (void**)&P->sig_emb, (size_t)B * kSigmaDim * sizeof(float), &P->bytes)) return 1;
   if (dev_alloc(P->allocs, (void**)&P->cond_b, (size_t)B * tot * sizeof(float), &P->bytes)) return 1;
-  if (dev_alloc(P->allocs, (void**)&P->rng, 2 * sizeof(unsigned long long), &P->bytes)) return 1;
   if (dev_alloc(P->allocs, (void**)&P->err_flag, sizeof(int), &P->bytes)) return 1;
   CUDA_OK(cudaStreamCreateWithFlags(&P->cap_stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreateWithFlags(&P->ev_last, cudaEventDisableTiming));
+  P->opt_tail_fusion = g_opt_tail_fusion;
+  P->opt_head_fusion = g_opt_head_fusion;
 
   // ---- hoisted, step-independent part of TextStyleEncoder (text_style.py:92-99) ----
   Builder once{c, P, &P->once_ops, &P->launches_once};
@@ -1096,8 +1103,8 @@ int run_chain(dhg_ctx* c, Plan* P, int mode, bool has_noise, cudaStream_t st) {
     sc.skip_input_dense = i != DHG_NUM_STEPS - 1;   // written by the previous step's head kernel
     sc.fuse_next_input = i != 0;
     sc.text_set = i % n;
-    sc.fuse_tail = (P->prec == PREC_BF16 && P->gemm_impl == 1) ? (g_opt_tail_fusion > 2 ? 2 : g_opt_tail_fusion) : 0;
-    sc.fuse_head = g_opt_head_fusion && P->prec == PREC_BF16 && P->gemm_impl == 1;
+    sc.fuse_tail = (P->prec == PREC_BF16 && P->gemm_impl == 1) ? (P->opt_tail_fusion > 2 ? 2 : P->opt_tail_fusion) : 0;
+    sc.fuse_head = P->opt_head_fusion && P->prec == PREC_BF16 && P->gemm_impl == 1;
     sc.step = i;
     head_for_step(c, P, i, mode, has_noise, false, &sc.head);
     if (run_ops(P->step_ops, st, sc)) return 1;
@@ -1128,6 +1135,27 @@ int check_ready(const dhg_ctx* c, bool need_plan) {
   if (!c) return fail("null ctx");
   if (!c->finalized) return fail("dhg_finalize has not been called");
   if (need_plan && !c->plan) return fail("dhg_plan has not been called");
+  return 0;
+}
+
+// Stream rule of the plan (include/dhg_b200.h): a call first waits (on its own stream) for the previous call on this
+// plan, whatever stream that one used, and leaves its own completion in ev_last.
+int plan_enter(Plan* P, cudaStream_t st) {
+  CUDA_OK(cudaStreamWaitEvent(st, P->ev_last, 0));
+  return 0;
+}
+int plan_leave(Plan* P, cudaStream_t st) {
+  CUDA_OK(cudaEventRecord(P->ev_last, st));
+  return 0;
+}
+// After a synchronisation: did any kernel of the plan flag bad input (token id outside the embedding table)?
+int plan_check_flags(Plan* P) {
+  int flag = 0;
+  CUDA_OK(cudaMemcpy(&flag, P->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag) {
+    CUDA_OK(cudaMemset(P->err_flag, 0, sizeof(int)));
+    return fail("text token id out of range [0, %d) (the reference's nn.Embedding raises IndexError here)", kVocab);
+  }
   return 0;
 }
 
@@ -1411,6 +1439,7 @@ int32_t dhg_denoise(dhg_ctx* c, const float* strokes, const int64_t* text, const
   Plan* P = c->plan;
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_OK(cudaSetDevice(c->device));
+  if (plan_enter(P, st)) return 1;
   CUDA_OK(cudaMemcpyAsync(P->text, text, (size_t)P->B * P->L * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
   CUDA_OK(cudaMemcpyAsync(P->style, style, (size_t)P->B * P->S * kStyleWidth * sizeof(float), cudaMemcpyDeviceToDevice, st));
   launch_sigma_ffn(sigma, c->sff_w1, c->sff_b1, c->sff_w2, c->sff_b2, kSigmaHidden, P->sig_emb, P->B, st);
@@ -1436,7 +1465,7 @@ int32_t dhg_denoise(dhg_ctx* c, const float* strokes, const int64_t* text, const
   }
   CUDA_OK(cudaGetLastError());
   c->last_launches = 2 + P->launches_once + P->launches_text + P->launches_step;
-  return 0;
+  return plan_leave(P, st);
 }
 
 int32_t dhg_sample(dhg_ctx* c, int32_t batch, const float* x0, const float* noise, uint64_t seed, const int64_t* text,
@@ -1444,11 +1473,12 @@ int32_t dhg_sample(dhg_ctx* c, int32_t batch, const float* x0, const float* nois
   if (check_ready(c, true)) return 1;
   if (batch < 1 || !x0 || !text || !style || !out) return fail("dhg_sample: bad argument");
   if (mode != DHG_MODE_NEW && mode != DHG_MODE_STANDARD) return fail("dhg_sample: bad diffusion mode %d", mode);
-  if (!noise) return fail("dhg_sample: seeded in-kernel noise is not available in this build; pass injected noise [60,batch,T,2]");
+  if (!noise) return fail("dhg_sample: noise is mandatory: pass the injected draws [60,batch,T,2] (the library has no generator of its own)");
   (void)seed;
   Plan* P = c->plan;
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_OK(cudaSetDevice(c->device));
+  if (plan_enter(P, st)) return 1;
   const size_t xs = (size_t)P->T * 2, ss = (size_t)P->S * kStyleWidth;
   if (!P->noise) {
     if (dev_alloc(P->allocs, (void**)&P->noise, (size_t)DHG_NUM_STEPS * P->B * xs * sizeof(float), &P->bytes)) return 1;
@@ -1471,17 +1501,20 @@ int32_t dhg_sample(dhg_ctx* c, int32_t batch, const float* x0, const float* nois
     if (launch_chain(c, P, mode, true, st)) return 1;
     CUDA_OK(cudaMemcpyAsync(out + (size_t)c0 * P->T * 3, P->out, (size_t)nb * P->T * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     launches += P->launches_once + (int64_t)DHG_NUM_STEPS * (P->launches_text + P->launches_step) - (DHG_NUM_STEPS - 1);   // input_dense is fused after step 1
-    if (g_opt_tail_fusion && P->prec == PREC_BF16 && P->gemm_impl == 1) launches -= DHG_NUM_STEPS;   // dec1.fc lives in the head kernel
+    if (P->opt_tail_fusion && P->prec == PREC_BF16 && P->gemm_impl == 1) launches -= DHG_NUM_STEPS;   // dec1.fc lives in the head kernel
   }
   c->last_launches = launches;
-  return 0;
+  return plan_leave(P, st);
 }
 
 int32_t dhg_sample_host(dhg_ctx* c, int32_t batch, const float* x0, const float* noise, uint64_t seed, const int64_t* text,
                         const float* style, int32_t mode, float* out) {
   if (check_ready(c, true)) return 1;
   if (batch < 1 || !x0 || !text || !style || !out) return fail("dhg_sample_host: bad argument");
+  if (!noise) return fail("dhg_sample_host: noise is mandatory: pass the injected draws [60,batch,T,2]");
   Plan* P = c->plan;
+  for (size_t i = 0, n = (size_t)batch * P->L; i < n; ++i)   // host ids: checked here, before anything is copied
+    if (text[i] < 0 || text[i] >= kVocab) return fail("text token id %lld at index %zu out of range [0, %d)", (long long)text[i], i, kVocab);
   CUDA_OK(cudaSetDevice(c->device));
   const size_t xs = (size_t)P->T * 2, ss = (size_t)P->S * kStyleWidth;
   // device staging for the host buffers: owned by the plan and kept between calls (no allocation, clearing or freeing
@@ -1507,6 +1540,7 @@ int32_t dhg_sample_host(dhg_ctx* c, int32_t batch, const float* x0, const float*
     fprintf(stderr, "dhg_sample_host: %-10s at %.2f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
   };
   cudaStream_t st = P->cap_stream;
+  if (plan_enter(P, st)) return 1;   // the staging buffers may still be read by an earlier stream-ordered call
   CUDA_OK(cudaMemcpyAsync(hs.x, x0, (size_t)batch * xs * sizeof(float), cudaMemcpyHostToDevice, st));
   CUDA_OK(cudaMemcpyAsync(hs.style, style, (size_t)batch * ss * sizeof(float), cudaMemcpyHostToDevice, st));
   CUDA_OK(cudaMemcpyAsync(hs.text, text, (size_t)batch * P->L * sizeof(int64_t), cudaMemcpyHostToDevice, st));
@@ -1517,7 +1551,7 @@ int32_t dhg_sample_host(dhg_ctx* c, int32_t batch, const float* x0, const float*
   CUDA_OK(cudaMemcpyAsync(out, hs.out, (size_t)batch * P->T * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
   lap("d2h");
-  return 0;
+  return plan_check_flags(P);
 }
 
 int32_t dhg_posterior_step(dhg_ctx* c, int32_t step, int32_t mode, const float* x, const float* eps, const float* noise,
@@ -1547,6 +1581,14 @@ int32_t dhg_posterior_step(dhg_ctx* c, int32_t step, int32_t mode, const float* 
   return 0;
 }
 
+int32_t dhg_check_errors(dhg_ctx* c, void* stream) {
+  if (check_ready(c, true)) return 1;
+  CUDA_OK(cudaSetDevice(c->device));
+  CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+  CUDA_OK(cudaGetLastError());
+  return plan_check_flags(c->plan);
+}
+
 int64_t dhg_last_launch_count(const dhg_ctx* c) { return c ? c->last_launches : 0; }
 int64_t dhg_plan_bytes(const dhg_ctx* c) { return (c && c->plan) ? (int64_t)c->plan->bytes : 0; }
 
@@ -1573,7 +1615,6 @@ int32_t dhg_set_option(dhg_ctx* c, const char* key, int32_t value) {
   if (!strcmp(key, "gemm")) c->opt_gemm = value ? 1 : 0;
   else if (!strcmp(key, "graph")) c->opt_graph = value ? 1 : 0;
   else if (!strcmp(key, "attn")) c->opt_attn = value ? 1 : 0;
-  else if (!strcmp(key, "sample_offset")) c->opt_sample_offset = value;
   else return fail("dhg_set_option: unknown key %s", key);
   return 0;
 }
@@ -1589,6 +1630,7 @@ int64_t dhg_debug_read(dhg_ctx* c, const char* name, float* host_out, int64_t ca
   if (!host_out) return n;
   if (capacity < n) { fail("dhg_debug_read: capacity %lld < %lld", (long long)capacity, (long long)n); return -1; }
   if (cudaSetDevice(c->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) { fail("dhg_debug_read: device error"); return -1; }
+  if (plan_check_flags(P)) return -1;
   std::vector<char> tmp((size_t)a.rows * a.C * P->esize);
   if (cudaMemcpy(tmp.data(), a.p, tmp.size(), cudaMemcpyDeviceToHost) != cudaSuccess) { fail("dhg_debug_read: copy failed"); return -1; }
   for (int b = 0; b < P->B; ++b)

@@ -793,6 +793,7 @@ struct TcGemmPlan {
   size_t smem;
   TcKernFn fn_shared;    // FiLM (if any) with one vector for the batch
   TcKernFn fn_generic;   // per-sample FiLM or anything unusual
+  int pdl;               // programmatic dependent launch, as the option stood when the plan was built
 };
 
 TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W, int K, int N, int taps, const Epilogue& e,
@@ -842,6 +843,7 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
 
   TcGemmPlan* p = new TcGemmPlan();
+  p->pdl = g_opt_pdl;
   TcShape& sh = p->sh;
   sh.rows = rows; sh.K = K; sh.N = N; sh.taps = taps; sh.BN = BN;
   sh.n_groups = N / BN;
@@ -1004,7 +1006,7 @@ int tc_gemm_launch(const TcGemmPlan* p, const Epilogue& e, cudaStream_t st) {
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   int na = 0;
-  if (g_opt_pdl) {
+  if (p->pdl) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;

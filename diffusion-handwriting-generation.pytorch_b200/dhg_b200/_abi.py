@@ -54,6 +54,7 @@ SIGNATURES = {
     "dhg_denoise": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dhg_sample": (c_i32, [c_vp, c_i32, c_vp, c_vp, c_u64, c_vp, c_vp, c_i32, c_vp, c_vp]),
     "dhg_sample_host": (c_i32, [c_vp, c_i32, c_vp, c_vp, c_u64, c_vp, c_vp, c_i32, c_vp]),
+    "dhg_check_errors": (c_i32, [c_vp, c_vp]),
     "dhg_posterior_step": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "dhg_last_launch_count": (c_i64, [c_vp]),
     "dhg_plan_bytes": (c_i64, [c_vp]),

@@ -77,3 +77,38 @@ def infer(prompt, source, config_path=None, checkpoint_path=None, experiment_pat
 
         save_strokes_png(strokes.numpy(), f"./{output}.png")
     return strokes
+
+
+def main(argv=None):
+    """Command line of the reference: `python diffusion_handwriting_generation/inference.py --prompt=... --source=...
+    --experiment_path=... --output=...` (inference.py:101-102 `fire.Fire(infer)`, driven by `make infer TEXT= SOURCE=
+    EXP= OUTPUT=`, Makefile:14-21).  `fire` is not installed here, so the same flags are parsed with argparse; both
+    `--flag value` and fire's `--flag=value` spellings work, and the positional order is infer()'s."""
+    import argparse
+
+    ap = argparse.ArgumentParser(prog="python -m dhg_b200.inference", description=infer.__doc__ or main.__doc__)
+    ap.add_argument("prompt_pos", nargs="?", default=None, help="text to write (or --prompt)")
+    ap.add_argument("source_pos", nargs="?", default=None, help="style source (or --source)")
+    ap.add_argument("--prompt", "--text", dest="prompt", default=None)
+    ap.add_argument("--source", default=None, help="handwriting image, or a .pt/.npy file with a [14,1280] style tensor")
+    ap.add_argument("--config_path", "--config-path", dest="config_path", default=None)
+    ap.add_argument("--checkpoint_path", "--checkpoint-path", dest="checkpoint_path", default=None)
+    ap.add_argument("--experiment_path", "--experiment-path", "--exp", dest="experiment_path", default=None)
+    ap.add_argument("--output", default="result")
+    ap.add_argument("--diffusion_mode", "--diffusion-mode", dest="diffusion_mode", default="new", choices=["new", "standard"])
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--device", default="cuda:0")
+    ap.add_argument("--seed", type=int, default=None)
+    a = ap.parse_args(argv)
+    prompt = a.prompt if a.prompt is not None else a.prompt_pos
+    source = a.source if a.source is not None else a.source_pos
+    if prompt is None or source is None:
+        ap.error("prompt and source are required (infer(prompt, source, ...), inference.py:19-27)")
+    strokes = infer(prompt, source, a.config_path, a.checkpoint_path, a.experiment_path, a.output, a.diffusion_mode,
+                    dtype=a.dtype, device=a.device, seed=a.seed)
+    print(f"wrote ./{a.output}.png ({strokes.shape[0]} stroke points)")
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

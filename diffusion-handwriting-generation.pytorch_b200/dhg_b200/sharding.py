@@ -29,8 +29,20 @@ def sample_sharded(sample_fn, text, style, x0, noise, rank, world, gather=True, 
         local = x0.new_zeros((0, x0.shape[1], 3))
     if not gather or world == 1:
         return local
+    return gather_outputs(local, text.shape[0], rank, world, group=group)
+
+
+def gather_outputs(local, total, rank, world, group=None):
+    """All-gather the per-rank [b_r, T, 3] results into [total, T, 3] on every rank, in rank order.  One tensor
+    collective (NCCL for CUDA tensors, gloo for CPU tensors): shards differ by at most one sample, so every rank
+    contributes a buffer of the largest shard size and the padding row is dropped afterwards."""
     import torch.distributed as dist
 
-    parts = [None] * world
-    dist.all_gather_object(parts, local.cpu(), group=group)
-    return torch.cat(parts, dim=0)
+    sizes = [hi - lo for lo, hi in (shard_bounds(total, r, world) for r in range(world))]
+    width = max(sizes)
+    send = local.new_zeros((width,) + tuple(local.shape[1:]))
+    send[: local.shape[0]] = local
+    recv = local.new_empty((world * width,) + tuple(local.shape[1:]))
+    dist.all_gather_into_tensor(recv, send.contiguous(), group=group)
+    recv = recv.view((world, width) + tuple(local.shape[1:]))
+    return torch.cat([recv[r, : sizes[r]] for r in range(world)], dim=0)

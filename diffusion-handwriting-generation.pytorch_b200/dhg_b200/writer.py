@@ -158,6 +158,41 @@ class DiffusionWriter:
             raise IndexError("text token id out of range [0, 73)")
         self._tokens_ok = (weakref.ref(obj), obj._version)
 
+    @staticmethod
+    def _check_mode(diffusion_mode):
+        if diffusion_mode not in _MODE:
+            raise ValueError(f"diffusion_mode must be 'new' or 'standard', got {diffusion_mode!r}")
+        return _MODE[diffusion_mode]
+
+    @staticmethod
+    def _check_chain_shapes(text, style, x0, noise):
+        """Shape contract of the chain entry points (sample / sample_host): every pointer handed to the C ABI is
+        sized from these, so nothing is passed on before they hold."""
+        if text.dim() != 2:
+            raise ValueError("text must be [B,L]")
+        B, L = text.shape
+        if style.dim() != 3 or style.shape[0] != B or style.shape[2] != STYLE_WIDTH or style.shape[1] < 1:
+            raise ValueError("style_vector must be [B,S,1280]")
+        if x0.dim() != 3 or tuple(x0.shape[::2]) != (B, 2):
+            raise ValueError("x0 must be [B,T,2] and noise [60,B,T,2]")
+        T = x0.shape[1]
+        if T % 8 or T <= 0:
+            raise ValueError("T must be a positive multiple of 8")
+        if tuple(noise.shape) != (NUM_STEPS, B, T, 2):
+            raise ValueError("x0 must be [B,T,2] and noise [60,B,T,2]")
+        return B, T, L, style.shape[1]
+
+    def check_errors(self):
+        """Synchronise the current stream and raise IndexError if a stream-ordered call met a token id outside
+        [0, 73) (the reference's nn.Embedding raises there; the kernel can only flag it)."""
+        with torch.cuda.device(self.device):
+            rc = self._lib.dhg_check_errors(self._ctx, self._stream())
+        if rc != 0:
+            msg = self._lib.dhg_last_error().decode("utf-8", "replace")
+            if "token id" in msg:
+                raise IndexError(msg)
+            raise _abi.DhgError(msg)
+
     # -- DiffusionModel.forward (model.py:121-182) -----------------------------
     @torch.no_grad()
     def denoise(self, strokes, text, sigma, style_vector):
@@ -196,12 +231,13 @@ class DiffusionWriter:
         (noise[i] is consumed at loop index i); by default drawn with torch's CUDA
         generator (seeded with `seed` if given).
         """
-        if diffusion_mode not in _MODE:
-            raise ValueError(f"diffusion_mode must be 'new' or 'standard', got {diffusion_mode!r}")
+        mode = self._check_mode(diffusion_mode)
         if isinstance(text, (list, tuple)) and text and isinstance(text[0], str):
             text = self.encode(text)
         text_in = text
         text = self._dev(text, torch.int64)
+        if text.dim() != 2:
+            raise ValueError("text must be [B,L]")
         self._check_tokens(text, text_in)
         B, L = text.shape
         style = self._dev(style_vector, torch.float32)
@@ -221,13 +257,14 @@ class DiffusionWriter:
             noise = torch.randn(NUM_STEPS, B, T, 2, device=self.device, generator=gen)
         x0 = self._dev(x0, torch.float32)
         noise = self._dev(noise, torch.float32)
-        if tuple(x0.shape) != (B, T, 2) or tuple(noise.shape) != (NUM_STEPS, B, T, 2):
+        if tuple(x0.shape) != (B, T, 2):
             raise ValueError("x0 must be [B,T,2] and noise [60,B,T,2]")
+        self._check_chain_shapes(text, style, x0, noise)
         self._plan(min(B, self.chunk), T, L, style.shape[1])
         out = torch.empty(B, T, 3, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
             _abi.check(self._lib.dhg_sample(self._ctx, B, _ptr(x0), _ptr(noise), 0, _ptr(text), _ptr(style),
-                                            _MODE[diffusion_mode], _ptr(out), self._stream()))
+                                            mode, _ptr(out), self._stream()))
         return out
 
     @torch.no_grad()
@@ -237,16 +274,18 @@ class DiffusionWriter:
         staging buffer owned by the writer (allocating pinned memory per call costs tens of
         milliseconds every time the caching host allocator runs dry); the result is returned as a
         fresh tensor, or written into `out` ([B,T,3] fp32 CPU; pinned: no staging copy at all)."""
+        mode = self._check_mode(diffusion_mode)
+        if isinstance(text, (list, tuple)) and text and isinstance(text[0], str):
+            text = self.encode(text)
         text = torch.as_tensor(text).to("cpu", torch.int64).contiguous()
-        self._check_tokens(text)
         style = torch.as_tensor(style_vector).to("cpu", torch.float32).contiguous()
         x0 = torch.as_tensor(x0).to("cpu", torch.float32).contiguous()
         noise = torch.as_tensor(noise).to("cpu", torch.float32).contiguous()
-        B, L = text.shape
-        T = x0.shape[1]
-        if tuple(x0.shape) != (B, T, 2) or tuple(noise.shape) != (NUM_STEPS, B, T, 2):
-            raise ValueError("x0 must be [B,T,2] and noise [60,B,T,2]")
-        self._plan(min(B, self.chunk), T, L, style.shape[1])
+        B, T, L, S = self._check_chain_shapes(text, style, x0, noise)
+        # host ids: always checked (no device synchronisation involved); the library checks them once more
+        if text.numel() and (int(text.min()) < 0 or int(text.max()) >= 73):
+            raise IndexError("text token id out of range [0, 73)")
+        self._plan(min(B, self.chunk), T, L, S)
         direct = out is not None and out.is_pinned() and out.is_contiguous()
         if out is not None and (tuple(out.shape) != (B, T, 3) or out.dtype != torch.float32 or out.device.type != "cpu"):
             raise ValueError("out must be a [B,T,3] fp32 CPU tensor")
@@ -258,7 +297,7 @@ class DiffusionWriter:
                 stage = self._host_stage = torch.empty(B, T, 3, dtype=torch.float32, pin_memory=True)
         with torch.cuda.device(self.device):
             _abi.check(self._lib.dhg_sample_host(self._ctx, B, _ptr(x0), _ptr(noise), 0, _ptr(text), _ptr(style),
-                                                 _MODE[diffusion_mode], _ptr(stage)))
+                                                 mode, _ptr(stage)))
         if direct:
             return out
         if out is not None:

@@ -15,6 +15,13 @@
  *    has completed); the library never frees or keeps them.
  *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
  *  - one ctx per device; a ctx is not re-entrant: one host thread at a time.
+ *  - stream rule: dhg_denoise / dhg_sample / dhg_sample_host all work on the
+ *    plan's own buffers and captured graph.  Each call first makes its stream
+ *    wait for the previous call on the same ctx (whatever stream that used) and
+ *    records its own completion, so calls on different streams, or a
+ *    stream-ordered call followed by dhg_sample_host, never overlap on those
+ *    buffers.  The CALLER's buffers follow the usual rule: they must stay valid
+ *    until the work enqueued on `stream` has completed.
  *  - there is no CPU fallback: every entry point that computes needs a CUDA
  *    device of compute capability 10.x and fails loudly otherwise.
  */
@@ -93,8 +100,9 @@ int32_t dhg_denoise(dhg_ctx* ctx, const float* dev_strokes, const int64_t* dev_t
 /* Replaces: the 60-step loop of infer(), inference.py:81-96, for `batch`
  * samples (any batch >= 1: processed in chunks of the planned B).
  * x0 [batch,T,2] f32; noise [60,batch,T,2] f32, noise[i] consumed at loop index i
- * (the draw of randn_like in utils/nn.py:86,111), or NULL with `seed` for the
- * library's own counter-based generator; text [batch,L] i64; style
+ * (the draw of randn_like in utils/nn.py:86,111).  The draws are MANDATORY: the
+ * library has no generator of its own (NULL fails); `seed` is reserved and
+ * ignored.  text [batch,L] i64; style
  * [batch,S,1280] f32 -> out [batch,T,3] f32 = cat(x, pen_lifts of the last step).
  * Stream-ordered; the chain runs as one CUDA graph per chunk. */
 int32_t dhg_sample(dhg_ctx* ctx, int32_t batch, const float* dev_x0, const float* dev_noise,
@@ -106,6 +114,12 @@ int32_t dhg_sample(dhg_ctx* ctx, int32_t batch, const float* dev_x0, const float
 int32_t dhg_sample_host(dhg_ctx* ctx, int32_t batch, const float* host_x0, const float* host_noise,
                         uint64_t seed, const int64_t* host_text, const float* host_style,
                         int32_t mode, float* host_out);
+
+/* Stream-ordered calls cannot report bad input found on the device (a token id outside [0, 73), where the
+ * reference's nn.Embedding raises IndexError): the kernel substitutes id 0 and raises a flag.  This call
+ * synchronises `stream` and fails with "token id out of range" if the flag is set (and clears it).
+ * dhg_sample_host checks its host ids before copying and the flag after its own synchronisation. */
+int32_t dhg_check_errors(dhg_ctx* ctx, void* stream);
 
 /* Replaces: new_diffusion_step / standard_diffusion_step (utils/nn.py:64-112)
  * with the noise draw injected: one fused streaming kernel over n = B*T*2 floats.
@@ -120,11 +134,13 @@ int32_t dhg_posterior_step(dhg_ctx* ctx, int32_t step, int32_t mode, const float
 int64_t dhg_last_launch_count(const dhg_ctx* ctx);
 /* Bytes of device memory held by the current plan. */
 int64_t dhg_plan_bytes(const dhg_ctx* ctx);
-/* Engine switches, mainly for tests and A/B measurements.  Per context (take effect at the next dhg_plan):
+/* Engine switches, mainly for tests and A/B measurements.  ALL of them are read when a plan is built (dhg_plan) and
+ * stored in it: setting one afterwards has no effect on the current plan, its captured graphs or its launch count.
+ * Per context:
  *   "gemm"  0 CUDA-core GEMM + row epilogue kernel, 1 tcgen05 GEMM with fused epilogue (bf16 only; default 1)
  *   "attn"  0 CUDA-core attention, 1 tcgen05 attention (bf16 only; default 1)
  *   "graph" 0/1 one CUDA graph per chain in dhg_sample (default 1)
- * Process-wide (ctx may be NULL; take effect at the next dhg_plan):
+ * Process-wide (ctx may be NULL; shared by every context of the process):
  *   "text_sets"    1..6 text sides of that many consecutive steps run at once on their own streams (default 2)
  *   "autotune"     0/1 time the GEMM tile configurations and the attention tile-load order at plan time (default 1)
  *   "serpentine"   0/1 alternate the row walking direction from kernel to kernel (default 1)

@@ -4,9 +4,9 @@ BASELINE batch size.  Needs a B200: run with `-m gpu`.
 
 Tolerances (BASELINE.json north_star / SURVEY.md 8d):
   fp32 mode : strokes rel-L2 <= 1e-3 after the full 60-step chain, pen-lift (p > 0.5) agreement >= 99.9 %
-  bf16 mode : strokes rel-L2 <= 1.5e-2, pen-lift agreement >= 97 % over positions with
-              |p_ref - 0.5| > 0.02 (random-init pen probabilities sit near 0.5; the CPU bf16-autocast
-              reference itself lands at 6e-3 / 98.7 %)
+  bf16 mode : strokes rel-L2 <= 1e-2, pen-lift agreement >= 98.5 % over positions with
+              |p_ref - 0.5| > 0.01 (SURVEY.md 8d's anchor: random-init pen probabilities sit near 0.5; the
+              CPU bf16-autocast reference itself lands at 6e-3 / 98.7 %)
 """
 import os
 
@@ -19,7 +19,7 @@ from oracle import dhg_oracle as O
 pytestmark = pytest.mark.gpu
 
 FP32_REL, FP32_PEN = 1e-3, 0.999
-BF16_REL, BF16_PEN, BF16_PEN_MARGIN = 1.5e-2, 0.97, 0.02
+BF16_REL, BF16_PEN, BF16_PEN_MARGIN = 1e-2, 0.985, 0.01
 
 
 def _rel(a, b):

@@ -123,3 +123,58 @@ def test_polylines_and_png(tmp_path):
     p = save_strokes_png(strokes, str(tmp_path / "out.png"))
     data = open(p, "rb").read()
     assert data[:8] == b"\x89PNG\r\n\x1a\n" and data[-8:-4] == b"IEND"
+
+
+def test_chain_shape_contract():
+    """Every pointer handed to dhg_sample / dhg_sample_host is sized from these checks (sample_host used to
+    skip them and could read past the end of a host buffer)."""
+    from dhg_b200.writer import DiffusionWriter
+
+    chk = DiffusionWriter._check_chain_shapes
+    B, T, L = 3, 16, 5
+    text, style = torch.zeros(B, L, dtype=torch.int64), torch.zeros(B, 14, 1280)
+    x0, noise = torch.zeros(B, T, 2), torch.zeros(60, B, T, 2)
+    assert chk(text, style, x0, noise) == (B, T, L, 14)
+    bad = [
+        (text, style[:1], x0, noise),                  # one style for B > 1 prompts
+        (text, style[0], x0, noise),                   # 2-D style
+        (text, torch.zeros(B, 14, 1279), x0, noise),   # wrong style width
+        (text, style, x0[:, :, :1], noise),            # not (dx, dy)
+        (text, style, x0, noise[:59]),                 # 59 draws
+        (text, style, x0, noise[:, :2]),               # noise of another batch
+        (text, style, torch.zeros(B, 12, 2), torch.zeros(60, B, 12, 2)),   # T not a multiple of 8
+        (text[0], style, x0, noise),                   # 1-D text
+    ]
+    for args in bad:
+        with pytest.raises(ValueError):
+            chk(*args)
+    assert DiffusionWriter._check_mode("new") == 0 and DiffusionWriter._check_mode("standard") == 1
+    with pytest.raises(ValueError):
+        DiffusionWriter._check_mode("ddim")
+
+
+def test_cli_mirrors_make_infer(monkeypatch, capsys):
+    """`make infer` of the reference passes --prompt= --source= --experiment_path= --config_path="" --checkpoint_path=""
+    --output= (Makefile:14-21) to fire.Fire(infer) (inference.py:101-102)."""
+    from dhg_b200 import inference
+
+    seen = {}
+
+    def fake_infer(prompt, source, config_path=None, checkpoint_path=None, experiment_path=None, output="result",
+                   diffusion_mode="new", **kw):
+        seen.update(prompt=prompt, source=source, config_path=config_path, checkpoint_path=checkpoint_path,
+                    experiment_path=experiment_path, output=output, diffusion_mode=diffusion_mode, **kw)
+        return torch.zeros(24, 3)
+
+    monkeypatch.setattr(inference, "infer", fake_infer)
+    rc = inference.main(["--prompt=Hello World and goodbye", "--source=style.pt", "--experiment_path=data/best_exp",
+                         "--config_path=", "--checkpoint_path=", "--output=prediction"])
+    assert rc == 0 and "prediction.png" in capsys.readouterr().out
+    assert seen["prompt"] == "Hello World and goodbye" and seen["source"] == "style.pt"
+    assert seen["experiment_path"] == "data/best_exp" and seen["output"] == "prediction"
+    assert not seen["config_path"] and not seen["checkpoint_path"] and seen["diffusion_mode"] == "new"
+    # fire also accepts the positional order of infer()
+    inference.main(["Follow the White Rabbit", "style.npy", "--experiment_path", "exp", "--diffusion_mode", "standard"])
+    assert seen["prompt"] == "Follow the White Rabbit" and seen["source"] == "style.npy" and seen["diffusion_mode"] == "standard"
+    with pytest.raises(SystemExit):
+        inference.main(["--prompt=only a prompt"])
