@@ -18,6 +18,15 @@ typedef __nv_bfloat16 bf16;
 
 enum Precision { PREC_FP32 = 0, PREC_BF16 = 1 };
 
+// Split storage of an fp32 value for the fp32-contract mode on tensor cores: x ~ hi + lo with hi = bf16(x),
+// lo = bf16(x - hi), 16 mantissa bits together (relative error <= 2^-17).  A row of C such elements IS a bf16 row of
+// 2C elements (hi_0 lo_0 hi_1 lo_1 ..), so it feeds the bf16 tensor-core GEMM directly: with the weights split the
+// same way, x . w = (hi + lo) . w_hi + hi . w_lo (+ lo . w_lo, dropped: 2^-18) is two bf16 GEMMs over that row, one
+// against (w_hi, w_hi)-interleaved and one against (w_lo, 0)-interleaved weights, accumulated in fp32 (gemm_tc.cu).
+struct __align__(4) bfs {
+  __nv_bfloat16 hi, lo;
+};
+
 // How a flat row index maps to (sample, position): rows are grouped in periods
 // of `period` rows per sample; if `pad_first`, the first row of each period is
 // the zero halo row.  Rows >= nvalid (= B * period) are trailing padding.
@@ -57,6 +66,8 @@ struct Epilogue {
   float* dot_out;
   int dot_act;
   int dot_planned;         // plan-time flag like film_planned: dot_w is supplied at launch
+  int split_io;            // tcgen05 path: every activation operand (A, residuals, per-position rows, outputs) is `bfs`
+                           // split storage; pitches stay in elements.  The fp32-contract mode (engine.cu).
   RowMap map;
 };
 
@@ -72,11 +83,27 @@ template <> __device__ __forceinline__ float silu_out<__nv_bfloat16>(float x) {
   return fmaf(h, t, h);
 }
 
+__device__ __forceinline__ uint32_t split_pack(float x) {   // -> hi in the low half-word, lo in the high one
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+  return (uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(l) << 16);
+}
+__device__ __forceinline__ float split_unpack(uint32_t w) {
+  return __uint_as_float(w << 16) + __uint_as_float(w & 0xffff0000u);
+}
+
 template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<bfs>(bfs v) { return __bfloat162float(v.hi) + __bfloat162float(v.lo); }
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
 
 template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ bfs from_f<bfs>(float v) {
+  bfs r;
+  r.hi = __float2bfloat16_rn(v);
+  r.lo = __float2bfloat16_rn(v - __bfloat162float(r.hi));
+  return r;
+}
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
 
@@ -92,7 +119,14 @@ template <> __device__ __forceinline__ float4 load4<bf16>(const bf16* p) {
   float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
   return make_float4(fa.x, fa.y, fb.x, fb.y);
 }
+template <> __device__ __forceinline__ float4 load4<bfs>(const bfs* p) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  return make_float4(split_unpack(u.x), split_unpack(u.y), split_unpack(u.z), split_unpack(u.w));
+}
 template <typename T> __device__ __forceinline__ void store4(T* p, float4 v);
+template <> __device__ __forceinline__ void store4<bfs>(bfs* p, float4 v) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(split_pack(v.x), split_pack(v.y), split_pack(v.z), split_pack(v.w));
+}
 template <> __device__ __forceinline__ void store4<float>(float* p, float4 v) {
   *reinterpret_cast<float4*>(p) = v;
 }
@@ -120,7 +154,16 @@ template <> __device__ __forceinline__ void load8<bf16>(const bf16* p, float* v)
     v[2 * i] = f.x; v[2 * i + 1] = f.y;
   }
 }
+template <> __device__ __forceinline__ void load8<bfs>(const bfs* p, float* v) {
+  const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 4);
+  v[0] = split_unpack(a.x); v[1] = split_unpack(a.y); v[2] = split_unpack(a.z); v[3] = split_unpack(a.w);
+  v[4] = split_unpack(b.x); v[5] = split_unpack(b.y); v[6] = split_unpack(b.z); v[7] = split_unpack(b.w);
+}
 template <typename T> __device__ __forceinline__ void store8(T* p, const float* v);
+template <> __device__ __forceinline__ void store8<bfs>(bfs* p, const float* v) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(split_pack(v[0]), split_pack(v[1]), split_pack(v[2]), split_pack(v[3]));
+  *reinterpret_cast<uint4*>(p + 4) = make_uint4(split_pack(v[4]), split_pack(v[5]), split_pack(v[6]), split_pack(v[7]));
+}
 template <> __device__ __forceinline__ void store8<float>(float* p, const float* v) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);

@@ -48,7 +48,9 @@ constexpr int TMEM_COLS = 512;
 enum { AUX_NONE = 0, AUX_RES_PRE = 1, AUX_RES_POST = 2, AUX_RES_POST_UP = 3, AUX_ROWBIAS = 4 };
 
 struct TcShape {
-  int rows, K, N, taps;
+  int rows, K, N, taps;   // taps = weight slabs per k-block: 1 linear, 3 conv; split I/O doubles them (2 / 6, see base_taps)
+  int base_taps;   // row shifts of the A operand: slab s reads the A tile shifted by s % base_taps rows (1 or 3)
+  int sio;         // split I/O (Epilogue::split_io): activations are bfs pairs; K, lda and the A map are in bf16 units (2 per element)
   int BN;          // tile width
   int n_groups;    // N / BN
   int m_tiles;
@@ -105,6 +107,7 @@ __device__ __forceinline__ void mma_issue_loop(const TcShape& sh, const bool lea
                                                uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, const int t_first,
                                                const int t_end, const int t_step, unsigned& tr_n, const int tr_role,
                                                const int lane) {
+  constexpr int BASE = (TAPS % 3 == 0) ? 3 : 1;   // slab -> row shift of the A tile (split I/O: two slabs per shift)
   const uint32_t nb2 = (uint32_t)(PAIR ? sh.umma_n / 2 : sh.umma_n) * TC_BK * 2;   // byte offset of the second N half (BN = 384)
   const bool two_n = sh.n_umma == 2;
   const bool resident = sh.w_resident != 0;
@@ -149,10 +152,10 @@ __device__ __forceinline__ void mma_issue_loop(const TcShape& sh, const bool lea
 #pragma unroll
               for (int sub = 0; sub < G; ++sub) {
                 if (PAIR)
-                  umma_bf16_pair(acc, umma_desc_make(alo[0] + tap * 8 + 2 * k, kDescHiSw128), umma_desc_make(blo + 2 * k, kDescHiSw128),
+                  umma_bf16_pair(acc, umma_desc_make(alo[0] + (tap % BASE) * 8 + 2 * k, kDescHiSw128), umma_desc_make(blo + 2 * k, kDescHiSw128),
                                  sh.idesc, (tap | k) ? 1u : first);
                 else
-                  umma_bf16(acc + (uint32_t)(sub * sh.BN), umma_desc_make(alo[sub] + tap * 8 + 2 * k, kDescHiSw128),
+                  umma_bf16(acc + (uint32_t)(sub * sh.BN), umma_desc_make(alo[sub] + (tap % BASE) * 8 + 2 * k, kDescHiSw128),
                             umma_desc_make(blo + 2 * k, kDescHiSw128), sh.idesc, (tap | k) ? 1u : first);
               }
           } else {
@@ -160,14 +163,14 @@ __device__ __forceinline__ void mma_issue_loop(const TcShape& sh, const bool lea
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k) {
               if (PAIR) {
-                umma_bf16_pair(acc, umma_desc_make(alo[0] + tap * 8 + 2 * k, kDescHiSw128), umma_desc_make(blo + 2 * k, kDescHiSw128),
+                umma_bf16_pair(acc, umma_desc_make(alo[0] + (tap % BASE) * 8 + 2 * k, kDescHiSw128), umma_desc_make(blo + 2 * k, kDescHiSw128),
                                sh.idesc, (tap | k) ? 1u : first);
-                umma_bf16_pair(acc + (uint32_t)sh.umma_n, umma_desc_make(alo[0] + tap * 8 + 2 * k, kDescHiSw128),
+                umma_bf16_pair(acc + (uint32_t)sh.umma_n, umma_desc_make(alo[0] + (tap % BASE) * 8 + 2 * k, kDescHiSw128),
                                umma_desc_make(blo2 + 2 * k, kDescHiSw128), sh.idesc, (tap | k) ? 1u : first);
               } else {
-                umma_bf16(acc, umma_desc_make(alo[0] + tap * 8 + 2 * k, kDescHiSw128), umma_desc_make(blo + 2 * k, kDescHiSw128), sh.idesc,
+                umma_bf16(acc, umma_desc_make(alo[0] + (tap % BASE) * 8 + 2 * k, kDescHiSw128), umma_desc_make(blo + 2 * k, kDescHiSw128), sh.idesc,
                           (tap | k) ? 1u : first);
-                umma_bf16(acc + (uint32_t)sh.umma_n, umma_desc_make(alo[0] + tap * 8 + 2 * k, kDescHiSw128),
+                umma_bf16(acc + (uint32_t)sh.umma_n, umma_desc_make(alo[0] + (tap % BASE) * 8 + 2 * k, kDescHiSw128),
                           umma_desc_make(blo2 + 2 * k, kDescHiSw128), sh.idesc, (tap | k) ? 1u : first);
               }
             }
@@ -192,7 +195,7 @@ __device__ __forceinline__ void mma_issue_loop(const TcShape& sh, const bool lea
 // Template parameters fix the epilogue variant at compile time (-1 = read the flag at run time: the
 // generic instance).  kLN: LayerNorm; kAUX: AUX_* kind; kFILM: 0 none, 1 vectors shared by the batch
 // (smem), 2 per-sample vectors (global loads); kOUT: 1 raw, 2 SiLU'd, 3 both.
-template <int kLN, int kAUX, int kFILM, int kOUT, bool kPAIR, bool kSPLIT = false>
+template <int kLN, int kAUX, int kFILM, int kOUT, bool kPAIR, bool kSPLIT = false, bool kSIO = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_w,
                                                                 const __grid_constant__ CUtensorMap map_oraw,
@@ -296,7 +299,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   if (warp == 0) {
     // ===== TMA producer: the whole warp runs the (uniform) loop, one elected lane issues the copies =====
     const bool leader = elect_one();
-    const int a_row_off = sh.taps == 3 ? -1 : 0;   // 3 taps: one 130-row tile starting one row early
+    const int a_row_off = sh.base_taps == 3 ? -1 : 0;   // 3 taps: one 130-row tile starting one row early
     if (sh.w_resident) {
       const int n0 = my_group * sh.BN;
       const uint32_t wb = smem_u32(w_all_bar);
@@ -380,8 +383,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
                            tmem_empty_bar, t_first, t_end, t_step, tr_n, tr_role, lane)
     if (kPAIR) {
       if (cta_rank == 0) {   // rank 0 issues for both CTAs
-        if (sh.taps == 3) DHG_MMA_LOOP_PAIR(3); else DHG_MMA_LOOP_PAIR(1);
+        if (kSIO) { if (sh.taps == 6) DHG_MMA_LOOP_PAIR(6); else DHG_MMA_LOOP_PAIR(2); }
+        else if (sh.taps == 3) DHG_MMA_LOOP_PAIR(3); else DHG_MMA_LOOP_PAIR(1);
       }
+    } else if (kSIO) {   // split I/O: 2 slabs per row shift (hi+lo against w_hi, hi against w_lo); no interleaving (G = 1)
+      if (sh.taps == 6) DHG_MMA_LOOP(6, 1); else DHG_MMA_LOOP(2, 1);
     } else if (sh.taps == 3) {
       if (sh.G == 4) DHG_MMA_LOOP(3, 4); else if (sh.G == 2) DHG_MMA_LOOP(3, 2); else DHG_MMA_LOOP(3, 1);
     } else {
@@ -407,13 +413,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     const uint32_t bias_sa = smem_u32(bias_s), gamma_sa = smem_u32(gamma_s), betap_sa = smem_u32(betap_s);
     float2* ln_s = reinterpret_cast<float2*>(smem + sh.off_ln);   // [2 parity][128 rows][EPI_PARTS (x2 in split mode)] {mean, M2} of each column part
     const int aux_ncols = aux_kind == AUX_ROWBIAS ? e.rowbias16_cols : 0x7fffffff;   // aux only for columns below this
-    constexpr int aux_depth = AUX_DEPTH;
-    constexpr uint32_t aux_slot_bytes = AUX_SLOT_BYTES;
+    // split I/O: a 32-column chunk of bfs elements is 128 bytes per row: slots twice as large, half as many
+    constexpr int aux_depth = kSIO ? AUX_DEPTH / 2 : AUX_DEPTH;
+    constexpr uint32_t aux_slot_bytes = kSIO ? 2 * AUX_SLOT_BYTES : AUX_SLOT_BYTES;
+    constexpr int esz = kSIO ? 4 : 2;   // bytes per activation element
     const char* aux_base = nullptr;
     size_t aux_pitch_bytes = 0;
-    if (aux_kind == AUX_RES_PRE) { aux_base = (const char*)e.res_pre; aux_pitch_bytes = (size_t)e.res_pre_pitch * 2; }
-    else if (aux_kind == AUX_RES_POST || aux_kind == AUX_RES_POST_UP) { aux_base = (const char*)e.res_post; aux_pitch_bytes = (size_t)e.res_post_pitch * 2; }
-    else if (aux_kind == AUX_ROWBIAS) { aux_base = (const char*)e.rowbias16; aux_pitch_bytes = (size_t)e.rowbias16_cols * 2; }
+    if (aux_kind == AUX_RES_PRE) { aux_base = (const char*)e.res_pre; aux_pitch_bytes = (size_t)e.res_pre_pitch * esz; }
+    else if (aux_kind == AUX_RES_POST || aux_kind == AUX_RES_POST_UP) { aux_base = (const char*)e.res_post; aux_pitch_bytes = (size_t)e.res_post_pitch * esz; }
+    else if (aux_kind == AUX_ROWBIAS) { aux_base = (const char*)e.rowbias16; aux_pitch_bytes = (size_t)e.rowbias16_cols * esz; }
     const bool aux_in_pass1 = ln && aux_kind == AUX_RES_PRE;
     const int r_tile = q * 32 + lane;   // my accumulator row inside the tile
     const uint32_t lane_sel = ((uint32_t)(q * 32)) << 16;
@@ -457,7 +465,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         const int aux_src = iss_src, fng = iss_ng;
         const int col0 = fng * sh.BN + (c_lo + ci) * 32;
         const uint32_t slot = aux_ring + (f % (uint32_t)aux_depth) * aux_slot_bytes;
-        if (aux_same_row) {   // residual rows = my own rows: lane -> (row, 16-byte piece) directly
+        if (kSIO) {   // 32 rows x 128 bytes: lane -> (row, one of 8 16-byte pieces), 128B-row xor swizzle
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + (lane >> 3), piece = lane & 7;
+            int src;
+            if (aux_same_row) { src = iss_row0 + rr; if (src >= sh.rows) src = -1; }
+            else src = __shfl_sync(0xffffffffu, aux_src, rr);
+            if (aux_same_row || !aux_col_limited || col0 < aux_ncols) {
+              const char* gp = aux_base + (size_t)(src < 0 ? 0 : src) * aux_pitch_bytes + (size_t)col0 * 4 + piece * 16;
+              cp_async16(slot + rr * 128 + ((piece ^ (rr & 7)) << 4), gp, src < 0 ? 0u : 16u);
+            }
+          }
+        } else if (aux_same_row) {   // residual rows = my own rows: lane -> (row, 16-byte piece) directly
           const char* gp0 = aux_base + (size_t)col0 * 2 + (lane & 3) * 16;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -484,11 +504,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     };
     // wait for the oldest aux chunk, add my row of it to v, refill its slot with the next flat chunk
     auto consume_aux = [&](float* v, int col0) {
-      cp_async_wait<AUX_DEPTH - 1>();
+      cp_async_wait<aux_depth - 1>();
       __syncwarp();
       const uint32_t slot = aux_ring + (aux_consumed % (uint32_t)aux_depth) * aux_slot_bytes;
       ++aux_consumed;
-      if (!aux_col_limited || col0 < aux_ncols) {
+      if (kSIO) {
+        if (!aux_col_limited || col0 < aux_ncols) {
+#pragma unroll
+          for (int p = 0; p < 8; ++p) {
+            const uint4 u = lds128_v(slot + (uint32_t)lane * 128u + (uint32_t)((p ^ (lane & 7)) << 4));
+            v[p * 4] += split_unpack(u.x); v[p * 4 + 1] += split_unpack(u.y);
+            v[p * 4 + 2] += split_unpack(u.z); v[p * 4 + 3] += split_unpack(u.w);
+          }
+        }
+      } else if (!aux_col_limited || col0 < aux_ncols) {
         uint4 u[4];
 #pragma unroll
         for (int p = 0; p < 4; ++p) u[p] = lds128_v(slot + st_row + ((p ^ st_sw) << 4));
@@ -534,6 +563,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       // (the buffer store k+1 will use); the other lanes learn about it through the next warp barrier they pass:
       // the one in front of the next chunk's tcgen05.ld, or `sync_first` for a second store of the same chunk.
       auto store_chunk = [&](const CUtensorMap* omap, int col0, const float* v, bool act, bool sync_first) {
+        if (kSIO) {   // 32 rows x 32 bfs = one 4 KB SWIZZLE_128B tile (the warp's whole staging area), exact SiLU
+          if (sync_first) __syncwarp();
+#pragma unroll
+          for (int p = 0; p < 8; ++p) {
+            uint32_t w[4];
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) {
+              const float a = v[p * 4 + k2];
+              w[k2] = split_pack(act ? silu_f(a) : a);
+            }
+            sts128(out_st + (uint32_t)lane * 128u + (uint32_t)((p ^ (lane & 7)) << 4), make_uint4(w[0], w[1], w[2], w[3]));
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(omap, out_st, col0 * 2, m0 + q * 32);
+            bulk_commit();
+            bulk_wait_read<0>();
+          }
+          return;
+        }
         const uint32_t buf = out_st + ((st_flip && sh.out_bufs == 2) ? 2048u : 0u);
         st_flip ^= 1u;
         if (sync_first) __syncwarp();
@@ -776,6 +826,8 @@ static const TcKernEntry kTcKernels[] = {
     DHG_TC_KL(AUX_RES_PRE, 1, 2),       // text-style mha.dense
     {-1, -1, -1, -1, tc_gemm_kernel<-1, -1, -1, -1, false>, tc_gemm_kernel<-1, -1, -1, -1, true>, tc_gemm_kernel<-1, -1, -1, -1, false, true>},   // generic
 };
+// split I/O (fp32-contract mode): the generic instance only, plain and CTA pair
+static const TcKernFn kTcKernelsSio[2] = {tc_gemm_kernel<-1, -1, -1, -1, false, false, true>, tc_gemm_kernel<-1, -1, -1, -1, true, false, true>};
 static TcKernFn pick_kernel(int ln, int aux, int film, int out, int cluster_mode) {   // 0 plain, 1 CTA pair, 2 column-split LayerNorm
   const int n = (int)(sizeof(kTcKernels) / sizeof(kTcKernels[0]));
   auto of = [&](const TcKernEntry& k) { return cluster_mode == 2 ? k.fn_split : cluster_mode == 1 ? k.fn_pair : k.fn; };
@@ -800,13 +852,16 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
                                 char* err, int errlen, const TcTune* tune) {
   const TcTune tn = tune ? *tune : g_tune_default;
   if (rows >= (1 << 24)) { snprintf(err, errlen, "rows = %d: the epilogue's row arithmetic needs rows < 2^24 (plan a smaller chunk)", rows); return nullptr; }
-  if (rows <= 0 || K % 8 || N % 32 || (taps != 1 && taps != 3)) {
-    snprintf(err, errlen, "unsupported shape rows=%d K=%d N=%d taps=%d", rows, K, N, taps);
+  const bool sio = e.split_io != 0;   // K, lda in bf16 units (2 per activation element), taps = 2 weight slabs per row shift
+  if (rows <= 0 || K % 8 || N % 32 || (!sio && taps != 1 && taps != 3) || (sio && taps != 2 && taps != 6)) {
+    snprintf(err, errlen, "unsupported shape rows=%d K=%d N=%d taps=%d%s", rows, K, N, taps, sio ? " (split I/O)" : "");
     return nullptr;
   }
+  const int base_taps = taps % 3 == 0 ? 3 : 1;
   int BN = 0;
   // pair == 2: column-split LayerNorm, a 2-CTA cluster per row tile, each CTA accumulates N/2 columns double-buffered
   const bool split = tn.pair == 2;
+  if (split && sio) { snprintf(err, errlen, "column-split LayerNorm is not built for split I/O"); return nullptr; }
   if (split && !(e.ln && N % 128 == 0 && N / 2 <= 256)) { snprintf(err, errlen, "column-split mode does not fit: it needs a LayerNorm epilogue with N = 128, 256 or 384 (N=%d)", N); return nullptr; }
   if (e.ln) {
     if (!((N <= 256 && N >= 64) || N == 384)) { snprintf(err, errlen, "LayerNorm epilogue needs 64 <= N <= 256 or N == 384, got %d", N); return nullptr; }
@@ -820,6 +875,7 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
     }
   }
   const bool dot = e.dot_planned || e.dot_w != nullptr;
+  if (dot && sio) { snprintf(err, errlen, "dot mode is not built for split I/O"); return nullptr; }
   if (dot && (e.ln || e.out_raw || e.out_act || N > 256 || !e.dot_out)) { snprintf(err, errlen, "dot mode needs N <= 256, no LayerNorm, no stored outputs and a dot_out buffer"); return nullptr; }
   if (dot) {
     if (tn.bn > 0 && tn.bn != N) { snprintf(err, errlen, "dot mode does not fit a tile width below N"); return nullptr; }
@@ -846,6 +902,7 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   p->pdl = g_opt_pdl;
   TcShape& sh = p->sh;
   sh.rows = rows; sh.K = K; sh.N = N; sh.taps = taps; sh.BN = BN;
+  sh.base_taps = base_taps; sh.sio = sio ? 1 : 0;
   sh.n_groups = N / BN;
   const int m_tiles = (rows + TC_BM - 1) / TC_BM;
   sh.m_tiles = m_tiles;
@@ -864,7 +921,8 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   sh.film_n = e.film_planned ? N : 0;
   // independent accumulators per super-tile: as many as fit in one 256-column TMEM group, at most 4
   int G = 1;
-  if (g_opt_interleave && BN <= 128 && !split) G = BN <= 64 ? 4 : 2;
+  if (g_opt_interleave && BN <= 128 && !split && !sio) G = BN <= 64 ? 4 : 2;
+  if (sio && tn.g > 1) { snprintf(err, errlen, "split I/O does not fit interleaved accumulators"); delete p; return nullptr; }
   if (split && tn.g > 1) { snprintf(err, errlen, "column-split mode does not fit interleaved accumulators"); delete p; return nullptr; }
   if (tn.g > 0) {
     if ((tn.g != 1 && tn.g != 2 && tn.g != 4) || (tn.g > 1 && tn.g * BN > 256)) { snprintf(err, errlen, "%d interleaved accumulators of %d columns do not fit a 256-column TMEM group", tn.g, BN); delete p; return nullptr; }
@@ -873,7 +931,7 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   while (G > 1 && (m_tiles + G - 1) / G * sh.n_groups < num_sms) G >>= 1;   // keep every SM busy on small problems
   sh.G = G;
   sh.m_super = (m_tiles + G - 1) / G;
-  const int a_rows = taps == 3 ? TC_BM + 2 : TC_BM;
+  const int a_rows = base_taps == 3 ? TC_BM + 2 : TC_BM;
   sh.a_tx_bytes = (uint32_t)a_rows * TC_BK * 2;
   sh.a_stage_bytes = (sh.a_tx_bytes + 1023u) & ~1023u;
   sh.w_tile_bytes = (uint32_t)BN * TC_BK * 2;
@@ -885,7 +943,7 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
                  (size_t)(sh.vec_bias_n + 2 * sh.film_n + sh.dot_n) * 4 + 16 + ln_bytes + 64 * 8;
   size_t budget = 227 * 1024 - 1024 - fixed;
   sh.out_bufs = OUT_STAGE_BYTES >= 4096 ? 2 : 1;
-  if (sh.out_bufs == 2 && 2 * (size_t)(sh.a_stage_bytes + BN * TC_BK * 2) > budget) {   // not even two A + two W stages: give up the second store tile
+  if (sh.out_bufs == 2 && !sio && 2 * (size_t)(sh.a_stage_bytes + BN * TC_BK * 2) > budget) {   // not even two A + two W stages: give up the second store tile
     sh.out_bufs = 1;
     fixed -= (size_t)EPI_WARPS * OUT_STAGE_BYTES / 2;
     budget += (size_t)EPI_WARPS * OUT_STAGE_BYTES / 2;
@@ -966,8 +1024,11 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   }
   // output tensor maps: [32 rows x 32 columns] SWIZZLE_64B boxes for the epilogue's TMA stores
   p->map_oraw = p->map_a; p->map_oact = p->map_a;   // placeholders for absent outputs (never used)
-  if ((e.out_raw && !make_map(&p->map_oraw, e.out_raw, (uint64_t)rows, (uint64_t)N, (uint64_t)e.out_raw_pitch, 32, err, errlen, 32)) ||
-      (e.out_act && !make_map(&p->map_oact, e.out_act, (uint64_t)rows, (uint64_t)N, (uint64_t)e.out_act_pitch, 32, err, errlen, 32))) {
+  // (split I/O: a row of N bfs elements is 2N bf16; [32 rows x 64 bf16] SWIZZLE_128B boxes)
+  const uint64_t om = sio ? 2 : 1;
+  const uint32_t obox = sio ? 64 : 32;
+  if ((e.out_raw && !make_map(&p->map_oraw, e.out_raw, (uint64_t)rows, om * N, om * e.out_raw_pitch, 32, err, errlen, obox)) ||
+      (e.out_act && !make_map(&p->map_oact, e.out_act, (uint64_t)rows, om * N, om * e.out_act_pitch, 32, err, errlen, obox))) {
     delete p;
     return nullptr;
   }
@@ -976,6 +1037,7 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   p->fn_shared = e.bias ? pick_kernel(e.ln ? 1 : 0, aux_kind, e.film_planned ? 1 : 0, out_mode, cluster_mode)
                         : pick_kernel(-1, -1, -1, -1, cluster_mode);   // the specialised variants assume a bias vector
   p->fn_generic = pick_kernel(-1, -1, -1, -1, cluster_mode);
+  if (sio) p->fn_shared = p->fn_generic = kTcKernelsSio[sh.pair ? 1 : 0];
   for (TcKernFn fn : {p->fn_shared, p->fn_generic}) {
     cudaError_t ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (ce != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); delete p; return nullptr; }

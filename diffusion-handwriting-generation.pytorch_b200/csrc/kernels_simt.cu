@@ -336,6 +336,7 @@ int launch_attention_simt(const AttnParams& p, cudaStream_t st) {
 }
 template int launch_attention_simt<float>(const AttnParams&, cudaStream_t);
 template int launch_attention_simt<bf16>(const AttnParams&, cudaStream_t);
+template int launch_attention_simt<bfs>(const AttnParams&, cudaStream_t);
 
 // ---------------------------------------------------------------------------
 // FiLM over rows: out[r, c] = in[r, c] * gamma[b, c] + beta[b, c]   (conditioning.py:19)
@@ -372,6 +373,7 @@ void launch_film_rows(const T* in, T* out, int rows, int C, int period, const fl
 }
 template void launch_film_rows<float>(const float*, float*, int, int, int, const float*, const float*, int, cudaStream_t);
 template void launch_film_rows<bf16>(const bf16*, bf16*, int, int, int, const float*, const float*, int, cudaStream_t);
+template void launch_film_rows<bfs>(const bfs*, bfs*, int, int, int, const float*, const float*, int, cudaStream_t);
 
 // ---------------------------------------------------------------------------
 // AvgPool1d(2) over T in the padded row layout (model.py:93): level l -> l+1.
@@ -409,6 +411,7 @@ void launch_pool(const T* in, T* out_raw, T* out_act, int B, int Tlo, int C, cud
 }
 template void launch_pool<float>(const float*, float*, float*, int, int, int, cudaStream_t);
 template void launch_pool<bf16>(const bf16*, bf16*, bf16*, int, int, int, cudaStream_t);
+template void launch_pool<bfs>(const bfs*, bfs*, bfs*, int, int, int, cudaStream_t);
 
 // ---------------------------------------------------------------------------
 // input_dense: Linear(2, C) on the fp32 strokes (model.py:82,139) -> padded rows,
@@ -440,6 +443,7 @@ void launch_input_dense(const float* x, const float* W, const float* bias, T* ou
 }
 template void launch_input_dense<float>(const float*, const float*, const float*, float*, float*, int, int, int, cudaStream_t);
 template void launch_input_dense<bf16>(const float*, const float*, const float*, bf16*, bf16*, int, int, int, cudaStream_t);
+template void launch_input_dense<bfs>(const float*, const float*, const float*, bfs*, bfs*, int, int, int, cudaStream_t);
 
 // ---------------------------------------------------------------------------
 // Head fusion: enc1.conv_skip(input_dense(x)) straight from x.  input_dense is linear (model.py:139) and conv_skip
@@ -756,6 +760,7 @@ int launch_heads_update(const T* h, int C, const float* Wo, const float* bo, con
 }
 template int launch_heads_update<float>(const float*, int, const float*, const float*, const float*, const float*, const HeadParams&, cudaStream_t);
 template int launch_heads_update<bf16>(const bf16*, int, const float*, const float*, const float*, const float*, const HeadParams&, cudaStream_t);
+template int launch_heads_update<bfs>(const bfs*, int, const float*, const float*, const float*, const float*, const HeadParams&, cudaStream_t);
 
 // ---------------------------------------------------------------------------
 // Standalone posterior update (drop-in for utils/nn.py:64-112 with injected z):
@@ -888,6 +893,7 @@ void launch_embed_ln(const int64_t* ids, const float* emb, int vocab, int C, T* 
 }
 template void launch_embed_ln<float>(const int64_t*, const float*, int, int, float*, int, int*, cudaStream_t);
 template void launch_embed_ln<bf16>(const int64_t*, const float*, int, int, bf16*, int, int*, cudaStream_t);
+template void launch_embed_ln<bfs>(const int64_t*, const float*, int, int, bfs*, int, int*, cudaStream_t);
 
 // SiLU + dtype conversion over a flat fp32 array (style vector -> style_ffn input;
 // reshape_up(style, 5) is a pure reinterpretation of the contiguous buffer).
@@ -905,5 +911,6 @@ void launch_silu_convert(const float* in, T* out, size_t n, cudaStream_t st) {
 }
 template void launch_silu_convert<float>(const float*, float*, size_t, cudaStream_t);
 template void launch_silu_convert<bf16>(const float*, bf16*, size_t, cudaStream_t);
+template void launch_silu_convert<bfs>(const float*, bfs*, size_t, cudaStream_t);
 
 }  // namespace dhg
