@@ -35,6 +35,7 @@
 #include <functional>
 #include <map>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/dhg_b200.h"
@@ -91,6 +92,8 @@ struct Lin {
   float* w32 = nullptr;   // [taps][K][N] exact fp32               (fp32 mode, CUDA-core GEMM)
   float* w32r = nullptr;  // [taps][K][N] bf16-rounded, as fp32    (bf16 mode, CUDA-core GEMM)
   bf16* w16 = nullptr;    // [taps][N][K] bf16, K contiguous       (bf16 mode, tcgen05 GEMM)
+  bf16* w16s = nullptr;   // [2 taps][N][2K] bf16: slab `tap` = (w_hi, w_hi) interleaved along K, slab `taps + tap` =
+                          // (w_lo, 0) interleaved, w = w_hi + w_lo  (fp32 mode on tcgen05: split storage, common.cuh bfs)
   float* bias = nullptr;  // [N]
   std::vector<float> h_w;  // host copy [taps][K][N] (for PE-folded bias tables)
   std::vector<float> h_b;
@@ -117,6 +120,15 @@ struct Act {
   int rows = 0, C = 0;
 };
 
+// Activation storage of a plan -> element type of the CUDA-core kernels: fp32, bf16, or the bfs split pairs.
+template <typename F>
+inline auto by_storage(int prec, bool split, F&& f) {
+  if (prec == PREC_BF16) return f((bf16*)nullptr);
+  if (split) return f((bfs*)nullptr);
+  return f((float*)nullptr);
+}
+#define DHG_STORAGE(Pl, T, ...) by_storage((Pl)->prec, (Pl)->split, [&](auto* tag_) { using T = std::remove_pointer_t<decltype(tag_)>; __VA_ARGS__ })
+
 struct EpiSpec {
   bool bias = true;
   const float* rowbias = nullptr;
@@ -139,6 +151,9 @@ struct EpiSpec {
 
 struct Plan {
   int B = 0, T = 0, L = 0, S = 0, SP = 0, prec = 0, gemm_impl = 0;
+  bool split = false;   // fp32 precision on the tensor cores: activations stored as bfs pairs (common.cuh), every GEMM as two
+                        // bf16 tcgen05 GEMMs over the split row (hi + lo against w_hi, hi against w_lo), fp32 accumulate
+  bool tc() const { return gemm_impl == 1; }   // GEMMs run on tcgen05 (bf16 storage, or split storage in fp32 precision)
   int Tl[4], R[4], RT = 0, RS = 0;
   size_t esize = 4;
   std::vector<void*> allocs;
@@ -352,6 +367,20 @@ int make_lin(dhg_ctx* c, const std::string& key, const std::vector<std::string>&
   if (dev_upload(c->allocs, &L.bias, L.h_b)) return 1;
   if (dev_alloc(c->allocs, (void**)&L.w16, w16.size() * sizeof(bf16))) return 1;
   CUDA_OK(cudaMemcpy(L.w16, w16.data(), w16.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+  {
+    std::vector<bf16> ws((size_t)2 * L.taps * N * 2 * K);
+    for (int t = 0; t < L.taps; ++t)
+      for (int n = 0; n < N; ++n)
+        for (int k = 0; k < K; ++k) {
+          const float v = L.h_w[((size_t)t * K + k) * N + n];
+          const bf16 hi = __float2bfloat16_rn(v), lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+          const size_t a = (((size_t)t * N + n) * K + k) * 2, b = (((size_t)(L.taps + t) * N + n) * K + k) * 2;
+          ws[a] = hi; ws[a + 1] = hi;
+          ws[b] = lo; ws[b + 1] = __float2bfloat16_rn(0.f);
+        }
+    if (dev_alloc(c->allocs, (void**)&L.w16s, ws.size() * sizeof(bf16))) return 1;
+    CUDA_OK(cudaMemcpy(L.w16s, ws.data(), ws.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+  }
   c->lins[key] = std::move(L);
   return 0;
 }
@@ -417,7 +446,18 @@ int make_rowbias(Plan* P, const Lin& W, const std::vector<float>& pe, int len, i
     }
   if (dev_alloc(P->allocs, (void**)out, t.size() * sizeof(float), &P->bytes)) return 1;
   CUDA_OK(cudaMemcpy(*out, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
-  if (out16) {   // bf16 [len, n_pe1 - n_pe0] table of the positional term alone (the bias stays an fp32 vector)
+  if (out16 && P->split) {   // the same table as bfs split pairs (hi in the low half-word, common.cuh)
+    const int cols = n_pe1 - n_pe0;
+    std::vector<uint32_t> ts((size_t)len * cols);
+    for (int i = 0; i < len; ++i)
+      for (int n = 0; n < cols; ++n) {
+        const float v = t[(size_t)i * W.N + n_pe0 + n] - W.h_b[n_pe0 + n];
+        const bf16 hi = __float2bfloat16_rn(v), lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        ts[(size_t)i * cols + n] = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+      }
+    if (dev_alloc(P->allocs, out16, ts.size() * sizeof(uint32_t), &P->bytes)) return 1;
+    CUDA_OK(cudaMemcpy(*out16, ts.data(), ts.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  } else if (out16) {   // bf16 [len, n_pe1 - n_pe0] table of the positional term alone (the bias stays an fp32 vector)
     const int cols = n_pe1 - n_pe0;
     std::vector<bf16> t16((size_t)len * cols);
     for (int i = 0; i < len; ++i)
@@ -466,9 +506,8 @@ struct Builder {
   // Time the launch under every tile configuration the kernel supports for this shape (tile width, interleaved
   // accumulators, resident or streamed W, CTA pairs) on the plan's own buffers and keep the fastest.  All configurations
   // compute the same bits (kernels.h TcTune), so this only moves time.  `base` is the plan of the built-in rule.
-  TcGemmPlan* autotune(TcGemmPlan* base, const bf16* Ap, int lda, int rows, const Lin* W, const Epilogue& e, const Epilogue& et,
-                       const std::string& wkey) {
-    const int N = W->N;
+  TcGemmPlan* autotune(TcGemmPlan* base, const bf16* Ap, int lda, int rows, const bf16* Wp, int K, int N, int taps, const Epilogue& e,
+                       const Epilogue& et, const std::string& wkey) {
     cudaStream_t st = P->cap_stream;
     cudaEvent_t e0, e1;
     if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { fail("autotune: event"); tc_gemm_plan_destroy(base); return nullptr; }
@@ -509,7 +548,8 @@ struct Builder {
           if (mode >= 3 && !e.ln) continue;
           TcTune t{bn, g, (mode == 0 || mode == 3) ? 1 : 0, mode == 2 ? 1 : mode >= 3 ? 2 : 0};
           char buf[256];
-          TcGemmPlan* p = tc_gemm_plan_create(Ap, lda, rows, W->w16, W->K, N, W->taps, e, buf, sizeof(buf), &t);
+          if (e.split_io && (g != 1 || mode >= 3)) continue;   // split I/O: no interleaved accumulators, no column-split cluster
+          TcGemmPlan* p = tc_gemm_plan_create(Ap, lda, rows, Wp, K, N, taps, e, buf, sizeof(buf), &t);
           if (!p) continue;   // configuration not available for this shape
           TcTune got;
           tc_gemm_plan_config(p, &got);
@@ -536,7 +576,7 @@ struct Builder {
     }
     if (getenv("DHG_DESCRIBE"))
       fprintf(stderr, "autotune %-28s rows=%d K=%d N=%d taps=%d: rule {bn=%d g=%d res=%d pair=%d} %.1f us -> {bn=%d g=%d res=%d pair=%d} %.1f us (%zu tried)\n",
-              wkey.c_str(), rows, W->K, N, W->taps, cfg0.bn, cfg0.g, cfg0.resident, cfg0.pair, t0 * 1e3f, best_cfg.bn, best_cfg.g,
+              wkey.c_str(), rows, K, N, taps, cfg0.bn, cfg0.g, cfg0.resident, cfg0.pair, t0 * 1e3f, best_cfg.bn, best_cfg.g,
               best_cfg.resident, best_cfg.pair, best * 1e3f, seen.size());
     return best_plan;
   }
@@ -549,7 +589,9 @@ struct Builder {
     if (A.C != W->K) { fail("plan: gemm %s K mismatch (%d vs %d)", wkey.c_str(), A.C, W->K); failed = true; return; }
     Epilogue e;
     memset(&e, 0, sizeof(e));
-    const bool tc_path = P->prec == PREC_BF16 && P->gemm_impl == 1;
+    const bool tc_path = P->tc();
+    const bool sio = tc_path && P->split;
+    e.split_io = sio ? 1 : 0;
     e.bias = (s.bias && (tc_path || !s.rowbias)) ? W->bias : nullptr;
     e.rowbias = tc_path ? nullptr : s.rowbias;
     e.rowbias16 = tc_path ? s.rowbias16 : nullptr;
@@ -569,14 +611,17 @@ struct Builder {
     size_t need = (size_t)rows * N;
     if (need > P->scratch_elems) P->scratch_elems = need;
     TcGemmPlan* tcp = nullptr;
-    if (P->prec == PREC_BF16 && P->gemm_impl == 1) {
+    // tcgen05 operands: split storage is a bf16 row of 2 K columns against 2 weight slabs per tap
+    const bf16* Wp = sio ? W->w16s : W->w16;
+    const int Kt = sio ? 2 * K : K, ldt = sio ? 2 * A.C : A.C, tapst = sio ? 2 * taps : taps;
+    if (tc_path) {
       char buf[512];
-      tcp = tc_gemm_plan_create((const bf16*)Ap, A.C, rows, W->w16, K, N, taps, e, buf, sizeof(buf));
+      tcp = tc_gemm_plan_create((const bf16*)Ap, ldt, rows, Wp, Kt, N, tapst, e, buf, sizeof(buf));
       if (!tcp) { fail("plan: tcgen05 gemm %s: %s", wkey.c_str(), buf); failed = true; return; }
       if (g_opt_autotune) {
         Epilogue et = e;
         if (film_off >= 0) { et.gamma = c->cond60 + film_off; et.beta = c->cond60 + film_off + N; et.film_bstride = 0; }
-        tcp = autotune(tcp, (const bf16*)Ap, A.C, rows, W, e, et, wkey);
+        tcp = autotune(tcp, (const bf16*)Ap, ldt, rows, Wp, Kt, N, tapst, e, et, wkey);
         if (!tcp) { failed = true; return; }
       }
       const int dir = g_opt_serpentine ? !dir_of(Ap) : 0;
@@ -610,7 +655,7 @@ struct Builder {
       if (g_opt_autotune) {
         Epilogue et = e_alt;
         if (film_off >= 0) { et.gamma = c->cond60 + film_off; et.beta = c->cond60 + film_off + Na; et.film_bstride = 0; }
-        tcp_alt = autotune(tcp_alt, (const bf16*)Ap, A.C, rows, Wa, e_alt, et, wkey + " (dot)");
+        tcp_alt = autotune(tcp_alt, (const bf16*)Ap, A.C, rows, Wa->w16, K, Na, taps, e_alt, et, wkey + " (dot)");
         if (!tcp_alt) { failed = true; return; }
       }
       tc_gemm_plan_set_reverse(tcp_alt, g_opt_serpentine ? !dir_of(Ap) : 0);
@@ -642,7 +687,7 @@ struct Builder {
         ee.film_bstride = sc.bstride;
       }
       if (tcp) return tc_gemm_launch(tcp, ee, st) ? fail("tcgen05 gemm launch failed: %s", cudaGetErrorString(cudaGetLastError())) : 0;
-      if (Pl->prec == PREC_FP32) {
+      if (Pl->prec == PREC_FP32) {   // (never split storage: that only exists on the tcgen05 path)
         launch_gemm_simt<float>((const float*)Ap, K, rows, W->w32, K, N, taps, Pl->scratch, st);
         launch_rowpost<float>(Pl->scratch, rows, N, ee, st);
       } else {
@@ -714,7 +759,7 @@ struct Builder {
     ops->push_back([=](cudaStream_t st, const StepCtx& sc) -> int {
       const int set = (sc.text_set >= 0 && sc.text_set < nsets) ? sc.text_set : 0;
       if (tc) return attn_tc_launch(plans[set], st) ? fail("tcgen05 attention launch failed: %s", cudaGetErrorString(cudaGetLastError())) : 0;
-      const int r = Pl->prec == PREC_FP32 ? launch_attention_simt<float>(a[set], st) : launch_attention_simt<bf16>(a[set], st);
+      const int r = DHG_STORAGE(Pl, T, return launch_attention_simt<T>(a[set], st););
       return r ? fail("attention: unsupported head depth %d", a[set].D) : 0;
     });
   }
@@ -730,10 +775,7 @@ struct Builder {
     ops->push_back([=](cudaStream_t st, const StepCtx& sc) -> int {
       const float* g = sc.cond + film_off;
       const float* b = sc.cond + film_off + in.C;
-      if (Pl->prec == PREC_FP32)
-        launch_film_rows<float>((const float*)in.p, (float*)out.p, in.rows, in.C, period, g, b, sc.bstride, st);
-      else
-        launch_film_rows<bf16>((const bf16*)in.p, (bf16*)out.p, in.rows, in.C, period, g, b, sc.bstride, st);
+      DHG_STORAGE(Pl, T, launch_film_rows<T>((const T*)in.p, (T*)out.p, in.rows, in.C, period, g, b, sc.bstride, st););
       return 0;
     });
   }
@@ -743,10 +785,7 @@ struct Builder {
     Plan* Pl = P;
     *nlaunch += 1;
     ops->push_back([=](cudaStream_t st, const StepCtx&) -> int {
-      if (Pl->prec == PREC_FP32)
-        launch_pool<float>((const float*)in.p, (float*)out_raw.p, (float*)out_act.p, Pl->B, Tlo, in.C, st);
-      else
-        launch_pool<bf16>((const bf16*)in.p, (bf16*)out_raw.p, (bf16*)out_act.p, Pl->B, Tlo, in.C, st);
+      DHG_STORAGE(Pl, T, launch_pool<T>((const T*)in.p, (T*)out_raw.p, (T*)out_act.p, Pl->B, Tlo, in.C, st););
       return 0;
     });
   }
@@ -880,13 +919,9 @@ int build_plan(dhg_ctx* c, Plan* P) {
     P->launches_once += 2;
     P->once_ops.push_back([=](cudaStream_t st, const StepCtx&) -> int {
       const size_t n = (size_t)Pl->B * Pl->S * kStyleWidth;
-      if (Pl->prec == PREC_FP32) {
-        launch_silu_convert<float>(Pl->style, (float*)style_act.p, n, st);
-        launch_embed_ln<float>(Pl->text, c->emb, kVocab, t0.C, (float*)t0.p, Pl->RT, Pl->err_flag, st);
-      } else {
-        launch_silu_convert<bf16>(Pl->style, (bf16*)style_act.p, n, st);
-        launch_embed_ln<bf16>(Pl->text, c->emb, kVocab, t0.C, (bf16*)t0.p, Pl->RT, Pl->err_flag, st);
-      }
+      DHG_STORAGE(Pl, T,
+                  launch_silu_convert<T>(Pl->style, (T*)style_act.p, n, st);
+                  launch_embed_ln<T>(Pl->text, c->emb, kVocab, t0.C, (T*)t0.p, Pl->RT, Pl->err_flag, st););
       return 0;
     });
   }
@@ -901,7 +936,7 @@ int build_plan(dhg_ctx* c, Plan* P) {
   for (int i = 0; i < c->cfg.num_layers; ++i) enc_names.push_back("att_layers." + std::to_string(i));
   // several sets (and streams) only where every text-side launch is a self-contained tcgen05 kernel: the CUDA-core
   // GEMM path shares one fp32 scratch buffer between launches and must stay serial
-  P->text_sets = (P->prec == PREC_BF16 && P->gemm_impl == 1) ? std::min(std::max(g_opt_text_sets, 1), kMaxTextSets) : 1;
+  P->text_sets = P->tc() ? std::min(std::max(g_opt_text_sets, 1), kMaxTextSets) : 1;
   if (P->text_sets > 1) {
     CUDA_OK(cudaEventCreateWithFlags(&P->ev_fork, cudaEventDisableTiming));
     for (int i = 1; i < P->text_sets; ++i) {
@@ -943,10 +978,7 @@ int build_plan(dhg_ctx* c, Plan* P) {
     P->step_ops.push_back([=](cudaStream_t st, const StepCtx& sc) -> int {
       if (sc.skip_input_dense) return 0;
       const float* x = sc.head.x_io ? sc.head.x_io : Pl->x_state;
-      if (Pl->prec == PREC_FP32)
-        launch_input_dense<float>(x, c->in_W, c->in_b, (float*)in_raw.p, (float*)in_act.p, Pl->B, Pl->T, in_raw.C, st);
-      else
-        launch_input_dense<bf16>(x, c->in_W, c->in_b, (bf16*)in_raw.p, (bf16*)in_act.p, Pl->B, Pl->T, in_raw.C, st);
+      DHG_STORAGE(Pl, T, launch_input_dense<T>(x, c->in_W, c->in_b, (T*)in_raw.p, (T*)in_act.p, Pl->B, Pl->T, in_raw.C, st););
       return 0;
     });
   }
@@ -1022,13 +1054,11 @@ int build_plan(dhg_ctx* c, Plan* P) {
         return launch_heads_update<bf16>((const bf16*)Pl->tail_a2.p, C, A, cc, A + 2 * C, cc + 2, hp, st)
                    ? fail("head kernel: unsupported channel count %d", C) : 0;
       }
-      const int rc = Pl->prec == PREC_FP32
-          ? launch_heads_update<float>((const float*)d1.p, d1.C, c->out_W, c->out_b, c->pen_W, c->pen_b, hp, st)
-          : launch_heads_update<bf16>((const bf16*)d1.p, d1.C, c->out_W, c->out_b, c->pen_W, c->pen_b, hp, st);
+      const int rc = DHG_STORAGE(Pl, T, return launch_heads_update<T>((const T*)d1.p, d1.C, c->out_W, c->out_b, c->pen_W, c->pen_b, hp, st););
       return rc ? fail("head kernel: unsupported channel count %d", d1.C) : 0;
     });
   }
-  if (P->scratch_elems && !(P->prec == PREC_BF16 && P->gemm_impl == 1))
+  if (P->scratch_elems && !P->tc())
     if (dev_alloc(P->allocs, (void**)&P->scratch, P->scratch_elems * sizeof(float), &P->bytes)) return 1;
   return 0;
 }
@@ -1424,7 +1454,8 @@ int32_t dhg_plan(dhg_ctx* c, int32_t B, int32_t T, int32_t L, int32_t S, int32_t
   c->plan = nullptr;
   Plan* P = new Plan();
   P->B = B; P->T = T; P->L = L; P->S = S; P->prec = precision;
-  P->gemm_impl = (precision == DHG_PREC_BF16) ? c->opt_gemm : 0;
+  P->gemm_impl = c->opt_gemm;   // 1: tcgen05 GEMMs (bf16 storage, or split storage in fp32 precision); 0: CUDA-core GEMMs
+  P->split = precision == DHG_PREC_FP32 && P->gemm_impl == 1;
   P->attn_impl = (precision == DHG_PREC_BF16) ? c->opt_attn : 0;
   if (build_plan(c, P)) { free_plan(P); return 1; }
   CUDA_OK(cudaDeviceSynchronize());
@@ -1638,8 +1669,16 @@ int64_t dhg_debug_read(dhg_ctx* c, const char* name, float* host_out, int64_t ca
       const size_t r = (size_t)b * period + pad + t;
       for (int ch = 0; ch < a.C; ++ch) {
         const size_t src = r * a.C + ch;
-        host_out[((size_t)b * per + t) * a.C + ch] =
-            P->esize == 4 ? reinterpret_cast<const float*>(tmp.data())[src] : __bfloat162float(reinterpret_cast<const bf16*>(tmp.data())[src]);
+        float val;
+        if (P->split) {
+          const uint32_t w = reinterpret_cast<const uint32_t*>(tmp.data())[src];
+          uint32_t hi = w << 16, lo = w & 0xffff0000u;
+          float fh, fl;
+          memcpy(&fh, &hi, 4); memcpy(&fl, &lo, 4);
+          val = fh + fl;
+        } else if (P->esize == 4) val = reinterpret_cast<const float*>(tmp.data())[src];
+        else val = __bfloat162float(reinterpret_cast<const bf16*>(tmp.data())[src]);
+        host_out[((size_t)b * per + t) * a.C + ch] = val;
       }
     }
   return n;
@@ -1680,6 +1719,7 @@ int32_t dhg_debug_tc_gemm_ex(int32_t device, const void* a, int32_t lda, int32_t
   e.out_raw = d->out_raw; e.out_raw_pitch = d->out_raw_pitch;
   e.out_act = d->out_act; e.out_act_pitch = d->out_act_pitch;
   e.dot_w = d->dot_w; e.dot_out = d->dot_out; e.dot_act = d->dot_act; e.dot_planned = d->dot_w ? 1 : 0;
+  e.split_io = d->split_io;
   e.map = RowMap{d->period > 0 ? d->period : (rows > 0 ? rows : 1), d->pad_first, d->nvalid > 0 ? d->nvalid : rows};
   char buf[512];
   TcGemmPlan* p = tc_gemm_plan_create((const bf16*)a, lda, rows, (const bf16*)w, K, N, taps, e, buf, sizeof(buf));

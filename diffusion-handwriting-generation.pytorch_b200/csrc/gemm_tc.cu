@@ -563,24 +563,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       // (the buffer store k+1 will use); the other lanes learn about it through the next warp barrier they pass:
       // the one in front of the next chunk's tcgen05.ld, or `sync_first` for a second store of the same chunk.
       auto store_chunk = [&](const CUtensorMap* omap, int col0, const float* v, bool act, bool sync_first) {
-        if (kSIO) {   // 32 rows x 32 bfs = one 4 KB SWIZZLE_128B tile (the warp's whole staging area), exact SiLU
-          if (sync_first) __syncwarp();
+        if (kSIO) {   // 32 bfs per row = 128 bytes: two [32 rows x 32 bf16] SWIZZLE_64B tiles of 16 elements each, exact SiLU
 #pragma unroll
-          for (int p = 0; p < 8; ++p) {
-            uint32_t w[4];
+          for (int half = 0; half < 2; ++half) {
+            const uint32_t buf = out_st + ((st_flip && sh.out_bufs == 2) ? 2048u : 0u);
+            st_flip ^= 1u;
+            if (sync_first || half) __syncwarp();   // lane 0 has waited for this buffer's previous store to be read out
 #pragma unroll
-            for (int k2 = 0; k2 < 4; ++k2) {
-              const float a = v[p * 4 + k2];
-              w[k2] = split_pack(act ? silu_f(a) : a);
+            for (int p = 0; p < 4; ++p) {
+              uint32_t w[4];
+#pragma unroll
+              for (int k2 = 0; k2 < 4; ++k2) {
+                const float a = v[half * 16 + p * 4 + k2];
+                w[k2] = split_pack(act ? silu_f(a) : a);
+              }
+              sts128(buf + st_row + ((p ^ st_sw) << 4), make_uint4(w[0], w[1], w[2], w[3]));
             }
-            sts128(out_st + (uint32_t)lane * 128u + (uint32_t)((p ^ (lane & 7)) << 4), make_uint4(w[0], w[1], w[2], w[3]));
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(omap, out_st, col0 * 2, m0 + q * 32);
-            bulk_commit();
-            bulk_wait_read<0>();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(omap, buf, (col0 + half * 16) * 2, m0 + q * 32);
+              bulk_commit();
+              if (sh.out_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+            }
           }
           return;
         }
@@ -943,7 +948,7 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
                  (size_t)(sh.vec_bias_n + 2 * sh.film_n + sh.dot_n) * 4 + 16 + ln_bytes + 64 * 8;
   size_t budget = 227 * 1024 - 1024 - fixed;
   sh.out_bufs = OUT_STAGE_BYTES >= 4096 ? 2 : 1;
-  if (sh.out_bufs == 2 && !sio && 2 * (size_t)(sh.a_stage_bytes + BN * TC_BK * 2) > budget) {   // not even two A + two W stages: give up the second store tile
+  if (sh.out_bufs == 2 && 2 * (size_t)(sh.a_stage_bytes + BN * TC_BK * 2) > budget) {   // not even two A + two W stages: give up the second store tile
     sh.out_bufs = 1;
     fixed -= (size_t)EPI_WARPS * OUT_STAGE_BYTES / 2;
     budget += (size_t)EPI_WARPS * OUT_STAGE_BYTES / 2;
@@ -1024,9 +1029,9 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   }
   // output tensor maps: [32 rows x 32 columns] SWIZZLE_64B boxes for the epilogue's TMA stores
   p->map_oraw = p->map_a; p->map_oact = p->map_a;   // placeholders for absent outputs (never used)
-  // (split I/O: a row of N bfs elements is 2N bf16; [32 rows x 64 bf16] SWIZZLE_128B boxes)
+  // (split I/O: a row of N bfs elements is 2N bf16; a 32-column chunk leaves as two such boxes)
   const uint64_t om = sio ? 2 : 1;
-  const uint32_t obox = sio ? 64 : 32;
+  const uint32_t obox = 32;
   if ((e.out_raw && !make_map(&p->map_oraw, e.out_raw, (uint64_t)rows, om * N, om * e.out_raw_pitch, 32, err, errlen, obox)) ||
       (e.out_act && !make_map(&p->map_oact, e.out_act, (uint64_t)rows, om * N, om * e.out_act_pitch, 32, err, errlen, obox))) {
     delete p;

@@ -22,7 +22,7 @@ class DebugEpilogue(ctypes.Structure):
         ("gamma", c_vp), ("beta", c_vp), ("film_bstride", c_i32), ("res_post", c_vp), ("res_post_pitch", c_i32),
         ("res_post_up", c_i32), ("res_post_period_lo", c_i32), ("out_raw", c_vp), ("out_raw_pitch", c_i32),
         ("out_act", c_vp), ("out_act_pitch", c_i32), ("period", c_i32), ("pad_first", c_i32), ("nvalid", c_i32),
-        ("dot_w", c_vp), ("dot_out", c_vp), ("dot_act", c_i32),
+        ("dot_w", c_vp), ("dot_out", c_vp), ("dot_act", c_i32), ("split_io", c_i32),
     ]
 
 

@@ -43,8 +43,9 @@ class DiffusionWriter:
             `channels` are given.
         checkpoint_path: `model_final.pth`-style file, or pass `state_dict`.
         device: CUDA device (there is no CPU path).
-        dtype: "bf16" (tcgen05 tensor cores, fp32 accumulate) or "fp32"
-            (CUDA-core fp32; the parity mode).
+        dtype: "bf16" (bf16 storage, tcgen05 tensor cores, fp32 accumulate) or "fp32" (the reference's precision:
+            parity 1e-3 after the chain.  Runs on the tensor cores too, on split bf16 hi/lo storage with three-term
+            products; `gemm=0` selects plain fp32 storage with CUDA-core FMA GEMMs instead).
         chunk: samples per captured chain; larger batches run as several chunks.
     """
 

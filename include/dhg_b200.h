@@ -45,7 +45,10 @@ typedef struct dhg_config {
                          (conditioning.py:9) */
 } dhg_config;
 
-#define DHG_PREC_FP32 0 /* fp32 storage, fp32 CUDA-core accumulate (parity mode) */
+#define DHG_PREC_FP32 0 /* the reference's precision (parity 1e-3 after 60 steps).  Default ("gemm" = 1): tcgen05 tensor cores on
+                           split storage -- every fp32 activation / weight is a {bf16 hi, bf16 lo} pair and every GEMM is
+                           x.w = (hi + lo).w_hi + hi.w_lo in bf16 MMAs with fp32 accumulation (~2^-17 per product), all
+                           epilogue arithmetic in fp32.  "gemm" = 0: plain fp32 storage and CUDA-core fp32 FMA GEMMs. */
 #define DHG_PREC_BF16 1 /* bf16 storage, tcgen05 bf16 MMA, fp32 accumulate/statistics */
 
 #define DHG_MODE_NEW 0      /* utils/nn.py:90-112 new_diffusion_step (inference.py default) */
@@ -137,7 +140,8 @@ int64_t dhg_plan_bytes(const dhg_ctx* ctx);
 /* Engine switches, mainly for tests and A/B measurements.  ALL of them are read when a plan is built (dhg_plan) and
  * stored in it: setting one afterwards has no effect on the current plan, its captured graphs or its launch count.
  * Per context:
- *   "gemm"  0 CUDA-core GEMM + row epilogue kernel, 1 tcgen05 GEMM with fused epilogue (bf16 only; default 1)
+ *   "gemm"  0 CUDA-core GEMM + row epilogue kernel, 1 tcgen05 GEMM with fused epilogue (default 1; in fp32 precision
+ *           1 selects the split-storage tensor-core path, 0 the exact fp32 FMA path)
  *   "attn"  0 CUDA-core attention, 1 tcgen05 attention (bf16 only; default 1)
  *   "graph" 0/1 one CUDA graph per chain in dhg_sample (default 1)
  * Process-wide (ctx may be NULL; shared by every context of the process):
@@ -193,6 +197,10 @@ typedef struct dhg_debug_epilogue {
   const float* dot_w;      /* fp32 [3, N] or NULL */
   float* dot_out;          /* fp32 [rows, 4] */
   int32_t dot_act;
+  /* split I/O (the fp32-contract mode): every activation operand (A, res_pre, res_post, rowbias, outputs) holds
+   * {bf16 hi, bf16 lo} pairs, value = hi + lo; pitches stay in elements; the caller passes K = 2 * (elements per A row),
+   * lda in bf16 units and W as [2 taps][N][K]: slab t = (w_hi, w_hi) interleaved along K, slab taps + t = (w_lo, 0). */
+  int32_t split_io;
 } dhg_debug_epilogue;
 int32_t dhg_debug_tc_gemm_ex(int32_t device, const void* dev_a_bf16, int32_t lda, int32_t rows,
                              const void* dev_w_bf16, int32_t K, int32_t N, int32_t taps,

@@ -8,6 +8,51 @@ import torch
 from dhg_b200 import _abi
 
 
+def split_pack(x):
+    """fp32 tensor -> int32 tensor of {bf16 hi, bf16 lo} pairs (csrc/common.cuh `bfs`: hi in the low half-word)."""
+    hi = x.float().bfloat16()
+    lo = (x.float() - hi.float()).bfloat16()
+    return (hi.view(torch.int16).to(torch.int32) & 0xFFFF) | (lo.view(torch.int16).to(torch.int32) << 16)
+
+
+def split_unpack(w):
+    hi = (w << 16).view(torch.float32)
+    lo = (w & -65536).view(torch.float32)
+    return hi + lo
+
+
+def split_weights(w):
+    """[taps, N, K] fp32 -> [2 taps, N, 2K] bf16: slab t = (w_hi, w_hi) interleaved along K, slab taps + t = (w_lo, 0)."""
+    hi = w.float().bfloat16()
+    lo = (w.float() - hi.float()).bfloat16()
+    a = torch.stack((hi, hi), dim=-1).flatten(-2)
+    b = torch.stack((lo, torch.zeros_like(lo)), dim=-1).flatten(-2)
+    return torch.cat((a, b), dim=0).contiguous()
+
+
+def make_split_case(rows, K, N, taps, **kw):
+    """The same case in split I/O (fp32-contract mode): fp32 values, every activation operand stored as bfs pairs."""
+    device = kw.get("device", "cuda")
+    c = make_case(rows, K, N, taps, **kw)
+    g = torch.Generator().manual_seed(kw.get("seed", 0) + 99)
+    f = {}   # the fp32 values behind every operand (the reference works on these)
+    a = torch.randn(rows, K, generator=g)
+    a[c["pad"].cpu()] = 0
+    f["a"] = a.to(device)
+    f["w"] = (torch.randn(taps, N, K, generator=g) / (K * taps) ** 0.5).to(device)
+    for k in ("rowbias", "res_pre", "res_post"):
+        f[k] = torch.randn(c[k].shape, generator=g).to(device) if c[k] is not None else None
+    c["f32"] = f
+    c["a"], c["w"] = split_pack(f["a"]), split_weights(f["w"])
+    for k in ("rowbias", "res_pre", "res_post"):
+        c[k] = split_pack(f[k]) if f[k] is not None else None
+    for k in ("out_raw", "out_act"):
+        if c[k] is not None:
+            c[k] = torch.full((rows, N), 0x7FC07FC0, dtype=torch.int32, device=device)   # NaN pairs
+    c["split"] = True
+    return c
+
+
 def make_case(rows, K, N, taps, *, period=None, pad_first=0, bias=True, rowbias=False, res_pre=False, ln=False,
               film=0, res_post=False, up=False, raw=True, act=False, dot=0, seed=0, device="cuda"):
     """film: 0 none, 1 one vector for the batch (bstride 0), 2 per-sample vectors.
@@ -57,8 +102,14 @@ def make_case(rows, K, N, taps, *, period=None, pad_first=0, bias=True, rowbias=
 
 def reference(c):
     rows, N, taps, period, pf = c["rows"], c["N"], c["taps"], c["period"], c["pad_first"]
-    af, wf = c["a"].float(), c["w"].float()
-    x = torch.zeros(rows, N, device=af.device)
+    if c.get("split"):   # fp64 reference on the fp32 values themselves
+        c = dict(c, **{k: (v.double() if v is not None else None) for k, v in c["f32"].items()})
+        c = dict(c, bias=c["bias"].double() if c["bias"] is not None else None,
+                 gamma=c["gamma"].double() if c["gamma"] is not None else None, beta=c["beta"].double() if c["beta"] is not None else None)
+        af, wf = c["a"], c["w"]
+    else:
+        af, wf = c["a"].float(), c["w"].float()
+    x = torch.zeros(rows, N, device=af.device, dtype=af.dtype)
     for t in range(taps):
         shift = t - taps // 2
         src = torch.zeros_like(af)
@@ -71,9 +122,9 @@ def reference(c):
     if c["bias"] is not None:
         x += c["bias"][None]
     if c["rowbias"] is not None:
-        x[:, :c["rowbias_cols"]] += c["rowbias"].float()[pos]
+        x[:, :c["rowbias_cols"]] += c["rowbias"].to(x.dtype)[pos]
     if c["res_pre"] is not None:
-        x += c["res_pre"].float()
+        x += c["res_pre"].to(x.dtype)
     if c["ln"]:
         x = torch.nn.functional.layer_norm(x, (N,), eps=1e-6)
     if c["gamma"] is not None:
@@ -83,9 +134,9 @@ def reference(c):
             x = x * c["gamma"][None] + c["beta"][None]
     if c["res_post"] is not None:
         if c["up"]:
-            x += c["res_post"].float()[b * c["period_lo"] + 1 + pos // 2]
+            x += c["res_post"].to(x.dtype)[b * c["period_lo"] + 1 + pos // 2]
         else:
-            x += c["res_post"].float()
+            x += c["res_post"].to(x.dtype)
     x[c["pad"]] = 0
     return x
 
@@ -98,9 +149,11 @@ def run(lib, c, repeats=0, allow_unavailable=False):
     e = _abi.DebugEpilogue(
         p(c["bias"]), p(c["rowbias"]), c["rowbias_cols"], p(c["res_pre"]), N, int(c["ln"]), p(c["gamma"]), p(c["beta"]), c["bstride"],
         p(c["res_post"]), N, int(c["up"]), c["period_lo"], p(c["out_raw"]), N, p(c["out_act"]), N,
-        c["period"], c["pad_first"], c["nvalid"], p(c.get("dot_w")), p(c.get("dot_out")), int(c.get("dot_act", 0)))
+        c["period"], c["pad_first"], c["nvalid"], p(c.get("dot_w")), p(c.get("dot_out")), int(c.get("dot_act", 0)),
+        1 if c.get("split") else 0)
     ms = ctypes.c_float(0)
-    rc = lib.dhg_debug_tc_gemm_ex(0, p(c["a"]), c["K"], c["rows"], p(c["w"]), c["K"], N, c["taps"], ctypes.byref(e),
+    km = 2 if c.get("split") else 1   # split I/O: K and lda in bf16 units, two weight slabs per tap
+    rc = lib.dhg_debug_tc_gemm_ex(0, p(c["a"]), km * c["K"], c["rows"], p(c["w"]), km * c["K"], N, km * c["taps"], ctypes.byref(e),
                                   repeats, ctypes.byref(ms), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     if rc != 0 and allow_unavailable:
         msg = lib.dhg_last_error().decode()

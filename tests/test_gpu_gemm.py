@@ -92,6 +92,35 @@ def test_tc_gemm_fused_epilogue(built_lib, name, rows, K, N, taps, kw):
         assert err < 2e-2 * scale, (name, "act", err)
 
 
+SPLIT_CASES = [c for c in EPI_CASES if c[0] in (
+    "conv_film_act", "conv_film_act_n96", "conv_skip_raw", "fc_film_respost", "skipconv_up", "skipconv_up_384", "rowbias_q", "rowbias_qkv_1152",
+    "rowbias_text", "ln_film_respost_192", "ln_film_respre_256", "ln_film_respre_384", "ln_film_respost_384", "ln_only_style",
+    "film_per_sample", "ln_film_per_sample", "ffn1_act_768", "many_tiles", "many_tiles_ln384")]
+
+
+@pytest.mark.parametrize("name,rows,K,N,taps,kw", SPLIT_CASES, ids=[c[0] for c in SPLIT_CASES])
+def test_tc_gemm_split_io_meets_fp32_contract(built_lib, name, rows, K, N, taps, kw):
+    """Split I/O (the fp32-contract mode, DHG_PREC_FP32 on tcgen05): operands are {bf16 hi, bf16 lo} pairs, the GEMM is
+    (hi + lo) . w_hi + hi . w_lo in bf16 MMAs.  Against an fp64 reference on the fp32 values: 1e-4 of the output scale
+    (the products carry ~2^-17 each, the stored result another 2^-17), three orders below the bf16 mode."""
+    import gemm_ref
+
+    c = gemm_ref.make_split_case(rows, K, N, taps, seed=len(name) + rows, **kw)
+    gemm_ref.run(built_lib, c)
+    ref = gemm_ref.reference(c)
+    scale = max(1.0, ref.abs().max().item())
+    if c["out_raw"] is not None:
+        got = gemm_ref.split_unpack(c["out_raw"]).double()
+        assert torch.isfinite(got).all()
+        err = (got - ref).abs().max().item()
+        assert err < 1e-4 * scale, (name, "raw", err)
+    if c["out_act"] is not None:
+        got = gemm_ref.split_unpack(c["out_act"]).double()
+        assert torch.isfinite(got).all()
+        err = (got - torch.nn.functional.silu(ref)).abs().max().item()
+        assert err < 1e-4 * scale, (name, "act", err)
+
+
 DOT_CASES = [
     ("dot_conv_skip", 3000, 192, 128, 3, dict(period=393, pad_first=1, dot=1)),
     ("dot_conv2_film_act", 3000, 64, 128, 3, dict(period=393, pad_first=1, film=1, dot=2)),

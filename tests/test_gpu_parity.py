@@ -2,8 +2,12 @@
 reference itself, the CPU oracle on seeded inputs, and size-independent properties at the
 BASELINE batch size.  Needs a B200: run with `-m gpu`.
 
+Modes: "fp32" = DHG_PREC_FP32 as shipped (tcgen05 tensor cores on split bf16 hi/lo storage), "fp32_simt" = the same
+precision with plain fp32 storage and CUDA-core FMA GEMMs (option gemm = 0), "bf16" = the benchmarked bf16 mode.
+
 Tolerances (BASELINE.json north_star / SURVEY.md 8d):
-  fp32 mode : strokes rel-L2 <= 1e-3 after the full 60-step chain, pen-lift (p > 0.5) agreement >= 99.9 %
+  fp32 modes: strokes rel-L2 <= 1e-3 after the full 60-step chain, pen-lift (p > 0.5) agreement >= 99.9 %;
+              one forward: eps rel-L2 <= 1e-4, every tapped activation <= 1e-4 (split storage) / 1e-5 (fp32 storage)
   bf16 mode : strokes rel-L2 <= 1e-2, pen-lift agreement >= 98.5 % over positions with
               |p_ref - 0.5| > 0.01 (SURVEY.md 8d's anchor: random-init pen probabilities sit near 0.5; the
               CPU bf16-autocast reference itself lands at 6e-3 / 98.7 %)
@@ -37,6 +41,7 @@ def writers(state_dict):
 
     ws = {
         "fp32": DiffusionWriter(state_dict=state_dict, num_layers=2, channels=128, dtype="fp32"),
+        "fp32_simt": DiffusionWriter(state_dict=state_dict, num_layers=2, channels=128, dtype="fp32", gemm=0),
         "bf16": DiffusionWriter(state_dict=state_dict, num_layers=2, channels=128, dtype="bf16"),
     }
     yield ws
@@ -49,11 +54,12 @@ def _t(g, *keys):
 
 
 # ----------------------------------------------------------------------------- single forward
+@pytest.mark.parametrize("mode", ["fp32", "fp32_simt"])
 @pytest.mark.parametrize("case", ["fwd_small", "fwd_reftest"])
-def test_denoise_fp32_matches_reference_golden(writers, golden, case):
+def test_denoise_fp32_matches_reference_golden(writers, golden, case, mode):
     g = golden(case)
     strokes, text, sigma, style = _t(g, "strokes", "text", "sigma", "style")
-    eps, pen, third = writers["fp32"].denoise(strokes, text, sigma, style)
+    eps, pen, third = writers[mode].denoise(strokes, text, sigma, style)
     assert third is None and eps.shape == strokes.shape and pen.shape == strokes.shape[:2]
     assert _rel(eps.cpu(), torch.tensor(g["eps"])) < 1e-4
     assert (pen.cpu() - torch.tensor(g["pen"])).abs().max() < 1e-4
@@ -82,7 +88,7 @@ def test_intermediate_activations_match_oracle(writers, state_dict, golden):
     strokes, text, sigma, style = _t(g, "strokes", "text", "sigma", "style")
     taps = {}
     O.denoiser_forward(state_dict, strokes, text, sigma, style, taps=taps)
-    for mode, tol in (("fp32", 1e-5), ("bf16", 1.5e-2)):
+    for mode, tol in (("fp32_simt", 1e-5), ("fp32", 1e-4), ("bf16", 1.5e-2)):
         w = writers[mode]
         w.denoise(strokes, text, sigma, style)
         for name in ("h1", "h2c", "h2", "h3c", "h3", "att_in", "att0", "att1", "d3", "d2", "d1"):
@@ -106,7 +112,7 @@ def test_denoise_other_shapes_match_oracle(writers, state_dict, name, B, T, L, p
     sigma = torch.rand(B, 1, generator=g) * 0.9 + 0.05
     style = torch.randn(B, 14, 1280, generator=g)
     eps_o, pen_o = O.denoiser_forward(state_dict, strokes, text, sigma, style)
-    for mode, tol, ptol in (("fp32", 1e-4, 1e-4), ("bf16", BF16_REL, 1e-2)):
+    for mode, tol, ptol in (("fp32", 1e-4, 1e-4), ("fp32_simt", 1e-4, 1e-4), ("bf16", BF16_REL, 1e-2)):
         eps, pen, _ = writers[mode].denoise(strokes, text, sigma, style)
         assert torch.isfinite(eps).all() and torch.isfinite(pen).all()
         assert _rel(eps.cpu(), eps_o) < tol, (name, mode)
@@ -114,21 +120,23 @@ def test_denoise_other_shapes_match_oracle(writers, state_dict, name, B, T, L, p
 
 
 # ----------------------------------------------------------------------------- full chains
-def test_chain_c1_fp32_matches_reference_golden(writers, golden):
+@pytest.mark.parametrize("fp32_mode", ["fp32", "fp32_simt"])
+def test_chain_c1_fp32_matches_reference_golden(writers, golden, fp32_mode):
     g = golden("chain_c1")     # BASELINE configs[0]: batch 1, 'Follow the White Rabbit', T=392
     text, style, x0, noise = _t(g, "text", "style", "x0", "noise")
-    out = writers["fp32"].sample(text, style, x0=x0, noise=noise).cpu()
+    out = writers[fp32_mode].sample(text, style, x0=x0, noise=noise).cpu()
     ref = torch.tensor(g["out_new"])
     assert out.shape == (1, 392, 3)
     assert _rel(out[..., :2], ref[..., :2]) < FP32_REL
     assert _pen_agree(out[..., 2], ref[..., 2]) >= FP32_PEN
 
 
+@pytest.mark.parametrize("fp32_mode", ["fp32", "fp32_simt"])
 @pytest.mark.parametrize("mode", ["new", "standard"])
-def test_chain_small_fp32_both_modes(writers, golden, mode):
+def test_chain_small_fp32_both_modes(writers, golden, mode, fp32_mode):
     g = golden("chain_small")  # ragged text (zero padding), both update rules
     text, style, x0, noise = _t(g, "text", "style", "x0", "noise")
-    out = writers["fp32"].sample(text, style, x0=x0, noise=noise, diffusion_mode=mode).cpu()
+    out = writers[fp32_mode].sample(text, style, x0=x0, noise=noise, diffusion_mode=mode).cpu()
     ref = torch.tensor(g["out_" + mode])
     assert _rel(out[..., :2], ref[..., :2]) < FP32_REL
     assert _pen_agree(out[..., 2], ref[..., 2]) >= FP32_PEN
@@ -155,15 +163,15 @@ def test_host_buffer_entry_point_matches_device_entry_point(writers, golden):
     assert w.last_launch_count > 60 * 50
 
 
-@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
-def test_chunking_and_graph_do_not_change_results(state_dict, golden, dtype):
+@pytest.mark.parametrize("dtype,gemm", [("fp32", 1), ("fp32", 0), ("bf16", 1)])
+def test_chunking_and_graph_do_not_change_results(state_dict, golden, dtype, gemm):
     from dhg_b200 import DiffusionWriter
 
     g = golden("chain_small")
     text, style, x0, noise = _t(g, "text", "style", "x0", "noise")
     outs = []
     for chunk, graph in ((8, 1), (2, 1), (1, 0)):   # 3 samples: one chunk / ragged 2+1 / one by one, no graph
-        w = DiffusionWriter(state_dict=state_dict, num_layers=2, channels=128, dtype=dtype, chunk=chunk, graph=graph)
+        w = DiffusionWriter(state_dict=state_dict, num_layers=2, channels=128, dtype=dtype, chunk=chunk, graph=graph, gemm=gemm)
         outs.append(w.sample(text, style, x0=x0, noise=noise).cpu())
         w.close()
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
