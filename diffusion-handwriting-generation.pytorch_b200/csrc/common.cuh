@@ -66,6 +66,7 @@ struct Epilogue {
   float* dot_out;
   int dot_act;
   int dot_planned;         // plan-time flag like film_planned: dot_w is supplied at launch
+  int w_row_off;           // tcgen05 path, launch time: first row of the weight variant to use (TcDual stacks; 0 otherwise)
   int split_io;            // tcgen05 path: every activation operand (A, residuals, per-position rows, outputs) is `bfs`
                            // split storage; pitches stay in elements.  The fp32-contract mode (engine.cu).
   RowMap map;

@@ -52,6 +52,7 @@ static int g_opt_l2_hints = 1;   // streamed GEMM inputs get L2 evict-first prio
 static int g_opt_head_fusion = 1; // chain: enc1.conv_skip(input_dense(x)) computed from x by a K = 6 kernel ("head_fusion")
 static int g_opt_tail_fusion = 3; // chain: 1 last fc + FiLM + skip + heads as one kernel on folded tables, 2 also conv2 / conv_skip of the
                                   // last block in dot mode, so neither a2 nor skip nor d1 exist ("tail_fusion")
+static int g_opt_skip_fusion = 31; // chain: conv_skip folded into the last GEMM of a ConvBlock (bit i: enc1, enc2, enc4, dec3, dec2) ("skip_fusion")
 static int g_opt_serpentine = 1; // consumer kernels walk their rows opposite to their producer ("serpentine")
 static int g_opt_text_sets = 2;  // text sides of this many consecutive steps run at once (dhg_set_option "text_sets")
 static int fail(const char* fmt, ...) {
@@ -110,6 +111,7 @@ struct StepCtx {
   bool fuse_head;         // enc1.conv_skip is computed from x (skip_from_x), the head kernel does not write in_raw
   int fuse_tail;          // 1: dec1.fc is not launched, the head kernel works on (a2, skip) with the step's folded tables;
                           // 2: dec1.conv2 / conv_skip run in dot mode and the head kernel only adds up their 3 dots per point
+  int fuse_skip;          // bit mask of ConvBlocks whose conv_skip is folded into their last GEMM (Plan::opt_skip_fusion; chain only)
   int step;               // sampling step index (tail tables)
   HeadParams head;
 };
@@ -171,7 +173,7 @@ struct Plan {
   size_t scratch_elems = 0;
   int* err_flag = nullptr;    // set by embed_ln_kernel on a token id outside [0, vocab); read at the synchronising entry points
   // dhg_set_option switches as they were when the plan was built: the chain (and its cached graphs) only ever see these
-  int opt_tail_fusion = 0, opt_head_fusion = 0;
+  int opt_tail_fusion = 0, opt_head_fusion = 0, opt_skip_fusion = 0;
   // Every entry point works on the plan's own buffers and graph.  `ev_last` is recorded at the end of each call on the
   // stream it used and waited for at the start of the next one, so calls on different streams are ordered.
   cudaEvent_t ev_last = nullptr;
@@ -219,6 +221,10 @@ struct dhg_ctx {
   float* cond60 = nullptr;  // [60, tot]
   // tail fusion (see finalize): eps|pen = a2 . tail_A[step] + skip . tail_H + tail_c[step]
   float *tail_A = nullptr, *tail_c = nullptr, *tail_H = nullptr;   // [60,3,C] | [60,3] | [3,C]
+  // skip fusion: per block, fc weights with the step's FiLM scale folded in, [60 * N][K] bf16, and the matching bias
+  // gamma_s * b_fc + beta_s + b_skip, [60][N] fp32 (dhg_finalize)
+  std::map<std::string, bf16*> fc60_w;
+  std::map<std::string, float*> fc60_bias;
   float* tail_pick = nullptr;   // [3, 32] one-hot rows: dot mode reading columns 0..2 of the folded conv_skip
   // head fusion: enc1.conv_skip(input_dense(x)) = sum_tau (x[t+tau] . head_M[tau] + head_v[tau]) + head_b
   float *head_M = nullptr, *head_v = nullptr, *head_b = nullptr;   // [3,2,C] | [3,C] | [C]
@@ -478,6 +484,11 @@ struct Builder {
   bool tail_gemm = false;   // the next gemm() is dec1.fc: skipped when the step runs with the fused tail
   const EpiSpec* tail_alt = nullptr;   // the next gemm() gets a second plan with this epilogue, used when sc.fuse_tail == 2
   bool head_gemm = false;   // the next gemm() is enc1.conv_skip: replaced by skip_from_x when the step runs with the fused head
+  // skip fusion: the next gemm() is a conv_skip that is not launched when its block's bit is set in
+  // sc.fuse_skip / the next gemm() is that block's fc and gets a dual-operand twin that also contracts x with conv_skip's weights
+  int skipfs_bit = 0;
+  struct FsSpec { Act x_raw; std::string block; int bit; };
+  const FsSpec* fs_alt = nullptr;
 
   // Walking direction of the kernel that wrote each activation (P->dir_of: buffer -> 0 first row to last, 1 last to
   // first).  A GEMM / attention launch walks its rows in the direction OPPOSITE to the producer of its input, so it
@@ -507,7 +518,7 @@ struct Builder {
   // accumulators, resident or streamed W, CTA pairs) on the plan's own buffers and keep the fastest.  All configurations
   // compute the same bits (kernels.h TcTune), so this only moves time.  `base` is the plan of the built-in rule.
   TcGemmPlan* autotune(TcGemmPlan* base, const bf16* Ap, int lda, int rows, const bf16* Wp, int K, int N, int taps, const Epilogue& e,
-                       const Epilogue& et, const std::string& wkey) {
+                       const Epilogue& et, const std::string& wkey, const TcDual* dual = nullptr) {
     cudaStream_t st = P->cap_stream;
     cudaEvent_t e0, e1;
     if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { fail("autotune: event"); tc_gemm_plan_destroy(base); return nullptr; }
@@ -549,7 +560,8 @@ struct Builder {
           TcTune t{bn, g, (mode == 0 || mode == 3) ? 1 : 0, mode == 2 ? 1 : mode >= 3 ? 2 : 0};
           char buf[256];
           if (e.split_io && (g != 1 || mode >= 3)) continue;   // split I/O: no interleaved accumulators, no column-split cluster
-          TcGemmPlan* p = tc_gemm_plan_create(Ap, lda, rows, Wp, K, N, taps, e, buf, sizeof(buf), &t);
+          if (dual && mode >= 3) continue;
+          TcGemmPlan* p = tc_gemm_plan_create(Ap, lda, rows, Wp, K, N, taps, e, buf, sizeof(buf), &t, dual);
           if (!p) continue;   // configuration not available for this shape
           TcTune got;
           tc_gemm_plan_config(p, &got);
@@ -662,6 +674,32 @@ struct Builder {
       tc_gemm_plan_set_a_evict_first(tcp_alt, g_opt_l2_hints);
       P->tc_plans.push_back(tcp_alt);
     }
+    // skip fusion twin of a ConvBlock's fc: out = a2 . (gamma_s W_fc)^T + conv_skip(x) + (gamma_s b_fc + beta_s + b_skip)
+    TcGemmPlan* tcp_fs = nullptr;
+    Epilogue e_fs = e;
+    const FsSpec* fs = fs_alt;
+    fs_alt = nullptr;
+    const int fs_bit = fs ? fs->bit : 0;
+    const float* fs_bias = nullptr;
+    if (fs && tcp && (P->opt_skip_fusion & fs->bit)) {
+      const Lin& sk = c->lins.at(fs->block + ".conv_skip");
+      fs_bias = c->fc60_bias.at(fs->block);
+      e_fs.res_post = nullptr; e_fs.res_post_up = 0; e_fs.film_planned = 0; e_fs.gamma = e_fs.beta = nullptr;
+      e_fs.bias = fs_bias;
+      TcDual dual{(const bf16*)fs->x_raw.p, fs->x_raw.C, sk.K, sk.w16, DHG_NUM_STEPS * N};
+      char buf[512];
+      tcp_fs = tc_gemm_plan_create((const bf16*)Ap, A.C, rows, c->fc60_w.at(fs->block), K, N, 1, e_fs, buf, sizeof(buf), nullptr, &dual);
+      if (!tcp_fs) { fail("plan: tcgen05 gemm %s (skip fusion): %s", wkey.c_str(), buf); failed = true; return; }
+      if (g_opt_autotune) {
+        tcp_fs = autotune(tcp_fs, (const bf16*)Ap, A.C, rows, c->fc60_w.at(fs->block), K, N, 1, e_fs, e_fs, wkey + " (+skip)", &dual);
+        if (!tcp_fs) { failed = true; return; }
+      }
+      tc_gemm_plan_set_reverse(tcp_fs, g_opt_serpentine ? !dir_of(Ap) : 0);
+      tc_gemm_plan_set_a_evict_first(tcp_fs, g_opt_l2_hints);
+      P->tc_plans.push_back(tcp_fs);
+    }
+    const int skip_bit = skipfs_bit;
+    skipfs_bit = 0;
     *nlaunch += tcp ? 1 : 2;
     const bool skippable = tail_gemm, replaceable = head_gemm;
     tail_gemm = false;
@@ -669,6 +707,13 @@ struct Builder {
     dhg_ctx* cc = c;
     ops->push_back([=](cudaStream_t st, const StepCtx& sc) -> int {
       if (skippable && sc.fuse_tail) return 0;
+      if (skip_bit & sc.fuse_skip) return 0;   // this conv_skip is contracted inside the block's last GEMM
+      if (tcp_fs && (fs_bit & sc.fuse_skip)) {
+        Epilogue ef = e_fs;
+        ef.bias = fs_bias + (size_t)sc.step * N;
+        ef.w_row_off = sc.step * N;
+        return tc_gemm_launch(tcp_fs, ef, st) ? fail("tcgen05 gemm (skip fusion) launch failed: %s", cudaGetErrorString(cudaGetLastError())) : 0;
+      }
       if (tcp_alt && sc.fuse_tail == 2) {
         Epilogue ea = e_alt;
         if (film_off >= 0) { ea.gamma = sc.cond + film_off; ea.beta = sc.cond + film_off + Na; ea.film_bstride = sc.bstride; }
@@ -816,6 +861,12 @@ struct Builder {
     EpiSpec s0; s0.out_raw = skip;
     if (p == "enc1") head_gemm = true;
     if (tail) tail_alt = &d0;
+    static const char* kFsBlocks[5] = {"enc1", "enc2", "enc4", "dec3", "dec2"};
+    int fs_bit = 0;
+    for (int i = 0; i < 5; ++i)
+      if (p == kFsBlocks[i]) fs_bit = 1 << i;
+    FsSpec fsp{in_raw, p, fs_bit};
+    skipfs_bit = fs_bit;
     gemm(in_raw, p + ".conv_skip", s0, m);
     EpiSpec s1; s1.film_off = film(p + ".affine1"); s1.out_act = a1;
     gemm(in_act, p + ".conv1", s1, m);
@@ -825,6 +876,7 @@ struct Builder {
     EpiSpec s3; s3.film_off = film(p + ".affine3"); s3.res_post = skip; s3.out_raw = out;
     if (want_act) { *out_act = act(R, Cout); s3.out_act = *out_act; }
     if (p == "dec1") { P->tail_a2 = a2; P->tail_skip = skip; tail_gemm = true; }
+    if (fs_bit) fs_alt = &fsp;
     gemm(a2, p + ".fc", s3, m);
     return out;
   }
@@ -908,6 +960,7 @@ int build_plan(dhg_ctx* c, Plan* P) {
   CUDA_OK(cudaEventCreateWithFlags(&P->ev_last, cudaEventDisableTiming));
   P->opt_tail_fusion = g_opt_tail_fusion;
   P->opt_head_fusion = g_opt_head_fusion;
+  P->opt_skip_fusion = (P->prec == PREC_BF16 && P->gemm_impl == 1) ? g_opt_skip_fusion : 0;
 
   // ---- hoisted, step-independent part of TextStyleEncoder (text_style.py:92-99) ----
   Builder once{c, P, &P->once_ops, &P->launches_once};
@@ -1134,7 +1187,9 @@ int run_chain(dhg_ctx* c, Plan* P, int mode, bool has_noise, cudaStream_t st) {
     sc.fuse_next_input = i != 0;
     sc.text_set = i % n;
     sc.fuse_tail = (P->prec == PREC_BF16 && P->gemm_impl == 1) ? (P->opt_tail_fusion > 2 ? 2 : P->opt_tail_fusion) : 0;
-    sc.fuse_head = P->opt_head_fusion && P->prec == PREC_BF16 && P->gemm_impl == 1;
+    sc.fuse_skip = P->opt_skip_fusion;
+    // enc1.conv_skip inside enc1.fc reads the raw input rows, so the head kernel keeps writing them
+    sc.fuse_head = P->opt_head_fusion && P->prec == PREC_BF16 && P->gemm_impl == 1 && !(sc.fuse_skip & 1);
     sc.step = i;
     head_for_step(c, P, i, mode, has_noise, false, &sc.head);
     if (run_ops(P->step_ops, st, sc)) return 1;
@@ -1415,6 +1470,36 @@ int32_t dhg_finalize(dhg_ctx* c) {
     for (int j = 0; j < 3; ++j) { pick[(size_t)j * 32 + j] = 1.f; pick[(size_t)j * 32 + j + 3] = 1.f; }
     if (dev_upload(c->allocs, &c->tail_pick, pick)) return 1;
   }
+  // Skip fusion tables.  A ConvBlock ends with  out = FiLM3(fc(a2)) + conv_skip(x)  (cnn.py:66,81-87).  In sampling the
+  // FiLM vectors only depend on the step, so
+  //   out = a2 . (diag(gamma_s) W_fc)^T + sum_tap x[t + tap] . W_skip[tap]^T + (gamma_s * b_fc + beta_s + b_skip)
+  // is ONE accumulation over two operands: 60 scaled copies of W_fc (bf16) and bias vectors (fp32) per block.
+  {
+    std::vector<float> cond((size_t)DHG_NUM_STEPS * c->film_total);
+    CUDA_OK(cudaMemcpy(cond.data(), c->cond60, cond.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (const char* blk : {"enc1", "enc2", "enc4", "dec3", "dec2"}) {
+      const std::string p = blk;
+      const Lin& fc = c->lins.at(p + ".fc");
+      const Lin& sk = c->lins.at(p + ".conv_skip");
+      const int N = fc.N, K = fc.K, foff = c->film_off.at(p + ".affine3");
+      std::vector<bf16> w((size_t)DHG_NUM_STEPS * N * K);
+      std::vector<float> bias((size_t)DHG_NUM_STEPS * N);
+      for (int st = 0; st < DHG_NUM_STEPS; ++st) {
+        const float* g = cond.data() + (size_t)st * c->film_total + foff;
+        const float* be = g + N;
+        for (int n = 0; n < N; ++n) {
+          bias[(size_t)st * N + n] = g[n] * fc.h_b[n] + be[n] + sk.h_b[n];
+          for (int k = 0; k < K; ++k) w[((size_t)st * N + n) * K + k] = __float2bfloat16_rn(g[n] * fc.h_w[(size_t)k * N + n]);   // h_w: [K][N]
+        }
+      }
+      bf16* dw = nullptr;
+      float* db = nullptr;
+      if (dev_alloc(c->allocs, (void**)&dw, w.size() * sizeof(bf16)) || dev_upload(c->allocs, &db, bias)) return 1;
+      CUDA_OK(cudaMemcpy(dw, w.data(), w.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+      c->fc60_w[p] = dw;
+      c->fc60_bias[p] = db;
+    }
+  }
   // Head fusion tables (kernels_simt.cu skip_from_x_kernel)
   {
     const int C = c->c1;
@@ -1533,6 +1618,8 @@ int32_t dhg_sample(dhg_ctx* c, int32_t batch, const float* x0, const float* nois
     CUDA_OK(cudaMemcpyAsync(out + (size_t)c0 * P->T * 3, P->out, (size_t)nb * P->T * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     launches += P->launches_once + (int64_t)DHG_NUM_STEPS * (P->launches_text + P->launches_step) - (DHG_NUM_STEPS - 1);   // input_dense is fused after step 1
     if (P->opt_tail_fusion && P->prec == PREC_BF16 && P->gemm_impl == 1) launches -= DHG_NUM_STEPS;   // dec1.fc lives in the head kernel
+    for (int b = 0; b < 5; ++b)
+      if (P->opt_skip_fusion & (1 << b)) launches -= DHG_NUM_STEPS;   // that block's conv_skip lives in its last GEMM
   }
   c->last_launches = launches;
   return plan_leave(P, st);
@@ -1636,6 +1723,7 @@ int32_t dhg_set_option(dhg_ctx* c, const char* key, int32_t value) {
   if (key && !strcmp(key, "l2_hints")) { g_opt_l2_hints = value ? 1 : 0; return 0; }
   if (key && !strcmp(key, "tail_fusion")) { g_opt_tail_fusion = value < 0 ? 0 : value > 3 ? 3 : value; return 0; }
   if (key && !strcmp(key, "head_fusion")) { g_opt_head_fusion = value ? 1 : 0; return 0; }
+  if (key && !strcmp(key, "skip_fusion")) { g_opt_skip_fusion = value & 31; return 0; }
   if (key && !strcmp(key, "tune_rev")) { tc_gemm_set_option(14, value); return 0; }
   if (key && !strcmp(key, "tune_bn")) { tc_gemm_set_option(10, value); return 0; }
   if (key && !strcmp(key, "tune_g")) { tc_gemm_set_option(11, value); return 0; }

@@ -50,6 +50,9 @@ enum { AUX_NONE = 0, AUX_RES_PRE = 1, AUX_RES_POST = 2, AUX_RES_POST_UP = 3, AUX
 struct TcShape {
   int rows, K, N, taps;   // taps = weight slabs per k-block: 1 linear, 3 conv; split I/O doubles them (2 / 6, see base_taps)
   int base_taps;   // row shifts of the A operand: slab s reads the A tile shifted by s % base_taps rows (1 or 3)
+  int kb2;         // dual-operand mode: k-blocks of the SECOND A matrix (3-tap weights, rows shifted -1..+1) that follow the
+                   // kb_per_tap k-blocks of the first one (1 tap) into the same accumulators; 0 = single operand
+  uint32_t a2_tx_bytes;   // bytes of one 130-row tile of the second A matrix
   int sio;         // split I/O (Epilogue::split_io): activations are bfs pairs; K, lda and the A map are in bf16 units (2 per element)
   int BN;          // tile width
   int n_groups;    // N / BN
@@ -97,20 +100,93 @@ __device__ __forceinline__ void fast_divmod(int m, int period, float inv_period,
   if (r >= period) { r -= period; ++q; }
 }
 
-// The MMA warp's main loop, specialised on the tap count and on the number of interleaved accumulators so that
-// everything inside a k-block is straight-line code (the single issuing warp is latency-critical: every
-// instruction between two tcgen05.mma shows up in the tile time).
+// One k-block of the MMA warp's main loop, specialised on the tap count and on the number of interleaved accumulators so
+// that everything inside it is straight-line code (the single issuing warp is latency-critical: every instruction
+// between two tcgen05.mma shows up in the tile time).  `first` = 0: the first MMA overwrites the accumulators.
+// Resident W: tap t of this k-block is tile w_tile0 + t * w_tap_stride of the resident set.
 template <int TAPS, int G, bool PAIR>
+__device__ __forceinline__ void mma_kblock(const TcShape& sh, const bool leader, const uint32_t acc, const uint32_t a_ring_addr,
+                                           const uint32_t w_addr, uint64_t* full_a, uint64_t* empty_a, uint64_t* full_w, uint64_t* empty_w,
+                                           uint32_t& sa, uint32_t& pa, uint32_t& sw, uint32_t& pw, const uint32_t first, const int w_tile0,
+                                           const int w_tap_stride, const int it, unsigned& tr_n, const int tr_role, const int lane) {
+  constexpr int BASE = (TAPS % 3 == 0) ? 3 : 1;   // slab -> row shift of the A tile (split I/O: two slabs per shift)
+  const uint32_t nb2 = (uint32_t)(PAIR ? sh.umma_n / 2 : sh.umma_n) * TC_BK * 2;   // byte offset of the second N half (BN = 384)
+  const bool two_n = sh.n_umma == 2;
+  const bool resident = sh.w_resident != 0;
+  uint32_t alo[G], slot[G];
+#pragma unroll
+  for (int sub = 0; sub < G; ++sub) {
+    mbar_wait(smem_u32(&full_a[sa]), pa);
+    slot[sub] = sa;
+    alo[sub] = umma_desc_lo(a_ring_addr + sa * sh.a_stage_bytes);
+    if (++sa == (uint32_t)sh.stages_a) { sa = 0; pa ^= 1u; }
+  }
+  tc_fence_after();
+  DHG_TR(0x21, it);
+#pragma unroll
+  for (int tap = 0; tap < TAPS; ++tap) {
+    uint32_t b_addr;
+    if (resident) {
+      b_addr = w_addr + (uint32_t)(w_tile0 + tap * w_tap_stride) * sh.w_tile_bytes;
+    } else {
+      mbar_wait(smem_u32(&full_w[sw]), pw);
+      tc_fence_after();
+      b_addr = w_addr + sw * sh.w_tile_bytes;
+    }
+    const uint32_t blo = umma_desc_lo(b_addr);
+    if (leader) {
+      // shifted tap: logical row r of the A operand is physical row r + tap of the 130-row tile (the 128B
+      // swizzle is a function of the absolute smem address, so a +128 B start address just works)
+      if (!two_n) {
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k)
+#pragma unroll
+          for (int sub = 0; sub < G; ++sub) {
+            if (PAIR)
+              umma_bf16_pair(acc, umma_desc_make(alo[0] + (tap % BASE) * 8 + 2 * k, kDescHiSw128), umma_desc_make(blo + 2 * k, kDescHiSw128),
+                             sh.idesc, (tap | k) ? 1u : first);
+            else
+              umma_bf16(acc + (uint32_t)(sub * sh.BN), umma_desc_make(alo[sub] + (tap % BASE) * 8 + 2 * k, kDescHiSw128),
+                        umma_desc_make(blo + 2 * k, kDescHiSw128), sh.idesc, (tap | k) ? 1u : first);
+          }
+      } else {
+        const uint32_t blo2 = umma_desc_lo(b_addr + nb2);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          if (PAIR) {
+            umma_bf16_pair(acc, umma_desc_make(alo[0] + (tap % BASE) * 8 + 2 * k, kDescHiSw128), umma_desc_make(blo + 2 * k, kDescHiSw128),
+                           sh.idesc, (tap | k) ? 1u : first);
+            umma_bf16_pair(acc + (uint32_t)sh.umma_n, umma_desc_make(alo[0] + (tap % BASE) * 8 + 2 * k, kDescHiSw128),
+                           umma_desc_make(blo2 + 2 * k, kDescHiSw128), sh.idesc, (tap | k) ? 1u : first);
+          } else {
+            umma_bf16(acc, umma_desc_make(alo[0] + (tap % BASE) * 8 + 2 * k, kDescHiSw128), umma_desc_make(blo + 2 * k, kDescHiSw128), sh.idesc,
+                      (tap | k) ? 1u : first);
+            umma_bf16(acc + (uint32_t)sh.umma_n, umma_desc_make(alo[0] + (tap % BASE) * 8 + 2 * k, kDescHiSw128),
+                      umma_desc_make(blo2 + 2 * k, kDescHiSw128), sh.idesc, (tap | k) ? 1u : first);
+          }
+        }
+      }
+      if (!resident) { if (PAIR) umma_commit_pair(smem_u32(&empty_w[sw])); else umma_commit(smem_u32(&empty_w[sw])); }   // frees the W slot (in both CTAs of a pair) when these MMAs retire
+    }
+    __syncwarp();
+    if (!resident && ++sw == (uint32_t)sh.stages_w) { sw = 0; pw ^= 1u; }
+  }
+  if (leader) {
+#pragma unroll
+    for (int sub = 0; sub < G; ++sub) { if (PAIR) umma_commit_pair(smem_u32(&empty_a[slot[sub]])); else umma_commit(smem_u32(&empty_a[slot[sub]])); }   // frees the A slots
+  }
+  __syncwarp();
+}
+
+// The MMA warp's main loop.  DUAL: the accumulation runs over two operand segments (TcShape::kb2): kb_per_tap k-blocks
+// of the first A matrix against 1-tap weights, then kb2 k-blocks of the second A matrix against 3-tap weights.
+template <int TAPS, int G, bool PAIR, bool DUAL = false>
 __device__ __forceinline__ void mma_issue_loop(const TcShape& sh, const bool leader, const uint32_t tmem_base,
                                                const uint32_t a_ring_addr, const uint32_t w_addr, uint64_t* full_a,
                                                uint64_t* empty_a, uint64_t* full_w, uint64_t* empty_w,
                                                uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, const int t_first,
                                                const int t_end, const int t_step, unsigned& tr_n, const int tr_role,
                                                const int lane) {
-  constexpr int BASE = (TAPS % 3 == 0) ? 3 : 1;   // slab -> row shift of the A tile (split I/O: two slabs per shift)
-  const uint32_t nb2 = (uint32_t)(PAIR ? sh.umma_n / 2 : sh.umma_n) * TC_BK * 2;   // byte offset of the second N half (BN = 384)
-  const bool two_n = sh.n_umma == 2;
-  const bool resident = sh.w_resident != 0;
   uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
   int it = 0;
   for (int t = t_first; t < t_end; t += t_step, ++it) {
@@ -120,72 +196,13 @@ __device__ __forceinline__ void mma_issue_loop(const TcShape& sh, const bool lea
     tc_fence_after();
     DHG_TR(0x20, it);
     const uint32_t acc = tmem_base + (uint32_t)as * 256u;
-    for (int kbi = 0; kbi < sh.kb_per_tap; ++kbi) {
-      uint32_t alo[G], slot[G];
-#pragma unroll
-      for (int sub = 0; sub < G; ++sub) {
-        mbar_wait(smem_u32(&full_a[sa]), pa);
-        slot[sub] = sa;
-        alo[sub] = umma_desc_lo(a_ring_addr + sa * sh.a_stage_bytes);
-        if (++sa == (uint32_t)sh.stages_a) { sa = 0; pa ^= 1u; }
-      }
-      tc_fence_after();
-      DHG_TR(0x21, it);
-      const uint32_t first = kbi == 0 ? 0u : 1u;
-#pragma unroll
-      for (int tap = 0; tap < TAPS; ++tap) {
-        uint32_t b_addr;
-        if (resident) {
-          b_addr = w_addr + (uint32_t)(tap * sh.kb_per_tap + kbi) * sh.w_tile_bytes;
-        } else {
-          mbar_wait(smem_u32(&full_w[sw]), pw);
-          tc_fence_after();
-          b_addr = w_addr + sw * sh.w_tile_bytes;
-        }
-        const uint32_t blo = umma_desc_lo(b_addr);
-        if (leader) {
-          // shifted tap: logical row r of the A operand is physical row r + tap of the 130-row tile (the 128B
-          // swizzle is a function of the absolute smem address, so a +128 B start address just works)
-          if (!two_n) {
-#pragma unroll
-            for (int k = 0; k < TC_BK / 16; ++k)
-#pragma unroll
-              for (int sub = 0; sub < G; ++sub) {
-                if (PAIR)
-                  umma_bf16_pair(acc, umma_desc_make(alo[0] + (tap % BASE) * 8 + 2 * k, kDescHiSw128), umma_desc_make(blo + 2 * k, kDescHiSw128),
-                                 sh.idesc, (tap | k) ? 1u : first);
-                else
-                  umma_bf16(acc + (uint32_t)(sub * sh.BN), umma_desc_make(alo[sub] + (tap % BASE) * 8 + 2 * k, kDescHiSw128),
-                            umma_desc_make(blo + 2 * k, kDescHiSw128), sh.idesc, (tap | k) ? 1u : first);
-              }
-          } else {
-            const uint32_t blo2 = umma_desc_lo(b_addr + nb2);
-#pragma unroll
-            for (int k = 0; k < TC_BK / 16; ++k) {
-              if (PAIR) {
-                umma_bf16_pair(acc, umma_desc_make(alo[0] + (tap % BASE) * 8 + 2 * k, kDescHiSw128), umma_desc_make(blo + 2 * k, kDescHiSw128),
-                               sh.idesc, (tap | k) ? 1u : first);
-                umma_bf16_pair(acc + (uint32_t)sh.umma_n, umma_desc_make(alo[0] + (tap % BASE) * 8 + 2 * k, kDescHiSw128),
-                               umma_desc_make(blo2 + 2 * k, kDescHiSw128), sh.idesc, (tap | k) ? 1u : first);
-              } else {
-                umma_bf16(acc, umma_desc_make(alo[0] + (tap % BASE) * 8 + 2 * k, kDescHiSw128), umma_desc_make(blo + 2 * k, kDescHiSw128), sh.idesc,
-                          (tap | k) ? 1u : first);
-                umma_bf16(acc + (uint32_t)sh.umma_n, umma_desc_make(alo[0] + (tap % BASE) * 8 + 2 * k, kDescHiSw128),
-                          umma_desc_make(blo2 + 2 * k, kDescHiSw128), sh.idesc, (tap | k) ? 1u : first);
-              }
-            }
-          }
-          if (!resident) { if (PAIR) umma_commit_pair(smem_u32(&empty_w[sw])); else umma_commit(smem_u32(&empty_w[sw])); }   // frees the W slot (in both CTAs of a pair) when these MMAs retire
-        }
-        __syncwarp();
-        if (!resident && ++sw == (uint32_t)sh.stages_w) { sw = 0; pw ^= 1u; }
-      }
-      if (leader) {
-#pragma unroll
-        for (int sub = 0; sub < G; ++sub) { if (PAIR) umma_commit_pair(smem_u32(&empty_a[slot[sub]])); else umma_commit(smem_u32(&empty_a[slot[sub]])); }   // frees the A slots
-      }
-      __syncwarp();
-    }
+    for (int kbi = 0; kbi < sh.kb_per_tap; ++kbi)
+      mma_kblock<TAPS, G, PAIR>(sh, leader, acc, a_ring_addr, w_addr, full_a, empty_a, full_w, empty_w, sa, pa, sw, pw, kbi == 0 ? 0u : 1u, kbi,
+                                sh.kb_per_tap, it, tr_n, tr_role, lane);
+    if (DUAL)
+      for (int kbi = 0; kbi < sh.kb2; ++kbi)
+        mma_kblock<3, G, PAIR>(sh, leader, acc, a_ring_addr, w_addr, full_a, empty_a, full_w, empty_w, sa, pa, sw, pw, 1u,
+                               sh.taps * sh.kb_per_tap + kbi, sh.kb2, it, tr_n, tr_role, lane);
     if (leader) { if (PAIR) umma_commit_pair(smem_u32(&tmem_full_bar[as])); else umma_commit(smem_u32(&tmem_full_bar[as])); }   // accumulators complete
     __syncwarp();
     DHG_TR(0x22, it);
@@ -195,11 +212,13 @@ __device__ __forceinline__ void mma_issue_loop(const TcShape& sh, const bool lea
 // Template parameters fix the epilogue variant at compile time (-1 = read the flag at run time: the
 // generic instance).  kLN: LayerNorm; kAUX: AUX_* kind; kFILM: 0 none, 1 vectors shared by the batch
 // (smem), 2 per-sample vectors (global loads); kOUT: 1 raw, 2 SiLU'd, 3 both.
-template <int kLN, int kAUX, int kFILM, int kOUT, bool kPAIR, bool kSPLIT = false, bool kSIO = false>
+template <int kLN, int kAUX, int kFILM, int kOUT, bool kPAIR, bool kSPLIT = false, bool kSIO = false, bool kDUAL = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_w,
                                                                 const __grid_constant__ CUtensorMap map_oraw,
                                                                 const __grid_constant__ CUtensorMap map_oact,
+                                                                const __grid_constant__ CUtensorMap map_a2,
+                                                                const __grid_constant__ CUtensorMap map_w2,
                                                                 const TcShape sh, const Epilogue e) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -256,6 +275,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_oraw)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_oact)) : "memory");
+    if (kDUAL) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a2)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w2)) : "memory");
+    }
     for (int s = 0; s < 8; ++s) {
       mbar_init(smem_u32(&full_a[s]), 1);
       mbar_init(smem_u32(&empty_a[s]), 1);
@@ -303,13 +326,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     if (sh.w_resident) {
       const int n0 = my_group * sh.BN;
       const uint32_t wb = smem_u32(w_all_bar);
-      if (leader) mbar_expect_tx(wb, (uint32_t)(sh.taps * sh.kb_per_tap) * sh.w_tile_bytes);
+      if (leader) mbar_expect_tx(wb, (uint32_t)(sh.taps * sh.kb_per_tap + 3 * sh.kb2) * sh.w_tile_bytes);
       for (int tap = 0; tap < sh.taps; ++tap)
         for (int kbi = 0; kbi < sh.kb_per_tap; ++kbi) {
           const uint32_t dst = smem_u32(w_base + (size_t)(tap * sh.kb_per_tap + kbi) * sh.w_tile_bytes);
           if (leader)
             for (int j = 0; j < sh.n_umma; ++j)
-              tma_load_2d(dst + (uint32_t)j * sh.umma_n * TC_BK * 2, &map_w, wb, kbi * TC_BK, tap * sh.N + n0 + j * sh.umma_n);
+              tma_load_2d(dst + (uint32_t)j * sh.umma_n * TC_BK * 2, &map_w, wb, kbi * TC_BK, e.w_row_off + tap * sh.N + n0 + j * sh.umma_n);
+        }
+      for (int tap = 0; tap < 3; ++tap)   // second operand's weights (dual mode)
+        for (int kbi = 0; kbi < sh.kb2; ++kbi) {
+          const uint32_t dst = smem_u32(w_base + (size_t)(sh.taps * sh.kb_per_tap + tap * sh.kb2 + kbi) * sh.w_tile_bytes);
+          if (leader)
+            for (int j = 0; j < sh.n_umma; ++j)
+              tma_load_2d(dst + (uint32_t)j * sh.umma_n * TC_BK * 2, &map_w2, wb, kbi * TC_BK, tap * sh.N + n0 + j * sh.umma_n);
         }
     }
     // weights are constants; the activations are produced by the previous kernel of the chain
@@ -322,28 +352,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       const int ng = bound_group ? my_group : t - mts_f * sh.n_groups;
       const int mts = sh.rev ? sh.m_super - 1 - mts_f : mts_f;
       const int n0 = ng * sh.BN;
-      for (int kbi = 0; kbi < sh.kb_per_tap; ++kbi) {
-        const int kk = kbi * TC_BK;
+      for (int kbi = 0; kbi < sh.kb_per_tap + sh.kb2; ++kbi) {
+        const bool s2 = kbi >= sh.kb_per_tap;   // dual mode: k-block of the second operand
+        const int kk = (s2 ? kbi - sh.kb_per_tap : kbi) * TC_BK;
+        const CUtensorMap* ma = s2 ? &map_a2 : &map_a;
+        const CUtensorMap* mw = s2 ? &map_w2 : &map_w;
+        const int roff = s2 ? -1 : a_row_off;
+        const uint32_t a_tx = s2 ? sh.a2_tx_bytes : sh.a_tx_bytes;
+        const int ntaps = s2 ? 3 : sh.taps;
+        const int w_row0 = s2 ? 0 : e.w_row_off;
         for (int sub = 0; sub < sh.G; ++sub) {   // the G row tiles of this super-tile share every W tile
           mbar_wait(smem_u32(&empty_a[sa]), pa ^ 1u);
           DHG_TR(0x10, sa);
           const uint32_t fb = smem_u32(&full_a[sa]);
           if (leader) {
-            const int row0 = (mts * tiles_per_super + sub + (int)cta_rank) * TC_BM + a_row_off;
+            const int row0 = (mts * tiles_per_super + sub + (int)cta_rank) * TC_BM + roff;
             if (kPAIR) {   // both CTAs' bytes are counted on rank 0's barrier
-              if (cta_rank == 0) mbar_expect_tx(fb, 2 * sh.a_tx_bytes);
-              if (sh.a_evict_first) tma_load_2d_pair_hint(smem_u32(a_ring + (size_t)sa * sh.a_stage_bytes), &map_a, fb, kk, row0, pol_a);
-              else tma_load_2d_pair(smem_u32(a_ring + (size_t)sa * sh.a_stage_bytes), &map_a, fb, kk, row0);
+              if (cta_rank == 0) mbar_expect_tx(fb, 2 * a_tx);
+              if (sh.a_evict_first) tma_load_2d_pair_hint(smem_u32(a_ring + (size_t)sa * sh.a_stage_bytes), ma, fb, kk, row0, pol_a);
+              else tma_load_2d_pair(smem_u32(a_ring + (size_t)sa * sh.a_stage_bytes), ma, fb, kk, row0);
             } else {
-              mbar_expect_tx(fb, sh.a_tx_bytes);
-              if (sh.a_evict_first) tma_load_2d_hint(smem_u32(a_ring + (size_t)sa * sh.a_stage_bytes), &map_a, fb, kk, row0, pol_a);
-              else tma_load_2d(smem_u32(a_ring + (size_t)sa * sh.a_stage_bytes), &map_a, fb, kk, row0);
+              mbar_expect_tx(fb, a_tx);
+              if (sh.a_evict_first) tma_load_2d_hint(smem_u32(a_ring + (size_t)sa * sh.a_stage_bytes), ma, fb, kk, row0, pol_a);
+              else tma_load_2d(smem_u32(a_ring + (size_t)sa * sh.a_stage_bytes), ma, fb, kk, row0);
             }
           }
           if (++sa == (uint32_t)sh.stages_a) { sa = 0; pa ^= 1u; }
         }
         if (!sh.w_resident) {
-          for (int tap = 0; tap < sh.taps; ++tap) {
+          for (int tap = 0; tap < ntaps; ++tap) {
             mbar_wait(smem_u32(&empty_w[sw]), pw ^ 1u);
             const uint32_t fw = smem_u32(&full_w[sw]);
             const uint32_t dst = smem_u32(w_base + (size_t)sw * sh.w_tile_bytes);
@@ -352,11 +389,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
                 const int hn = sh.umma_n >> 1;
                 if (cta_rank == 0) mbar_expect_tx(fw, 2 * sh.w_tile_bytes);
                 for (int j = 0; j < sh.n_umma; ++j)
-                  tma_load_2d_pair(dst + (uint32_t)j * hn * TC_BK * 2, &map_w, fw, kk, tap * sh.N + n0 + j * sh.umma_n + (int)cta_rank * hn);
+                  tma_load_2d_pair(dst + (uint32_t)j * hn * TC_BK * 2, mw, fw, kk, w_row0 + tap * sh.N + n0 + j * sh.umma_n + (int)cta_rank * hn);
               } else {
                 mbar_expect_tx(fw, sh.w_tile_bytes);
                 for (int j = 0; j < sh.n_umma; ++j)
-                  tma_load_2d(dst + (uint32_t)j * sh.umma_n * TC_BK * 2, &map_w, fw, kk, tap * sh.N + n0 + j * sh.umma_n);
+                  tma_load_2d(dst + (uint32_t)j * sh.umma_n * TC_BK * 2, mw, fw, kk, w_row0 + tap * sh.N + n0 + j * sh.umma_n);
               }
             }
             if (++sw == (uint32_t)sh.stages_w) { sw = 0; pw ^= 1u; }
@@ -381,7 +418,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 #define DHG_MMA_LOOP_PAIR(TAPS)                                                                                         \
   mma_issue_loop<TAPS, 1, true>(sh, leader, tmem_base, a_ring_addr, w_addr, full_a, empty_a, full_w, empty_w, tmem_full_bar, \
                            tmem_empty_bar, t_first, t_end, t_step, tr_n, tr_role, lane)
-    if (kPAIR) {
+#define DHG_MMA_LOOP_DUAL(GG, PP)                                                                                        \
+  mma_issue_loop<1, GG, PP, true>(sh, leader, tmem_base, a_ring_addr, w_addr, full_a, empty_a, full_w, empty_w, tmem_full_bar, \
+                           tmem_empty_bar, t_first, t_end, t_step, tr_n, tr_role, lane)
+    if (kDUAL) {   // two operand segments into the same accumulators (1-tap first operand, 3-tap second operand)
+      if (kPAIR) { if (cta_rank == 0) DHG_MMA_LOOP_DUAL(1, true); }
+      else if (sh.G == 4) DHG_MMA_LOOP_DUAL(4, false); else if (sh.G == 2) DHG_MMA_LOOP_DUAL(2, false); else DHG_MMA_LOOP_DUAL(1, false);
+    } else if (kPAIR) {
       if (cta_rank == 0) {   // rank 0 issues for both CTAs
         if (kSIO) { if (sh.taps == 6) DHG_MMA_LOOP_PAIR(6); else DHG_MMA_LOOP_PAIR(2); }
         else if (sh.taps == 3) DHG_MMA_LOOP_PAIR(3); else DHG_MMA_LOOP_PAIR(1);
@@ -395,6 +438,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     }
 #undef DHG_MMA_LOOP
 #undef DHG_MMA_LOOP_PAIR
+#undef DHG_MMA_LOOP_DUAL
   } else {
     // ===== epilogue warps; warp (q, part): TMEM lanes [32q, 32q+32), one contiguous part of the column chunks =====
     asm volatile("griddepcontrol.wait;" ::: "memory");   // residual rows are read / outputs written only after the previous kernel
@@ -807,7 +851,7 @@ void tc_gemm_set_option(int which, int value) {
   else if (which == 3) g_opt_specialize = value;
 }
 
-typedef void (*TcKernFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcShape, const Epilogue);
+typedef void (*TcKernFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcShape, const Epilogue);
 struct TcKernEntry { int ln, aux, film, out; TcKernFn fn, fn_pair, fn_split; };   // fn_pair: the cta_group::2 build, fn_split: column-split LayerNorm (cluster launches only)
 #define DHG_TC_K(ln, aux, film, out) {ln, aux, film, out, tc_gemm_kernel<ln, aux, film, out, false>, tc_gemm_kernel<ln, aux, film, out, true>, nullptr}
 #define DHG_TC_KL(aux, film, out) {1, aux, film, out, tc_gemm_kernel<1, aux, film, out, false>, tc_gemm_kernel<1, aux, film, out, true>, tc_gemm_kernel<1, aux, film, out, false, true>}
@@ -831,6 +875,10 @@ static const TcKernEntry kTcKernels[] = {
     DHG_TC_KL(AUX_RES_PRE, 1, 2),       // text-style mha.dense
     {-1, -1, -1, -1, tc_gemm_kernel<-1, -1, -1, -1, false>, tc_gemm_kernel<-1, -1, -1, -1, true>, tc_gemm_kernel<-1, -1, -1, -1, false, true>},   // generic
 };
+// dual-operand mode (engine.cu: conv_skip folded into the last GEMM of a ConvBlock): bias-only epilogue, raw (or raw + SiLU'd) output
+static const TcKernFn kTcKernelsDual[2][2] = {
+    {tc_gemm_kernel<0, AUX_NONE, 0, 1, false, false, false, true>, tc_gemm_kernel<0, AUX_NONE, 0, 1, true, false, false, true>},
+    {tc_gemm_kernel<0, AUX_NONE, 0, 3, false, false, false, true>, tc_gemm_kernel<0, AUX_NONE, 0, 3, true, false, false, true>}};
 // split I/O (fp32-contract mode): the generic instance only, plain and CTA pair
 static const TcKernFn kTcKernelsSio[2] = {tc_gemm_kernel<-1, -1, -1, -1, false, false, true>, tc_gemm_kernel<-1, -1, -1, -1, true, false, true>};
 static TcKernFn pick_kernel(int ln, int aux, int film, int out, int cluster_mode) {   // 0 plain, 1 CTA pair, 2 column-split LayerNorm
@@ -844,7 +892,7 @@ static TcKernFn pick_kernel(int ln, int aux, int film, int out, int cluster_mode
 }
 
 struct TcGemmPlan {
-  CUtensorMap map_a, map_w, map_oraw, map_oact;
+  CUtensorMap map_a, map_w, map_oraw, map_oact, map_a2, map_w2;
   TcShape sh;
   dim3 grid;
   size_t smem;
@@ -854,7 +902,7 @@ struct TcGemmPlan {
 };
 
 TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W, int K, int N, int taps, const Epilogue& e,
-                                char* err, int errlen, const TcTune* tune) {
+                                char* err, int errlen, const TcTune* tune, const TcDual* dual) {
   const TcTune tn = tune ? *tune : g_tune_default;
   if (rows >= (1 << 24)) { snprintf(err, errlen, "rows = %d: the epilogue's row arithmetic needs rows < 2^24 (plan a smaller chunk)", rows); return nullptr; }
   const bool sio = e.split_io != 0;   // K, lda in bf16 units (2 per activation element), taps = 2 weight slabs per row shift
@@ -863,6 +911,11 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
     return nullptr;
   }
   const int base_taps = taps % 3 == 0 ? 3 : 1;
+  if (dual && (sio || taps != 1 || e.ln || e.rowbias16 || e.res_pre || e.res_post || e.film_planned || !e.bias || dual->K2 % 8 || !dual->A2 || !dual->W2 ||
+               dual->w1_rows < N)) {
+    snprintf(err, errlen, "dual-operand mode needs a 1-tap first operand and a bias-only epilogue");
+    return nullptr;
+  }
   int BN = 0;
   // pair == 2: column-split LayerNorm, a 2-CTA cluster per row tile, each CTA accumulates N/2 columns double-buffered
   const bool split = tn.pair == 2;
@@ -908,6 +961,8 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   TcShape& sh = p->sh;
   sh.rows = rows; sh.K = K; sh.N = N; sh.taps = taps; sh.BN = BN;
   sh.base_taps = base_taps; sh.sio = sio ? 1 : 0;
+  sh.kb2 = dual ? (dual->K2 + TC_BK - 1) / TC_BK : 0;
+  sh.a2_tx_bytes = (uint32_t)(TC_BM + 2) * TC_BK * 2;
   sh.n_groups = N / BN;
   const int m_tiles = (rows + TC_BM - 1) / TC_BM;
   sh.m_tiles = m_tiles;
@@ -938,7 +993,7 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   sh.m_super = (m_tiles + G - 1) / G;
   const int a_rows = base_taps == 3 ? TC_BM + 2 : TC_BM;
   sh.a_tx_bytes = (uint32_t)a_rows * TC_BK * 2;
-  sh.a_stage_bytes = (sh.a_tx_bytes + 1023u) & ~1023u;
+  sh.a_stage_bytes = ((dual ? sh.a2_tx_bytes : sh.a_tx_bytes) + 1023u) & ~1023u;
   sh.w_tile_bytes = (uint32_t)BN * TC_BK * 2;
   // smem carve-up: A ring | W ring or resident W | aux rings | out staging | vectors | LN exchange | barriers
   sh.dot_n = dot ? 3 * N : 0;
@@ -953,7 +1008,8 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
     fixed -= (size_t)EPI_WARPS * OUT_STAGE_BYTES / 2;
     budget += (size_t)EPI_WARPS * OUT_STAGE_BYTES / 2;
   }
-  const size_t w_all = (size_t)taps * sh.kb_per_tap * sh.w_tile_bytes;
+  const size_t w_all = (size_t)(taps * sh.kb_per_tap + 3 * sh.kb2) * sh.w_tile_bytes;
+  const int ring_taps = dual ? 3 : taps;   // W tiles per k-block the streamed ring must hold
   const int min_a = G > 1 ? 2 * G : 3;
   const int want_resident = tn.resident >= 0 ? tn.resident : g_opt_w_resident;
   sh.w_resident = (want_resident && w_all + (size_t)min_a * sh.a_stage_bytes <= budget && sh.m_super * sh.n_groups > num_sms) ? 1 : 0;
@@ -963,7 +1019,7 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   // Measured (profiles/): pairing pays when the MMA / W-stream phase dominates the tile (K*taps >= 512 and a light
   // epilogue, or the single-buffered 384-wide LayerNorm rows); with g_opt_pair == 2 every non-resident GEMM is paired.
   const int out_mode_plan = dot ? 4 : ((e.out_raw ? 1 : 0) | (e.out_act ? 2 : 0));
-  const bool pair_pays = BN == 384 || (taps * K >= 512 && out_mode_plan != 3 && !(e.ln && N <= 192));
+  const bool pair_pays = BN == 384 || (taps * K + (dual ? 3 * dual->K2 : 0) >= 512 && out_mode_plan != 3 && !(e.ln && N <= 192));
   const bool want_pair = split ? false : tn.pair >= 0 ? tn.pair != 0 : (g_opt_pair && (g_opt_pair == 2 || pair_pays));
   sh.pair = (!sh.w_resident && want_pair && G == 1 && sh.umma_n % 16 == 0 &&
              (m_tiles + 1) / 2 * sh.n_groups >= num_sms / 2) ? 1 : 0;
@@ -981,7 +1037,7 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
     w_bytes = w_all;
   } else {
     // per k-block: G A tiles and `taps` W tiles
-    int sa = (int)(budget / ((size_t)G * sh.a_stage_bytes + (size_t)taps * sh.w_tile_bytes)) * G;
+    int sa = (int)(budget / ((size_t)G * sh.a_stage_bytes + (size_t)ring_taps * sh.w_tile_bytes)) * G;
     if (sa < 2 * G) sa = G > 1 ? 2 * G : 2;
     if (sa > 8) sa = 8;
     if ((size_t)sa * sh.a_stage_bytes + 2 * (size_t)sh.w_tile_bytes > budget) { snprintf(err, errlen, "not enough shared memory for BN=%d", BN); delete p; return nullptr; }
@@ -1023,7 +1079,13 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   }
   p->grid = dim3(grid);
   if (!make_map(&p->map_a, A, (uint64_t)rows, (uint64_t)K, (uint64_t)lda, (uint32_t)a_rows, err, errlen) ||
-      !make_map(&p->map_w, W, (uint64_t)taps * N, (uint64_t)K, (uint64_t)K, (uint32_t)(sh.pair ? sh.umma_n / 2 : sh.umma_n), err, errlen)) {
+      !make_map(&p->map_w, W, dual ? (uint64_t)dual->w1_rows : (uint64_t)taps * N, (uint64_t)K, (uint64_t)K, (uint32_t)(sh.pair ? sh.umma_n / 2 : sh.umma_n), err, errlen)) {
+    delete p;
+    return nullptr;
+  }
+  p->map_a2 = p->map_a; p->map_w2 = p->map_w;   // placeholders (never used) unless this is a dual-operand plan
+  if (dual && (!make_map(&p->map_a2, dual->A2, (uint64_t)rows, (uint64_t)dual->K2, (uint64_t)dual->lda2, (uint32_t)(TC_BM + 2), err, errlen) ||
+               !make_map(&p->map_w2, dual->W2, (uint64_t)3 * N, (uint64_t)dual->K2, (uint64_t)dual->K2, (uint32_t)(sh.pair ? sh.umma_n / 2 : sh.umma_n), err, errlen))) {
     delete p;
     return nullptr;
   }
@@ -1043,6 +1105,11 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
                         : pick_kernel(-1, -1, -1, -1, cluster_mode);   // the specialised variants assume a bias vector
   p->fn_generic = pick_kernel(-1, -1, -1, -1, cluster_mode);
   if (sio) p->fn_shared = p->fn_generic = kTcKernelsSio[sh.pair ? 1 : 0];
+  if (dual) {
+    if (out_mode != 1 && out_mode != 3) { snprintf(err, errlen, "dual-operand mode stores a raw (or raw + SiLU'd) output"); delete p; return nullptr; }
+    if (sh.split) { snprintf(err, errlen, "dual-operand mode does not fit the column-split cluster"); delete p; return nullptr; }
+    p->fn_shared = p->fn_generic = kTcKernelsDual[out_mode == 3 ? 1 : 0][sh.pair ? 1 : 0];
+  }
   for (TcKernFn fn : {p->fn_shared, p->fn_generic}) {
     cudaError_t ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (ce != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); delete p; return nullptr; }
@@ -1087,7 +1154,7 @@ int tc_gemm_launch(const TcGemmPlan* p, const Epilogue& e, cudaStream_t st) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, fn, p->map_a, p->map_w, p->map_oraw, p->map_oact, p->sh, e) == cudaSuccess ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, fn, p->map_a, p->map_w, p->map_oraw, p->map_oact, p->map_a2, p->map_w2, p->sh, e) == cudaSuccess ? 0 : 1;
 }
 
 }  // namespace dhg

@@ -79,8 +79,14 @@ struct TcGemmPlan;  // opaque: tensor maps + launch geometry, built once at plan
 // through distributed shared memory; N = 128, 256 or 384).  Every configuration computes the same bits: the K order of
 // a row's dot product and the grouping of the LayerNorm partial sums do not depend on it.
 struct TcTune { int bn, g, resident, pair; };
+// Dual-operand GEMM: out = A . W^T + sum_tap A2[row + tap - 1] . W2[tap]^T + bias, one accumulation over two operand
+// segments (the first with 1-tap weights, the second with 3-tap weights and the zero halo of the padded-row layout).
+// W (the first operand's weights) may be a stack of w1_rows / N variants of [N, K]; the launch picks one through
+// Epilogue::w_row_off (a multiple of N).  Used for  FiLM(fc(a2)) + conv_skip(x)  with the FiLM scale folded into fc's
+// weights per sampling step (engine.cu).
+struct TcDual { const bf16* A2; int lda2; int K2; const bf16* W2; int w1_rows; };
 TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W, int K, int N, int taps,
-                                const Epilogue& e, char* err, int errlen, const TcTune* tune = nullptr);
+                                const Epilogue& e, char* err, int errlen, const TcTune* tune = nullptr, const TcDual* dual = nullptr);
 void tc_gemm_plan_config(const TcGemmPlan*, TcTune* out);   // what the plan ended up with
 // Walk the row tiles from the last to the first.  The engine gives every kernel the direction opposite to the kernel
 // that wrote its input, so it starts on the rows that are still in the 126 MB L2 (same bits either way).

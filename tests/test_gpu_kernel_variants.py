@@ -58,7 +58,8 @@ def test_chain_is_bit_identical_with_and_without_text_overlap(tmp_path):
     outs = {}
     for name, opts, graph in [("overlap", "", "graph"), ("serial", "text_sets=1", "graph"), ("overlap_streams", "text_sets=3", "nograph"),
                               ("one_direction", "serpentine=0,autotune=0", "graph"), ("no_tail_fusion", "tail_fusion=0", "graph"), ("tail_fusion_1", "tail_fusion=1", "graph"), ("tail_fusion_2", "tail_fusion=2", "graph"),
-                              ("no_head_fusion", "head_fusion=0", "graph")]:
+                              ("no_head_fusion", "head_fusion=0", "graph"), ("no_skip_fusion", "skip_fusion=0", "graph"),
+                              ("skip_fusion_enc_only", "skip_fusion=7", "graph"), ("skip_fusion_one_direction", "serpentine=0,autotune=0,skip_fusion=31", "graph")]:
         f = str(tmp_path / f"{name}.npy")
         r = subprocess.run([sys.executable, "-c", code, f, graph], env=dict(os.environ, DHG_OPTS=opts), capture_output=True, text=True,
                            cwd=ROOT, timeout=900)
@@ -68,9 +69,12 @@ def test_chain_is_bit_identical_with_and_without_text_overlap(tmp_path):
     assert np.array_equal(outs["overlap"], outs["serial"])
     assert np.array_equal(outs["overlap"], outs["overlap_streams"])
     assert np.array_equal(outs["overlap"], outs["one_direction"])   # tile order and tile configuration only move time
+    assert np.array_equal(outs["overlap"], outs["skip_fusion_one_direction"])   # also for the dual-operand GEMMs
     # the fused tail (fc + FiLM + skip + heads on folded fp32 tables) skips one bf16 rounding of d1: close, not identical
     # (likewise the fused head: enc1.conv_skip from x in fp32 instead of from the bf16 input_dense rows)
-    for other in ("no_tail_fusion", "tail_fusion_1", "tail_fusion_2", "no_head_fusion"):
+    # (likewise skip fusion: conv_skip accumulated inside the block's last GEMM in fp32 instead of through a bf16 `skip` row,
+    # and the FiLM scale folded into bf16 weights)
+    for other in ("no_tail_fusion", "tail_fusion_1", "tail_fusion_2", "no_head_fusion", "no_skip_fusion", "skip_fusion_enc_only"):
         a, b = outs["overlap"].astype(np.float64), outs[other].astype(np.float64)
         assert np.linalg.norm(a[..., :2] - b[..., :2]) / np.linalg.norm(b[..., :2]) < 1e-2, other
         assert np.abs(a[..., 2] - b[..., 2]).mean() < 2e-2 and np.abs(a[..., 2] - b[..., 2]).max() < 0.25, other   # pen probabilities (two bf16 variants of a 60-step chain)
