@@ -284,6 +284,249 @@ __global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Long key sequences (Tk > 256: the self-attentions of long lines, e.g. T = 1200 -> 600 / 300 keys).  Same work item
+// (128-query tile, head, sample), but the keys are walked in blocks of 128 and the softmax is taken in TWO PASSES over
+// the blocks, so nothing is ever rescaled:
+//   pass A   S_j = Q K_j^T for every block j, row maximum over all keys (the score MMAs are cheap: D = 64);
+//   pass B   S_j again, p = 2^(s - max) -> row sum and bf16 P_j in shared memory, O += P_j V_j accumulated in TMEM.
+// Per slot: Q tile, two K block buffers (the next block travels while this one is multiplied and read), one V block,
+// one P tile; TMEM: 128 score columns + 64 output columns.  Two slots per CTA work on different items, so one slot's
+// loads and MMAs hide behind the other's softmax.  Unmasked, head depth 64 (self-attention only needs that).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int ATL_KB = 128;      // keys per block
+constexpr int ATL_SLOTS = 2;
+constexpr int ATL_TMEM_SLOT = 192;   // 128 score + 64 output columns
+
+struct AttnLongShape {
+  int nkb;       // key blocks
+  int QT, items, rev;
+  uint32_t idesc_s, idesc_o;
+  uint32_t off_k, off_v, off_p, slot_bytes, off_bar;
+  float scale_log2;
+};
+
+__global__ void __launch_bounds__(ATL_SLOTS * 160, 1) attn_tc_long_kernel(const __grid_constant__ CUtensorMap map_q,
+                                                                          const __grid_constant__ CUtensorMap map_k,
+                                                                          const __grid_constant__ CUtensorMap map_v,
+                                                                          const AttnLongShape sh, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // per slot: 0 full_q, 1-2 full_k[2], 3 full_v, 4 bar_s, 5 s_free, 6 bar_p, 7 bar_o, 8 slot_free
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sh.off_bar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9 * ATL_SLOTS);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NS = ATL_SLOTS;
+  const int stride = (int)gridDim.x * NS;
+  const int nkb = sh.nkb;
+
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_k)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_v)) : "memory");
+      for (int s = 0; s < NS; ++s) {
+        for (int i = 0; i < 5; ++i) mbar_init(smem_u32(&bars[s * 9 + i]), 1);
+        mbar_init(smem_u32(&bars[s * 9 + 5]), 128);
+        mbar_init(smem_u32(&bars[s * 9 + 6]), 128);
+        mbar_init(smem_u32(&bars[s * 9 + 7]), 1);
+        mbar_init(smem_u32(&bars[s * 9 + 8]), 128);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  if (warp < NS) {
+    // ===== control warp of slot `warp` =====
+    const bool leader = elect_one();
+    const int s = warp;
+    uint8_t* q_s = smem + (size_t)s * sh.slot_bytes;
+    uint64_t* sb = bars + s * 9;
+    const uint32_t tm_s = tmem_base + (uint32_t)(s * ATL_TMEM_SLOT), tm_o = tm_s + 128u;
+    const uint32_t qlo = umma_desc_lo(smem_u32(q_s));
+    const uint32_t klo[2] = {umma_desc_lo(smem_u32(q_s + sh.off_k)), umma_desc_lo(smem_u32(q_s + sh.off_k + 16384u))};
+    const uint32_t vlo_mn = (umma_desc_lo(smem_u32(q_s + sh.off_v)) & ~(1u << 16)) | ((1024u >> 4) << 16);   // MN-major: LBO field
+    const uint32_t plo = umma_desc_lo(smem_u32(q_s + sh.off_p));
+    uint32_t ph_q = 0, ph_k[2] = {0, 0}, ph_v = 0, ph_sf = 0, ph_p = 0, ph_o = 0, ph_free = 0;
+    for (int item = (int)blockIdx.x * NS + s; item < sh.items; item += stride) {
+      int it2 = sh.rev ? sh.items - 1 - item : item;
+      const int qt = it2 % sh.QT, bh = it2 / sh.QT, h = bh % p.H, b = bh / p.H;
+      const int krow0 = b * p.k_period + p.k_pad;
+      auto kload = [&](int jblk, int buf) {
+        mbar_expect_tx(smem_u32(&sb[1 + buf]), 16384u);
+        tma_load_2d(smem_u32(q_s + sh.off_k + (uint32_t)buf * 16384u), &map_k, smem_u32(&sb[1 + buf]), h * 64, krow0 + jblk * ATL_KB);
+      };
+      mbar_wait(smem_u32(&sb[8]), ph_free ^ 1u);   // the previous item's O has been read out: every tile and TMEM column of the slot is free
+      ph_free ^= 1u;
+      if (leader) {
+        mbar_expect_tx(smem_u32(&sb[0]), 16384u);
+        tma_load_2d(smem_u32(q_s), &map_q, smem_u32(&sb[0]), h * 64, b * p.q_period + p.q_pad + qt * 128);
+        kload(0, 0);
+      }
+      mbar_wait(smem_u32(&sb[0]), ph_q);
+      ph_q ^= 1u;
+      const int nsteps = 2 * nkb;
+      for (int g = 0; g < nsteps; ++g) {
+        const int buf = g & 1, j = g < nkb ? g : g - nkb;
+        const bool pass_b = g >= nkb;
+        if (g > 0) {   // the softmax group has read S of step g-1 (so that MMA is complete and its K buffer is free)
+          mbar_wait(smem_u32(&sb[5]), ph_sf);
+          ph_sf ^= 1u;
+        }
+        if (leader) {
+          if (g + 1 < nsteps) kload(g + 1 < nkb ? g + 1 : g + 1 - nkb, buf ^ 1);
+          if (pass_b) {   // V block (its buffer is free: the previous P V product has completed, see the wait below)
+            mbar_expect_tx(smem_u32(&sb[3]), 16384u);
+            tma_load_2d(smem_u32(q_s + sh.off_v), &map_v, smem_u32(&sb[3]), h * 64, krow0 + j * ATL_KB);
+          }
+        }
+        mbar_wait(smem_u32(&sb[1 + buf]), ph_k[buf]);
+        ph_k[buf] ^= 1u;
+        tc_fence_after();
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tm_s, umma_desc_make(qlo + 2 * k, kDescHiSw128), umma_desc_make(klo[buf] + 2 * k, kDescHiSw128), sh.idesc_s, k ? 1u : 0u);
+          umma_commit(smem_u32(&sb[4]));
+        }
+        __syncwarp();
+        if (pass_b) {
+          mbar_wait(smem_u32(&sb[3]), ph_v);
+          ph_v ^= 1u;
+          mbar_wait(smem_u32(&sb[6]), ph_p);   // P_j written
+          ph_p ^= 1u;
+          tc_fence_after();
+          if (leader) {
+#pragma unroll
+            for (int kk = 0; kk < ATL_KB / 16; ++kk) {
+              const uint32_t alo = plo + (uint32_t)(kk >> 2) * (16384u >> 4) + (uint32_t)(kk & 3) * 2u;
+              umma_bf16(tm_o, umma_desc_make(alo, kDescHiSw128), umma_desc_make(vlo_mn + (uint32_t)kk * (2048u >> 4), kDescHiSw128),
+                        sh.idesc_o, (j | kk) ? 1u : 0u);
+            }
+            umma_commit(smem_u32(&sb[7]));
+          }
+          __syncwarp();
+          mbar_wait(smem_u32(&sb[7]), ph_o);   // P V done: the P tile and the V block may be overwritten
+          ph_o ^= 1u;
+        }
+      }
+      // the last step's S is read by the softmax group before it arrives on s_free one more time: consume that phase
+      mbar_wait(smem_u32(&sb[5]), ph_sf);
+      ph_sf ^= 1u;
+    }
+  } else {
+    // ===== softmax group of slot `slot`: thread = query row =====
+    const int slot = (warp - NS) >> 2, wq = warp & 3;
+    uint8_t* q_s = smem + (size_t)slot * sh.slot_bytes;
+    uint64_t* sb = bars + slot * 9;
+    const int r = wq * 32 + lane;
+    const uint32_t lane_sel = ((uint32_t)(wq * 32)) << 16;
+    const uint32_t tm_s = tmem_base + (uint32_t)(slot * ATL_TMEM_SLOT) + lane_sel, tm_o = tm_s + 128u;
+    const uint32_t p_sa = smem_u32(q_s + sh.off_p);
+    uint32_t ph_s = 0, ph_o = 0;
+    float v[32];
+    for (int item = (int)blockIdx.x * NS + slot; item < sh.items; item += stride) {
+      int it2 = sh.rev ? sh.items - 1 - item : item;
+      const int qt = it2 % sh.QT, bh = it2 / sh.QT, h = bh % p.H, b = bh / p.H;
+      const int tq = qt * 128 + r;
+      // pass A: row maximum of the raw scores (scale > 0: scaled once at the end)
+      float mx = -INFINITY;
+      for (int j = 0; j < nkb; ++j) {
+        mbar_wait(smem_u32(&sb[4]), ph_s);
+        ph_s ^= 1u;
+        tc_fence_after();
+        const int k0 = j * ATL_KB;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          if (k0 + c * 32 >= p.Tk) break;
+          tmem_ld32(tm_s + c * 32, v);
+          if (k0 + c * 32 + 32 <= p.Tk) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, v[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (k0 + c * 32 + i < p.Tk) mx = fmaxf(mx, v[i]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(smem_u32(&sb[5]));
+      }
+      const float nmx = -mx * sh.scale_log2;
+      // pass B: p = 2^(s * scale_log2 - max), row sum, bf16 P block in the swizzled K-major operand layout
+      float sum = 0.f;
+      for (int j = 0; j < nkb; ++j) {
+        mbar_wait(smem_u32(&sb[4]), ph_s);
+        ph_s ^= 1u;
+        tc_fence_after();
+        const int k0 = j * ATL_KB;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const bool any = k0 + c * 32 < p.Tk;
+          if (any) tmem_ld32(tm_s + c * 32, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float t = fmaf(v[i], sh.scale_log2, nmx);
+            float e;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+            v[i] = (any && k0 + c * 32 + i < p.Tk) ? e : 0.f;
+            sum += v[i];
+          }
+          const uint32_t blk = p_sa + (uint32_t)(c >> 1) * 16384u + (uint32_t)r * 128u;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int chunk = (c & 1) * 4 + g;
+            sts128(blk + ((chunk ^ (r & 7)) << 4),
+                   make_uint4(pack_bf16x2(v[g * 8], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
+                              pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7])));
+          }
+        }
+        tc_fence_before();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(smem_u32(&sb[6]));   // P_j ready
+        mbar_arrive(smem_u32(&sb[5]));   // S read
+      }
+      // O: nkb completions of bar_o per item, the last one is the finished accumulator
+      ph_o ^= (uint32_t)((nkb - 1) & 1);
+      mbar_wait(smem_u32(&sb[7]), ph_o);
+      ph_o ^= 1u;
+      tc_fence_after();
+      const float inv = 1.f / sum;
+      bf16* orow = reinterpret_cast<bf16*>(p.o) + ((size_t)b * p.q_period + p.q_pad + tq) * p.o_pitch + h * 64;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        tmem_ld32(tm_o + c * 32, v);
+        if (tq < p.Tq) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) =
+                make_uint4(pack_bf16x2(v[g * 8] * inv, v[g * 8 + 1] * inv), pack_bf16x2(v[g * 8 + 2] * inv, v[g * 8 + 3] * inv),
+                           pack_bf16x2(v[g * 8 + 4] * inv, v[g * 8 + 5] * inv), pack_bf16x2(v[g * 8 + 6] * inv, v[g * 8 + 7] * inv));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&sb[8]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 }  // namespace
 
 int g_attn_dbg = 0, g_attn_halves = 1, g_attn_pdl = 1, g_attn_early = 1;
@@ -291,6 +534,8 @@ void attn_tc_set_debug(int v) { if (v == -200 || v == -201) g_attn_early = v == 
 
 struct AttnTcPlan {
   CUtensorMap map_q, map_k, map_v;
+  bool long_keys = false;   // Tk > 256: attn_tc_long_kernel (key blocks, two-pass softmax)
+  AttnLongShape lsh;
   AttnTcShape sh;
   AttnParams p;
   dim3 grid;
@@ -299,12 +544,14 @@ struct AttnTcPlan {
   int pdl;   // programmatic dependent launch, as the option stood when the plan was built
 };
 
+static bool attn_tc_long_capable(const AttnParams& p) { return p.D == 64 && p.Tk > ATL_KB && p.text == nullptr; }
+static bool attn_tc_long(const AttnParams& p) { return attn_tc_long_capable(p) && p.Tk > 256; }
 bool attn_tc_supported(const AttnParams& p) {
-  return (p.D == 64 || p.D == 48) && p.Tk >= 1 && p.Tk <= 256 && p.q_pitch % 8 == 0 && p.k_pitch % 8 == 0 && p.v_pitch % 8 == 0 &&
-         p.o_pitch % 8 == 0;
+  return (((p.D == 64 || p.D == 48) && p.Tk >= 1 && p.Tk <= 256) || attn_tc_long(p)) && p.q_pitch % 8 == 0 && p.k_pitch % 8 == 0 &&
+         p.v_pitch % 8 == 0 && p.o_pitch % 8 == 0;
 }
 
-AttnTcPlan* attn_tc_plan_create(const AttnParams& p, int q_rows, int k_rows, char* err, int errlen) {
+AttnTcPlan* attn_tc_plan_create(const AttnParams& p, int q_rows, int k_rows, char* err, int errlen, int prefer_long) {
   if (!attn_tc_supported(p)) { snprintf(err, errlen, "attention shape not supported by the tcgen05 kernel (D=%d Tk=%d)", p.D, p.Tk); return nullptr; }
   int dev = 0, num_sms = 148;
   cudaGetDevice(&dev);
@@ -312,6 +559,36 @@ AttnTcPlan* attn_tc_plan_create(const AttnParams& p, int q_rows, int k_rows, cha
   AttnTcPlan* a = new AttnTcPlan();
   a->p = p;
   a->pdl = g_attn_pdl;
+  if (prefer_long && !attn_tc_long_capable(p)) { snprintf(err, errlen, "the key-block kernel needs unmasked keys, head depth 64 and Tk > 128"); delete a; return nullptr; }
+  if (attn_tc_long(p) || prefer_long) {
+    a->long_keys = true;
+    AttnLongShape& l = a->lsh;
+    l.nkb = (p.Tk + ATL_KB - 1) / ATL_KB;
+    l.QT = (p.Tq + 127) / 128;
+    l.items = p.B * p.H * l.QT;
+    l.rev = 0;
+    const uint32_t base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
+    l.idesc_s = base | ((uint32_t)(ATL_KB >> 3) << 17);
+    l.idesc_o = base | (1u << 16) | ((uint32_t)(64 >> 3) << 17);   // B = V is MN-major, N = head depth
+    l.scale_log2 = p.scale * 1.4426950408889634f;
+    l.off_k = 16384u; l.off_v = 16384u + 2u * 16384u; l.off_p = l.off_v + 16384u;
+    l.slot_bytes = l.off_p + 32768u;
+    l.off_bar = ATL_SLOTS * l.slot_bytes;
+    a->smem = l.off_bar + (9 * ATL_SLOTS + 2) * 8 + 1024;
+    const int ctas = (l.items + ATL_SLOTS - 1) / ATL_SLOTS;
+    a->grid = dim3(ctas < num_sms ? ctas : num_sms);
+    a->threads = ATL_SLOTS * 160;
+    const uint64_t cols = (uint64_t)p.H * p.D;
+    if (!make_map(&a->map_q, p.q, (uint64_t)q_rows, cols, (uint64_t)p.q_pitch, 128, err, errlen) ||
+        !make_map(&a->map_k, p.k, (uint64_t)k_rows, cols, (uint64_t)p.k_pitch, ATL_KB, err, errlen) ||
+        !make_map(&a->map_v, p.v, (uint64_t)k_rows, cols, (uint64_t)p.v_pitch, ATL_KB, err, errlen)) {
+      delete a;
+      return nullptr;
+    }
+    cudaError_t ce = cudaFuncSetAttribute(attn_tc_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (ce != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); delete a; return nullptr; }
+    return a;
+  }
   AttnTcShape& sh = a->sh;
   sh.N = (p.Tk + 15) & ~15;
   sh.nblk = (sh.N + 63) / 64;
@@ -364,7 +641,8 @@ AttnTcPlan* attn_tc_plan_create(const AttnParams& p, int q_rows, int k_rows, cha
 }
 
 void attn_tc_plan_destroy(AttnTcPlan* a) { delete a; }
-void attn_tc_plan_set_reverse(AttnTcPlan* a, int rev) { a->sh.rev = rev ? 1 : 0; }
+bool attn_tc_plan_is_long(const AttnTcPlan* a) { return a->long_keys; }
+void attn_tc_plan_set_reverse(AttnTcPlan* a, int rev) { a->sh.rev = rev ? 1 : 0; a->lsh.rev = rev ? 1 : 0; }
 void attn_tc_plan_set_early_load(AttnTcPlan* a, int on) { a->sh.early = on ? 1 : 0; }
 
 int attn_tc_launch(const AttnTcPlan* a, cudaStream_t st) {
@@ -378,6 +656,7 @@ int attn_tc_launch(const AttnTcPlan* a, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = a->pdl ? 1 : 0;
+  if (a->long_keys) return cudaLaunchKernelEx(&cfg, attn_tc_long_kernel, a->map_q, a->map_k, a->map_v, a->lsh, a->p) == cudaSuccess ? 0 : 1;
   return cudaLaunchKernelEx(&cfg, attn_tc_kernel, a->map_q, a->map_k, a->map_v, a->sh, a->p) == cudaSuccess ? 0 : 1;
 }
 

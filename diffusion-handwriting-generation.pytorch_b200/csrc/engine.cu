@@ -745,26 +745,37 @@ struct Builder {
 
   // When to request the next item's Q / K / V tiles (attention_tc.cu): right after P V helps the shapes with few slots
   // per SM and costs a little where 4-6 items are in flight anyway, so it is timed per shape like the GEMM tiles.
-  int attention_pick_early(AttnTcPlan* ap) {
+  float attention_time(AttnTcPlan* ap) {   // ms per launch, < 0 on failure
     cudaStream_t st = P->cap_stream;
     cudaEvent_t e0, e1;
-    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return -1;
-    float t[2] = {0.f, 0.f};
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return -1.f;
     bool ok = true;
-    for (int v = 0; v < 2 && ok; ++v) {
-      attn_tc_plan_set_early_load(ap, v);
-      for (int i = 0; i < 2 && ok; ++i) ok = attn_tc_launch(ap, st) == 0;
-      cudaEventRecord(e0, st);
-      for (int i = 0; i < 4 && ok; ++i) ok = attn_tc_launch(ap, st) == 0;
-      cudaEventRecord(e1, st);
-      ok = ok && cudaEventSynchronize(e1) == cudaSuccess;
-      if (ok) cudaEventElapsedTime(&t[v], e0, e1);
-    }
+    float t = 0.f;
+    for (int i = 0; i < 2 && ok; ++i) ok = attn_tc_launch(ap, st) == 0;
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < 4 && ok; ++i) ok = attn_tc_launch(ap, st) == 0;
+    cudaEventRecord(e1, st);
+    ok = ok && cudaEventSynchronize(e1) == cudaSuccess;
+    if (ok) cudaEventElapsedTime(&t, e0, e1);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    if (!ok) return -1;
-    if (getenv("DHG_DESCRIBE")) fprintf(stderr, "autotune attention: late load %.1f us, early load %.1f us\n", t[0] * 250.f, t[1] * 250.f);
-    return t[1] < t[0] * 0.985f ? 1 : 0;
+    return ok ? t / 4.f : -1.f;
+  }
+  // Variant of the attention launch for this shape, timed on the plan's buffers like the GEMM tiles: 0 / 1 = all keys
+  // at once, next item's tiles requested after O is stored / right after P V; 2 = key-block kernel (where it applies)
+  int attention_pick(AttnTcPlan* ap, AttnTcPlan* ap_long) {
+    float t[3] = {-1.f, -1.f, -1.f};
+    if (attn_tc_plan_is_long(ap)) return 2;
+    for (int v = 0; v < 2; ++v) {
+      attn_tc_plan_set_early_load(ap, v);
+      t[v] = attention_time(ap);
+      if (t[v] < 0.f) return -1;
+    }
+    if (ap_long) { t[2] = attention_time(ap_long); if (t[2] < 0.f) return -1; }
+    if (getenv("DHG_DESCRIBE")) fprintf(stderr, "autotune attention: late load %.1f us, early load %.1f us, key blocks %.1f us\n", t[0] * 1e3f, t[1] * 1e3f, t[2] * 1e3f);
+    int best = t[1] < t[0] * 0.985f ? 1 : 0;
+    if (ap_long && t[2] < t[best] * 0.985f) best = 2;
+    return best;
   }
 
   // k / v may exist in several copies (text sets); the launch picks sc.text_set.
@@ -774,7 +785,7 @@ struct Builder {
     if (failed) return;
     std::vector<AttnParams> a(nsets);
     std::vector<AttnTcPlan*> plans(nsets, nullptr);
-    int early = 1;
+    int variant = 1;
     Plan* Pl = P;
     *nlaunch += 1;
     bool tc = false;
@@ -793,9 +804,21 @@ struct Builder {
         attn_tc_plan_set_reverse(plans[s], dir);
         wrote(o.p, dir);
         if (g_opt_autotune) {
-          if (s == 0) early = attention_pick_early(plans[0]);
-          if (early < 0) { fail("plan: attention autotune launch failed: %s", cudaGetErrorString(cudaGetLastError())); failed = true; return; }
-          attn_tc_plan_set_early_load(plans[s], early);
+          if (s == 0) {
+            AttnTcPlan* alt = attn_tc_plan_create(a[s], q_rows, k_rows, buf, sizeof(buf), 1);   // null where the key-block kernel does not apply
+            if (alt) attn_tc_plan_set_reverse(alt, dir);
+            variant = attention_pick(plans[0], alt);
+            if (alt) attn_tc_plan_destroy(alt);
+          }
+          if (variant < 0) { fail("plan: attention autotune launch failed: %s", cudaGetErrorString(cudaGetLastError())); failed = true; return; }
+          if (variant == 2 && !attn_tc_plan_is_long(plans[s])) {
+            attn_tc_plan_destroy(plans[s]);
+            plans[s] = attn_tc_plan_create(a[s], q_rows, k_rows, buf, sizeof(buf), 1);
+            if (!plans[s]) { fail("plan: tcgen05 attention: %s", buf); failed = true; return; }
+            attn_tc_plan_set_reverse(plans[s], dir);
+          } else if (variant < 2) {
+            attn_tc_plan_set_early_load(plans[s], variant);
+          }
         }
         P->attn_plans.push_back(plans[s]);
         tc = true;
@@ -1896,9 +1919,9 @@ int32_t dhg_debug_attention(int32_t device, const dhg_debug_attn* d, int32_t imp
   a.text = d->text;
   cudaStream_t st = (cudaStream_t)stream;
   AttnTcPlan* ap = nullptr;
-  if (impl == 1) {
+  if (impl >= 1) {   // 2: the key-block kernel also where all keys would fit at once (128 < Tk <= 256)
     char buf[512];
-    ap = attn_tc_plan_create(a, d->q_rows, d->k_rows, buf, sizeof(buf));
+    ap = attn_tc_plan_create(a, d->q_rows, d->k_rows, buf, sizeof(buf), impl == 2 ? 1 : 0);
     if (!ap) return fail("dhg_debug_attention: %s", buf);
   }
   auto launch = [&]() -> int { return ap ? attn_tc_launch(ap, st) : launch_attention_simt<bf16>(a, st); };

@@ -99,11 +99,14 @@ void tc_gemm_describe(const TcGemmPlan*, char* out, int n);
 int tc_gemm_launch(const TcGemmPlan*, const Epilogue& e, cudaStream_t st);
 void tc_gemm_set_option(int which, int value);   // 2 w_resident, 3 specialize, 4 interleave, 6 pdl, 7 pair; 10..13 forced TcTune {bn, g, resident, pair}
 
-// tcgen05 attention for head depth 64 and Tk <= 256 (attention_tc.cu).  q_rows / k_rows: total rows
+// tcgen05 attention for head depth 64 / 48 (attention_tc.cu): all keys at once for Tk <= 256, key blocks beyond.  q_rows / k_rows: total rows
 // of the q / k,v row matrices (TMA bounds).
 struct AttnTcPlan;
 bool attn_tc_supported(const AttnParams& p);
-AttnTcPlan* attn_tc_plan_create(const AttnParams& p, int q_rows, int k_rows, char* err, int errlen);
+// prefer_long: use the key-block kernel (two-pass softmax over blocks of 128 keys; always used for Tk > 256) also for
+// 128 < Tk <= 256 (unmasked, head depth 64); the engine times both at plan time
+AttnTcPlan* attn_tc_plan_create(const AttnParams& p, int q_rows, int k_rows, char* err, int errlen, int prefer_long = 0);
+bool attn_tc_plan_is_long(const AttnTcPlan*);
 void attn_tc_plan_destroy(AttnTcPlan*);
 void attn_tc_plan_set_reverse(AttnTcPlan*, int rev);   // work items from the last sample to the first
 void attn_tc_plan_set_early_load(AttnTcPlan*, int on);   // next item's Q/K/V requested right after P V (default) or after O is stored

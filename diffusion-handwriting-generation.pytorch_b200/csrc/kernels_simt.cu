@@ -665,16 +665,19 @@ __global__ void __launch_bounds__(256, DHG_HEADS_MINB) heads_update_kernel(const
 }
 // Tail fusion, level 2: the three head values of a point are already sitting in two [rows, 4] fp32 arrays (dot mode of
 // the last ConvBlock's conv2 and conv_skip GEMMs): eps | pen = dot_a[row] + dot_b[row] + c.  What is left is the
-// posterior update and input_dense of the next step: 16 lanes per point, 8 channels each, like heads_update_kernel.
+// posterior update and input_dense of the next step.  A warp owns 32 consecutive points: lane i does the scalar work of
+// point i (coalesced 16-byte / 8-byte loads, one update per lane instead of one per 16 lanes), then the warp writes the
+// 32 next-step input rows one after the other, lane = 4 of the C = 128 channels (one 256-byte row per store
+// instruction): ~30 warp instructions per point instead of ~75, the kernel is a store stream (C * 2 B per point and copy).
 template <typename T_>
 __global__ void __launch_bounds__(256) heads_from_dots_kernel(const float4* __restrict__ dot_a, const float4* __restrict__ dot_b,
                                                               const float* __restrict__ cst /*[3]*/, int C, HeadParams p) {
-  const int lane = threadIdx.x & 31, sub = lane & 15, grp = lane >> 4;
-  const int c0 = sub * 8;
-  float iw0[8], iw1[8], ib[8];
+  const int lane = threadIdx.x & 31;
+  const int c0 = lane * 4;
+  float iw0[4], iw1[4], ib[4];
   const bool next_in = p.next_raw != nullptr || p.next_act != nullptr;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
+  for (int k = 0; k < 4; ++k) {
     iw0[k] = next_in ? p.in_W[(c0 + k) * 2] : 0.f;
     iw1[k] = next_in ? p.in_W[(c0 + k) * 2 + 1] : 0.f;
     ib[k] = next_in ? p.in_b[c0 + k] : 0.f;
@@ -682,29 +685,17 @@ __global__ void __launch_bounds__(256) heads_from_dots_kernel(const float4* __re
   const float b0 = cst[0], b1 = cst[1], bpv = cst[2];
   const float r_div = 1.f / p.c_div, r_eps2 = p.c_eps2 != 0.f ? 1.f / p.c_eps2 : 0.f;
   const uint32_t npts = (uint32_t)p.B * (uint32_t)p.T, T = (uint32_t)p.T;
-  const uint32_t stride = ((gridDim.x * blockDim.x) >> 5) * 2;
-  const uint32_t stride_b = stride / T, stride_t = stride - stride_b * T;
-  // the inputs of the NEXT point are requested before the current one is worked on (the kernel is a latency chain
-  // otherwise); (sample, position) advance incrementally, one division per thread
-  uint32_t i = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 2 + grp;
-  uint32_t b = i / T, t = i - b * T;
-  float4 da_n = make_float4(0.f, 0.f, 0.f, 0.f), db_n = da_n;
-  float2 xx_n = make_float2(0.f, 0.f), zz_n = xx_n;
-  auto fetch = [&](uint32_t ii, uint32_t bb) {
-    const size_t r = (size_t)ii + bb + 1;
-    da_n = dot_a[r]; db_n = dot_b[r];
-    if (p.x_io) xx_n = *reinterpret_cast<const float2*>(p.x_io + (size_t)ii * 2);
-    if (p.noise) zz_n = *reinterpret_cast<const float2*>(p.noise + (size_t)ii * 2);
-  };
-  if (i < npts) fetch(i, b);
-  for (; i < npts;) {
-    const size_t row = (size_t)i + b + 1;
-    const float4 da = da_n, db = db_n;
-    const float2 xx = xx_n, zz = zz_n;
-    const uint32_t i_cur = i;
-    i += stride; b += stride_b; t += stride_t;
-    if (t >= T) { t -= T; ++b; }
-    if (i < npts) fetch(i, b);
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; base < npts; base += warps * 32u) {
+    const uint32_t i = base + lane;
+    const bool ok = i < npts;
+    const uint32_t ii = ok ? i : npts - 1;
+    const uint32_t b = ii / T;
+    const uint32_t row = ii + b + 1;   // point i = b * T + t lives in row b * (T + 1) + 1 + t
+    const float4 da = dot_a[row], db = dot_b[row];
+    float2 xx = make_float2(0.f, 0.f), zz = xx;
+    if (p.x_io) xx = *reinterpret_cast<const float2*>(p.x_io + (size_t)ii * 2);
+    if (p.noise) zz = *reinterpret_cast<const float2*>(p.noise + (size_t)ii * 2);
     const float e0 = da.x + db.x + b0, e1 = da.y + db.y + b1, pl = da.z + db.z + bpv;
     float y0 = 0.f, y1 = 0.f;
     if (p.x_io) {
@@ -717,30 +708,36 @@ __global__ void __launch_bounds__(256) heads_from_dots_kernel(const float4* __re
         y1 = fmaf(p.c_noise, zz.y, p.c_div * (xx.y - p.c_eps * e1 * r_eps2));
       }
     }
-    if (sub == 0) {
-      if (p.eps_out) { p.eps_out[(size_t)i_cur * 2] = e0; p.eps_out[(size_t)i_cur * 2 + 1] = e1; }
-      if (p.pen_out) p.pen_out[(size_t)i_cur * p.pen_stride + p.pen_offset] = 1.f / (1.f + expf(-pl));
+    if (ok) {
+      if (p.eps_out) *reinterpret_cast<float2*>(p.eps_out + (size_t)i * 2) = make_float2(e0, e1);
+      if (p.pen_out) p.pen_out[(size_t)i * p.pen_stride + p.pen_offset] = 1.f / (1.f + expf(-pl));
       if (p.x_io) {
         float* xo = p.x_out ? p.x_out : p.x_io;
-        xo[(size_t)i_cur * p.x_out_stride] = y0;
-        xo[(size_t)i_cur * p.x_out_stride + 1] = y1;
+        xo[(size_t)i * p.x_out_stride] = y0;
+        xo[(size_t)i * p.x_out_stride + 1] = y1;
       }
     }
     if (next_in) {
-      float v[8];
+      const uint32_t nvalid = npts - base < 32u ? npts - base : 32u;   // warp-uniform
+      T_* raw = reinterpret_cast<T_*>(p.next_raw);
+      T_* act = reinterpret_cast<T_*>(p.next_act);
+#pragma unroll 4
+      for (uint32_t j = 0; j < nvalid; ++j) {
+        const float yj0 = __shfl_sync(0xffffffffu, y0, j), yj1 = __shfl_sync(0xffffffffu, y1, j);
+        const size_t off = (size_t)__shfl_sync(0xffffffffu, row, j) * C + c0;
+        float v[4];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = fmaf(y1, iw1[k], fmaf(y0, iw0[k], ib[k]));
-      if (p.next_raw) store8<T_>(reinterpret_cast<T_*>(p.next_raw) + row * C + c0, v);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = silu_out<T_>(v[k]);
-      if (p.next_act) store8<T_>(reinterpret_cast<T_*>(p.next_act) + row * C + c0, v);
+        for (int k = 0; k < 4; ++k) v[k] = fmaf(yj1, iw1[k], fmaf(yj0, iw0[k], ib[k]));
+        if (raw) store4<T_>(raw + off, make_float4(v[0], v[1], v[2], v[3]));
+        if (act) store4<T_>(act + off, make_float4(silu_out<T_>(v[0]), silu_out<T_>(v[1]), silu_out<T_>(v[2]), silu_out<T_>(v[3])));
+      }
     }
   }
 }
 template <typename T>
 int launch_heads_from_dots(const float* dot_a, const float* dot_b, const float* cst, int C, const HeadParams& p, cudaStream_t st) {
   if (C != 128) return 1;
-  const size_t nw = ((size_t)p.B * p.T + 1) / 2;
+  const size_t nw = ((size_t)p.B * p.T + 31) / 32;   // one warp per 32 points
   size_t blocks = (nw + 7) / 8;
   if (blocks > 148 * 16) blocks = 148 * 16;
   heads_from_dots_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(dot_a), reinterpret_cast<const float4*>(dot_b), cst, C, p);

@@ -72,6 +72,12 @@ CASES = [
     ("self_small", 3, 3, 64, 32, 32, True, False),
     ("self_tiny", 2, 6, 64, 8, 8, True, False),
     ("self_256", 2, 3, 64, 256, 256, True, False),
+    # Tk > 256: key blocks of 128 with a two-pass softmax (attn_tc_long_kernel); BASELINE configs[4]: T = 1200 -> 600 / 300 keys
+    ("self_600_c5_L1", 3, 3, 64, 600, 600, True, False),
+    ("self_300_c5_L2", 4, 4, 64, 300, 300, True, False),
+    ("self_257", 2, 3, 64, 257, 257, True, False),
+    ("self_384_exact_blocks", 2, 6, 64, 384, 384, True, False),
+    ("self_1000_many_items", 40, 3, 64, 1000, 1000, True, False),
     ("cross_L1", 5, 3, 64, 196, 24, False, True),
     ("cross_L3", 9, 6, 64, 49, 24, False, True),
     ("cross_L81", 4, 4, 64, 150, 81, False, True),
@@ -93,3 +99,11 @@ def test_text_style_attention_depth48(built_lib, impl):
     got, ref, _ = run_attention(built_lib, 6, 8, 48, 24, 70, False, False, impl, seed=5)
     assert torch.isfinite(got).all()
     assert (got - ref).abs().max().item() < 3e-2
+
+
+@pytest.mark.parametrize("name,B,H,Tq", [("self_L1", 5, 3, 196), ("self_256", 2, 3, 256), ("self_129", 3, 4, 129), ("self_600", 2, 3, 600)])
+def test_key_block_kernel_where_all_keys_would_fit(built_lib, name, B, H, Tq):
+    """The engine times the key-block kernel against the all-keys-at-once kernel for 128 < Tk <= 256 and keeps the faster."""
+    got, ref, _ = run_attention(built_lib, B, H, 64, Tq, Tq, True, False, 2, seed=len(name) + Tq)
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() < 3e-2, name
