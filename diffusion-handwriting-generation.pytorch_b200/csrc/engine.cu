@@ -1831,9 +1831,11 @@ int32_t dhg_debug_tc_gemm_ex(int32_t device, const void* a, int32_t lda, int32_t
   e.out_act = d->out_act; e.out_act_pitch = d->out_act_pitch;
   e.dot_w = d->dot_w; e.dot_out = d->dot_out; e.dot_act = d->dot_act; e.dot_planned = d->dot_w ? 1 : 0;
   e.split_io = d->split_io;
+  e.w_row_off = d->w_row_off;
   e.map = RowMap{d->period > 0 ? d->period : (rows > 0 ? rows : 1), d->pad_first, d->nvalid > 0 ? d->nvalid : rows};
   char buf[512];
-  TcGemmPlan* p = tc_gemm_plan_create((const bf16*)a, lda, rows, (const bf16*)w, K, N, taps, e, buf, sizeof(buf));
+  TcDual dual{(const bf16*)d->dual_a2, d->dual_lda2, d->dual_K2, (const bf16*)d->dual_w2, d->dual_w1_rows};
+  TcGemmPlan* p = tc_gemm_plan_create((const bf16*)a, lda, rows, (const bf16*)w, K, N, taps, e, buf, sizeof(buf), nullptr, d->dual_a2 ? &dual : nullptr);
   if (!p) return fail("dhg_debug_tc_gemm_ex: %s", buf);
   cudaStream_t st = (cudaStream_t)stream;
   if (getenv("DHG_DESCRIBE")) { tc_gemm_describe(p, buf, sizeof(buf)); fprintf(stderr, "tc_gemm plan: %s\n", buf); }

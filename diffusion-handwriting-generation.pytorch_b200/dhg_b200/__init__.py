@@ -11,10 +11,11 @@ from .checkpoint import DiffusionModel, load_model
 from .config import DLConfig
 from .diffusion import NUM_STEPS, get_alpha_bar, get_beta_set
 from .inference import infer, resolve_experiment
+from .style import StyleExtractor, read_img, remove_whitespace
 from .tokenizer import Tokenizer, stroke_length
 from .writer import DiffusionWriter
 
 __all__ = [
     "DiffusionWriter", "DiffusionModel", "load_model", "infer", "resolve_experiment", "Tokenizer",
-    "stroke_length", "DLConfig", "get_beta_set", "get_alpha_bar", "NUM_STEPS",
+    "stroke_length", "DLConfig", "StyleExtractor", "read_img", "remove_whitespace", "get_beta_set", "get_alpha_bar", "NUM_STEPS",
 ]

@@ -23,6 +23,7 @@ class DebugEpilogue(ctypes.Structure):
         ("res_post_up", c_i32), ("res_post_period_lo", c_i32), ("out_raw", c_vp), ("out_raw_pitch", c_i32),
         ("out_act", c_vp), ("out_act_pitch", c_i32), ("period", c_i32), ("pad_first", c_i32), ("nvalid", c_i32),
         ("dot_w", c_vp), ("dot_out", c_vp), ("dot_act", c_i32), ("split_io", c_i32),
+        ("dual_a2", c_vp), ("dual_lda2", c_i32), ("dual_K2", c_i32), ("dual_w2", c_vp), ("dual_w1_rows", c_i32), ("w_row_off", c_i32),
     ]
 
 
@@ -65,6 +66,12 @@ SIGNATURES = {
     "dhg_debug_attention": (c_i32, [c_i32, ctypes.POINTER(DebugAttn), c_i32, c_i32, ctypes.POINTER(ctypes.c_float), c_vp]),
     "dhg_debug_tc_gemm_ex": (c_i32, [c_i32, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, ctypes.POINTER(DebugEpilogue),
                                      c_i32, ctypes.POINTER(ctypes.c_float), c_vp]),
+    "dhg_style_last_error": (c_cp, []),
+    "dhg_style_create": (c_i32, [c_i32, ctypes.POINTER(c_vp)]),
+    "dhg_style_destroy": (c_i32, [c_vp]),
+    "dhg_style_load_weight": (c_i32, [c_vp, c_cp, c_vp, ctypes.POINTER(c_i64), c_i32]),
+    "dhg_style_finalize": (c_i32, [c_vp]),
+    "dhg_style_extract": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
 }
 
 

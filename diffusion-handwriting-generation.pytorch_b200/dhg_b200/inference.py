@@ -1,11 +1,12 @@
 """`infer()` with the reference's signature and checkpoint discovery
 (inference.py:19-98), running the chain on the B200 engine.
 
-Differences forced by the environment, not by design: the reference derives the
-style vector from a handwriting image with a pretrained MobileNetV2
-(text_style.py:11-59) whose weights cannot be fetched offline, so `source` may
-also be a `.pt`/`.npy` file holding a precomputed [14,1280] (or [1,14,1280])
-style tensor; and the PNG is rasterised by `vis.save_strokes_png` because
+`source` is the reference's writer image (read_img(source, 96) -> StyleExtractor,
+inference.py:67-70; here `dhg_b200.style`, CUDA).  The reference downloads the
+pretrained MobileNetV2 weights at that point; offline they come from `style_weights`
+(a torchvision mobilenet_v2 state_dict or its path) or DHG_MOBILENET_WEIGHTS.
+`source` may also be a `.pt`/`.npy` file holding a precomputed [14,1280] (or
+[1,14,1280]) style tensor.  The PNG is rasterised by `vis.save_strokes_png` because
 matplotlib is not installed.
 """
 from pathlib import Path
@@ -45,7 +46,7 @@ def resolve_experiment(config_path=None, checkpoint_path=None, experiment_path=N
     return config_path, checkpoint_path
 
 
-def load_style(source):
+def load_style(source, style_weights=None, device="cuda:0"):
     if isinstance(source, torch.Tensor):
         s = source
     elif str(source).endswith(".npy"):
@@ -54,20 +55,22 @@ def load_style(source):
         s = torch.from_numpy(np.load(source))
     elif str(source).endswith((".pt", ".pth")):
         s = torch.load(source, map_location="cpu")
-    else:
-        raise NotImplementedError(
-            "style extraction from an image needs the pretrained MobileNetV2 of the reference's "
-            "StyleExtractor, which is outside this path; pass a precomputed [14,1280] style tensor (.pt/.npy)"
-        )
+    else:   # a writer image: inference.py:67-70
+        from .style import StyleExtractor, read_img
+
+        extractor = StyleExtractor(style_weights, device=device)
+        writer_img = read_img(source, 96)[None, None, :]
+        s = extractor(writer_img).cpu()
+        extractor.close()
     s = s.float()
     return s[None] if s.dim() == 2 else s
 
 
 def infer(prompt, source, config_path=None, checkpoint_path=None, experiment_path=None, output="result",
-          diffusion_mode="new", *, dtype="fp32", device="cuda:0", seed=None):
+          diffusion_mode="new", *, dtype="fp32", device="cuda:0", seed=None, style_weights=None):
     config_path, checkpoint_path = resolve_experiment(config_path, checkpoint_path, experiment_path)
     writer = DiffusionWriter(config_path, checkpoint_path, dtype=dtype, device=device)
-    style = load_style(source)
+    style = load_style(source, style_weights, device)
     ids = Tokenizer().encode(prompt)
     text = torch.tensor([ids])
     strokes = writer.sample(text, style, T=stroke_length(len(ids)), diffusion_mode=diffusion_mode, seed=seed)
@@ -99,13 +102,15 @@ def main(argv=None):
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--device", default="cuda:0")
     ap.add_argument("--seed", type=int, default=None)
+    ap.add_argument("--style_weights", "--style-weights", dest="style_weights", default=None,
+                    help="torchvision mobilenet_v2 weights file for an image --source (default: $DHG_MOBILENET_WEIGHTS)")
     a = ap.parse_args(argv)
     prompt = a.prompt if a.prompt is not None else a.prompt_pos
     source = a.source if a.source is not None else a.source_pos
     if prompt is None or source is None:
         ap.error("prompt and source are required (infer(prompt, source, ...), inference.py:19-27)")
     strokes = infer(prompt, source, a.config_path, a.checkpoint_path, a.experiment_path, a.output, a.diffusion_mode,
-                    dtype=a.dtype, device=a.device, seed=a.seed)
+                    dtype=a.dtype, device=a.device, seed=a.seed, style_weights=a.style_weights)
     print(f"wrote ./{a.output}.png ({strokes.shape[0]} stroke points)")
     return 0
 

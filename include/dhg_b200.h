@@ -201,6 +201,13 @@ typedef struct dhg_debug_epilogue {
    * {bf16 hi, bf16 lo} pairs, value = hi + lo; pitches stay in elements; the caller passes K = 2 * (elements per A row),
    * lda in bf16 units and W as [2 taps][N][K]: slab t = (w_hi, w_hi) interleaved along K, slab taps + t = (w_lo, 0). */
   int32_t split_io;
+  /* dual-operand mode: out = A . W[w_row_off : w_row_off + N]^T + sum_tap A2[row + tap - 1] . W2[tap]^T + bias, one
+   * accumulation (taps must be 1; bias-only epilogue).  W is a stack of dual_w1_rows / N variants of [N, K]; A2 is
+   * bf16 [rows, dual_K2] (pitch dual_lda2) in the same padded-row layout, W2 bf16 [3][N][dual_K2].  NULL dual_a2 = off. */
+  const void* dual_a2;
+  int32_t dual_lda2, dual_K2;
+  const void* dual_w2;
+  int32_t dual_w1_rows, w_row_off;
 } dhg_debug_epilogue;
 int32_t dhg_debug_tc_gemm_ex(int32_t device, const void* dev_a_bf16, int32_t lda, int32_t rows,
                              const void* dev_w_bf16, int32_t K, int32_t N, int32_t taps,
@@ -224,6 +231,21 @@ int32_t dhg_debug_time_text(dhg_ctx* ctx, int32_t sets, int32_t repeats, float* 
 
 int32_t dhg_debug_attention(int32_t device, const dhg_debug_attn* a, int32_t impl, int32_t repeats,
                             float* ms_per_launch, void* stream);
+
+/* ---- StyleExtractor: the step right before the sampling path ----------------------------------
+ * Replaces: StyleExtractor.forward, text_style.py:43-59 -- torchvision MobileNetV2 `features` in eval mode on the grey
+ * writer image (x / 127.5 - 1, repeated to 3 channels), AvgPool2d(3, 3), AdaptiveAvgPool2d((1, 14)) -> [B, 14, 1280].
+ * Weights: the `features.*` entries of a torchvision mobilenet_v2 state_dict (conv weights and BatchNorm weight / bias /
+ * running_mean / running_var; other keys are ignored), fp32 host pointers; BatchNorm is folded at finalize.
+ * dhg_style_extract: host_img fp32 [B, H, W] grey levels 0..255 (read_img(path, 96), utils/io.py:98-115, gives H = 96)
+ * -> dev_out fp32 [B, 14, 1280] on the device; stream-ordered.  Errors: dhg_style_last_error(). */
+typedef struct dhg_style dhg_style;
+const char* dhg_style_last_error(void);
+int32_t dhg_style_create(int32_t device, dhg_style** out);
+int32_t dhg_style_destroy(dhg_style* s);
+int32_t dhg_style_load_weight(dhg_style* s, const char* name, const float* host_data, const int64_t* shape, int32_t ndim);
+int32_t dhg_style_finalize(dhg_style* s);
+int32_t dhg_style_extract(dhg_style* s, const float* host_img, int32_t B, int32_t H, int32_t W, float* dev_out, void* stream);
 
 #ifdef __cplusplus
 }

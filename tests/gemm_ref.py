@@ -54,7 +54,7 @@ def make_split_case(rows, K, N, taps, **kw):
 
 
 def make_case(rows, K, N, taps, *, period=None, pad_first=0, bias=True, rowbias=False, res_pre=False, ln=False,
-              film=0, res_post=False, up=False, raw=True, act=False, dot=0, seed=0, device="cuda"):
+              film=0, res_post=False, up=False, raw=True, act=False, dot=0, seed=0, device="cuda", dual_K2=0, variants=3):
     """film: 0 none, 1 one vector for the batch (bstride 0), 2 per-sample vectors.
     dot: 0 normal stores; 1 / 2 dot mode on the value / on SiLU(value) (no stored outputs)."""
     g = torch.Generator().manual_seed(seed)
@@ -97,6 +97,16 @@ def make_case(rows, K, N, taps, *, period=None, pad_first=0, bias=True, rowbias=
     c["dot_act"] = 1 if dot == 2 else 0
     c["dot_w"] = (torch.randn(3, N, generator=g) / N ** 0.5).to(device) if dot else None
     c["dot_out"] = torch.full((rows, 4), float("nan"), device=device) if dot else None
+    # dual-operand mode: a second A matrix against 3-tap weights joins the accumulation; the first operand's weights
+    # are one of `variants` stacked [N, K] matrices (engine.cu: fc with the step's FiLM scale folded in)
+    c["dual_K2"] = dual_K2
+    if dual_K2:
+        a2 = torch.randn(rows, dual_K2, generator=g)
+        a2[pad] = 0
+        c["a2"] = a2.bfloat16().to(device)
+        c["w2"] = (torch.randn(3, N, dual_K2, generator=g) / (3 * dual_K2) ** 0.5).bfloat16().to(device)
+        c["w"] = (torch.randn(variants, N, K, generator=g) / K ** 0.5).bfloat16().to(device)
+        c["variant"] = variants - 1
     return c
 
 
@@ -110,6 +120,15 @@ def reference(c):
     else:
         af, wf = c["a"].float(), c["w"].float()
     x = torch.zeros(rows, N, device=af.device, dtype=af.dtype)
+    if c.get("dual_K2"):
+        wf = wf[c["variant"]:c["variant"] + 1]
+        a2, w2 = c["a2"].float(), c["w2"].float()
+        for t in range(3):
+            shift = t - 1
+            src = torch.zeros_like(a2)
+            lo, hi = max(0, -shift), min(rows, rows - shift)
+            src[lo:hi] = a2[lo + shift:hi + shift]
+            x += src @ w2[t].T
     for t in range(taps):
         shift = t - taps // 2
         src = torch.zeros_like(af)
@@ -150,7 +169,9 @@ def run(lib, c, repeats=0, allow_unavailable=False):
         p(c["bias"]), p(c["rowbias"]), c["rowbias_cols"], p(c["res_pre"]), N, int(c["ln"]), p(c["gamma"]), p(c["beta"]), c["bstride"],
         p(c["res_post"]), N, int(c["up"]), c["period_lo"], p(c["out_raw"]), N, p(c["out_act"]), N,
         c["period"], c["pad_first"], c["nvalid"], p(c.get("dot_w")), p(c.get("dot_out")), int(c.get("dot_act", 0)),
-        1 if c.get("split") else 0)
+        1 if c.get("split") else 0,
+        p(c.get("a2")), c.get("dual_K2", 0), c.get("dual_K2", 0), p(c.get("w2")), (c["w"].shape[0] * N) if c.get("dual_K2") else 0,
+        (c["variant"] * N) if c.get("dual_K2") else 0)
     ms = ctypes.c_float(0)
     km = 2 if c.get("split") else 1   # split I/O: K and lda in bf16 units, two weight slabs per tap
     rc = lib.dhg_debug_tc_gemm_ex(0, p(c["a"]), km * c["K"], c["rows"], p(c["w"]), km * c["K"], N, km * c["taps"], ctypes.byref(e),

@@ -121,6 +121,33 @@ def test_tc_gemm_split_io_meets_fp32_contract(built_lib, name, rows, K, N, taps,
         assert err < 1e-4 * scale, (name, "act", err)
 
 
+DUAL_CASES = [
+    # the five ConvBlocks whose conv_skip is contracted inside their last GEMM (engine.cu skip fusion): K = Cout, K2 = Cin
+    ("dual_enc1", 3000, 128, 128, 1, dict(period=393, pad_first=1, dual_K2=128)),
+    ("dual_enc2", 1971, 192, 192, 1, dict(period=197, pad_first=1, dual_K2=128)),
+    ("dual_enc4", 991, 256, 256, 1, dict(period=99, pad_first=1, dual_K2=192)),
+    ("dual_dec3", 991, 256, 256, 1, dict(period=99, pad_first=1, dual_K2=384, act=True)),
+    ("dual_dec2", 1971, 192, 192, 1, dict(period=197, pad_first=1, dual_K2=256)),
+    ("dual_many_tiles", 40000, 128, 128, 1, dict(period=393, pad_first=1, dual_K2=128)),
+    ("dual_many_tiles_192", 30000, 192, 192, 1, dict(period=197, pad_first=1, dual_K2=256)),
+]
+
+
+@pytest.mark.parametrize("name,rows,K,N,taps,kw", DUAL_CASES, ids=[c[0] for c in DUAL_CASES])
+def test_tc_gemm_dual_operand(built_lib, name, rows, K, N, taps, kw):
+    """Dual-operand mode: a2 . W1[variant]^T + conv3(x, W2) + bias in one accumulation (two A matrices, two tensor maps)."""
+    import gemm_ref
+
+    c = gemm_ref.make_case(rows, K, N, taps, seed=len(name) + rows, **kw)
+    gemm_ref.run(built_lib, c)
+    ref = gemm_ref.reference(c)
+    scale = max(1.0, ref.abs().max().item())
+    assert torch.isfinite(c["out_raw"].float()).all()
+    assert (c["out_raw"].float() - ref).abs().max().item() < 2e-2 * scale, name
+    if c["out_act"] is not None:
+        assert (c["out_act"].float() - torch.nn.functional.silu(ref)).abs().max().item() < 2e-2 * scale, name
+
+
 DOT_CASES = [
     ("dot_conv_skip", 3000, 192, 128, 3, dict(period=393, pad_first=1, dot=1)),
     ("dot_conv2_film_act", 3000, 64, 128, 3, dict(period=393, pad_first=1, film=1, dot=2)),
@@ -162,6 +189,8 @@ TUNE_CASES = [
     ("ln_film_respost_192", 20685, 192, 192, 1, dict(period=197, pad_first=1, ln=True, film=1, res_post=True)),
     ("ln_film_respre_256_act", 19999, 512, 256, 1, dict(period=99, pad_first=1, ln=True, film=1, res_pre=True, act=True)),
     ("ln_film_k768_384_act", 20050, 768, 384, 1, dict(period=50, pad_first=1, ln=True, film=1, raw=False, act=True)),
+    ("dual_fc_conv_skip_192", 20685, 192, 192, 1, dict(period=197, pad_first=1, dual_K2=256)),
+    ("dual_fc_conv_skip_128", 19999, 128, 128, 1, dict(period=393, pad_first=1, dual_K2=128)),
 ]
 
 

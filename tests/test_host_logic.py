@@ -108,8 +108,32 @@ def test_style_loading(tmp_path):
     np.save(tmp_path / "style.npy", s.numpy())
     assert load_style(str(tmp_path / "style.pt")).shape == (1, 14, 1280)
     assert torch.equal(load_style(str(tmp_path / "style.npy"))[0], s)
-    with pytest.raises(NotImplementedError):
-        load_style("writer.tif")
+
+
+def test_read_img_and_remove_whitespace(tmp_path):
+    """utils/preprocessing.py:47-62 and utils/io.py:98-115: crop to the dark rows / columns (the last one is cut too, as
+    in the reference's rows[0]:rows[-1]), then bicubic resize to the requested height keeping the aspect ratio."""
+    import cv2
+
+    from dhg_b200.style import read_img, remove_whitespace
+
+    img = np.full((50, 80), 255, np.uint8)
+    img[10:30, 20:60] = 0
+    img[12, 5] = 200          # lighter than the threshold: still whitespace
+    out = remove_whitespace(img, thresh=127)
+    assert out.shape == (19, 39) and out.max() == 0
+    holes = img.copy()
+    holes[15:20, :] = 255
+    assert remove_whitespace(holes, 127, remove_middle=True).shape == (15, 40)
+    cv2.imwrite(str(tmp_path / "w.png"), img)
+    r = read_img(tmp_path / "w.png", 96)
+    assert r.shape == (96, 96 * 39 // 19) and r.dtype == np.uint8
+    with pytest.raises(FileNotFoundError):
+        read_img(tmp_path / "nope.png", 96)
+    with pytest.raises(ValueError, match="MobileNetV2 weights"):
+        os.environ.pop("DHG_MOBILENET_WEIGHTS", None)
+        from dhg_b200.style import _load_weights
+        _load_weights(None)
 
 
 def test_polylines_and_png(tmp_path):

@@ -1,5 +1,5 @@
 """Run one GEMM family a few times (for ncu / DHG_TRACE).
-python tools/gemm_one.py rows K N taps [period=393] [film] [res_post] [res_pre] [ln] [rowbias] [act] [both]"""
+python tools/gemm_one.py rows K N taps [period=393] [film] [res_post] [res_pre] [ln] [rowbias] [act] [both] [dual=K2]"""
 import os
 import sys
 
@@ -16,6 +16,8 @@ kw = dict(period=393, pad_first=1)
 for f in flags:
     if f.startswith("period="):
         kw["period"] = int(f[7:])
+    if f.startswith("dual="):
+        kw["dual_K2"] = int(f[5:])
 if "film" in flags:
     kw.update(film=1)
 if "act" in flags:
