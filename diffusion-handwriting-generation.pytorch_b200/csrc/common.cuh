@@ -19,13 +19,37 @@ typedef __nv_bfloat16 bf16;
 enum Precision { PREC_FP32 = 0, PREC_BF16 = 1 };
 
 // Split storage of an fp32 value for the fp32-contract mode on tensor cores: x ~ hi + lo with hi = bf16(x),
-// lo = bf16(x - hi), 16 mantissa bits together (relative error <= 2^-17).  A row of C such elements IS a bf16 row of
-// 2C elements (hi_0 lo_0 hi_1 lo_1 ..), so it feeds the bf16 tensor-core GEMM directly: with the weights split the
-// same way, x . w = (hi + lo) . w_hi + hi . w_lo (+ lo . w_lo, dropped: 2^-18) is two bf16 GEMMs over that row, one
-// against (w_hi, w_hi)-interleaved and one against (w_lo, 0)-interleaved weights, accumulated in fp32 (gemm_tc.cu).
+// lo = bf16(x - hi), 16 mantissa bits together (relative error <= 2^-17).  Rows are laid out in GROUPS of 32 elements:
+// 128 bytes = the 32 hi halves (64 B) followed by the 32 lo halves (64 B).  A row of C elements is therefore a bf16 row
+// of 2C numbers in which every 64-wide k-block of the tensor-core GEMM holds the hi and the lo parts of 32 elements, and
+// with the weights stored the same way (w_hi x 32 | w_lo x 32 per group) one A tile and one W tile per k-block give
+//   x . w = hi . w_hi + lo . w_hi + hi . w_lo      (+ lo . w_lo, dropped: 2^-18)
+// as three pairs of tcgen05.mma k-steps into the same fp32 accumulator (gemm_tc.cu, mma_kblock).
+// `bfs` is the 4-byte element TAG of such a row for the CUDA-core kernels: pointer arithmetic in elements works as for
+// float, but the element is never dereferenced -- the accessors below find the two halves from the ADDRESS (row bases
+// are 128-byte aligned: cudaMalloc bases, C a multiple of 32, column offsets in multiples of 4 within a group).
 struct __align__(4) bfs {
-  __nv_bfloat16 hi, lo;
+  uint32_t tag;
 };
+__device__ __forceinline__ const char* bfs_hi_ptr(const void* p) {   // address of the hi half of element p; lo is 64 bytes on
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  return reinterpret_cast<const char*>((a & ~(uintptr_t)127) + ((a & 127) >> 1));
+}
+__device__ __forceinline__ float bf16_bits_to_f(uint32_t h) { return __uint_as_float(h << 16); }
+__device__ __forceinline__ uint32_t bf16_pair_hi(float x0, float x1, float& r0, float& r1) {   // packs bf16(x), returns the remainders
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+  r0 = x0 - __bfloat162float(h0);
+  r1 = x1 - __bfloat162float(h1);
+  return (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+}
+__device__ __forceinline__ uint32_t bf16_pair(float x0, float x1) {
+  return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(x0)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(x1)) << 16);
+}
+// two packed bf16 (low, high half-word) of the hi word + of the lo word -> the two fp32 values
+__device__ __forceinline__ void split_unpack2(uint32_t wh, uint32_t wl, float& a, float& b) {
+  a = __uint_as_float(wh << 16) + __uint_as_float(wl << 16);
+  b = __uint_as_float(wh & 0xffff0000u) + __uint_as_float(wl & 0xffff0000u);
+}
 
 // How a flat row index maps to (sample, position): rows are grouped in periods
 // of `period` rows per sample; if `pad_first`, the first row of each period is
@@ -68,11 +92,14 @@ struct Epilogue {
   int dot_planned;         // plan-time flag like film_planned: dot_w is supplied at launch
   int w_row_off;           // tcgen05 path, launch time: first row of the weight variant to use (TcDual stacks; 0 otherwise)
   int split_io;            // tcgen05 path: every activation operand (A, residuals, per-position rows, outputs) is `bfs`
-                           // split storage; pitches stay in elements.  The fp32-contract mode (engine.cu).
+                           // split storage (groups of 32 hi | 32 lo); pitches stay in elements.  The fp32-contract mode.
   RowMap map;
 };
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// the same through a correctly rounded reciprocal instead of a full division (1 ulp apart; half the instructions):
+// the tcgen05 epilogue of the fp32-contract mode
+__device__ __forceinline__ float silu_rcp(float x) { return x * __frcp_rn(1.0f + __expf(-x)); }
 // SiLU of a value that is stored in T right away: for bf16 the one-MUFU form h + h * tanh.approx(h), h = x / 2
 // (2^-11 relative, far below the bf16 rounding; 3 instructions instead of the ~15 of an fp32 division); fp32 keeps
 // the exact form (the fp32 mode is the parity mode).
@@ -84,27 +111,11 @@ template <> __device__ __forceinline__ float silu_out<__nv_bfloat16>(float x) {
   return fmaf(h, t, h);
 }
 
-__device__ __forceinline__ uint32_t split_pack(float x) {   // -> hi in the low half-word, lo in the high one
-  const __nv_bfloat16 h = __float2bfloat16_rn(x);
-  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
-  return (uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(l) << 16);
-}
-__device__ __forceinline__ float split_unpack(uint32_t w) {
-  return __uint_as_float(w << 16) + __uint_as_float(w & 0xffff0000u);
-}
-
 template <typename T> __device__ __forceinline__ float to_f(T v);
-template <> __device__ __forceinline__ float to_f<bfs>(bfs v) { return __bfloat162float(v.hi) + __bfloat162float(v.lo); }
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
 
 template <typename T> __device__ __forceinline__ T from_f(float v);
-template <> __device__ __forceinline__ bfs from_f<bfs>(float v) {
-  bfs r;
-  r.hi = __float2bfloat16_rn(v);
-  r.lo = __float2bfloat16_rn(v - __bfloat162float(r.hi));
-  return r;
-}
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
 
@@ -121,12 +132,24 @@ template <> __device__ __forceinline__ float4 load4<bf16>(const bf16* p) {
   return make_float4(fa.x, fa.y, fb.x, fb.y);
 }
 template <> __device__ __forceinline__ float4 load4<bfs>(const bfs* p) {
-  const uint4 u = *reinterpret_cast<const uint4*>(p);
-  return make_float4(split_unpack(u.x), split_unpack(u.y), split_unpack(u.z), split_unpack(u.w));
+  const char* h = bfs_hi_ptr(p);
+  const uint2 uh = *reinterpret_cast<const uint2*>(h), ul = *reinterpret_cast<const uint2*>(h + 64);
+  float4 v;
+  split_unpack2(uh.x, ul.x, v.x, v.y);
+  split_unpack2(uh.y, ul.y, v.z, v.w);
+  return v;
 }
 template <typename T> __device__ __forceinline__ void store4(T* p, float4 v);
 template <> __device__ __forceinline__ void store4<bfs>(bfs* p, float4 v) {
-  *reinterpret_cast<uint4*>(p) = make_uint4(split_pack(v.x), split_pack(v.y), split_pack(v.z), split_pack(v.w));
+  char* h = const_cast<char*>(bfs_hi_ptr(p));
+  float r0, r1, r2, r3;
+  uint2 uh, ul;
+  uh.x = bf16_pair_hi(v.x, v.y, r0, r1);
+  uh.y = bf16_pair_hi(v.z, v.w, r2, r3);
+  ul.x = bf16_pair(r0, r1);
+  ul.y = bf16_pair(r2, r3);
+  *reinterpret_cast<uint2*>(h) = uh;
+  *reinterpret_cast<uint2*>(h + 64) = ul;
 }
 template <> __device__ __forceinline__ void store4<float>(float* p, float4 v) {
   *reinterpret_cast<float4*>(p) = v;
@@ -156,14 +179,28 @@ template <> __device__ __forceinline__ void load8<bf16>(const bf16* p, float* v)
   }
 }
 template <> __device__ __forceinline__ void load8<bfs>(const bfs* p, float* v) {
-  const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 4);
-  v[0] = split_unpack(a.x); v[1] = split_unpack(a.y); v[2] = split_unpack(a.z); v[3] = split_unpack(a.w);
-  v[4] = split_unpack(b.x); v[5] = split_unpack(b.y); v[6] = split_unpack(b.z); v[7] = split_unpack(b.w);
+  const char* h = bfs_hi_ptr(p);
+  const uint4 uh = *reinterpret_cast<const uint4*>(h), ul = *reinterpret_cast<const uint4*>(h + 64);
+  split_unpack2(uh.x, ul.x, v[0], v[1]);
+  split_unpack2(uh.y, ul.y, v[2], v[3]);
+  split_unpack2(uh.z, ul.z, v[4], v[5]);
+  split_unpack2(uh.w, ul.w, v[6], v[7]);
 }
 template <typename T> __device__ __forceinline__ void store8(T* p, const float* v);
 template <> __device__ __forceinline__ void store8<bfs>(bfs* p, const float* v) {
-  *reinterpret_cast<uint4*>(p) = make_uint4(split_pack(v[0]), split_pack(v[1]), split_pack(v[2]), split_pack(v[3]));
-  *reinterpret_cast<uint4*>(p + 4) = make_uint4(split_pack(v[4]), split_pack(v[5]), split_pack(v[6]), split_pack(v[7]));
+  char* h = const_cast<char*>(bfs_hi_ptr(p));
+  float r[8];
+  uint4 uh, ul;
+  uh.x = bf16_pair_hi(v[0], v[1], r[0], r[1]);
+  uh.y = bf16_pair_hi(v[2], v[3], r[2], r[3]);
+  uh.z = bf16_pair_hi(v[4], v[5], r[4], r[5]);
+  uh.w = bf16_pair_hi(v[6], v[7], r[6], r[7]);
+  ul.x = bf16_pair(r[0], r[1]);
+  ul.y = bf16_pair(r[2], r[3]);
+  ul.z = bf16_pair(r[4], r[5]);
+  ul.w = bf16_pair(r[6], r[7]);
+  *reinterpret_cast<uint4*>(h) = uh;
+  *reinterpret_cast<uint4*>(h + 64) = ul;
 }
 template <> __device__ __forceinline__ void store8<float>(float* p, const float* v) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);

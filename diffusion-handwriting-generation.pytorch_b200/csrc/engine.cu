@@ -93,8 +93,8 @@ struct Lin {
   float* w32 = nullptr;   // [taps][K][N] exact fp32               (fp32 mode, CUDA-core GEMM)
   float* w32r = nullptr;  // [taps][K][N] bf16-rounded, as fp32    (bf16 mode, CUDA-core GEMM)
   bf16* w16 = nullptr;    // [taps][N][K] bf16, K contiguous       (bf16 mode, tcgen05 GEMM)
-  bf16* w16s = nullptr;   // [2 taps][N][2K] bf16: slab `tap` = (w_hi, w_hi) interleaved along K, slab `taps + tap` =
-                          // (w_lo, 0) interleaved, w = w_hi + w_lo  (fp32 mode on tcgen05: split storage, common.cuh bfs)
+  bf16* w16s = nullptr;   // [taps][N][2K] bf16, K in groups of 32: (w_hi x 32 | w_lo x 32), w = w_hi + w_lo
+                          // (fp32 mode on tcgen05: split storage, common.cuh bfs)
   float* bias = nullptr;  // [N]
   std::vector<float> h_w;  // host copy [taps][K][N] (for PE-folded bias tables)
   std::vector<float> h_b;
@@ -373,16 +373,16 @@ int make_lin(dhg_ctx* c, const std::string& key, const std::vector<std::string>&
   if (dev_upload(c->allocs, &L.bias, L.h_b)) return 1;
   if (dev_alloc(c->allocs, (void**)&L.w16, w16.size() * sizeof(bf16))) return 1;
   CUDA_OK(cudaMemcpy(L.w16, w16.data(), w16.size() * sizeof(bf16), cudaMemcpyHostToDevice));
-  {
-    std::vector<bf16> ws((size_t)2 * L.taps * N * 2 * K);
+  if (K % 32 == 0) {   // (every GEMM of the denoiser; the folded 3-channel heads weights never run in this mode)
+    std::vector<bf16> ws((size_t)L.taps * N * 2 * K);
     for (int t = 0; t < L.taps; ++t)
       for (int n = 0; n < N; ++n)
         for (int k = 0; k < K; ++k) {
           const float v = L.h_w[((size_t)t * K + k) * N + n];
           const bf16 hi = __float2bfloat16_rn(v), lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-          const size_t a = (((size_t)t * N + n) * K + k) * 2, b = (((size_t)(L.taps + t) * N + n) * K + k) * 2;
-          ws[a] = hi; ws[a + 1] = hi;
-          ws[b] = lo; ws[b + 1] = __float2bfloat16_rn(0.f);
+          const size_t g = ((size_t)t * N + n) * 2 * K + (size_t)(k / 32) * 64 + (k % 32);
+          ws[g] = hi;
+          ws[g + 32] = lo;
         }
     if (dev_alloc(c->allocs, (void**)&L.w16s, ws.size() * sizeof(bf16))) return 1;
     CUDA_OK(cudaMemcpy(L.w16s, ws.data(), ws.size() * sizeof(bf16), cudaMemcpyHostToDevice));
@@ -452,17 +452,19 @@ int make_rowbias(Plan* P, const Lin& W, const std::vector<float>& pe, int len, i
     }
   if (dev_alloc(P->allocs, (void**)out, t.size() * sizeof(float), &P->bytes)) return 1;
   CUDA_OK(cudaMemcpy(*out, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
-  if (out16 && P->split) {   // the same table as bfs split pairs (hi in the low half-word, common.cuh)
+  if (out16 && P->split) {   // the same table in split storage (common.cuh bfs: groups of 32 hi | 32 lo), cols % 32 == 0
     const int cols = n_pe1 - n_pe0;
-    std::vector<uint32_t> ts((size_t)len * cols);
+    std::vector<bf16> ts((size_t)len * cols * 2);
     for (int i = 0; i < len; ++i)
       for (int n = 0; n < cols; ++n) {
         const float v = t[(size_t)i * W.N + n_pe0 + n] - W.h_b[n_pe0 + n];
         const bf16 hi = __float2bfloat16_rn(v), lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-        ts[(size_t)i * cols + n] = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+        const size_t g = (size_t)i * cols * 2 + (size_t)(n / 32) * 64 + (n % 32);
+        ts[g] = hi;
+        ts[g + 32] = lo;
       }
-    if (dev_alloc(P->allocs, out16, ts.size() * sizeof(uint32_t), &P->bytes)) return 1;
-    CUDA_OK(cudaMemcpy(*out16, ts.data(), ts.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (dev_alloc(P->allocs, out16, ts.size() * sizeof(bf16), &P->bytes)) return 1;
+    CUDA_OK(cudaMemcpy(*out16, ts.data(), ts.size() * sizeof(bf16), cudaMemcpyHostToDevice));
   } else if (out16) {   // bf16 [len, n_pe1 - n_pe0] table of the positional term alone (the bias stays an fp32 vector)
     const int cols = n_pe1 - n_pe0;
     std::vector<bf16> t16((size_t)len * cols);
@@ -623,9 +625,10 @@ struct Builder {
     size_t need = (size_t)rows * N;
     if (need > P->scratch_elems) P->scratch_elems = need;
     TcGemmPlan* tcp = nullptr;
-    // tcgen05 operands: split storage is a bf16 row of 2 K columns against 2 weight slabs per tap
+    // tcgen05 operands: split storage is a bf16 row of 2 K columns (groups of 32 hi | 32 lo), weights packed alike
     const bf16* Wp = sio ? W->w16s : W->w16;
-    const int Kt = sio ? 2 * K : K, ldt = sio ? 2 * A.C : A.C, tapst = sio ? 2 * taps : taps;
+    const int Kt = sio ? 2 * K : K, ldt = sio ? 2 * A.C : A.C, tapst = taps;
+    if (sio && !Wp) { fail("plan: gemm %s has no split weights (K = %d is not a multiple of 32)", wkey.c_str(), K); failed = true; return; }
     if (tc_path) {
       char buf[512];
       tcp = tc_gemm_plan_create((const bf16*)Ap, ldt, rows, Wp, Kt, N, tapst, e, buf, sizeof(buf));
@@ -1781,12 +1784,9 @@ int64_t dhg_debug_read(dhg_ctx* c, const char* name, float* host_out, int64_t ca
       for (int ch = 0; ch < a.C; ++ch) {
         const size_t src = r * a.C + ch;
         float val;
-        if (P->split) {
-          const uint32_t w = reinterpret_cast<const uint32_t*>(tmp.data())[src];
-          uint32_t hi = w << 16, lo = w & 0xffff0000u;
-          float fh, fl;
-          memcpy(&fh, &hi, 4); memcpy(&fl, &lo, 4);
-          val = fh + fl;
+        if (P->split) {   // groups of 32 hi | 32 lo bf16 (common.cuh bfs)
+          const bf16* rowp = reinterpret_cast<const bf16*>(tmp.data()) + r * 2 * a.C + (size_t)(ch / 32) * 64 + (ch % 32);
+          val = __bfloat162float(rowp[0]) + __bfloat162float(rowp[32]);
         } else if (P->esize == 4) val = reinterpret_cast<const float*>(tmp.data())[src];
         else val = __bfloat162float(reinterpret_cast<const bf16*>(tmp.data())[src]);
         host_out[((size_t)b * per + t) * a.C + ch] = val;

@@ -48,8 +48,8 @@ constexpr int TMEM_COLS = 512;
 enum { AUX_NONE = 0, AUX_RES_PRE = 1, AUX_RES_POST = 2, AUX_RES_POST_UP = 3, AUX_ROWBIAS = 4 };
 
 struct TcShape {
-  int rows, K, N, taps;   // taps = weight slabs per k-block: 1 linear, 3 conv; split I/O doubles them (2 / 6, see base_taps)
-  int base_taps;   // row shifts of the A operand: slab s reads the A tile shifted by s % base_taps rows (1 or 3)
+  int rows, K, N, taps;   // taps: 1 linear, 3 conv (row-shifted A tile)
+  int base_taps;   // == taps (row shifts of the A operand)
   int kb2;         // dual-operand mode: k-blocks of the SECOND A matrix (3-tap weights, rows shifted -1..+1) that follow the
                    // kb_per_tap k-blocks of the first one (1 tap) into the same accumulators; 0 = single operand
   uint32_t a2_tx_bytes;   // bytes of one 130-row tile of the second A matrix
@@ -104,12 +104,14 @@ __device__ __forceinline__ void fast_divmod(int m, int period, float inv_period,
 // that everything inside it is straight-line code (the single issuing warp is latency-critical: every instruction
 // between two tcgen05.mma shows up in the tile time).  `first` = 0: the first MMA overwrites the accumulators.
 // Resident W: tap t of this k-block is tile w_tile0 + t * w_tap_stride of the resident set.
-template <int TAPS, int G, bool PAIR>
+template <int TAPS, int G, bool PAIR, bool SIO = false>
 __device__ __forceinline__ void mma_kblock(const TcShape& sh, const bool leader, const uint32_t acc, const uint32_t a_ring_addr,
                                            const uint32_t w_addr, uint64_t* full_a, uint64_t* empty_a, uint64_t* full_w, uint64_t* empty_w,
                                            uint32_t& sa, uint32_t& pa, uint32_t& sw, uint32_t& pw, const uint32_t first, const int w_tile0,
                                            const int w_tap_stride, const int it, unsigned& tr_n, const int tr_role, const int lane) {
-  constexpr int BASE = (TAPS % 3 == 0) ? 3 : 1;   // slab -> row shift of the A tile (split I/O: two slabs per shift)
+  // Split I/O: the 64-wide k-block holds the hi (k-steps 0, 1) and lo (k-steps 2, 3) halves of 32 elements, in the A
+  // tile and in the W tile alike; x . w = hi . w_hi + lo . w_hi + hi . w_lo is six k-steps (a-step, b-step) instead of four.
+  constexpr int NK = SIO ? 6 : TC_BK / 16;
   const uint32_t nb2 = (uint32_t)(PAIR ? sh.umma_n / 2 : sh.umma_n) * TC_BK * 2;   // byte offset of the second N half (BN = 384)
   const bool two_n = sh.n_umma == 2;
   const bool resident = sh.w_resident != 0;
@@ -137,32 +139,31 @@ __device__ __forceinline__ void mma_kblock(const TcShape& sh, const bool leader,
     if (leader) {
       // shifted tap: logical row r of the A operand is physical row r + tap of the 130-row tile (the 128B
       // swizzle is a function of the absolute smem address, so a +128 B start address just works)
-      if (!two_n) {
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k)
+      for (int k = 0; k < NK; ++k) {
+        // (A k-step, B k-step) in 16-byte descriptor units: plain 0..3 | split: (0,0) (1,1) (2,0) (3,1) (0,2) (1,3)
+        const uint32_t ka = SIO ? (uint32_t)(k < 4 ? k : k - 4) * 2u : (uint32_t)k * 2u;
+        const uint32_t kb = SIO ? (uint32_t)(k < 2 ? k : k < 4 ? k - 2 : k - 2) * 2u : (uint32_t)k * 2u;
+        const uint32_t accum = (tap | k) ? 1u : first;
+        if (!two_n) {
 #pragma unroll
           for (int sub = 0; sub < G; ++sub) {
             if (PAIR)
-              umma_bf16_pair(acc, umma_desc_make(alo[0] + (tap % BASE) * 8 + 2 * k, kDescHiSw128), umma_desc_make(blo + 2 * k, kDescHiSw128),
-                             sh.idesc, (tap | k) ? 1u : first);
+              umma_bf16_pair(acc, umma_desc_make(alo[0] + tap * 8 + ka, kDescHiSw128), umma_desc_make(blo + kb, kDescHiSw128), sh.idesc, accum);
             else
-              umma_bf16(acc + (uint32_t)(sub * sh.BN), umma_desc_make(alo[sub] + (tap % BASE) * 8 + 2 * k, kDescHiSw128),
-                        umma_desc_make(blo + 2 * k, kDescHiSw128), sh.idesc, (tap | k) ? 1u : first);
+              umma_bf16(acc + (uint32_t)(sub * sh.BN), umma_desc_make(alo[sub] + tap * 8 + ka, kDescHiSw128),
+                        umma_desc_make(blo + kb, kDescHiSw128), sh.idesc, accum);
           }
-      } else {
-        const uint32_t blo2 = umma_desc_lo(b_addr + nb2);
-#pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
+        } else {
+          const uint32_t blo2 = umma_desc_lo(b_addr + nb2);
           if (PAIR) {
-            umma_bf16_pair(acc, umma_desc_make(alo[0] + (tap % BASE) * 8 + 2 * k, kDescHiSw128), umma_desc_make(blo + 2 * k, kDescHiSw128),
-                           sh.idesc, (tap | k) ? 1u : first);
-            umma_bf16_pair(acc + (uint32_t)sh.umma_n, umma_desc_make(alo[0] + (tap % BASE) * 8 + 2 * k, kDescHiSw128),
-                           umma_desc_make(blo2 + 2 * k, kDescHiSw128), sh.idesc, (tap | k) ? 1u : first);
+            umma_bf16_pair(acc, umma_desc_make(alo[0] + tap * 8 + ka, kDescHiSw128), umma_desc_make(blo + kb, kDescHiSw128), sh.idesc, accum);
+            umma_bf16_pair(acc + (uint32_t)sh.umma_n, umma_desc_make(alo[0] + tap * 8 + ka, kDescHiSw128),
+                           umma_desc_make(blo2 + kb, kDescHiSw128), sh.idesc, accum);
           } else {
-            umma_bf16(acc, umma_desc_make(alo[0] + (tap % BASE) * 8 + 2 * k, kDescHiSw128), umma_desc_make(blo + 2 * k, kDescHiSw128), sh.idesc,
-                      (tap | k) ? 1u : first);
-            umma_bf16(acc + (uint32_t)sh.umma_n, umma_desc_make(alo[0] + (tap % BASE) * 8 + 2 * k, kDescHiSw128),
-                      umma_desc_make(blo2 + 2 * k, kDescHiSw128), sh.idesc, (tap | k) ? 1u : first);
+            umma_bf16(acc, umma_desc_make(alo[0] + tap * 8 + ka, kDescHiSw128), umma_desc_make(blo + kb, kDescHiSw128), sh.idesc, accum);
+            umma_bf16(acc + (uint32_t)sh.umma_n, umma_desc_make(alo[0] + tap * 8 + ka, kDescHiSw128),
+                      umma_desc_make(blo2 + kb, kDescHiSw128), sh.idesc, accum);
           }
         }
       }
@@ -180,7 +181,7 @@ __device__ __forceinline__ void mma_kblock(const TcShape& sh, const bool leader,
 
 // The MMA warp's main loop.  DUAL: the accumulation runs over two operand segments (TcShape::kb2): kb_per_tap k-blocks
 // of the first A matrix against 1-tap weights, then kb2 k-blocks of the second A matrix against 3-tap weights.
-template <int TAPS, int G, bool PAIR, bool DUAL = false>
+template <int TAPS, int G, bool PAIR, bool DUAL = false, bool SIO = false>
 __device__ __forceinline__ void mma_issue_loop(const TcShape& sh, const bool leader, const uint32_t tmem_base,
                                                const uint32_t a_ring_addr, const uint32_t w_addr, uint64_t* full_a,
                                                uint64_t* empty_a, uint64_t* full_w, uint64_t* empty_w,
@@ -197,8 +198,8 @@ __device__ __forceinline__ void mma_issue_loop(const TcShape& sh, const bool lea
     DHG_TR(0x20, it);
     const uint32_t acc = tmem_base + (uint32_t)as * 256u;
     for (int kbi = 0; kbi < sh.kb_per_tap; ++kbi)
-      mma_kblock<TAPS, G, PAIR>(sh, leader, acc, a_ring_addr, w_addr, full_a, empty_a, full_w, empty_w, sa, pa, sw, pw, kbi == 0 ? 0u : 1u, kbi,
-                                sh.kb_per_tap, it, tr_n, tr_role, lane);
+      mma_kblock<TAPS, G, PAIR, SIO>(sh, leader, acc, a_ring_addr, w_addr, full_a, empty_a, full_w, empty_w, sa, pa, sw, pw, kbi == 0 ? 0u : 1u, kbi,
+                                     sh.kb_per_tap, it, tr_n, tr_role, lane);
     if (DUAL)
       for (int kbi = 0; kbi < sh.kb2; ++kbi)
         mma_kblock<3, G, PAIR>(sh, leader, acc, a_ring_addr, w_addr, full_a, empty_a, full_w, empty_w, sa, pa, sw, pw, 1u,
@@ -418,6 +419,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 #define DHG_MMA_LOOP_PAIR(TAPS)                                                                                         \
   mma_issue_loop<TAPS, 1, true>(sh, leader, tmem_base, a_ring_addr, w_addr, full_a, empty_a, full_w, empty_w, tmem_full_bar, \
                            tmem_empty_bar, t_first, t_end, t_step, tr_n, tr_role, lane)
+#define DHG_MMA_LOOP_SIO(TAPS, PP)                                                                                       \
+  mma_issue_loop<TAPS, 1, PP, false, true>(sh, leader, tmem_base, a_ring_addr, w_addr, full_a, empty_a, full_w, empty_w, tmem_full_bar, \
+                           tmem_empty_bar, t_first, t_end, t_step, tr_n, tr_role, lane)
 #define DHG_MMA_LOOP_DUAL(GG, PP)                                                                                        \
   mma_issue_loop<1, GG, PP, true>(sh, leader, tmem_base, a_ring_addr, w_addr, full_a, empty_a, full_w, empty_w, tmem_full_bar, \
                            tmem_empty_bar, t_first, t_end, t_step, tr_n, tr_role, lane)
@@ -426,11 +430,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       else if (sh.G == 4) DHG_MMA_LOOP_DUAL(4, false); else if (sh.G == 2) DHG_MMA_LOOP_DUAL(2, false); else DHG_MMA_LOOP_DUAL(1, false);
     } else if (kPAIR) {
       if (cta_rank == 0) {   // rank 0 issues for both CTAs
-        if (kSIO) { if (sh.taps == 6) DHG_MMA_LOOP_PAIR(6); else DHG_MMA_LOOP_PAIR(2); }
+        if (kSIO) { if (sh.taps == 3) DHG_MMA_LOOP_SIO(3, true); else DHG_MMA_LOOP_SIO(1, true); }
         else if (sh.taps == 3) DHG_MMA_LOOP_PAIR(3); else DHG_MMA_LOOP_PAIR(1);
       }
-    } else if (kSIO) {   // split I/O: 2 slabs per row shift (hi+lo against w_hi, hi against w_lo); no interleaving (G = 1)
-      if (sh.taps == 6) DHG_MMA_LOOP(6, 1); else DHG_MMA_LOOP(2, 1);
+    } else if (kSIO) {   // split I/O: six k-steps per k-block (hi.w_hi, lo.w_hi, hi.w_lo); no interleaving (G = 1)
+      if (sh.taps == 3) DHG_MMA_LOOP_SIO(3, false); else DHG_MMA_LOOP_SIO(1, false);
     } else if (sh.taps == 3) {
       if (sh.G == 4) DHG_MMA_LOOP(3, 4); else if (sh.G == 2) DHG_MMA_LOOP(3, 2); else DHG_MMA_LOOP(3, 1);
     } else {
@@ -439,6 +443,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 #undef DHG_MMA_LOOP
 #undef DHG_MMA_LOOP_PAIR
 #undef DHG_MMA_LOOP_DUAL
+#undef DHG_MMA_LOOP_SIO
   } else {
     // ===== epilogue warps; warp (q, part): TMEM lanes [32q, 32q+32), one contiguous part of the column chunks =====
     asm volatile("griddepcontrol.wait;" ::: "memory");   // residual rows are read / outputs written only after the previous kernel
@@ -555,10 +560,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       if (kSIO) {
         if (!aux_col_limited || col0 < aux_ncols) {
 #pragma unroll
-          for (int p = 0; p < 8; ++p) {
-            const uint4 u = lds128_v(slot + (uint32_t)lane * 128u + (uint32_t)((p ^ (lane & 7)) << 4));
-            v[p * 4] += split_unpack(u.x); v[p * 4 + 1] += split_unpack(u.y);
-            v[p * 4 + 2] += split_unpack(u.z); v[p * 4 + 3] += split_unpack(u.w);
+          for (int p = 0; p < 4; ++p) {   // 16-byte pieces 0..3 of the row: hi halves of 8 elements each; 4..7: the lo halves
+            const uint4 uh = lds128_v(slot + (uint32_t)lane * 128u + (uint32_t)((p ^ (lane & 7)) << 4));
+            const uint4 ul = lds128_v(slot + (uint32_t)lane * 128u + (uint32_t)(((p + 4) ^ (lane & 7)) << 4));
+            float a, b;
+            split_unpack2(uh.x, ul.x, a, b); v[p * 8] += a; v[p * 8 + 1] += b;
+            split_unpack2(uh.y, ul.y, a, b); v[p * 8 + 2] += a; v[p * 8 + 3] += b;
+            split_unpack2(uh.z, ul.z, a, b); v[p * 8 + 4] += a; v[p * 8 + 5] += b;
+            split_unpack2(uh.w, ul.w, a, b); v[p * 8 + 6] += a; v[p * 8 + 7] += b;
           }
         }
       } else if (!aux_col_limited || col0 < aux_ncols) {
@@ -607,7 +616,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       // (the buffer store k+1 will use); the other lanes learn about it through the next warp barrier they pass:
       // the one in front of the next chunk's tcgen05.ld, or `sync_first` for a second store of the same chunk.
       auto store_chunk = [&](const CUtensorMap* omap, int col0, const float* v, bool act, bool sync_first) {
-        if (kSIO) {   // 32 bfs per row = 128 bytes: two [32 rows x 32 bf16] SWIZZLE_64B tiles of 16 elements each, exact SiLU
+        if (kSIO) {   // a group of 32 elements = 64 B of hi halves + 64 B of lo halves per row: one [32 rows x 32 bf16]
+                      // SWIZZLE_64B tile each (hi tile at column 2 * col0, lo tile 32 columns on); exact SiLU, fp32 remainders
+          float r[32];
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             const uint32_t buf = out_st + ((st_flip && sh.out_bufs == 2) ? 2048u : 0u);
@@ -618,15 +629,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
               uint32_t w[4];
 #pragma unroll
               for (int k2 = 0; k2 < 4; ++k2) {
-                const float a = v[half * 16 + p * 4 + k2];
-                w[k2] = split_pack(act ? silu_f(a) : a);
+                const int i = p * 8 + k2 * 2;
+                if (half == 0) {
+                  const float a = act ? silu_rcp(v[i]) : v[i], c = act ? silu_rcp(v[i + 1]) : v[i + 1];
+                  w[k2] = bf16_pair_hi(a, c, r[i], r[i + 1]);
+                } else {
+                  w[k2] = bf16_pair(r[i], r[i + 1]);
+                }
               }
               sts128(buf + st_row + ((p ^ st_sw) << 4), make_uint4(w[0], w[1], w[2], w[3]));
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(omap, buf, (col0 + half * 16) * 2, m0 + q * 32);
+              tma_store_2d(omap, buf, col0 * 2 + half * 32, m0 + q * 32);
               bulk_commit();
               if (sh.out_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
             }
@@ -905,12 +921,12 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
                                 char* err, int errlen, const TcTune* tune, const TcDual* dual) {
   const TcTune tn = tune ? *tune : g_tune_default;
   if (rows >= (1 << 24)) { snprintf(err, errlen, "rows = %d: the epilogue's row arithmetic needs rows < 2^24 (plan a smaller chunk)", rows); return nullptr; }
-  const bool sio = e.split_io != 0;   // K, lda in bf16 units (2 per activation element), taps = 2 weight slabs per row shift
-  if (rows <= 0 || K % 8 || N % 32 || (!sio && taps != 1 && taps != 3) || (sio && taps != 2 && taps != 6)) {
+  const bool sio = e.split_io != 0;   // K, lda in bf16 units (2 per activation element: groups of 32 hi | 32 lo)
+  if (rows <= 0 || K % 8 || N % 32 || (taps != 1 && taps != 3) || (sio && K % 64)) {
     snprintf(err, errlen, "unsupported shape rows=%d K=%d N=%d taps=%d%s", rows, K, N, taps, sio ? " (split I/O)" : "");
     return nullptr;
   }
-  const int base_taps = taps % 3 == 0 ? 3 : 1;
+  const int base_taps = taps;
   if (dual && (sio || taps != 1 || e.ln || e.rowbias16 || e.res_pre || e.res_post || e.film_planned || !e.bias || dual->K2 % 8 || !dual->A2 || !dual->W2 ||
                dual->w1_rows < N)) {
     snprintf(err, errlen, "dual-operand mode needs a 1-tap first operand and a bias-only epilogue");

@@ -46,8 +46,8 @@ typedef struct dhg_config {
 } dhg_config;
 
 #define DHG_PREC_FP32 0 /* the reference's precision (parity 1e-3 after 60 steps).  Default ("gemm" = 1): tcgen05 tensor cores on
-                           split storage -- every fp32 activation / weight is a {bf16 hi, bf16 lo} pair and every GEMM is
-                           x.w = (hi + lo).w_hi + hi.w_lo in bf16 MMAs with fp32 accumulation (~2^-17 per product), all
+                           split storage -- every fp32 activation / weight is a bf16 pair hi + lo and every GEMM is
+                           x.w = hi.w_hi + lo.w_hi + hi.w_lo in bf16 MMAs with fp32 accumulation (~2^-17 per product), all
                            epilogue arithmetic in fp32.  "gemm" = 0: plain fp32 storage and CUDA-core fp32 FMA GEMMs. */
 #define DHG_PREC_BF16 1 /* bf16 storage, tcgen05 bf16 MMA, fp32 accumulate/statistics */
 
@@ -197,9 +197,10 @@ typedef struct dhg_debug_epilogue {
   const float* dot_w;      /* fp32 [3, N] or NULL */
   float* dot_out;          /* fp32 [rows, 4] */
   int32_t dot_act;
-  /* split I/O (the fp32-contract mode): every activation operand (A, res_pre, res_post, rowbias, outputs) holds
-   * {bf16 hi, bf16 lo} pairs, value = hi + lo; pitches stay in elements; the caller passes K = 2 * (elements per A row),
-   * lda in bf16 units and W as [2 taps][N][K]: slab t = (w_hi, w_hi) interleaved along K, slab taps + t = (w_lo, 0). */
+  /* split I/O (the fp32-contract mode): every activation operand (A, res_pre, res_post, rowbias, outputs) is in split
+   * storage: value = hi + lo, two bf16, rows laid out in groups of 32 elements (32 hi, then 32 lo: 128 bytes); pitches
+   * and column counts stay in elements (multiples of 32); the caller passes K = 2 * (elements per A row), lda in bf16
+   * units and W as [taps][N][K] with K grouped the same way (w_hi x 32 | w_lo x 32). */
   int32_t split_io;
   /* dual-operand mode: out = A . W[w_row_off : w_row_off + N]^T + sum_tap A2[row + tap - 1] . W2[tap]^T + bias, one
    * accumulation (taps must be 1; bias-only epilogue).  W is a stack of dual_w1_rows / N variants of [N, K]; A2 is

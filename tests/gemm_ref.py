@@ -9,25 +9,25 @@ from dhg_b200 import _abi
 
 
 def split_pack(x):
-    """fp32 tensor -> int32 tensor of {bf16 hi, bf16 lo} pairs (csrc/common.cuh `bfs`: hi in the low half-word)."""
-    hi = x.float().bfloat16()
-    lo = (x.float() - hi.float()).bfloat16()
-    return (hi.view(torch.int16).to(torch.int32) & 0xFFFF) | (lo.view(torch.int16).to(torch.int32) << 16)
+    """fp32 [rows, C] (C % 32 == 0) -> bf16 [rows, 2C] in split storage (csrc/common.cuh `bfs`): per group of 32
+    elements the 32 hi halves, then the 32 lo halves; value = hi + lo."""
+    x = x.float()
+    hi = x.bfloat16()
+    lo = (x - hi.float()).bfloat16()
+    r, c = x.shape
+    return torch.stack((hi.view(r, c // 32, 32), lo.view(r, c // 32, 32)), dim=2).reshape(r, 2 * c).contiguous()
 
 
 def split_unpack(w):
-    hi = (w << 16).view(torch.float32)
-    lo = (w & -65536).view(torch.float32)
-    return hi + lo
+    r, c2 = w.shape
+    g = w.float().view(r, c2 // 64, 2, 32)
+    return (g[:, :, 0] + g[:, :, 1]).reshape(r, c2 // 2)
 
 
 def split_weights(w):
-    """[taps, N, K] fp32 -> [2 taps, N, 2K] bf16: slab t = (w_hi, w_hi) interleaved along K, slab taps + t = (w_lo, 0)."""
-    hi = w.float().bfloat16()
-    lo = (w.float() - hi.float()).bfloat16()
-    a = torch.stack((hi, hi), dim=-1).flatten(-2)
-    b = torch.stack((lo, torch.zeros_like(lo)), dim=-1).flatten(-2)
-    return torch.cat((a, b), dim=0).contiguous()
+    """[taps, N, K] fp32 -> [taps, N, 2K] bf16 with K grouped like the activations (w_hi x 32 | w_lo x 32)."""
+    t, n, k = w.shape
+    return split_pack(w.reshape(t * n, k)).view(t, n, 2 * k).contiguous()
 
 
 def make_split_case(rows, K, N, taps, **kw):
@@ -48,7 +48,7 @@ def make_split_case(rows, K, N, taps, **kw):
         c[k] = split_pack(f[k]) if f[k] is not None else None
     for k in ("out_raw", "out_act"):
         if c[k] is not None:
-            c[k] = torch.full((rows, N), 0x7FC07FC0, dtype=torch.int32, device=device)   # NaN pairs
+            c[k] = torch.full((rows, 2 * N), float("nan"), dtype=torch.bfloat16, device=device)
     c["split"] = True
     return c
 
@@ -173,8 +173,8 @@ def run(lib, c, repeats=0, allow_unavailable=False):
         p(c.get("a2")), c.get("dual_K2", 0), c.get("dual_K2", 0), p(c.get("w2")), (c["w"].shape[0] * N) if c.get("dual_K2") else 0,
         (c["variant"] * N) if c.get("dual_K2") else 0)
     ms = ctypes.c_float(0)
-    km = 2 if c.get("split") else 1   # split I/O: K and lda in bf16 units, two weight slabs per tap
-    rc = lib.dhg_debug_tc_gemm_ex(0, p(c["a"]), km * c["K"], c["rows"], p(c["w"]), km * c["K"], N, km * c["taps"], ctypes.byref(e),
+    km = 2 if c.get("split") else 1   # split I/O: K and lda in bf16 units
+    rc = lib.dhg_debug_tc_gemm_ex(0, p(c["a"]), km * c["K"], c["rows"], p(c["w"]), km * c["K"], N, c["taps"], ctypes.byref(e),
                                   repeats, ctypes.byref(ms), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     if rc != 0 and allow_unavailable:
         msg = lib.dhg_last_error().decode()
