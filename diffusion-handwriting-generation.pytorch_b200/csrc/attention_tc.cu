@@ -43,6 +43,8 @@ struct AttnTcShape {
   int early;      // request the next item's tiles right after P V (else: after O has been stored)
   uint32_t idesc_s, idesc_o;
   uint32_t off_k, off_v, off_mask, off_xchg, slot_bytes, off_bar;
+  uint32_t kv_bytes;  // bytes of one [N keys x 64 bf16] K or V block
+  uint32_t off_pl;    // split storage: offset of the P_lo tile behind the P_hi tile
   float scale_log2;   // scale * log2(e)
   int dbg;            // timing experiments: 1 skip max pass, 2 skip exp, 4 skip P stores, 8 skip O stores, 16 skip PV MMAs, 32 skip S MMAs
 };
@@ -55,6 +57,13 @@ __device__ __forceinline__ void item_coords(const AttnTcShape& sh, const AttnPar
   b = bh / p.H;
 }
 
+// SPLIT: the fp32-contract mode.  q / k / v / o are in split storage (common.cuh bfs: per 32 elements 32 bf16 hi
+// halves, then 32 lo halves), so a head's 64 elements are TWO 64-wide bf16 k-blocks, each (hi x 32 | lo x 32), for Q and K
+// alike: S = Q K^T is the six-k-step pattern of the split GEMM (hi.hi, lo.hi, hi.lo) per k-block.  P is written as a
+// bf16 hi tile and a lo tile; V's two blocks are two MN-major B operands of 64 columns each, (v_hi x 32 | v_lo x 32), so
+// O' = (P_hi + P_lo) V' has 128 fp32 columns and O[d] = O'[hi column of d] + O'[lo column of d]; the row is normalised in
+// fp32 and stored split again.
+template <bool SPLIT>
 __global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __grid_constant__ CUtensorMap map_q,
                                                                             const __grid_constant__ CUtensorMap map_k,
                                                                             const __grid_constant__ CUtensorMap map_v,
@@ -103,12 +112,22 @@ __global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __
     const uint32_t tm = tmem_base + (uint32_t)(s * sh.tmem_cols);
     const uint32_t qlo = umma_desc_lo(smem_u32(q_s)), klo = umma_desc_lo(smem_u32(q_s + sh.off_k));
     const uint32_t vlo_mn = (umma_desc_lo(smem_u32(q_s + sh.off_v)) & ~(1u << 16)) | ((1024u >> 4) << 16);   // MN-major: LBO field
+    const uint32_t vlo_mn2 = (umma_desc_lo(smem_u32(q_s + sh.off_v + sh.kv_bytes)) & ~(1u << 16)) | ((1024u >> 4) << 16);   // SPLIT: V block 1
     const int nk = N >> 4;
     uint32_t par = 0;
     const uint32_t lb = smem_u32(&sb[0]);
     auto issue_load = [&](int it) {
       int qt, h, b;
       item_coords(sh, p, it, qt, h, b);
+      if (SPLIT) {   // two 64-wide bf16 blocks per operand: bf16 columns [128 h, 128 h + 64) and [128 h + 64, 128 h + 128)
+        mbar_expect_tx(lb, (uint32_t)(2 * 128 * 128 + 4 * N * 128));
+        for (int j = 0; j < 2; ++j) {
+          tma_load_2d(smem_u32(q_s + j * 16384), &map_q, lb, h * 128 + j * 64, b * p.q_period + p.q_pad + qt * 128);
+          tma_load_2d(smem_u32(q_s + sh.off_k + j * sh.kv_bytes), &map_k, lb, h * 128 + j * 64, b * p.k_period + p.k_pad);
+          tma_load_2d(smem_u32(q_s + sh.off_v + j * sh.kv_bytes), &map_v, lb, h * 128 + j * 64, b * p.k_period + p.k_pad);
+        }
+        return;
+      }
       mbar_expect_tx(lb, (uint32_t)(128 * 128 + 2 * N * 128));
       // 64-column boxes starting at the head's first column; for D = 48 the last 16 columns belong to
       // the next head (or are zero-filled past the matrix) and are never touched by the MMAs
@@ -130,8 +149,19 @@ __global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __
       tc_fence_after();
       // S = Q K^T
       if (leader) {
-        for (int k = 0; k < ((sh.dbg & 32) ? 1 : (p.D >> 4)); ++k)
-          umma_bf16(tm, umma_desc_make(qlo + 2 * k, kDescHiSw128), umma_desc_make(klo + 2 * k, kDescHiSw128), sh.idesc_s, k ? 1u : 0u);
+        if (SPLIT) {   // per k-block (A k-step, B k-step): (0,0) (1,1) hi.hi | (2,0) (3,1) lo.hi | (0,2) (1,3) hi.lo
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+              const uint32_t ka = (uint32_t)(k < 4 ? k : k - 4) * 2u, kb = (uint32_t)(k < 2 ? k : k - 2) * 2u;
+              umma_bf16(tm, umma_desc_make(qlo + (uint32_t)j * (16384u >> 4) + ka, kDescHiSw128),
+                        umma_desc_make(klo + (uint32_t)j * (sh.kv_bytes >> 4) + kb, kDescHiSw128), sh.idesc_s, (j | k) ? 1u : 0u);
+            }
+        } else {
+          for (int k = 0; k < ((sh.dbg & 32) ? 1 : (p.D >> 4)); ++k)
+            umma_bf16(tm, umma_desc_make(qlo + 2 * k, kDescHiSw128), umma_desc_make(klo + 2 * k, kDescHiSw128), sh.idesc_s, k ? 1u : 0u);
+        }
         umma_commit(smem_u32(&sb[1]));
       }
       __syncwarp();
@@ -141,8 +171,17 @@ __global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __
       if (leader) {
         for (int kk = 0; kk < ((sh.dbg & 16) ? 1 : nk); ++kk) {
           const uint32_t alo = qlo + (uint32_t)(kk >> 2) * (16384u >> 4) + (uint32_t)(kk & 3) * 2u;
-          umma_bf16(tm, umma_desc_make(alo, kDescHiSw128), umma_desc_make(vlo_mn + (uint32_t)kk * (2048u >> 4), kDescHiSw128),
-                    sh.idesc_o, kk ? 1u : 0u);
+          if (SPLIT) {   // (P_hi + P_lo) against both V blocks: O' columns [0, 64) and [64, 128)
+            const uint32_t alo2 = alo + (sh.off_pl >> 4);
+            const uint32_t v0 = vlo_mn + (uint32_t)kk * (2048u >> 4), v1 = vlo_mn2 + (uint32_t)kk * (2048u >> 4);
+            umma_bf16(tm, umma_desc_make(alo, kDescHiSw128), umma_desc_make(v0, kDescHiSw128), sh.idesc_o, kk ? 1u : 0u);
+            umma_bf16(tm, umma_desc_make(alo2, kDescHiSw128), umma_desc_make(v0, kDescHiSw128), sh.idesc_o, 1u);
+            umma_bf16(tm + 64u, umma_desc_make(alo, kDescHiSw128), umma_desc_make(v1, kDescHiSw128), sh.idesc_o, kk ? 1u : 0u);
+            umma_bf16(tm + 64u, umma_desc_make(alo2, kDescHiSw128), umma_desc_make(v1, kDescHiSw128), sh.idesc_o, 1u);
+          } else {
+            umma_bf16(tm, umma_desc_make(alo, kDescHiSw128), umma_desc_make(vlo_mn + (uint32_t)kk * (2048u >> 4), kDescHiSw128),
+                      sh.idesc_o, kk ? 1u : 0u);
+          }
         }
         umma_commit(smem_u32(&sb[3]));
       }
@@ -243,9 +282,21 @@ __global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __
 #pragma unroll
           for (int g = 0; g < ((sh.dbg & 4) ? 0 : 4); ++g) {
             const int chunk = (c & 1) * 4 + g;   // 16-byte chunk (8 keys) inside the 64-key block row
-            sts128(blk + ((chunk ^ (r & 7)) << 4),
-                   make_uint4(pack_bf16x2(v[g * 8], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
-                              pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7])));
+            if (SPLIT) {   // P = P_hi + P_lo, two bf16 tiles with the same layout
+              uint32_t wh[4], wl[4];
+#pragma unroll
+              for (int k2 = 0; k2 < 4; ++k2) {
+                float r0, r1;
+                wh[k2] = bf16_pair_hi(v[g * 8 + 2 * k2], v[g * 8 + 2 * k2 + 1], r0, r1);
+                wl[k2] = bf16_pair(r0, r1);
+              }
+              sts128(blk + ((chunk ^ (r & 7)) << 4), make_uint4(wh[0], wh[1], wh[2], wh[3]));
+              sts128(blk + sh.off_pl + ((chunk ^ (r & 7)) << 4), make_uint4(wl[0], wl[1], wl[2], wl[3]));
+            } else {
+              sts128(blk + ((chunk ^ (r & 7)) << 4),
+                     make_uint4(pack_bf16x2(v[g * 8], v[g * 8 + 1]), pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]),
+                                pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]), pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7])));
+            }
           }
         }
         if (sh.halves == 2) xchg[256 + half * 128 + r] = sum;
@@ -257,8 +308,32 @@ __global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __
         tc_fence_after();
         if (sh.halves == 2) sum += xchg[256 + (half ^ 1) * 128 + r];   // written before the partner's bar_p arrive, which precedes bar_o
         const float inv = 1.f / sum;
+        if (SPLIT) {   // O' = [sum p v_hi (0..31) | sum p v_lo (0..31) | v_hi (32..63) | v_lo (32..63)]: 2 groups of 32 elements
+          char* og = reinterpret_cast<char*>(p.o) + (((size_t)b * p.q_period + p.q_pad + tq) * p.o_pitch + (size_t)h * 64) * 4;
+          float w[32];
+#pragma unroll 1
+          for (int g = 0; g < 2; ++g) {
+            tmem_ld32(trow + g * 64, v);
+            tmem_ld32(trow + g * 64 + 32, w);
+            if (tq < p.Tq) {
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                uint32_t wh[4], wl[4];
+#pragma unroll
+                for (int k2 = 0; k2 < 4; ++k2) {
+                  const int i = q4 * 8 + 2 * k2;
+                  float r0, r1;
+                  wh[k2] = bf16_pair_hi((v[i] + w[i]) * inv, (v[i + 1] + w[i + 1]) * inv, r0, r1);
+                  wl[k2] = bf16_pair(r0, r1);
+                }
+                *reinterpret_cast<uint4*>(og + g * 128 + q4 * 16) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+                *reinterpret_cast<uint4*>(og + g * 128 + 64 + q4 * 16) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+              }
+            }
+          }
+        }
         bf16* orow = reinterpret_cast<bf16*>(p.o) + ((size_t)b * p.q_period + p.q_pad + tq) * p.o_pitch + h * p.D;
-        for (int c = oc_lo; c < oc_hi; ++c) {
+        for (int c = oc_lo; c < (SPLIT ? oc_lo : oc_hi); ++c) {
           tmem_ld32(trow + c * 32, v);
           if (tq < p.Tq && !(sh.dbg & 8)) {
 #pragma unroll
@@ -544,9 +619,11 @@ struct AttnTcPlan {
   int pdl;   // programmatic dependent launch, as the option stood when the plan was built
 };
 
-static bool attn_tc_long_capable(const AttnParams& p) { return p.D == 64 && p.Tk > ATL_KB && p.text == nullptr; }
+static bool attn_tc_long_capable(const AttnParams& p) { return p.D == 64 && p.Tk > ATL_KB && p.text == nullptr && !p.split; }
 static bool attn_tc_long(const AttnParams& p) { return attn_tc_long_capable(p) && p.Tk > 256; }
 bool attn_tc_supported(const AttnParams& p) {
+  if (p.split)   // split storage: head depth 64 only (a head = two groups of 32 elements), all keys at once
+    return p.D == 64 && p.Tk >= 1 && p.Tk <= 256 && p.q_pitch % 32 == 0 && p.k_pitch % 32 == 0 && p.v_pitch % 32 == 0 && p.o_pitch % 32 == 0;
   return (((p.D == 64 || p.D == 48) && p.Tk >= 1 && p.Tk <= 256) || attn_tc_long(p)) && p.q_pitch % 8 == 0 && p.k_pitch % 8 == 0 &&
          p.v_pitch % 8 == 0 && p.o_pitch % 8 == 0;
 }
@@ -594,6 +671,7 @@ AttnTcPlan* attn_tc_plan_create(const AttnParams& p, int q_rows, int k_rows, cha
   sh.nblk = (sh.N + 63) / 64;
   sh.nchunk = (sh.N + 31) / 32;
   int cols = sh.nchunk * 32 < 64 ? 64 : sh.nchunk * 32;
+  if (p.split && cols < 128) cols = 128;   // O' has 128 columns (hi and lo column of every output element)
   sh.tmem_cols = cols <= 64 ? 64 : cols <= 128 ? 128 : 256;
   sh.QT = (p.Tq + 127) / 128;
   sh.items = p.B * p.H * sh.QT;
@@ -602,15 +680,18 @@ AttnTcPlan* attn_tc_plan_create(const AttnParams& p, int q_rows, int k_rows, cha
   // c_format F32 [4,6) | a,b BF16 [7,10),[10,13) | b_major [16] | N>>3 [17,23) | M>>4 [24,29)
   const uint32_t base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
   sh.idesc_s = base | ((uint32_t)(sh.N >> 3) << 17);
-  sh.idesc_o = base | (1u << 16) | ((uint32_t)(p.D >> 3) << 17);   // B = V is MN-major, N = head depth
+  sh.idesc_o = base | (1u << 16) | ((uint32_t)((p.split ? 64 : p.D) >> 3) << 17);   // B = V is MN-major, N = head depth (split: one 64-column block)
   sh.scale_log2 = p.scale * 1.4426950408889634f;
   sh.dbg = g_attn_dbg;
   const uint32_t kv_bytes = (uint32_t)sh.N * 128u;
-  uint32_t pq = 16384u + kv_bytes;                    // Q | K
-  if (pq < (uint32_t)sh.nblk * 16384u) pq = (uint32_t)sh.nblk * 16384u;   // overlaid by P
-  sh.off_k = 16384u;
+  const uint32_t nb = p.split ? 2u : 1u;              // 64-wide bf16 blocks per operand (split storage: hi|lo groups)
+  sh.kv_bytes = kv_bytes;
+  sh.off_pl = (uint32_t)sh.nblk * 16384u;             // P_lo behind P_hi (split)
+  uint32_t pq = nb * (16384u + kv_bytes);             // Q | K
+  if (pq < nb * (uint32_t)sh.nblk * 16384u) pq = nb * (uint32_t)sh.nblk * 16384u;   // overlaid by P (split: P_hi | P_lo)
+  sh.off_k = nb * 16384u;
   sh.off_v = pq;
-  sh.off_mask = pq + kv_bytes;
+  sh.off_mask = pq + nb * kv_bytes;
   sh.off_xchg = sh.off_mask + (uint32_t)sh.nchunk * 32u * 4u;
   sh.slot_bytes = (sh.off_xchg + 4u * 128u * 4u + 1023u) & ~1023u;
   sh.halves = (g_attn_halves == 2 && sh.nchunk >= 4) ? 2 : 1;   // splitting the columns did not pay off (measured): off by default
@@ -628,14 +709,16 @@ AttnTcPlan* attn_tc_plan_create(const AttnParams& p, int q_rows, int k_rows, cha
   const int ctas = (sh.items + ns - 1) / ns;
   a->grid = dim3(ctas < num_sms ? ctas : num_sms);
   a->threads = (32 + 128 * sh.halves) * ns;
-  const uint64_t qcols = (uint64_t)p.H * p.D, kcols = (uint64_t)p.H * p.D;
-  if (!make_map(&a->map_q, p.q, (uint64_t)q_rows, qcols, (uint64_t)p.q_pitch, 128, err, errlen) ||
-      !make_map(&a->map_k, p.k, (uint64_t)k_rows, kcols, (uint64_t)p.k_pitch, (uint32_t)sh.N, err, errlen) ||
-      !make_map(&a->map_v, p.v, (uint64_t)k_rows, kcols, (uint64_t)p.v_pitch, (uint32_t)sh.N, err, errlen)) {
+  const uint64_t em = p.split ? 2 : 1;   // bf16 numbers per element (split storage: the row matrices are viewed as bf16 [rows, 2 * pitch])
+  const uint64_t qcols = em * p.H * p.D, kcols = em * p.H * p.D;
+  if (!make_map(&a->map_q, p.q, (uint64_t)q_rows, qcols, em * p.q_pitch, 128, err, errlen) ||
+      !make_map(&a->map_k, p.k, (uint64_t)k_rows, kcols, em * p.k_pitch, (uint32_t)sh.N, err, errlen) ||
+      !make_map(&a->map_v, p.v, (uint64_t)k_rows, kcols, em * p.v_pitch, (uint32_t)sh.N, err, errlen)) {
     delete a;
     return nullptr;
   }
-  cudaError_t ce = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t ce = p.split ? cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                           : cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (ce != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); delete a; return nullptr; }
   return a;
 }
@@ -657,7 +740,8 @@ int attn_tc_launch(const AttnTcPlan* a, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = a->pdl ? 1 : 0;
   if (a->long_keys) return cudaLaunchKernelEx(&cfg, attn_tc_long_kernel, a->map_q, a->map_k, a->map_v, a->lsh, a->p) == cudaSuccess ? 0 : 1;
-  return cudaLaunchKernelEx(&cfg, attn_tc_kernel, a->map_q, a->map_k, a->map_v, a->sh, a->p) == cudaSuccess ? 0 : 1;
+  if (a->p.split) return cudaLaunchKernelEx(&cfg, attn_tc_kernel<true>, a->map_q, a->map_k, a->map_v, a->sh, a->p) == cudaSuccess ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, attn_tc_kernel<false>, a->map_q, a->map_k, a->map_v, a->sh, a->p) == cudaSuccess ? 0 : 1;
 }
 
 }  // namespace dhg

@@ -799,7 +799,8 @@ struct Builder {
       a[s].B = P->B; a[s].H = H; a[s].D = D; a[s].Tq = Tq; a[s].Tk = Tk;
       a[s].scale = 1.0f / sqrtf((float)D);
       a[s].text = masked ? P->text : nullptr;
-      if (P->prec == PREC_BF16 && P->attn_impl == 1 && attn_tc_supported(a[s])) {
+      a[s].split = P->split ? 1 : 0;
+      if ((P->prec == PREC_BF16 || P->split) && P->attn_impl == 1 && attn_tc_supported(a[s])) {
         char buf[512];
         plans[s] = attn_tc_plan_create(a[s], q_rows, k_rows, buf, sizeof(buf));
         if (!plans[s]) { fail("plan: tcgen05 attention: %s", buf); failed = true; return; }
@@ -1567,7 +1568,7 @@ int32_t dhg_plan(dhg_ctx* c, int32_t B, int32_t T, int32_t L, int32_t S, int32_t
   P->B = B; P->T = T; P->L = L; P->S = S; P->prec = precision;
   P->gemm_impl = c->opt_gemm;   // 1: tcgen05 GEMMs (bf16 storage, or split storage in fp32 precision); 0: CUDA-core GEMMs
   P->split = precision == DHG_PREC_FP32 && P->gemm_impl == 1;
-  P->attn_impl = (precision == DHG_PREC_BF16) ? c->opt_attn : 0;
+  P->attn_impl = (precision == DHG_PREC_BF16 || P->split) ? c->opt_attn : 0;   // tcgen05 attention (bf16 or split storage)
   if (build_plan(c, P)) { free_plan(P); return 1; }
   CUDA_OK(cudaDeviceSynchronize());
   c->plan = P;
@@ -1919,6 +1920,7 @@ int32_t dhg_debug_attention(int32_t device, const dhg_debug_attn* d, int32_t imp
   a.B = d->B; a.H = d->H; a.D = d->D; a.Tq = d->Tq; a.Tk = d->Tk;
   a.scale = 1.0f / sqrtf((float)d->D);
   a.text = d->text;
+  a.split = impl == 3 ? 1 : 0;   // 3: tcgen05 kernel on split storage (the fp32-contract mode); pitches in elements
   cudaStream_t st = (cudaStream_t)stream;
   AttnTcPlan* ap = nullptr;
   if (impl >= 1) {   // 2: the key-block kernel also where all keys would fit at once (128 < Tk <= 256)

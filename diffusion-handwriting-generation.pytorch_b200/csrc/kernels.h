@@ -12,6 +12,7 @@ struct AttnParams {
   int B, H, D, Tq, Tk;
   float scale;                                             // 1/sqrt(D)
   const int64_t* text;                                     // [B, Tk] token ids (0 = masked key) or null
+  int split = 0;                                           // tcgen05 kernel: q / k / v / o are in split storage (common.cuh bfs)
 };
 
 struct HeadParams {

@@ -217,7 +217,9 @@ int32_t dhg_debug_tc_gemm_ex(int32_t device, const void* dev_a_bf16, int32_t lda
 
 /* Test hook: one attention launch over caller-provided bf16 row matrices (head h = columns
  * [h*D, h*D+D)); row(b, t) = b*period + pad + t.  impl 0 = CUDA-core kernel, 1 = tcgen05 kernel
- * (all keys at once for Tk <= 256, key blocks beyond), 2 = tcgen05 key-block kernel (unmasked, D = 64, Tk > 128). */
+ * (all keys at once for Tk <= 256, key blocks beyond), 2 = tcgen05 key-block kernel (unmasked, D = 64, Tk > 128),
+ * 3 = tcgen05 kernel on split storage (fp32-contract mode: q / k / v / o in groups of 32 hi | 32 lo bf16, pitches in
+ * elements, D = 64, Tk <= 256). */
 typedef struct dhg_debug_attn {
   const void* q; const void* k; const void* v; void* o;
   int32_t q_pitch, k_pitch, v_pitch, o_pitch;
