@@ -115,7 +115,14 @@ struct StepCtx {
   int step;               // sampling step index (tail tables)
   HeadParams head;
 };
-typedef std::function<int(cudaStream_t, const StepCtx&)> Op;
+// One launch (or a short fixed group of launches) of the plan; `name` is for DHG_SYNC_OPS=1 fault localisation.
+struct Op {
+  std::function<int(cudaStream_t, const StepCtx&)> fn;
+  std::string name;
+  template <typename F>
+  Op(F f) : fn(std::move(f)) {}
+  int operator()(cudaStream_t st, const StepCtx& sc) const { return fn(st, sc); }
+};
 
 struct Act {
   void* p = nullptr;
@@ -708,6 +715,7 @@ struct Builder {
     tail_gemm = false;
     head_gemm = false;
     dhg_ctx* cc = c;
+    const std::string op_name = "gemm " + wkey + " rows=" + std::to_string(rows);
     ops->push_back([=](cudaStream_t st, const StepCtx& sc) -> int {
       if (skippable && sc.fuse_tail) return 0;
       if (skip_bit & sc.fuse_skip) return 0;   // this conv_skip is contracted inside the block's last GEMM
@@ -744,6 +752,7 @@ struct Builder {
       }
       return 0;
     });
+    ops->back().name = op_name;
   }
 
   // When to request the next item's Q / K / V tiles (attention_tc.cu): right after P V helps the shapes with few slots
@@ -834,6 +843,7 @@ struct Builder {
       const int r = DHG_STORAGE(Pl, T, return launch_attention_simt<T>(a[set], st););
       return r ? fail("attention: unsupported head depth %d", a[set].D) : 0;
     });
+    ops->back().name = std::string(tc ? "attention (tcgen05)" : "attention (CUDA cores)") + " Tq=" + std::to_string(Tq) + " Tk=" + std::to_string(Tk) + " H=" + std::to_string(H);
   }
   void attention(const void* q, int qp, const void* k, int kp, const void* v, int vp, const Act& o, int H, int D,
                  int Tq, int q_period, int q_pad, int Tk, int k_period, int k_pad, bool masked, int q_rows, int k_rows) {
@@ -1144,8 +1154,18 @@ int build_plan(dhg_ctx* c, Plan* P) {
 }
 
 int run_ops(const std::vector<Op>& ops, cudaStream_t st, const StepCtx& sc) {
-  for (auto& op : ops)
-    if (op(st, sc)) return 1;
+  static const bool sync_ops = getenv("DHG_SYNC_OPS") != nullptr;   // debugging aid: synchronise after every op and name the one that faulted
+  for (size_t i = 0; i < ops.size(); ++i) {
+    if (ops[i](st, sc)) return 1;
+    if (sync_ops) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(st, &cs);
+      if (cs == cudaStreamCaptureStatusNone) {
+        const cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return fail("op %zu (%s) faulted: %s", i, ops[i].name.c_str(), cudaGetErrorString(e));
+      }
+    }
+  }
   return 0;
 }
 
@@ -1605,6 +1625,10 @@ int32_t dhg_denoise(dhg_ctx* c, const float* strokes, const int64_t* text, const
   for (size_t i = 0; i < P->step_ops.size(); ++i) {
     const bool is_head = (i + 1 == P->step_ops.size());
     if (P->step_ops[i](st, is_head ? sc : sc_in)) return 1;
+    if (getenv("DHG_SYNC_OPS")) {
+      const cudaError_t e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) return fail("step op %zu (%s) faulted: %s", i, P->step_ops[i].name.c_str(), cudaGetErrorString(e));
+    }
   }
   CUDA_OK(cudaGetLastError());
   c->last_launches = 2 + P->launches_once + P->launches_text + P->launches_step;

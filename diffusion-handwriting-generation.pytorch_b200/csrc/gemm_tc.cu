@@ -749,8 +749,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       const float* gam_g = nullptr;
       const float* bet_g = nullptr;
       if (film_mode == 2) {   // per-sample FiLM vectors (dhg_denoise with per-sample sigma): global loads
-        gam_g = e.gamma + (size_t)b * e.film_bstride;
-        bet_g = e.beta + (size_t)b * e.film_bstride;
+        // halo / trailing rows are zeroed below, but their "sample" index can be one past the batch (the trailing
+        // zero row of the padded layout): they read sample 0's vectors instead of running off the [B, tot] table
+        const size_t bs = live ? (size_t)b : 0;
+        gam_g = e.gamma + bs * e.film_bstride;
+        bet_g = e.beta + bs * e.film_bstride;
       }
       if (my_nch == 0 && last_sub) {   // no column chunk for this warp in this tile shape: just release the accumulators
         tc_fence_before();

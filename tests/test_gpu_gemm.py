@@ -191,6 +191,8 @@ TUNE_CASES = [
     ("ln_film_k768_384_act", 20050, 768, 384, 1, dict(period=50, pad_first=1, ln=True, film=1, raw=False, act=True)),
     ("dual_fc_conv_skip_192", 20685, 192, 192, 1, dict(period=197, pad_first=1, dual_K2=256)),
     ("dual_fc_conv_skip_128", 19999, 128, 128, 1, dict(period=393, pad_first=1, dual_K2=128)),
+    ("tiny_rows_qkv", 3, 384, 1152, 1, dict(period=2, pad_first=1, rowbias=True)),
+    ("tiny_rows_ln", 3, 768, 384, 1, dict(period=2, pad_first=1, ln=True, film=1, res_pre=True)),
 ]
 
 
@@ -240,5 +242,64 @@ def test_tc_gemm_every_tile_configuration_gives_the_same_bits(built_lib, name, r
         gemm_ref.run(built_lib, c)
         for got, want in zip(outputs(c), base):
             assert torch.equal(got.view(torch.int16), want.view(torch.int16)), (name, "reverse")
+    finally:
+        setopt(bn=-1, g=-1, resident=-1, pair=-1, rev=0)
+
+
+SPLIT_TUNE_CASES = [
+    ("conv_film_act", 20000, 128, 64, 3, dict(period=50, pad_first=1, film=1, raw=False, act=True)),
+    ("rowbias_qkv", 20685, 192, 576, 1, dict(period=197, pad_first=1, rowbias=True)),
+    ("ffn1_act_768", 20050, 384, 768, 1, dict(period=50, pad_first=1, raw=False, act=True)),
+    ("ln_film_respre_384", 20050, 384, 384, 1, dict(period=50, pad_first=1, ln=True, film=1, res_pre=True)),
+    ("skipconv_up", 23660, 128, 192, 3, dict(period=169, pad_first=1, res_post=True, up=True, act=True)),
+    ("tiny_rows_qkv", 3, 384, 1152, 1, dict(period=2, pad_first=1, rowbias=True)),
+    ("tiny_rows_conv", 10, 128, 128, 3, dict(period=9, pad_first=1, film=1, raw=False, act=True)),
+    ("tiny_rows_ln", 3, 768, 384, 1, dict(period=2, pad_first=1, ln=True, film=1, res_pre=True)),
+    ("tiny_enc2_conv2", 6, 96, 192, 3, dict(period=5, pad_first=1, film=2, raw=False, act=True)),
+    ("tiny_enc2_conv1", 6, 128, 96, 3, dict(period=5, pad_first=1, film=2, raw=False, act=True)),
+    ("small_k96", 700, 96, 192, 3, dict(period=99, pad_first=1, film=1, raw=False, act=True)),
+]
+
+
+@pytest.mark.parametrize("name,rows,K,N,taps,kw", SPLIT_TUNE_CASES, ids=[c[0] for c in SPLIT_TUNE_CASES])
+def test_tc_gemm_split_io_every_tile_configuration_gives_the_same_bits(built_lib, name, rows, K, N, taps, kw):
+    """The plan-time tuner picks among these by timing, so every one of them must be right (and bit-identical) in split
+    I/O too, down to matrices of a few rows (T = 8 -> one stroke row per sample at the deepest level)."""
+    import gemm_ref
+
+    def setopt(**o):
+        for k, v in o.items():
+            assert built_lib.dhg_set_option(None, f"tune_{k}".encode(), v) == 0
+
+    def outputs(c):
+        return [t.clone() for t in (c["out_raw"], c["out_act"]) if t is not None]
+
+    try:
+        setopt(bn=-1, g=-1, resident=-1, pair=-1)
+        c = gemm_ref.make_split_case(rows, K, N, taps, seed=len(name) + rows, **kw)
+        gemm_ref.run(built_lib, c)
+        base = outputs(c)
+        ref = gemm_ref.reference(c)
+        got = gemm_ref.split_unpack(base[0]).double()
+        want = ref if c["out_raw"] is not None else torch.nn.functional.silu(ref)
+        assert (got - want).abs().max().item() < 1e-4 * max(1.0, want.abs().max().item())
+        tried = 0
+        bns = [N] if kw.get("ln") else [b for b in (384, 256, 192, 128, 96, 64) if N % b == 0]
+        for bn in bns:
+            for resident, pair in ((1, 0), (0, 0), (0, 1)):
+                setopt(bn=-1 if kw.get("ln") else bn, g=1, resident=resident, pair=pair)
+                for t in (c["out_raw"], c["out_act"]):
+                    if t is not None:
+                        t.fill_(float("nan"))
+                if gemm_ref.run(built_lib, c, allow_unavailable=True) is None:
+                    continue
+                tried += 1
+                for g_, w_ in zip(outputs(c), base):
+                    assert torch.equal(g_.view(torch.int16), w_.view(torch.int16)), (name, bn, resident, pair)
+        assert tried >= 1, tried
+        setopt(bn=-1, g=-1, resident=-1, pair=-1, rev=1)
+        gemm_ref.run(built_lib, c)
+        for g_, w_ in zip(outputs(c), base):
+            assert torch.equal(g_.view(torch.int16), w_.view(torch.int16)), (name, "reverse")
     finally:
         setopt(bn=-1, g=-1, resident=-1, pair=-1, rev=0)

@@ -113,8 +113,11 @@ def test_denoise_other_shapes_match_oracle(writers, state_dict, name, B, T, L, p
     style = torch.randn(B, 14, 1280, generator=g)
     eps_o, pen_o = O.denoiser_forward(state_dict, strokes, text, sigma, style)
     for mode, tol, ptol in (("fp32", 1e-4, 1e-4), ("fp32_simt", 1e-4, 1e-4), ("bf16", BF16_REL, 1e-2)):
-        eps, pen, _ = writers[mode].denoise(strokes, text, sigma, style)
-        assert torch.isfinite(eps).all() and torch.isfinite(pen).all()
+        try:
+            eps, pen, _ = writers[mode].denoise(strokes, text, sigma, style)
+            assert torch.isfinite(eps).all() and torch.isfinite(pen).all()
+        except Exception as e:   # name the mode: a device fault surfaces wherever the next synchronisation happens
+            raise AssertionError(f"{name} / {mode}: {type(e).__name__}: {e}") from e
         assert _rel(eps.cpu(), eps_o) < tol, (name, mode)
         assert (pen.cpu() - pen_o).abs().max() < ptol, (name, mode)
 
