@@ -871,9 +871,13 @@ void tc_gemm_set_option(int which, int value) {
 }
 
 typedef void (*TcKernFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcShape, const Epilogue);
-struct TcKernEntry { int ln, aux, film, out; TcKernFn fn, fn_pair, fn_split; };   // fn_pair: the cta_group::2 build, fn_split: column-split LayerNorm (cluster launches only)
-#define DHG_TC_K(ln, aux, film, out) {ln, aux, film, out, tc_gemm_kernel<ln, aux, film, out, false>, tc_gemm_kernel<ln, aux, film, out, true>, nullptr}
-#define DHG_TC_KL(aux, film, out) {1, aux, film, out, tc_gemm_kernel<1, aux, film, out, false>, tc_gemm_kernel<1, aux, film, out, true>, tc_gemm_kernel<1, aux, film, out, false, true>}
+// fn_pair: the cta_group::2 build, fn_split: column-split LayerNorm (cluster launches only), fn_sio / fn_sio_pair: split I/O
+struct TcKernEntry { int ln, aux, film, out; TcKernFn fn, fn_pair, fn_split, fn_sio, fn_sio_pair; };
+#define DHG_TC_K(ln, aux, film, out) {ln, aux, film, out, tc_gemm_kernel<ln, aux, film, out, false>, tc_gemm_kernel<ln, aux, film, out, true>, nullptr, \
+                                      tc_gemm_kernel<ln, aux, film, out, false, false, true>, tc_gemm_kernel<ln, aux, film, out, true, false, true>}
+#define DHG_TC_KD(ln, aux, film, out) {ln, aux, film, out, tc_gemm_kernel<ln, aux, film, out, false>, tc_gemm_kernel<ln, aux, film, out, true>, nullptr, nullptr, nullptr}
+#define DHG_TC_KL(aux, film, out) {1, aux, film, out, tc_gemm_kernel<1, aux, film, out, false>, tc_gemm_kernel<1, aux, film, out, true>, tc_gemm_kernel<1, aux, film, out, false, true>, \
+                                   tc_gemm_kernel<1, aux, film, out, false, false, true>, tc_gemm_kernel<1, aux, film, out, true, false, true>}
 // Every epilogue variant the denoiser plan uses (engine.cu), film = 1 (sampling: one FiLM vector per step);
 // anything else (per-sample FiLM in dhg_denoise, test-only combinations) runs the generic instance.
 static const TcKernEntry kTcKernels[] = {
@@ -883,8 +887,8 @@ static const TcKernEntry kTcKernels[] = {
     DHG_TC_K(0, AUX_RES_POST, 1, 1),      // fc + skip
     DHG_TC_K(0, AUX_RES_POST_UP, 0, 3),   // skip_conv_k + upsample
     DHG_TC_K(0, AUX_ROWBIAS, 0, 1),       // q / kv / qkv projections with the PE-folded bias table
-    DHG_TC_K(0, AUX_NONE, 0, 4),          // dec1.conv_skip in dot mode (tail fusion)
-    DHG_TC_K(0, AUX_NONE, 1, 4),          // dec1.conv2 in dot mode
+    DHG_TC_KD(0, AUX_NONE, 0, 4),         // dec1.conv_skip in dot mode (tail fusion; bf16 only)
+    DHG_TC_KD(0, AUX_NONE, 1, 4),         // dec1.conv2 in dot mode
     DHG_TC_KL(AUX_NONE, 1, 1),          // text_dense
     DHG_TC_KL(AUX_NONE, 0, 1),          // style_ffn.3
     DHG_TC_KL(AUX_NONE, 1, 2),          // text_ffn.3
@@ -892,17 +896,16 @@ static const TcKernEntry kTcKernels[] = {
     DHG_TC_KL(AUX_RES_PRE, 1, 3),       // mha2.dense
     DHG_TC_KL(AUX_RES_PRE, 1, 1),       // ffn.3
     DHG_TC_KL(AUX_RES_PRE, 1, 2),       // text-style mha.dense
-    {-1, -1, -1, -1, tc_gemm_kernel<-1, -1, -1, -1, false>, tc_gemm_kernel<-1, -1, -1, -1, true>, tc_gemm_kernel<-1, -1, -1, -1, false, true>},   // generic
+    {-1, -1, -1, -1, tc_gemm_kernel<-1, -1, -1, -1, false>, tc_gemm_kernel<-1, -1, -1, -1, true>, tc_gemm_kernel<-1, -1, -1, -1, false, true>,
+     tc_gemm_kernel<-1, -1, -1, -1, false, false, true>, tc_gemm_kernel<-1, -1, -1, -1, true, false, true>},   // generic
 };
 // dual-operand mode (engine.cu: conv_skip folded into the last GEMM of a ConvBlock): bias-only epilogue, raw (or raw + SiLU'd) output
 static const TcKernFn kTcKernelsDual[2][2] = {
     {tc_gemm_kernel<0, AUX_NONE, 0, 1, false, false, false, true>, tc_gemm_kernel<0, AUX_NONE, 0, 1, true, false, false, true>},
     {tc_gemm_kernel<0, AUX_NONE, 0, 3, false, false, false, true>, tc_gemm_kernel<0, AUX_NONE, 0, 3, true, false, false, true>}};
-// split I/O (fp32-contract mode): the generic instance only, plain and CTA pair
-static const TcKernFn kTcKernelsSio[2] = {tc_gemm_kernel<-1, -1, -1, -1, false, false, true>, tc_gemm_kernel<-1, -1, -1, -1, true, false, true>};
-static TcKernFn pick_kernel(int ln, int aux, int film, int out, int cluster_mode) {   // 0 plain, 1 CTA pair, 2 column-split LayerNorm
+static TcKernFn pick_kernel(int ln, int aux, int film, int out, int cluster_mode) {   // 0 plain, 1 CTA pair, 2 column-split LayerNorm, 3 / 4 split I/O plain / pair
   const int n = (int)(sizeof(kTcKernels) / sizeof(kTcKernels[0]));
-  auto of = [&](const TcKernEntry& k) { return cluster_mode == 2 ? k.fn_split : cluster_mode == 1 ? k.fn_pair : k.fn; };
+  auto of = [&](const TcKernEntry& k) { return cluster_mode == 4 ? k.fn_sio_pair : cluster_mode == 3 ? k.fn_sio : cluster_mode == 2 ? k.fn_split : cluster_mode == 1 ? k.fn_pair : k.fn; };
   if (g_opt_specialize)
     for (int i = 0; i < n - 1; ++i)
       if (kTcKernels[i].ln == ln && kTcKernels[i].aux == aux && kTcKernels[i].film == film && kTcKernels[i].out == out && of(kTcKernels[i]))
@@ -1119,11 +1122,10 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
     return nullptr;
   }
   const int out_mode = dot ? 4 : ((e.out_raw ? 1 : 0) | (e.out_act ? 2 : 0));
-  const int cluster_mode = sh.split ? 2 : sh.pair ? 1 : 0;
+  const int cluster_mode = sio ? (sh.pair ? 4 : 3) : sh.split ? 2 : sh.pair ? 1 : 0;
   p->fn_shared = e.bias ? pick_kernel(e.ln ? 1 : 0, aux_kind, e.film_planned ? 1 : 0, out_mode, cluster_mode)
                         : pick_kernel(-1, -1, -1, -1, cluster_mode);   // the specialised variants assume a bias vector
   p->fn_generic = pick_kernel(-1, -1, -1, -1, cluster_mode);
-  if (sio) p->fn_shared = p->fn_generic = kTcKernelsSio[sh.pair ? 1 : 0];
   if (dual) {
     if (out_mode != 1 && out_mode != 3) { snprintf(err, errlen, "dual-operand mode stores a raw (or raw + SiLU'd) output"); delete p; return nullptr; }
     if (sh.split) { snprintf(err, errlen, "dual-operand mode does not fit the column-split cluster"); delete p; return nullptr; }
