@@ -763,7 +763,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       for (int ci = 0; ci < my_nch; ++ci) {
         const int c = c_lo + ci;
         const int n = n0 + c * 32;
+        if (ew == 0) DHG_TR(0x33, ci);
         tmem_ld32(trow + c * 32, v);
+        if (ew == 0) DHG_TR(0x34, ci);
         if (ci == my_nch - 1 && last_sub) {   // my last TMEM read of this super-tile: hand the accumulators back
           tc_fence_before();
           __syncwarp();
@@ -804,6 +806,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
+        if (ew == 0) DHG_TR(0x35, ci);
         if (out_mode == 4) {   // dot mode: 3 partial dot products of my columns, the row itself is not stored
           const uint32_t dsa = smem_u32(dot_s) + (uint32_t)n * 4u;
           const uint32_t nb = (uint32_t)sh.N * 4u;
@@ -820,6 +823,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         } else {
           if (out_mode & 1) store_chunk(&map_oraw, n, v, false, false);
           if (out_mode & 2) store_chunk(&map_oact, n, v, true, (out_mode & 1) != 0);
+          if (ew == 0) DHG_TR(0x36, ci);
         }
       }
       if (out_mode == 4) {   // add up the column parts of the row through shared memory (tables alternate with the tile parity)
