@@ -142,7 +142,7 @@ int64_t dhg_plan_bytes(const dhg_ctx* ctx);
  * Per context:
  *   "gemm"  0 CUDA-core GEMM + row epilogue kernel, 1 tcgen05 GEMM with fused epilogue (default 1; in fp32 precision
  *           1 selects the split-storage tensor-core path, 0 the exact fp32 FMA path)
- *   "attn"  0 CUDA-core attention, 1 tcgen05 attention (bf16 only; default 1)
+ *   "attn"  0 CUDA-core attention, 1 tcgen05 attention (bf16 storage, and split storage in fp32 precision; default 1)
  *   "graph" 0/1 one CUDA graph per chain in dhg_sample (default 1)
  * Process-wide (ctx may be NULL; shared by every context of the process):
  *   "text_sets"    1..6 text sides of that many consecutive steps run at once on their own streams (default 2)
@@ -152,10 +152,16 @@ int64_t dhg_plan_bytes(const dhg_ctx* ctx);
  *   "tail_fusion"  0..3 chain only: 1 last fc + FiLM + skip + heads as one kernel on per-step folded tables, 2 also the
  *                  last block's conv2 / conv_skip in dot mode (no a2, skip, d1), 3 conv_skip folded onto the 3 head
  *                  channels (default 3)
- *   "head_fusion"  0/1 chain only: enc1.conv_skip(input_dense(x)) straight from x (default 1)
+ *   "head_fusion"  0/1 chain only: enc1.conv_skip(input_dense(x)) straight from x (default 1; unused while bit 0 of
+ *                  "skip_fusion" is set)
+ *   "skip_fusion"  bit mask 0..31, bf16 chain only: conv_skip of ConvBlock enc1 / enc2 / enc4 / dec3 / dec2 (bits 0..4) is
+ *                  contracted inside the block's last GEMM (dual-operand launch, FiLM scale folded into per-step weights;
+ *                  default 31)
  *   "w_resident", "specialize", "interleave", "pair", "pdl", "attn_early", "tune_bn", "tune_g", "tune_resident",
  *   "tune_pair", "tune_rev": kernel-selection overrides used by tests/test_gpu_kernel_variants.py and test_gpu_gemm.py
- * None of them changes results beyond the documented tolerances; all but the two fusions leave the bits unchanged. */
+ * None of them changes results beyond the documented tolerances; all but the three fusions leave the bits unchanged.
+ * Debugging aid (environment): DHG_SYNC_OPS=1 synchronises after every launch of the un-graphed paths (dhg_denoise,
+ * "graph" = 0) and names the launch that faulted in dhg_last_error(). */
 int32_t dhg_set_option(dhg_ctx* ctx, const char* key, int32_t value);
 
 /* Test hook: copy a named intermediate activation of the last forward ("h1", "h2c",
