@@ -518,6 +518,9 @@ def run_b200(args, rank, world, local_rank):
                 other[key] = {"failed": str(e)[:200]}
         line["other_configs"] = other
         line["gpu_eager_baseline"] = gpu_eager_leg(dev, args.eager_batch)
+        # BASELINE configs[1] / configs[0] shapes: the reference's PyTorch path on this GPU beside `other_configs`
+        line["gpu_eager_baseline_small"] = {f"B={b}": {k: v for k, v in gpu_eager_leg(dev, b).items() if k in ("fp32", "bf16_autocast")}
+                                            for b in (64, 1)}
     if args.cpu_baseline and world >= 1:
         lines_s, s_chain, cores, kind = cpu_reference_leg(args.cpu_batch, 1, 1)
         line["cpu_baseline"] = {
