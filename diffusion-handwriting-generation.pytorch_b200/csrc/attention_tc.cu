@@ -47,7 +47,16 @@ struct AttnTcShape {
   uint32_t off_pl;    // split storage: offset of the P_lo tile behind the P_hi tile
   float scale_log2;   // scale * log2(e)
   int dbg;            // timing experiments: 1 skip max pass, 2 skip exp, 4 skip P stores, 8 skip O stores, 16 skip PV MMAs, 32 skip S MMAs
+  unsigned long long* trace;   // debug: CTA 0, slot 0 appends (clock << 16 | code << 8 | item) events: role 0 control warp, 1 first softmax warp
+  int trace_cap;
 };
+
+#define DHG_ATR(role, code, it)                                                                             \
+  do {                                                                                                      \
+    if (sh.trace && blockIdx.x == 0 && lane == 0 && tr_n < (unsigned)sh.trace_cap)                          \
+      sh.trace[(size_t)(role) * sh.trace_cap + tr_n++] =                                                    \
+          ((unsigned long long)clock64() << 16) | ((unsigned long long)(code) << 8) | (unsigned)((it) & 0xff); \
+  } while (0)
 
 __device__ __forceinline__ void item_coords(const AttnTcShape& sh, const AttnParams& p, int item, int& qt, int& h, int& b) {
   if (sh.rev) item = sh.items - 1 - item;
@@ -63,8 +72,10 @@ __device__ __forceinline__ void item_coords(const AttnTcShape& sh, const AttnPar
 // bf16 hi tile and a lo tile; V's two blocks are two MN-major B operands of 64 columns each, (v_hi x 32 | v_lo x 32), so
 // O' = (P_hi + P_lo) V' has 128 fp32 columns and O[d] = O'[hi column of d] + O'[lo column of d]; the row is normalised in
 // fp32 and stored split again.
-template <bool SPLIT>
-__global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __grid_constant__ CUtensorMap map_q,
+// MAXS: slots per CTA this instance may be launched with.  The block is 160 * slots threads, so the 2-slot shapes
+// (level-1 self-attention: 208 score columns per item) get a 200-register budget instead of the 64 of a 960-thread block.
+template <bool SPLIT, int MAXS>
+__global__ void __launch_bounds__(160 * MAXS, 1) attn_tc_kernel(const __grid_constant__ CUtensorMap map_q,
                                                                             const __grid_constant__ CUtensorMap map_k,
                                                                             const __grid_constant__ CUtensorMap map_v,
                                                                             const AttnTcShape sh, const AttnParams p) {
@@ -115,6 +126,9 @@ __global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __
     const uint32_t vlo_mn2 = (umma_desc_lo(smem_u32(q_s + sh.off_v + sh.kv_bytes)) & ~(1u << 16)) | ((1024u >> 4) << 16);   // SPLIT: V block 1
     const int nk = N >> 4;
     uint32_t par = 0;
+    unsigned tr_n = 0;
+    const bool tr_on = s == 0;
+    int tr_i = 0;
     const uint32_t lb = smem_u32(&sb[0]);
     auto issue_load = [&](int it) {
       int qt, h, b;
@@ -145,8 +159,10 @@ __global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __
         if (leader) issue_load(item);
       }
       mbar_wait(lb, par);
+      if (tr_on) DHG_ATR(0, 0x02, tr_i);
       if (sh.early) mbar_wait(smem_u32(&sb[4]), par ^ 1u);   // TMEM columns free (previous item's O has been read out)
       tc_fence_after();
+      if (tr_on) DHG_ATR(0, 0x03, tr_i);
       // S = Q K^T
       if (leader) {
         if (SPLIT) {   // per k-block (A k-step, B k-step): (0,0) (1,1) hi.hi | (2,0) (3,1) lo.hi | (0,2) (1,3) hi.lo
@@ -168,6 +184,7 @@ __global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __
       // O = P V   (P written by the softmax threads over the Q/K tiles)
       mbar_wait(smem_u32(&sb[2]), par);
       tc_fence_after();
+      if (tr_on) DHG_ATR(0, 0x05, tr_i);
       if (leader) {
         for (int kk = 0; kk < ((sh.dbg & 16) ? 1 : nk); ++kk) {
           const uint32_t alo = qlo + (uint32_t)(kk >> 2) * (16384u >> 4) + (uint32_t)(kk & 3) * 2u;
@@ -188,9 +205,11 @@ __global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __
       __syncwarp();
       if (sh.early && item + stride < sh.items) {
         mbar_wait(smem_u32(&sb[3]), par);   // P V done: Q / K(P) / V tiles are dead
+        if (tr_on) DHG_ATR(0, 0x07, tr_i);
         if (leader) issue_load(item + stride);
         __syncwarp();
       }
+      ++tr_i;
     }
   } else {
     // ===== softmax group of slot `slot`: thread = (query row, column half) =====
@@ -211,11 +230,15 @@ __global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __
       const int c_hi = sh.halves == 2 ? (half ? sh.nchunk : (sh.nchunk + 1) / 2) : sh.nchunk;
       const int oc_lo = sh.halves == 2 ? half : 0, oc_hi = sh.halves == 2 ? half + 1 : 2;   // 32-column chunks of O
       uint32_t par = 0;
+      unsigned tr_n = 0;
+      const bool tr_on = slot == 0 && wis == 0;
+      int tr_i = 0;
       float v[32];
-      for (int item = (int)blockIdx.x * NS + slot; item < sh.items; item += stride, par ^= 1u) {
+      for (int item = (int)blockIdx.x * NS + slot; item < sh.items; item += stride, par ^= 1u, ++tr_i) {
         int qt, h, b;
         item_coords(sh, p, item, qt, h, b);
         const int tq = qt * 128 + r;
+        if (tr_on) DHG_ATR(1, 0x11, tr_i);
         if (masked) {
           // additive key mask (attention.py:44: mask * -1e9), pre-multiplied by log2(e)
           for (int j = gtid; j < sh.nchunk * 32; j += gthreads)
@@ -224,6 +247,7 @@ __global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __
         }
         mbar_wait(smem_u32(&sb[1]), par);
         tc_fence_after();
+        if (tr_on) DHG_ATR(1, 0x12, tr_i);
         // pass 1: row maximum (log2 units); keys >= Tk never count.  Unmasked: max over the raw scores, scaled once
         // (scale > 0); only the last chunk can contain padding keys.
         const int c_full = p.Tk >> 5;   // chunks [0, c_full) hold real keys only
@@ -237,9 +261,16 @@ __global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __
               const float t = fmaf(v[i], sh.scale_log2, mask_s[j]);
               if (j < p.Tk) mx = fmaxf(mx, t);
             }
-          } else if (c < c_full) {
+          } else if (c < c_full) {   // four independent chains: the 32-deep dependent one paced the whole pass
+            float m0 = fmaxf(v[0], v[1]), m1 = fmaxf(v[2], v[3]), m2 = fmaxf(v[4], v[5]), m3 = fmaxf(v[6], v[7]);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, v[i]);
+            for (int i = 8; i < 32; i += 8) {
+              m0 = fmaxf(m0, fmaxf(v[i], v[i + 1]));
+              m1 = fmaxf(m1, fmaxf(v[i + 2], v[i + 3]));
+              m2 = fmaxf(m2, fmaxf(v[i + 4], v[i + 5]));
+              m3 = fmaxf(m3, fmaxf(v[i + 6], v[i + 7]));
+            }
+            mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
@@ -252,6 +283,7 @@ __global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __
           asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(gthreads) : "memory");
           mx = fmaxf(mx, xchg[(half ^ 1) * 128 + r]);
         }
+        if (tr_on) DHG_ATR(1, 0x13, tr_i);
         // pass 2: p = 2^(t - max), row sum, bf16 P into the swizzled K-major operand layout
         float sum = 0.f;
         const float nmx = -mx;
@@ -269,14 +301,16 @@ __global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __
               sum += v[i];
             }
           } else {
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // independent partial sums (see pass 1)
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const float t = fmaf(v[i], sh.scale_log2, nmx);
               float e = t;
               if (!(sh.dbg & 2)) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
               v[i] = e;
-              sum += e;
+              if ((i & 3) == 0) s0 += e; else if ((i & 3) == 1) s1 += e; else if ((i & 3) == 2) s2 += e; else s3 += e;
             }
+            sum += (s0 + s1) + (s2 + s3);
           }
           const uint32_t blk = smem_u32(q_s) + (uint32_t)(c >> 1) * 16384u + (uint32_t)r * 128u;
 #pragma unroll
@@ -303,9 +337,11 @@ __global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __
         tc_fence_before();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the MMA
         mbar_arrive(smem_u32(&sb[2]));
+        if (tr_on) DHG_ATR(1, 0x14, tr_i);
         // O row
         mbar_wait(smem_u32(&sb[3]), par);
         tc_fence_after();
+        if (tr_on) DHG_ATR(1, 0x15, tr_i);
         if (sh.halves == 2) sum += xchg[256 + (half ^ 1) * 128 + r];   // written before the partner's bar_p arrive, which precedes bar_o
         const float inv = 1.f / sum;
         if (SPLIT) {   // O' = [sum p v_hi (0..31) | sum p v_lo (0..31) | v_hi (32..63) | v_lo (32..63)]: 2 groups of 32 elements
@@ -333,9 +369,23 @@ __global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __
           }
         }
         bf16* orow = reinterpret_cast<bf16*>(p.o) + ((size_t)b * p.q_period + p.q_pad + tq) * p.o_pitch + h * p.D;
+        const bool wide = (p.o_pitch & 15) == 0 && ((reinterpret_cast<uintptr_t>(p.o) | (uintptr_t)(h * p.D * 2)) & 31) == 0 && (p.D & 15) == 0;
         for (int c = oc_lo; c < (SPLIT ? oc_lo : oc_hi); ++c) {
           tmem_ld32(trow + c * 32, v);
           if (tq < p.Tq && !(sh.dbg & 8)) {
+            if (wide) {   // 32-byte stores: whole sectors, half the store instructions
+#pragma unroll
+              for (int g = 0; g < 2; ++g) {
+                if (c * 32 + g * 16 >= p.D) break;
+                uint32_t w8[8];
+#pragma unroll
+                for (int k2 = 0; k2 < 8; ++k2) w8[k2] = pack_bf16x2(v[g * 16 + 2 * k2] * inv, v[g * 16 + 2 * k2 + 1] * inv);
+                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(orow + c * 32 + g * 16), "r"(w8[0]), "r"(w8[1]),
+                             "r"(w8[2]), "r"(w8[3]), "r"(w8[4]), "r"(w8[5]), "r"(w8[6]), "r"(w8[7])
+                             : "memory");
+              }
+              continue;
+            }
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               if (c * 32 + g * 8 >= p.D) break;
@@ -345,9 +395,11 @@ __global__ void __launch_bounds__(160 * AT_MAX_SLOTS, 1) attn_tc_kernel(const __
             }
           }
         }
-        // the slot's smem tiles and TMEM columns may be overwritten by the next item
+        // the slot's smem tiles and TMEM columns may be overwritten by the next item.  (Handing the slot back BEFORE the
+        // stores, with the packed row held in registers, was measured: -2 % with 2 slots, spills with 6: not kept.)
         tc_fence_before();
         mbar_arrive(smem_u32(&sb[4]));
+        if (tr_on) DHG_ATR(1, 0x16, tr_i);
       }
     }
   }
@@ -604,10 +656,19 @@ __global__ void __launch_bounds__(ATL_SLOTS * 160, 1) attn_tc_long_kernel(const 
 
 }  // namespace
 
-int g_attn_dbg = 0, g_attn_halves = 1, g_attn_pdl = 1, g_attn_early = 1;
-void attn_tc_set_debug(int v) { if (v == -200 || v == -201) g_attn_early = v == -201; else if (v >= 0) g_attn_dbg = v; else if (v <= -100) g_attn_pdl = v == -101; else g_attn_halves = -v; }
+int g_attn_dbg = 0, g_attn_halves = 1, g_attn_pdl = 1, g_attn_early = 1, g_attn_max_slots = AT_MAX_SLOTS;
+void attn_tc_set_debug(int v) { if (v <= -300 && v >= -306) g_attn_max_slots = -300 - v > 0 ? -300 - v : AT_MAX_SLOTS; else if (v == -200 || v == -201) g_attn_early = v == -201; else if (v >= 0) g_attn_dbg = v; else if (v <= -100) g_attn_pdl = v == -101; else g_attn_halves = -v; }
+
+using AttnTcFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnTcShape, const AttnParams);
+// the instance with the smallest thread bound (= largest register budget) that covers the block
+static AttnTcFn attn_tc_instance(bool split, int threads) {
+  if (threads <= 160 * 2) return split ? attn_tc_kernel<true, 2> : attn_tc_kernel<false, 2>;
+  if (threads <= 160 * 4) return split ? attn_tc_kernel<true, 4> : attn_tc_kernel<false, 4>;
+  return split ? attn_tc_kernel<true, AT_MAX_SLOTS> : attn_tc_kernel<false, AT_MAX_SLOTS>;
+}
 
 struct AttnTcPlan {
+  AttnTcFn fn = nullptr;
   CUtensorMap map_q, map_k, map_v;
   bool long_keys = false;   // Tk > 256: attn_tc_long_kernel (key blocks, two-pass softmax)
   AttnLongShape lsh;
@@ -683,6 +744,7 @@ AttnTcPlan* attn_tc_plan_create(const AttnParams& p, int q_rows, int k_rows, cha
   sh.idesc_o = base | (1u << 16) | ((uint32_t)((p.split ? 64 : p.D) >> 3) << 17);   // B = V is MN-major, N = head depth (split: one 64-column block)
   sh.scale_log2 = p.scale * 1.4426950408889634f;
   sh.dbg = g_attn_dbg;
+  sh.trace = nullptr; sh.trace_cap = 0;
   const uint32_t kv_bytes = (uint32_t)sh.N * 128u;
   const uint32_t nb = p.split ? 2u : 1u;              // 64-wide bf16 blocks per operand (split storage: hi|lo groups)
   sh.kv_bytes = kv_bytes;
@@ -701,6 +763,7 @@ AttnTcPlan* attn_tc_plan_create(const AttnParams& p, int q_rows, int k_rows, cha
   const size_t bar_bytes = (5 * AT_MAX_SLOTS + 2) * 8;
   while (ns > 1 && (size_t)ns * sh.slot_bytes + bar_bytes + 1024 > (size_t)227 * 1024) --ns;
   if (ns > AT_MAX_SLOTS) ns = AT_MAX_SLOTS;
+  if (ns > g_attn_max_slots) ns = g_attn_max_slots;   // experiment: fewer slots = more registers per thread
   while (ns > 1 && (sh.items + ns - 1) / ns < num_sms) --ns;   // small problems: spread over the SMs first
   sh.NS = ns;
   sh.off_bar = (uint32_t)ns * sh.slot_bytes;
@@ -717,8 +780,8 @@ AttnTcPlan* attn_tc_plan_create(const AttnParams& p, int q_rows, int k_rows, cha
     delete a;
     return nullptr;
   }
-  cudaError_t ce = p.split ? cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
-                           : cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  a->fn = attn_tc_instance(p.split != 0, a->threads);
+  cudaError_t ce = cudaFuncSetAttribute(a->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (ce != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); delete a; return nullptr; }
   return a;
 }
@@ -727,6 +790,8 @@ void attn_tc_plan_destroy(AttnTcPlan* a) { delete a; }
 bool attn_tc_plan_is_long(const AttnTcPlan* a) { return a->long_keys; }
 void attn_tc_plan_set_reverse(AttnTcPlan* a, int rev) { a->sh.rev = rev ? 1 : 0; a->lsh.rev = rev ? 1 : 0; }
 void attn_tc_plan_set_early_load(AttnTcPlan* a, int on) { a->sh.early = on ? 1 : 0; }
+void attn_tc_plan_set_trace(AttnTcPlan* a, unsigned long long* buf, int cap) { a->sh.trace = buf; a->sh.trace_cap = cap; }
+int attn_tc_plan_slots(const AttnTcPlan* a) { return a->long_keys ? ATL_SLOTS : a->sh.NS; }
 
 int attn_tc_launch(const AttnTcPlan* a, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
@@ -740,8 +805,7 @@ int attn_tc_launch(const AttnTcPlan* a, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = a->pdl ? 1 : 0;
   if (a->long_keys) return cudaLaunchKernelEx(&cfg, attn_tc_long_kernel, a->map_q, a->map_k, a->map_v, a->lsh, a->p) == cudaSuccess ? 0 : 1;
-  if (a->p.split) return cudaLaunchKernelEx(&cfg, attn_tc_kernel<true>, a->map_q, a->map_k, a->map_v, a->sh, a->p) == cudaSuccess ? 0 : 1;
-  return cudaLaunchKernelEx(&cfg, attn_tc_kernel<false>, a->map_q, a->map_k, a->map_v, a->sh, a->p) == cudaSuccess ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, a->fn, a->map_q, a->map_k, a->map_v, a->sh, a->p) == cudaSuccess ? 0 : 1;
 }
 
 }  // namespace dhg

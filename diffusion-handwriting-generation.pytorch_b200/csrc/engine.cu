@@ -1765,6 +1765,7 @@ int32_t dhg_set_option(dhg_ctx* c, const char* key, int32_t value) {
   if (key && !strcmp(key, "interleave")) { tc_gemm_set_option(4, value); return 0; }
   if (key && !strcmp(key, "attn_dbg")) { attn_tc_set_debug(value); return 0; }
   if (key && !strcmp(key, "attn_early")) { attn_tc_set_debug(value ? -201 : -200); return 0; }
+  if (key && !strcmp(key, "attn_max_slots")) { attn_tc_set_debug(-300 - (value < 0 ? 0 : value > 6 ? 6 : value)); return 0; }
   if (key && !strcmp(key, "pair")) { tc_gemm_set_option(7, value); return 0; }
   if (key && !strcmp(key, "pdl")) { tc_gemm_set_option(6, value); attn_tc_set_debug(value ? -101 : -100); return 0; }
   if (key && !strcmp(key, "w_resident")) { tc_gemm_set_option(2, value); return 0; }
@@ -1781,6 +1782,7 @@ int32_t dhg_set_option(dhg_ctx* c, const char* key, int32_t value) {
   if (key && !strcmp(key, "tune_resident")) { tc_gemm_set_option(12, value); return 0; }
   if (key && !strcmp(key, "tune_pair")) { tc_gemm_set_option(13, value); return 0; }
   if (key && !strcmp(key, "specialize")) { tc_gemm_set_option(3, value); return 0; }
+  if (key && !strcmp(key, "max_stages_a")) { tc_gemm_set_option(15, value); return 0; }
   if (!c || !key) return fail("dhg_set_option: null argument");
   if (!strcmp(key, "gemm")) c->opt_gemm = value ? 1 : 0;
   else if (!strcmp(key, "graph")) c->opt_graph = value ? 1 : 0;
@@ -1865,23 +1867,26 @@ int32_t dhg_debug_tc_gemm_ex(int32_t device, const void* a, int32_t lda, int32_t
   cudaStream_t st = (cudaStream_t)stream;
   if (getenv("DHG_DESCRIBE")) { tc_gemm_describe(p, buf, sizeof(buf)); fprintf(stderr, "tc_gemm plan: %s\n", buf); }
   if (getenv("DHG_TRACE")) {   // timeline of CTA 0 for one launch, printed to stderr
-    const int cap = 4096;   // entries per role (3 roles)
+    const int cap = 4096, roles = 10;   // entries per role: producer, MMA, 8 epilogue warps
     unsigned long long* tb = nullptr;
-    cudaMalloc(&tb, 3 * cap * sizeof(unsigned long long));
-    cudaMemset(tb, 0, 3 * cap * sizeof(unsigned long long));
+    cudaMalloc(&tb, roles * cap * sizeof(unsigned long long));
+    cudaMemset(tb, 0, roles * cap * sizeof(unsigned long long));
     tc_gemm_launch(p, e, st);   // warm
     cudaStreamSynchronize(st);
     tc_gemm_set_trace(p, tb, cap);
     tc_gemm_launch(p, e, st);
     cudaStreamSynchronize(st);
     tc_gemm_set_trace(p, nullptr, 0);
-    std::vector<unsigned long long> h(3 * cap);
-    cudaMemcpy(h.data(), tb, 3 * cap * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    std::vector<unsigned long long> h((size_t)roles * cap);
+    cudaMemcpy(h.data(), tb, (size_t)roles * cap * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     cudaFree(tb);
     unsigned long long t0 = ~0ull;
     for (auto x : h) if (x && (x >> 16) < t0) t0 = x >> 16;
-    for (auto x : h)
-      if (x) fprintf(stderr, "TR %llu %02x %u\n", (x >> 16) - t0, (unsigned)((x >> 8) & 0xff), (unsigned)(x & 0xff));
+    for (size_t i = 0; i < h.size(); ++i) {   // TR: producer, MMA and first epilogue warp (tools/trace_summary.py); TW: the other epilogue warps
+      const unsigned long long x = h[i];
+      const int role = (int)(i / cap);
+      if (x) fprintf(stderr, "%s %llu %02x %u %d\n", role <= 2 ? "TR" : "TW", (x >> 16) - t0, (unsigned)((x >> 8) & 0xff), (unsigned)(x & 0xff), role);
+    }
   }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -1953,6 +1958,26 @@ int32_t dhg_debug_attention(int32_t device, const dhg_debug_attn* d, int32_t imp
     if (!ap) return fail("dhg_debug_attention: %s", buf);
   }
   auto launch = [&]() -> int { return ap ? attn_tc_launch(ap, st) : launch_attention_simt<bf16>(a, st); };
+  if (ap && getenv("DHG_TRACE") && !attn_tc_plan_is_long(ap)) {   // timeline of CTA 0 / slot 0 for one launch, printed to stderr
+    const int cap = 2048;
+    unsigned long long* tb = nullptr;
+    cudaMalloc(&tb, 2 * cap * sizeof(unsigned long long));
+    cudaMemset(tb, 0, 2 * cap * sizeof(unsigned long long));
+    launch();
+    cudaStreamSynchronize(st);
+    attn_tc_plan_set_trace(ap, tb, cap);
+    launch();
+    cudaStreamSynchronize(st);
+    attn_tc_plan_set_trace(ap, nullptr, 0);
+    std::vector<unsigned long long> h(2 * cap);
+    cudaMemcpy(h.data(), tb, 2 * cap * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(tb);
+    unsigned long long t0 = ~0ull;
+    for (auto x : h) if (x && (x >> 16) < t0) t0 = x >> 16;
+    fprintf(stderr, "attention plan: slots=%d\n", attn_tc_plan_slots(ap));
+    for (auto x : h)
+      if (x) fprintf(stderr, "ATR %llu %02x %u\n", (x >> 16) - t0, (unsigned)((x >> 8) & 0xff), (unsigned)(x & 0xff));
+  }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   int rc = launch();

@@ -91,6 +91,14 @@ struct TcShape {
           ((unsigned long long)clock64() << 16) | ((unsigned long long)(code) << 8) | (unsigned)((tile) & 0xff); \
   } while (0)
 
+// per-chunk points (tcgen05.ld / math / store phases of tools/trace_summary.py): only in a -DDHG_TRACE_FINE build, they
+// cost ~5 executed instructions each inside the hottest loop of the library even when no trace is taken
+#ifdef DHG_TRACE_FINE
+#define DHG_TR_FINE(code, tile) DHG_TR(code, tile)
+#else
+#define DHG_TR_FINE(code, tile) do { } while (0)
+#endif
+
 // m / period and m % period for 0 <= m < 2^24 (checked at plan time) without the ~40-instruction integer division:
 // float estimate, exact after one correction step either way.
 __device__ __forceinline__ void fast_divmod(int m, int period, float inv_period, int& q, int& r) {
@@ -240,7 +248,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned tr_n = 0;
-  const int tr_role = warp < 2 ? warp : 2;
+  const int tr_role = warp;   // 0 producer, 1 MMA, 2.. epilogue warps (the per-chunk points only from the first one)
   // work assignment: tile `it` of this CTA -> (m tile, column group)
   // sticky: the CTAs [grp_cta0[g], grp_cta0[g+1]) work on column group g only (more CTAs for the groups whose
   // epilogue also has per-position bias rows to fetch), so that group's W tiles can stay resident
@@ -484,7 +492,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     // flight while this tile is being finished.
     uint32_t aux_issued = 0, aux_consumed = 0, st_flip = 0;
     int iss_t = t_first, iss_sub = 0, iss_ci = 0;   // (super-tile, row tile, chunk) of the next flat chunk to issue
-    int iss_src = -1, iss_ng = 0;                   // cached per issue tile: my row's source row, the column group
+    int iss_ng = 0;                                 // cached per issue tile: the column group,
+    uint32_t iss_off[4] = {0, 0, 0, 0};             //   (gathered rows) source offsets in 16-byte units of the 4 rows this lane copies; ~0u: none
     int iss_row0 = 0;                               //   and (same-row residuals) the first row of my 32-row slab
     const bool aux_same_row = aux_kind == AUX_RES_PRE || aux_kind == AUX_RES_POST;
     const bool aux_col_limited = aux_kind == AUX_ROWBIAS;
@@ -507,11 +516,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
             const bool f_pad = (fmm >= nvalid) || (pad_first && fj == 0);
             const int fpos = f_pad ? 0 : fj - pad_first;
             const bool f_live = f_in && !f_pad;
-            if (aux_kind == AUX_RES_POST_UP) iss_src = f_live ? fb * e.res_post_period_lo + 1 + (fpos >> 1) : -1;
-            else iss_src = f_live ? fpos : -1;
+            int my_src;
+            if (aux_kind == AUX_RES_POST_UP) my_src = f_live ? fb * e.res_post_period_lo + 1 + (fpos >> 1) : -1;
+            else my_src = f_live ? fpos : -1;
+            if (!kSIO) {   // the rows this lane copies (i * 8 + lane / 4), once per row tile instead of once per chunk
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int src = __shfl_sync(0xffffffffu, my_src, i * 8 + (lane >> 2));
+                iss_off[i] = src < 0 ? ~0u : (uint32_t)(((size_t)src * aux_pitch_bytes) >> 4);
+              }
+            } else {
+              iss_off[0] = (uint32_t)my_src;
+            }
           }
         }
-        const int aux_src = iss_src, fng = iss_ng;
+        const int aux_src = kSIO ? (int)iss_off[0] : 0, fng = iss_ng;
         const int col0 = fng * sh.BN + (c_lo + ci) * 32;
         const uint32_t slot = aux_ring + (f % (uint32_t)aux_depth) * aux_slot_bytes;
         if (kSIO) {   // 32 rows x 128 bytes: lane -> (row, one of 8 16-byte pieces), 128B-row xor swizzle
@@ -536,12 +555,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
             cp_async16(slot + rr * 64 + (((lane & 3) ^ ((rr >> 1) & 3)) << 4), gp0 + (size_t)(ok ? src : 0) * aux_pitch_bytes, ok ? 16u : 0u);
           }
         } else if (!aux_col_limited || col0 < aux_ncols) {
+          const char* gp0 = aux_base + (size_t)col0 * 2 + (lane & 3) * 16;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int rr = i * 8 + (lane >> 2), piece = lane & 3;
-            const int src = __shfl_sync(0xffffffffu, aux_src, rr);
-            const char* gp = aux_base + (size_t)(src < 0 ? 0 : src) * aux_pitch_bytes + (size_t)col0 * 2 + piece * 16;
-            cp_async16(slot + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4), gp, src < 0 ? 0u : 16u);
+            const bool ok = iss_off[i] != ~0u;
+            cp_async16(slot + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4), gp0 + ((size_t)(ok ? iss_off[i] : 0u) << 4), ok ? 16u : 0u);
           }
         }
       }
@@ -551,7 +570,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       }
       cp_async_commit();
     };
-    // wait for the oldest aux chunk, add my row of it to v, refill its slot with the next flat chunk
+    // wait for the oldest aux chunk, add my row of it to v, refill its slot with the next flat chunk.
+    // Note: cp.async groups and bulk (TMA store) groups are counted on the same scoreboard (both waits are DEPBAR.LE SB0
+    // in SASS; tools/micro/depbar_share.cu: a bulk wait_group.read behind a fresh cp.async takes 1500 instead of 200
+    // cycles), so the store's `bulk_wait_read<1>` also waits for all but one of the refills in flight.  Refilling only
+    // after the store's wait was measured and is NOT faster (q|k|v 90.5 -> 93.4 us, LayerNorm GEMMs +1..+4 us): the
+    // launch is not bound by this wait.
     auto consume_aux = [&](float* v, int col0) {
       cp_async_wait<aux_depth - 1>();
       __syncwarp();
@@ -592,10 +616,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
      const int n0 = ng * sh.BN;
      const int as = sh.acc_stages == 2 ? (it & 1) : 0;
      const uint32_t use = sh.acc_stages == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;
-     if (ew == 0) DHG_TR(0x30, it);
+     DHG_TR(0x30, it);
      mbar_wait(smem_u32(&tmem_full_bar[as]), use & 1u);
      tc_fence_after();
-     if (ew == 0) DHG_TR(0x31, it);
+     DHG_TR(0x31, it);
      for (int sub = 0; sub < sh.G; ++sub, ++tile_no) {
       const int m0 = (mts * tiles_per_super + sub + (int)cta_rank) * TC_BM;
       const bool last_sub = sub == sh.G - 1;
@@ -763,13 +787,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       for (int ci = 0; ci < my_nch; ++ci) {
         const int c = c_lo + ci;
         const int n = n0 + c * 32;
-        if (ew == 0) DHG_TR(0x33, ci);
+        if (ew == 0) DHG_TR_FINE(0x33, ci);
         tmem_ld32(trow + c * 32, v);
-        if (ew == 0) DHG_TR(0x34, ci);
+        if (ew == 0) DHG_TR_FINE(0x34, ci);
         if (ci == my_nch - 1 && last_sub) {   // my last TMEM read of this super-tile: hand the accumulators back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) { if (cta_rank) mbar_arrive_remote(smem_u32(&tmem_empty_bar[as]), 0); else mbar_arrive(smem_u32(&tmem_empty_bar[as])); }
+          DHG_TR(0x37, it);
         }
         if (ln) {
 #pragma unroll
@@ -806,7 +831,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
-        if (ew == 0) DHG_TR(0x35, ci);
+        if (ew == 0) DHG_TR_FINE(0x35, ci);
         if (out_mode == 4) {   // dot mode: 3 partial dot products of my columns, the row itself is not stored
           const uint32_t dsa = smem_u32(dot_s) + (uint32_t)n * 4u;
           const uint32_t nb = (uint32_t)sh.N * 4u;
@@ -823,7 +848,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         } else {
           if (out_mode & 1) store_chunk(&map_oraw, n, v, false, false);
           if (out_mode & 2) store_chunk(&map_oact, n, v, true, (out_mode & 1) != 0);
-          if (ew == 0) DHG_TR(0x36, ci);
+          if (ew == 0) DHG_TR_FINE(0x36, ci);
         }
       }
       if (out_mode == 4) {   // add up the column parts of the row through shared memory (tables alternate with the tile parity)
@@ -837,7 +862,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         }
       }
      }
-     if (ew == 0) DHG_TR(0x32, it);
+     DHG_TR(0x32, it);
     }
     if (aux_active) cp_async_wait<0>();
     if (lane == 0) bulk_wait<0>();   // all my output tiles have left shared memory and are written
@@ -858,6 +883,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 
 // experiment switches (dhg_set_option: "w_resident", "specialize", "interleave")
 int g_opt_w_resident = 1, g_opt_specialize = 1, g_opt_interleave = 1, g_opt_pdl = 1, g_opt_pair = 1;
+int g_opt_max_stages_a = 0;   // > 0: cap the A ring of resident-W plans (experiment: how much prefetch depth does a launch need?)
 // forced tile configuration for plans created without an explicit TcTune (tests sweep these through dhg_set_option)
 static TcTune g_tune_default = {-1, -1, -1, -1};
 static int g_tune_rev = 0;   // default walking direction of new plans (tests)
@@ -872,6 +898,7 @@ void tc_gemm_set_option(int which, int value) {
   else if (which == 6) g_opt_pdl = value;
   else if (which == 7) g_opt_pair = value;
   else if (which == 3) g_opt_specialize = value;
+  else if (which == 15) g_opt_max_stages_a = value;
 }
 
 typedef void (*TcKernFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcShape, const Epilogue);
@@ -1059,6 +1086,7 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   if (sh.w_resident) {
     int sa = (int)((budget - w_all) / sh.a_stage_bytes);
     sh.stages_a = sa > 8 ? 8 : sa;
+    if (g_opt_max_stages_a > 0 && sh.stages_a > g_opt_max_stages_a && g_opt_max_stages_a >= G) sh.stages_a = g_opt_max_stages_a;
     sh.stages_w = 1;
     w_bytes = w_all;
   } else {

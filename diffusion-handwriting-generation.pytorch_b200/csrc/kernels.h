@@ -107,6 +107,8 @@ bool attn_tc_supported(const AttnParams& p);
 // prefer_long: use the key-block kernel (two-pass softmax over blocks of 128 keys; always used for Tk > 256) also for
 // 128 < Tk <= 256 (unmasked, head depth 64); the engine times both at plan time
 AttnTcPlan* attn_tc_plan_create(const AttnParams& p, int q_rows, int k_rows, char* err, int errlen, int prefer_long = 0);
+void attn_tc_plan_set_trace(AttnTcPlan*, unsigned long long* buf, int cap);   // debug timeline of CTA 0, slot 0
+int attn_tc_plan_slots(const AttnTcPlan*);
 bool attn_tc_plan_is_long(const AttnTcPlan*);
 void attn_tc_plan_destroy(AttnTcPlan*);
 void attn_tc_plan_set_reverse(AttnTcPlan*, int rev);   // work items from the last sample to the first

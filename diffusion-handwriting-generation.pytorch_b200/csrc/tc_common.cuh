@@ -290,14 +290,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
+// v[0..8) += the 8 bf16 of u.  A bf16 is the upper half of an fp32: one shift / one mask per pair and a packed add
+// (the cvt route costs PRMT + IMAD.U32 per upper element and scalar FADDs: 20 instead of 12 instructions per call)
 __device__ __forceinline__ void add_bf16x8(const uint4& u, float* v) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
-    v[j * 2] += f.x;
-    v[j * 2 + 1] += f.y;
-  }
+  for (int j = 0; j < 4; ++j) add2(v[j * 2], v[j * 2 + 1], __uint_as_float(w[j] << 16), __uint_as_float(w[j] & 0xffff0000u));
 }
 
 

@@ -16,9 +16,12 @@ CASES = [("self L1 196x196 h3", 3, 196, 196, True, False, 1), ("self L2 98x98 h4
          ("cross L2 98x24 h4", 4, 98, 24, False, True, 1), ("cross L3 49x24 h6", 6, 49, 24, False, True, 2),
          ("text-style 24x70 h8 d48", 8, 24, 70, False, False, 1)]
 tot = [0.0, 0.0]
+if os.environ.get("ATTN_MAX_SLOTS"):
+    lib.dhg_set_option(None, b"attn_max_slots", int(os.environ["ATTN_MAX_SLOTS"]))
+IMPLS = (1,) if os.environ.get("ATTN_TC_ONLY") else (0, 1)
 for name, H, Tq, Tk, sa, mk, cnt in CASES:
     line = f"{name:22s}"
-    for impl in (0, 1):
+    for impl in IMPLS:
         D = 48 if "d48" in name else 64
         got, ref, ms = run_attention(lib, B, H, D, Tq, Tk, sa, mk, impl, seed=1, repeats=5)
         fl = 4.0 * B * H * Tq * Tk * D

@@ -6,7 +6,7 @@ ev = []
 for l in open(sys.argv[1]):
     if l.startswith('tc_gemm plan'): print(l.strip())
     if l.startswith('TR '):
-        _, t, c, i = l.split(); ev.append((int(t), int(c, 16), int(i)))
+        f = l.split(); t, c, i = f[1:4]; ev.append((int(t), int(c, 16), int(i)))
 ev.sort()
 lo, hi = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (6, 8)
 print(len(ev), 'events; span', ev[-1][0] - ev[0][0], 'cycles')
