@@ -53,6 +53,7 @@ static int g_opt_head_fusion = 1; // chain: enc1.conv_skip(input_dense(x)) compu
 static int g_opt_tail_fusion = 3; // chain: 1 last fc + FiLM + skip + heads as one kernel on folded tables, 2 also conv2 / conv_skip of the
                                   // last block in dot mode, so neither a2 nor skip nor d1 exist ("tail_fusion")
 static int g_opt_skip_fusion = 31; // chain: conv_skip folded into the last GEMM of a ConvBlock (bit i: enc1, enc2, enc4, dec3, dec2) ("skip_fusion")
+static int g_opt_attn_keyblock_auto = 0; // plan-time timing may pick the key-block attention kernel for 128 < Tk <= 256 ("attn_keyblock_auto")
 static int g_opt_serpentine = 1; // consumer kernels walk their rows opposite to their producer ("serpentine")
 static int g_opt_text_sets = 2;  // text sides of this many consecutive steps run at once (dhg_set_option "text_sets")
 static int fail(const char* fmt, ...) {
@@ -818,7 +819,11 @@ struct Builder {
         wrote(o.p, dir);
         if (g_opt_autotune) {
           if (s == 0) {
-            AttnTcPlan* alt = attn_tc_plan_create(a[s], q_rows, k_rows, buf, sizeof(buf), 1);   // null where the key-block kernel does not apply
+            // The key-block kernel sums its probabilities in another order than the all-keys kernel: letting a timing
+            // decide between them made the BITS of a result depend on the batch a plan was built for (seen as different
+            // sha1s of the same 64 prompts sharded over 1 and 2 GPUs).  Only the numerically identical variants (tile-load
+            // order) are timed by default; "attn_keyblock_auto" = 1 adds the key-block kernel for 128 < Tk <= 256.
+            AttnTcPlan* alt = g_opt_attn_keyblock_auto ? attn_tc_plan_create(a[s], q_rows, k_rows, buf, sizeof(buf), 1) : nullptr;
             if (alt) attn_tc_plan_set_reverse(alt, dir);
             variant = attention_pick(plans[0], alt);
             if (alt) attn_tc_plan_destroy(alt);
@@ -1772,6 +1777,7 @@ int32_t dhg_set_option(dhg_ctx* c, const char* key, int32_t value) {
   if (key && !strcmp(key, "text_sets")) { g_opt_text_sets = value; return 0; }
   if (key && !strcmp(key, "autotune")) { g_opt_autotune = value ? 1 : 0; return 0; }
   if (key && !strcmp(key, "serpentine")) { g_opt_serpentine = value ? 1 : 0; return 0; }
+  if (key && !strcmp(key, "attn_keyblock_auto")) { g_opt_attn_keyblock_auto = value ? 1 : 0; return 0; }
   if (key && !strcmp(key, "l2_hints")) { g_opt_l2_hints = value ? 1 : 0; return 0; }
   if (key && !strcmp(key, "tail_fusion")) { g_opt_tail_fusion = value < 0 ? 0 : value > 3 ? 3 : value; return 0; }
   if (key && !strcmp(key, "head_fusion")) { g_opt_head_fusion = value ? 1 : 0; return 0; }
@@ -1783,6 +1789,7 @@ int32_t dhg_set_option(dhg_ctx* c, const char* key, int32_t value) {
   if (key && !strcmp(key, "tune_pair")) { tc_gemm_set_option(13, value); return 0; }
   if (key && !strcmp(key, "specialize")) { tc_gemm_set_option(3, value); return 0; }
   if (key && !strcmp(key, "max_stages_a")) { tc_gemm_set_option(15, value); return 0; }
+  if (key && !strcmp(key, "direct_store")) { tc_gemm_set_option(16, value); return 0; }
   if (!c || !key) return fail("dhg_set_option: null argument");
   if (!strcmp(key, "gemm")) c->opt_gemm = value ? 1 : 0;
   else if (!strcmp(key, "graph")) c->opt_graph = value ? 1 : 0;

@@ -60,6 +60,7 @@ struct TcShape {
   int G;           // row tiles per super-tile (independent accumulators interleaved by the MMA warp)
   int m_super;     // ceil(m_tiles / G)
   int rev;         // walk the super-tiles from the last row to the first (see tc_gemm_plan_set_reverse)
+  int direct_store;   // bf16 outputs: each thread stores its 32 columns as two 32-byte st.global (no smem staging, no TMA store)
   int a_evict_first;   // A rows are read once by this launch: give them L2 evict-first priority
   int split;           // column-split LayerNorm: 2-CTA cluster per row tile, rank = column half
   int dot_n;           // dot mode: 3 * N floats of dot vectors in shared memory (0 = normal stores)
@@ -577,8 +578,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     // after the store's wait was measured and is NOT faster (q|k|v 90.5 -> 93.4 us, LayerNorm GEMMs +1..+4 us): the
     // launch is not bound by this wait.
     auto consume_aux = [&](float* v, int col0) {
+      if (ew == 0) DHG_TR_FINE(0x38, 0);
       cp_async_wait<aux_depth - 1>();
       __syncwarp();
+      if (ew == 0) DHG_TR_FINE(0x39, 0);
       const uint32_t slot = aux_ring + (aux_consumed % (uint32_t)aux_depth) * aux_slot_bytes;
       ++aux_consumed;
       if (kSIO) {
@@ -602,7 +605,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         for (int p = 0; p < 4; ++p) add_bf16x8(u[p], v + p * 8);
       }
       __syncwarp();
+      if (ew == 0) DHG_TR_FINE(0x3a, 0);
       issue_aux_flat();
+      if (ew == 0) DHG_TR_FINE(0x3b, 0);
     };
     const bool aux_active = aux_kind != AUX_NONE && my_nch > 0;
     if (aux_active)
@@ -669,6 +674,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
               tma_store_2d(omap, buf, col0 * 2 + half * 32, m0 + q * 32);
               bulk_commit();
               if (sh.out_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+            }
+          }
+          return;
+        }
+        if (sh.direct_store) {
+          if (in_range) {
+            bf16* orow = reinterpret_cast<bf16*>(act ? e.out_act : e.out_raw) + (size_t)m * (size_t)(act ? e.out_act_pitch : e.out_raw_pitch) + col0;
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              uint32_t w8[8];
+#pragma unroll
+              for (int k2 = 0; k2 < 8; ++k2) {
+                float a = v[g * 16 + k2 * 2], c = v[g * 16 + k2 * 2 + 1];
+                if (act) silu_fast2(a, c);
+                w8[k2] = pack_bf16x2(a, c);
+              }
+              asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(orow + g * 16), "r"(w8[0]), "r"(w8[1]), "r"(w8[2]),
+                           "r"(w8[3]), "r"(w8[4]), "r"(w8[5]), "r"(w8[6]), "r"(w8[7])
+                           : "memory");
             }
           }
           return;
@@ -883,6 +907,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 
 // experiment switches (dhg_set_option: "w_resident", "specialize", "interleave")
 int g_opt_w_resident = 1, g_opt_specialize = 1, g_opt_interleave = 1, g_opt_pdl = 1, g_opt_pair = 1;
+int g_opt_direct_store = 0;   // experiment: register -> global 32-byte stores instead of smem staging + TMA store
 int g_opt_max_stages_a = 0;   // > 0: cap the A ring of resident-W plans (experiment: how much prefetch depth does a launch need?)
 // forced tile configuration for plans created without an explicit TcTune (tests sweep these through dhg_set_option)
 static TcTune g_tune_default = {-1, -1, -1, -1};
@@ -899,6 +924,7 @@ void tc_gemm_set_option(int which, int value) {
   else if (which == 7) g_opt_pair = value;
   else if (which == 3) g_opt_specialize = value;
   else if (which == 15) g_opt_max_stages_a = value;
+  else if (which == 16) g_opt_direct_store = value;
 }
 
 typedef void (*TcKernFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcShape, const Epilogue);
@@ -1029,6 +1055,10 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   sh.aux_kind = aux_kind;
   sh.trace = nullptr; sh.trace_cap = 0;
   sh.rev = g_tune_rev;
+  // direct stores need 32-byte aligned rows: pitches in multiples of 16 elements, 32-byte aligned bases (not in split-I/O mode)
+  sh.direct_store = (g_opt_direct_store && !sio && !dot &&
+                     (!e.out_raw || (e.out_raw_pitch % 16 == 0 && (reinterpret_cast<uintptr_t>(e.out_raw) & 31) == 0)) &&
+                     (!e.out_act || (e.out_act_pitch % 16 == 0 && (reinterpret_cast<uintptr_t>(e.out_act) & 31) == 0))) ? 1 : 0;
   sh.a_evict_first = 0;
   sh.vec_bias_n = e.bias ? N : 0;
   sh.film_n = e.film_planned ? N : 0;

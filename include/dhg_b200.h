@@ -157,9 +157,14 @@ int64_t dhg_plan_bytes(const dhg_ctx* ctx);
  *   "skip_fusion"  bit mask 0..31, bf16 chain only: conv_skip of ConvBlock enc1 / enc2 / enc4 / dec3 / dec2 (bits 0..4) is
  *                  contracted inside the block's last GEMM (dual-operand launch, FiLM scale folded into per-step weights;
  *                  default 31)
+ *   "attn_keyblock_auto" 0/1 the plan-time timing may also pick the key-block attention kernel for 128 < Tk <= 256
+ *                  (default 0: that kernel sums in another order, so the BITS of a result would depend on which
+ *                  variant won the timing for the batch a plan was built for; Tk > 256 always uses it)
  *   "w_resident", "specialize", "interleave", "pair", "pdl", "attn_early", "tune_bn", "tune_g", "tune_resident",
  *   "tune_pair", "tune_rev": kernel-selection overrides used by tests/test_gpu_kernel_variants.py and test_gpu_gemm.py
- * None of them changes results beyond the documented tolerances; all but the three fusions leave the bits unchanged.
+ *   "max_stages_a", "direct_store", "attn_max_slots", "attn_dbg": measurement switches of tools/ 
+ * None of them changes results beyond the documented tolerances; all but the three fusions and "attn_keyblock_auto"
+ * leave the bits unchanged.
  * Debugging aid (environment): DHG_SYNC_OPS=1 synchronises after every launch of the un-graphed paths (dhg_denoise,
  * "graph" = 0) and names the launch that faulted in dhg_last_error(). */
 int32_t dhg_set_option(dhg_ctx* ctx, const char* key, int32_t value);

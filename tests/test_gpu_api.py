@@ -82,18 +82,20 @@ def test_sample_host_validates_like_sample(writer):
         writer.sample(text, style, x0=x0, noise=None, T=60)   # T not a multiple of 8
 
 
-@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
-def test_result_does_not_depend_on_the_sharding(state_dict, dtype):
-    """'results independent of N'.  A 16-prompt global batch through sharding.sample_sharded as 1, 2, 4 and 8
+@pytest.mark.parametrize("dtype,G,T,L,worlds", [("bf16", 16, 64, 10, (1, 2, 4, 8, 3)), ("fp32", 16, 64, 10, (1, 2, 4, 8, 3)),
+                                                 # BASELINE length: 196 keys at level 1, where two attention kernels with different
+                                                 # summation orders apply (the plan-time timing must not choose between them)
+                                                 ("bf16", 6, 392, 24, (1, 2, 3))])
+def test_result_does_not_depend_on_the_sharding(state_dict, dtype, G, T, L, worlds):
+    """'results independent of N'.  A G-prompt global batch through sharding.sample_sharded as 1, 2, 4 and 8
     'ranks' (each rank's slice is its own plan of its own batch size, exactly what a rank of an N-GPU job runs): the
     concatenated result has the same bits every time."""
     from dhg_b200 import DiffusionWriter
     from dhg_b200.sharding import sample_sharded, shard_bounds
 
-    G = 16
-    text, style, x0, noise = _inputs(G, 64, 10, seed=21)
+    text, style, x0, noise = _inputs(G, T, L, seed=21)
     results = []
-    for world in (1, 2, 4, 8, 3):
+    for world in worlds:
         parts = []
         for rank in range(world):
             lo, hi = shard_bounds(G, rank, world)
