@@ -128,7 +128,7 @@ class ClockSampler:
 def measured_traffic():
     """DRAM bytes per denoiser step from the committed ncu capture (profiles/): dram__bytes_read + dram__bytes_write
     summed over the launches of one step.  None when the summary is missing."""
-    for name in ("r2_step_dram_traffic.json", "r1_step_dram_traffic_v12.json"):
+    for name in ("r2f_step_dram_traffic.json", "r2_step_dram_traffic.json", "r1_step_dram_traffic_v12.json"):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 d = json.load(f)
