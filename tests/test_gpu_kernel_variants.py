@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("opts", ["specialize=0", "pair=2", "pair=0,interleave=0,w_resident=0", "pdl=0"])
+@pytest.mark.parametrize("opts", ["specialize=0", "pair=2", "pair=0,interleave=0,w_resident=0", "pdl=0",
+                                  "direct_store=1,max_stages_a=2"])   # register -> global stores, shallow A ring
 def test_gemm_cases_under_switch(opts):
     env = dict(os.environ, DHG_OPTS=opts)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_gemm.py"), "-x", "-q", "-m", "gpu",
@@ -20,10 +21,12 @@ def test_gemm_cases_under_switch(opts):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-def test_attention_cases_with_late_tile_loads():
+@pytest.mark.parametrize("opts", ["attn_early=0", "attn_max_slots=3"])
+def test_attention_cases_with_late_tile_loads(opts):
     """attention_tc.cu requests the next item's Q/K/V right after P V by default; the plan-time tuner may switch a
-    shape back to loading after O has been stored, so that order gets the same unit cases."""
-    env = dict(os.environ, DHG_OPTS="attn_early=0")
+    shape back to loading after O has been stored, so that order gets the same unit cases.  attn_max_slots=3: the
+    kernel instances compiled for fewer slots (more registers per thread) on the shapes that normally run with 4-6."""
+    env = dict(os.environ, DHG_OPTS=opts)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_attention.py"), "-x", "-q", "-m", "gpu",
                         "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, cwd=ROOT, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
@@ -59,7 +62,8 @@ def test_chain_is_bit_identical_with_and_without_text_overlap(tmp_path):
     for name, opts, graph in [("overlap", "", "graph"), ("serial", "text_sets=1", "graph"), ("overlap_streams", "text_sets=3", "nograph"),
                               ("one_direction", "serpentine=0,autotune=0", "graph"), ("no_tail_fusion", "tail_fusion=0", "graph"), ("tail_fusion_1", "tail_fusion=1", "graph"), ("tail_fusion_2", "tail_fusion=2", "graph"),
                               ("no_head_fusion", "head_fusion=0", "graph"), ("no_skip_fusion", "skip_fusion=0", "graph"),
-                              ("skip_fusion_enc_only", "skip_fusion=7", "graph"), ("skip_fusion_one_direction", "serpentine=0,autotune=0,skip_fusion=31", "graph")]:
+                              ("skip_fusion_enc_only", "skip_fusion=7", "graph"), ("skip_fusion_one_direction", "serpentine=0,autotune=0,skip_fusion=31", "graph"),
+                              ("direct_store_few_slots", "direct_store=1,attn_max_slots=2,max_stages_a=3", "graph")]:
         f = str(tmp_path / f"{name}.npy")
         r = subprocess.run([sys.executable, "-c", code, f, graph], env=dict(os.environ, DHG_OPTS=opts), capture_output=True, text=True,
                            cwd=ROOT, timeout=900)
@@ -70,6 +74,7 @@ def test_chain_is_bit_identical_with_and_without_text_overlap(tmp_path):
     assert np.array_equal(outs["overlap"], outs["overlap_streams"])
     assert np.array_equal(outs["overlap"], outs["one_direction"])   # tile order and tile configuration only move time
     assert np.array_equal(outs["overlap"], outs["skip_fusion_one_direction"])   # also for the dual-operand GEMMs
+    assert np.array_equal(outs["overlap"], outs["direct_store_few_slots"])      # store path, slot count, ring depth: time only
     # the fused tail (fc + FiLM + skip + heads on folded fp32 tables) skips one bf16 rounding of d1: close, not identical
     # (likewise the fused head: enc1.conv_skip from x in fp32 instead of from the bf16 input_dense rows)
     # (likewise skip fusion: conv_skip accumulated inside the block's last GEMM in fp32 instead of through a bf16 `skip` row,
