@@ -34,7 +34,7 @@ struct AttnTcShape {
   int N;          // keys padded to a multiple of 16 (UMMA N of the score MMA, K extent of the PV MMA)
   int nblk;       // 64-key blocks of P
   int nchunk;     // 32-column chunks of the score row
-  int tmem_cols;  // TMEM columns per slot: power of two >= max(64, nchunk * 32)
+  int tmem_cols;  // TMEM columns per slot: max(64, nchunk * 32)
   int NS;         // slots per CTA
   int halves;     // softmax warps per TMEM lane quarter (1 or 2): the score columns are split between them
   int QT;         // query tiles per (sample, head)
@@ -733,7 +733,7 @@ AttnTcPlan* attn_tc_plan_create(const AttnParams& p, int q_rows, int k_rows, cha
   sh.nchunk = (sh.N + 31) / 32;
   int cols = sh.nchunk * 32 < 64 ? 64 : sh.nchunk * 32;
   if (p.split && cols < 128) cols = 128;   // O' has 128 columns (hi and lo column of every output element)
-  sh.tmem_cols = cols <= 64 ? 64 : cols <= 128 ? 128 : 256;
+  sh.tmem_cols = cols <= 64 ? 64 : (cols + 31) & ~31;   // the CTA owns all 512 columns and cuts them itself: any multiple of a 32-column chunk (text/style: 96 -> 5 slots instead of 4)
   sh.QT = (p.Tq + 127) / 128;
   sh.items = p.B * p.H * sh.QT;
   sh.rev = 0;
