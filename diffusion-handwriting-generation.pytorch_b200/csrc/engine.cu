@@ -1790,6 +1790,7 @@ int32_t dhg_set_option(dhg_ctx* c, const char* key, int32_t value) {
   if (key && !strcmp(key, "specialize")) { tc_gemm_set_option(3, value); return 0; }
   if (key && !strcmp(key, "max_stages_a")) { tc_gemm_set_option(15, value); return 0; }
   if (key && !strcmp(key, "direct_store")) { tc_gemm_set_option(16, value); return 0; }
+  if (key && !strcmp(key, "split_n")) { tc_gemm_set_option(17, value); return 0; }
   if (!c || !key) return fail("dhg_set_option: null argument");
   if (!strcmp(key, "gemm")) c->opt_gemm = value ? 1 : 0;
   else if (!strcmp(key, "graph")) c->opt_graph = value ? 1 : 0;

@@ -625,6 +625,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
      mbar_wait(smem_u32(&tmem_full_bar[as]), use & 1u);
      tc_fence_after();
      DHG_TR(0x31, it);
+     if (sh.direct_store == 2) {   // measurement only ("direct_store" = 2): no epilogue at all, the accumulators go straight back
+       tc_fence_before();
+       __syncwarp();
+       if (lane == 0) { if (cta_rank) mbar_arrive_remote(smem_u32(&tmem_empty_bar[as]), 0); else mbar_arrive(smem_u32(&tmem_empty_bar[as])); }
+       tile_no += sh.G;
+       continue;
+     }
      for (int sub = 0; sub < sh.G; ++sub, ++tile_no) {
       const int m0 = (mts * tiles_per_super + sub + (int)cta_rank) * TC_BM;
       const bool last_sub = sub == sh.G - 1;
@@ -908,6 +915,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 // experiment switches (dhg_set_option: "w_resident", "specialize", "interleave")
 int g_opt_w_resident = 1, g_opt_specialize = 1, g_opt_interleave = 1, g_opt_pdl = 1, g_opt_pair = 1;
 int g_opt_direct_store = 0;   // experiment: register -> global 32-byte stores instead of smem staging + TMA store
+int g_opt_split_n = 0;        // experiment: two half-width MMAs per k-step (independent accumulators) for 128 <= BN <= 256
 int g_opt_max_stages_a = 0;   // > 0: cap the A ring of resident-W plans (experiment: how much prefetch depth does a launch need?)
 // forced tile configuration for plans created without an explicit TcTune (tests sweep these through dhg_set_option)
 static TcTune g_tune_default = {-1, -1, -1, -1};
@@ -925,6 +933,7 @@ void tc_gemm_set_option(int which, int value) {
   else if (which == 3) g_opt_specialize = value;
   else if (which == 15) g_opt_max_stages_a = value;
   else if (which == 16) g_opt_direct_store = value;
+  else if (which == 17) g_opt_split_n = value;
 }
 
 typedef void (*TcKernFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcShape, const Epilogue);
@@ -1046,7 +1055,9 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   const int m_tiles = (rows + TC_BM - 1) / TC_BM;
   sh.m_tiles = m_tiles;
   sh.kb_per_tap = (K + TC_BK - 1) / TC_BK;
-  sh.n_umma = BN > 256 ? 2 : 1;
+  // BN > 256: two MMAs per k-step by necessity.  "split_n": also for 128 <= BN <= 256 with one row tile per accumulator
+  // stage (G = 1), so that consecutive MMAs accumulate into different TMEM tiles (dependent accumulation is the slow case)
+  sh.n_umma = (BN > 256 || (g_opt_split_n && BN > 128 && (BN / 2) % 16 == 0 && !split && !sio)) ? 2 : 1;   // BN > 128: always G = 1
   sh.umma_n = BN / sh.n_umma;
   // cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6) | a_format BF16 (1) [7,10) | b_format BF16 (1) [10,13) |
   // a,b K-major (0) | N>>3 [17,23) | M>>4 [24,29)
@@ -1056,7 +1067,7 @@ TcGemmPlan* tc_gemm_plan_create(const bf16* A, int lda, int rows, const bf16* W,
   sh.trace = nullptr; sh.trace_cap = 0;
   sh.rev = g_tune_rev;
   // direct stores need 32-byte aligned rows: pitches in multiples of 16 elements, 32-byte aligned bases (not in split-I/O mode)
-  sh.direct_store = (g_opt_direct_store && !sio && !dot &&
+  sh.direct_store = g_opt_direct_store == 2 ? 2 : (g_opt_direct_store && !sio && !dot &&
                      (!e.out_raw || (e.out_raw_pitch % 16 == 0 && (reinterpret_cast<uintptr_t>(e.out_raw) & 31) == 0)) &&
                      (!e.out_act || (e.out_act_pitch % 16 == 0 && (reinterpret_cast<uintptr_t>(e.out_act) & 31) == 0))) ? 1 : 0;
   sh.a_evict_first = 0;

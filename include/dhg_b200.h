@@ -162,7 +162,7 @@ int64_t dhg_plan_bytes(const dhg_ctx* ctx);
  *                  variant won the timing for the batch a plan was built for; Tk > 256 always uses it)
  *   "w_resident", "specialize", "interleave", "pair", "pdl", "attn_early", "tune_bn", "tune_g", "tune_resident",
  *   "tune_pair", "tune_rev": kernel-selection overrides used by tests/test_gpu_kernel_variants.py and test_gpu_gemm.py
- *   "max_stages_a", "direct_store", "attn_max_slots", "attn_dbg": measurement switches of tools/ 
+ *   "max_stages_a", "direct_store" (2: no epilogue at all, timing only), "split_n", "attn_max_slots", "attn_dbg": measurement switches of tools/ 
  * None of them changes results beyond the documented tolerances; all but the three fusions and "attn_keyblock_auto"
  * leave the bits unchanged.
  * Debugging aid (environment): DHG_SYNC_OPS=1 synchronises after every launch of the un-graphed paths (dhg_denoise,
