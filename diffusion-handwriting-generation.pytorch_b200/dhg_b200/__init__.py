@@ -13,9 +13,11 @@ from .diffusion import NUM_STEPS, get_alpha_bar, get_beta_set
 from .inference import infer, resolve_experiment
 from .style import StyleExtractor, read_img, remove_whitespace
 from .tokenizer import Tokenizer, stroke_length
+from .train import FlatAdam, InvSqrtSchedule, exchange_gradients, loss_fn, perturb
 from .writer import DiffusionWriter
 
 __all__ = [
     "DiffusionWriter", "DiffusionModel", "load_model", "infer", "resolve_experiment", "Tokenizer",
     "stroke_length", "DLConfig", "save_checkpoint", "save_model_final", "StyleExtractor", "read_img", "remove_whitespace", "get_beta_set", "get_alpha_bar", "NUM_STEPS",
+    "FlatAdam", "InvSqrtSchedule", "exchange_gradients", "loss_fn", "perturb",
 ]

@@ -72,6 +72,13 @@ SIGNATURES = {
     "dhg_style_load_weight": (c_i32, [c_vp, c_cp, c_vp, ctypes.POINTER(c_i64), c_i32]),
     "dhg_style_finalize": (c_i32, [c_vp]),
     "dhg_style_extract": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "dhg_train_last_error": (c_cp, []),
+    "dhg_train_scratch_doubles": (c_i32, []),
+    "dhg_train_perturb": (c_i32, [c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
+    "dhg_train_loss": (c_i32, [c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "dhg_train_sqnorm": (c_i32, [c_i32, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "dhg_train_adam_step": (c_i32, [c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                    ctypes.c_double, ctypes.c_double, c_vp, ctypes.c_double, c_i32, c_vp]),
 }
 
 

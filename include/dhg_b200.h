@@ -261,6 +261,32 @@ int32_t dhg_style_load_weight(dhg_style* s, const char* name, const float* host_
 int32_t dhg_style_finalize(dhg_style* s);
 int32_t dhg_style_extract(dhg_style* s, const float* host_img, int32_t B, int32_t H, int32_t W, float* dev_out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Update half of the training step (SURVEY.md 8e "optional train step", 8f-3).  Replaces, on device buffers:
+ *   dhg_train_perturb    train.py:38-43   x_perturbed = sqrt(alpha) x + sqrt(1 - alpha) eps      (x, eps, out [B, T, 2]; alphas [B])
+ *   dhg_train_loss       loss.py:5-39     losses[3] = {total, score_loss, pen_lifts_loss} and, when the pointers are
+ *                                         non-NULL, d total / d score_pred [B, T, 2] and d total / d pen_lifts_pred [B, T]
+ *   dhg_train_sqnorm     utils/clip_grad.py:27-46 mode "norm" (torch clip_grad_norm_): sum of squares of the flat gradient
+ *   dhg_train_adam_step  scheduler.py:1-35 + torch.optim.Adam (config.yml:33-38): one update of the flat parameter buffer;
+ *                        the gradient that enters is grad * (1 / world_size) * min(1, max_norm / (||grad|| / world_size + 1e-6))
+ *                        with ||grad||^2 read from dev_sqnorm (NULL: no clipping), so a data-parallel caller all-reduces
+ *                        (sums) the flat gradient once and never rescales it; `lr` is the scheduled rate of this step
+ *                        (dhg_b200.train.InvSqrtSchedule), `step` counts from 1.
+ * dev_scratch: dhg_train_scratch_doubles() doubles.  Everything is stream-ordered, nothing synchronises; reductions are
+ * deterministic (fixed partial sums).  The backward pass of the denoiser is not part of this library: the flat
+ * gradient is an input.  Errors: dhg_train_last_error(). */
+const char* dhg_train_last_error(void);
+int32_t dhg_train_scratch_doubles(void);
+int32_t dhg_train_perturb(int32_t device, const float* dev_x, const float* dev_alphas, const float* dev_eps, float* dev_out, int32_t B,
+                          int32_t T, void* stream);
+int32_t dhg_train_loss(int32_t device, const float* dev_eps, const float* dev_score_pred, const float* dev_pen_lifts,
+                       const float* dev_pen_lifts_pred, const float* dev_alphas, int32_t B, int32_t T, float* dev_losses,
+                       float* dev_grad_score, float* dev_grad_pen_pred, double* dev_scratch, void* stream);
+int32_t dhg_train_sqnorm(int32_t device, const float* dev_grad, int64_t n, double* dev_out, double* dev_scratch, void* stream);
+int32_t dhg_train_adam_step(int32_t device, float* dev_param, const float* dev_grad, float* dev_exp_avg, float* dev_exp_avg_sq, int64_t n,
+                            int32_t step, double lr, double beta1, double beta2, double eps, double weight_decay,
+                            const double* dev_sqnorm, double max_norm, int32_t world_size, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,69 @@
+"""Host side of the update half of the training step (dhg_b200/train.py): the learning-rate schedule of
+scheduler.py:22-35, the flat parameter layout, and the one collective of a data-parallel step over gloo (world size 2)."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "diffusion-handwriting-generation.pytorch_b200"))
+
+
+def test_inv_sqrt_schedule_matches_scheduler_py():
+    from dhg_b200.train import InvSqrtSchedule
+
+    s = InvSqrtSchedule(1.0, 256, 10000)   # train.py:150-155 with config.yml: channels 128 -> d_model 256, warmup 10000
+    for n in (1, 2, 9999, 10000, 10001, 60000):
+        want = 1.0 * (256 ** -0.5) * min(n ** (-0.5), n * 10000 ** (-1.5))
+        assert s.lr(n) == want
+    assert s.lr(10000) == max(s.lr(n) for n in (1, 5000, 10000, 20000))   # the peak is at the end of the warm-up
+    assert abs(s.lr(10000) - 6.25e-4) < 1e-12
+    with pytest.raises(ValueError):
+        s.lr(0)
+
+
+def test_flatten_params_round_trip():
+    from dhg_b200.train import flatten_params
+
+    g = torch.Generator().manual_seed(0)
+    ts = [torch.randn(3, 4, 5, generator=g), torch.randn(7, generator=g), torch.randn(1, 1, generator=g)]
+    flat, table = flatten_params(ts, "cpu")
+    assert flat.numel() == 60 + 7 + 1 and [o for o, _ in table] == [0, 60, 67]
+    for (o, shp), t in zip(table, ts):
+        assert torch.equal(flat[o:o + t.numel()].view(shp), t)
+
+
+def _rank_main(rank, world, port, out):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dhg_b200.train import exchange_gradients
+
+    g = torch.full((1000,), float(rank + 1))
+    n = exchange_gradients(g)
+    out.put((rank, n, g[0].item(), g[-1].item()))
+    dist.destroy_process_group()
+
+
+def test_exchange_gradients_sums_over_two_ranks():
+    """one all-reduce (sum) per step; the division by N is left to the optimiser kernel (world_size argument)."""
+    import torch.multiprocessing as mp
+
+    from dhg_b200.train import exchange_gradients
+
+    assert exchange_gradients(torch.ones(4)) == 1   # no process group: nothing to exchange
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, 2, 3.0, 3.0), (1, 2, 3.0, 3.0)]
