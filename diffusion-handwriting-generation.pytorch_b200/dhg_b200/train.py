@@ -131,6 +131,8 @@ class FlatAdam:
         self.schedule = InvSqrtSchedule(lr_mul, d_model, n_warmup_steps)
         self.betas, self.eps, self.weight_decay, self.clip_grad = betas, eps, weight_decay, clip_grad
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:   # "cuda" = the current device of this process (one rank per GPU)
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.param, self.table = flatten_params([p.detach() for p in params], self.device)
         self.exp_avg = torch.zeros_like(self.param)
         self.exp_avg_sq = torch.zeros_like(self.param)
