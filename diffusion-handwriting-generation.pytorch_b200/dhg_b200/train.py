@@ -137,6 +137,7 @@ class FlatAdam:
         self.exp_avg = torch.zeros_like(self.param)
         self.exp_avg_sq = torch.zeros_like(self.param)
         self.n_steps = 0
+        self._world = 1
         self._sq = torch.zeros(1, dtype=torch.float64, device=self.device)
         self._scratch = _scratch(self.device)
 
