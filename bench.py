@@ -66,6 +66,32 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def train_update_leg(dev, peaks):
+    """SURVEY 8e / 8f-3, the part that exists: one gradient-norm + clipped Adam step over the reference's
+    10,028,451 parameters (dhg_b200.train.FlatAdam -> dhg_train_sqnorm + dhg_train_adam_step), device-timed."""
+    try:
+        from dhg_b200.train import FlatAdam
+
+        n = 10_028_451
+        opt = FlatAdam([torch.zeros(n, device=dev)], clip_grad=100.0, device=dev)
+        grad = torch.randn(n, device=dev)
+        for _ in range(3):
+            opt.step_and_update_lr(grad)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            opt.step_and_update_lr(grad)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / 20
+        gbs = n * 32 / us / 1e3
+        return {"parameters": n, "us_per_step": us, "bytes_per_step": n * 32, "achieved_gbs": gbs, "peak_gbs": peaks["hbm_gbs"],
+                "frac": gbs / peaks["hbm_gbs"], "what": "gradient 2-norm + clip + Adam (inv-sqrt schedule) on the flat fp32 buffer; "
+                "28 B (Adam) + 4 B (norm) per parameter; the backward pass that produces the gradient is not built"}
+    except Exception as e:   # noqa: BLE001
+        return {"failed": str(e)[:200]}
+
+
 def synthetic_inputs(lo, hi, T, L, pin=False, seed=SEED):
     """Synthetic prompts [lo, hi) of a GLOBAL batch: random ids in [2,72] with end token 1,
     random style vectors, injected x0 and per-step noise.  Sample g is drawn from its own generator seeded
@@ -521,6 +547,7 @@ def run_b200(args, rank, world, local_rank):
         # BASELINE configs[1] / configs[0] shapes: the reference's PyTorch path on this GPU beside `other_configs`
         line["gpu_eager_baseline_small"] = {f"B={b}": {k: v for k, v in gpu_eager_leg(dev, b).items() if k in ("fp32", "bf16_autocast")}
                                             for b in (64, 1)}
+        line["train_update"] = train_update_leg(dev, peaks)
     if args.cpu_baseline and world >= 1:
         lines_s, s_chain, cores, kind = cpu_reference_leg(args.cpu_batch, 1, 1)
         line["cpu_baseline"] = {
