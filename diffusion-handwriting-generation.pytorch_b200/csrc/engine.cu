@@ -55,6 +55,7 @@ static int g_opt_tail_fusion = 3; // chain: 1 last fc + FiLM + skip + heads as o
 static int g_opt_skip_fusion = 31; // chain: conv_skip folded into the last GEMM of a ConvBlock (bit i: enc1, enc2, enc4, dec3, dec2) ("skip_fusion")
 static int g_opt_attn_keyblock_auto = 0; // plan-time timing may pick the key-block attention kernel for 128 < Tk <= 256 ("attn_keyblock_auto")
 static int g_opt_serpentine = 1; // consumer kernels walk their rows opposite to their producer ("serpentine")
+static int g_opt_host_overlap = 1; // dhg_sample_host: noise of the later steps travels while the first steps run ("host_overlap")
 static int g_opt_text_sets = 2;  // text sides of this many consecutive steps run at once (dhg_set_option "text_sets")
 static int fail(const char* fmt, ...) {
   va_list ap;
@@ -200,6 +201,11 @@ struct Plan {
   int attn_impl = 1;
   cudaStream_t cap_stream = nullptr;
   cudaGraphExec_t graphs[4] = {nullptr, nullptr, nullptr, nullptr};  // [mode*2 + has_noise]
+  // dhg_sample_host: the chain as two graphs ([mode][part]; part 0 = the first head_steps steps) so that most of the noise can
+  // travel from the host while part 0 runs; copy_stream carries that copy, ev_copy_go / ev_copy_done fork and join it
+  cudaGraphExec_t host_graphs[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copy_go = nullptr, ev_copy_done = nullptr;
   int64_t launches_once = 0, launches_step = 0, launches_text = 0;
   struct HostStage { float *x = nullptr, *noise = nullptr, *style = nullptr, *out = nullptr; int64_t* text = nullptr; int cap = 0; };
   HostStage stage;   // device copies of dhg_sample_host's host buffers
@@ -417,6 +423,12 @@ void free_plan(Plan* p) {
   if (!p) return;
   for (int i = 0; i < 4; ++i)
     if (p->graphs[i]) cudaGraphExecDestroy(p->graphs[i]);
+  for (auto& m : p->host_graphs)
+    for (auto g : m)
+      if (g) cudaGraphExecDestroy(g);
+  if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
+  if (p->ev_copy_go) cudaEventDestroy(p->ev_copy_go);
+  if (p->ev_copy_done) cudaEventDestroy(p->ev_copy_done);
   for (auto t : p->tc_plans) tc_gemm_plan_destroy(t);
   for (auto t : p->attn_plans) attn_tc_plan_destroy(t);
   if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
@@ -1204,12 +1216,15 @@ void head_for_step(const dhg_ctx* c, Plan* P, int i, int mode, bool has_noise, b
   }
 }
 
-int run_chain(dhg_ctx* c, Plan* P, int mode, bool has_noise, cudaStream_t st) {
+// Steps i_first, i_first - 1, .., i_last of the chain (default: all 60).  A partial range must start on a text-set group
+// boundary ((59 - i_first) % text_sets == 0); the once-ops belong to the part that starts at step 59.
+int run_chain(dhg_ctx* c, Plan* P, int mode, bool has_noise, cudaStream_t st, int i_first = DHG_NUM_STEPS - 1, int i_last = 0) {
   StepCtx sc;
   memset(&sc, 0, sizeof(sc));
   sc.cond = c->cond60;
   sc.bstride = 0;
-  if (run_ops(P->once_ops, st, sc)) return 1;
+  if ((DHG_NUM_STEPS - 1 - i_first) % P->text_sets != 0) return fail("run_chain: step %d is not a text-set boundary", i_first);
+  if (i_first == DHG_NUM_STEPS - 1 && run_ops(P->once_ops, st, sc)) return 1;
   // The text side of a step does not depend on x.  Before step i with (59 - i) % n == 0 the text sides of steps
   // i, i-1, .., i-n+1 are launched together, set (j % n) for step j, set 0's on st and the others on their own streams
   // (forked from and joined back into st); the previous reader of a set, step j+n, has finished by then.
@@ -1221,7 +1236,7 @@ int run_chain(dhg_ctx* c, Plan* P, int mode, bool has_noise, cudaStream_t st) {
     t.bstride = 0;
     return t;
   };
-  for (int i = DHG_NUM_STEPS - 1; i >= 0; --i) {
+  for (int i = i_first; i >= i_last; --i) {
     if ((DHG_NUM_STEPS - 1 - i) % n == 0) {
       if (n > 1) CUDA_OK(cudaEventRecord(P->ev_fork, st));
       for (int j = i; j > i - n && j >= 0; --j) {
@@ -1265,6 +1280,32 @@ int launch_chain(dhg_ctx* c, Plan* P, int mode, bool has_noise, cudaStream_t st)
     if (ce != cudaSuccess) return fail("graph instantiate failed: %s", cudaGetErrorString(ce));
   }
   CUDA_OK(cudaGraphLaunch(P->graphs[gi], st));
+  return 0;
+}
+
+// First part of the chain for dhg_sample_host: a multiple of the text-set group size, about ten steps (33 ms at B = 1024:
+// ample for the 160 MB of noise the remaining steps need to arrive over PCIe)
+int host_head_steps(const Plan* P) {
+  const int n = P->text_sets;
+  return ((10 + n - 1) / n) * n;
+}
+int launch_chain_part(dhg_ctx* c, Plan* P, int mode, int part, cudaStream_t st) {
+  const int k = host_head_steps(P);
+  const int i_first = part == 0 ? DHG_NUM_STEPS - 1 : DHG_NUM_STEPS - 1 - k, i_last = part == 0 ? DHG_NUM_STEPS - k : 0;
+  if (!c->opt_graph) return run_chain(c, P, mode, true, st, i_first, i_last);
+  cudaGraphExec_t& ge = P->host_graphs[mode][part];
+  if (!ge) {
+    cudaGraph_t g = nullptr;
+    CUDA_OK(cudaStreamBeginCapture(P->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = run_chain(c, P, mode, true, P->cap_stream, i_first, i_last);
+    cudaError_t ce = cudaStreamEndCapture(P->cap_stream, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); return 1; }
+    if (ce != cudaSuccess) return fail("graph capture failed: %s", cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(&ge, g, 0);
+    cudaGraphDestroy(g);
+    if (ce != cudaSuccess) return fail("graph instantiate failed: %s", cudaGetErrorString(ce));
+  }
+  CUDA_OK(cudaGraphLaunch(ge, st));
   return 0;
 }
 
@@ -1691,6 +1732,44 @@ int32_t dhg_sample_host(dhg_ctx* c, int32_t batch, const float* x0, const float*
     if (text[i] < 0 || text[i] >= kVocab) return fail("text token id %lld at index %zu out of range [0, %d)", (long long)text[i], i, kVocab);
   CUDA_OK(cudaSetDevice(c->device));
   const size_t xs = (size_t)P->T * 2, ss = (size_t)P->S * kStyleWidth;
+  if (mode != DHG_MODE_NEW && mode != DHG_MODE_STANDARD) return fail("dhg_sample_host: bad diffusion mode %d", mode);
+  if (batch == P->B && g_opt_host_overlap) {
+    // One chunk that fills the plan: the host buffers go straight into the plan's own buffers (no staging copy), and
+    // only the noise of the first steps is waited for -- the chain starts with step 59, i.e. the END of the noise array;
+    // the rest (steps 59 - k .. 0, 5/6 of it) travels on a second stream while the first k steps run.  The chain is two
+    // graphs with the join between them; same kernels, same order, same bits as dhg_sample.
+    cudaStream_t st = P->cap_stream;
+    if (!P->copy_stream) {
+      CUDA_OK(cudaStreamCreateWithFlags(&P->copy_stream, cudaStreamNonBlocking));
+      CUDA_OK(cudaEventCreateWithFlags(&P->ev_copy_go, cudaEventDisableTiming));
+      CUDA_OK(cudaEventCreateWithFlags(&P->ev_copy_done, cudaEventDisableTiming));
+    }
+    if (!P->noise && dev_alloc(P->allocs, (void**)&P->noise, (size_t)DHG_NUM_STEPS * P->B * xs * sizeof(float), &P->bytes)) return 1;
+    if (plan_enter(P, st)) return 1;
+    const int k = host_head_steps(P);
+    const size_t step_elems = (size_t)P->B * xs, tail_steps = (size_t)(DHG_NUM_STEPS - k);
+    CUDA_OK(cudaEventRecord(P->ev_copy_go, st));   // the plan's noise buffer may still be read by an earlier call
+    CUDA_OK(cudaStreamWaitEvent(P->copy_stream, P->ev_copy_go, 0));
+    CUDA_OK(cudaMemcpyAsync(P->text, text, (size_t)batch * P->L * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(P->style, style, (size_t)batch * ss * sizeof(float), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(P->x_state, x0, (size_t)batch * xs * sizeof(float), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(P->noise + tail_steps * step_elems, noise + tail_steps * step_elems, (size_t)k * step_elems * sizeof(float),
+                            cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(P->noise, noise, tail_steps * step_elems * sizeof(float), cudaMemcpyHostToDevice, P->copy_stream));
+    CUDA_OK(cudaEventRecord(P->ev_copy_done, P->copy_stream));
+    if (launch_chain_part(c, P, mode, 0, st)) return 1;
+    CUDA_OK(cudaStreamWaitEvent(st, P->ev_copy_done, 0));
+    if (launch_chain_part(c, P, mode, 1, st)) return 1;
+    CUDA_OK(cudaMemcpyAsync(out, P->out, (size_t)batch * P->T * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    int64_t launches = P->launches_once + (int64_t)DHG_NUM_STEPS * (P->launches_text + P->launches_step) - (DHG_NUM_STEPS - 1);
+    if (P->opt_tail_fusion && P->prec == PREC_BF16 && P->gemm_impl == 1) launches -= DHG_NUM_STEPS;
+    for (int b = 0; b < 5; ++b)
+      if (P->opt_skip_fusion & (1 << b)) launches -= DHG_NUM_STEPS;
+    c->last_launches = launches;
+    if (plan_leave(P, st)) return 1;
+    CUDA_OK(cudaStreamSynchronize(st));
+    return plan_check_flags(P);
+  }
   // device staging for the host buffers: owned by the plan and kept between calls (no allocation, clearing or freeing
   // inside the call once it has been sized)
   Plan::HostStage& hs = P->stage;
@@ -1775,6 +1854,7 @@ int32_t dhg_set_option(dhg_ctx* c, const char* key, int32_t value) {
   if (key && !strcmp(key, "pdl")) { tc_gemm_set_option(6, value); attn_tc_set_debug(value ? -101 : -100); return 0; }
   if (key && !strcmp(key, "w_resident")) { tc_gemm_set_option(2, value); return 0; }
   if (key && !strcmp(key, "text_sets")) { g_opt_text_sets = value; return 0; }
+  if (key && !strcmp(key, "host_overlap")) { g_opt_host_overlap = value ? 1 : 0; return 0; }
   if (key && !strcmp(key, "autotune")) { g_opt_autotune = value ? 1 : 0; return 0; }
   if (key && !strcmp(key, "serpentine")) { g_opt_serpentine = value ? 1 : 0; return 0; }
   if (key && !strcmp(key, "attn_keyblock_auto")) { g_opt_attn_keyblock_auto = value ? 1 : 0; return 0; }

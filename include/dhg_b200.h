@@ -113,7 +113,13 @@ int32_t dhg_sample(dhg_ctx* ctx, int32_t batch, const float* dev_x0, const float
                    float* dev_out, void* stream);
 /* Same, with HOST buffers: the host->device copies of every input, the chain,
  * and the device->host copy of the result all happen inside the call, which
- * returns when `host_out` is complete. */
+ * returns when `host_out` is complete.  When `batch` equals the planned B the
+ * buffers are copied straight into the plan (no staging) and only the noise of
+ * the first ten or so steps is waited for: the loop starts at index 59, so the
+ * rest of the array travels on a second stream while those steps run (the chain
+ * is then two CUDA graphs with the join between them; same kernels, same bits;
+ * "host_overlap" = 0 restores the copy-everything-first path).  Pinned host
+ * memory is what makes the copies asynchronous; pageable memory still works. */
 int32_t dhg_sample_host(dhg_ctx* ctx, int32_t batch, const float* host_x0, const float* host_noise,
                         uint64_t seed, const int64_t* host_text, const float* host_style,
                         int32_t mode, float* host_out);
@@ -145,6 +151,7 @@ int64_t dhg_plan_bytes(const dhg_ctx* ctx);
  *   "attn"  0 CUDA-core attention, 1 tcgen05 attention (bf16 storage, and split storage in fp32 precision; default 1)
  *   "graph" 0/1 one CUDA graph per chain in dhg_sample (default 1)
  * Process-wide (ctx may be NULL; shared by every context of the process):
+ *   "host_overlap" 0/1 dhg_sample_host overlaps the noise copy with the first steps (default 1)
  *   "text_sets"    1..6 text sides of that many consecutive steps run at once on their own streams (default 2)
  *   "autotune"     0/1 time the GEMM tile configurations and the attention tile-load order at plan time (default 1)
  *   "serpentine"   0/1 alternate the row walking direction from kernel to kernel (default 1)
