@@ -126,3 +126,19 @@ def test_cli_end_to_end(tmp_path, state_dict, golden):
                        cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert (tmp_path / "prediction.png").exists() and "stroke points" in r.stdout
+
+
+@pytest.mark.parametrize("chunk", [5, 2])
+def test_host_entry_point_direct_and_staged_paths_give_the_device_bits(state_dict, chunk):
+    """dhg_sample_host: a batch that fills the plan goes straight into the plan's buffers with the noise of the later
+    steps copied while the first steps run (two graphs); any other batch is staged and chunked.  Both must return the
+    bits of the device-resident call, twice in a row (the second call re-uses graphs and buffers)."""
+    from dhg_b200 import DiffusionWriter
+
+    text, style, x0, noise = _inputs(5, 64, 10, seed=33)
+    w = DiffusionWriter(state_dict=state_dict, num_layers=2, channels=128, dtype="bf16", chunk=chunk)
+    ref = w.sample(text.cuda(), style.cuda(), x0=x0.cuda(), noise=noise.cuda()).cpu()
+    for _ in range(2):
+        got = w.sample_host(text, style, x0.pin_memory(), noise.pin_memory())
+        assert torch.equal(got, ref)
+    w.close()
