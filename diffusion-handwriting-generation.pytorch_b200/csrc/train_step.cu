@@ -1,0 +1,809 @@
+// Forward + backward pass of the denoiser for the reference's training step (BASELINE configs[3]):
+//
+//   train.py:46-55   strokes_pred, pen_lifts_pred, _ = model(x_perturbed, text, sqrt(alphas), style); loss.backward()
+//
+// i.e. DiffusionModel.forward in training form (model.py:121-182 with every activation kept) and the gradient of the
+// loss with respect to all 323 parameter tensors, written into ONE flat fp32 buffer in checkpoint key order -- the
+// buffer dhg_train_sqnorm / dhg_train_adam_step (train_update.cu) and the data-parallel all-reduce work on.  Together
+// with dhg_train_perturb / dhg_train_loss this is the whole of TrainingLoop.train_step on the device.
+//
+// Arithmetic is fp32 on the CUDA cores, like the reference's training (fp32 parameters, fp32 autograd): every
+// contraction -- Linear, the three taps of a k3 Conv1d, Q K^T, P V, and all their data / weight gradients -- is ONE
+// strided batched GEMM (`Bmm`: C[z] (+)= alpha A[z] B[z] (+ bias), arbitrary element strides, so transposes, head
+// splitting and the row shift of a conv tap are pointer arithmetic and never a copy); weight gradients are split per
+// sample over the batch axis and reduced with fp32 atomics.  Everything else (SiLU, FiLM, LayerNorm, softmax + padding
+// mask, pooling, upsampling, embedding, PE add) is a per-element or per-row kernel.  The plan is a tape built once for
+// (B, T, L): forward = the tape, backward = zero the gradient arena, then the tape in reverse.  Everything is
+// stream-ordered; nothing synchronises; the caller may capture forward + loss + backward + update in a CUDA graph.
+//
+// What this is NOT: it does not use the tensor cores (the sampling path's tcgen05 GEMMs are bf16 / split-bf16 forward
+// kernels with fused epilogues; their backward twins are not written).  DESIGN.md 4.10 has the measured step time
+// beside the reference's eager step on the same GPU.
+//
+// The same source also builds as plain C++ (-DDHG_HOSTSIM, g++ -fopenmp): every kernel body is a functor over a flat
+// index, so the host build runs the identical bodies in a loop.  That build exists ONLY for tests/ (gradient check
+// against torch autograd without a GPU, tests/test_train_step_hostsim.py); it is never part of libdhg_b200.so and the
+// product has no CPU path.
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#ifndef DHG_HOSTSIM
+#include <cuda_runtime.h>
+#define TS_FN __device__ __forceinline__
+typedef cudaStream_t ts_stream;
+#else
+#define TS_FN inline
+typedef void* ts_stream;
+#endif
+
+#include "../../include/dhg_b200.h"
+
+namespace {
+
+thread_local char g_serr[512] = "";
+int sfail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_serr, sizeof(g_serr), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+int g_use_tiled = 1;   // GPU build: shared-memory tiled GEMM (0: the per-thread body the host build runs; dhg_trainer_set_option)
+
+// ------------------------------------------------------------------------------------------------------------------
+// launch layer
+// ------------------------------------------------------------------------------------------------------------------
+#ifndef DHG_HOSTSIM
+template <class F>
+__global__ void __launch_bounds__(256) ts_kernel(long n, F f) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) f(i);
+}
+TS_FN void ts_atomic_add(float* p, float v) { atomicAdd(p, v); }
+#else
+TS_FN void ts_atomic_add(float* p, float v) {
+#pragma omp atomic
+  *p += v;
+}
+#endif
+
+struct Launcher {
+  ts_stream st = nullptr;
+  long launches = 0;
+  int grid_cap = 148 * 16;
+  template <class F>
+  void run(long n, const F& f) {
+    if (n <= 0) return;
+#ifndef DHG_HOSTSIM
+    long blocks = (n + 255) / 256;
+    if (blocks > grid_cap) blocks = grid_cap;
+    ts_kernel<F><<<(unsigned)blocks, 256, 0, st>>>(n, f);
+#else
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < n; ++i) f(i);
+#endif
+    ++launches;
+  }
+  void zero(void* p, size_t bytes) {
+    if (!bytes) return;
+#ifndef DHG_HOSTSIM
+    cudaMemsetAsync(p, 0, bytes, st);
+#else
+    memset(p, 0, bytes);
+#endif
+  }
+  void copy(void* dst, const void* src, size_t bytes) {
+    if (!bytes) return;
+#ifndef DHG_HOSTSIM
+    cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st);
+#else
+    memcpy(dst, src, bytes);
+#endif
+  }
+};
+
+void* dev_alloc(size_t bytes) {
+  if (!bytes) bytes = 256;
+#ifndef DHG_HOSTSIM
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+  return p;
+#else
+  return aligned_alloc(256, (bytes + 255) / 256 * 256);
+#endif
+}
+void dev_free(void* p) {
+  if (!p) return;
+#ifndef DHG_HOSTSIM
+  cudaFree(p);
+#else
+  free(p);
+#endif
+}
+void to_dev(void* dst, const void* src, size_t bytes) {
+#ifndef DHG_HOSTSIM
+  cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+#else
+  memcpy(dst, src, bytes);
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// the one contraction: C[z](i, j) (+)= alpha * sum_k A[z](i, k) B[z](k, j) (+ bias[j]),  z = z1 * Z2 + z2
+// ------------------------------------------------------------------------------------------------------------------
+struct Bmm {
+  const float* A = nullptr;
+  const float* B = nullptr;
+  float* C = nullptr;
+  const float* bias = nullptr;   // only with a plain store
+  int M = 0, N = 0, K = 0, Z1 = 1, Z2 = 1;
+  long sAz1 = 0, sAz2 = 0, sAi = 0, sAk = 0;
+  long sBz1 = 0, sBz2 = 0, sBk = 0, sBj = 0;
+  long sCz1 = 0, sCz2 = 0, sCi = 0, sCj = 0;
+  float alpha = 1.f;
+  int mode = 0;   // 0: C = v   1: C += v (one writer per element)   2: atomicAdd(C, v) (batch items share C)
+};
+
+TS_FN void bmm_store(const Bmm& p, float* C, int i, int j, float acc) {
+  float v = p.alpha * acc;
+  float* c = C + (long)i * p.sCi + (long)j * p.sCj;
+  if (p.mode == 0) *c = p.bias ? v + p.bias[j] : v;
+  else if (p.mode == 1) *c += v;
+  else ts_atomic_add(c, v);
+}
+
+// one thread = one 4 x 4 block of C, operands straight from memory (the body the host build runs; on the GPU the
+// reference the tiled kernel is checked against)
+struct BmmBody {
+  Bmm p;
+  int tm, tn;
+  TS_FN void operator()(long gid) const {
+    const int tj = (int)(gid % tn);
+    long r = gid / tn;
+    const int ti = (int)(r % tm);
+    const int z = (int)(r / tm);
+    const int z1 = z / p.Z2, z2 = z % p.Z2;
+    const float* A = p.A + z1 * p.sAz1 + z2 * p.sAz2;
+    const float* B = p.B + z1 * p.sBz1 + z2 * p.sBz2;
+    float* C = p.C + z1 * p.sCz1 + z2 * p.sCz2;
+    const int i0 = ti * 4, j0 = tj * 4;
+    float acc[4][4];
+    for (int a = 0; a < 4; ++a)
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    for (int k = 0; k < p.K; ++k) {
+      float av[4], bv[4];
+      for (int a = 0; a < 4; ++a) av[a] = (i0 + a < p.M) ? A[(long)(i0 + a) * p.sAi + (long)k * p.sAk] : 0.f;
+      for (int b = 0; b < 4; ++b) bv[b] = (j0 + b < p.N) ? B[(long)k * p.sBk + (long)(j0 + b) * p.sBj] : 0.f;
+      for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+    }
+    for (int a = 0; a < 4; ++a)
+      for (int b = 0; b < 4; ++b)
+        if (i0 + a < p.M && j0 + b < p.N) bmm_store(p, C, i0 + a, j0 + b, acc[a][b]);
+  }
+};
+
+#ifndef DHG_HOSTSIM
+// 64 x 64 tile of C per CTA, 16-deep k slabs through shared memory, 4 x 4 per thread.  The slab loads walk whichever
+// of the two operand axes is contiguous, so any of the stride patterns above reads coalesced 64-byte runs or better.
+constexpr int kBM = 64, kBN = 64, kBK = 16;
+__global__ void __launch_bounds__(256) ts_bmm_tiled(Bmm p) {
+  __shared__ __align__(16) float As[kBK][kBM + 4];
+  __shared__ __align__(16) float Bs[kBK][kBN + 4];
+  const int z = blockIdx.z, z1 = z / p.Z2, z2 = z % p.Z2;
+  const float* __restrict__ A = p.A + z1 * p.sAz1 + z2 * p.sAz2;
+  const float* __restrict__ B = p.B + z1 * p.sBz1 + z2 * p.sBz2;
+  float* C = p.C + z1 * p.sCz1 + z2 * p.sCz2;
+  const int bi = blockIdx.y * kBM, bj = blockIdx.x * kBN;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const bool a_k_fast = p.sAk == 1, b_k_fast = p.sBk == 1 && p.sBj != 1;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  for (int k0 = 0; k0 < p.K; k0 += kBK) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int e = tid + 256 * r;
+      int kk, ii;
+      if (a_k_fast) { kk = e & 15; ii = e >> 4; } else { ii = e & 63; kk = e >> 6; }
+      const int gi = bi + ii, gk = k0 + kk;
+      As[kk][ii] = (gi < p.M && gk < p.K) ? A[(long)gi * p.sAi + (long)gk * p.sAk] : 0.f;
+      int kb, jj;
+      if (b_k_fast) { kb = e & 15; jj = e >> 4; } else { jj = e & 63; kb = e >> 6; }
+      const int gj = bj + jj, gkb = k0 + kb;
+      Bs[kb][jj] = (gj < p.N && gkb < p.K) ? B[(long)gkb * p.sBk + (long)gj * p.sBj] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kBK; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = bi + ty * 4 + a, j = bj + tx * 4 + b;
+      if (i < p.M && j < p.N) bmm_store(p, C, i, j, acc[a][b]);
+    }
+}
+#endif
+
+void run_bmm(Launcher& L, const Bmm& p) {
+  if (p.M <= 0 || p.N <= 0 || p.Z1 <= 0 || p.Z2 <= 0) return;
+  if (p.K <= 0 && p.mode != 0) return;
+#ifndef DHG_HOSTSIM
+  if (g_use_tiled && (long)p.Z1 * p.Z2 <= 65535 && (p.M + kBM - 1) / kBM <= 65535) {
+    dim3 grid((p.N + kBN - 1) / kBN, (p.M + kBM - 1) / kBM, p.Z1 * p.Z2);
+    ts_bmm_tiled<<<grid, 256, 0, L.st>>>(p);
+    ++L.launches;
+    return;
+  }
+#endif
+  BmmBody f;
+  f.p = p;
+  f.tm = (p.M + 3) / 4;
+  f.tn = (p.N + 3) / 4;
+  L.run((long)f.tm * f.tn * p.Z1 * p.Z2, f);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// per-element / per-row kernels (forward and backward of each)
+// ------------------------------------------------------------------------------------------------------------------
+TS_FN float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+struct SiluFwd { const float* x; float* y; TS_FN void operator()(long i) const { const float v = x[i]; y[i] = v * sigmoidf_(v); } };
+struct SiluBwd {
+  const float* x; const float* gy; float* gx;
+  TS_FN void operator()(long i) const { const float v = x[i], s = sigmoidf_(v); gx[i] += gy[i] * (s * (1.f + v * (1.f - s))); }
+};
+struct SigmoidFwd { const float* x; float* y; TS_FN void operator()(long i) const { y[i] = sigmoidf_(x[i]); } };
+struct SigmoidBwd { const float* y; const float* gy; float* gx; TS_FN void operator()(long i) const { const float s = y[i]; gx[i] += gy[i] * s * (1.f - s); } };
+struct MulFwd { const float* x; const float* m; float* y; TS_FN void operator()(long i) const { y[i] = m ? x[i] * m[i] : x[i]; } };
+struct AddFwd { const float* a; const float* b; float* y; TS_FN void operator()(long i) const { y[i] = a[i] + b[i]; } };
+struct AddBwd { const float* gy; float* ga; float* gb; TS_FN void operator()(long i) const { const float g = gy[i]; if (ga) ga[i] += g; if (gb) gb[i] += g; } };
+// y[r, c] = x[r, c] + pe[(r % period), c]   (attention.py:15-23 tables, constant)
+struct AddPeFwd { const float* x; const float* pe; float* y; int C, period; TS_FN void operator()(long i) const { const long r = i / C; y[i] = x[i] + pe[(r % period) * C + (i % C)]; } };
+struct AccBwd { const float* gy; float* gx; TS_FN void operator()(long i) const { gx[i] += gy[i]; } };
+// FiLM (conditioning.py:16-19): y[r, c] = x[r, c] * gamma[b, c] + beta[b, c], b = r / period
+struct FilmFwd {
+  const float* x; const float* gam; const float* bet; float* y; int C, period;
+  TS_FN void operator()(long i) const { const long b = i / ((long)C * period); const int c = (int)(i % C); y[i] = x[i] * gam[b * C + c] + bet[b * C + c]; }
+};
+struct FilmBwdX {
+  const float* gy; const float* gam; float* gx; int C, period;
+  TS_FN void operator()(long i) const { const long b = i / ((long)C * period); gx[i] += gy[i] * gam[b * C + (i % C)]; }
+};
+struct FilmBwdCond {   // one thread per (b, c): sums over the sample's rows
+  const float* gy; const float* x; float* ggam; float* gbet; int C, period;
+  TS_FN void operator()(long i) const {
+    const long b = i / C; const int c = (int)(i % C);
+    const float* g = gy + b * period * (long)C + c; const float* xv = x + b * period * (long)C + c;
+    float sg = 0.f, sb = 0.f;
+    for (int t = 0; t < period; ++t) { const float d = g[(long)t * C]; sg = fmaf(d, xv[(long)t * C], sg); sb += d; }
+    ggam[i] += sg; gbet[i] += sb;
+  }
+};
+// LayerNorm(eps 1e-6, no affine) (model.py:25, text_style.py:80); one thread per row
+struct LnFwd {
+  const float* x; float* y; float* rstd; int C;
+  TS_FN void operator()(long r) const {
+    const float* xr = x + r * C; float* yr = y + r * C;
+    float m = 0.f; for (int c = 0; c < C; ++c) m += xr[c]; m /= C;
+    float v = 0.f; for (int c = 0; c < C; ++c) { const float d = xr[c] - m; v = fmaf(d, d, v); } v /= C;
+    const float rs = 1.f / sqrtf(v + 1e-6f); rstd[r] = rs;
+    for (int c = 0; c < C; ++c) yr[c] = (xr[c] - m) * rs;
+  }
+};
+struct LnBwd {
+  const float* y; const float* gy; const float* rstd; float* gx; int C;
+  TS_FN void operator()(long r) const {
+    const float* yr = y + r * C; const float* gr = gy + r * C; float* gxr = gx + r * C;
+    float m1 = 0.f, m2 = 0.f; for (int c = 0; c < C; ++c) { m1 += gr[c]; m2 = fmaf(gr[c], yr[c], m2); } m1 /= C; m2 /= C;
+    const float rs = rstd[r];
+    for (int c = 0; c < C; ++c) gxr[c] += rs * (gr[c] - m1 - yr[c] * m2);
+  }
+};
+// softmax over the keys of one (b, h, query) row, with the additive -1e9 padding mask (attention.py:43, utils/nn.py:178-191)
+struct SoftmaxFwd {
+  const float* s; float* p; const int64_t* ids; int Tk; long rows_per_b;
+  TS_FN void operator()(long r) const {
+    const float* sr = s + r * Tk; float* pr = p + r * Tk;
+    const int64_t* id = ids ? ids + (r / rows_per_b) * Tk : nullptr;
+    float mx = -INFINITY;
+    for (int j = 0; j < Tk; ++j) { const float v = sr[j] + ((id && id[j] == 0) ? -1e9f : 0.f); pr[j] = v; mx = fmaxf(mx, v); }
+    float sum = 0.f; for (int j = 0; j < Tk; ++j) { const float e = expf(pr[j] - mx); pr[j] = e; sum += e; }
+    const float inv = 1.f / sum; for (int j = 0; j < Tk; ++j) pr[j] *= inv;
+  }
+};
+struct SoftmaxBwd {
+  const float* p; const float* gp; float* gs; int Tk;
+  TS_FN void operator()(long r) const {
+    const float* pr = p + r * Tk; const float* gr = gp + r * Tk; float* go = gs + r * Tk;
+    float d = 0.f; for (int j = 0; j < Tk; ++j) d = fmaf(pr[j], gr[j], d);
+    for (int j = 0; j < Tk; ++j) go[j] += pr[j] * (gr[j] - d);
+  }
+};
+// AvgPool1d(2) / nearest x2 over the rows of each sample (model.py:93-99, 163)
+struct PoolFwd { const float* x; float* y; int C; TS_FN void operator()(long i) const { const long r = i / C; const int c = (int)(i % C); y[i] = 0.5f * (x[(2 * r) * C + c] + x[(2 * r + 1) * C + c]); } };
+struct PoolBwd { const float* gy; float* gx; int C; TS_FN void operator()(long i) const { const long r = i / C; const int c = (int)(i % C); gx[i] += 0.5f * gy[(r >> 1) * C + c]; } };
+struct UpFwd { const float* x; float* y; int C; TS_FN void operator()(long i) const { const long r = i / C; const int c = (int)(i % C); y[i] = x[(r >> 1) * C + c]; } };
+struct UpBwd { const float* gy; float* gx; int C; TS_FN void operator()(long i) const { const long r = i / C; const int c = (int)(i % C); gx[i] += gy[(2 * r) * C + c] + gy[(2 * r + 1) * C + c]; } };
+struct EmbedFwd { const int64_t* ids; const float* E; float* y; int C; TS_FN void operator()(long i) const { y[i] = E[ids[i / C] * C + (i % C)]; } };
+struct EmbedBwd { const int64_t* ids; const float* gy; float* gE; int C; TS_FN void operator()(long i) const { ts_atomic_add(gE + ids[i / C] * C + (i % C), gy[i]); } };
+// column sums of a [rows, N] matrix in chunks of 64 rows (bias gradients)
+struct ColSum {
+  const float* g; float* out; int rows, N;
+  TS_FN void operator()(long i) const {
+    const int j = (int)(i % N); const long ch = i / N; const long r0 = ch * 64; const long r1 = r0 + 64 < rows ? r0 + 64 : rows;
+    float s = 0.f; for (long r = r0; r < r1; ++r) s += g[r * N + j];
+    ts_atomic_add(out + j, s);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// parameter layout: checkpoint key order (checkpoint.py:256-297, train.py:131)
+// ------------------------------------------------------------------------------------------------------------------
+struct PSpec { std::string name; long off, numel; };
+struct Layout {
+  std::vector<PSpec> items;
+  std::map<std::string, int> index;
+  long total = 0;
+  void add(const std::string& n, long numel) { index[n] = (int)items.size(); items.push_back({n, total, numel}); total += numel; }
+  void lin(const std::string& p, int in, int out) { add(p + ".weight", (long)in * out); add(p + ".bias", out); }
+  void conv(const std::string& p, int in, int out) { add(p + ".weight", (long)in * out * 3); add(p + ".bias", out); }
+  void affine(const std::string& p, int h) { lin(p + ".gamma_emb", 32, h); lin(p + ".beta_emb", 32, h); }
+  void mha(const std::string& p, int d) { for (const char* n : {"wq", "wk", "wv", "dense"}) lin(p + "." + n, d, d); }
+  void conv_block(const std::string& p, int in, int out) {
+    affine(p + ".affine1", out / 2); affine(p + ".affine2", out); affine(p + ".affine3", out);
+    conv(p + ".conv_skip", in, out); conv(p + ".conv1", in, out / 2); conv(p + ".conv2", out / 2, out); lin(p + ".fc", out, out);
+  }
+  void enc_layer(const std::string& p, int in, int out) {
+    lin(p + ".text_dense", in, out); lin(p + ".ffn.1", out, 2 * out); lin(p + ".ffn.3", 2 * out, out);
+    mha(p + ".mha", out); mha(p + ".mha2", out);
+    for (int i = 0; i < 4; ++i) affine(p + ".affine" + std::to_string(i), out);
+  }
+  void build(int num_layers, int ch) {
+    const int c1 = ch, c2 = ch * 3 / 2, c3 = ch * 2, d = 2 * c2;
+    lin("input_dense", 2, c1); lin("sigma_ffn.1", 1, 2048); lin("sigma_ffn.3", 2048, c1 / 4);
+    conv_block("enc1", c1, c1); conv_block("enc2", c1, c2); enc_layer("enc3", d, c2);
+    conv_block("enc4", c2, c3); enc_layer("enc5", d, c3);
+    conv("skip_conv1", c1, c2); conv("skip_conv2", c2, c3); conv("skip_conv3", c3, d);
+    add("text_style_model.emb.weight", 73L * d);
+    lin("text_style_model.style_ffn.1", 256, 4 * c2); lin("text_style_model.style_ffn.3", 4 * c2, d);
+    lin("text_style_model.text_ffn.1", d, 2 * d); lin("text_style_model.text_ffn.3", 2 * d, d);
+    mha("text_style_model.mha", d);
+    for (int i = 1; i <= 4; ++i) affine("text_style_model.affine" + std::to_string(i), d);
+    lin("att_dense", 2 * c1, d);
+    for (int i = 0; i < num_layers; ++i) enc_layer("att_layers." + std::to_string(i), d, d);
+    conv_block("dec3", d, c3); conv_block("dec2", c3, c2); conv_block("dec1", c2, c1);
+    lin("output_dense", c1, 2); lin("pen_lifts_dense.0", c1, 1);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// tape
+// ------------------------------------------------------------------------------------------------------------------
+struct Ten {
+  float* v = nullptr;
+  float* g = nullptr;   // null: no gradient wanted (inputs)
+  int rows = 0, C = 0, period = 1;   // rows = samples * period
+  long n() const { return (long)rows * C; }
+};
+struct OpRec { std::function<void(Launcher&)> fwd, bwd; };
+
+}  // namespace
+
+struct dhg_trainer {
+  int device = 0, num_layers = 2, ch = 128, B = 0, T = 0, L = 0;
+  int c1, c2, c3, d;
+  Layout lay;
+  float* params = nullptr;
+  float* grads = nullptr;
+  // arenas: values, gradients (zeroed at the start of every backward), constants
+  bool dry = true;
+  size_t v_need = 0, g_need = 0, v_used = 0, g_used = 0;
+  float* v_arena = nullptr;
+  float* g_arena = nullptr;
+  std::vector<void*> consts;
+  std::vector<OpRec> tape;
+  std::string err;
+  // plan-owned copies of the inputs, and the outputs
+  Ten in_x, in_sigma, in_style, style_keep, out_score, out_pen;
+  int64_t* text = nullptr;
+  bool have_keep = false;
+  long last_launches = 0;
+
+  float* P(const std::string& n) { auto it = lay.index.find(n); if (it == lay.index.end()) { err = "unknown parameter " + n; return params; } return params + lay.items[it->second].off; }
+  float* G(const std::string& n) { auto it = lay.index.find(n); if (it == lay.index.end()) { err = "unknown parameter " + n; return grads; } return grads + lay.items[it->second].off; }
+
+  Ten make(int rows, int C, int period, bool grad = true) {
+    Ten t; t.rows = rows; t.C = C; t.period = period;
+    const size_t n = ((size_t)rows * C + 63) / 64 * 64;
+    if (dry) { v_need += n; if (grad) g_need += n; return t; }
+    t.v = v_arena + v_used; v_used += n;
+    if (grad) { t.g = g_arena + g_used; g_used += n; }
+    return t;
+  }
+  void rec(std::function<void(Launcher&)> f, std::function<void(Launcher&)> b) { if (!dry) tape.push_back({std::move(f), std::move(b)}); }
+
+  // ---- ops ----
+  Ten unary_silu(const Ten& x) {
+    Ten y = make(x.rows, x.C, x.period);
+    rec([=](Launcher& L) { L.run(x.n(), SiluFwd{x.v, y.v}); }, [=](Launcher& L) { if (x.g) L.run(x.n(), SiluBwd{x.v, y.g, x.g}); });
+    return y;
+  }
+  Ten sigmoid(const Ten& x) {
+    Ten y = make(x.rows, x.C, x.period);
+    rec([=](Launcher& L) { L.run(x.n(), SigmoidFwd{x.v, y.v}); }, [=](Launcher& L) { if (x.g) L.run(x.n(), SigmoidBwd{y.v, y.g, x.g}); });
+    return y;
+  }
+  Ten add(const Ten& a, const Ten& b) {
+    Ten y = make(a.rows, a.C, a.period);
+    rec([=](Launcher& L) { L.run(a.n(), AddFwd{a.v, b.v, y.v}); }, [=](Launcher& L) { L.run(a.n(), AddBwd{y.g, a.g, b.g}); });
+    return y;
+  }
+  Ten add_pe(const Ten& x, const float* pe) {
+    Ten y = make(x.rows, x.C, x.period);
+    rec([=](Launcher& L) { L.run(x.n(), AddPeFwd{x.v, pe, y.v, x.C, x.period}); }, [=](Launcher& L) { if (x.g) L.run(x.n(), AccBwd{y.g, x.g}); });
+    return y;
+  }
+  Ten pool(const Ten& x) {
+    Ten y = make(x.rows / 2, x.C, x.period / 2);
+    rec([=](Launcher& L) { L.run(y.n(), PoolFwd{x.v, y.v, x.C}); }, [=](Launcher& L) { if (x.g) L.run(x.n(), PoolBwd{y.g, x.g, x.C}); });
+    return y;
+  }
+  Ten up(const Ten& x) {
+    Ten y = make(x.rows * 2, x.C, x.period * 2);
+    rec([=](Launcher& L) { L.run(y.n(), UpFwd{x.v, y.v, x.C}); }, [=](Launcher& L) { if (x.g) L.run(x.n(), UpBwd{y.g, x.g, x.C}); });
+    return y;
+  }
+  Ten ln(const Ten& x) {
+    Ten y = make(x.rows, x.C, x.period);
+    Ten rs = make(x.rows, 1, x.period, false);
+    rec([=](Launcher& L) { L.run(x.rows, LnFwd{x.v, y.v, rs.v, x.C}); }, [=](Launcher& L) { if (x.g) L.run(x.rows, LnBwd{y.v, y.g, rs.v, x.g, x.C}); });
+    return y;
+  }
+  // weight-gradient batching: one batch item per sample when the matrix is large, else one item
+  static void wgrad_split(const Ten& x, int& Z, int& rpz) {
+    if (x.rows > 256 && x.period > 1 && x.rows % x.period == 0) { Z = x.rows / x.period; rpz = x.period; } else { Z = 1; rpz = x.rows; }
+  }
+  // nn.Linear: W [N, K], b [N]
+  Ten linear(const Ten& x, const std::string& name, int N) {
+    const int K = x.C;
+    Ten y = make(x.rows, N, x.period);
+    const float* W = P(name + ".weight"); const float* b = P(name + ".bias");
+    float* gW = G(name + ".weight"); float* gb = G(name + ".bias");
+    const long have = lay.index.count(name + ".weight") ? lay.items[lay.index[name + ".weight"]].numel : -1;
+    if (have != (long)N * K) err = "shape mismatch at " + name;
+    rec([=](Launcher& L) {
+          Bmm p; p.A = x.v; p.B = W; p.C = y.v; p.bias = b; p.M = x.rows; p.N = N; p.K = K;
+          p.sAi = K; p.sAk = 1; p.sBk = 1; p.sBj = K; p.sCi = N; p.sCj = 1;
+          run_bmm(L, p);
+        },
+        [=](Launcher& L) {
+          if (x.g) {   // dx += dy W
+            Bmm p; p.A = y.g; p.B = W; p.C = x.g; p.M = x.rows; p.N = K; p.K = N; p.mode = 1;
+            p.sAi = N; p.sAk = 1; p.sBk = K; p.sBj = 1; p.sCi = K; p.sCj = 1;
+            run_bmm(L, p);
+          }
+          int Z, rpz; wgrad_split(x, Z, rpz);
+          Bmm q; q.A = x.v; q.B = y.g; q.C = gW; q.M = K; q.N = N; q.K = rpz; q.Z1 = Z; q.mode = 2;   // dW[n, k] += sum_r x[r, k] dy[r, n]
+          q.sAz1 = (long)rpz * K; q.sAi = 1; q.sAk = K; q.sBz1 = (long)rpz * N; q.sBk = N; q.sBj = 1; q.sCz1 = 0; q.sCi = 1; q.sCj = K;
+          run_bmm(L, q);
+          L.run((long)N * ((x.rows + 63) / 64), ColSum{y.g, gb, x.rows, N});
+        });
+    return y;
+  }
+  // nn.Conv1d(k = 3, padding 1) in channels-last form (cnn.py:32-47): W [N, K, 3]; tap j reads row t + j - 1 of the same sample
+  Ten conv3(const Ten& x, const std::string& name, int N) {
+    const int K = x.C, Tn = x.period, nb = x.rows / x.period;
+    Ten y = make(x.rows, N, x.period);
+    const float* W = P(name + ".weight"); const float* b = P(name + ".bias");
+    float* gW = G(name + ".weight"); float* gb = G(name + ".bias");
+    const long have = lay.index.count(name + ".weight") ? lay.items[lay.index[name + ".weight"]].numel : -1;
+    if (have != (long)N * K * 3) err = "shape mismatch at " + name;
+    auto range = [=](int tap, int& lo, int& hi) { lo = tap == 0 ? 1 : 0; hi = tap == 2 ? Tn - 1 : Tn; };
+    rec([=](Launcher& L) {
+          const int order[3] = {1, 0, 2};
+          for (int o = 0; o < 3; ++o) {
+            const int tap = order[o]; int lo, hi; range(tap, lo, hi);
+            Bmm p; p.A = x.v + (long)(lo + tap - 1) * K; p.B = W + tap; p.C = y.v + (long)lo * N; p.bias = o == 0 ? b : nullptr;
+            p.M = hi - lo; p.N = N; p.K = K; p.Z1 = nb; p.mode = o == 0 ? 0 : 1;
+            p.sAz1 = (long)Tn * K; p.sAi = K; p.sAk = 1; p.sBk = 3; p.sBj = 3L * K; p.sCz1 = (long)Tn * N; p.sCi = N; p.sCj = 1;
+            run_bmm(L, p);
+          }
+        },
+        [=](Launcher& L) {
+          for (int tap = 0; tap < 3; ++tap) {
+            int lo, hi; range(tap, lo, hi);
+            if (x.g) {   // dx[t + tap - 1, k] += sum_n dy[t, n] W[n, k, tap]
+              Bmm p; p.A = y.g + (long)lo * N; p.B = W + tap; p.C = x.g + (long)(lo + tap - 1) * K; p.M = hi - lo; p.N = K; p.K = N; p.Z1 = nb; p.mode = 1;
+              p.sAz1 = (long)Tn * N; p.sAi = N; p.sAk = 1; p.sBk = 3L * K; p.sBj = 3; p.sCz1 = (long)Tn * K; p.sCi = K; p.sCj = 1;
+              run_bmm(L, p);
+            }
+            Bmm q; q.A = x.v + (long)(lo + tap - 1) * K; q.B = y.g + (long)lo * N; q.C = gW + tap; q.M = K; q.N = N; q.K = hi - lo; q.Z1 = nb; q.mode = 2;
+            q.sAz1 = (long)Tn * K; q.sAi = 1; q.sAk = K; q.sBz1 = (long)Tn * N; q.sBk = N; q.sBj = 1; q.sCz1 = 0; q.sCi = 3; q.sCj = 3L * K;
+            run_bmm(L, q);
+          }
+          L.run((long)N * ((x.rows + 63) / 64), ColSum{y.g, gb, x.rows, N});
+        });
+    return y;
+  }
+  // AffineTransformLayer (conditioning.py:5-19): gamma / beta = Linear(32, C)(sigma embedding) per sample
+  Ten film(const Ten& x, const Ten& sig, const std::string& name) {
+    Ten gam = linear(sig, name + ".gamma_emb", x.C);
+    Ten bet = linear(sig, name + ".beta_emb", x.C);
+    Ten y = make(x.rows, x.C, x.period);
+    const int nb = x.rows / x.period;
+    rec([=](Launcher& L) { L.run(x.n(), FilmFwd{x.v, gam.v, bet.v, y.v, x.C, x.period}); },
+        [=](Launcher& L) {
+          if (x.g) L.run(x.n(), FilmBwdX{y.g, gam.v, x.g, x.C, x.period});
+          L.run((long)nb * x.C, FilmBwdCond{y.g, x.v, gam.g, bet.g, x.C, x.period});
+        });
+    return y;
+  }
+  // ff_network(act_before=True) (utils/nn.py:145-175): SiLU -> Linear -> SiLU -> Linear
+  Ten ffn(const Ten& x, const std::string& name, int hidden, int out) {
+    return linear(unary_silu(linear(unary_silu(x), name + ".1", hidden)), name + ".3", out);
+  }
+  // MultiHeadAttention.forward (attention.py:49-87) with scaled_dp_attn (attention.py:26-46); mask_ids: key token ids or null
+  Ten mha(const std::string& name, const Ten& q_in, const Ten& k_in, const Ten& v_in, int heads, const int64_t* mask_ids) {
+    const int dm = q_in.C, D = dm / heads, Tq = q_in.period, Tk = k_in.period, nb = q_in.rows / q_in.period;
+    Ten q = linear(q_in, name + ".wq", dm), k = linear(k_in, name + ".wk", dm), v = linear(v_in, name + ".wv", dm);
+    Ten s = make(nb * heads * Tq, Tk, heads * Tq), pr = make(nb * heads * Tq, Tk, heads * Tq), o = make(q_in.rows, dm, Tq);
+    const float scale = 1.f / sqrtf((float)D);
+    const long sQ = (long)Tq * dm, sK = (long)Tk * dm, sS1 = (long)heads * Tq * Tk, sS2 = (long)Tq * Tk;
+    rec([=](Launcher& L) {
+          Bmm a; a.A = q.v; a.B = k.v; a.C = s.v; a.M = Tq; a.N = Tk; a.K = D; a.Z1 = nb; a.Z2 = heads; a.alpha = scale;   // S = scale Q K^T
+          a.sAz1 = sQ; a.sAz2 = D; a.sAi = dm; a.sAk = 1; a.sBz1 = sK; a.sBz2 = D; a.sBk = 1; a.sBj = dm; a.sCz1 = sS1; a.sCz2 = sS2; a.sCi = Tk; a.sCj = 1;
+          run_bmm(L, a);
+          L.run(s.rows, SoftmaxFwd{s.v, pr.v, mask_ids, Tk, (long)heads * Tq});
+          Bmm c; c.A = pr.v; c.B = v.v; c.C = o.v; c.M = Tq; c.N = D; c.K = Tk; c.Z1 = nb; c.Z2 = heads;                    // O = P V
+          c.sAz1 = sS1; c.sAz2 = sS2; c.sAi = Tk; c.sAk = 1; c.sBz1 = sK; c.sBz2 = D; c.sBk = dm; c.sBj = 1; c.sCz1 = sQ; c.sCz2 = D; c.sCi = dm; c.sCj = 1;
+          run_bmm(L, c);
+        },
+        [=](Launcher& L) {
+          Bmm a; a.A = pr.v; a.B = o.g; a.C = v.g; a.M = Tk; a.N = D; a.K = Tq; a.Z1 = nb; a.Z2 = heads; a.mode = 1;          // dV += P^T dO
+          a.sAz1 = sS1; a.sAz2 = sS2; a.sAi = 1; a.sAk = Tk; a.sBz1 = sQ; a.sBz2 = D; a.sBk = dm; a.sBj = 1; a.sCz1 = sK; a.sCz2 = D; a.sCi = dm; a.sCj = 1;
+          run_bmm(L, a);
+          Bmm b; b.A = o.g; b.B = v.v; b.C = pr.g; b.M = Tq; b.N = Tk; b.K = D; b.Z1 = nb; b.Z2 = heads; b.mode = 1;          // dP += dO V^T
+          b.sAz1 = sQ; b.sAz2 = D; b.sAi = dm; b.sAk = 1; b.sBz1 = sK; b.sBz2 = D; b.sBk = 1; b.sBj = dm; b.sCz1 = sS1; b.sCz2 = sS2; b.sCi = Tk; b.sCj = 1;
+          run_bmm(L, b);
+          L.run(s.rows, SoftmaxBwd{pr.v, pr.g, s.g, Tk});
+          Bmm c; c.A = s.g; c.B = k.v; c.C = q.g; c.M = Tq; c.N = D; c.K = Tk; c.Z1 = nb; c.Z2 = heads; c.mode = 1; c.alpha = scale;   // dQ += scale dS K
+          c.sAz1 = sS1; c.sAz2 = sS2; c.sAi = Tk; c.sAk = 1; c.sBz1 = sK; c.sBz2 = D; c.sBk = dm; c.sBj = 1; c.sCz1 = sQ; c.sCz2 = D; c.sCi = dm; c.sCj = 1;
+          run_bmm(L, c);
+          Bmm e; e.A = s.g; e.B = q.v; e.C = k.g; e.M = Tk; e.N = D; e.K = Tq; e.Z1 = nb; e.Z2 = heads; e.mode = 1; e.alpha = scale;   // dK += scale dS^T Q
+          e.sAz1 = sS1; e.sAz2 = sS2; e.sAi = 1; e.sAk = Tk; e.sBz1 = sQ; e.sBz2 = D; e.sBk = dm; e.sBj = 1; e.sCz1 = sK; e.sCz2 = D; e.sCi = dm; e.sCj = 1;
+          run_bmm(L, e);
+        });
+    return linear(o, name + ".dense", dm);
+  }
+  // ConvBlock.forward (cnn.py:52-87)
+  Ten conv_block(const std::string& p, const Ten& x, const Ten& sig, int out) {
+    Ten skip = conv3(x, p + ".conv_skip", out);
+    Ten y = film(conv3(unary_silu(x), p + ".conv1", out / 2), sig, p + ".affine1");
+    y = film(conv3(unary_silu(y), p + ".conv2", out), sig, p + ".affine2");
+    y = film(linear(unary_silu(y), p + ".fc", out), sig, p + ".affine3");
+    return add(y, skip);
+  }
+  // attention.py:15-23: halves concatenated (sin | cos), fp32 like the reference
+  const float* pos_table(int length, int dim, float pos_factor) {
+    if (dry) return nullptr;
+    const int half = dim / 2;
+    std::vector<float> h((size_t)length * dim);
+    const double step = log(10000.0) / (half - 1);
+    for (int t = 0; t < length; ++t)
+      for (int j = 0; j < half; ++j) {
+        const float freq = expf((float)j * (float)(-step));
+        const float ang = (float)t * freq * pos_factor;
+        h[(size_t)t * dim + j] = sinf(ang);
+        h[(size_t)t * dim + half + j] = cosf(ang);
+      }
+    float* dptr = (float*)dev_alloc(h.size() * sizeof(float));
+    if (!dptr) { err = "out of memory (position table)"; return nullptr; }
+    consts.push_back(dptr);
+    to_dev(dptr, h.data(), h.size() * sizeof(float));
+    return dptr;
+  }
+  // EncoderLayer.forward (model.py:35-58)
+  Ten encoder_layer(const std::string& p, const Ten& x, const Ten& text_in, const Ten& sig, int heads, float pos_factor) {
+    const int dm = x.C;
+    Ten t = film(ln(linear(unary_silu(text_in), p + ".text_dense", dm)), sig, p + ".affine0");
+    Ten t_pe = add_pe(t, pos_table(t.period, dm, 1.f));
+    const float* xpos = pos_table(x.period, dm, pos_factor);
+    Ten x_pe = add_pe(x, xpos);
+    Ten x2 = mha(p + ".mha", x_pe, t_pe, t, heads, text);                 // v carries no PE; padding mask on the text keys
+    x2 = add(film(ln(x2), sig, p + ".affine1"), x);                        // no residual inside this LayerNorm
+    Ten x2_pe = add_pe(x2, xpos);
+    Ten x3 = mha(p + ".mha2", x2_pe, x2_pe, x2, heads, nullptr);
+    x3 = film(ln(add(x2, x3)), sig, p + ".affine2");
+    Ten x4 = add(ffn(x3, p + ".ffn", 2 * dm, dm), x3);
+    return film(ln(x4), sig, p + ".affine3");
+  }
+  // TextStyleEncoder.forward (text_style.py:91-104); the Dropout(0.3) on the style vectors is the caller's keep mask
+  Ten text_style(const Ten& sig) {
+    const std::string p = "text_style_model";
+    Ten sdrop = make(in_style.rows, in_style.C, in_style.period, false);
+    {
+      const Ten a = in_style, m = style_keep; const bool* hk = &have_keep;
+      rec([=](Launcher& L) { L.run(a.n(), MulFwd{a.v, *hk ? m.v : nullptr, sdrop.v}); }, [=](Launcher&) {});
+    }
+    Ten s = sdrop; s.rows = B * 70; s.C = 256; s.period = 70;              // reshape_up(style, 5): a plain view (utils/nn.py:115-127)
+    s = film(ln(ffn(s, p + ".style_ffn", 4 * c2, d)), sig, p + ".affine1");
+    Ten t = make(B * L, d, L);
+    {
+      const int64_t* ids = text; const float* E = P(p + ".emb.weight"); float* gE = G(p + ".emb.weight"); const int dd = d;
+      rec([=](Launcher& L_) { L_.run(t.n(), EmbedFwd{ids, E, t.v, dd}); }, [=](Launcher& L_) { L_.run(t.n(), EmbedBwd{ids, t.g, gE, dd}); });
+    }
+    t = film(ln(t), sig, p + ".affine2");
+    Ten m = mha(p + ".mha", t, s, s, 8, nullptr);                          // no mask here
+    t = film(ln(add(t, m)), sig, p + ".affine3");
+    return film(ln(ffn(t, p + ".text_ffn", 2 * d, d)), sig, p + ".affine4");   // no residual
+  }
+  // DiffusionModel.forward (model.py:121-182)
+  void build_model() {
+    tape.clear();
+    v_used = g_used = 0;
+    in_x = make(B * T, 2, T, false);
+    in_sigma = make(B, 1, 1, false);
+    in_style = make(B * 14, 1280, 14, false);
+    style_keep = make(B * 14, 1280, 14, false);
+    Ten sig = ffn(in_sigma, "sigma_ffn", 2048, c1 / 4);
+    Ten text_t = text_style(sig);
+    Ten x = linear(in_x, "input_dense", c1);
+    Ten h1 = conv_block("enc1", x, sig, c1);
+    Ten h2 = conv_block("enc2", pool(h1), sig, c2);
+    h2 = encoder_layer("enc3", h2, text_t, sig, 3, 4.f);
+    Ten h3 = conv_block("enc4", pool(h2), sig, c3);
+    h3 = encoder_layer("enc5", h3, text_t, sig, 4, 2.f);
+    x = linear(pool(h3), "att_dense", d);
+    for (int i = 0; i < num_layers; ++i) x = encoder_layer("att_layers." + std::to_string(i), x, text_t, sig, 6, 1.f);
+    x = conv_block("dec3", add(up(x), conv3(h3, "skip_conv3", d)), sig, c3);
+    x = conv_block("dec2", add(up(x), conv3(h2, "skip_conv2", c3)), sig, c2);
+    x = conv_block("dec1", add(up(x), conv3(h1, "skip_conv1", c2)), sig, c1);
+    out_score = linear(x, "output_dense", 2);
+    out_pen = sigmoid(linear(x, "pen_lifts_dense.0", 1));
+  }
+};
+
+extern "C" {
+
+const char* dhg_trainer_last_error(void) { return g_serr; }
+
+int64_t dhg_trainer_param_count(int32_t num_layers, int32_t channels) {
+  if (num_layers < 0 || channels < 8 || channels % 8) return -1;
+  Layout l;
+  l.build(num_layers, channels);
+  return l.total;
+}
+
+int32_t dhg_trainer_param_info(int32_t num_layers, int32_t channels, int32_t index, char* name_out, int32_t name_cap, int64_t* offset,
+                               int64_t* numel) {
+  if (num_layers < 0 || channels < 8 || channels % 8) return sfail("dhg_trainer_param_info: bad model size");
+  Layout l;
+  l.build(num_layers, channels);
+  if (index < 0 || index >= (int)l.items.size()) return -1;   // past the end: not an error, the caller's loop stops here
+  if (name_out && name_cap > 0) snprintf(name_out, (size_t)name_cap, "%s", l.items[index].name.c_str());
+  if (offset) *offset = l.items[index].off;
+  if (numel) *numel = l.items[index].numel;
+  return 0;
+}
+
+int32_t dhg_trainer_create(int32_t device, int32_t num_layers, int32_t channels, int32_t B, int32_t T, int32_t L, float* dev_params,
+                           float* dev_grads, dhg_trainer** out) {
+  if (!out) return sfail("dhg_trainer_create: out is NULL");
+  *out = nullptr;
+  if (!dev_params || !dev_grads) return sfail("dhg_trainer_create: parameter / gradient buffer is NULL");
+  if (num_layers < 0 || channels < 8 || channels % 8) return sfail("dhg_trainer_create: bad model size");
+  if (B < 1 || L < 1 || T < 8 || T % 8) return sfail("dhg_trainer_create: need B >= 1, L >= 1 and T a positive multiple of 8 (got B=%d T=%d L=%d)", B, T, L);
+#ifndef DHG_HOSTSIM
+  if (cudaSetDevice(device) != cudaSuccess) return sfail("dhg_trainer_create: cudaSetDevice(%d) failed", device);
+#endif
+  dhg_trainer* t = new dhg_trainer();
+  t->device = device; t->num_layers = num_layers; t->ch = channels; t->B = B; t->T = T; t->L = L;
+  t->c1 = channels; t->c2 = channels * 3 / 2; t->c3 = channels * 2; t->d = 2 * t->c2;
+  t->lay.build(num_layers, channels);
+  t->params = dev_params; t->grads = dev_grads;
+  t->dry = true;
+  t->build_model();
+  if (!t->err.empty()) { sfail("dhg_trainer_create: %s", t->err.c_str()); delete t; return 1; }
+  t->v_arena = (float*)dev_alloc(t->v_need * sizeof(float));
+  t->g_arena = (float*)dev_alloc(t->g_need * sizeof(float));
+  t->text = (int64_t*)dev_alloc((size_t)B * L * sizeof(int64_t));
+  if (!t->v_arena || !t->g_arena || !t->text) {
+    sfail("dhg_trainer_create: out of device memory (%.1f MB of activations + gradients)", (t->v_need + t->g_need) * 4.0 / 1e6);
+    dev_free(t->v_arena); dev_free(t->g_arena); dev_free(t->text); delete t; return 1;
+  }
+  t->dry = false;
+  t->build_model();
+  if (!t->err.empty()) { sfail("dhg_trainer_create: %s", t->err.c_str()); dhg_trainer_destroy(t); return 1; }
+  *out = t;
+  return 0;
+}
+
+int32_t dhg_trainer_destroy(dhg_trainer* t) {
+  if (!t) return 0;
+#ifndef DHG_HOSTSIM
+  cudaSetDevice(t->device);
+  cudaDeviceSynchronize();
+#endif
+  dev_free(t->v_arena); dev_free(t->g_arena); dev_free(t->text);
+  for (void* p : t->consts) dev_free(p);
+  delete t;
+  return 0;
+}
+
+int64_t dhg_trainer_workspace_bytes(const dhg_trainer* t) { return t ? (int64_t)((t->v_need + t->g_need) * sizeof(float)) : 0; }
+int64_t dhg_trainer_last_launches(const dhg_trainer* t) { return t ? t->last_launches : 0; }
+
+int32_t dhg_trainer_set_option(const char* name, int32_t value) {
+  if (name && !strcmp(name, "tiled_gemm")) { g_use_tiled = value; return 0; }
+  return sfail("dhg_trainer_set_option: unknown option");
+}
+
+int32_t dhg_trainer_forward(dhg_trainer* t, const float* dev_x, const int64_t* dev_text, const float* dev_sigma, const float* dev_style,
+                            const float* dev_style_keep, float* dev_score_pred, float* dev_pen_pred, void* stream) {
+  if (!t) return sfail("dhg_trainer_forward: trainer is NULL");
+  if (!dev_x || !dev_text || !dev_sigma || !dev_style) return sfail("dhg_trainer_forward: NULL input");
+#ifndef DHG_HOSTSIM
+  if (cudaSetDevice(t->device) != cudaSuccess) return sfail("dhg_trainer_forward: cudaSetDevice failed");
+#endif
+  Launcher L; L.st = (ts_stream)stream;
+  L.copy(t->in_x.v, dev_x, (size_t)t->B * t->T * 2 * sizeof(float));
+  L.copy(t->text, dev_text, (size_t)t->B * t->L * sizeof(int64_t));
+  L.copy(t->in_sigma.v, dev_sigma, (size_t)t->B * sizeof(float));
+  L.copy(t->in_style.v, dev_style, (size_t)t->B * 14 * 1280 * sizeof(float));
+  t->have_keep = dev_style_keep != nullptr;
+  if (dev_style_keep) L.copy(t->style_keep.v, dev_style_keep, (size_t)t->B * 14 * 1280 * sizeof(float));
+  for (auto& op : t->tape) op.fwd(L);
+  if (dev_score_pred) L.copy(dev_score_pred, t->out_score.v, (size_t)t->B * t->T * 2 * sizeof(float));
+  if (dev_pen_pred) L.copy(dev_pen_pred, t->out_pen.v, (size_t)t->B * t->T * sizeof(float));
+  t->last_launches = L.launches;
+#ifndef DHG_HOSTSIM
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return sfail("dhg_trainer_forward: %s", cudaGetErrorString(e));
+#endif
+  return 0;
+}
+
+int32_t dhg_trainer_backward(dhg_trainer* t, const float* dev_grad_score, const float* dev_grad_pen_pred, void* stream) {
+  if (!t) return sfail("dhg_trainer_backward: trainer is NULL");
+  if (!dev_grad_score || !dev_grad_pen_pred) return sfail("dhg_trainer_backward: NULL gradient");
+#ifndef DHG_HOSTSIM
+  if (cudaSetDevice(t->device) != cudaSuccess) return sfail("dhg_trainer_backward: cudaSetDevice failed");
+#endif
+  Launcher L; L.st = (ts_stream)stream;
+  L.zero(t->g_arena, t->g_need * sizeof(float));
+  L.zero(t->grads, (size_t)t->lay.total * sizeof(float));
+  L.copy(t->out_score.g, dev_grad_score, (size_t)t->B * t->T * 2 * sizeof(float));
+  L.copy(t->out_pen.g, dev_grad_pen_pred, (size_t)t->B * t->T * sizeof(float));
+  for (auto it = t->tape.rbegin(); it != t->tape.rend(); ++it) it->bwd(L);
+  t->last_launches += L.launches;
+#ifndef DHG_HOSTSIM
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return sfail("dhg_trainer_backward: %s", cudaGetErrorString(e));
+#endif
+  return 0;
+}
+
+}  // extern "C"

@@ -79,6 +79,17 @@ SIGNATURES = {
     "dhg_train_sqnorm": (c_i32, [c_i32, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "dhg_train_adam_step": (c_i32, [c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                     ctypes.c_double, ctypes.c_double, c_vp, ctypes.c_double, c_i32, c_vp]),
+    # forward + backward pass of the denoiser (csrc/train_step.cu)
+    "dhg_trainer_last_error": (c_cp, []),
+    "dhg_trainer_param_count": (c_i64, [c_i32, c_i32]),
+    "dhg_trainer_param_info": (c_i32, [c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp]),
+    "dhg_trainer_create": (c_i32, [c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "dhg_trainer_destroy": (c_i32, [c_vp]),
+    "dhg_trainer_workspace_bytes": (c_i64, [c_vp]),
+    "dhg_trainer_last_launches": (c_i64, [c_vp]),
+    "dhg_trainer_set_option": (c_i32, [c_cp, c_i32]),
+    "dhg_trainer_forward": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "dhg_trainer_backward": (c_i32, [c_vp, c_vp, c_vp, c_vp]),
 }
 
 

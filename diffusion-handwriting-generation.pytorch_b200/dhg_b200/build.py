@@ -15,7 +15,7 @@ PROJ_DIR = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PROJ_DIR, "csrc")
 LIB_DIR = os.path.join(PROJ_DIR, "lib")
 LIB_PATH = os.environ.get("DHG_LIB_PATH") or os.path.join(LIB_DIR, "libdhg_b200.so")   # DHG_LIB_PATH: A/B builds
-SOURCES = ["engine.cu", "kernels_simt.cu", "gemm_tc.cu", "attention_tc.cu", "style_extractor.cu", "train_update.cu"]
+SOURCES = ["engine.cu", "kernels_simt.cu", "gemm_tc.cu", "attention_tc.cu", "style_extractor.cu", "train_update.cu", "train_step.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--shared", "-Xcompiler", "-fPIC", "--use_fast_math=false",

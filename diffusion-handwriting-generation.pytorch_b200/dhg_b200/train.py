@@ -10,8 +10,14 @@ names and argument meaning:
 
 The kernels are CUDA (`csrc/train_update.cu`, C ABI `dhg_train_*`); torch tensors only carry the device memory, and
 `torch.distributed` does the one collective of a data-parallel step (a SUM all-reduce of the flat fp32 gradient; the
-division by the world size and the clip coefficient are folded into the optimiser kernel).  The backward pass of the
-denoiser is NOT built: `step_and_update_lr` takes the flat gradient as an argument.
+division by the world size and the clip coefficient are folded into the optimiser kernel).
+
+The forward + backward pass of the denoiser (`csrc/train_step.cu`, C ABI `dhg_trainer_*`) is `DenoiserTrainer`:
+
+    DenoiserTrainer(state_dict, B, T, L).forward(x_perturbed, text, sigma, style)   model(...) in train.py:46-51
+        .backward(grad_score, grad_pen)                                             loss.backward(), train.py:55
+        .train_step(strokes, pen_lifts, text, style, alphas, eps)                   TrainingLoop.train_step, train.py:26-67
+    get_alphas(batch_size, alpha_set)                                               utils/nn.py:42-61
 """
 import ctypes
 
@@ -167,3 +173,139 @@ class FlatAdam:
                                        self.n_steps, lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, _p(sq),
                                        float(self.clip_grad or 0.0), self._world, st))
         return lr
+
+
+def get_alphas(batch_size, alpha_set, generator=None):
+    """utils/nn.py:42-61: one alpha per sample, uniform between two neighbouring entries of the alpha schedule.  Host
+    side like the reference (its result is moved to the device by the caller); `generator` makes the draw repeatable."""
+    idx = torch.randint(low=0, high=len(alpha_set) - 1, size=(batch_size, 1), dtype=torch.int64, generator=generator)
+    lower, upper = alpha_set[idx], alpha_set[idx + 1]
+    return torch.rand(lower.shape, generator=generator) * (upper - lower) + lower
+
+
+def _trainer_check(rc):
+    if rc != 0:
+        raise DhgTrainError(_abi.lib().dhg_trainer_last_error().decode("utf-8", "replace"))
+
+
+def param_layout(num_layers=2, channels=128):
+    """Checkpoint key -> (offset, numel) of the flat parameter / gradient buffer (dhg_trainer_param_info): the 323 keys of
+    model_final.pth in file order, tensors back to back with their checkpoint shapes."""
+    from collections import OrderedDict
+
+    lib = _abi.lib()
+    name = ctypes.create_string_buffer(256)
+    off, num = ctypes.c_int64(), ctypes.c_int64()
+    out, i = OrderedDict(), 0
+    while True:
+        rc = lib.dhg_trainer_param_info(num_layers, channels, i, name, 256, ctypes.byref(off), ctypes.byref(num))
+        if rc == -1:
+            break
+        _trainer_check(rc)
+        out[name.value.decode()] = (off.value, num.value)
+        i += 1
+    return out
+
+
+class DenoiserTrainer:
+    """TrainingLoop.train_step (train.py:26-67) on the device: DiffusionModel.forward with every activation kept, the
+    backward pass into ONE flat gradient buffer, and FlatAdam on the flat parameter buffer -- forward, loss, backward,
+    gradient exchange and update are CUDA kernels of this library plus one NCCL all-reduce; nothing synchronises.
+
+    `state_dict`: the checkpoint's tensors (any device); `B, T, L`: the plan's batch, stroke length (multiple of 8) and
+    text length.  Optimiser arguments as in FlatAdam (config.yml:18-38)."""
+
+    def __init__(self, state_dict, B, T, L, num_layers=None, channels=128, device="cuda", **optim):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise DhgTrainError("DenoiserTrainer needs a CUDA device: there is no CPU path")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        if num_layers is None:
+            num_layers = len({k.split(".")[1] for k in state_dict if k.startswith("att_layers.")})
+        self.num_layers, self.channels, self.B, self.T, self.L = num_layers, channels, B, T, L
+        self.layout = param_layout(num_layers, channels)
+        missing = [k for k in self.layout if k not in state_dict]
+        extra = [k for k in state_dict if k not in self.layout]
+        if missing or extra:   # strict, like load_state_dict(strict=True) (checkpoint.py:83-87)
+            raise RuntimeError(f"state_dict does not match the model: missing {missing[:3]}, unexpected {extra[:3]}")
+        for k, (_, n) in self.layout.items():
+            if state_dict[k].numel() != n:
+                raise RuntimeError(f"size mismatch for {k}: {tuple(state_dict[k].shape)}")
+        self._shapes = {k: tuple(state_dict[k].shape) for k in self.layout}
+        optim.setdefault("d_model", 2 * channels)
+        self.optimizer = FlatAdam([state_dict[k].to(torch.float32) for k in self.layout], device=self.device, **optim)
+        self.param = self.optimizer.param
+        self.grad = torch.zeros_like(self.param)
+        self._h = ctypes.c_void_p()
+        _trainer_check(_abi.lib().dhg_trainer_create(self.device.index, num_layers, channels, B, T, L, _p(self.param), _p(self.grad),
+                                                     ctypes.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            _abi.lib().dhg_trainer_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 -- interpreter shutdown
+            pass
+
+    @property
+    def workspace_bytes(self):
+        return _abi.lib().dhg_trainer_workspace_bytes(self._h)
+
+    @property
+    def last_launch_count(self):
+        return _abi.lib().dhg_trainer_last_launches(self._h)
+
+    def state_dict(self):
+        """Views of the flat parameter buffer under the checkpoint's keys and shapes (what save_checkpoint writes)."""
+        from collections import OrderedDict
+
+        return OrderedDict((k, self.param[o:o + n].view(self._shapes[k])) for k, (o, n) in self.layout.items())
+
+    def grad_dict(self):
+        from collections import OrderedDict
+
+        return OrderedDict((k, self.grad[o:o + n].view(self._shapes[k])) for k, (o, n) in self.layout.items())
+
+    def forward(self, strokes, text, sigma, style_vector, style_keep=None):
+        """model(x_perturbed, text, sigma, style) (model.py:121-182) -> (score_pred [B, T, 2], pen_lifts_pred [B, T], None).
+        sigma: [B, 1] or [B, 1, 1]; text: integer [B, L]; style_keep: the Dropout(0.3) keep mask / 0.7 of text_style.py:92
+        (None: no dropout)."""
+        B, T, L = self.B, self.T, self.L
+        strokes = _f32(strokes, (B, T, 2), "strokes")
+        style_vector = _f32(style_vector, (B, 14, 1280), "style_vector")
+        if style_keep is not None:
+            style_keep = _f32(style_keep, (B, 14, 1280), "style_keep")
+        sigma = _f32(sigma.reshape(B), (B,), "sigma")
+        if not (isinstance(text, torch.Tensor) and text.is_cuda and tuple(text.shape) == (B, L)) or text.is_floating_point():
+            raise ValueError(f"text: expected an integer CUDA tensor of shape {(B, L)}")
+        text = text.to(torch.int64).contiguous()
+        score = torch.empty(B, T, 2, dtype=torch.float32, device=self.device)
+        pen = torch.empty(B, T, dtype=torch.float32, device=self.device)
+        _trainer_check(_abi.lib().dhg_trainer_forward(self._h, _p(strokes), _p(text), _p(sigma), _p(style_vector), _p(style_keep), _p(score),
+                                                      _p(pen), _stream()))
+        return score, pen, None
+
+    def backward(self, grad_score, grad_pen_pred):
+        """loss.backward() (train.py:55) from d loss / d score_pred and d loss / d pen_lifts_pred: fills and returns the flat gradient."""
+        B, T = self.B, self.T
+        grad_score = _f32(grad_score, (B, T, 2), "grad_score")
+        grad_pen_pred = _f32(grad_pen_pred.reshape(B, T), (B, T), "grad_pen_pred")
+        _trainer_check(_abi.lib().dhg_trainer_backward(self._h, _p(grad_score), _p(grad_pen_pred), _stream()))
+        return self.grad
+
+    def train_step(self, strokes, pen_lifts, text, style_vectors, alphas, eps, style_keep=None, group=None):
+        """TrainingLoop.train_step (train.py:26-67) with the two random draws (alphas: get_alphas, eps: randn_like) injected.
+        Returns (loss, score_loss, pen_lifts_loss) as 0-dim CUDA tensors; the parameters are updated in place."""
+        B = self.B
+        alphas = alphas.reshape(B, 1)
+        x_perturbed = perturb(strokes, alphas, eps)                                                 # train.py:40-43
+        score_pred, pen_pred, _ = self.forward(x_perturbed, text, torch.sqrt(alphas), style_vectors, style_keep)   # :46-51
+        loss, score_loss, pen_loss, g_s, g_p = loss_fn(eps, score_pred, pen_lifts, pen_pred, alphas, with_grads=True)   # :52-54
+        self.backward(g_s, g_p)                                                                    # :55
+        self.optimizer.step_and_update_lr(self.grad, group)                                        # :57-63
+        return loss, score_loss, pen_loss

@@ -294,6 +294,37 @@ int32_t dhg_train_adam_step(int32_t device, float* dev_param, const float* dev_g
                             int32_t step, double lr, double beta1, double beta2, double eps, double weight_decay,
                             const double* dev_sqnorm, double max_norm, int32_t world_size, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Forward + backward pass of the denoiser for the training step (csrc/train_step.cu).  Replaces
+ *   train.py:46-55   strokes_pred, pen_lifts_pred, _ = model(x_perturbed, text, sqrt(alphas), style);  loss.backward()
+ * The parameters live in ONE flat fp32 device buffer in checkpoint key order (dhg_trainer_param_info enumerates
+ * name / offset / numel; Linear [out, in], Conv1d [out, in, 3] exactly as in model_final.pth) and the gradients in a
+ * second buffer of the same layout -- the buffers dhg_train_sqnorm / dhg_train_adam_step work on.  Both are borrowed
+ * for the life of the trainer.  A trainer is a plan for one (B, T, L); T a multiple of 8 (inference.py:78).
+ *   dhg_trainer_forward   dev_x [B, T, 2] (x_perturbed), dev_text int64 [B, L] (0 = padding), dev_sigma [B]
+ *                         (sqrt(alphas)), dev_style [B, 14, 1280], dev_style_keep [B, 14, 1280] or NULL: the keep mask
+ *                         of text_style.py:83,92 Dropout(0.3) already divided by 0.7 (NULL = eval mode) ->
+ *                         dev_score_pred [B, T, 2], dev_pen_pred [B, T] (after the sigmoid); every activation is kept
+ *   dhg_trainer_backward  dev_grad_score [B, T, 2], dev_grad_pen_pred [B, T] (what dhg_train_loss writes) -> the flat
+ *                         gradient buffer is zeroed and filled.  Weight gradients are summed with fp32 atomics: the
+ *                         last bits depend on the order.
+ * Stream-ordered, nothing synchronises, no allocation after create (graph-capturable).  fp32 on the CUDA cores.
+ * Errors: dhg_trainer_last_error(). */
+typedef struct dhg_trainer dhg_trainer;
+const char* dhg_trainer_last_error(void);
+int64_t dhg_trainer_param_count(int32_t num_layers, int32_t channels);
+int32_t dhg_trainer_param_info(int32_t num_layers, int32_t channels, int32_t index, char* name_out, int32_t name_cap, int64_t* offset,
+                               int64_t* numel);   /* 0 ok, -1 index past the end */
+int32_t dhg_trainer_create(int32_t device, int32_t num_layers, int32_t channels, int32_t B, int32_t T, int32_t L, float* dev_params,
+                           float* dev_grads, dhg_trainer** out);
+int32_t dhg_trainer_destroy(dhg_trainer* t);
+int64_t dhg_trainer_workspace_bytes(const dhg_trainer* t);
+int64_t dhg_trainer_last_launches(const dhg_trainer* t);   /* launches of the last forward (+ backward) */
+int32_t dhg_trainer_set_option(const char* name, int32_t value);   /* "tiled_gemm" 1 (default) / 0: per-thread GEMM body (checks) */
+int32_t dhg_trainer_forward(dhg_trainer* t, const float* dev_x, const int64_t* dev_text, const float* dev_sigma, const float* dev_style,
+                            const float* dev_style_keep, float* dev_score_pred, float* dev_pen_pred, void* stream);
+int32_t dhg_trainer_backward(dhg_trainer* t, const float* dev_grad_score, const float* dev_grad_pen_pred, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
