@@ -87,9 +87,93 @@ def train_update_leg(dev, peaks):
         gbs = n * 32 / us / 1e3
         return {"parameters": n, "us_per_step": us, "bytes_per_step": n * 32, "achieved_gbs": gbs, "peak_gbs": peaks["hbm_gbs"],
                 "frac": gbs / peaks["hbm_gbs"], "what": "gradient 2-norm + clip + Adam (inv-sqrt schedule) on the flat fp32 buffer; "
-                "28 B (Adam) + 4 B (norm) per parameter; the backward pass that produces the gradient is not built"}
+                "28 B (Adam) + 4 B (norm) per parameter; the gradient comes from dhg_trainer_backward (train_step leg)"}
     except Exception as e:   # noqa: BLE001
         return {"failed": str(e)[:200]}
+
+
+def train_step_leg(dev, B=96, T=480, L=50, steps=5):
+    """BASELINE configs[3] / SURVEY 8f-3: TrainingLoop.train_step (train.py:26-67) at batch 96, seq_len 480, text 50 on ONE GPU:
+    dhg_b200.train.DenoiserTrainer (perturb, forward with kept activations, loss, backward, clip + Adam; csrc/train_step.cu +
+    train_update.cu, fp32 on the CUDA cores) and, beside it, the UNMODIFIED reference's step in PyTorch eager fp32 on the same
+    GPU (model.train(), loss_fn, backward, clip_grad_norm_, Adam in InvSqrtScheduledOptim).  Device-timed, synthetic batch."""
+    out = {"config": {"B": B, "T": T, "L": L, "workload": "configs[3]: train.py denoiser step, seq_len 480, batch 96 (per GPU)"}}
+    from oracle.dhg_oracle import alpha_bar, beta_schedule, init_state_dict
+
+    g = torch.Generator().manual_seed(SEED)
+    strokes = torch.randn(B, T, 2, generator=g).to(dev)
+    pen = (torch.rand(B, T, generator=g) < 0.05).float().to(dev)
+    text = torch.randint(2, 73, (B, L), generator=g)
+    text[:, -1] = 1
+    text[: B // 2, L // 2:] = 0     # half of the prompts padded (config.yml: max_text_len 50)
+    text[: B // 2, L // 2 - 1] = 1
+    text = text.to(dev)
+    style = torch.randn(B, S_STYLE, 1280, generator=g).to(dev)
+    keep = ((torch.rand(B, S_STYLE, 1280, generator=g) >= 0.3).float() / 0.7).to(dev)
+    eps = torch.randn(B, T, 2, generator=g).to(dev)
+    abar = alpha_bar(beta_schedule())
+    idx = torch.randint(0, len(abar) - 1, (B, 1), generator=g)
+    alphas = (torch.rand(B, 1, generator=g) * (abar[idx + 1] - abar[idx]) + abar[idx]).to(dev)
+    sd = init_state_dict(0)
+
+    def timed(fn):
+        for _ in range(2):
+            r = fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / steps, r
+
+    try:
+        from dhg_b200.train import DenoiserTrainer
+
+        tr = DenoiserTrainer(sd, B, T, L, device=dev)
+        ms, losses = timed(lambda: tr.train_step(strokes, pen, text, style, alphas, eps, style_keep=keep))
+        flop = 3.0 * B * (flops_alg_per_sample_step(T, L) + 983_040 * 70 + 1_323_008)   # forward F_exec (SURVEY 8d) x 3 for fwd + bwd
+        out["b200"] = {"ms_per_step": ms, "samples_per_s": B / (ms * 1e-3), "loss": float(losses[0].item()), "finite": bool(torch.isfinite(losses[0]).item()),
+                       "launches_fwd_bwd": int(tr.last_launch_count), "workspace_GB": tr.workspace_bytes / 1e9,
+                       "tflops_fp32_3x_forward": flop / (ms * 1e-3) / 1e12, "dtype": "fp32 (CUDA cores)"}
+        tr.close()
+        del tr
+        torch.cuda.empty_cache()
+    except Exception as e:   # noqa: BLE001
+        out["b200"] = {"failed": f"{type(e).__name__}: {str(e)[:300]}"}
+    try:
+        mods = reference_modules()
+        if mods is None:
+            raise RuntimeError("baseline/_ref is missing")
+        from diffusion_handwriting_generation.loss import loss_fn
+        from diffusion_handwriting_generation.scheduler import InvSqrtScheduledOptim
+        from diffusion_handwriting_generation.utils.clip_grad import dispatch_clip_grad
+
+        model = mods[0](num_layers=2, c1=128, c2=192, c3=256, drop_rate=0.0)
+        model.load_state_dict(sd, strict=True)
+        model.to(dev).train()
+        opt = InvSqrtScheduledOptim(torch.optim.Adam(model.parameters(), lr=3e-4, weight_decay=1e-5, betas=(0.9, 0.98)), 1.0, 256, 10000)
+
+        def ref_step():   # train.py:38-63
+            x_p = torch.sqrt(alphas).unsqueeze(-1) * strokes + torch.sqrt(1 - alphas).unsqueeze(-1) * eps
+            opt.zero_grad()
+            score_pred, pen_pred, _ = model(x_p, text, torch.sqrt(alphas), style)
+            loss, _, _ = loss_fn(eps, score_pred, pen, pen_pred, alphas)
+            loss.backward()
+            dispatch_clip_grad(model.parameters(), value=100.0)
+            opt.step_and_update_lr()
+            return loss
+
+        ms, loss = timed(ref_step)
+        out["reference_eager_fp32"] = {"ms_per_step": ms, "samples_per_s": B / (ms * 1e-3), "loss": float(loss.item()),
+                                       "flags": {"matmul_allow_tf32": bool(torch.backends.cuda.matmul.allow_tf32),
+                                                 "cudnn_allow_tf32": bool(torch.backends.cudnn.allow_tf32)}}
+        del model, opt
+        torch.cuda.empty_cache()
+    except Exception as e:   # noqa: BLE001
+        out["reference_eager_fp32"] = {"failed": f"{type(e).__name__}: {str(e)[:300]}"}
+    return out
 
 
 def synthetic_inputs(lo, hi, T, L, pin=False, seed=SEED):
@@ -548,6 +632,7 @@ def run_b200(args, rank, world, local_rank):
         line["gpu_eager_baseline_small"] = {f"B={b}": {k: v for k, v in gpu_eager_leg(dev, b).items() if k in ("fp32", "bf16_autocast")}
                                             for b in (64, 1)}
         line["train_update"] = train_update_leg(dev, peaks)
+        line["train_step"] = train_step_leg(dev)
     if args.cpu_baseline and world >= 1:
         lines_s, s_chain, cores, kind = cpu_reference_leg(args.cpu_batch, 1, 1)
         line["cpu_baseline"] = {

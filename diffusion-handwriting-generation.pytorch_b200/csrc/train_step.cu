@@ -482,9 +482,15 @@ struct dhg_trainer {
     rec([=](Launcher& L) { L.run(x.rows, LnFwd{x.v, y.v, rs.v, x.C}); }, [=](Launcher& L) { if (x.g) L.run(x.rows, LnBwd{y.v, y.g, rs.v, x.g, x.C}); });
     return y;
   }
-  // weight-gradient batching: one batch item per sample when the matrix is large, else one item
+  // weight-gradient batching of a Linear: the rows are cut into Z equal runs of whole samples, about 512 rows each (one
+  // batch item per run, reduced into dW with atomics); small matrices are one item
   static void wgrad_split(const Ten& x, int& Z, int& rpz) {
-    if (x.rows > 256 && x.period > 1 && x.rows % x.period == 0) { Z = x.rows / x.period; rpz = x.period; } else { Z = 1; rpz = x.rows; }
+    Z = 1; rpz = x.rows;
+    if (x.rows <= 512 || x.rows % x.period) return;
+    const int nb = x.rows / x.period;
+    int g = 1;
+    for (int c = 1; c <= nb; ++c) if (nb % c == 0 && (long)c * x.period <= 512) g = c;
+    Z = nb / g; rpz = g * x.period;
   }
   // nn.Linear: W [N, K], b [N]
   Ten linear(const Ten& x, const std::string& name, int N) {
@@ -506,8 +512,8 @@ struct dhg_trainer {
             run_bmm(L, p);
           }
           int Z, rpz; wgrad_split(x, Z, rpz);
-          Bmm q; q.A = x.v; q.B = y.g; q.C = gW; q.M = K; q.N = N; q.K = rpz; q.Z1 = Z; q.mode = 2;   // dW[n, k] += sum_r x[r, k] dy[r, n]
-          q.sAz1 = (long)rpz * K; q.sAi = 1; q.sAk = K; q.sBz1 = (long)rpz * N; q.sBk = N; q.sBj = 1; q.sCz1 = 0; q.sCi = 1; q.sCj = K;
+          Bmm q; q.A = y.g; q.B = x.v; q.C = gW; q.M = N; q.N = K; q.K = rpz; q.Z1 = Z; q.mode = 2;   // dW[n, k] += sum_r dy[r, n] x[r, k]  (k fastest: coalesced atomics)
+          q.sAz1 = (long)rpz * N; q.sAi = 1; q.sAk = N; q.sBz1 = (long)rpz * K; q.sBk = K; q.sBj = 1; q.sCz1 = 0; q.sCi = K; q.sCj = 1;
           run_bmm(L, q);
           L.run((long)N * ((x.rows + 63) / 64), ColSum{y.g, gb, x.rows, N});
         });
@@ -540,8 +546,8 @@ struct dhg_trainer {
               p.sAz1 = (long)Tn * N; p.sAi = N; p.sAk = 1; p.sBk = 3L * K; p.sBj = 3; p.sCz1 = (long)Tn * K; p.sCi = K; p.sCj = 1;
               run_bmm(L, p);
             }
-            Bmm q; q.A = x.v + (long)(lo + tap - 1) * K; q.B = y.g + (long)lo * N; q.C = gW + tap; q.M = K; q.N = N; q.K = hi - lo; q.Z1 = nb; q.mode = 2;
-            q.sAz1 = (long)Tn * K; q.sAi = 1; q.sAk = K; q.sBz1 = (long)Tn * N; q.sBk = N; q.sBj = 1; q.sCz1 = 0; q.sCi = 3; q.sCj = 3L * K;
+            Bmm q; q.A = y.g + (long)lo * N; q.B = x.v + (long)(lo + tap - 1) * K; q.C = gW + tap; q.M = N; q.N = K; q.K = hi - lo; q.Z1 = nb; q.mode = 2;   // dW[n, k, tap]
+            q.sAz1 = (long)Tn * N; q.sAi = 1; q.sAk = N; q.sBz1 = (long)Tn * K; q.sBk = K; q.sBj = 1; q.sCz1 = 0; q.sCi = 3L * K; q.sCj = 3;
             run_bmm(L, q);
           }
           L.run((long)N * ((x.rows + 63) / 64), ColSum{y.g, gb, x.rows, N});
