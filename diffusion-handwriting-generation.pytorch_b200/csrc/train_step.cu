@@ -68,6 +68,20 @@ template <class F>
 __global__ void __launch_bounds__(256) ts_kernel(long n, F f) {
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) f(i);
 }
+// one warp per row (LayerNorm, softmax): f.warp(row, lane) does the same arithmetic as f(row) with lane-strided columns
+template <class F>
+__global__ void __launch_bounds__(256) ts_row_kernel(long rows, F f) {
+  const int lane = threadIdx.x & 31;
+  for (long r = (long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (long)gridDim.x * 8) f.warp(r, lane);
+}
+__device__ __forceinline__ float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
 TS_FN void ts_atomic_add(float* p, float v) { atomicAdd(p, v); }
 #else
 TS_FN void ts_atomic_add(float* p, float v) {
@@ -92,6 +106,21 @@ struct Launcher {
     for (long i = 0; i < n; ++i) f(i);
 #endif
     ++launches;
+  }
+  // per-row kernels: a warp per row on the GPU (the per-thread body with "tiled_gemm" 0 and in the host build)
+  template <class F>
+  void run_rows(long rows, const F& f) {
+    if (rows <= 0) return;
+#ifndef DHG_HOSTSIM
+    if (g_use_tiled) {
+      long blocks = (rows + 7) / 8;
+      if (blocks > grid_cap) blocks = grid_cap;
+      ts_row_kernel<F><<<(unsigned)blocks, 256, 0, st>>>(rows, f);
+      ++launches;
+      return;
+    }
+#endif
+    run(rows, f);
   }
   void zero(void* p, size_t bytes) {
     if (!bytes) return;
@@ -138,7 +167,9 @@ void to_dev(void* dst, const void* src, size_t bytes) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// the one contraction: C[z](i, j) (+)= alpha * sum_k A[z](i, k) B[z](k, j) (+ bias[j]),  z = z1 * Z2 + z2
+// the one contraction:  C[z](i, j) (+)= alpha * sum_tap sum_k A[z](i + shift_tap, k) B_tap[z](k, j) (+ bias[j]),
+// z = z1 * Z2 + z2.  taps = 1 for everything but a k3 convolution, where tap t reads row i + shift0 + t * dshift of the
+// same batch item (= sample) and rows outside [0, M) are the zero padding (cnn.py:32-47: padding 1).
 // ------------------------------------------------------------------------------------------------------------------
 struct Bmm {
   const float* A = nullptr;
@@ -149,6 +180,8 @@ struct Bmm {
   long sAz1 = 0, sAz2 = 0, sAi = 0, sAk = 0;
   long sBz1 = 0, sBz2 = 0, sBk = 0, sBj = 0;
   long sCz1 = 0, sCz2 = 0, sCi = 0, sCj = 0;
+  int taps = 1, shift0 = 0, dshift = 0;
+  long sBtap = 0;
   float alpha = 1.f;
   int mode = 0;   // 0: C = v   1: C += v (one writer per element)   2: atomicAdd(C, v) (batch items share C)
 };
@@ -179,12 +212,19 @@ struct BmmBody {
     float acc[4][4];
     for (int a = 0; a < 4; ++a)
       for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-    for (int k = 0; k < p.K; ++k) {
-      float av[4], bv[4];
-      for (int a = 0; a < 4; ++a) av[a] = (i0 + a < p.M) ? A[(long)(i0 + a) * p.sAi + (long)k * p.sAk] : 0.f;
-      for (int b = 0; b < 4; ++b) bv[b] = (j0 + b < p.N) ? B[(long)k * p.sBk + (long)(j0 + b) * p.sBj] : 0.f;
-      for (int a = 0; a < 4; ++a)
-        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+    for (int t = 0; t < p.taps; ++t) {
+      const int sh = p.shift0 + t * p.dshift;
+      const float* Bt = B + t * p.sBtap;
+      for (int k = 0; k < p.K; ++k) {
+        float av[4], bv[4];
+        for (int a = 0; a < 4; ++a) {
+          const int row = i0 + a + sh;
+          av[a] = (i0 + a < p.M && row >= 0 && row < p.M) ? A[(long)row * p.sAi + (long)k * p.sAk] : 0.f;
+        }
+        for (int b = 0; b < 4; ++b) bv[b] = (j0 + b < p.N) ? Bt[(long)k * p.sBk + (long)(j0 + b) * p.sBj] : 0.f;
+        for (int a = 0; a < 4; ++a)
+          for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+      }
     }
     for (int a = 0; a < 4; ++a)
       for (int b = 0; b < 4; ++b)
@@ -193,57 +233,109 @@ struct BmmBody {
 };
 
 #ifndef DHG_HOSTSIM
-// 64 x 64 tile of C per CTA, 16-deep k slabs through shared memory, 4 x 4 per thread.  The slab loads walk whichever
-// of the two operand axes is contiguous, so any of the stride patterns above reads coalesced 64-byte runs or better.
-constexpr int kBM = 64, kBN = 64, kBK = 16;
+// BM x BN tile of C per CTA of 256 threads, TM x TN per thread (in 4-wide groups BM/2 resp. BN/2 apart, so that the
+// shared-memory reads of a warp are two broadcasts and one conflict-free 16-lane run), 16-deep k slabs: the next slab
+// travels from memory into registers while the current one is multiplied.  The slab loads walk whichever of the two
+// operand axes is contiguous, so any of the stride patterns reads whole sectors.
+constexpr int kBK = 16;
+template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(256) ts_bmm_tiled(Bmm p) {
-  __shared__ __align__(16) float As[kBK][kBM + 4];
-  __shared__ __align__(16) float Bs[kBK][kBN + 4];
+  static_assert((BM / TM) * (BN / TN) == 256, "256 threads");
+  constexpr int NX = BN / TN, LA = BM * kBK / 256, LB = BN * kBK / 256, GA = TM / 4, GB = TN / 4;
+  __shared__ __align__(16) float As[kBK][BM + 4];
+  __shared__ __align__(16) float Bs[kBK][BN + 4];
   const int z = blockIdx.z, z1 = z / p.Z2, z2 = z % p.Z2;
   const float* __restrict__ A = p.A + z1 * p.sAz1 + z2 * p.sAz2;
   const float* __restrict__ B = p.B + z1 * p.sBz1 + z2 * p.sBz2;
   float* C = p.C + z1 * p.sCz1 + z2 * p.sCz2;
-  const int bi = blockIdx.y * kBM, bj = blockIdx.x * kBN;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int bi = blockIdx.y * BM, bj = blockIdx.x * BN;
+  const int tid = threadIdx.x, tx = tid % NX, ty = tid / NX;
   const bool a_k_fast = p.sAk == 1, b_k_fast = p.sBk == 1 && p.sBj != 1;
-  float acc[4][4];
+  const int nk = (p.K + kBK - 1) / kBK, ns = nk * p.taps;
+  float acc[TM][TN];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < TM; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-  for (int k0 = 0; k0 < p.K; k0 += kBK) {
+    for (int b = 0; b < TN; ++b) acc[a][b] = 0.f;
+  float ra[LA], rb[LB];
+  auto fetch = [&](int s) {
+    const int tap = s / nk, k0 = (s - tap * nk) * kBK, sh = p.shift0 + tap * p.dshift;
+    const float* __restrict__ Bt = B + tap * p.sBtap;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < LA; ++r) {
       const int e = tid + 256 * r;
       int kk, ii;
-      if (a_k_fast) { kk = e & 15; ii = e >> 4; } else { ii = e & 63; kk = e >> 6; }
-      const int gi = bi + ii, gk = k0 + kk;
-      As[kk][ii] = (gi < p.M && gk < p.K) ? A[(long)gi * p.sAi + (long)gk * p.sAk] : 0.f;
-      int kb, jj;
-      if (b_k_fast) { kb = e & 15; jj = e >> 4; } else { jj = e & 63; kb = e >> 6; }
-      const int gj = bj + jj, gkb = k0 + kb;
-      Bs[kb][jj] = (gj < p.N && gkb < p.K) ? B[(long)gkb * p.sBk + (long)gj * p.sBj] : 0.f;
+      if (a_k_fast) { kk = e & 15; ii = e >> 4; } else { ii = e % BM; kk = e / BM; }
+      const int gi = bi + ii, gk = k0 + kk, row = gi + sh;
+      ra[r] = (gi < p.M && gk < p.K && row >= 0 && row < p.M) ? A[(long)row * p.sAi + (long)gk * p.sAk] : 0.f;
     }
+#pragma unroll
+    for (int r = 0; r < LB; ++r) {
+      const int e = tid + 256 * r;
+      int kb, jj;
+      if (b_k_fast) { kb = e & 15; jj = e >> 4; } else { jj = e % BN; kb = e / BN; }
+      const int gj = bj + jj, gkb = k0 + kb;
+      rb[r] = (gj < p.N && gkb < p.K) ? Bt[(long)gkb * p.sBk + (long)gj * p.sBj] : 0.f;
+    }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int r = 0; r < LA; ++r) {
+      const int e = tid + 256 * r;
+      if (a_k_fast) As[e & 15][e >> 4] = ra[r]; else As[e / BM][e % BM] = ra[r];
+    }
+#pragma unroll
+    for (int r = 0; r < LB; ++r) {
+      const int e = tid + 256 * r;
+      if (b_k_fast) Bs[e & 15][e >> 4] = rb[r]; else Bs[e / BN][e % BN] = rb[r];
+    }
+  };
+  if (ns > 0) fetch(0);
+  for (int s = 0; s < ns; ++s) {
+    stash();
     __syncthreads();
+    if (s + 1 < ns) fetch(s + 1);
 #pragma unroll
     for (int kk = 0; kk < kBK; ++kk) {
-      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-      const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+      float av[TM], bv[TN];
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int g = 0; g < GA; ++g) {
+        const float4 v = *reinterpret_cast<const float4*>(&As[kk][g * (BM / GA) + ty * 4]);
+        av[4 * g] = v.x; av[4 * g + 1] = v.y; av[4 * g + 2] = v.z; av[4 * g + 3] = v.w;
+      }
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+      for (int g = 0; g < GB; ++g) {
+        const float4 v = *reinterpret_cast<const float4*>(&Bs[kk][g * (BN / GB) + tx * 4]);
+        bv[4 * g] = v.x; bv[4 * g + 1] = v.y; bv[4 * g + 2] = v.z; bv[4 * g + 3] = v.w;
+      }
+#pragma unroll
+      for (int a = 0; a < TM; ++a)
+#pragma unroll
+        for (int b = 0; b < TN; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < TM; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int i = bi + ty * 4 + a, j = bj + tx * 4 + b;
+    for (int b = 0; b < TN; ++b) {
+      const int i = bi + (a / 4) * (BM / GA) + ty * 4 + (a & 3), j = bj + (b / 4) * (BN / GB) + tx * 4 + (b & 3);
       if (i < p.M && j < p.N) bmm_store(p, C, i, j, acc[a][b]);
     }
+}
+
+// tile choice: the largest tile that still gives every SM about two CTAs and does not multiply mostly padding
+template <int BM, int BN, int TM, int TN>
+bool try_tiled(Launcher& L, const Bmm& p, bool force) {
+  const long gx = (p.N + BN - 1) / BN, gy = (p.M + BM - 1) / BM, gz = (long)p.Z1 * p.Z2;
+  if (gz > 65535 || gy > 65535) return false;
+  if (!force) {
+    if (gx * gy * gz < 2 * 148) return false;
+    if ((double)gx * BN * gy * BM > 1.34 * (double)p.M * p.N) return false;
+  }
+  ts_bmm_tiled<BM, BN, TM, TN><<<dim3((unsigned)gx, (unsigned)gy, (unsigned)gz), 256, 0, L.st>>>(p);
+  ++L.launches;
+  return true;
 }
 #endif
 
@@ -251,11 +343,12 @@ void run_bmm(Launcher& L, const Bmm& p) {
   if (p.M <= 0 || p.N <= 0 || p.Z1 <= 0 || p.Z2 <= 0) return;
   if (p.K <= 0 && p.mode != 0) return;
 #ifndef DHG_HOSTSIM
-  if (g_use_tiled && (long)p.Z1 * p.Z2 <= 65535 && (p.M + kBM - 1) / kBM <= 65535) {
-    dim3 grid((p.N + kBN - 1) / kBN, (p.M + kBM - 1) / kBM, p.Z1 * p.Z2);
-    ts_bmm_tiled<<<grid, 256, 0, L.st>>>(p);
-    ++L.launches;
-    return;
+  if (g_use_tiled == 1) {
+    if (try_tiled<128, 128, 8, 8>(L, p, false) || try_tiled<128, 64, 8, 4>(L, p, false) || try_tiled<64, 128, 4, 8>(L, p, false) ||
+        try_tiled<64, 64, 4, 4>(L, p, true))
+      return;
+  } else if (g_use_tiled == 2) {   // measurement: the small tile only
+    if (try_tiled<64, 64, 4, 4>(L, p, true)) return;
   }
 #endif
   BmmBody f;
@@ -292,14 +385,15 @@ struct FilmBwdX {
   const float* gy; const float* gam; float* gx; int C, period;
   TS_FN void operator()(long i) const { const long b = i / ((long)C * period); gx[i] += gy[i] * gam[b * C + (i % C)]; }
 };
-struct FilmBwdCond {   // one thread per (b, c): sums over the sample's rows
-  const float* gy; const float* x; float* ggam; float* gbet; int C, period;
+struct FilmBwdCond {   // one thread per (b, 32-row chunk, c): partial sums over the chunk, atomics into [B, C]
+  const float* gy; const float* x; float* ggam; float* gbet; int C, period, chunks;
   TS_FN void operator()(long i) const {
-    const long b = i / C; const int c = (int)(i % C);
+    const int c = (int)(i % C); const long q = i / C; const int ch = (int)(q % chunks); const long b = q / chunks;
+    const int t0 = ch * 32, t1 = t0 + 32 < period ? t0 + 32 : period;
     const float* g = gy + b * period * (long)C + c; const float* xv = x + b * period * (long)C + c;
     float sg = 0.f, sb = 0.f;
-    for (int t = 0; t < period; ++t) { const float d = g[(long)t * C]; sg = fmaf(d, xv[(long)t * C], sg); sb += d; }
-    ggam[i] += sg; gbet[i] += sb;
+    for (int t = t0; t < t1; ++t) { const float d = g[(long)t * C]; sg = fmaf(d, xv[(long)t * C], sg); sb += d; }
+    ts_atomic_add(ggam + b * C + c, sg); ts_atomic_add(gbet + b * C + c, sb);
   }
 };
 // LayerNorm(eps 1e-6, no affine) (model.py:25, text_style.py:80); one thread per row
@@ -312,6 +406,15 @@ struct LnFwd {
     const float rs = 1.f / sqrtf(v + 1e-6f); rstd[r] = rs;
     for (int c = 0; c < C; ++c) yr[c] = (xr[c] - m) * rs;
   }
+#ifndef DHG_HOSTSIM
+  __device__ void warp(long r, int lane) const {
+    const float* xr = x + r * C; float* yr = y + r * C;
+    float m = 0.f; for (int c = lane; c < C; c += 32) m += xr[c]; m = warp_sum(m) / C;
+    float v = 0.f; for (int c = lane; c < C; c += 32) { const float d = xr[c] - m; v = fmaf(d, d, v); } v = warp_sum(v) / C;
+    const float rs = 1.f / sqrtf(v + 1e-6f); if (lane == 0) rstd[r] = rs;
+    for (int c = lane; c < C; c += 32) yr[c] = (xr[c] - m) * rs;
+  }
+#endif
 };
 struct LnBwd {
   const float* y; const float* gy; const float* rstd; float* gx; int C;
@@ -321,6 +424,15 @@ struct LnBwd {
     const float rs = rstd[r];
     for (int c = 0; c < C; ++c) gxr[c] += rs * (gr[c] - m1 - yr[c] * m2);
   }
+#ifndef DHG_HOSTSIM
+  __device__ void warp(long r, int lane) const {
+    const float* yr = y + r * C; const float* gr = gy + r * C; float* gxr = gx + r * C;
+    float m1 = 0.f, m2 = 0.f; for (int c = lane; c < C; c += 32) { m1 += gr[c]; m2 = fmaf(gr[c], yr[c], m2); }
+    m1 = warp_sum(m1) / C; m2 = warp_sum(m2) / C;
+    const float rs = rstd[r];
+    for (int c = lane; c < C; c += 32) gxr[c] += rs * (gr[c] - m1 - yr[c] * m2);
+  }
+#endif
 };
 // softmax over the keys of one (b, h, query) row, with the additive -1e9 padding mask (attention.py:43, utils/nn.py:178-191)
 struct SoftmaxFwd {
@@ -333,6 +445,17 @@ struct SoftmaxFwd {
     float sum = 0.f; for (int j = 0; j < Tk; ++j) { const float e = expf(pr[j] - mx); pr[j] = e; sum += e; }
     const float inv = 1.f / sum; for (int j = 0; j < Tk; ++j) pr[j] *= inv;
   }
+#ifndef DHG_HOSTSIM
+  __device__ void warp(long r, int lane) const {
+    const float* sr = s + r * Tk; float* pr = p + r * Tk;
+    const int64_t* id = ids ? ids + (r / rows_per_b) * Tk : nullptr;
+    float mx = -INFINITY;
+    for (int j = lane; j < Tk; j += 32) { const float v = sr[j] + ((id && id[j] == 0) ? -1e9f : 0.f); pr[j] = v; mx = fmaxf(mx, v); }
+    mx = warp_max(mx);
+    float sum = 0.f; for (int j = lane; j < Tk; j += 32) { const float e = expf(pr[j] - mx); pr[j] = e; sum += e; }
+    const float inv = 1.f / warp_sum(sum); for (int j = lane; j < Tk; j += 32) pr[j] *= inv;
+  }
+#endif
 };
 struct SoftmaxBwd {
   const float* p; const float* gp; float* gs; int Tk;
@@ -341,6 +464,14 @@ struct SoftmaxBwd {
     float d = 0.f; for (int j = 0; j < Tk; ++j) d = fmaf(pr[j], gr[j], d);
     for (int j = 0; j < Tk; ++j) go[j] += pr[j] * (gr[j] - d);
   }
+#ifndef DHG_HOSTSIM
+  __device__ void warp(long r, int lane) const {
+    const float* pr = p + r * Tk; const float* gr = gp + r * Tk; float* go = gs + r * Tk;
+    float d = 0.f; for (int j = lane; j < Tk; j += 32) d = fmaf(pr[j], gr[j], d);
+    d = warp_sum(d);
+    for (int j = lane; j < Tk; j += 32) go[j] += pr[j] * (gr[j] - d);
+  }
+#endif
 };
 // AvgPool1d(2) / nearest x2 over the rows of each sample (model.py:93-99, 163)
 struct PoolFwd { const float* x; float* y; int C; TS_FN void operator()(long i) const { const long r = i / C; const int c = (int)(i % C); y[i] = 0.5f * (x[(2 * r) * C + c] + x[(2 * r + 1) * C + c]); } };
@@ -479,7 +610,7 @@ struct dhg_trainer {
   Ten ln(const Ten& x) {
     Ten y = make(x.rows, x.C, x.period);
     Ten rs = make(x.rows, 1, x.period, false);
-    rec([=](Launcher& L) { L.run(x.rows, LnFwd{x.v, y.v, rs.v, x.C}); }, [=](Launcher& L) { if (x.g) L.run(x.rows, LnBwd{y.v, y.g, rs.v, x.g, x.C}); });
+    rec([=](Launcher& L) { L.run_rows(x.rows, LnFwd{x.v, y.v, rs.v, x.C}); }, [=](Launcher& L) { if (x.g) L.run_rows(x.rows, LnBwd{y.v, y.g, rs.v, x.g, x.C}); });
     return y;
   }
   // weight-gradient batching of a Linear: the rows are cut into Z equal runs of whole samples, about 512 rows each (one
@@ -528,25 +659,22 @@ struct dhg_trainer {
     const long have = lay.index.count(name + ".weight") ? lay.items[lay.index[name + ".weight"]].numel : -1;
     if (have != (long)N * K * 3) err = "shape mismatch at " + name;
     auto range = [=](int tap, int& lo, int& hi) { lo = tap == 0 ? 1 : 0; hi = tap == 2 ? Tn - 1 : Tn; };
-    rec([=](Launcher& L) {
-          const int order[3] = {1, 0, 2};
-          for (int o = 0; o < 3; ++o) {
-            const int tap = order[o]; int lo, hi; range(tap, lo, hi);
-            Bmm p; p.A = x.v + (long)(lo + tap - 1) * K; p.B = W + tap; p.C = y.v + (long)lo * N; p.bias = o == 0 ? b : nullptr;
-            p.M = hi - lo; p.N = N; p.K = K; p.Z1 = nb; p.mode = o == 0 ? 0 : 1;
-            p.sAz1 = (long)Tn * K; p.sAi = K; p.sAk = 1; p.sBk = 3; p.sBj = 3L * K; p.sCz1 = (long)Tn * N; p.sCi = N; p.sCj = 1;
-            run_bmm(L, p);
-          }
+    rec([=](Launcher& L) {   // y[t, n] = b[n] + sum_tap sum_k x[t + tap - 1, k] W[n, k, tap], one batch item per sample
+          Bmm p; p.A = x.v; p.B = W; p.C = y.v; p.bias = b; p.M = Tn; p.N = N; p.K = K; p.Z1 = nb;
+          p.taps = 3; p.shift0 = -1; p.dshift = 1; p.sBtap = 1;
+          p.sAz1 = (long)Tn * K; p.sAi = K; p.sAk = 1; p.sBk = 3; p.sBj = 3L * K; p.sCz1 = (long)Tn * N; p.sCi = N; p.sCj = 1;
+          run_bmm(L, p);
         },
         [=](Launcher& L) {
-          for (int tap = 0; tap < 3; ++tap) {
+          if (x.g) {   // dx[t, k] += sum_tap sum_n dy[t - (tap - 1), n] W[n, k, tap]
+            Bmm p; p.A = y.g; p.B = W; p.C = x.g; p.M = Tn; p.N = K; p.K = N; p.Z1 = nb; p.mode = 1;
+            p.taps = 3; p.shift0 = 1; p.dshift = -1; p.sBtap = 1;
+            p.sAz1 = (long)Tn * N; p.sAi = N; p.sAk = 1; p.sBk = 3L * K; p.sBj = 3; p.sCz1 = (long)Tn * K; p.sCi = K; p.sCj = 1;
+            run_bmm(L, p);
+          }
+          for (int tap = 0; tap < 3; ++tap) {   // dW[n, k, tap] += sum_b sum_t dy[t, n] x[t + tap - 1, k]
             int lo, hi; range(tap, lo, hi);
-            if (x.g) {   // dx[t + tap - 1, k] += sum_n dy[t, n] W[n, k, tap]
-              Bmm p; p.A = y.g + (long)lo * N; p.B = W + tap; p.C = x.g + (long)(lo + tap - 1) * K; p.M = hi - lo; p.N = K; p.K = N; p.Z1 = nb; p.mode = 1;
-              p.sAz1 = (long)Tn * N; p.sAi = N; p.sAk = 1; p.sBk = 3L * K; p.sBj = 3; p.sCz1 = (long)Tn * K; p.sCi = K; p.sCj = 1;
-              run_bmm(L, p);
-            }
-            Bmm q; q.A = y.g + (long)lo * N; q.B = x.v + (long)(lo + tap - 1) * K; q.C = gW + tap; q.M = N; q.N = K; q.K = hi - lo; q.Z1 = nb; q.mode = 2;   // dW[n, k, tap]
+            Bmm q; q.A = y.g + (long)lo * N; q.B = x.v + (long)(lo + tap - 1) * K; q.C = gW + tap; q.M = N; q.N = K; q.K = hi - lo; q.Z1 = nb; q.mode = 2;
             q.sAz1 = (long)Tn * N; q.sAi = 1; q.sAk = N; q.sBz1 = (long)Tn * K; q.sBk = K; q.sBj = 1; q.sCz1 = 0; q.sCi = 3L * K; q.sCj = 3;
             run_bmm(L, q);
           }
@@ -563,7 +691,8 @@ struct dhg_trainer {
     rec([=](Launcher& L) { L.run(x.n(), FilmFwd{x.v, gam.v, bet.v, y.v, x.C, x.period}); },
         [=](Launcher& L) {
           if (x.g) L.run(x.n(), FilmBwdX{y.g, gam.v, x.g, x.C, x.period});
-          L.run((long)nb * x.C, FilmBwdCond{y.g, x.v, gam.g, bet.g, x.C, x.period});
+          const int chunks = (x.period + 31) / 32;
+          L.run((long)nb * chunks * x.C, FilmBwdCond{y.g, x.v, gam.g, bet.g, x.C, x.period, chunks});
         });
     return y;
   }
@@ -582,7 +711,7 @@ struct dhg_trainer {
           Bmm a; a.A = q.v; a.B = k.v; a.C = s.v; a.M = Tq; a.N = Tk; a.K = D; a.Z1 = nb; a.Z2 = heads; a.alpha = scale;   // S = scale Q K^T
           a.sAz1 = sQ; a.sAz2 = D; a.sAi = dm; a.sAk = 1; a.sBz1 = sK; a.sBz2 = D; a.sBk = 1; a.sBj = dm; a.sCz1 = sS1; a.sCz2 = sS2; a.sCi = Tk; a.sCj = 1;
           run_bmm(L, a);
-          L.run(s.rows, SoftmaxFwd{s.v, pr.v, mask_ids, Tk, (long)heads * Tq});
+          L.run_rows(s.rows, SoftmaxFwd{s.v, pr.v, mask_ids, Tk, (long)heads * Tq});
           Bmm c; c.A = pr.v; c.B = v.v; c.C = o.v; c.M = Tq; c.N = D; c.K = Tk; c.Z1 = nb; c.Z2 = heads;                    // O = P V
           c.sAz1 = sS1; c.sAz2 = sS2; c.sAi = Tk; c.sAk = 1; c.sBz1 = sK; c.sBz2 = D; c.sBk = dm; c.sBj = 1; c.sCz1 = sQ; c.sCz2 = D; c.sCi = dm; c.sCj = 1;
           run_bmm(L, c);
@@ -594,7 +723,7 @@ struct dhg_trainer {
           Bmm b; b.A = o.g; b.B = v.v; b.C = pr.g; b.M = Tq; b.N = Tk; b.K = D; b.Z1 = nb; b.Z2 = heads; b.mode = 1;          // dP += dO V^T
           b.sAz1 = sQ; b.sAz2 = D; b.sAi = dm; b.sAk = 1; b.sBz1 = sK; b.sBz2 = D; b.sBk = 1; b.sBj = dm; b.sCz1 = sS1; b.sCz2 = sS2; b.sCi = Tk; b.sCj = 1;
           run_bmm(L, b);
-          L.run(s.rows, SoftmaxBwd{pr.v, pr.g, s.g, Tk});
+          L.run_rows(s.rows, SoftmaxBwd{pr.v, pr.g, s.g, Tk});
           Bmm c; c.A = s.g; c.B = k.v; c.C = q.g; c.M = Tq; c.N = D; c.K = Tk; c.Z1 = nb; c.Z2 = heads; c.mode = 1; c.alpha = scale;   // dQ += scale dS K
           c.sAz1 = sS1; c.sAz2 = sS2; c.sAi = Tk; c.sAk = 1; c.sBz1 = sK; c.sBz2 = D; c.sBk = dm; c.sBj = 1; c.sCz1 = sQ; c.sCz2 = D; c.sCi = dm; c.sCj = 1;
           run_bmm(L, c);
