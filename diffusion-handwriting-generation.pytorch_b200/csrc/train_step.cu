@@ -236,10 +236,17 @@ struct BmmBody {
 // BM x BN tile of C per CTA of 256 threads, TM x TN per thread (in 4-wide groups BM/2 resp. BN/2 apart, so that the
 // shared-memory reads of a warp are two broadcasts and one conflict-free 16-lane run), 16-deep k slabs: the next slab
 // travels from memory into registers while the current one is multiplied.  The slab loads walk whichever of the two
-// operand axes is contiguous, so any of the stride patterns reads whole sectors.
+// operand axes is contiguous -- as 16-byte vectors when the strides and the base allow it -- and the tile is stored /
+// accumulated / atomically added as 16-byte vectors when C's rows are contiguous (red.global.add.v4.f32 for the
+// weight gradients).
 constexpr int kBK = 16;
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ bool al4(long v) { return (v & 3) == 0; }
+__device__ __forceinline__ bool al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
 template <int BM, int BN, int TM, int TN>
-__global__ void __launch_bounds__(256) ts_bmm_tiled(Bmm p) {
+__global__ void __launch_bounds__(256, (BM * BN <= 4096) ? 4 : 2) ts_bmm_tiled(Bmm p) {
   static_assert((BM / TM) * (BN / TN) == 256, "256 threads");
   constexpr int NX = BN / TN, LA = BM * kBK / 256, LB = BN * kBK / 256, GA = TM / 4, GB = TN / 4;
   __shared__ __align__(16) float As[kBK][BM + 4];
@@ -250,7 +257,12 @@ __global__ void __launch_bounds__(256) ts_bmm_tiled(Bmm p) {
   float* C = p.C + z1 * p.sCz1 + z2 * p.sCz2;
   const int bi = blockIdx.y * BM, bj = blockIdx.x * BN;
   const int tid = threadIdx.x, tx = tid % NX, ty = tid / NX;
-  const bool a_k_fast = p.sAk == 1, b_k_fast = p.sBk == 1 && p.sBj != 1;
+  // operand walk: 0 scalar along i / j, 1 scalar along k, 2 vector along k, 3 vector along i / j
+  int am = p.sAk == 1 ? 1 : 0, bm = (p.sBk == 1 && p.sBj != 1) ? 1 : 0;
+  if (am == 1 && al4(p.K) && al4(p.sAi) && al16(A)) am = 2;
+  if (am == 0 && p.sAi == 1 && p.taps == 1 && p.shift0 == 0 && al4(p.M) && al4(p.sAk) && al16(A)) am = 3;
+  if (bm == 1 && al4(p.K) && al4(p.sBj) && al4(p.sBtap) && al16(B)) bm = 2;
+  if (bm == 0 && p.sBj == 1 && al4(p.N) && al4(p.sBk) && al4(p.sBtap) && al16(B)) bm = 3;
   const int nk = (p.K + kBK - 1) / kBK, ns = nk * p.taps;
   float acc[TM][TN];
 #pragma unroll
@@ -261,33 +273,95 @@ __global__ void __launch_bounds__(256) ts_bmm_tiled(Bmm p) {
   auto fetch = [&](int s) {
     const int tap = s / nk, k0 = (s - tap * nk) * kBK, sh = p.shift0 + tap * p.dshift;
     const float* __restrict__ Bt = B + tap * p.sBtap;
+    if (am >= 2) {
 #pragma unroll
-    for (int r = 0; r < LA; ++r) {
-      const int e = tid + 256 * r;
-      int kk, ii;
-      if (a_k_fast) { kk = e & 15; ii = e >> 4; } else { ii = e % BM; kk = e / BM; }
-      const int gi = bi + ii, gk = k0 + kk, row = gi + sh;
-      ra[r] = (gi < p.M && gk < p.K && row >= 0 && row < p.M) ? A[(long)row * p.sAi + (long)gk * p.sAk] : 0.f;
+      for (int r = 0; r < LA / 4; ++r) {
+        const int e = tid + 256 * r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (am == 2) {
+          const int gi = bi + (e >> 2), gk = k0 + 4 * (e & 3), row = gi + sh;
+          if (gi < p.M && gk < p.K && row >= 0 && row < p.M) v = *reinterpret_cast<const float4*>(A + (long)row * p.sAi + gk);
+        } else {
+          const int gi = bi + 4 * (e % (BM / 4)), gk = k0 + e / (BM / 4);
+          if (gi < p.M && gk < p.K) v = *reinterpret_cast<const float4*>(A + gi + (long)gk * p.sAk);
+        }
+        ra[4 * r] = v.x; ra[4 * r + 1] = v.y; ra[4 * r + 2] = v.z; ra[4 * r + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < LA; ++r) {
+        const int e = tid + 256 * r;
+        int kk, ii;
+        if (am == 1) { kk = e & 15; ii = e >> 4; } else { ii = e % BM; kk = e / BM; }
+        const int gi = bi + ii, gk = k0 + kk, row = gi + sh;
+        ra[r] = (gi < p.M && gk < p.K && row >= 0 && row < p.M) ? A[(long)row * p.sAi + (long)gk * p.sAk] : 0.f;
+      }
     }
+    if (bm >= 2) {
 #pragma unroll
-    for (int r = 0; r < LB; ++r) {
-      const int e = tid + 256 * r;
-      int kb, jj;
-      if (b_k_fast) { kb = e & 15; jj = e >> 4; } else { jj = e % BN; kb = e / BN; }
-      const int gj = bj + jj, gkb = k0 + kb;
-      rb[r] = (gj < p.N && gkb < p.K) ? Bt[(long)gkb * p.sBk + (long)gj * p.sBj] : 0.f;
+      for (int r = 0; r < LB / 4; ++r) {
+        const int e = tid + 256 * r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bm == 2) {
+          const int gj = bj + (e >> 2), gk = k0 + 4 * (e & 3);
+          if (gj < p.N && gk < p.K) v = *reinterpret_cast<const float4*>(Bt + gk + (long)gj * p.sBj);
+        } else {
+          const int gj = bj + 4 * (e % (BN / 4)), gk = k0 + e / (BN / 4);
+          if (gj < p.N && gk < p.K) v = *reinterpret_cast<const float4*>(Bt + (long)gk * p.sBk + gj);
+        }
+        rb[4 * r] = v.x; rb[4 * r + 1] = v.y; rb[4 * r + 2] = v.z; rb[4 * r + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < LB; ++r) {
+        const int e = tid + 256 * r;
+        int kb, jj;
+        if (bm == 1) { kb = e & 15; jj = e >> 4; } else { jj = e % BN; kb = e / BN; }
+        const int gj = bj + jj, gkb = k0 + kb;
+        rb[r] = (gj < p.N && gkb < p.K) ? Bt[(long)gkb * p.sBk + (long)gj * p.sBj] : 0.f;
+      }
     }
   };
   auto stash = [&]() {
+    if (am == 2) {
 #pragma unroll
-    for (int r = 0; r < LA; ++r) {
-      const int e = tid + 256 * r;
-      if (a_k_fast) As[e & 15][e >> 4] = ra[r]; else As[e / BM][e % BM] = ra[r];
+      for (int r = 0; r < LA / 4; ++r) {
+        const int e = tid + 256 * r;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) As[4 * (e & 3) + q][e >> 2] = ra[4 * r + q];
+      }
+    } else if (am == 3) {
+#pragma unroll
+      for (int r = 0; r < LA / 4; ++r) {
+        const int e = tid + 256 * r;
+        *reinterpret_cast<float4*>(&As[e / (BM / 4)][4 * (e % (BM / 4))]) = make_float4(ra[4 * r], ra[4 * r + 1], ra[4 * r + 2], ra[4 * r + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < LA; ++r) {
+        const int e = tid + 256 * r;
+        if (am == 1) As[e & 15][e >> 4] = ra[r]; else As[e / BM][e % BM] = ra[r];
+      }
     }
+    if (bm == 2) {
 #pragma unroll
-    for (int r = 0; r < LB; ++r) {
-      const int e = tid + 256 * r;
-      if (b_k_fast) Bs[e & 15][e >> 4] = rb[r]; else Bs[e / BN][e % BN] = rb[r];
+      for (int r = 0; r < LB / 4; ++r) {
+        const int e = tid + 256 * r;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) Bs[4 * (e & 3) + q][e >> 2] = rb[4 * r + q];
+      }
+    } else if (bm == 3) {
+#pragma unroll
+      for (int r = 0; r < LB / 4; ++r) {
+        const int e = tid + 256 * r;
+        *reinterpret_cast<float4*>(&Bs[e / (BN / 4)][4 * (e % (BN / 4))]) = make_float4(rb[4 * r], rb[4 * r + 1], rb[4 * r + 2], rb[4 * r + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < LB; ++r) {
+        const int e = tid + 256 * r;
+        if (bm == 1) Bs[e & 15][e >> 4] = rb[r]; else Bs[e / BN][e % BN] = rb[r];
+      }
     }
   };
   if (ns > 0) fetch(0);
@@ -315,27 +389,59 @@ __global__ void __launch_bounds__(256) ts_bmm_tiled(Bmm p) {
     }
     __syncthreads();
   }
+  const bool cvec = p.sCj == 1 && al4(p.N) && al4(p.sCi) && al16(C);
 #pragma unroll
-  for (int a = 0; a < TM; ++a)
+  for (int a = 0; a < TM; ++a) {
+    const int i = bi + (a / 4) * (BM / GA) + ty * 4 + (a & 3);
+    if (i >= p.M) continue;
 #pragma unroll
-    for (int b = 0; b < TN; ++b) {
-      const int i = bi + (a / 4) * (BM / GA) + ty * 4 + (a & 3), j = bj + (b / 4) * (BN / GB) + tx * 4 + (b & 3);
-      if (i < p.M && j < p.N) bmm_store(p, C, i, j, acc[a][b]);
+    for (int g = 0; g < GB; ++g) {
+      const int j = bj + g * (BN / GB) + tx * 4;
+      if (cvec) {
+        if (j >= p.N) continue;
+        float* c = C + (long)i * p.sCi + j;
+        float4 v = make_float4(p.alpha * acc[a][4 * g], p.alpha * acc[a][4 * g + 1], p.alpha * acc[a][4 * g + 2], p.alpha * acc[a][4 * g + 3]);
+        if (p.mode == 0) {
+          if (p.bias) { v.x += p.bias[j]; v.y += p.bias[j + 1]; v.z += p.bias[j + 2]; v.w += p.bias[j + 3]; }
+          *reinterpret_cast<float4*>(c) = v;
+        } else if (p.mode == 1) {
+          const float4 o = *reinterpret_cast<const float4*>(c);
+          *reinterpret_cast<float4*>(c) = make_float4(o.x + v.x, o.y + v.y, o.z + v.z, o.w + v.w);
+        } else {
+          red_add_v4(c, v.x, v.y, v.z, v.w);
+        }
+      } else {
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (j + b < p.N) bmm_store(p, C, i, j + b, acc[a][4 * g + b]);
+      }
     }
+  }
 }
 
-// tile choice: the largest tile that still gives every SM about two CTAs and does not multiply mostly padding
+// tile choice: predicted time = waves over the 148 SMs x work of a tile / relative speed of the tile shape
 template <int BM, int BN, int TM, int TN>
-bool try_tiled(Launcher& L, const Bmm& p, bool force) {
+void launch_tiled(Launcher& L, const Bmm& p) {
   const long gx = (p.N + BN - 1) / BN, gy = (p.M + BM - 1) / BM, gz = (long)p.Z1 * p.Z2;
-  if (gz > 65535 || gy > 65535) return false;
-  if (!force) {
-    if (gx * gy * gz < 2 * 148) return false;
-    if ((double)gx * BN * gy * BM > 1.34 * (double)p.M * p.N) return false;
-  }
   ts_bmm_tiled<BM, BN, TM, TN><<<dim3((unsigned)gx, (unsigned)gy, (unsigned)gz), 256, 0, L.st>>>(p);
   ++L.launches;
-  return true;
+}
+int pick_tile(const Bmm& p) {
+  static const int bm[4] = {128, 128, 64, 64}, bn[4] = {128, 64, 128, 64}, per_sm[4] = {2, 2, 2, 4};
+  static const double speed[4] = {1.0, 0.85, 0.85, 0.62};
+  int best = 3;
+  double best_t = 1e300;
+  for (int c = 0; c < 4; ++c) {
+    const long ctas = (long)((p.N + bn[c] - 1) / bn[c]) * ((p.M + bm[c] - 1) / bm[c]) * p.Z1 * p.Z2;
+    const long slots = 148L * per_sm[c];
+    const double waves = (double)((ctas + slots - 1) / slots);
+    // a partial last wave still costs a full tile time, but fewer CTAs per SM run faster: count it at 0.6 + 0.4 * fill
+    const long rem = ctas % slots;
+    const double last = rem ? 0.6 + 0.4 * (double)rem / slots : 1.0;
+    const double t = (waves - 1.0 + last) * bm[c] * bn[c] * per_sm[c] / speed[c];
+    if (t < best_t) { best_t = t; best = c; }
+  }
+  return best;
 }
 #endif
 
@@ -343,12 +449,14 @@ void run_bmm(Launcher& L, const Bmm& p) {
   if (p.M <= 0 || p.N <= 0 || p.Z1 <= 0 || p.Z2 <= 0) return;
   if (p.K <= 0 && p.mode != 0) return;
 #ifndef DHG_HOSTSIM
-  if (g_use_tiled == 1) {
-    if (try_tiled<128, 128, 8, 8>(L, p, false) || try_tiled<128, 64, 8, 4>(L, p, false) || try_tiled<64, 128, 4, 8>(L, p, false) ||
-        try_tiled<64, 64, 4, 4>(L, p, true))
-      return;
-  } else if (g_use_tiled == 2) {   // measurement: the small tile only
-    if (try_tiled<64, 64, 4, 4>(L, p, true)) return;
+  if (g_use_tiled && (long)p.Z1 * p.Z2 <= 65535 && (p.M + 63) / 64 <= 65535) {
+    switch (g_use_tiled == 2 ? 3 : pick_tile(p)) {   // "tiled_gemm" 2: the small tile only (measurement)
+      case 0: launch_tiled<128, 128, 8, 8>(L, p); break;
+      case 1: launch_tiled<128, 64, 8, 4>(L, p); break;
+      case 2: launch_tiled<64, 128, 4, 8>(L, p); break;
+      default: launch_tiled<64, 64, 4, 4>(L, p); break;
+    }
+    return;
   }
 #endif
   BmmBody f;
@@ -480,6 +588,7 @@ struct UpFwd { const float* x; float* y; int C; TS_FN void operator()(long i) co
 struct UpBwd { const float* gy; float* gx; int C; TS_FN void operator()(long i) const { const long r = i / C; const int c = (int)(i % C); gx[i] += gy[(2 * r) * C + c] + gy[(2 * r + 1) * C + c]; } };
 struct EmbedFwd { const int64_t* ids; const float* E; float* y; int C; TS_FN void operator()(long i) const { y[i] = E[ids[i / C] * C + (i % C)]; } };
 struct EmbedBwd { const int64_t* ids; const float* gy; float* gE; int C; TS_FN void operator()(long i) const { ts_atomic_add(gE + ids[i / C] * C + (i % C), gy[i]); } };
+struct ConvWFold { const float* tmp; float* gW; long nk; TS_FN void operator()(long i) const { const long tap = i % 3, e = i / 3; gW[i] = tmp[tap * nk + e]; } };
 // column sums of a [rows, N] matrix in chunks of 64 rows (bias gradients)
 struct ColSum {
   const float* g; float* out; int rows, N;
@@ -659,6 +768,7 @@ struct dhg_trainer {
     const long have = lay.index.count(name + ".weight") ? lay.items[lay.index[name + ".weight"]].numel : -1;
     if (have != (long)N * K * 3) err = "shape mismatch at " + name;
     auto range = [=](int tap, int& lo, int& hi) { lo = tap == 0 ? 1 : 0; hi = tap == 2 ? Tn - 1 : Tn; };
+    Ten wtmp = make(3 * N, K, 1);   // only its gradient half is used: zeroed with the arena at the start of every backward
     rec([=](Launcher& L) {   // y[t, n] = b[n] + sum_tap sum_k x[t + tap - 1, k] W[n, k, tap], one batch item per sample
           Bmm p; p.A = x.v; p.B = W; p.C = y.v; p.bias = b; p.M = Tn; p.N = N; p.K = K; p.Z1 = nb;
           p.taps = 3; p.shift0 = -1; p.dshift = 1; p.sBtap = 1;
@@ -672,12 +782,13 @@ struct dhg_trainer {
             p.sAz1 = (long)Tn * N; p.sAi = N; p.sAk = 1; p.sBk = 3L * K; p.sBj = 3; p.sCz1 = (long)Tn * K; p.sCi = K; p.sCj = 1;
             run_bmm(L, p);
           }
-          for (int tap = 0; tap < 3; ++tap) {   // dW[n, k, tap] += sum_b sum_t dy[t, n] x[t + tap - 1, k]
+          for (int tap = 0; tap < 3; ++tap) {   // scratch[tap][n][k] += sum_b sum_t dy[t, n] x[t + tap - 1, k]  (k contiguous: vector atomics)
             int lo, hi; range(tap, lo, hi);
-            Bmm q; q.A = y.g + (long)lo * N; q.B = x.v + (long)(lo + tap - 1) * K; q.C = gW + tap; q.M = N; q.N = K; q.K = hi - lo; q.Z1 = nb; q.mode = 2;
-            q.sAz1 = (long)Tn * N; q.sAi = 1; q.sAk = N; q.sBz1 = (long)Tn * K; q.sBk = K; q.sBj = 1; q.sCz1 = 0; q.sCi = 3L * K; q.sCj = 3;
+            Bmm q; q.A = y.g + (long)lo * N; q.B = x.v + (long)(lo + tap - 1) * K; q.C = wtmp.g + (long)tap * N * K; q.M = N; q.N = K; q.K = hi - lo; q.Z1 = nb; q.mode = 2;
+            q.sAz1 = (long)Tn * N; q.sAi = 1; q.sAk = N; q.sBz1 = (long)Tn * K; q.sBk = K; q.sBj = 1; q.sCz1 = 0; q.sCi = K; q.sCj = 1;
             run_bmm(L, q);
           }
+          L.run(3L * N * K, ConvWFold{wtmp.g, gW, (long)N * K});   // dW[n, k, tap] = scratch[tap][n][k]
           L.run((long)N * ((x.rows + 63) / 64), ColSum{y.g, gb, x.rows, N});
         });
     return y;
