@@ -588,6 +588,14 @@ struct UpFwd { const float* x; float* y; int C; TS_FN void operator()(long i) co
 struct UpBwd { const float* gy; float* gx; int C; TS_FN void operator()(long i) const { const long r = i / C; const int c = (int)(i % C); gx[i] += gy[(2 * r) * C + c] + gy[(2 * r + 1) * C + c]; } };
 struct EmbedFwd { const int64_t* ids; const float* E; float* y; int C; TS_FN void operator()(long i) const { y[i] = E[ids[i / C] * C + (i % C)]; } };
 struct EmbedBwd { const int64_t* ids; const float* gy; float* gE; int C; TS_FN void operator()(long i) const { ts_atomic_add(gE + ids[i / C] * C + (i % C), gy[i]); } };
+struct ConvWPack {   // W [n][k][tap] -> wf [tap][k][n], wd [tap][n][k]
+  const float* W; float* wf; float* wd; int N, K;
+  TS_FN void operator()(long i) const {
+    const int tap = (int)(i % 3); const long e = i / 3; const int k = (int)(e % K), n = (int)(e / K);
+    const float v = W[i];
+    wf[((long)tap * K + k) * N + n] = v; wd[((long)tap * N + n) * K + k] = v;
+  }
+};
 struct ConvWFold { const float* tmp; float* gW; long nk; TS_FN void operator()(long i) const { const long tap = i % 3, e = i / 3; gW[i] = tmp[tap * nk + e]; } };
 // column sums of a [rows, N] matrix in chunks of 64 rows (bias gradients)
 struct ColSum {
@@ -769,17 +777,21 @@ struct dhg_trainer {
     if (have != (long)N * K * 3) err = "shape mismatch at " + name;
     auto range = [=](int tap, int& lo, int& hi) { lo = tap == 0 ? 1 : 0; hi = tap == 2 ? Tn - 1 : Tn; };
     Ten wtmp = make(3 * N, K, 1);   // only its gradient half is used: zeroed with the arena at the start of every backward
+    // the checkpoint layout [n][k][tap] has no contiguous axis for either contraction (stride 3 / 3K): repacked once per
+    // forward into [tap][k][n] (forward: n contiguous) and [tap][n][k] (data gradient: k contiguous); 2 x 12 bytes per weight
+    Ten wf = make(3 * K, N, 1, false), wd = make(3 * N, K, 1, false);
     rec([=](Launcher& L) {   // y[t, n] = b[n] + sum_tap sum_k x[t + tap - 1, k] W[n, k, tap], one batch item per sample
-          Bmm p; p.A = x.v; p.B = W; p.C = y.v; p.bias = b; p.M = Tn; p.N = N; p.K = K; p.Z1 = nb;
-          p.taps = 3; p.shift0 = -1; p.dshift = 1; p.sBtap = 1;
-          p.sAz1 = (long)Tn * K; p.sAi = K; p.sAk = 1; p.sBk = 3; p.sBj = 3L * K; p.sCz1 = (long)Tn * N; p.sCi = N; p.sCj = 1;
+          L.run(3L * N * K, ConvWPack{W, wf.v, wd.v, N, K});
+          Bmm p; p.A = x.v; p.B = wf.v; p.C = y.v; p.bias = b; p.M = Tn; p.N = N; p.K = K; p.Z1 = nb;
+          p.taps = 3; p.shift0 = -1; p.dshift = 1; p.sBtap = (long)K * N;
+          p.sAz1 = (long)Tn * K; p.sAi = K; p.sAk = 1; p.sBk = N; p.sBj = 1; p.sCz1 = (long)Tn * N; p.sCi = N; p.sCj = 1;
           run_bmm(L, p);
         },
         [=](Launcher& L) {
           if (x.g) {   // dx[t, k] += sum_tap sum_n dy[t - (tap - 1), n] W[n, k, tap]
-            Bmm p; p.A = y.g; p.B = W; p.C = x.g; p.M = Tn; p.N = K; p.K = N; p.Z1 = nb; p.mode = 1;
-            p.taps = 3; p.shift0 = 1; p.dshift = -1; p.sBtap = 1;
-            p.sAz1 = (long)Tn * N; p.sAi = N; p.sAk = 1; p.sBk = 3L * K; p.sBj = 3; p.sCz1 = (long)Tn * K; p.sCi = K; p.sCj = 1;
+            Bmm p; p.A = y.g; p.B = wd.v; p.C = x.g; p.M = Tn; p.N = K; p.K = N; p.Z1 = nb; p.mode = 1;
+            p.taps = 3; p.shift0 = 1; p.dshift = -1; p.sBtap = (long)N * K;
+            p.sAz1 = (long)Tn * N; p.sAi = N; p.sAk = 1; p.sBk = K; p.sBj = 1; p.sCz1 = (long)Tn * K; p.sCi = K; p.sCj = 1;
             run_bmm(L, p);
           }
           for (int tap = 0; tap < 3; ++tap) {   // scratch[tap][n][k] += sum_b sum_t dy[t, n] x[t + tap - 1, k]  (k contiguous: vector atomics)
