@@ -58,7 +58,8 @@ int sfail(const char* fmt, ...) {
   return 1;
 }
 
-int g_use_tiled = 1;   // GPU build: shared-memory tiled GEMM (0: the per-thread body the host build runs; dhg_trainer_set_option)
+int g_use_tiled = 1;   // GPU build, dhg_trainer_set_option("tiled_gemm"): 1 tiled GEMM with 3 x TF32 tensor-core products, 3 tiled GEMM with fp32 FMAs,
+                       // 2 the latter with the smallest tile only, 0 the per-thread bodies the host build runs (GEMM and per-row kernels)
 
 // ------------------------------------------------------------------------------------------------------------------
 // launch layer
@@ -245,12 +246,30 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 }
 __device__ __forceinline__ bool al4(long v) { return (v & 3) == 0; }
 __device__ __forceinline__ bool al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
-template <int BM, int BN, int TM, int TN>
+// TC = true: the products run on the tensor cores as 3 x TF32 (mma.sync m16n8k8: a = a_hi + a_lo, b = b_hi + b_lo in TF32,
+// a_lo b_hi + a_hi b_lo + a_hi b_hi accumulated in fp32 -- the dropped a_lo b_lo term is 2^-22 relative), which keeps the
+// fp32 contract of the training step; (TM, TN) is then the warp grid (TM x TN = 8 warps, each (BM / TM) x (BN / TN)).
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+template <int BM, int BN, int TM, int TN, bool TC>
 __global__ void __launch_bounds__(256, (BM * BN <= 4096) ? 4 : 2) ts_bmm_tiled(Bmm p) {
-  static_assert((BM / TM) * (BN / TN) == 256, "256 threads");
-  constexpr int NX = BN / TN, LA = BM * kBK / 256, LB = BN * kBK / 256, GA = TM / 4, GB = TN / 4;
-  __shared__ __align__(16) float As[kBK][BM + 4];
-  __shared__ __align__(16) float Bs[kBK][BN + 4];
+  static_assert(TC ? (TM * TN == 8) : ((BM / TM) * (BN / TN) == 256), "256 threads");
+  constexpr int NX = TC ? 1 : BN / TN, LA = BM * kBK / 256, LB = BN * kBK / 256, GA = TC ? 1 : TM / 4, GB = TC ? 1 : TN / 4;
+  constexpr int PAD = TC ? 8 : 4;   // TC: a fragment's (k, row) pairs fall on 32 different banks with a pitch of 8 mod 32
+  constexpr int WM = TC ? BM / TM : 16, WN = TC ? BN / TN : 8, MT = WM / 16, NT = WN / 8;
+  __shared__ __align__(16) float As[kBK][BM + PAD];
+  __shared__ __align__(16) float Bs[kBK][BN + PAD];
   const int z = blockIdx.z, z1 = z / p.Z2, z2 = z % p.Z2;
   const float* __restrict__ A = p.A + z1 * p.sAz1 + z2 * p.sAz2;
   const float* __restrict__ B = p.B + z1 * p.sBz1 + z2 * p.sBz2;
@@ -264,11 +283,18 @@ __global__ void __launch_bounds__(256, (BM * BN <= 4096) ? 4 : 2) ts_bmm_tiled(B
   if (bm == 1 && al4(p.K) && al4(p.sBj) && al4(p.sBtap) && al16(B)) bm = 2;
   if (bm == 0 && p.sBj == 1 && al4(p.N) && al4(p.sBk) && al4(p.sBtap) && al16(B)) bm = 3;
   const int nk = (p.K + kBK - 1) / kBK, ns = nk * p.taps;
-  float acc[TM][TN];
+  float acc[TC ? 1 : TM][TC ? 1 : TN];
+  float accm[TC ? MT : 1][TC ? NT : 1][4];
 #pragma unroll
-  for (int a = 0; a < TM; ++a)
+  for (int a = 0; a < (TC ? 1 : TM); ++a)
 #pragma unroll
-    for (int b = 0; b < TN; ++b) acc[a][b] = 0.f;
+    for (int b = 0; b < (TC ? 1 : TN); ++b) acc[a][b] = 0.f;
+#pragma unroll
+  for (int a = 0; a < (TC ? MT : 1); ++a)
+#pragma unroll
+    for (int b = 0; b < (TC ? NT : 1); ++b) accm[a][b][0] = accm[a][b][1] = accm[a][b][2] = accm[a][b][3] = 0.f;
+  const int lane = tid & 31, wid = tid >> 5, gq = lane >> 2, tq = lane & 3;
+  const int wm0 = TC ? (wid / TN) * WM : 0, wn0 = TC ? (wid % TN) * WN : 0;
   float ra[LA], rb[LB];
   auto fetch = [&](int s) {
     const int tap = s / nk, k0 = (s - tap * nk) * kBK, sh = p.shift0 + tap * p.dshift;
@@ -369,6 +395,32 @@ __global__ void __launch_bounds__(256, (BM * BN <= 4096) ? 4 : 2) ts_bmm_tiled(B
     stash();
     __syncthreads();
     if (s + 1 < ns) fetch(s + 1);
+    if constexpr (TC) {
+#pragma unroll
+      for (int kb = 0; kb < kBK; kb += 8) {
+        uint32_t bh[NT][2], bl[NT][2];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          split_tf32(Bs[kb + tq][wn0 + nt * 8 + gq], bh[nt][0], bl[nt][0]);
+          split_tf32(Bs[kb + tq + 4][wn0 + nt * 8 + gq], bh[nt][1], bl[nt][1]);
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          uint32_t ah[4], al[4];
+          const int r0 = wm0 + mt * 16 + gq;
+          split_tf32(As[kb + tq][r0], ah[0], al[0]);
+          split_tf32(As[kb + tq][r0 + 8], ah[1], al[1]);
+          split_tf32(As[kb + tq + 4][r0], ah[2], al[2]);
+          split_tf32(As[kb + tq + 4][r0 + 8], ah[3], al[3]);
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            mma_tf32(accm[mt][nt], al, bh[nt][0], bh[nt][1]);
+            mma_tf32(accm[mt][nt], ah, bl[nt][0], bl[nt][1]);
+            mma_tf32(accm[mt][nt], ah, bh[nt][0], bh[nt][1]);
+          }
+        }
+      }
+    } else {
 #pragma unroll
     for (int kk = 0; kk < kBK; ++kk) {
       float av[TM], bv[TN];
@@ -387,7 +439,41 @@ __global__ void __launch_bounds__(256, (BM * BN <= 4096) ? 4 : 2) ts_bmm_tiled(B
 #pragma unroll
         for (int b = 0; b < TN; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
     }
+    }
     __syncthreads();
+  }
+  if constexpr (TC) {   // fragment layout of the accumulator: rows gq, gq + 8; columns 2 tq, 2 tq + 1
+    const bool cvec2 = p.sCj == 1 && (p.N & 1) == 0 && (p.sCi & 1) == 0 && (reinterpret_cast<uintptr_t>(C) & 7) == 0;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = bi + wm0 + mt * 16 + gq + 8 * h;
+        if (i >= p.M) continue;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const int j = bj + wn0 + nt * 8 + 2 * tq;
+          const float v0 = accm[mt][nt][2 * h], v1 = accm[mt][nt][2 * h + 1];
+          if (cvec2) {
+            if (j >= p.N) continue;
+            float* c = C + (long)i * p.sCi + j;
+            float2 v = make_float2(p.alpha * v0, p.alpha * v1);
+            if (p.mode == 0) {
+              if (p.bias) { v.x += p.bias[j]; v.y += p.bias[j + 1]; }
+              *reinterpret_cast<float2*>(c) = v;
+            } else if (p.mode == 1) {
+              const float2 o = *reinterpret_cast<const float2*>(c);
+              *reinterpret_cast<float2*>(c) = make_float2(o.x + v.x, o.y + v.y);
+            } else {
+              red_add_v2(c, v.x, v.y);
+            }
+          } else {
+            if (j < p.N) bmm_store(p, C, i, j, v0);
+            if (j + 1 < p.N) bmm_store(p, C, i, j + 1, v1);
+          }
+        }
+      }
+    return;
   }
   const bool cvec = p.sCj == 1 && al4(p.N) && al4(p.sCi) && al16(C);
 #pragma unroll
@@ -420,10 +506,10 @@ __global__ void __launch_bounds__(256, (BM * BN <= 4096) ? 4 : 2) ts_bmm_tiled(B
 }
 
 // tile choice: predicted time = waves over the 148 SMs x work of a tile / relative speed of the tile shape
-template <int BM, int BN, int TM, int TN>
+template <int BM, int BN, int TM, int TN, bool TC>
 void launch_tiled(Launcher& L, const Bmm& p) {
   const long gx = (p.N + BN - 1) / BN, gy = (p.M + BM - 1) / BM, gz = (long)p.Z1 * p.Z2;
-  ts_bmm_tiled<BM, BN, TM, TN><<<dim3((unsigned)gx, (unsigned)gy, (unsigned)gz), 256, 0, L.st>>>(p);
+  ts_bmm_tiled<BM, BN, TM, TN, TC><<<dim3((unsigned)gx, (unsigned)gy, (unsigned)gz), 256, 0, L.st>>>(p);
   ++L.launches;
 }
 int pick_tile(const Bmm& p) {
@@ -450,11 +536,21 @@ void run_bmm(Launcher& L, const Bmm& p) {
   if (p.K <= 0 && p.mode != 0) return;
 #ifndef DHG_HOSTSIM
   if (g_use_tiled && (long)p.Z1 * p.Z2 <= 65535 && (p.M + 63) / 64 <= 65535) {
-    switch (g_use_tiled == 2 ? 3 : pick_tile(p)) {   // "tiled_gemm" 2: the small tile only (measurement)
-      case 0: launch_tiled<128, 128, 8, 8>(L, p); break;
-      case 1: launch_tiled<128, 64, 8, 4>(L, p); break;
-      case 2: launch_tiled<64, 128, 4, 8>(L, p); break;
-      default: launch_tiled<64, 64, 4, 4>(L, p); break;
+    const int tile = g_use_tiled == 2 ? 3 : pick_tile(p);   // "tiled_gemm" 2: the small CUDA-core tile only (measurement)
+    if (g_use_tiled == 1) {   // 3 x TF32 on the tensor cores
+      switch (tile) {
+        case 0: launch_tiled<128, 128, 2, 4, true>(L, p); break;
+        case 1: launch_tiled<128, 64, 4, 2, true>(L, p); break;
+        case 2: launch_tiled<64, 128, 2, 4, true>(L, p); break;
+        default: launch_tiled<64, 64, 2, 4, true>(L, p); break;
+      }
+    } else {                  // "tiled_gemm" 3 (or 2): fp32 FMAs on the CUDA cores
+      switch (tile) {
+        case 0: launch_tiled<128, 128, 8, 8, false>(L, p); break;
+        case 1: launch_tiled<128, 64, 8, 4, false>(L, p); break;
+        case 2: launch_tiled<64, 128, 4, 8, false>(L, p); break;
+        default: launch_tiled<64, 64, 4, 4, false>(L, p); break;
+      }
     }
     return;
   }
