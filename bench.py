@@ -136,7 +136,17 @@ def train_step_leg(dev, B=96, T=480, L=50, steps=5):
         flop = 3.0 * B * (flops_alg_per_sample_step(T, L) + 983_040 * 70 + 1_323_008)   # forward F_exec x 3 for fwd + bwd
         out["b200"] = {"ms_per_step": ms, "samples_per_s": B / (ms * 1e-3), "loss": float(losses[0].item()), "finite": bool(torch.isfinite(losses[0]).item()),
                        "launches_fwd_bwd": int(tr.last_launch_count), "workspace_GB": tr.workspace_bytes / 1e9,
-                       "tflops_fp32_3x_forward": flop / (ms * 1e-3) / 1e12, "dtype": "fp32 (CUDA cores)"}
+                       "tflops_fp32_3x_forward": flop / (ms * 1e-3) / 1e12, "dtype": "fp32 (CUDA cores)",
+                       "frac_of_fp32_fma_peak": flop / (ms * 1e-3) / 1e12 / 72.7, "fp32_fma_peak_tflops": 72.7}
+        # the same step with plain TF32 products on the tensor cores (torch's allow_tf32 precision class, outside the fp32 contract)
+        from dhg_b200 import _abi
+        _abi.lib().dhg_trainer_set_option(b"tiled_gemm", 4)
+        try:
+            ms4, l4 = timed(lambda: tr.train_step(strokes, pen, text, style, alphas, eps, style_keep=keep))
+            out["b200_tf32"] = {"ms_per_step": ms4, "samples_per_s": B / (ms4 * 1e-3), "loss": float(l4[0].item()),
+                                "dtype": "TF32 products (mma.sync), fp32 accumulate and storage"}
+        finally:
+            _abi.lib().dhg_trainer_set_option(b"tiled_gemm", 1)
         tr.close()
         del tr
         torch.cuda.empty_cache()
@@ -169,6 +179,14 @@ def train_step_leg(dev, B=96, T=480, L=50, steps=5):
         out["reference_eager_fp32"] = {"ms_per_step": ms, "samples_per_s": B / (ms * 1e-3), "loss": float(loss.item()),
                                        "flags": {"matmul_allow_tf32": bool(torch.backends.cuda.matmul.allow_tf32),
                                                  "cudnn_allow_tf32": bool(torch.backends.cudnn.allow_tf32)}}
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            ms, loss = timed(ref_step)
+            out["reference_eager_tf32"] = {"ms_per_step": ms, "samples_per_s": B / (ms * 1e-3), "loss": float(loss.item()),
+                                           "flags": {"matmul_allow_tf32": True, "cudnn_allow_tf32": bool(torch.backends.cudnn.allow_tf32)}}
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
         del model, opt
         torch.cuda.empty_cache()
     except Exception as e:   # noqa: BLE001

@@ -58,8 +58,13 @@ int sfail(const char* fmt, ...) {
   return 1;
 }
 
-int g_use_tiled = 1;   // GPU build, dhg_trainer_set_option("tiled_gemm"): 1 tiled GEMM with 3 x TF32 tensor-core products, 3 tiled GEMM with fp32 FMAs,
-                       // 2 the latter with the smallest tile only, 0 the per-thread bodies the host build runs (GEMM and per-row kernels)
+// GPU build, dhg_trainer_set_option("tiled_gemm", v):
+//   1 (default) shared-memory tiled GEMM, fp32 FMAs on the CUDA cores; warp-per-row LayerNorm / softmax
+//   2 the same with the smallest tile only (measurement)
+//   3 tiled GEMM with 3 x TF32 tensor-core products (mma.sync; same fp32 contract; measured: no faster)
+//   4 tiled GEMM with plain TF32 products (one mma per product: what torch's allow_tf32 does; ~1e-3 relative, NOT the fp32 contract)
+//   0 the per-thread bodies the host build runs (GEMM and per-row kernels)
+int g_use_tiled = 1;
 
 // ------------------------------------------------------------------------------------------------------------------
 // launch layer
@@ -262,8 +267,9 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 __device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
-template <int BM, int BN, int TM, int TN, bool TC>
+template <int BM, int BN, int TM, int TN, int TCT>   // TCT: 0 CUDA cores, 3 / 1 tensor cores with that many TF32 products per fp32 product
 __global__ void __launch_bounds__(256, (BM * BN <= 4096) ? 4 : 2) ts_bmm_tiled(Bmm p) {
+  constexpr bool TC = TCT != 0;
   static_assert(TC ? (TM * TN == 8) : ((BM / TM) * (BN / TN) == 256), "256 threads");
   constexpr int NX = TC ? 1 : BN / TN, LA = BM * kBK / 256, LB = BN * kBK / 256, GA = TC ? 1 : TM / 4, GB = TC ? 1 : TN / 4;
   constexpr int PAD = TC ? 8 : 4;   // TC: a fragment's (k, row) pairs fall on 32 different banks with a pitch of 8 mod 32
@@ -414,8 +420,10 @@ __global__ void __launch_bounds__(256, (BM * BN <= 4096) ? 4 : 2) ts_bmm_tiled(B
           split_tf32(As[kb + tq + 4][r0 + 8], ah[3], al[3]);
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) {
-            mma_tf32(accm[mt][nt], al, bh[nt][0], bh[nt][1]);
-            mma_tf32(accm[mt][nt], ah, bl[nt][0], bl[nt][1]);
+            if constexpr (TCT == 3) {
+              mma_tf32(accm[mt][nt], al, bh[nt][0], bh[nt][1]);
+              mma_tf32(accm[mt][nt], ah, bl[nt][0], bl[nt][1]);
+            }
             mma_tf32(accm[mt][nt], ah, bh[nt][0], bh[nt][1]);
           }
         }
@@ -506,7 +514,7 @@ __global__ void __launch_bounds__(256, (BM * BN <= 4096) ? 4 : 2) ts_bmm_tiled(B
 }
 
 // tile choice: predicted time = waves over the 148 SMs x work of a tile / relative speed of the tile shape
-template <int BM, int BN, int TM, int TN, bool TC>
+template <int BM, int BN, int TM, int TN, int TC>
 void launch_tiled(Launcher& L, const Bmm& p) {
   const long gx = (p.N + BN - 1) / BN, gy = (p.M + BM - 1) / BM, gz = (long)p.Z1 * p.Z2;
   ts_bmm_tiled<BM, BN, TM, TN, TC><<<dim3((unsigned)gx, (unsigned)gy, (unsigned)gz), 256, 0, L.st>>>(p);
@@ -536,20 +544,27 @@ void run_bmm(Launcher& L, const Bmm& p) {
   if (p.K <= 0 && p.mode != 0) return;
 #ifndef DHG_HOSTSIM
   if (g_use_tiled && (long)p.Z1 * p.Z2 <= 65535 && (p.M + 63) / 64 <= 65535) {
-    const int tile = g_use_tiled == 2 ? 3 : pick_tile(p);   // "tiled_gemm" 2: the small CUDA-core tile only (measurement)
-    if (g_use_tiled == 1) {   // 3 x TF32 on the tensor cores
+    const int tile = g_use_tiled == 2 ? 3 : pick_tile(p);
+    if (g_use_tiled == 3) {          // 3 x TF32 on the tensor cores
       switch (tile) {
-        case 0: launch_tiled<128, 128, 2, 4, true>(L, p); break;
-        case 1: launch_tiled<128, 64, 4, 2, true>(L, p); break;
-        case 2: launch_tiled<64, 128, 2, 4, true>(L, p); break;
-        default: launch_tiled<64, 64, 2, 4, true>(L, p); break;
+        case 0: launch_tiled<128, 128, 2, 4, 3>(L, p); break;
+        case 1: launch_tiled<128, 64, 4, 2, 3>(L, p); break;
+        case 2: launch_tiled<64, 128, 2, 4, 3>(L, p); break;
+        default: launch_tiled<64, 64, 2, 4, 3>(L, p); break;
       }
-    } else {                  // "tiled_gemm" 3 (or 2): fp32 FMAs on the CUDA cores
+    } else if (g_use_tiled == 4) {   // plain TF32
       switch (tile) {
-        case 0: launch_tiled<128, 128, 8, 8, false>(L, p); break;
-        case 1: launch_tiled<128, 64, 8, 4, false>(L, p); break;
-        case 2: launch_tiled<64, 128, 4, 8, false>(L, p); break;
-        default: launch_tiled<64, 64, 4, 4, false>(L, p); break;
+        case 0: launch_tiled<128, 128, 2, 4, 1>(L, p); break;
+        case 1: launch_tiled<128, 64, 4, 2, 1>(L, p); break;
+        case 2: launch_tiled<64, 128, 2, 4, 1>(L, p); break;
+        default: launch_tiled<64, 64, 2, 4, 1>(L, p); break;
+      }
+    } else {                         // fp32 FMAs on the CUDA cores
+      switch (tile) {
+        case 0: launch_tiled<128, 128, 8, 8, 0>(L, p); break;
+        case 1: launch_tiled<128, 64, 8, 4, 0>(L, p); break;
+        case 2: launch_tiled<64, 128, 4, 8, 0>(L, p); break;
+        default: launch_tiled<64, 64, 4, 4, 0>(L, p); break;
       }
     }
     return;

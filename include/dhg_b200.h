@@ -320,7 +320,10 @@ int32_t dhg_trainer_create(int32_t device, int32_t num_layers, int32_t channels,
 int32_t dhg_trainer_destroy(dhg_trainer* t);
 int64_t dhg_trainer_workspace_bytes(const dhg_trainer* t);
 int64_t dhg_trainer_last_launches(const dhg_trainer* t);   /* launches of the last forward (+ backward) */
-int32_t dhg_trainer_set_option(const char* name, int32_t value);   /* "tiled_gemm" 1 (default) / 0: per-thread GEMM body (checks) */
+int32_t dhg_trainer_set_option(const char* name, int32_t value);   /* "tiled_gemm": 1 (default) tiled fp32 GEMM on the CUDA cores, 3 tiled with
+                                                                       3 x TF32 tensor-core products (same fp32 contract), 4 plain TF32 products
+                                                                       (torch's allow_tf32; about 1e-3, outside the fp32 contract), 2 smallest tile
+                                                                       only, 0 per-thread kernel bodies (checks) */
 int32_t dhg_trainer_forward(dhg_trainer* t, const float* dev_x, const int64_t* dev_text, const float* dev_sigma, const float* dev_style,
                             const float* dev_style_keep, float* dev_score_pred, float* dev_pen_pred, void* stream);
 int32_t dhg_trainer_backward(dhg_trainer* t, const float* dev_grad_score, const float* dev_grad_pen_pred, void* stream);

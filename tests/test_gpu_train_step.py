@@ -43,18 +43,21 @@ def test_forward_backward_match_the_reference_training_step(state_dict):
     gd = {k: v.cpu() for k, v in tr.grad_dict().items()}
     worst = train_ref.check_gradients(lambda k: gd[k], z, full, list(tr.layout))
     print("worst gradient error vs the reference:", worst, "launches", tr.last_launch_count)
-    # the shared-memory GEMM and the per-thread GEMM body (the one the host build checks) give the same gradients
+    # every kernel variant against the default: the per-thread bodies the host build checks (0), the smallest tile (2),
+    # 3 x TF32 tensor-core products (3: same fp32 contract), plain TF32 products (4: torch's allow_tf32 precision class)
     from dhg_b200 import _abi
 
-    _abi.lib().dhg_trainer_set_option(b"tiled_gemm", 0)
-    try:
-        score2, pen2, _ = tr.forward(x_p, _dev(inp["text"][0]), torch.sqrt(alphas), _dev(inp["style"][0]), _dev(inp["keep"][0]))
-        g2 = tr.backward(g_s, g_p).cpu()
-    finally:
-        _abi.lib().dhg_trainer_set_option(b"tiled_gemm", 1)
-    assert (score2 - score).abs().max() < 1e-5
     flat = torch.cat([gd[k].reshape(-1) for k in tr.layout])
-    assert (g2 - flat).norm() / flat.norm() < 1e-5
+    for mode, tol in ((0, 1e-5), (2, 1e-5), (3, 5e-5), (4, 5e-3)):
+        _abi.lib().dhg_trainer_set_option(b"tiled_gemm", mode)
+        try:
+            score2, pen2, _ = tr.forward(x_p, _dev(inp["text"][0]), torch.sqrt(alphas), _dev(inp["style"][0]), _dev(inp["keep"][0]))
+            g2 = tr.backward(g_s, g_p).cpu()
+        finally:
+            _abi.lib().dhg_trainer_set_option(b"tiled_gemm", 1)
+        err_s, err_g = ((score2 - score).norm() / score.norm()).item(), ((g2 - flat).norm() / flat.norm()).item()
+        print(f"tiled_gemm={mode}: score {err_s:.2e}, flat gradient {err_g:.2e} from the default")
+        assert err_s < tol and err_g < tol, (mode, err_s, err_g)
     tr.close()
 
 
