@@ -65,6 +65,7 @@ int sfail(const char* fmt, ...) {
 //   4 tiled GEMM with plain TF32 products (one mma per product: what torch's allow_tf32 does; ~1e-3 relative, NOT the fp32 contract)
 //   0 the per-thread bodies the host build runs (GEMM and per-row kernels)
 int g_use_tiled = 1;
+int g_side_stream = 1;   // "side_stream": weight / bias gradients on a second stream beside the data-gradient chain
 
 // ------------------------------------------------------------------------------------------------------------------
 // launch layer
@@ -100,6 +101,43 @@ struct Launcher {
   ts_stream st = nullptr;
   long launches = 0;
   int grid_cap = 148 * 16;
+  // Weight / bias gradients depend only on what the backward has already produced and nothing downstream reads them:
+  // they run on a second stream beside the data-gradient chain (most launches here are a single partial wave).
+  // side_begin(): the side stream waits for everything enqueued so far and becomes the launch stream; side_end():
+  // back to the caller's stream; side_join(): the caller's stream waits for the side stream (end of the backward).
+#ifndef DHG_HOSTSIM
+  cudaStream_t side = nullptr;
+  std::vector<cudaEvent_t>* events = nullptr;
+  size_t next_event = 0;
+  bool forked = false;
+  bool side_ok() const { return side && events && next_event < events->size(); }
+  void side_begin() {
+    if (!side_ok()) return;
+    cudaEvent_t e = (*events)[next_event++];
+    cudaEventRecord(e, st);
+    cudaStreamWaitEvent(side, e, 0);
+    std::swap(st, side);
+    forked = true;
+    in_side = true;
+  }
+  void side_end() {
+    if (!in_side) return;
+    std::swap(st, side);
+    in_side = false;
+  }
+  void side_join() {
+    if (!forked || !side_ok()) return;
+    cudaEvent_t e = (*events)[next_event++];
+    cudaEventRecord(e, side);
+    cudaStreamWaitEvent(st, e, 0);
+    forked = false;
+  }
+  bool in_side = false;
+#else
+  void side_begin() {}
+  void side_end() {}
+  void side_join() {}
+#endif
   template <class F>
   void run(long n, const F& f) {
     if (n <= 0) return;
@@ -570,6 +608,15 @@ void run_bmm(Launcher& L, const Bmm& p) {
     return;
   }
 #endif
+#ifdef DHG_HOSTSIM
+  // tools/train_gemm_shapes.py: list the contractions of a plan (shape, batch, taps, store mode) without computing them
+  static const bool log_only = getenv("DHG_TRAINER_LOG_BMM") != nullptr;
+  if (log_only) {
+    printf("BMM %d %d %d %d %d %d\n", p.M, p.N, p.K, p.Z1 * p.Z2, p.taps, p.mode);
+    ++L.launches;
+    return;
+  }
+#endif
   BmmBody f;
   f.p = p;
   f.tm = (p.M + 3) / 4;
@@ -765,6 +812,7 @@ struct Ten {
   float* v = nullptr;
   float* g = nullptr;   // null: no gradient wanted (inputs)
   int rows = 0, C = 0, period = 1;   // rows = samples * period
+  bool ng = false;                    // an input (or a pure function of inputs): no gradient is ever needed
   long n() const { return (long)rows * C; }
 };
 struct OpRec { std::function<void(Launcher&)> fwd, bwd; };
@@ -784,6 +832,10 @@ struct dhg_trainer {
   float* g_arena = nullptr;
   std::vector<void*> consts;
   std::vector<OpRec> tape;
+#ifndef DHG_HOSTSIM
+  cudaStream_t side_stream = nullptr;
+  std::vector<cudaEvent_t> side_events;
+#endif
   std::string err;
   // plan-owned copies of the inputs, and the outputs
   Ten in_x, in_sigma, in_style, style_keep, out_score, out_pen;
@@ -806,7 +858,8 @@ struct dhg_trainer {
 
   // ---- ops ----
   Ten unary_silu(const Ten& x) {
-    Ten y = make(x.rows, x.C, x.period);
+    Ten y = make(x.rows, x.C, x.period, !x.ng);
+    y.ng = x.ng;
     rec([=](Launcher& L) { L.run(x.n(), SiluFwd{x.v, y.v}); }, [=](Launcher& L) { if (x.g) L.run(x.n(), SiluBwd{x.v, y.g, x.g}); });
     return y;
   }
@@ -870,11 +923,13 @@ struct dhg_trainer {
             p.sAi = N; p.sAk = 1; p.sBk = K; p.sBj = 1; p.sCi = K; p.sCj = 1;
             run_bmm(L, p);
           }
+          L.side_begin();
           int Z, rpz; wgrad_split(x, Z, rpz);
           Bmm q; q.A = y.g; q.B = x.v; q.C = gW; q.M = N; q.N = K; q.K = rpz; q.Z1 = Z; q.mode = 2;   // dW[n, k] += sum_r dy[r, n] x[r, k]  (k fastest: coalesced atomics)
           q.sAz1 = (long)rpz * N; q.sAi = 1; q.sAk = N; q.sBz1 = (long)rpz * K; q.sBk = K; q.sBj = 1; q.sCz1 = 0; q.sCi = K; q.sCj = 1;
           run_bmm(L, q);
           L.run((long)N * ((x.rows + 63) / 64), ColSum{y.g, gb, x.rows, N});
+          L.side_end();
         });
     return y;
   }
@@ -905,6 +960,7 @@ struct dhg_trainer {
             p.sAz1 = (long)Tn * N; p.sAi = N; p.sAk = 1; p.sBk = K; p.sBj = 1; p.sCz1 = (long)Tn * K; p.sCi = K; p.sCj = 1;
             run_bmm(L, p);
           }
+          L.side_begin();
           for (int tap = 0; tap < 3; ++tap) {   // scratch[tap][n][k] += sum_b sum_t dy[t, n] x[t + tap - 1, k]  (k contiguous: vector atomics)
             int lo, hi; range(tap, lo, hi);
             Bmm q; q.A = y.g + (long)lo * N; q.B = x.v + (long)(lo + tap - 1) * K; q.C = wtmp.g + (long)tap * N * K; q.M = N; q.N = K; q.K = hi - lo; q.Z1 = nb; q.mode = 2;
@@ -913,6 +969,7 @@ struct dhg_trainer {
           }
           L.run(3L * N * K, ConvWFold{wtmp.g, gW, (long)N * K});   // dW[n, k, tap] = scratch[tap][n][k]
           L.run((long)N * ((x.rows + 63) / 64), ColSum{y.g, gb, x.rows, N});
+          L.side_end();
         });
     return y;
   }
@@ -1013,6 +1070,7 @@ struct dhg_trainer {
   Ten text_style(const Ten& sig) {
     const std::string p = "text_style_model";
     Ten sdrop = make(in_style.rows, in_style.C, in_style.period, false);
+    sdrop.ng = true;
     {
       const Ten a = in_style, m = style_keep; const bool* hk = &have_keep;
       rec([=](Launcher& L) { L.run(a.n(), MulFwd{a.v, *hk ? m.v : nullptr, sdrop.v}); }, [=](Launcher&) {});
@@ -1037,6 +1095,7 @@ struct dhg_trainer {
     in_sigma = make(B, 1, 1, false);
     in_style = make(B * 14, 1280, 14, false);
     style_keep = make(B * 14, 1280, 14, false);
+    in_x.ng = in_sigma.ng = in_style.ng = style_keep.ng = true;
     Ten sig = ffn(in_sigma, "sigma_ffn", 2048, c1 / 4);
     Ten text_t = text_style(sig);
     Ten x = linear(in_x, "input_dense", c1);
@@ -1105,6 +1164,15 @@ int32_t dhg_trainer_create(int32_t device, int32_t num_layers, int32_t channels,
   }
   t->dry = false;
   t->build_model();
+#ifndef DHG_HOSTSIM
+  if (cudaStreamCreateWithFlags(&t->side_stream, cudaStreamNonBlocking) == cudaSuccess) {
+    t->side_events.resize(t->tape.size() + 2);
+    for (auto& e : t->side_events)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) t->err = "cudaEventCreate failed";
+  } else {
+    t->side_stream = nullptr;
+  }
+#endif
   if (!t->err.empty()) { sfail("dhg_trainer_create: %s", t->err.c_str()); dhg_trainer_destroy(t); return 1; }
   *out = t;
   return 0;
@@ -1118,6 +1186,10 @@ int32_t dhg_trainer_destroy(dhg_trainer* t) {
 #endif
   dev_free(t->v_arena); dev_free(t->g_arena); dev_free(t->text);
   for (void* p : t->consts) dev_free(p);
+#ifndef DHG_HOSTSIM
+  for (auto e : t->side_events) if (e) cudaEventDestroy(e);
+  if (t->side_stream) cudaStreamDestroy(t->side_stream);
+#endif
   delete t;
   return 0;
 }
@@ -1127,6 +1199,7 @@ int64_t dhg_trainer_last_launches(const dhg_trainer* t) { return t ? t->last_lau
 
 int32_t dhg_trainer_set_option(const char* name, int32_t value) {
   if (name && !strcmp(name, "tiled_gemm")) { g_use_tiled = value; return 0; }
+  if (name && !strcmp(name, "side_stream")) { g_side_stream = value; return 0; }
   return sfail("dhg_trainer_set_option: unknown option");
 }
 
@@ -1166,7 +1239,11 @@ int32_t dhg_trainer_backward(dhg_trainer* t, const float* dev_grad_score, const 
   L.zero(t->grads, (size_t)t->lay.total * sizeof(float));
   L.copy(t->out_score.g, dev_grad_score, (size_t)t->B * t->T * 2 * sizeof(float));
   L.copy(t->out_pen.g, dev_grad_pen_pred, (size_t)t->B * t->T * sizeof(float));
+#ifndef DHG_HOSTSIM
+  if (g_side_stream && t->side_stream) { L.side = t->side_stream; L.events = &t->side_events; }
+#endif
   for (auto it = t->tape.rbegin(); it != t->tape.rend(); ++it) it->bwd(L);
+  L.side_join();
   t->last_launches += L.launches;
 #ifndef DHG_HOSTSIM
   cudaError_t e = cudaGetLastError();
