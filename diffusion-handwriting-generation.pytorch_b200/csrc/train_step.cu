@@ -868,9 +868,9 @@ struct dhg_trainer {
     rec([=](Launcher& L) { L.run(x.n(), SigmoidFwd{x.v, y.v}); }, [=](Launcher& L) { if (x.g) L.run(x.n(), SigmoidBwd{y.v, y.g, x.g}); });
     return y;
   }
-  Ten add(const Ten& a, const Ten& b) {
+  Ten add(const Ten& a, const Ten& b, bool join = false) {   // join: an operand was produced on the second stream
     Ten y = make(a.rows, a.C, a.period);
-    rec([=](Launcher& L) { L.run(a.n(), AddFwd{a.v, b.v, y.v}); }, [=](Launcher& L) { L.run(a.n(), AddBwd{y.g, a.g, b.g}); });
+    rec([=](Launcher& L) { if (join) L.side_join(); L.run(a.n(), AddFwd{a.v, b.v, y.v}); }, [=](Launcher& L) { L.run(a.n(), AddBwd{y.g, a.g, b.g}); });
     return y;
   }
   Ten add_pe(const Ten& x, const float* pe) {
@@ -934,7 +934,9 @@ struct dhg_trainer {
     return y;
   }
   // nn.Conv1d(k = 3, padding 1) in channels-last form (cnn.py:32-47): W [N, K, 3]; tap j reads row t + j - 1 of the same sample
-  Ten conv3(const Ten& x, const std::string& name, int N) {
+  // side = true: the forward launch goes to the second stream (a branch that is consumed later: conv_skip of a ConvBlock,
+  // the U-Net's skip convolutions); the consumer is an add(..., join = true)
+  Ten conv3(const Ten& x, const std::string& name, int N, bool side = false) {
     const int K = x.C, Tn = x.period, nb = x.rows / x.period;
     Ten y = make(x.rows, N, x.period);
     const float* W = P(name + ".weight"); const float* b = P(name + ".bias");
@@ -947,11 +949,13 @@ struct dhg_trainer {
     // forward into [tap][k][n] (forward: n contiguous) and [tap][n][k] (data gradient: k contiguous); 2 x 12 bytes per weight
     Ten wf = make(3 * K, N, 1, false), wd = make(3 * N, K, 1, false);
     rec([=](Launcher& L) {   // y[t, n] = b[n] + sum_tap sum_k x[t + tap - 1, k] W[n, k, tap], one batch item per sample
+          if (side) L.side_begin();
           L.run(3L * N * K, ConvWPack{W, wf.v, wd.v, N, K});
           Bmm p; p.A = x.v; p.B = wf.v; p.C = y.v; p.bias = b; p.M = Tn; p.N = N; p.K = K; p.Z1 = nb;
           p.taps = 3; p.shift0 = -1; p.dshift = 1; p.sBtap = (long)K * N;
           p.sAz1 = (long)Tn * K; p.sAi = K; p.sAk = 1; p.sBk = N; p.sBj = 1; p.sCz1 = (long)Tn * N; p.sCi = N; p.sCj = 1;
           run_bmm(L, p);
+          if (side) L.side_end();
         },
         [=](Launcher& L) {
           if (x.g) {   // dx[t, k] += sum_tap sum_n dy[t - (tap - 1), n] W[n, k, tap]
@@ -1026,11 +1030,11 @@ struct dhg_trainer {
   }
   // ConvBlock.forward (cnn.py:52-87)
   Ten conv_block(const std::string& p, const Ten& x, const Ten& sig, int out) {
-    Ten skip = conv3(x, p + ".conv_skip", out);
+    Ten skip = conv3(x, p + ".conv_skip", out, true);
     Ten y = film(conv3(unary_silu(x), p + ".conv1", out / 2), sig, p + ".affine1");
     y = film(conv3(unary_silu(y), p + ".conv2", out), sig, p + ".affine2");
     y = film(linear(unary_silu(y), p + ".fc", out), sig, p + ".affine3");
-    return add(y, skip);
+    return add(y, skip, true);
   }
   // attention.py:15-23: halves concatenated (sin | cos), fp32 like the reference
   const float* pos_table(int length, int dim, float pos_factor) {
@@ -1100,15 +1104,18 @@ struct dhg_trainer {
     Ten text_t = text_style(sig);
     Ten x = linear(in_x, "input_dense", c1);
     Ten h1 = conv_block("enc1", x, sig, c1);
+    Ten sk1 = conv3(h1, "skip_conv1", c2, true);   // model.py:169-181 adds these in the decoder; they only need h_k
     Ten h2 = conv_block("enc2", pool(h1), sig, c2);
     h2 = encoder_layer("enc3", h2, text_t, sig, 3, 4.f);
+    Ten sk2 = conv3(h2, "skip_conv2", c3, true);
     Ten h3 = conv_block("enc4", pool(h2), sig, c3);
     h3 = encoder_layer("enc5", h3, text_t, sig, 4, 2.f);
+    Ten sk3 = conv3(h3, "skip_conv3", d, true);
     x = linear(pool(h3), "att_dense", d);
     for (int i = 0; i < num_layers; ++i) x = encoder_layer("att_layers." + std::to_string(i), x, text_t, sig, 6, 1.f);
-    x = conv_block("dec3", add(up(x), conv3(h3, "skip_conv3", d)), sig, c3);
-    x = conv_block("dec2", add(up(x), conv3(h2, "skip_conv2", c3)), sig, c2);
-    x = conv_block("dec1", add(up(x), conv3(h1, "skip_conv1", c2)), sig, c1);
+    x = conv_block("dec3", add(up(x), sk3, true), sig, c3);
+    x = conv_block("dec2", add(up(x), sk2, true), sig, c2);
+    x = conv_block("dec1", add(up(x), sk1, true), sig, c1);
     out_score = linear(x, "output_dense", 2);
     out_pen = sigmoid(linear(x, "pen_lifts_dense.0", 1));
   }
@@ -1166,7 +1173,7 @@ int32_t dhg_trainer_create(int32_t device, int32_t num_layers, int32_t channels,
   t->build_model();
 #ifndef DHG_HOSTSIM
   if (cudaStreamCreateWithFlags(&t->side_stream, cudaStreamNonBlocking) == cudaSuccess) {
-    t->side_events.resize(t->tape.size() + 2);
+    t->side_events.resize(2 * t->tape.size() + 4);
     for (auto& e : t->side_events)
       if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) t->err = "cudaEventCreate failed";
   } else {
@@ -1217,7 +1224,11 @@ int32_t dhg_trainer_forward(dhg_trainer* t, const float* dev_x, const int64_t* d
   L.copy(t->in_style.v, dev_style, (size_t)t->B * 14 * 1280 * sizeof(float));
   t->have_keep = dev_style_keep != nullptr;
   if (dev_style_keep) L.copy(t->style_keep.v, dev_style_keep, (size_t)t->B * 14 * 1280 * sizeof(float));
+#ifndef DHG_HOSTSIM
+  if (g_side_stream && t->side_stream) { L.side = t->side_stream; L.events = &t->side_events; }
+#endif
   for (auto& op : t->tape) op.fwd(L);
+  L.side_join();
   if (dev_score_pred) L.copy(dev_score_pred, t->out_score.v, (size_t)t->B * t->T * 2 * sizeof(float));
   if (dev_pen_pred) L.copy(dev_pen_pred, t->out_pen.v, (size_t)t->B * t->T * sizeof(float));
   t->last_launches = L.launches;
