@@ -629,6 +629,43 @@ void run_bmm(Launcher& L, const Bmm& p) {
 // ------------------------------------------------------------------------------------------------------------------
 TS_FN float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
+// 16-byte versions of the streaming kernels (used when the channel count is a multiple of 4: every activation but sigma [B, 1])
+struct alignas(16) f4 { float x, y, z, w; };
+TS_FN f4 ld4(const float* p) { return *reinterpret_cast<const f4*>(p); }
+TS_FN void st4(float* p, const f4& v) { *reinterpret_cast<f4*>(p) = v; }
+TS_FN float silu_(float v) { return v * sigmoidf_(v); }
+TS_FN float dsilu_(float v) { const float s = sigmoidf_(v); return s * (1.f + v * (1.f - s)); }
+struct Silu4Fwd { const float* x; float* y; TS_FN void operator()(long i) const { const f4 v = ld4(x + 4 * i); st4(y + 4 * i, f4{silu_(v.x), silu_(v.y), silu_(v.z), silu_(v.w)}); } };
+struct Silu4Bwd {
+  const float* x; const float* gy; float* gx;
+  TS_FN void operator()(long i) const {
+    const f4 v = ld4(x + 4 * i), g = ld4(gy + 4 * i), o = ld4(gx + 4 * i);
+    st4(gx + 4 * i, f4{o.x + g.x * dsilu_(v.x), o.y + g.y * dsilu_(v.y), o.z + g.z * dsilu_(v.z), o.w + g.w * dsilu_(v.w)});
+  }
+};
+struct Add4Fwd { const float* a; const float* b; float* y; TS_FN void operator()(long i) const { const f4 u = ld4(a + 4 * i), v = ld4(b + 4 * i); st4(y + 4 * i, f4{u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w}); } };
+struct Acc4Bwd { const float* gy; float* gx; TS_FN void operator()(long i) const { const f4 g = ld4(gy + 4 * i), o = ld4(gx + 4 * i); st4(gx + 4 * i, f4{o.x + g.x, o.y + g.y, o.z + g.z, o.w + g.w}); } };
+struct Add4Bwd { const float* gy; float* ga; float* gb; TS_FN void operator()(long i) const { if (ga) Acc4Bwd{gy, ga}(i); if (gb) Acc4Bwd{gy, gb}(i); } };
+struct AddPe4Fwd {
+  const float* x; const float* pe; float* y; int C, period;
+  TS_FN void operator()(long i) const { const long e = 4 * i, r = e / C; const f4 u = ld4(x + e), v = ld4(pe + (r % period) * C + (e % C)); st4(y + e, f4{u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w}); }
+};
+struct Film4Fwd {
+  const float* x; const float* gam; const float* bet; float* y; int C, period;
+  TS_FN void operator()(long i) const {
+    const long e = 4 * i, o = (e / ((long)C * period)) * C + (e % C);
+    const f4 u = ld4(x + e), g = ld4(gam + o), b = ld4(bet + o);
+    st4(y + e, f4{u.x * g.x + b.x, u.y * g.y + b.y, u.z * g.z + b.z, u.w * g.w + b.w});
+  }
+};
+struct Film4BwdX {
+  const float* gy; const float* gam; float* gx; int C, period;
+  TS_FN void operator()(long i) const {
+    const long e = 4 * i, o = (e / ((long)C * period)) * C + (e % C);
+    const f4 d = ld4(gy + e), g = ld4(gam + o), a = ld4(gx + e);
+    st4(gx + e, f4{a.x + d.x * g.x, a.y + d.y * g.y, a.z + d.z * g.z, a.w + d.w * g.w});
+  }
+};
 struct SiluFwd { const float* x; float* y; TS_FN void operator()(long i) const { const float v = x[i]; y[i] = v * sigmoidf_(v); } };
 struct SiluBwd {
   const float* x; const float* gy; float* gx;
@@ -860,7 +897,9 @@ struct dhg_trainer {
   Ten unary_silu(const Ten& x) {
     Ten y = make(x.rows, x.C, x.period, !x.ng);
     y.ng = x.ng;
-    rec([=](Launcher& L) { L.run(x.n(), SiluFwd{x.v, y.v}); }, [=](Launcher& L) { if (x.g) L.run(x.n(), SiluBwd{x.v, y.g, x.g}); });
+    const bool v4 = x.C % 4 == 0;
+    rec([=](Launcher& L) { if (v4) L.run(x.n() / 4, Silu4Fwd{x.v, y.v}); else L.run(x.n(), SiluFwd{x.v, y.v}); },
+        [=](Launcher& L) { if (!x.g) return; if (v4) L.run(x.n() / 4, Silu4Bwd{x.v, y.g, x.g}); else L.run(x.n(), SiluBwd{x.v, y.g, x.g}); });
     return y;
   }
   Ten sigmoid(const Ten& x) {
@@ -870,12 +909,16 @@ struct dhg_trainer {
   }
   Ten add(const Ten& a, const Ten& b, bool join = false) {   // join: an operand was produced on the second stream
     Ten y = make(a.rows, a.C, a.period);
-    rec([=](Launcher& L) { if (join) L.side_join(); L.run(a.n(), AddFwd{a.v, b.v, y.v}); }, [=](Launcher& L) { L.run(a.n(), AddBwd{y.g, a.g, b.g}); });
+    const bool v4 = a.C % 4 == 0;
+    rec([=](Launcher& L) { if (join) L.side_join(); if (v4) L.run(a.n() / 4, Add4Fwd{a.v, b.v, y.v}); else L.run(a.n(), AddFwd{a.v, b.v, y.v}); },
+        [=](Launcher& L) { if (v4) L.run(a.n() / 4, Add4Bwd{y.g, a.g, b.g}); else L.run(a.n(), AddBwd{y.g, a.g, b.g}); });
     return y;
   }
   Ten add_pe(const Ten& x, const float* pe) {
     Ten y = make(x.rows, x.C, x.period);
-    rec([=](Launcher& L) { L.run(x.n(), AddPeFwd{x.v, pe, y.v, x.C, x.period}); }, [=](Launcher& L) { if (x.g) L.run(x.n(), AccBwd{y.g, x.g}); });
+    const bool v4 = x.C % 4 == 0;
+    rec([=](Launcher& L) { if (v4) L.run(x.n() / 4, AddPe4Fwd{x.v, pe, y.v, x.C, x.period}); else L.run(x.n(), AddPeFwd{x.v, pe, y.v, x.C, x.period}); },
+        [=](Launcher& L) { if (!x.g) return; if (v4) L.run(x.n() / 4, Acc4Bwd{y.g, x.g}); else L.run(x.n(), AccBwd{y.g, x.g}); });
     return y;
   }
   Ten pool(const Ten& x) {
@@ -983,9 +1026,10 @@ struct dhg_trainer {
     Ten bet = linear(sig, name + ".beta_emb", x.C);
     Ten y = make(x.rows, x.C, x.period);
     const int nb = x.rows / x.period;
-    rec([=](Launcher& L) { L.run(x.n(), FilmFwd{x.v, gam.v, bet.v, y.v, x.C, x.period}); },
+    const bool v4 = x.C % 4 == 0;
+    rec([=](Launcher& L) { if (v4) L.run(x.n() / 4, Film4Fwd{x.v, gam.v, bet.v, y.v, x.C, x.period}); else L.run(x.n(), FilmFwd{x.v, gam.v, bet.v, y.v, x.C, x.period}); },
         [=](Launcher& L) {
-          if (x.g) L.run(x.n(), FilmBwdX{y.g, gam.v, x.g, x.C, x.period});
+          if (x.g) { if (v4) L.run(x.n() / 4, Film4BwdX{y.g, gam.v, x.g, x.C, x.period}); else L.run(x.n(), FilmBwdX{y.g, gam.v, x.g, x.C, x.period}); }
           const int chunks = (x.period + 31) / 32;
           L.run((long)nb * chunks * x.C, FilmBwdCond{y.g, x.v, gam.g, bet.g, x.C, x.period, chunks});
         });
