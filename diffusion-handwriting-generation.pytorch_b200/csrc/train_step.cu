@@ -781,8 +781,11 @@ struct PoolFwd { const float* x; float* y; int C; TS_FN void operator()(long i) 
 struct PoolBwd { const float* gy; float* gx; int C; TS_FN void operator()(long i) const { const long r = i / C; const int c = (int)(i % C); gx[i] += 0.5f * gy[(r >> 1) * C + c]; } };
 struct UpFwd { const float* x; float* y; int C; TS_FN void operator()(long i) const { const long r = i / C; const int c = (int)(i % C); y[i] = x[(r >> 1) * C + c]; } };
 struct UpBwd { const float* gy; float* gx; int C; TS_FN void operator()(long i) const { const long r = i / C; const int c = (int)(i % C); gx[i] += gy[(2 * r) * C + c] + gy[(2 * r + 1) * C + c]; } };
-struct EmbedFwd { const int64_t* ids; const float* E; float* y; int C; TS_FN void operator()(long i) const { y[i] = E[ids[i / C] * C + (i % C)]; } };
-struct EmbedBwd { const int64_t* ids; const float* gy; float* gE; int C; TS_FN void operator()(long i) const { ts_atomic_add(gE + ids[i / C] * C + (i % C), gy[i]); } };
+// nn.Embedding(73, d) (text_style.py:70).  Ids are validated by the caller (DenoiserTrainer raises IndexError like the
+// reference); the clamp only keeps a bad id from reading outside the table.
+TS_FN long embed_row(int64_t id) { return id < 0 ? 0 : id > 72 ? 72 : (long)id; }
+struct EmbedFwd { const int64_t* ids; const float* E; float* y; int C; TS_FN void operator()(long i) const { y[i] = E[embed_row(ids[i / C]) * C + (i % C)]; } };
+struct EmbedBwd { const int64_t* ids; const float* gy; float* gE; int C; TS_FN void operator()(long i) const { ts_atomic_add(gE + embed_row(ids[i / C]) * C + (i % C), gy[i]); } };
 struct ConvWPack {   // W [n][k][tap] -> wf [tap][k][n], wd [tap][n][k]
   const float* W; float* wf; float* wd; int N, K;
   TS_FN void operator()(long i) const {

@@ -284,11 +284,22 @@ class DenoiserTrainer:
         if not (isinstance(text, torch.Tensor) and text.is_cuda and tuple(text.shape) == (B, L)) or text.is_floating_point():
             raise ValueError(f"text: expected an integer CUDA tensor of shape {(B, L)}")
         text = text.to(torch.int64).contiguous()
+        self._check_tokens(text)
         score = torch.empty(B, T, 2, dtype=torch.float32, device=self.device)
         pen = torch.empty(B, T, dtype=torch.float32, device=self.device)
         _trainer_check(_abi.lib().dhg_trainer_forward(self._h, _p(strokes), _p(text), _p(sigma), _p(style_vector), _p(style_keep), _p(score),
                                                       _p(pen), _stream()))
         return score, pen, None
+
+    def _check_tokens(self, text):
+        """Embedding(73, d) raises IndexError on an id outside [0, 73) (text_style.py:70).  The check reads one flag back from
+        the device, so a tensor that was already checked and not written since (same object, same version) is not re-read."""
+        key = (text.data_ptr(), text._version, tuple(text.shape))
+        if getattr(self, "_tokens_ok", None) == key:
+            return
+        if bool(((text < 0) | (text >= 73)).any().item()):
+            raise IndexError("text token id out of range [0, 73)")
+        self._tokens_ok = key
 
     def backward(self, grad_score, grad_pen_pred):
         """loss.backward() (train.py:55) from d loss / d score_pred and d loss / d pen_lifts_pred: fills and returns the flat gradient."""

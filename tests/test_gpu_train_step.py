@@ -129,4 +129,7 @@ def test_trainer_error_behaviour(state_dict):
     with pytest.raises(ValueError):
         tr.forward(torch.zeros(2, 16, 2, device="cuda"), torch.ones(2, 5, device="cuda"), torch.ones(2, 1, device="cuda"),
                    torch.zeros(2, 14, 1280, device="cuda"))
+    with pytest.raises(IndexError):
+        tr.forward(torch.zeros(2, 16, 2, device="cuda"), torch.full((2, 5), 73, dtype=torch.int64, device="cuda"), torch.ones(2, 1, device="cuda"),
+                   torch.zeros(2, 14, 1280, device="cuda"))
     tr.close()
