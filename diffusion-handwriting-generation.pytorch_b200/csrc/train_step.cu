@@ -9,16 +9,21 @@
 //
 // Arithmetic is fp32 on the CUDA cores, like the reference's training (fp32 parameters, fp32 autograd): every
 // contraction -- Linear, the three taps of a k3 Conv1d, Q K^T, P V, and all their data / weight gradients -- is ONE
-// strided batched GEMM (`Bmm`: C[z] (+)= alpha A[z] B[z] (+ bias), arbitrary element strides, so transposes, head
-// splitting and the row shift of a conv tap are pointer arithmetic and never a copy); weight gradients are split per
-// sample over the batch axis and reduced with fp32 atomics.  Everything else (SiLU, FiLM, LayerNorm, softmax + padding
-// mask, pooling, upsampling, embedding, PE add) is a per-element or per-row kernel.  The plan is a tape built once for
-// (B, T, L): forward = the tape, backward = zero the gradient arena, then the tape in reverse.  Everything is
-// stream-ordered; nothing synchronises; the caller may capture forward + loss + backward + update in a CUDA graph.
+// strided batched GEMM (`Bmm`: C[z] (+)= alpha sum_tap A[z](i + shift_tap, :) B_tap[z] (+ bias), arbitrary element
+// strides, so transposes, head splitting and the row shift of a conv tap are pointer arithmetic and never a copy);
+// weight gradients are cut into batch items along the row axis and reduced with fp32 vector atomics.  On the GPU the
+// GEMM is a shared-memory tiled kernel (64..128 x 64..128 tiles, register prefetch of the next k slab, 16-byte
+// operand loads and stores where the strides allow); its products can also run on the tensor cores as 3 x TF32 or
+// plain TF32 (mma.sync; dhg_trainer_set_option "tiled_gemm" 3 / 4 -- measured in DESIGN.md 4.10, not the default).
+// Everything else (SiLU, FiLM, LayerNorm, softmax + padding mask, pooling, upsampling, embedding, PE add) is a
+// per-element or warp-per-row kernel.  The plan is a tape built once for (B, T, L): forward = the tape, backward = zero
+// the gradient arena, then the tape in reverse; weight / bias gradients and the forward's skip branches run on a
+// second stream (event fork / join).  Everything is stream-ordered; nothing synchronises with the host; the caller
+// may capture forward + loss + backward + update in a CUDA graph.
 //
-// What this is NOT: it does not use the tensor cores (the sampling path's tcgen05 GEMMs are bf16 / split-bf16 forward
-// kernels with fused epilogues; their backward twins are not written).  DESIGN.md 4.10 has the measured step time
-// beside the reference's eager step on the same GPU.
+// What this is NOT: a tcgen05 path (the sampling path's tcgen05 GEMMs are bf16 / split-bf16 forward kernels with
+// fused epilogues; their backward twins are not written).  DESIGN.md 4.10 has the measured step time beside the
+// reference's eager step on the same GPU.
 //
 // The same source also builds as plain C++ (-DDHG_HOSTSIM, g++ -fopenmp): every kernel body is a functor over a flat
 // index, so the host build runs the identical bodies in a loop.  That build exists ONLY for tests/ (gradient check
