@@ -67,3 +67,42 @@ def test_exchange_gradients_sums_over_two_ranks():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, 2, 3.0, 3.0), (1, 2, 3.0, 3.0)]
+
+
+def test_param_layout_is_the_checkpoint_and_needs_no_gpu():
+    """dhg_trainer_param_info through the product library (host-only call): 323 keys in model_final.pth order, back to back."""
+    from dhg_b200.train import param_layout
+    from oracle.dhg_oracle import state_dict_spec
+
+    lay = param_layout(2, 128)
+    spec = state_dict_spec(2, 128)
+    assert list(lay) == [k for k, _ in spec] and len(lay) == 323
+    off = 0
+    for k, shape in spec:
+        n = int(torch.Size(shape).numel())
+        assert lay[k] == (off, n)
+        off += n
+    assert off == 10_028_451
+
+
+def test_trainer_has_no_cpu_path():
+    from dhg_b200.train import DenoiserTrainer, DhgTrainError
+    from oracle.dhg_oracle import init_state_dict
+
+    with pytest.raises(DhgTrainError, match="no CPU path"):
+        DenoiserTrainer(init_state_dict(0), 2, 16, 5, device="cpu")
+
+
+def test_get_alphas_follows_the_reference_draws():
+    """utils/nn.py:42-61: same two draws from the same generator state give the same alphas (the reference uses the global one)."""
+    from dhg_b200.diffusion import get_alpha_bar
+    from dhg_b200.train import get_alphas
+
+    alpha_set = torch.as_tensor(get_alpha_bar())
+    g = torch.Generator().manual_seed(3)
+    a = get_alphas(16, alpha_set, generator=g)
+    g = torch.Generator().manual_seed(3)
+    idx = torch.randint(low=0, high=len(alpha_set) - 1, size=(16, 1), dtype=torch.int64, generator=g)
+    want = torch.rand(16, 1, generator=g) * (alpha_set[idx + 1] - alpha_set[idx]) + alpha_set[idx]
+    assert a.shape == (16, 1) and torch.equal(a, want)
+    assert (a <= alpha_set[0]).all() and (a >= alpha_set[-1]).all()
