@@ -11,8 +11,8 @@
 // caller sums the flat gradient over the ranks (NCCL through torch.distributed: plumbing), the 1/N and the clip
 // coefficient are folded into the optimiser kernel, so the gradient is read exactly once after the exchange.
 //
-// NOT here: the backward pass of the denoiser (dgrad / wgrad of 65 GEMMs with their epilogues, LayerNorm, attention,
-// FiLM, pooling): DESIGN.md section 7.  These entry points take the flat gradient as an input.
+// The forward + backward pass of the denoiser that produces the flat gradient is train_step.cu (dhg_trainer_*); these
+// entry points take the flat gradient as an input.
 //
 // All of it is HBM-bound streaming: Adam reads p, g, m, v and writes p, m, v (28 bytes per parameter: 281 MB per step for
 // the reference's 10.0 M parameters), the reductions are two-stage and deterministic (fixed block partials in double).

@@ -320,3 +320,58 @@ class DenoiserTrainer:
         self.backward(g_s, g_p)                                                                    # :55
         self.optimizer.step_and_update_lr(self.grad, group)                                        # :57-63
         return loss, score_loss, pen_loss
+
+
+def fit(trainer, batches, steps, exp_dir, alpha_set=None, log_freq=5, save_freq=1000, logger=None, generator=None):
+    """The loop of TrainingLoop.train (train.py:95-137) around `trainer.train_step`, with the reference's cadence and file
+    names: a log line whenever (count + 1) % log_freq == 0 (averages since the last line), `checkpoint_<count + 1>.pth`
+    whenever (count + 1) % save_freq == 0, `model_final.pth` after `steps` steps; on KeyboardInterrupt `checkpoint_last.pth`
+    and `model_last.pth`.  `batches`: an iterable of dicts with "strokes" [B, T, 3], "text" [B, L], "style" [B, 14, 1280]
+    (train.py:69-85 `process_batch`); it is restarted when exhausted.  The per-step draws (alphas: utils/nn.py:42-61, eps,
+    the Dropout(0.3) keep mask of text_style.py:92) come from `generator` (None: torch's global one).
+    Returns the list of logged (step, loss, score_loss, pen_lifts_loss)."""
+    import os
+    import time
+
+    from .checkpoint import save_checkpoint, save_model_final
+    from .diffusion import get_alpha_bar
+
+    if alpha_set is None:
+        alpha_set = torch.as_tensor(get_alpha_bar(), dtype=torch.float32)
+    say = logger.info if logger is not None else (lambda msg: None)
+    dev = getattr(trainer, "device", None)
+    to = (lambda t: t.to(dev, non_blocking=True)) if dev is not None else (lambda t: t)
+    history, acc, count, start = [], [], 0, time.time()
+    it = iter(batches)
+    try:
+        while True:
+            try:
+                batch = next(it)
+            except StopIteration:
+                it = iter(batches)
+                batch = next(it)
+            count += 1
+            strokes, text, style = batch["strokes"], batch["text"], batch["style"]
+            x, pen_lifts = strokes[:, :, :2].contiguous(), strokes[:, :, 2].contiguous()            # train.py:76
+            alphas = get_alphas(len(x), alpha_set, generator=generator)                              # train.py:36
+            eps = torch.randn(x.shape, generator=generator)                                          # train.py:37
+            keep = (torch.rand(style.shape, generator=generator) >= 0.3).float() / 0.7               # text_style.py:83,92
+            losses = trainer.train_step(to(x), to(pen_lifts), to(text), to(style), to(alphas), to(eps), style_keep=to(keep))
+            acc.append([float(v) for v in losses])                                                   # train.py:65-67 (.item())
+            if (count + 1) % log_freq == 0:
+                mean = [sum(c) / len(acc) for c in zip(*acc)]
+                say(f"Step {count + 1} | Loss: {mean[0]:.3f} | Score: {mean[1]:.3f} | Pen: {mean[2]:.3f} | Time: {time.time() - start:.3f} sec")
+                history.append((count + 1, *mean))
+                acc = []
+            if (count + 1) % save_freq == 0:
+                say("Saving checkpoint...")
+                save_checkpoint(trainer, os.path.join(exp_dir, f"checkpoint_{count + 1}.pth"))
+            if count >= steps:
+                say("Training finished, saving model weights.")
+                save_model_final(trainer, os.path.join(exp_dir, "model_final.pth"))
+                break
+    except KeyboardInterrupt:
+        say("Training interrupted by user.")
+        save_checkpoint(trainer, os.path.join(exp_dir, "checkpoint_last.pth"))
+        save_model_final(trainer, os.path.join(exp_dir, "model_last.pth"))
+    return history

@@ -269,7 +269,8 @@ int32_t dhg_style_finalize(dhg_style* s);
 int32_t dhg_style_extract(dhg_style* s, const float* host_img, int32_t B, int32_t H, int32_t W, float* dev_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
- * Update half of the training step (SURVEY.md 8e "optional train step", 8f-3).  Replaces, on device buffers:
+ * Training step, part 1: everything of train.py:26-67 around the model call and loss.backward() (SURVEY.md 8e "optional
+ * train step", 8f-3).  Replaces, on device buffers:
  *   dhg_train_perturb    train.py:38-43   x_perturbed = sqrt(alpha) x + sqrt(1 - alpha) eps      (x, eps, out [B, T, 2]; alphas [B])
  *   dhg_train_loss       loss.py:5-39     losses[3] = {total, score_loss, pen_lifts_loss} and, when the pointers are
  *                                         non-NULL, d total / d score_pred [B, T, 2] and d total / d pen_lifts_pred [B, T]
@@ -280,8 +281,8 @@ int32_t dhg_style_extract(dhg_style* s, const float* host_img, int32_t B, int32_
  *                        (sums) the flat gradient once and never rescales it; `lr` is the scheduled rate of this step
  *                        (dhg_b200.train.InvSqrtSchedule), `step` counts from 1.
  * dev_scratch: dhg_train_scratch_doubles() doubles.  Everything is stream-ordered, nothing synchronises; reductions are
- * deterministic (fixed partial sums).  The backward pass of the denoiser is not part of this library: the flat
- * gradient is an input.  Errors: dhg_train_last_error(). */
+ * deterministic (fixed partial sums).  The flat gradient is an input here; dhg_trainer_backward (below) produces it.
+ * Errors: dhg_train_last_error(). */
 const char* dhg_train_last_error(void);
 int32_t dhg_train_scratch_doubles(void);
 int32_t dhg_train_perturb(int32_t device, const float* dev_x, const float* dev_alphas, const float* dev_eps, float* dev_out, int32_t B,

@@ -106,3 +106,51 @@ def test_get_alphas_follows_the_reference_draws():
     want = torch.rand(16, 1, generator=g) * (alpha_set[idx + 1] - alpha_set[idx]) + alpha_set[idx]
     assert a.shape == (16, 1) and torch.equal(a, want)
     assert (a <= alpha_set[0]).all() and (a >= alpha_set[-1]).all()
+
+
+class _StubTrainer:
+    """Stands in for DenoiserTrainer in the loop test (the real one needs a GPU): records what fit() feeds it."""
+
+    def __init__(self, interrupt_at=None):
+        self.calls, self.interrupt_at = [], interrupt_at
+        self.w = torch.zeros(3)
+
+    def train_step(self, x, pen_lifts, text, style, alphas, eps, style_keep=None):
+        if self.interrupt_at is not None and len(self.calls) + 1 == self.interrupt_at:
+            raise KeyboardInterrupt
+        self.calls.append((x.shape, pen_lifts.shape, text.shape, style.shape, alphas.shape, eps.shape, style_keep.shape))
+        assert set(torch.unique(style_keep).tolist()) <= {0.0, float(torch.tensor(1.0) / 0.7)}
+        self.w += 1
+        n = float(len(self.calls))
+        return torch.tensor(n), torch.tensor(n / 2), torch.tensor(n / 4)
+
+    def state_dict(self):
+        return {"w": self.w}
+
+
+def test_fit_follows_the_reference_loop_cadence(tmp_path):
+    """train.py:95-137: log when (count + 1) % log_freq == 0, checkpoint_<count + 1>.pth when (count + 1) % save_freq == 0,
+    model_final.pth after `steps` steps; the batch iterable is restarted when it runs out."""
+    from dhg_b200.train import fit
+
+    batches = [{"strokes": torch.randn(2, 16, 3), "text": torch.ones(2, 5, dtype=torch.int64), "style": torch.randn(2, 14, 1280)}] * 2
+    tr = _StubTrainer()
+    lines = []
+    log = type("L", (), {"info": staticmethod(lines.append)})
+    hist = fit(tr, batches, steps=7, exp_dir=str(tmp_path), log_freq=3, save_freq=4, logger=log, generator=torch.Generator().manual_seed(0))
+    assert len(tr.calls) == 7 and tr.calls[0] == ((2, 16, 2), (2, 16), (2, 5), (2, 14, 1280), (2, 1), (2, 16, 2), (2, 14, 1280))
+    assert [h[0] for h in hist] == [3, 6] and hist[0][1] == pytest.approx(1.5) and hist[1][1] == pytest.approx(4.0)   # means of steps 1-2, 3-5
+    assert sorted(p.name for p in tmp_path.iterdir()) == ["checkpoint_4.pth", "checkpoint_8.pth", "model_final.pth"]
+    ck = torch.load(tmp_path / "checkpoint_4.pth")
+    assert set(ck) == {"meta", "state_dict"} and ck["state_dict"]["w"].tolist() == [3.0, 3.0, 3.0]    # saved after 3 steps
+    assert torch.load(tmp_path / "model_final.pth")["w"].tolist() == [7.0, 7.0, 7.0]
+    assert any(l.startswith("Step 3 | Loss: 1.500 | Score: 0.750 | Pen: 0.375") for l in lines)
+
+
+def test_fit_saves_the_last_state_on_interrupt(tmp_path):
+    from dhg_b200.train import fit
+
+    batches = [{"strokes": torch.randn(2, 16, 3), "text": torch.ones(2, 5, dtype=torch.int64), "style": torch.randn(2, 14, 1280)}]
+    fit(_StubTrainer(interrupt_at=3), batches, steps=10, exp_dir=str(tmp_path), log_freq=100, save_freq=100)
+    assert sorted(p.name for p in tmp_path.iterdir()) == ["checkpoint_last.pth", "model_last.pth"]
+    assert torch.load(tmp_path / "model_last.pth")["w"].tolist() == [2.0, 2.0, 2.0]
