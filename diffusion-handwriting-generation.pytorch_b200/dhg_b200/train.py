@@ -1,5 +1,5 @@
-"""The update half of the reference's training step (SURVEY.md 8e "optional train step", 8f-3) with the reference's
-names and argument meaning:
+"""The reference's training step (train.py:26-67; SURVEY.md 8a-18, 8e "optional train step", 8f-3) on the device, with the
+reference's names and argument meaning.  The part around the model call:
 
     loss_fn(eps, score_pred, pen_lifts, pen_lifts_pred, alphas)        loss.py:5-39
     perturb(x, alphas, eps)                                            train.py:38-43
@@ -18,6 +18,7 @@ The forward + backward pass of the denoiser (`csrc/train_step.cu`, C ABI `dhg_tr
         .backward(grad_score, grad_pen)                                             loss.backward(), train.py:55
         .train_step(strokes, pen_lifts, text, style, alphas, eps)                   TrainingLoop.train_step, train.py:26-67
     get_alphas(batch_size, alpha_set)                                               utils/nn.py:42-61
+    fit(trainer, batches, steps, exp_dir, ...)                                      the loop of TrainingLoop.train, train.py:95-137
 """
 import ctypes
 
