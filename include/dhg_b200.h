@@ -310,6 +310,10 @@ int32_t dhg_train_adam_step(int32_t device, float* dev_param, const float* dev_g
  *                         gradient buffer is zeroed and filled.  Weight gradients are summed with fp32 atomics: the
  *                         last bits depend on the order.
  * Stream-ordered, nothing synchronises, no allocation after create (graph-capturable).  fp32 on the CUDA cores.
+ * Stream rule: a trainer owns its activation / gradient arenas and one internal second stream (weight gradients and skip
+ * branches run there, forked from and joined back into the caller's stream inside every call), so all calls on one
+ * trainer must be issued on ONE stream (or be ordered by the caller); one host thread per trainer; the parameter
+ * buffer may be updated between a backward and the next forward on that same stream (dhg_train_adam_step does).
  * Errors: dhg_trainer_last_error(). */
 typedef struct dhg_trainer dhg_trainer;
 const char* dhg_trainer_last_error(void);
@@ -324,7 +328,8 @@ int64_t dhg_trainer_last_launches(const dhg_trainer* t);   /* launches of the la
 int32_t dhg_trainer_set_option(const char* name, int32_t value);   /* "tiled_gemm": 1 (default) tiled fp32 GEMM on the CUDA cores, 3 tiled with
                                                                        3 x TF32 tensor-core products (same fp32 contract), 4 plain TF32 products
                                                                        (torch's allow_tf32; about 1e-3, outside the fp32 contract), 2 smallest tile
-                                                                       only, 0 per-thread kernel bodies (checks) */
+                                                                       only, 0 per-thread kernel bodies (checks); "side_stream": 1 (default) / 0
+                                                                       everything on the caller's stream.  Process-wide measurement switches. */
 int32_t dhg_trainer_forward(dhg_trainer* t, const float* dev_x, const int64_t* dev_text, const float* dev_sigma, const float* dev_style,
                             const float* dev_style_keep, float* dev_score_pred, float* dev_pen_pred, void* stream);
 int32_t dhg_trainer_backward(dhg_trainer* t, const float* dev_grad_score, const float* dev_grad_pen_pred, void* stream);
