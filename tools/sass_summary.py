@@ -12,7 +12,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "diffusion-handwriting-generation.pytorch_b200", "lib", "libdhg_b200.so")
 WATCH = ["UTCHMMA", "UTCQMMA", "UTCBAR", "UTMALDG", "UTMASTG", "UTMAPF", "UBLKCP", "LDTM", "STTM", "HMMA", "HGMMA", "FFMA2", "FADD2", "FMUL2",
-         "MUFU.TANH", "MUFU.EX2", "LDGSTS", "SYNCS", "UCGABAR", "ELECT"]
+         "MUFU.TANH", "MUFU.EX2", "LDGSTS", "SYNCS", "UCGABAR", "ELECT", "FFMA", "REDG", "LDS.128"]
 
 
 def main():
