@@ -163,3 +163,68 @@ def test_smallest_shapes_and_four_attention_layers(hs, B, T, L, NL):
     tr.backward(g_s, g_p)
     assert (tr.grad - first).norm() / first.norm() < 1e-6
     tr.close()
+
+
+def _shard_gradient(hs_lib, sd, inp, lo, hi):
+    """Flat gradient of the loss of samples [lo, hi) (the loss is a mean over the shard, like a rank's own step)."""
+    B, T, L = hi - lo, inp["x"].shape[1], inp["text"].shape[1]
+    tr = HostTrainer(hs_lib, sd, B, T, L, 2)
+    alphas, eps = inp["alphas"][lo:hi].contiguous(), inp["eps"][lo:hi].contiguous()
+    score, pen = tr.forward(inp["x"][lo:hi].contiguous(), inp["text"][lo:hi].contiguous(), torch.sqrt(alphas).reshape(B).contiguous(),
+                            inp["style"][lo:hi].contiguous(), None)
+    g_s, g_p = train_ref.loss_grads(eps, score, inp["pen"][lo:hi], pen, alphas)
+    out = tr.backward(g_s.contiguous(), g_p.contiguous()).clone()
+    tr.close()
+    return out
+
+
+def _ddp_inputs():
+    g = torch.Generator().manual_seed(77)
+    G, T, L = 4, 16, 6
+    text = torch.randint(2, 73, (G, L), generator=g)
+    text[:, -1] = 1
+    text[2, 3:] = 0
+    return dict(x=torch.randn(G, T, 2, generator=g), text=text, style=torch.randn(G, 14, 1280, generator=g),
+                pen=(torch.rand(G, T, generator=g) < 0.2).float(), alphas=torch.rand(G, 1, generator=g) * 0.9 + 0.05,
+                eps=torch.randn(G, T, 2, generator=g))
+
+
+def _ddp_rank(rank, world, port, out):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="4")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dhg_b200.train import exchange_gradients
+
+    inp, sd = _ddp_inputs(), O.init_state_dict(0)
+    per = inp["x"].shape[0] // world
+    flat = _shard_gradient(hostsim_build.lib(), sd, inp, rank * per, (rank + 1) * per)
+    n = exchange_gradients(flat)               # the step's one collective: SUM over the ranks
+    out.put((rank, n, (flat / n).numpy()))     # the 1 / N the optimiser kernel folds in
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_equals_the_whole_batch_gradient(hs):
+    """SURVEY 8e / BASELINE configs[3] on the host build, two gloo ranks: each rank's backward on its half of the batch,
+    one SUM all-reduce of the flat gradient, divided by the world size = the gradient of the whole batch in one process."""
+    import socket
+
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ddp_rank, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=300) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == 2 and (res[0][2] == res[1][2]).all()          # every rank ends with the same averaged gradient
+    inp = _ddp_inputs()
+    whole = _shard_gradient(hs, O.init_state_dict(0), inp, 0, inp["x"].shape[0])
+    got = torch.from_numpy(res[0][2])
+    assert (got - whole).norm() / whole.norm() < 1e-5
